@@ -1,0 +1,1369 @@
+// pf_api.cu -- the extern "C" boundary (include/cracks_b200.h) and the host
+// side of the device-resident Newton/Krylov glue.  One pf_ctx per rank/GPU.
+//
+// Multi-GPU: z-slab (last coordinate) decomposition of the p4est-ordered
+// uniform forest; every rank evaluates its owned cell layers plus one
+// redundant layer above, so the only data-path collective per operator
+// application is one halo exchange of two node planes of x (NCCL send/recv
+// over NVLink), and one small all-reduce per Krylov orthogonalisation.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cracks_b200.h"
+#include "pf_apply3d.cuh"
+#include "pf_common.cuh"
+#include "pf_generic.cuh"
+#include "pf_vector.cuh"
+
+using namespace pf;
+
+// ---------------------------------------------------------------------------
+// minimal NCCL binding resolved at run time (only when nranks > 1), so the
+// single-GPU library has no NCCL link dependency and shares the NCCL already
+// loaded by the host process (e.g. torch's) when there is one.
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat64 = 8, ncclUint64 = 5 };
+enum { ncclSum = 0, ncclMax = 2 };
+struct NcclApi
+{
+  void *handle = nullptr;
+  int (*GetUniqueId) (ncclUniqueId *) = nullptr;
+  int (*CommInitRank) (ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy) (ncclComm_t) = nullptr;
+  int (*GroupStart) () = nullptr;
+  int (*GroupEnd) () = nullptr;
+  int (*Send) (const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv) (void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce) (const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString) (int) = nullptr;
+  bool load (std::string &err)
+  {
+    if (handle)
+      return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names)
+      {
+        handle = dlopen (n, RTLD_NOW | RTLD_GLOBAL);
+        if (handle)
+          break;
+      }
+    if (!handle)
+      {
+        err = std::string ("cannot dlopen libnccl: ") + dlerror ();
+        return false;
+      }
+#define PF_SYM(field, name)                                                        \
+  field = reinterpret_cast<decltype (field)> (dlsym (handle, name));               \
+  if (!field)                                                                      \
+    {                                                                              \
+      err = std::string ("missing NCCL symbol ") + name;                           \
+      return false;                                                                \
+    }
+    PF_SYM (GetUniqueId, "ncclGetUniqueId")
+    PF_SYM (CommInitRank, "ncclCommInitRank")
+    PF_SYM (CommDestroy, "ncclCommDestroy")
+    PF_SYM (GroupStart, "ncclGroupStart")
+    PF_SYM (GroupEnd, "ncclGroupEnd")
+    PF_SYM (Send, "ncclSend")
+    PF_SYM (Recv, "ncclRecv")
+    PF_SYM (AllReduce, "ncclAllReduce")
+    PF_SYM (GetErrorString, "ncclGetErrorString")
+#undef PF_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+} // namespace
+
+// ---------------------------------------------------------------------------
+struct pf_ctx
+{
+  int dim = 0, nc = 0;
+  Grid g{};
+  Phys p{};
+  pf_params prm{};
+  K3 k3{};
+  double pressure = 0, dt_old = 1, dt_oldold = 1;
+  int use_old_timestep_pf = 0;
+  int device = 0, rank = 0, nranks = 1;
+  int own_cell_begin = 0, own_cell_end = 0;
+  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;
+  long long n_local_dofs = 0, owned_lo = 0, owned_hi = 0; // node ranges (local indices)
+  // device state
+  double *sol = nullptr, *old = nullptr, *oldold = nullptr, *pt = nullptr;
+  double *diag = nullptr, *mass = nullptr, *r_total = nullptr, *r_pde = nullptr, *dx = nullptr;
+  double *stage = nullptr, *xa = nullptr, *ya = nullptr, *saved = nullptr;
+  uint8_t *mask = nullptr, *stage8 = nullptr;
+  int *cycle = nullptr;
+  void *fetab = nullptr;
+  double *red = nullptr, *partial = nullptr; // reduction scratch
+  unsigned long long *counts = nullptr;
+  double *h_red = nullptr; // pinned mirror
+  unsigned long long *h_counts = nullptr;
+  // Krylov workspace
+  int krylov_m = 30;
+  double *V = nullptr, *zvec = nullptr, *hdev = nullptr;
+  bool jac_ready = false, have_r = false;
+  double last_rnorm = 0;
+  long long launches = 0;
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::string err;
+};
+
+namespace {
+
+int
+fail (pf_ctx *c, int code, const char *fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start (ap, fmt);
+  vsnprintf (buf, sizeof buf, fmt, ap);
+  va_end (ap);
+  if (c)
+    c->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                           \
+  do                                                                                       \
+    {                                                                                      \
+      cudaError_t e_ = (call);                                                             \
+      if (e_ != cudaSuccess)                                                               \
+        return fail (ctx, PF_CUDA_ERROR, "%s:%d %s: %s", __FILE__, __LINE__, #call,        \
+                     cudaGetErrorString (e_));                                             \
+    }                                                                                      \
+  while (0)
+
+#define NC_(call)                                                                          \
+  do                                                                                       \
+    {                                                                                      \
+      int e_ = (call);                                                                     \
+      if (e_ != ncclSuccess)                                                               \
+        return fail (ctx, PF_NCCL_ERROR, "%s:%d %s: %s", __FILE__, __LINE__, #call,        \
+                     g_nccl.GetErrorString (e_));                                          \
+    }                                                                                      \
+  while (0)
+
+#define KCHECK()                                                                           \
+  do                                                                                       \
+    {                                                                                      \
+      ++ctx->launches;                                                                     \
+      cudaError_t e_ = cudaGetLastError ();                                                \
+      if (e_ != cudaSuccess)                                                               \
+        return fail (ctx, PF_CUDA_ERROR, "%s:%d kernel launch: %s", __FILE__, __LINE__,    \
+                     cudaGetErrorString (e_));                                             \
+    }                                                                                      \
+  while (0)
+
+inline unsigned
+nblk (long long n, int t)
+{
+  return (unsigned) ((n + t - 1) / t);
+}
+
+template <int DIM>
+void
+fill_fetab (FeTab<DIM> &t, const double *h)
+{
+  const double gq = 0.5 * std::sqrt (3.0 / 5.0);
+  const double xi[3] = {0.5 - gq, 0.5, 0.5 + gq};
+  const double w[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+  double vol = 1;
+  for (int d = 0; d < DIM; ++d)
+    vol *= h[d];
+  for (int q = 0; q < FeTab<DIM>::NQ; ++q)
+    {
+      const int qi[3] = {q % 3, (q / 3) % 3, q / 9};
+      double wq = vol;
+      for (int d = 0; d < DIM; ++d)
+        wq *= w[qi[d]];
+      t.JxW[q] = wq;
+      for (int v = 0; v < (1 << DIM); ++v)
+        {
+          double val = 1;
+          for (int d = 0; d < DIM; ++d)
+            val *= ((v >> d) & 1) ? xi[qi[d]] : 1.0 - xi[qi[d]];
+          t.N[q][v] = val;
+          for (int e = 0; e < DIM; ++e)
+            {
+              double gr = 1;
+              for (int d = 0; d < DIM; ++d)
+                {
+                  const int b = (v >> d) & 1;
+                  gr *= (d == e) ? (b ? 1.0 : -1.0) / h[d] : (b ? xi[qi[d]] : 1.0 - xi[qi[d]]);
+                }
+              t.dN[q][v][e] = gr;
+            }
+        }
+    }
+}
+
+void
+update_phys (pf_ctx *c)
+{
+  c->p.lambda = c->prm.lambda;
+  c->p.mu = c->prm.mu;
+  c->p.G_c = c->prm.G_c;
+  c->p.kappa = c->prm.kappa;
+  c->p.eps = c->prm.eps;
+  c->p.P1 = (c->prm.alpha_biot - 1.0) * c->pressure;
+  c->p.clamp_extra = c->use_old_timestep_pf ? 0 : 1;
+}
+
+// ghost planes of a local nodal vector <- owners (ncomp doubles per node)
+int
+halo_exchange (pf_ctx *ctx, double *v, int ncomp)
+{
+  if (ctx->nranks == 1)
+    return PF_OK;
+  const Grid &g = ctx->g;
+  const size_t cnt = (size_t) g.nodes_per_plane * ncomp;
+  auto plane = [&](int gp) { return v + (size_t) (gp - g.plane_begin) * cnt; };
+  NC_ (g_nccl.GroupStart ());
+  if (ctx->rank > 0)
+    {
+      // lower ghost = plane_begin (owned by rank-1); send my first owned plane down
+      NC_ (g_nccl.Recv (plane (g.plane_begin), cnt, ncclFloat64, ctx->rank - 1, ctx->comm, ctx->stream));
+      NC_ (g_nccl.Send (plane (g.owned_begin), cnt, ncclFloat64, ctx->rank - 1, ctx->comm, ctx->stream));
+    }
+  if (ctx->rank < ctx->nranks - 1)
+    {
+      NC_ (g_nccl.Recv (plane (g.plane_end - 1), cnt, ncclFloat64, ctx->rank + 1, ctx->comm, ctx->stream));
+      NC_ (g_nccl.Send (plane (g.owned_end - 1), cnt, ncclFloat64, ctx->rank + 1, ctx->comm, ctx->stream));
+    }
+  NC_ (g_nccl.GroupEnd ());
+  return PF_OK;
+}
+
+int
+allreduce_sum (pf_ctx *ctx, double *dev, int n)
+{
+  if (ctx->nranks == 1)
+    return PF_OK;
+  NC_ (g_nccl.AllReduce (dev, dev, n, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+  return PF_OK;
+}
+
+int
+allreduce_max (pf_ctx *ctx, double *dev, int n)
+{
+  if (ctx->nranks == 1)
+    return PF_OK;
+  NC_ (g_nccl.AllReduce (dev, dev, n, ncclFloat64, ncclMax, ctx->comm, ctx->stream));
+  return PF_OK;
+}
+
+// host block layout -> device internal layout, local planes
+int
+upload_block (pf_ctx *ctx, const double *host, double *dev)
+{
+  const Grid &g = ctx->g;
+  const int dim = ctx->dim;
+  const long long n0 = (long long) g.plane_begin * g.nodes_per_plane, nl = g.n_local_nodes;
+  double *ub = ctx->stage, *pb = ctx->stage + nl * dim;
+  CU (cudaMemcpyAsync (ub, host + n0 * dim, sizeof (double) * nl * dim, cudaMemcpyHostToDevice, ctx->stream));
+  CU (cudaMemcpyAsync (pb, host + g.n_global_nodes * dim + n0, sizeof (double) * nl, cudaMemcpyHostToDevice,
+                       ctx->stream));
+  if (dim == 2)
+    k_block_to_nodal<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ub, pb, dev);
+  else
+    k_block_to_nodal<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ub, pb, dev);
+  KCHECK ();
+  return PF_OK;
+}
+
+// device internal layout -> host block layout (owned planes only when nranks > 1)
+int
+download_block (pf_ctx *ctx, const double *dev, double *host)
+{
+  const Grid &g = ctx->g;
+  const int dim = ctx->dim;
+  const long long nl = g.n_local_nodes;
+  double *ub = ctx->stage, *pb = ctx->stage + nl * dim;
+  if (dim == 2)
+    k_nodal_to_block<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, dev, ub, pb);
+  else
+    k_nodal_to_block<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, dev, ub, pb);
+  KCHECK ();
+  const long long lo = ctx->owned_lo, cnt = ctx->owned_hi - ctx->owned_lo;
+  const long long n0 = (long long) g.plane_begin * g.nodes_per_plane + lo;
+  CU (cudaMemcpyAsync (host + n0 * dim, ub + lo * dim, sizeof (double) * cnt * dim, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  CU (cudaMemcpyAsync (host + g.n_global_nodes * dim + n0, pb + lo, sizeof (double) * cnt,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  return PF_OK;
+}
+
+int
+refresh_extrapolation (pf_ctx *ctx)
+{
+  const long long nl = ctx->g.n_local_nodes;
+  // (time-(time-dt_o-dt_oo)) / (time-dt_o-(time-dt_o-dt_oo)) = (dt_o+dt_oo)/dt_oo, cracks.cc:2268-2269
+  const double ct = (ctx->dt_old + ctx->dt_oldold) / ctx->dt_oldold;
+  if (ctx->dim == 2)
+    k_extrapolate<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ct, ctx->use_old_timestep_pf, ctx->old,
+                                                              ctx->oldold, ctx->pt);
+  else
+    k_extrapolate<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ct, ctx->use_old_timestep_pf, ctx->old,
+                                                              ctx->oldold, ctx->pt);
+  KCHECK ();
+  return PF_OK;
+}
+
+// ---- the operator application on device vectors (local slab) -------------
+template <int TX, int TY, int TZ>
+int
+launch_apply3d (pf_ctx *ctx, const double *x, double *y)
+{
+  using T = Tile3<TX, TY, TZ>;
+  const Grid &g = ctx->g;
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+  const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  static bool attr_set = false;
+  if (!attr_set)
+    {
+      CU (cudaFuncSetAttribute (k_apply3d<TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes));
+      attr_set = true;
+    }
+  k_apply3d<TX, TY, TZ><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes, ctx->stream>>> (
+    g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  KCHECK ();
+  return PF_OK;
+}
+
+int g_force_generic = 0;
+
+int
+apply_dev (pf_ctx *ctx, double *x, double *y)
+{
+  if (!ctx->jac_ready)
+    return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must be called before applying the Jacobian");
+  int rc = halo_exchange (ctx, x, ctx->nc);
+  if (rc)
+    return rc;
+  const Grid &g = ctx->g;
+  const long long nl = g.n_local_nodes;
+  if (ctx->dim == 2)
+    {
+      k_apply_init<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
+      KCHECK ();
+      k_apply_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+        g, ctx->p, (const FeTab<2> *) ctx->fetab, x, ctx->sol, ctx->pt, ctx->mask, y);
+      KCHECK ();
+    }
+  else
+    {
+      k_apply_init<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
+      KCHECK ();
+      if (g_force_generic)
+        {
+          k_apply_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+            g, ctx->p, (const FeTab<3> *) ctx->fetab, x, ctx->sol, ctx->pt, ctx->mask, y);
+          KCHECK ();
+        }
+      else
+        {
+          cudaEvent_t e0 = nullptr, e1 = nullptr;
+          if (ctx->profiling)
+            {
+              CU (cudaEventCreate (&e0));
+              CU (cudaEventCreate (&e1));
+              CU (cudaEventRecord (e0, ctx->stream));
+            }
+          rc = launch_apply3d<16, 4, 2> (ctx, x, y);
+          if (rc)
+            return rc;
+          if (ctx->profiling)
+            {
+              CU (cudaEventRecord (e1, ctx->stream));
+              ctx->prof_events.emplace_back (e0, e1);
+            }
+        }
+    }
+  return PF_OK;
+}
+
+int
+residual_dev (pf_ctx *ctx, double *l2)
+{
+  const Grid &g = ctx->g;
+  const long long nl = g.n_local_nodes;
+  CU (cudaMemsetAsync (ctx->r_total, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
+  if (ctx->dim == 2)
+    {
+      k_residual_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+        g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
+      KCHECK ();
+      k_residual_finish<2><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi,
+                                                                        ctx->r_total, ctx->mask, ctx->r_pde,
+                                                                        ctx->partial);
+    }
+  else
+    {
+      k_residual_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+        g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
+      KCHECK ();
+      k_residual_finish<3><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi,
+                                                                        ctx->r_total, ctx->mask, ctx->r_pde,
+                                                                        ctx->partial);
+    }
+  KCHECK ();
+  k_reduce_partials<<<1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, 1, ctx->partial, ctx->red);
+  KCHECK ();
+  int rc = allreduce_sum (ctx, ctx->red, 1);
+  if (rc)
+    return rc;
+  CU (cudaMemcpyAsync (ctx->h_red, ctx->red, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  ctx->last_rnorm = std::sqrt (ctx->h_red[0]);
+  ctx->have_r = true;
+  if (!std::isfinite (ctx->last_rnorm))
+    return fail (ctx, PF_NUMERIC, "non-finite residual norm");
+  if (l2)
+    *l2 = ctx->last_rnorm;
+  return PF_OK;
+}
+
+} // namespace
+
+// ===========================================================================
+extern "C" {
+
+int
+pf_nccl_unique_id (void *id128)
+{
+  std::string err;
+  if (!id128 || !g_nccl.load (err))
+    return PF_NCCL_ERROR;
+  return g_nccl.GetUniqueId (reinterpret_cast<ncclUniqueId *> (id128)) == ncclSuccess ? PF_OK : PF_NCCL_ERROR;
+}
+
+int
+pf_create (const pf_mesh *mesh, const pf_params *params, int device, int rank, int nranks,
+           const void *nccl_id, pf_ctx **out)
+{
+  if (!mesh || !params || !out || (mesh->dim != 2 && mesh->dim != 3) || nranks < 1 || rank < 0
+      || rank >= nranks)
+    return PF_BAD_ARG;
+  const int dim = mesh->dim;
+  for (int d = 0; d < dim; ++d)
+    if (mesh->n[d] < 1 || !(mesh->h[d] > 0))
+      return PF_BAD_ARG;
+  if (nranks > mesh->n[dim - 1])
+    return PF_BAD_ARG;
+  pf_ctx *ctx = new pf_ctx ();
+  *out = ctx;
+  ctx->dim = dim;
+  ctx->nc = dim + 1;
+  ctx->device = device;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  ctx->prm = *params;
+  CU (cudaSetDevice (device));
+  CU (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
+
+  Grid &g = ctx->g;
+  g.dim = dim;
+  g.nodes_per_plane = 1;
+  g.n_global_nodes = 1;
+  for (int d = 0; d < 3; ++d)
+    {
+      g.n[d] = d < dim ? mesh->n[d] : 1;
+      g.nn[d] = d < dim ? mesh->n[d] + 1 : 1;
+      g.h[d] = d < dim ? mesh->h[d] : 1.0;
+      g.origin[d] = d < dim ? mesh->origin[d] : 0.0;
+      g.n_global_nodes *= g.nn[d];
+      if (d < dim - 1)
+        g.nodes_per_plane *= g.nn[d];
+    }
+  const int ncl = g.n[dim - 1];
+  const int cb = (int) ((long long) ncl * rank / nranks), ce = (int) ((long long) ncl * (rank + 1) / nranks);
+  ctx->own_cell_begin = cb;
+  ctx->own_cell_end = ce;
+  g.owned_begin = rank == 0 ? 0 : cb + 1;
+  g.owned_end = ce + 1;
+  g.cell_begin = cb;
+  g.cell_end = rank == nranks - 1 ? ce : ce + 1;
+  g.plane_begin = cb;
+  g.plane_end = g.cell_end + 1;
+  g.n_local_nodes = g.nodes_per_plane * (g.plane_end - g.plane_begin);
+  long long cells_per_layer = 1;
+  for (int d = 0; d < dim - 1; ++d)
+    cells_per_layer *= g.n[d];
+  g.n_local_cells = cells_per_layer * (g.cell_end - g.cell_begin);
+  ctx->n_local_dofs = g.n_local_nodes * ctx->nc;
+  ctx->owned_lo = (long long) (g.owned_begin - g.plane_begin) * g.nodes_per_plane;
+  ctx->owned_hi = (long long) (g.owned_end - g.plane_begin) * g.nodes_per_plane;
+
+  const double s = std::sqrt (3.0 / 5.0);
+  ctx->k3.s = s;
+  ctx->k3.wvol = 1.0;
+  for (int d = 0; d < 3; ++d)
+    {
+      ctx->k3.gu[d] = 1.0 / (4.0 * g.h[d]);
+      ctx->k3.gp[d] = 2.0 / g.h[d];
+      ctx->k3.ih[d] = 1.0 / g.h[d];
+      ctx->k3.wvol *= g.h[d] / 2.0;
+    }
+  ctx->k3.wq[0] = ctx->k3.wq[2] = 5.0 / 9.0;
+  ctx->k3.wq[1] = 8.0 / 9.0;
+  update_phys (ctx);
+
+  const size_t nd = (size_t) ctx->n_local_dofs, nn = (size_t) g.n_local_nodes;
+  double **vecs[] = {&ctx->sol, &ctx->old, &ctx->oldold, &ctx->diag, &ctx->r_total, &ctx->r_pde,
+                     &ctx->dx,  &ctx->stage, &ctx->xa, &ctx->ya, &ctx->zvec, &ctx->saved};
+  for (double **v : vecs)
+    {
+      CU (cudaMalloc (v, nd * sizeof (double)));
+      CU (cudaMemsetAsync (*v, 0, nd * sizeof (double), ctx->stream));
+    }
+  CU (cudaMalloc (&ctx->pt, nn * sizeof (double)));
+  CU (cudaMalloc (&ctx->mass, nn * sizeof (double)));
+  CU (cudaMalloc (&ctx->mask, nn));
+  CU (cudaMalloc (&ctx->stage8, nd));
+  CU (cudaMalloc (&ctx->cycle, nn * sizeof (int)));
+  CU (cudaMemsetAsync (ctx->pt, 0, nn * sizeof (double), ctx->stream));
+  CU (cudaMemsetAsync (ctx->mask, 0, nn, ctx->stream));
+  CU (cudaMemsetAsync (ctx->cycle, 0, nn * sizeof (int), ctx->stream));
+  CU (cudaMalloc (&ctx->red, 64 * sizeof (double)));
+  CU (cudaMalloc (&ctx->hdev, 128 * sizeof (double)));
+  CU (cudaMalloc (&ctx->partial, (size_t) RED_BLOCKS * 64 * sizeof (double)));
+  CU (cudaMalloc (&ctx->counts, 4 * sizeof (unsigned long long)));
+  CU (cudaMallocHost (&ctx->h_red, 128 * sizeof (double)));
+  CU (cudaMallocHost (&ctx->h_counts, 4 * sizeof (unsigned long long)));
+  if (dim == 2)
+    {
+      FeTab<2> t;
+      fill_fetab<2> (t, g.h);
+      CU (cudaMalloc (&ctx->fetab, sizeof t));
+      CU (cudaMemcpy (ctx->fetab, &t, sizeof t, cudaMemcpyHostToDevice));
+      k_lumped_mass<2><<<nblk (nn, 256), 256, 0, ctx->stream>>> (g, ctx->mass);
+    }
+  else
+    {
+      FeTab<3> t;
+      fill_fetab<3> (t, g.h);
+      CU (cudaMalloc (&ctx->fetab, sizeof t));
+      CU (cudaMemcpy (ctx->fetab, &t, sizeof t, cudaMemcpyHostToDevice));
+      k_lumped_mass<3><<<nblk (nn, 256), 256, 0, ctx->stream>>> (g, ctx->mass);
+    }
+  KCHECK ();
+  if (nranks > 1)
+    {
+      if (!nccl_id)
+        return fail (ctx, PF_BAD_ARG, "nranks > 1 needs an ncclUniqueId");
+      if (!g_nccl.load (ctx->err))
+        return PF_NCCL_ERROR;
+      ncclUniqueId id;
+      memcpy (&id, nccl_id, sizeof id);
+      NC_ (g_nccl.CommInitRank (&ctx->comm, nranks, id, rank));
+    }
+  CU (cudaStreamSynchronize (ctx->stream));
+  return PF_OK;
+}
+
+int
+pf_destroy (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  cudaSetDevice (ctx->device);
+  if (ctx->stream)
+    cudaStreamSynchronize (ctx->stream);
+  if (ctx->comm)
+    g_nccl.CommDestroy (ctx->comm);
+  void *ptrs[] = {ctx->sol,   ctx->old,  ctx->oldold, ctx->pt,     ctx->diag,  ctx->mass, ctx->r_total,
+                  ctx->r_pde, ctx->dx,   ctx->stage,  ctx->xa,     ctx->ya,    ctx->zvec, ctx->mask,
+                  ctx->saved, ctx->stage8, ctx->cycle, ctx->fetab, ctx->red,   ctx->hdev,  ctx->partial, ctx->counts,
+                  ctx->V};
+  for (void *p : ptrs)
+    if (p)
+      cudaFree (p);
+  if (ctx->h_red)
+    cudaFreeHost (ctx->h_red);
+  if (ctx->h_counts)
+    cudaFreeHost (ctx->h_counts);
+  if (ctx->stream)
+    cudaStreamDestroy (ctx->stream);
+  delete ctx;
+  return PF_OK;
+}
+
+const char *
+pf_last_error (const pf_ctx *ctx)
+{
+  return ctx ? ctx->err.c_str () : "null context";
+}
+
+int
+pf_get_layout (const pf_ctx *ctx, pf_local_layout *out)
+{
+  if (!ctx || !out)
+    return PF_BAD_ARG;
+  out->n_nodes_global = ctx->g.n_global_nodes;
+  out->n_nodes_plane = ctx->g.nodes_per_plane;
+  out->plane_begin = ctx->g.plane_begin;
+  out->plane_end = ctx->g.plane_end;
+  out->owned_begin = ctx->g.owned_begin;
+  out->owned_end = ctx->g.owned_end;
+  out->ncomp = ctx->nc;
+  return PF_OK;
+}
+
+int64_t
+pf_n_dofs (const pf_ctx *ctx)
+{
+  return ctx ? ctx->g.n_global_nodes * ctx->nc : 0;
+}
+
+void *
+pf_stream (const pf_ctx *ctx)
+{
+  return ctx ? (void *) ctx->stream : nullptr;
+}
+
+int
+pf_synchronize (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  CU (cudaStreamSynchronize (ctx->stream));
+  return PF_OK;
+}
+
+int64_t
+pf_launch_count (const pf_ctx *ctx)
+{
+  return ctx ? ctx->launches : 0;
+}
+
+int
+pf_set_params (pf_ctx *ctx, const pf_params *params)
+{
+  if (!ctx || !params)
+    return PF_BAD_ARG;
+  ctx->prm = *params;
+  update_phys (ctx);
+  ctx->jac_ready = false;
+  return PF_OK;
+}
+
+int
+pf_set_state (pf_ctx *ctx, const double *sol, const double *old, const double *oldold, double dt_old,
+              double dt_oldold, int use_old_timestep_pf, double pressure)
+{
+  if (!ctx || !(dt_oldold > 0))
+    return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
+  int rc;
+  if (sol && (rc = upload_block (ctx, sol, ctx->sol)))
+    return rc;
+  if (old && (rc = upload_block (ctx, old, ctx->old)))
+    return rc;
+  if (oldold && (rc = upload_block (ctx, oldold, ctx->oldold)))
+    return rc;
+  ctx->dt_old = dt_old;
+  ctx->dt_oldold = dt_oldold;
+  ctx->use_old_timestep_pf = use_old_timestep_pf;
+  ctx->pressure = pressure;
+  update_phys (ctx);
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return refresh_extrapolation (ctx);
+}
+
+int
+pf_get_solution (pf_ctx *ctx, double *sol)
+{
+  if (!ctx || !sol)
+    return PF_BAD_ARG;
+  return download_block (ctx, ctx->sol, sol);
+}
+
+int
+pf_update_solution (pf_ctx *ctx, double alpha)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->n_local_dofs, alpha, ctx->dx, ctx->sol);
+  KCHECK ();
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return PF_OK;
+}
+
+int
+pf_set_constraints (pf_ctx *ctx, const uint8_t *dirichlet_mask, const uint8_t *active_mask)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  const Grid &g = ctx->g;
+  const int dim = ctx->dim;
+  const long long n0 = (long long) g.plane_begin * g.nodes_per_plane, nl = g.n_local_nodes;
+  uint8_t *ub = ctx->stage8, *pb = ctx->stage8 + nl * dim;
+  if (dirichlet_mask)
+    {
+      CU (cudaMemcpyAsync (ub, dirichlet_mask + n0 * dim, (size_t) nl * dim, cudaMemcpyHostToDevice, ctx->stream));
+      // phi rows of the Dirichlet mask are ignored: phi has no Dirichlet data
+      // in the Sneddon / Miehe / hetero cases (cracks.cc:2575-2625, 2686-2694)
+    }
+  if (active_mask)
+    CU (cudaMemcpyAsync (pb, active_mask + g.n_global_nodes * dim + n0, (size_t) nl, cudaMemcpyHostToDevice,
+                         ctx->stream));
+  if (dirichlet_mask || active_mask)
+    {
+      if (dim == 2)
+        k_mask_from_block<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ub, pb, dirichlet_mask != nullptr,
+                                                                      active_mask != nullptr, ctx->mask);
+      else
+        k_mask_from_block<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ub, pb, dirichlet_mask != nullptr,
+                                                                      active_mask != nullptr, ctx->mask);
+      KCHECK ();
+    }
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return PF_OK;
+}
+
+int
+pf_set_dirichlet_all_faces (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  const long long nl = ctx->g.n_local_nodes;
+  if (ctx->dim == 2)
+    k_mask_dirichlet_faces<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (ctx->g, ctx->mask);
+  else
+    k_mask_dirichlet_faces<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (ctx->g, ctx->mask);
+  KCHECK ();
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return PF_OK;
+}
+
+int
+pf_residual (pf_ctx *ctx, double *r_pde, double *r_total, double *l2_norm)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
+  int rc = residual_dev (ctx, l2_norm);
+  if (rc)
+    return rc;
+  if (r_pde && (rc = download_block (ctx, ctx->r_pde, r_pde)))
+    return rc;
+  if (r_total && (rc = download_block (ctx, ctx->r_total, r_total)))
+    return rc;
+  return PF_OK;
+}
+
+int
+pf_setup_jacobian (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
+  const Grid &g = ctx->g;
+  CU (cudaMemsetAsync (ctx->diag, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
+  if (ctx->dim == 2)
+    k_diag_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+      g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
+  else
+    k_diag_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+      g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
+  KCHECK ();
+  // complete the diagonal on the ghost planes (their cells are only partly local)
+  int rc = halo_exchange (ctx, ctx->diag, ctx->nc);
+  if (rc)
+    return rc;
+  ctx->jac_ready = true;
+  return PF_OK;
+}
+
+int
+pf_apply_jacobian_dev (pf_ctx *ctx, double *x_dev, double *y_dev)
+{
+  if (!ctx || !x_dev || !y_dev)
+    return PF_BAD_ARG;
+  return apply_dev (ctx, x_dev, y_dev);
+}
+
+int
+pf_apply_jacobian (pf_ctx *ctx, const double *x, double *y)
+{
+  if (!ctx || !x || !y)
+    return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
+  int rc = upload_block (ctx, x, ctx->xa);
+  if (rc)
+    return rc;
+  if ((rc = apply_dev (ctx, ctx->xa, ctx->ya)))
+    return rc;
+  return download_block (ctx, ctx->ya, y);
+}
+
+int
+pf_jacobian_diagonal (pf_ctx *ctx, double *diag)
+{
+  if (!ctx || !diag || !ctx->jac_ready)
+    return PF_BAD_ARG;
+  return download_block (ctx, ctx->diag, diag);
+}
+
+int
+pf_lumped_mass (pf_ctx *ctx, double *mass)
+{
+  if (!ctx || !mass)
+    return PF_BAD_ARG;
+  const Grid &g = ctx->g;
+  const long long lo = ctx->owned_lo, cnt = ctx->owned_hi - ctx->owned_lo;
+  CU (cudaMemcpyAsync (mass + (long long) g.plane_begin * g.nodes_per_plane + lo, ctx->mass + lo,
+                       sizeof (double) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  return PF_OK;
+}
+
+int
+pf_active_set_reset (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  const long long nl = ctx->g.n_local_nodes;
+  if (ctx->dim == 2)
+    k_clear_active<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, ctx->cycle);
+  else
+    k_clear_active<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, ctx->cycle);
+  KCHECK ();
+  ctx->jac_ready = false;
+  return PF_OK;
+}
+
+int
+pf_active_set_update (pf_ctx *ctx, double c, uint8_t *active_mask, int64_t *n_active, int64_t *n_cycling,
+                      int *changed)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  if (!ctx->have_r)
+    return fail (ctx, PF_BAD_ARG, "pf_active_set_update needs the r_total of a preceding pf_residual");
+  CU (cudaSetDevice (ctx->device));
+  const long long nl = ctx->g.n_local_nodes;
+  CU (cudaMemsetAsync (ctx->counts, 0, 4 * sizeof (unsigned long long), ctx->stream));
+  if (ctx->dim == 2)
+    k_active_set<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi, c, ctx->r_total,
+                                                             ctx->mass, ctx->old, ctx->sol, ctx->cycle,
+                                                             ctx->mask, ctx->counts);
+  else
+    k_active_set<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi, c, ctx->r_total,
+                                                             ctx->mass, ctx->old, ctx->sol, ctx->cycle,
+                                                             ctx->mask, ctx->counts);
+  KCHECK ();
+  if (ctx->nranks > 1)
+    {
+      NC_ (g_nccl.AllReduce (ctx->counts, ctx->counts, 3, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+      // ghost copies of phi and of the mask follow their owners
+      int rc = halo_exchange (ctx, ctx->sol, ctx->nc);
+      if (rc)
+        return rc;
+      // the mask is one byte per node: exchange through the double staging path
+      // is overkill; recompute is impossible (needs r_total), so send bytes.
+      const Grid &g = ctx->g;
+      const size_t cnt = (size_t) g.nodes_per_plane;
+      auto plane = [&](int gp) { return ctx->mask + (size_t) (gp - g.plane_begin) * cnt; };
+      NC_ (g_nccl.GroupStart ());
+      if (ctx->rank > 0)
+        {
+          NC_ (g_nccl.Recv (plane (g.plane_begin), cnt, /*ncclUint8*/ 1, ctx->rank - 1, ctx->comm, ctx->stream));
+          NC_ (g_nccl.Send (plane (g.owned_begin), cnt, 1, ctx->rank - 1, ctx->comm, ctx->stream));
+        }
+      if (ctx->rank < ctx->nranks - 1)
+        {
+          NC_ (g_nccl.Recv (plane (g.plane_end - 1), cnt, 1, ctx->rank + 1, ctx->comm, ctx->stream));
+          NC_ (g_nccl.Send (plane (g.owned_end - 1), cnt, 1, ctx->rank + 1, ctx->comm, ctx->stream));
+        }
+      NC_ (g_nccl.GroupEnd ());
+    }
+  CU (cudaMemcpyAsync (ctx->h_counts, ctx->counts, 4 * sizeof (unsigned long long), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  if (active_mask)
+    {
+      const Grid &g = ctx->g;
+      if (ctx->dim == 2)
+        k_get_active<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, ctx->stage8);
+      else
+        k_get_active<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, ctx->stage8);
+      KCHECK ();
+      const long long lo = ctx->owned_lo, cnt = ctx->owned_hi - ctx->owned_lo;
+      CU (cudaMemcpyAsync (active_mask + (long long) g.plane_begin * g.nodes_per_plane + lo, ctx->stage8 + lo,
+                           (size_t) cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  CU (cudaStreamSynchronize (ctx->stream));
+  if (n_active)
+    *n_active = (int64_t) ctx->h_counts[0];
+  if (n_cycling)
+    *n_cycling = (int64_t) ctx->h_counts[1];
+  if (changed)
+    *changed = ctx->h_counts[2] != 0;
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return PF_OK;
+}
+
+// ---- solve(): restarted right-preconditioned GMRES, CGS2 orthogonalisation
+int
+pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
+{
+  if (!ctx || max_it < 1)
+    return PF_BAD_ARG;
+  if (!ctx->jac_ready)
+    return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must precede pf_solve");
+  CU (cudaSetDevice (ctx->device));
+  const int m = ctx->krylov_m;
+  const long long nd = ctx->n_local_dofs;
+  const long long lo = ctx->owned_lo * ctx->nc, hi = ctx->owned_hi * ctx->nc;
+  if (!ctx->V)
+    CU (cudaMalloc (&ctx->V, sizeof (double) * nd * (size_t) (m + 1)));
+  double *V = ctx->V, *w = ctx->ya, *z = ctx->zvec, *x = ctx->dx, *b = ctx->r_pde;
+  int rc;
+  CU (cudaMemsetAsync (x, 0, sizeof (double) * nd, ctx->stream));
+
+  auto dots = [&](int k, const double *wv, int with_norm) -> int {
+    // hdev[0..k) = V^T w, hdev[k] = w.w (if with_norm); all-reduced
+    for (int j0 = 0; j0 < k || (j0 == 0 && with_norm); j0 += 8)
+      {
+        k_multi_dot<8><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (lo, hi, j0, k, V, nd, wv,
+                                                                     with_norm && j0 == 0, ctx->partial);
+        KCHECK ();
+        if (k == 0)
+          break;
+      }
+    k_reduce_partials<<<k + 1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, k + (with_norm ? 1 : 0), ctx->partial,
+                                                              ctx->hdev);
+    KCHECK ();
+    return allreduce_sum (ctx, ctx->hdev, k + 1);
+  };
+
+  // beta = ||b||
+  if ((rc = dots (0, b, 1)))
+    return rc;
+  CU (cudaMemcpyAsync (ctx->h_red, ctx->hdev, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  const double bnorm = std::sqrt (ctx->h_red[0]);
+  const double tol = tol_rel * bnorm;
+  int its = 0;
+  if (n_it)
+    *n_it = 0;
+  if (!(bnorm > 0))
+    {
+      if (dx)
+        return download_block (ctx, x, dx);
+      return PF_OK;
+    }
+  if (!std::isfinite (bnorm))
+    return fail (ctx, PF_NUMERIC, "non-finite right-hand side in pf_solve");
+
+  std::vector<double> H ((size_t) (m + 1) * m), cs (m), sn (m), gvec (m + 1), yv (m);
+  double res = bnorm;
+  bool converged = false;
+  bool first_cycle = true;
+  while (its < max_it && !converged)
+    {
+      // r = b - J x  (x = 0 on the first cycle)
+      double beta;
+      if (first_cycle)
+        {
+          k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, 1.0, 1, b, V);
+          KCHECK ();
+          beta = bnorm;
+          first_cycle = false;
+        }
+      else
+        {
+          if ((rc = apply_dev (ctx, x, w)))
+            return rc;
+          k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, -1.0, 0, w, w);
+          KCHECK ();
+          k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, 1.0, b, w);
+          KCHECK ();
+          if ((rc = dots (0, w, 1)))
+            return rc;
+          k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, 1.0, 1, w, V);
+          KCHECK ();
+          CU (cudaMemcpyAsync (ctx->h_red, ctx->hdev, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+          CU (cudaStreamSynchronize (ctx->stream));
+          beta = std::sqrt (ctx->h_red[0]);
+          res = beta;
+          if (beta <= tol)
+            {
+              converged = true;
+              break;
+            }
+        }
+      std::fill (gvec.begin (), gvec.end (), 0.0);
+      gvec[0] = beta;
+      int k = 0;
+      for (; k < m && its < max_it; ++k)
+        {
+          double *vk = V + (size_t) k * nd, *vk1 = V + (size_t) (k + 1) * nd;
+          // z = M^{-1} v_k ; w = J z
+          k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->diag, vk, z);
+          KCHECK ();
+          if ((rc = apply_dev (ctx, z, w)))
+            return rc;
+          // CGS2: two passes of classical Gram-Schmidt, fused multi-dot / multi-axpy
+          if ((rc = dots (k + 1, w, 0)))
+            return rc;
+          CU (cudaMemcpyAsync (ctx->h_red, ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+          k_multi_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w);
+          KCHECK ();
+          if ((rc = dots (k + 1, w, 0)))
+            return rc;
+          CU (cudaMemcpyAsync (ctx->h_red + 40, ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+          k_multi_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w);
+          KCHECK ();
+          if ((rc = dots (0, w, 1)))
+            return rc;
+          CU (cudaMemcpyAsync (ctx->h_red + 80, ctx->hdev, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+          k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, 1.0, 1, w, vk1);
+          KCHECK ();
+          CU (cudaStreamSynchronize (ctx->stream));
+          ++its;
+          for (int j = 0; j <= k; ++j)
+            H[(size_t) j * m + k] = ctx->h_red[j] + ctx->h_red[40 + j];
+          const double hk1 = std::sqrt (ctx->h_red[80]);
+          H[(size_t) (k + 1) * m + k] = hk1;
+          // Givens rotations
+          for (int j = 0; j < k; ++j)
+            {
+              const double t = cs[j] * H[(size_t) j * m + k] + sn[j] * H[(size_t) (j + 1) * m + k];
+              H[(size_t) (j + 1) * m + k] = -sn[j] * H[(size_t) j * m + k] + cs[j] * H[(size_t) (j + 1) * m + k];
+              H[(size_t) j * m + k] = t;
+            }
+          const double a = H[(size_t) k * m + k], bb = hk1, r = std::hypot (a, bb);
+          cs[k] = r > 0 ? a / r : 1.0;
+          sn[k] = r > 0 ? bb / r : 0.0;
+          H[(size_t) k * m + k] = r;
+          H[(size_t) (k + 1) * m + k] = 0;
+          gvec[k + 1] = -sn[k] * gvec[k];
+          gvec[k] = cs[k] * gvec[k];
+          res = std::fabs (gvec[k + 1]);
+          if (!std::isfinite (res))
+            return fail (ctx, PF_NUMERIC, "GMRES breakdown: non-finite residual");
+          if (res <= tol || !(hk1 > 0))
+            {
+              ++k;
+              converged = res <= tol;
+              break;
+            }
+        }
+      // y = H^{-1} g ; x += M^{-1} V y
+      for (int i = k - 1; i >= 0; --i)
+        {
+          double sum = gvec[i];
+          for (int j = i + 1; j < k; ++j)
+            sum -= H[(size_t) i * m + j] * yv[j];
+          yv[i] = sum / H[(size_t) i * m + i];
+        }
+      CU (cudaMemcpyAsync (ctx->hdev, yv.data (), sizeof (double) * k, cudaMemcpyHostToDevice, ctx->stream));
+      CU (cudaMemsetAsync (w, 0, sizeof (double) * nd, ctx->stream));
+      k_combine<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k, V, nd, ctx->hdev, w);
+      KCHECK ();
+      k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->diag, w, z);
+      KCHECK ();
+      k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, 1.0, z, x);
+      KCHECK ();
+      CU (cudaStreamSynchronize (ctx->stream));
+    }
+  // constraints_update.distribute(newton_update): homogeneous -> zero (cracks.cc:2773)
+  const long long nl = ctx->g.n_local_nodes;
+  if (ctx->dim == 2)
+    k_zero_constrained<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, x);
+  else
+    k_zero_constrained<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, x);
+  KCHECK ();
+  if ((rc = halo_exchange (ctx, x, ctx->nc)))
+    return rc;
+  if (n_it)
+    *n_it = its;
+  if (dx && (rc = download_block (ctx, x, dx)))
+    return rc;
+  CU (cudaStreamSynchronize (ctx->stream));
+  if (!converged)
+    return fail (ctx, PF_NO_CONVERGENCE, "GMRES: residual %.3e > tol %.3e after %d iterations", res, tol, its);
+  return PF_OK;
+}
+
+int
+pf_energy (pf_ctx *ctx, double *bulk, double *crack)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
+  const Grid &g = ctx->g;
+  CU (cudaMemsetAsync (ctx->red, 0, 4 * sizeof (double), ctx->stream));
+  if (ctx->dim == 2)
+    k_functionals_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+      g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->own_cell_begin, ctx->own_cell_end, ctx->red);
+  else
+    k_functionals_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+      g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->own_cell_begin, ctx->own_cell_end, ctx->red);
+  KCHECK ();
+  int rc = allreduce_sum (ctx, ctx->red, 3);
+  if (rc)
+    return rc;
+  CU (cudaMemcpyAsync (ctx->h_red, ctx->red, 3 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  if (bulk)
+    *bulk = ctx->h_red[0];
+  if (crack)
+    *crack = ctx->h_red[1];
+  ctx->h_red[100] = ctx->h_red[2];
+  return PF_OK;
+}
+
+int
+pf_tcv (pf_ctx *ctx, double *tcv)
+{
+  if (!ctx || !tcv)
+    return PF_BAD_ARG;
+  int rc = pf_energy (ctx, nullptr, nullptr);
+  if (rc)
+    return rc;
+  *tcv = ctx->h_red[100];
+  return PF_OK;
+}
+
+int
+pf_project_phase_field (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  const long long nl = ctx->g.n_local_nodes;
+  if (ctx->dim == 2)
+    k_project_phi<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->sol);
+  else
+    k_project_phi<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->sol);
+  KCHECK ();
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return PF_OK;
+}
+
+int
+pf_interpolate_sneddon (pf_ctx *ctx, double h_diam)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  const long long nl = ctx->g.n_local_nodes;
+  if (ctx->dim == 2)
+    k_interpolate_sneddon<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (ctx->g, h_diam, ctx->sol);
+  else
+    k_interpolate_sneddon<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (ctx->g, h_diam, ctx->sol);
+  KCHECK ();
+  const size_t bytes = sizeof (double) * ctx->n_local_dofs;
+  CU (cudaMemcpyAsync (ctx->old, ctx->sol, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU (cudaMemcpyAsync (ctx->oldold, ctx->sol, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return refresh_extrapolation (ctx);
+}
+
+int
+pf_advance_timestep (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  // old_old_solution = old_solution; old_solution = solution (cracks.cc:4302-4303)
+  std::swap (ctx->old, ctx->oldold);
+  CU (cudaMemcpyAsync (ctx->old, ctx->sol, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return refresh_extrapolation (ctx);
+}
+
+int
+pf_set_time_parameters (pf_ctx *ctx, double dt_old, double dt_oldold, int use_old_timestep_pf, double pressure)
+{
+  if (!ctx || !(dt_oldold > 0))
+    return PF_BAD_ARG;
+  ctx->dt_old = dt_old;
+  ctx->dt_oldold = dt_oldold;
+  ctx->use_old_timestep_pf = use_old_timestep_pf;
+  ctx->pressure = pressure;
+  update_phys (ctx);
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return refresh_extrapolation (ctx);
+}
+
+int
+pf_timestep_difference (pf_ctx *ctx, double *linfty)
+{
+  if (!ctx || !linfty)
+    return PF_BAD_ARG;
+  const long long lo = ctx->owned_lo * ctx->nc, hi = ctx->owned_hi * ctx->nc;
+  k_absdiff_max<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (lo, hi, ctx->old, ctx->sol, ctx->partial);
+  KCHECK ();
+  k_reduce_partials_max<<<1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, ctx->partial, ctx->red);
+  KCHECK ();
+  int rc = allreduce_max (ctx, ctx->red, 1);
+  if (rc)
+    return rc;
+  CU (cudaMemcpyAsync (ctx->h_red, ctx->red, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  *linfty = ctx->h_red[0];
+  return PF_OK;
+}
+
+int
+pf_restore_old_solution (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  CU (cudaMemcpyAsync (ctx->sol, ctx->old, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return PF_OK;
+}
+
+int
+pf_save_solution (pf_ctx *ctx)
+{
+  // saved_solution = solution (cracks.cc:2922)
+  if (!ctx)
+    return PF_BAD_ARG;
+  CU (cudaMemcpyAsync (ctx->saved, ctx->sol, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+  return PF_OK;
+}
+
+int
+pf_restore_saved_solution (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  CU (cudaMemcpyAsync (ctx->sol, ctx->saved, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice,
+                       ctx->stream));
+  // r_total deliberately stays that of the rejected trial (cracks.cc:2947-2955)
+  ctx->jac_ready = false;
+  return PF_OK;
+}
+
+int
+pf_scale_update (pf_ctx *ctx, double factor)
+{
+  // newton_update *= line_search_damping (cracks.cc:2956)
+  if (!ctx)
+    return PF_BAD_ARG;
+  k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->n_local_dofs, ctx->hdev, factor, 0, ctx->dx,
+                                                            ctx->dx);
+  KCHECK ();
+  return PF_OK;
+}
+
+int
+pf_device_vector (pf_ctx *ctx, double **out)
+{
+  if (!ctx || !out)
+    return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
+  CU (cudaMalloc (out, sizeof (double) * ctx->n_local_dofs));
+  CU (cudaMemsetAsync (*out, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
+  return PF_OK;
+}
+
+int
+pf_device_vector_free (pf_ctx *ctx, double *v)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  CU (cudaFree (v));
+  return PF_OK;
+}
+
+int
+pf_upload (pf_ctx *ctx, const double *host_block, double *dev)
+{
+  if (!ctx || !host_block || !dev)
+    return PF_BAD_ARG;
+  return upload_block (ctx, host_block, dev);
+}
+
+int
+pf_download (pf_ctx *ctx, const double *dev, double *host_block)
+{
+  if (!ctx || !host_block || !dev)
+    return PF_BAD_ARG;
+  return download_block (ctx, dev, host_block);
+}
+
+int
+pf_host_alloc (void **out, size_t bytes)
+{
+  return cudaMallocHost (out, bytes) == cudaSuccess ? PF_OK : PF_CUDA_ERROR;
+}
+
+int
+pf_host_free (void *p)
+{
+  return cudaFreeHost (p) == cudaSuccess ? PF_OK : PF_CUDA_ERROR;
+}
+
+int
+pf_profile_enable (pf_ctx *ctx, int on)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  ctx->profiling = on != 0;
+  return PF_OK;
+}
+
+int
+pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count)
+{
+  // CUDA-event time of the dominant kernel (the tiled 3-D apply) summed over
+  // the launches since the last read, on the launching stream
+  if (!ctx || !total_ms || !count)
+    return PF_BAD_ARG;
+  CU (cudaStreamSynchronize (ctx->stream));
+  double tot = 0;
+  for (auto &pr : ctx->prof_events)
+    {
+      float ms = 0;
+      CU (cudaEventElapsedTime (&ms, pr.first, pr.second));
+      tot += ms;
+      cudaEventDestroy (pr.first);
+      cudaEventDestroy (pr.second);
+    }
+  *total_ms = tot;
+  *count = (int64_t) ctx->prof_events.size ();
+  ctx->prof_events.clear ();
+  return PF_OK;
+}
+
+int
+pf_debug_force_generic (int on)
+{
+  g_force_generic = on;
+  return PF_OK;
+}
+
+} // extern "C"

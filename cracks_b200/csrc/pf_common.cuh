@@ -1,0 +1,54 @@
+// pf_common.cuh -- shared device-side definitions for the (u,phi) hot path.
+//
+// Physics restated from tjhei/cracks cracks.cc:2129-2498 (assemble_system).
+// Layout: node-major interleaved, NC = dim+1 doubles per node, local slab of
+// node planes [plane_begin, plane_end) of the slowest coordinate.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pf {
+
+struct Grid
+{
+  int dim;
+  int n[3];        // global cells per direction
+  int nn[3];       // global nodes per direction
+  double h[3];
+  double origin[3];
+  int plane_begin; // first local node plane of the slowest coordinate (incl. ghost)
+  int plane_end;   // one past last local node plane
+  int owned_begin; // owned node planes [owned_begin, owned_end)
+  int owned_end;
+  int cell_begin;  // cell layers [cell_begin, cell_end) evaluated by this rank
+  int cell_end;
+  long long nodes_per_plane;
+  long long n_local_nodes;
+  long long n_local_cells;
+  long long n_global_nodes;
+};
+
+// quantities that change per Newton step / time step
+struct Phys
+{
+  double lambda, mu, G_c, kappa, eps;
+  double P1;        // (alpha_biot - 1) * pressure   (cracks.cc:2381, 2409, 2428)
+  int clamp_extra;  // 1: pf_extra = clamp01(interp(pt)); 0: use_old_timestep_pf (cracks.cc:2276)
+};
+
+template <int DIM> struct FeTab
+{
+  static constexpr int NV = 1 << DIM;
+  static constexpr int NQ = DIM == 2 ? 9 : 27;
+  double N[NQ][NV];
+  double dN[NQ][NV][DIM];
+  double JxW[NQ];
+};
+
+// mask bits: bit c set <=> component c of the node is constrained
+// (Dirichlet rows for c < dim, active set for c == dim)
+__host__ __device__ inline bool is_constrained (uint8_t m, int c) { return (m >> c) & 1u; }
+
+#define PF_ACTIVE_BIT(DIM) (1u << (DIM))
+
+} // namespace pf

@@ -1,0 +1,385 @@
+// pf_generic.cuh -- DIM-templated cell kernels, one thread per cell, dense shape
+// tables.  This is the portable-in-dimension path: it serves dim = 2 and the
+// secondary 3-D kernels (residual, diagonal, functionals).  The 3-D operator
+// apply has its own tiled kernel in pf_apply3d.cuh.
+//
+// Weak form restated from cracks.cc:2235-2432 (no stress split: sigma+ = sigma).
+#pragma once
+#include "pf_common.cuh"
+
+namespace pf {
+
+template <int DIM>
+__device__ __forceinline__ void
+cell_nodes (const Grid &g, long long lc, long long *node)
+{
+  // lc = local cell index within [cell_begin, cell_end) layers, x fastest
+  long long rem = lc;
+  int ci[3] = {0, 0, 0};
+  for (int d = 0; d < DIM - 1; ++d)
+    {
+      ci[d] = (int) (rem % g.n[d]);
+      rem /= g.n[d];
+    }
+  ci[DIM - 1] = (int) rem + g.cell_begin - g.plane_begin; // local plane index
+  const long long sy = g.nn[0];
+  const long long sz = (long long) g.nn[0] * g.nn[1];
+  for (int v = 0; v < (1 << DIM); ++v)
+    {
+      long long id = (ci[0] + (v & 1)) + (ci[1] + ((v >> 1) & 1)) * sy;
+      if (DIM == 3)
+        id += (ci[2] + ((v >> 2) & 1)) * sz;
+      node[v] = id;
+    }
+}
+
+// q-point state for the no-split constitutive law
+template <int DIM> struct QState
+{
+  double pf, pf_extra, div_u, spE;
+  double gpf[DIM];
+  double gu[DIM][DIM];
+  double sp[DIM][DIM];
+};
+
+template <int DIM>
+__device__ __forceinline__ void
+eval_qstate (const FeTab<DIM> &t, int q, const Phys &p, const double (*ls)[DIM + 1],
+             const double *lpt, QState<DIM> &s)
+{
+  constexpr int NV = 1 << DIM;
+  double pf = 0, pte = 0;
+  for (int a = 0; a < DIM; ++a)
+    {
+      s.gpf[a] = 0;
+      for (int b = 0; b < DIM; ++b)
+        s.gu[a][b] = 0;
+    }
+  for (int v = 0; v < NV; ++v)
+    {
+      const double N = t.N[q][v];
+      pf += N * ls[v][DIM];
+      pte += N * lpt[v];
+      for (int e = 0; e < DIM; ++e)
+        {
+          const double d = t.dN[q][v][e];
+          s.gpf[e] += d * ls[v][DIM];
+          for (int c = 0; c < DIM; ++c)
+            s.gu[c][e] += d * ls[v][c];
+        }
+    }
+  if (p.clamp_extra)
+    pte = fmin (fmax (pte, 0.0), 1.0);
+  s.pf = pf;
+  s.pf_extra = pte;
+  double tr = 0;
+  for (int a = 0; a < DIM; ++a)
+    tr += s.gu[a][a];
+  s.div_u = tr;
+  double spE = 0;
+  for (int a = 0; a < DIM; ++a)
+    for (int b = 0; b < DIM; ++b)
+      {
+        const double E = 0.5 * (s.gu[a][b] + s.gu[b][a]);
+        s.sp[a][b] = (a == b ? p.lambda * tr : 0.0) + 2 * p.mu * E;
+        spE += s.sp[a][b] * E;
+      }
+  s.spE = spE;
+}
+
+// ---- y += J x on the cells of this rank (rows/cols of constrained dofs dropped)
+template <int DIM>
+__global__ void __launch_bounds__ (128)
+k_apply_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
+                 const double *__restrict__ x, const double *__restrict__ sol,
+                 const double *__restrict__ pt, const uint8_t *__restrict__ mask,
+                 double *__restrict__ y)
+{
+  constexpr int NC = DIM + 1, NV = 1 << DIM, NQ = FeTab<DIM>::NQ;
+  const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= g.n_local_cells)
+    return;
+  const FeTab<DIM> &t = *tab;
+  long long node[NV];
+  cell_nodes<DIM> (g, lc, node);
+  double lx[NV][NC], ls[NV][NC], lpt[NV], out[NV][NC];
+  uint8_t lm[NV];
+  for (int v = 0; v < NV; ++v)
+    {
+      lm[v] = mask[node[v]];
+      lpt[v] = pt[node[v]];
+      for (int c = 0; c < NC; ++c)
+        {
+          ls[v][c] = sol[node[v] * NC + c];
+          lx[v][c] = is_constrained (lm[v], c) ? 0.0 : x[node[v] * NC + c];
+          out[v][c] = 0;
+        }
+    }
+  for (int q = 0; q < NQ; ++q)
+    {
+      QState<DIM> s;
+      eval_qstate<DIM> (t, q, p, ls, lpt, s);
+      double G[DIM][DIM], dphi = 0, gdphi[DIM];
+      for (int a = 0; a < DIM; ++a)
+        {
+          gdphi[a] = 0;
+          for (int b = 0; b < DIM; ++b)
+            G[a][b] = 0;
+        }
+      for (int v = 0; v < NV; ++v)
+        {
+          dphi += t.N[q][v] * lx[v][DIM];
+          for (int e = 0; e < DIM; ++e)
+            {
+              const double d = t.dN[q][v][e];
+              gdphi[e] += d * lx[v][DIM];
+              for (int c = 0; c < DIM; ++c)
+                G[c][e] += d * lx[v][c];
+            }
+        }
+      double trG = 0, spG = 0;
+      for (int a = 0; a < DIM; ++a)
+        {
+          trG += G[a][a];
+          for (int b = 0; b < DIM; ++b)
+            spG += s.sp[a][b] * G[a][b];
+        }
+      const double gdeg = (1.0 - p.kappa) * s.pf_extra * s.pf_extra + p.kappa;
+      double Sig[DIM][DIM];
+      for (int a = 0; a < DIM; ++a)
+        for (int b = 0; b < DIM; ++b)
+          Sig[a][b] = gdeg * ((a == b ? p.lambda * trG : 0.0) + p.mu * (G[a][b] + G[b][a]));
+      // (phi,u) + (phi,phi) value coefficient, cracks.cc:2375-2382 with
+      // sigma(du):E(u) == sigma(u):E(du) for the unsplit law
+      const double a_val = s.pf * (2.0 * (1.0 - p.kappa) * spG - 2.0 * p.P1 * trG)
+                           + dphi * ((1.0 - p.kappa) * s.spE + p.G_c / p.eps - 2.0 * p.P1 * s.div_u);
+      const double w = t.JxW[q];
+      for (int v = 0; v < NV; ++v)
+        {
+          double gb = 0;
+          for (int e = 0; e < DIM; ++e)
+            {
+              const double d = t.dN[q][v][e];
+              gb += gdphi[e] * d;
+              for (int c = 0; c < DIM; ++c)
+                out[v][c] += w * Sig[c][e] * d;
+            }
+          out[v][DIM] += w * (a_val * t.N[q][v] + p.G_c * p.eps * gb);
+        }
+    }
+  for (int v = 0; v < NV; ++v)
+    for (int c = 0; c < NC; ++c)
+      if (!is_constrained (lm[v], c))
+        atomicAdd (&y[node[v] * NC + c], out[v][c]);
+}
+
+// ---- r_total += local_rhs (cracks.cc:2393-2432); constraints applied later
+template <int DIM>
+__global__ void __launch_bounds__ (128)
+k_residual_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
+                    const double *__restrict__ sol, const double *__restrict__ pt,
+                    double *__restrict__ r)
+{
+  constexpr int NC = DIM + 1, NV = 1 << DIM, NQ = FeTab<DIM>::NQ;
+  const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= g.n_local_cells)
+    return;
+  const FeTab<DIM> &t = *tab;
+  long long node[NV];
+  cell_nodes<DIM> (g, lc, node);
+  double ls[NV][NC], lpt[NV], out[NV][NC];
+  for (int v = 0; v < NV; ++v)
+    {
+      lpt[v] = pt[node[v]];
+      for (int c = 0; c < NC; ++c)
+        {
+          ls[v][c] = sol[node[v] * NC + c];
+          out[v][c] = 0;
+        }
+    }
+  for (int q = 0; q < NQ; ++q)
+    {
+      QState<DIM> s;
+      eval_qstate<DIM> (t, q, p, ls, lpt, s);
+      const double gdeg = (1.0 - p.kappa) * s.pf_extra * s.pf_extra + p.kappa;
+      const double w = t.JxW[q];
+      const double cphi = (1.0 - p.kappa) * s.spE * s.pf - p.G_c / p.eps * (1.0 - s.pf)
+                          - 2.0 * p.P1 * s.pf * s.div_u;
+      const double pe2 = p.P1 * s.pf_extra * s.pf_extra;
+      for (int v = 0; v < NV; ++v)
+        {
+          double gg = 0;
+          for (int e = 0; e < DIM; ++e)
+            gg += s.gpf[e] * t.dN[q][v][e];
+          for (int c = 0; c < DIM; ++c)
+            {
+              double sc = 0;
+              for (int e = 0; e < DIM; ++e)
+                sc += gdeg * s.sp[c][e] * t.dN[q][v][e];
+              out[v][c] -= w * (sc - pe2 * t.dN[q][v][c]);
+            }
+          out[v][DIM] -= w * (cphi * t.N[q][v] + p.G_c * p.eps * gg);
+        }
+    }
+  for (int v = 0; v < NV; ++v)
+    for (int c = 0; c < NC; ++c)
+      atomicAdd (&r[node[v] * NC + c], out[v][c]);
+}
+
+// ---- diag += sum_cells |local_matrix(i,i)| (average |diag| if zero), the value
+// AffineConstraints::distribute_local_to_global leaves on constrained rows.
+template <int DIM>
+__global__ void __launch_bounds__ (128)
+k_diag_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
+                const double *__restrict__ sol, const double *__restrict__ pt,
+                double *__restrict__ diag)
+{
+  constexpr int NC = DIM + 1, NV = 1 << DIM, NQ = FeTab<DIM>::NQ;
+  const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= g.n_local_cells)
+    return;
+  const FeTab<DIM> &t = *tab;
+  long long node[NV];
+  cell_nodes<DIM> (g, lc, node);
+  double ls[NV][NC], lpt[NV], out[NV][NC];
+  for (int v = 0; v < NV; ++v)
+    {
+      lpt[v] = pt[node[v]];
+      for (int c = 0; c < NC; ++c)
+        {
+          ls[v][c] = sol[node[v] * NC + c];
+          out[v][c] = 0;
+        }
+    }
+  for (int q = 0; q < NQ; ++q)
+    {
+      QState<DIM> s;
+      eval_qstate<DIM> (t, q, p, ls, lpt, s);
+      const double gdeg = (1.0 - p.kappa) * s.pf_extra * s.pf_extra + p.kappa;
+      const double w = t.JxW[q];
+      const double c0 = (1.0 - p.kappa) * s.spE + p.G_c / p.eps - 2.0 * p.P1 * s.div_u;
+      for (int v = 0; v < NV; ++v)
+        {
+          double g2 = 0;
+          for (int e = 0; e < DIM; ++e)
+            g2 += t.dN[q][v][e] * t.dN[q][v][e];
+          const double N = t.N[q][v];
+          for (int c = 0; c < DIM; ++c)
+            {
+              const double d = t.dN[q][v][c];
+              // g * (lambda d_c^2 + mu (|grad N|^2 + d_c^2))
+              out[v][c] += w * gdeg * (p.lambda * d * d + p.mu * (g2 + d * d));
+            }
+          out[v][DIM] += w * (c0 * N * N + p.G_c * p.eps * g2);
+        }
+    }
+  double avg = 0;
+  for (int v = 0; v < NV; ++v)
+    for (int c = 0; c < NC; ++c)
+      avg += fabs (out[v][c]);
+  avg /= (NV * NC);
+  for (int v = 0; v < NV; ++v)
+    for (int c = 0; c < NC; ++c)
+      {
+        const double d = fabs (out[v][c]);
+        atomicAdd (&diag[node[v] * NC + c], d != 0.0 ? d : avg);
+      }
+}
+
+// ---- functionals: bulk / crack energy (cracks.cc:3663-3681), TCV (3585-3586)
+// block-reduced, one atomicAdd per block into out[0..2]
+template <int DIM>
+__global__ void __launch_bounds__ (128)
+k_functionals_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
+                       const double *__restrict__ sol, int owned_cells_only_begin,
+                       int owned_cells_only_end, double *__restrict__ out3)
+{
+  constexpr int NC = DIM + 1, NV = 1 << DIM, NQ = FeTab<DIM>::NQ;
+  const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  double eb = 0, ec = 0, tcv = 0;
+  bool active = lc < g.n_local_cells;
+  if (active)
+    {
+      // cells are owned by exactly one rank: layers [owned_cells_only_begin, end)
+      long long per_layer = g.n[0];
+      if (DIM == 3)
+        per_layer *= g.n[1];
+      const int layer = (int) (lc / per_layer) + g.cell_begin;
+      active = layer >= owned_cells_only_begin && layer < owned_cells_only_end;
+    }
+  if (active)
+    {
+      const FeTab<DIM> &t = *tab;
+      long long node[NV];
+      cell_nodes<DIM> (g, lc, node);
+      double ls[NV][NC];
+      for (int v = 0; v < NV; ++v)
+        for (int c = 0; c < NC; ++c)
+          ls[v][c] = sol[node[v] * NC + c];
+      for (int q = 0; q < NQ; ++q)
+        {
+          double pf = 0, gpf[DIM], u[DIM], gu[DIM][DIM];
+          for (int a = 0; a < DIM; ++a)
+            {
+              gpf[a] = 0;
+              u[a] = 0;
+              for (int b = 0; b < DIM; ++b)
+                gu[a][b] = 0;
+            }
+          for (int v = 0; v < NV; ++v)
+            {
+              const double N = t.N[q][v];
+              pf += N * ls[v][DIM];
+              for (int e = 0; e < DIM; ++e)
+                {
+                  u[e] += N * ls[v][e];
+                  const double d = t.dN[q][v][e];
+                  gpf[e] += d * ls[v][DIM];
+                  for (int c = 0; c < DIM; ++c)
+                    gu[c][e] += d * ls[v][c];
+                }
+            }
+          double trE = 0, trE2 = 0, gg = 0, ug = 0;
+          for (int a = 0; a < DIM; ++a)
+            {
+              trE += gu[a][a];
+              gg += gpf[a] * gpf[a];
+              ug += u[a] * gpf[a];
+              for (int b = 0; b < DIM; ++b)
+                {
+                  const double E = 0.5 * (gu[a][b] + gu[b][a]);
+                  trE2 += E * E;
+                }
+            }
+          const double psi = 0.5 * p.lambda * trE * trE + p.mu * trE2;
+          const double w = t.JxW[q];
+          eb += ((1 + p.kappa) * pf * pf + p.kappa) * psi * w;
+          ec += p.G_c / 2.0 * ((pf - 1) * (pf - 1) / p.eps + p.eps * gg) * w;
+          tcv += ug * w;
+        }
+    }
+  __shared__ double red[3][4];
+  for (int o = 16; o > 0; o >>= 1)
+    {
+      eb += __shfl_down_sync (0xffffffffu, eb, o);
+      ec += __shfl_down_sync (0xffffffffu, ec, o);
+      tcv += __shfl_down_sync (0xffffffffu, tcv, o);
+    }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0)
+    {
+      red[0][w] = eb;
+      red[1][w] = ec;
+      red[2][w] = tcv;
+    }
+  __syncthreads ();
+  if (threadIdx.x < 3)
+    {
+      double s = 0;
+      for (int i = 0; i < (int) (blockDim.x >> 5); ++i)
+        s += red[threadIdx.x][i];
+      atomicAdd (&out3[threadIdx.x], s);
+    }
+}
+
+} // namespace pf

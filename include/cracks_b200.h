@@ -1,0 +1,203 @@
+/*
+ * cracks_b200.h -- C ABI of the B200-native (u,phi) hot path of tjhei/cracks.
+ *
+ * The reference (cracks.cc) has no plugin/FFI interface; its de-facto seam is
+ * deal.II's duck-typed linear operator (`A.vmult(dst, src)`) consumed by
+ * SolverGMRES at cracks.cc:2764-2771, fed by assemble_system() at
+ * cracks.cc:2917.  Each entry point below names the reference code it
+ * replaces.  All functions return PF_OK (0) or a negative pf_status; no C++
+ * exception crosses this boundary.  Plain pointers and sizes only.
+ *
+ * Mesh: the uniform box of GridGenerator::subdivided_hyper_rectangle +
+ * refine_global (cracks.cc:1248-1253, 1534), Q1 elements, nodes numbered
+ * lexicographically (x fastest).
+ *
+ * Host vector layout ("block layout", cracks.cc:1587-1590, 1657-1674):
+ *   [ u-block | phi-block ],  u-block = dim doubles per node (node-major),
+ *   phi-block = one double per node; length n_dofs = (dim+1) * n_nodes.
+ * Constraint masks use the same indexing, one byte per dof (0 / 1).
+ *
+ * Device-resident calls (suffix _dev) take pointers to device memory in the
+ * library's internal layout: node-major interleaved, (dim+1) doubles per node
+ * ([ux,uy,uz,phi] = 32 B per 3-D node), restricted to the calling rank's slab
+ * of node planes (see pf_local_layout).  They never touch host memory and
+ * enqueue on the context's stream.
+ *
+ * Threading: one host thread per context (like one MPI rank, cracks.cc:4587);
+ * calls on one context are not re-entrant.  With nranks > 1 every call marked
+ * [collective] must be entered by all ranks in the same order.
+ */
+#ifndef CRACKS_B200_H
+#define CRACKS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum
+{
+  PF_OK = 0,
+  PF_BAD_ARG = -1,
+  PF_CUDA_ERROR = -2,
+  PF_NCCL_ERROR = -3,
+  PF_NO_CONVERGENCE = -4, /* SolverControl::NoConvergence, cracks.cc:2987 / GMRES 2762-2771 */
+  PF_NUMERIC = -5,        /* non-finite values; the abort() of cracks.cc:1732-1736 */
+  PF_UNSUPPORTED = -6
+} pf_status;
+
+typedef struct pf_ctx pf_ctx;
+
+typedef struct
+{
+  int dim;          /* 2 or 3 (Global parameters / Dimension, cracks.cc:4641) */
+  int n[3];         /* cells per direction: 10 * 2^(global pre-refinement) for Sneddon */
+  double h[3];      /* cell edge lengths */
+  double origin[3]; /* lower corner of the box */
+} pf_mesh;
+
+typedef struct
+{
+  double lambda, mu;  /* Lame coefficients, cracks.cc:1507-1510 */
+  double G_c;         /* Fracture toughness G_c */
+  double kappa;       /* constant_k  = K reg(h),   cracks.cc:3879 */
+  double eps;         /* alpha_eps   = Eps reg(h), cracks.cc:3881 */
+  double alpha_biot;  /* 0 in the reference, cracks.cc:1497 */
+} pf_params;
+
+/* Slab decomposition of the node planes (last coordinate) over ranks. */
+typedef struct
+{
+  int64_t n_nodes_global;
+  int64_t n_nodes_plane;   /* nodes in one plane of the slowest coordinate */
+  int plane_begin;         /* first local node plane (global index), including the lower ghost */
+  int plane_end;           /* one past the last local node plane, including the upper ghost */
+  int owned_begin;         /* planes [owned_begin, owned_end) are owned by this rank */
+  int owned_end;
+  int ncomp;               /* dim + 1 */
+} pf_local_layout;
+
+/* ---- life cycle --------------------------------------------------------- */
+
+/* Replaces setup_system()'s allocation of matrix/vectors (cracks.cc:1579-1680):
+ * allocates all device state for one rank.  nccl_id is a 128-byte
+ * ncclUniqueId (from pf_nccl_unique_id on rank 0) or NULL when nranks == 1. */
+int pf_create (const pf_mesh *mesh, const pf_params *params, int device,
+               int rank, int nranks, const void *nccl_id, pf_ctx **out);
+int pf_destroy (pf_ctx *ctx);
+const char *pf_last_error (const pf_ctx *ctx);
+int pf_nccl_unique_id (void *id128);
+int pf_get_layout (const pf_ctx *ctx, pf_local_layout *out);
+int64_t pf_n_dofs (const pf_ctx *ctx);
+/* the CUDA stream all work of this context is enqueued on (a cudaStream_t) */
+void *pf_stream (const pf_ctx *ctx);
+int pf_synchronize (pf_ctx *ctx);
+
+/* ---- state and constraints ---------------------------------------------- */
+
+/* The three ghosted vectors assemble_system() imports (cracks.cc:2147-2154),
+ * the time-step sizes of the pf_extra extrapolation (2268-2277), the pressure
+ * func_pressure(time) (2145).  Host pointers, block layout.  old / oldold may
+ * be NULL to keep the previous ones.  [collective] */
+int pf_set_state (pf_ctx *ctx, const double *sol, const double *old, const double *oldold,
+                  double dt_old, double dt_oldold, int use_old_timestep_pf, double pressure);
+int pf_get_solution (pf_ctx *ctx, double *sol);
+/* in-place update of the linearisation point: sol += alpha * dx (line search, cracks.cc:2944) */
+int pf_update_solution (pf_ctx *ctx, double alpha);
+int pf_set_params (pf_ctx *ctx, const pf_params *params);
+
+/* constraints_update = Dirichlet rows (set_newton_bc, cracks.cc:2709-2714)
+ * united with the active set (2878-2881); both masks in block layout, either
+ * may be NULL (= keep).  */
+int pf_set_constraints (pf_ctx *ctx, const uint8_t *dirichlet_mask, const uint8_t *active_mask);
+/* Dirichlet rows of the Sneddon / 3-D cases: all u components on every face
+ * (cracks.cc:2575-2583, 2686-2694), built on the device. */
+int pf_set_dirichlet_all_faces (pf_ctx *ctx);
+
+/* ---- the hot path ------------------------------------------------------- */
+
+/* assemble_nl_residual() + constraints_update.set_zero + l2_norm
+ * (cracks.cc:2507-2512, 2790-2794, 2946-2949).  r_pde / r_total are host
+ * buffers in block layout and may be NULL.  [collective] */
+int pf_residual (pf_ctx *ctx, double *r_pde, double *r_total, double *l2_norm);
+
+/* Linearise at the current state: what assemble_system(false) does before
+ * solve() (cracks.cc:2917) minus the sparse matrix -- it computes the
+ * operator diagonal (used for constrained rows and by the preconditioner).
+ * Must be called after pf_set_state / pf_set_constraints and before
+ * pf_apply_jacobian / pf_solve.  [collective] */
+int pf_setup_jacobian (pf_ctx *ctx);
+
+/* y = J(U) x with constraints_update applied the way
+ * AffineConstraints::distribute_local_to_global does (rows and columns of
+ * constrained dofs eliminated, positive diagonal kept): the vmult of
+ * system_pde_matrix at cracks.cc:2770.  Host buffers, block layout.  [collective] */
+int pf_apply_jacobian (pf_ctx *ctx, const double *x, double *y);
+/* same, device-resident, internal layout, local slab (ghost planes of x are
+ * refreshed by the call).  [collective] */
+int pf_apply_jacobian_dev (pf_ctx *ctx, double *x_dev, double *y_dev);
+
+/* diag(J) as used for constrained rows and the Jacobi/Chebyshev smoother */
+int pf_jacobian_diagonal (pf_ctx *ctx, double *diag);
+
+/* assemble_diag_mass_matrix(), cracks.cc:2514-2562; one double per node */
+int pf_lumped_mass (pf_ctx *ctx, double *mass);
+
+/* New active set, cracks.cc:2822-2899 + cycle detection 2901-2907, using the
+ * r_total of the last pf_residual: a phi dof is active iff
+ *   r_total/m + c (phi - phi_old) > 0   or it switched >= 5 times.
+ * Resets phi to phi_old on the set, installs the set into the constraints.
+ * active_mask (one byte per node, may be NULL) receives the set.  [collective] */
+int pf_active_set_update (pf_ctx *ctx, double c, uint8_t *active_mask,
+                          int64_t *n_active, int64_t *n_cycling, int *changed);
+int pf_active_set_reset (pf_ctx *ctx);
+
+/* solve(): GMRES(<= max_it, tol_rel * ||r_pde||_2) on J dx = r_pde with the
+ * matrix-free operator, then constraints_update.distribute (constrained
+ * entries of dx = 0); cracks.cc:2744-2777.  dx (host, block layout) may be
+ * NULL: the update stays on the device for pf_update_solution.
+ * Returns PF_NO_CONVERGENCE like SolverControl.  [collective] */
+int pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it);
+
+/* ---- functionals (parity metrics) --------------------------------------- */
+int pf_energy (pf_ctx *ctx, double *bulk, double *crack);   /* cracks.cc:3615-3701 */
+int pf_tcv (pf_ctx *ctx, double *tcv);                      /* cracks.cc:3553-3589 */
+int pf_project_phase_field (pf_ctx *ctx);                   /* cracks.cc:3109-3137 */
+int pf_interpolate_sneddon (pf_ctx *ctx, double h_diam);    /* InitialValuesSneddon, cracks.cc:381-406 */
+/* time-step bookkeeping on the device: oldold <- old <- sol (cracks.cc:4302-4303);
+ * returns ||old - sol||_inf of the step just finished (4478-4483) */
+int pf_advance_timestep (pf_ctx *ctx);
+int pf_timestep_difference (pf_ctx *ctx, double *linfty);
+int pf_restore_old_solution (pf_ctx *ctx);                  /* solution = old_solution, cracks.cc:4340 */
+/* time-step sizes of the extrapolation, use_old_timestep_pf and Pressure(time)
+ * without touching the device-resident vectors (cracks.cc:2145, 2268-2277) */
+int pf_set_time_parameters (pf_ctx *ctx, double dt_old, double dt_oldold, int use_old_timestep_pf,
+                            double pressure);
+/* line search bookkeeping on the device (cracks.cc:2922, 2955-2956) */
+int pf_save_solution (pf_ctx *ctx);            /* saved_solution = solution */
+int pf_restore_saved_solution (pf_ctx *ctx);   /* solution = saved_solution */
+int pf_scale_update (pf_ctx *ctx, double factor); /* newton_update *= line_search_damping */
+
+/* ---- device-resident helpers for benchmarks / device-side solvers -------- */
+int pf_device_vector (pf_ctx *ctx, double **out);            /* local slab, internal layout */
+int pf_device_vector_free (pf_ctx *ctx, double *v);
+int pf_upload (pf_ctx *ctx, const double *host_block, double *dev);   /* block -> internal */
+int pf_download (pf_ctx *ctx, const double *dev, double *host_block); /* internal -> block */
+/* number of kernel launches issued on this context so far */
+int64_t pf_launch_count (const pf_ctx *ctx);
+/* CUDA-event timing of the dominant kernel (tiled 3-D apply) on the context's
+ * stream: enable, run, then read the summed milliseconds and launch count */
+int pf_profile_enable (pf_ctx *ctx, int on);
+int pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count);
+/* pinned host memory for callers that want full PCIe bandwidth */
+int pf_host_alloc (void **out, size_t bytes);
+int pf_host_free (void *p);
+/* testing aid: route the 3-D apply through the dimension-generic kernel */
+int pf_debug_force_generic (int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRACKS_B200_H */

@@ -1,0 +1,190 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Bit-level agreement is not expected for
+FP64 sums in a different order; the tolerance is 1e-12 relative l-infinity
+(SURVEY.md 8c)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def _mesh(pf, dim, n, h, origin):
+    m = pf.Mesh()
+    m.dim = dim
+    for d in range(3):
+        m.n[d] = n[d] if d < dim else 1
+        m.h[d] = h[d] if d < dim else 1.0
+        m.origin[d] = origin[d] if d < dim else 0.0
+    return m
+
+
+def _case(oracle, pf, dim, n, h, seed, kappa=1e-3, clamp_active=True):
+    """Random but physical state on an n[0] x n[1] (x n[2]) box; returns the oracle
+    problem, a GPU context with the same state, and the state in nodal layout."""
+    rng = np.random.default_rng(seed)
+    lo = tuple(-0.5 * n[d] * h[d] for d in range(dim))
+    hi = tuple(0.5 * n[d] * h[d] for d in range(dim))
+    prob = oracle.Problem(dim, tuple(n), lo, hi, kappa_of_h=lambda hh: kappa, eps_of_h=lambda hh: 2.0 * hh,
+                          pressure=1e-3)
+    nc = dim + 1
+    sol = np.zeros((prob.n_nodes, nc))
+    sol[:, :dim] = 1e-2 * rng.standard_normal((prob.n_nodes, dim))
+    sol[:, dim] = rng.random(prob.n_nodes)
+    old = sol.copy()
+    oo = sol.copy()
+    old[:, dim] = rng.random(prob.n_nodes)
+    # extrapolation leaves [0,1] on a good part of the nodes when clamp_active
+    oo[:, dim] = old[:, dim] + (0.5 if clamp_active else 0.05) * (rng.random(prob.n_nodes) - 0.5)
+    sol, old, oo = sol.reshape(-1), old.reshape(-1), oo.reshape(-1)
+    prob.prm.dt_old, prob.prm.dt_oldold = 1.0, 0.5
+    con = prob.dirichlet_mask().reshape(-1, nc)
+    con[rng.random(prob.n_nodes) < 0.2, dim] = 1
+    con = np.ascontiguousarray(con.reshape(-1))
+    mesh = _mesh(pf, dim, n, h, lo)
+    params = pf.Params(prob.prm.lam, prob.prm.mu, prob.prm.G_c, prob.prm.kappa, prob.prm.eps, 0.0)
+    ctx = pf.PhaseFieldContext(mesh, params)
+    ctx.set_state(ctx.to_block(sol), ctx.to_block(old), ctx.to_block(oo), dt_old=1.0, dt_oldold=0.5,
+                  use_old_timestep_pf=False, pressure=prob.pressure)
+    cb = ctx.to_block(con).astype(np.uint8)
+    ctx.set_constraints(cb, cb)
+    return prob, ctx, sol, old, oo, con, rng
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+CASES_3D = [((10, 10, 10), (2.0, 2.0, 2.0)),      # the KAT-1 mesh
+            ((16, 4, 2), (0.5, 0.5, 0.5)),        # exactly one tile
+            ((19, 7, 5), (0.3, 0.45, 0.7)),       # ragged tiles, anisotropic cells
+            ((1, 1, 1), (1.0, 1.0, 1.0)),         # a single cell
+            ((33, 9, 3), (0.25, 0.25, 0.25))]
+
+
+@pytest.mark.parametrize("n,h", CASES_3D)
+def test_apply_jacobian_3d(oracle, pf, n, h):
+    prob, ctx, sol, old, oo, con, rng = _case(oracle, pf, 3, n, h, seed=sum(n))
+    ctx.setup_jacobian()
+    x = rng.standard_normal(prob.n_dofs)
+    y_ref = prob.apply_jacobian(sol, old, oo, con, x)
+    y = np.zeros(prob.n_dofs)
+    ctx.vmult(y, ctx.to_block(x))
+    assert _relerr(ctx.to_nodal(y), y_ref) <= TOL
+    # the dimension-generic kernel is an independent second implementation
+    ctx.lib.pf_debug_force_generic(1)
+    try:
+        y2 = np.zeros(prob.n_dofs)
+        ctx.vmult(y2, ctx.to_block(x))
+    finally:
+        ctx.lib.pf_debug_force_generic(0)
+    assert _relerr(ctx.to_nodal(y2), y_ref) <= TOL
+    ctx.close()
+
+
+def test_apply_jacobian_3d_use_old_timestep_pf(oracle, pf):
+    prob, ctx, sol, old, oo, con, rng = _case(oracle, pf, 3, (9, 6, 4), (0.5, 0.5, 0.5), seed=11)
+    prob.prm.use_old_timestep_pf = 1
+    ctx.set_time_parameters(1.0, 0.5, True, prob.pressure)
+    ctx.setup_jacobian()
+    x = rng.standard_normal(prob.n_dofs)
+    y_ref = prob.apply_jacobian(sol, old, oo, con, x)
+    y = np.zeros(prob.n_dofs)
+    ctx.vmult(y, ctx.to_block(x))
+    assert _relerr(ctx.to_nodal(y), y_ref) <= TOL
+    ctx.close()
+
+
+def test_apply_jacobian_unit_vectors_match_csr_columns(oracle, pf):
+    prob, ctx, sol, old, oo, con, rng = _case(oracle, pf, 3, (4, 3, 3), (1.0, 0.8, 1.2), seed=2)
+    ctx.setup_jacobian()
+    J = prob.jacobian(sol, old, oo, con).tocsc()
+    scale = abs(J).max()
+    for j in rng.choice(prob.n_dofs, 24, replace=False):
+        e = np.zeros(prob.n_dofs)
+        e[j] = 1.0
+        y = np.zeros(prob.n_dofs)
+        ctx.vmult(y, ctx.to_block(e))
+        col = np.asarray(J[:, j].todense()).reshape(-1)
+        assert np.max(np.abs(ctx.to_nodal(y) - col)) <= TOL * scale
+    ctx.close()
+
+
+@pytest.mark.parametrize("n,h", [((10, 10), (2.0, 2.0)), ((13, 7), (0.3, 0.5)), ((1, 1), (1.0, 1.0))])
+def test_apply_jacobian_2d(oracle, pf, n, h):
+    prob, ctx, sol, old, oo, con, rng = _case(oracle, pf, 2, n, h, seed=sum(n))
+    ctx.setup_jacobian()
+    x = rng.standard_normal(prob.n_dofs)
+    y_ref = prob.apply_jacobian(sol, old, oo, con, x)
+    y = np.zeros(prob.n_dofs)
+    ctx.vmult(y, ctx.to_block(x))
+    assert _relerr(ctx.to_nodal(y), y_ref) <= TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("dim,n,h", [(3, (10, 10, 10), (2.0, 2.0, 2.0)), (3, (7, 5, 3), (0.3, 0.45, 0.7)),
+                                     (2, (13, 7), (0.3, 0.5))])
+def test_residual_diag_energy(oracle, pf, dim, n, h):
+    prob, ctx, sol, old, oo, con, rng = _case(oracle, pf, dim, n, h, seed=7 + sum(n))
+    r_pde_ref, r_tot_ref = prob.residual(sol, old, oo, con)
+    r_pde, r_tot, nrm = ctx.residual()
+    assert _relerr(ctx.to_nodal(r_tot), r_tot_ref) <= TOL
+    assert _relerr(ctx.to_nodal(r_pde), r_pde_ref) <= TOL
+    assert nrm == pytest.approx(np.linalg.norm(r_pde_ref), rel=1e-12)
+    ctx.setup_jacobian()
+    d_ref = prob.jacobian(sol, old, oo, None).diagonal()
+    assert np.all(d_ref > 0)
+    assert _relerr(ctx.to_nodal(ctx.jacobian_diagonal()), d_ref) <= TOL
+    b_ref, c_ref = prob.energy(sol)
+    b, c = ctx.energy()
+    assert b == pytest.approx(b_ref, rel=1e-12) and c == pytest.approx(c_ref, rel=1e-12)
+    assert ctx.tcv() == pytest.approx(prob.tcv(sol), rel=1e-11, abs=1e-15)
+    assert np.allclose(ctx.lumped_mass(), prob.lumped_mass(), rtol=1e-15)
+    ctx.close()
+
+
+def test_active_set_update(oracle, pf):
+    prob, ctx, sol, old, oo, con, rng = _case(oracle, pf, 3, (6, 5, 4), (0.5, 0.5, 0.5), seed=21)
+    _, r_tot, _ = ctx.residual()
+    r_tot_nodal = ctx.to_nodal(r_tot)
+    mass = prob.lumped_mass()
+    cycle = np.zeros(prob.n_nodes, dtype=np.int32)
+    sol_ref = sol.copy()
+    act_ref, cnt_ref, _ = prob.active_set(10.0, r_tot_nodal, mass, old, sol_ref, cycle)
+    ctx.active_set_reset()
+    act, cnt, ncyc, changed = ctx.active_set_update(10.0)
+    assert cnt == cnt_ref and ncyc == 0 and changed
+    assert np.array_equal(act, act_ref)
+    assert np.array_equal(ctx.to_nodal(ctx.get_solution()), sol_ref)
+    # a second update with the same residual changes nothing
+    ctx.residual(want_vectors=False)
+    ctx.close()
+
+
+def test_gmres_solves_the_newton_system(oracle, pf):
+    import scipy.sparse.linalg as spla
+    prob, ctx, sol, old, oo, con, rng = _case(oracle, pf, 3, (6, 6, 6), (1.0, 1.0, 1.0), seed=5, clamp_active=False)
+    r_pde_ref, _ = prob.residual(sol, old, oo, con)
+    J = prob.jacobian(sol, old, oo, con).tocsc()
+    dx_ref = spla.spsolve(J, r_pde_ref)
+    dx_ref[con == 1] = 0.0
+    ctx.residual(want_vectors=False)
+    ctx.setup_jacobian()
+    dx, its = ctx.solve(1e-10, 2000, want_dx=True)
+    assert 0 < its <= 2000
+    assert _relerr(ctx.to_nodal(dx), dx_ref) <= 1e-7
+    with pytest.raises(pf.NoConvergence):
+        ctx.solve(1e-14, 3)
+    ctx.close()
+
+
+def test_errors_are_loud(pf):
+    m = pf.sneddon_mesh(3, 0)
+    ctx = pf.PhaseFieldContext(m, pf.sneddon_params(m))
+    y = np.zeros(ctx.n_dofs)
+    with pytest.raises(pf.PFError):
+        ctx.vmult(y, y.copy())          # no pf_setup_jacobian yet
+    with pytest.raises(pf.PFError):
+        ctx.active_set_update(10.0)     # no residual yet
+    ctx.close()
