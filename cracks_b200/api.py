@@ -103,6 +103,7 @@ _SIGS = {
     "pf_host_alloc": [C.POINTER(C.c_void_p), C.c_size_t],
     "pf_host_free": [C.c_void_p],
     "pf_debug_force_generic": [C.c_int],
+    "pf_debug_set_variant": [C.c_int],
     "pf_profile_enable": [C.c_void_p, C.c_int],
     "pf_profile_read": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
 }

@@ -17,6 +17,7 @@
 
 #include "../../include/cracks_b200.h"
 #include "pf_apply3d.cuh"
+#include "pf_apply3d_v2.cuh"
 #include "pf_common.cuh"
 #include "pf_generic.cuh"
 #include "pf_vector.cuh"
@@ -345,6 +346,28 @@ launch_apply3d (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
+template <int TX, int TY, int TZ>
+int
+launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
+{
+  using T = Tile3v2<TX, TY, TZ>;
+  const Grid &g = ctx->g;
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+  const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  static bool attr_set = false;
+  if (!attr_set)
+    {
+      CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes));
+      attr_set = true;
+    }
+  k_apply3d_v2<TX, TY, TZ><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes, ctx->stream>>> (
+    g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  KCHECK ();
+  return PF_OK;
+}
+
+int g_apply_variant = 2;
 int g_force_generic = 0;
 
 int
@@ -384,7 +407,7 @@ apply_dev (pf_ctx *ctx, double *x, double *y)
               CU (cudaEventCreate (&e1));
               CU (cudaEventRecord (e0, ctx->stream));
             }
-          rc = launch_apply3d<16, 4, 2> (ctx, x, y);
+          rc = g_apply_variant == 1 ? launch_apply3d<16, 4, 2> (ctx, x, y) : launch_apply3d_v2<16, 4, 2> (ctx, x, y);
           if (rc)
             return rc;
           if (ctx->profiling)
@@ -1356,6 +1379,15 @@ pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count)
   *total_ms = tot;
   *count = (int64_t) ctx->prof_events.size ();
   ctx->prof_events.clear ();
+  return PF_OK;
+}
+
+int
+pf_debug_set_variant (int variant)
+{
+  if (variant != 1 && variant != 2)
+    return PF_BAD_ARG;
+  g_apply_variant = variant;
   return PF_OK;
 }
 

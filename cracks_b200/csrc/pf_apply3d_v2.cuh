@@ -1,0 +1,326 @@
+// pf_apply3d_v2.cuh -- second generation of the hot kernel (see pf_apply3d.cuh
+// for the weak form and the conventions; this file only changes the mapping).
+//
+// v1 kept the z-collapsed ("plane level") arrays of all 9 nodal fields in
+// registers; ptxas spilled 1.4 KB/thread and ncu showed the spills missing L1
+// (profiles/r1_v1_apply3d_ncu_summary.txt).  v2 removes them:
+//   stage 1  per node column (shared by the 4 cells around it) and Gauss plane
+//            qz: z-collapsed values A[qz][f] and scaled z-differences D[f] are
+//            computed once per tile and kept in shared memory;
+//   stage 2  the z-derivative chain does not depend on qz: its y-collapse
+//            Bz[f][qy] per (x-node, cell row) is staged once per tile too;
+//   stage 3  one thread per cell walks plane -> row -> point; a row needs
+//            4 x 9 loads of A and 2 x 7 of Bz, everything else is registers;
+//   stage 4  per plane, the 32 nodal contributions go to the shared y tile in
+//            8 conflict-free phases; the tile is flushed with red.global.add.
+#pragma once
+#include "pf_apply3d.cuh"
+
+namespace pf {
+
+template <int TX, int TY, int TZ> struct Tile3v2
+{
+  static constexpr int NX = TX + 1, NY = TY + 1, NZ = TZ + 1;
+  static constexpr int NN = NX * NY * NZ;
+  static constexpr int NC2 = NX * NY * TZ; // node columns x cell layers
+  static constexpr int NXC = NX * TY * TZ; // (x-node, cell row, layer)
+  static constexpr int NT = TX * TY * TZ;
+  static constexpr int SY = NX, SZ = NX * NY;
+  static constexpr size_t smem_doubles = (size_t) 27 * NC2 + 7 * NC2 + 21 * NXC + 4 * NN;
+  static constexpr size_t smem_bytes = smem_doubles * sizeof (double);
+};
+
+template <int TX, int TY, int TZ>
+__global__ void __launch_bounds__ (TX * TY * TZ, 2)
+k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
+              const double *__restrict__ x, const double *__restrict__ sol,
+              const double *__restrict__ pt, const uint8_t *__restrict__ mask,
+              double *__restrict__ y)
+{
+  using T = Tile3v2<TX, TY, TZ>;
+  constexpr int NN = T::NN, NT = T::NT, NX = T::NX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC;
+  extern __shared__ __align__ (16) unsigned char smem_raw[];
+  double *AZ = reinterpret_cast<double *> (smem_raw); // [3][9][NC2]
+  double *DZ = AZ + 27 * NC2;                         // [7][NC2]
+  double *BZ = DZ + 7 * NC2;                          // [7][3][NXC]
+  double *ys = BZ + 21 * NXC;                         // [4][NN]
+
+  const int tid = threadIdx.x;
+  int b = blockIdx.x;
+  const int bx = b % tiles_x;
+  b /= tiles_x;
+  const int by = b % tiles_y;
+  const int bz = b / tiles_y;
+  const int cx0 = bx * TX, cy0 = by * TY, cz0 = g.cell_begin + bz * TZ;
+  const int nnx = g.nn[0], nny = g.nn[1];
+  const int lz_off = g.plane_begin;
+  const long long pstride = g.nodes_per_plane;
+  const double S = k.s;
+
+  // ---- stage 1: z-collapse per node column --------------------------------
+  for (int i = tid; i < NC2; i += NT)
+    {
+      const int ix = i % NX, iy = (i / NX) % NY, tz = i / (NX * NY);
+      const int gx = cx0 + ix, gy = cy0 + iy, gz = cz0 + tz;
+      double f0[9], f1[9];
+#pragma unroll
+      for (int f = 0; f < 9; ++f)
+        f0[f] = f1[f] = 0;
+      if (gx < nnx && gy < nny && gz < g.cell_end)
+        {
+          const long long n0 = gx + (long long) nnx * gy + pstride * (gz - lz_off);
+          const long long n1 = n0 + pstride;
+          const double4 xa = *reinterpret_cast<const double4 *> (x + 4 * n0);
+          const double4 xb = *reinterpret_cast<const double4 *> (x + 4 * n1);
+          const double4 sa = *reinterpret_cast<const double4 *> (sol + 4 * n0);
+          const double4 sb = *reinterpret_cast<const double4 *> (sol + 4 * n1);
+          const uint8_t m0 = mask[n0], m1 = mask[n1];
+          f0[0] = (m0 & 1) ? 0.0 : xa.x;
+          f0[1] = (m0 & 2) ? 0.0 : xa.y;
+          f0[2] = (m0 & 4) ? 0.0 : xa.z;
+          f0[3] = (m0 & 8) ? 0.0 : 0.125 * xa.w;
+          f1[0] = (m1 & 1) ? 0.0 : xb.x;
+          f1[1] = (m1 & 2) ? 0.0 : xb.y;
+          f1[2] = (m1 & 4) ? 0.0 : xb.z;
+          f1[3] = (m1 & 8) ? 0.0 : 0.125 * xb.w;
+          f0[4] = sa.x, f0[5] = sa.y, f0[6] = sa.z, f0[7] = 0.125 * sa.w, f0[8] = 0.125 * pt[n0];
+          f1[4] = sb.x, f1[5] = sb.y, f1[6] = sb.z, f1[7] = 0.125 * sb.w, f1[8] = 0.125 * pt[n1];
+        }
+#pragma unroll
+      for (int f = 0; f < 9; ++f)
+        {
+          const double s = f0[f] + f1[f], r = f1[f] - f0[f];
+          AZ[(0 * 9 + f) * NC2 + i] = fma (-S, r, s);
+          AZ[(1 * 9 + f) * NC2 + i] = s;
+          AZ[(2 * 9 + f) * NC2 + i] = fma (S, r, s);
+          if (f < 7)
+            DZ[f * NC2 + i] = r * ((f == 3) ? k.gp[2] : k.gu[2]);
+        }
+    }
+  for (int i = tid; i < 4 * NN; i += NT)
+    ys[i] = 0;
+  __syncthreads ();
+  // ---- stage 2: y-collapse of the z-derivative chain ------------------------
+  for (int i = tid; i < NXC; i += NT)
+    {
+      const int ix = i % NX, cy = (i / NX) % TY, tz = i / (NX * TY);
+      const int c0 = ix + NX * (cy + NY * tz);
+#pragma unroll
+      for (int f = 0; f < 7; ++f)
+        {
+          const double d0 = DZ[f * NC2 + c0], d1 = DZ[f * NC2 + c0 + NX];
+          const double P = d0 + d1, R = d1 - d0;
+          BZ[(f * 3 + 0) * NXC + i] = fma (-S, R, P);
+          BZ[(f * 3 + 1) * NXC + i] = P;
+          BZ[(f * 3 + 2) * NXC + i] = fma (S, R, P);
+        }
+    }
+  __syncthreads ();
+
+  // ---- stage 3: one thread per cell -----------------------------------------
+  const int tx = tid % TX, ty = (tid / TX) % TY, tz = tid / (TX * TY);
+  const bool valid = (cx0 + tx < g.n[0]) && (cy0 + ty < g.n[1]) && (cz0 + tz < g.cell_end);
+  const int c00 = tx + NX * (ty + NY * tz);
+  const int it0 = tx + NX * (ty + TY * tz);
+  const int nbase = tx + T::SY * ty + T::SZ * tz;
+
+  const double omk = 1.0 - p.kappa;
+  const double c_gce = p.G_c / p.eps;
+  const double c_gceps = p.G_c * p.eps;
+  const double two_mu = 2.0 * p.mu;
+  const double es[3] = {-S, 0.0, S};
+
+#pragma unroll 1
+  for (int qz = 0; qz < 3; ++qz)
+    {
+      const double ez = (qz == 0) ? -S : (qz == 1 ? 0.0 : S);
+      const double *Aq = AZ + qz * 9 * NC2 + c00;
+      double VP[4][2], VR[4][2], DP[4][2], DR[4][2], YP[4], YR[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        {
+          YP[c] = YR[c] = 0;
+#pragma unroll
+          for (int vx = 0; vx < 2; ++vx)
+            VP[c][vx] = VR[c][vx] = DP[c][vx] = DR[c][vx] = 0;
+        }
+      if (valid)
+        {
+#pragma unroll
+          for (int qy = 0; qy < 3; ++qy)
+            {
+              const double ey = es[qy];
+              double PxB[9], RxB[9], PxBz[7], RxBz[7], dx[7], PxDy[7], RxDy[7];
+#pragma unroll
+              for (int f = 0; f < 9; ++f)
+                {
+                  const double a00 = Aq[f * NC2], a10 = Aq[f * NC2 + 1];
+                  const double a01 = Aq[f * NC2 + NX], a11 = Aq[f * NC2 + NX + 1];
+                  const double r0 = a01 - a00, r1 = a11 - a10;
+                  const double b0 = (qy == 1) ? a00 + a01 : fma (ey, r0, a00 + a01);
+                  const double b1 = (qy == 1) ? a10 + a11 : fma (ey, r1, a10 + a11);
+                  PxB[f] = b0 + b1;
+                  RxB[f] = b1 - b0;
+                  if (f < 7)
+                    {
+                      const double gys = (f == 3) ? k.gp[1] : k.gu[1];
+                      dx[f] = RxB[f] * ((f == 3) ? k.gp[0] : k.gu[0]);
+                      PxDy[f] = (r0 + r1) * gys;
+                      RxDy[f] = (r1 - r0) * gys;
+                      const double z0 = BZ[(f * 3 + qy) * NXC + it0], z1 = BZ[(f * 3 + qy) * NXC + it0 + 1];
+                      PxBz[f] = z0 + z1;
+                      RxBz[f] = z1 - z0;
+                    }
+                }
+              double XS[4], ZP[4], ZR[4], yP[4], yR[4];
+              double AP = 0, AR = 0;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                XS[c] = ZP[c] = ZR[c] = yP[c] = yR[c] = 0;
+
+#pragma unroll
+              for (int qx = 0; qx < 3; ++qx)
+                {
+                  const double ex = es[qx];
+                  double G[3][3], U[3][3], gph[3];
+#pragma unroll
+                  for (int c = 0; c < 3; ++c)
+                    {
+                      G[c][0] = dx[c];
+                      G[c][1] = (qx == 1) ? PxDy[c] : fma (ex, RxDy[c], PxDy[c]);
+                      G[c][2] = (qx == 1) ? PxBz[c] : fma (ex, RxBz[c], PxBz[c]);
+                      U[c][0] = dx[4 + c];
+                      U[c][1] = (qx == 1) ? PxDy[4 + c] : fma (ex, RxDy[4 + c], PxDy[4 + c]);
+                      U[c][2] = (qx == 1) ? PxBz[4 + c] : fma (ex, RxBz[4 + c], PxBz[4 + c]);
+                    }
+                  gph[0] = dx[3];
+                  gph[1] = (qx == 1) ? PxDy[3] : fma (ex, RxDy[3], PxDy[3]);
+                  gph[2] = (qx == 1) ? PxBz[3] : fma (ex, RxBz[3], PxBz[3]);
+                  const double dphi = (qx == 1) ? PxB[3] : fma (ex, RxB[3], PxB[3]);
+                  const double pf = (qx == 1) ? PxB[7] : fma (ex, RxB[7], PxB[7]);
+                  double pte = (qx == 1) ? PxB[8] : fma (ex, RxB[8], PxB[8]);
+                  if (p.clamp_extra)
+                    pte = fmin (fmax (pte, 0.0), 1.0);
+
+                  const double gdeg = fma (omk * pte, pte, p.kappa);
+                  const double trU = U[0][0] + U[1][1] + U[2][2];
+                  const double trG = G[0][0] + G[1][1] + G[2][2];
+                  const double o01 = G[0][1] + G[1][0], o02 = G[0][2] + G[2][0], o12 = G[1][2] + G[2][1];
+                  const double u01 = U[0][1] + U[1][0], u02 = U[0][2] + U[2][0], u12 = U[1][2] + U[2][1];
+                  const double ddot = fma (U[0][0], G[0][0], fma (U[1][1], G[1][1], U[2][2] * G[2][2]));
+                  const double odot = fma (u01, o01, fma (u02, o02, u12 * o12));
+                  const double spG = fma (p.lambda * trU, trG, two_mu * fma (0.5, odot, ddot));
+                  const double dd2 = fma (U[0][0], U[0][0], fma (U[1][1], U[1][1], U[2][2] * U[2][2]));
+                  const double od2 = fma (u01, u01, fma (u02, u02, u12 * u12));
+                  const double spE = fma (p.lambda * trU, trU, two_mu * fma (0.5, od2, dd2));
+                  const double a_val = pf * (2.0 * omk * spG - 2.0 * p.P1 * trG)
+                                       + dphi * (fma (omk, spE, c_gce) - 2.0 * p.P1 * trU);
+                  const double w = k.wvol * k.wq[qx] * k.wq[qy] * k.wq[qz];
+                  const double wg = w * gdeg;
+                  const double wgl = wg * p.lambda * trG, wgm = wg * p.mu, wg2m = wg * two_mu;
+                  const double S00 = fma (wg2m, G[0][0], wgl), S11 = fma (wg2m, G[1][1], wgl),
+                               S22 = fma (wg2m, G[2][2], wgl);
+                  const double S01 = wgm * o01, S02 = wgm * o02, S12 = wgm * o12;
+                  const double wa = w * a_val, wb = w * c_gceps;
+                  const double fx[4] = {S00, S01, S02, wb * gph[0]};
+                  const double fy[4] = {S01, S11, S12, wb * gph[1]};
+                  const double fz[4] = {S02, S12, S22, wb * gph[2]};
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    {
+                      XS[c] += fx[c];
+                      yP[c] += fy[c];
+                      ZP[c] += fz[c];
+                      if (qx != 1)
+                        {
+                          yR[c] = fma (ex, fy[c], yR[c]);
+                          ZR[c] = fma (ex, fz[c], ZR[c]);
+                        }
+                    }
+                  AP += wa;
+                  if (qx != 1)
+                    AR = fma (ex, wa, AR);
+                }
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                {
+                  const double gxs = (c == 3) ? k.gp[0] : k.gu[0];
+                  const double xv = XS[c] * gxs;
+                  double v0 = -xv, v1 = xv;
+                  if (c == 3)
+                    {
+                      v0 += AP - AR;
+                      v1 += AP + AR;
+                    }
+                  VP[c][0] += v0;
+                  VP[c][1] += v1;
+                  const double z0 = ZP[c] - ZR[c], z1 = ZP[c] + ZR[c];
+                  DP[c][0] += z0;
+                  DP[c][1] += z1;
+                  if (qy != 1)
+                    {
+                      VR[c][0] = fma (ey, v0, VR[c][0]);
+                      VR[c][1] = fma (ey, v1, VR[c][1]);
+                      DR[c][0] = fma (ey, z0, DR[c][0]);
+                      DR[c][1] = fma (ey, z1, DR[c][1]);
+                    }
+                  YP[c] += yP[c];
+                  YR[c] += yR[c];
+                }
+            }
+        }
+      // ---- stage 4: plane -> shared y tile, 8 conflict-free phases -----------
+#pragma unroll
+      for (int vy = 0; vy < 2; ++vy)
+#pragma unroll
+        for (int vx = 0; vx < 2; ++vx)
+          {
+            double lo[4], hi[4]; // vz = 0 / 1
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              {
+                const double gys = (c == 3) ? k.gp[1] : k.gu[1];
+                const double gzs = (c == 3) ? k.gp[2] : k.gu[2];
+                const double yv = (vx == 0 ? YP[c] - YR[c] : YP[c] + YR[c]) * gys;
+                const double a = (vy == 0) ? VP[c][vx] - VR[c][vx] - yv : VP[c][vx] + VR[c][vx] + yv;
+                const double d = ((vy == 0) ? DP[c][vx] - DR[c][vx] : DP[c][vx] + DR[c][vx]) * gzs;
+                const double sc = (c == 3) ? 0.125 : 1.0;
+                lo[c] = sc * (fma (-ez, a, a) - d);
+                hi[c] = sc * (fma (ez, a, a) + d);
+              }
+            const int n0 = nbase + vx + T::SY * vy;
+            if (valid)
+              {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  ys[c * NN + n0] += lo[c];
+              }
+            __syncthreads ();
+            if (valid)
+              {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  ys[c * NN + n0 + T::SZ] += hi[c];
+              }
+            __syncthreads ();
+          }
+    }
+
+  // ---- flush the y tile ---------------------------------------------------------
+  for (int i = tid; i < NN; i += NT)
+    {
+      const int ix = i % NX, iy = (i / NX) % NY, iz = i / (NX * NY);
+      const int gx = cx0 + ix, gy = cy0 + iy, gz = cz0 + iz;
+      if (gx < nnx && gy < nny && gz <= g.cell_end)
+        {
+          const long long n = gx + (long long) nnx * gy + pstride * (gz - lz_off);
+          const uint8_t m = mask[n];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (!((m >> c) & 1))
+              atomicAdd (&y[4 * n + c], ys[c * NN + i]);
+        }
+    }
+}
+
+} // namespace pf

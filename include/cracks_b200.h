@@ -196,6 +196,8 @@ int pf_host_alloc (void **out, size_t bytes);
 int pf_host_free (void *p);
 /* testing aid: route the 3-D apply through the dimension-generic kernel */
 int pf_debug_force_generic (int on);
+/* testing aid: select the generation of the tiled 3-D apply kernel (1 or 2, default 2) */
+int pf_debug_set_variant (int variant);
 
 #ifdef __cplusplus
 }
