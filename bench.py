@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--cpu-refine", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="debug: apply-kernel variant (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -214,6 +215,8 @@ def main():
     n = mesh.n[0]
     ctx = pf.PhaseFieldContext(mesh, params, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
     lib = ctx.lib
+    if args.variant:
+        lib.pf_debug_set_variant(args.variant)
     nd, nn = ctx.n_dofs, ctx.n_nodes
 
     sol, active = sneddon_state(n, mesh.h[0])
@@ -306,7 +309,7 @@ def main():
                     "note": "pf_apply_jacobian with pinned host buffers in the reference's block layout"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_apply3d<16,4,2>", "kernel_ms": k_ms,
+                         "traffic": traffic, "kernel": "k_apply3d_v2<16,4,1>", "kernel_ms": k_ms,
                          "kernel_share_of_step": kern_ms / ms_total, "algorithmic_bytes": b_alg, "peak_source": peak_src,
                          "note": "FP64-pipe bound: exact 27-point FP64 quadrature, no f64 tensor path (DESIGN.md)"},
         }

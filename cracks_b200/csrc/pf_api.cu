@@ -367,7 +367,7 @@ launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
-int g_apply_variant = 2;
+int g_apply_variant = 3;
 int g_force_generic = 0;
 
 int
@@ -407,7 +407,16 @@ apply_dev (pf_ctx *ctx, double *x, double *y)
               CU (cudaEventCreate (&e1));
               CU (cudaEventRecord (e0, ctx->stream));
             }
-          rc = g_apply_variant == 1 ? launch_apply3d<16, 4, 2> (ctx, x, y) : launch_apply3d_v2<16, 4, 2> (ctx, x, y);
+          switch (g_apply_variant)
+            {
+            case 1: rc = launch_apply3d<16, 4, 2> (ctx, x, y); break;
+            case 2: rc = launch_apply3d_v2<16, 4, 2> (ctx, x, y); break;
+            case 4: rc = launch_apply3d_v2<16, 8, 1> (ctx, x, y); break;
+            case 5: rc = launch_apply3d_v2<32, 2, 1> (ctx, x, y); break;
+            case 6: rc = launch_apply3d_v2<32, 4, 1> (ctx, x, y); break;
+            case 7: rc = launch_apply3d_v2<16, 2, 2> (ctx, x, y); break;
+            default: rc = launch_apply3d_v2<16, 4, 1> (ctx, x, y); break; // variant 3: fastest measured
+            }
           if (rc)
             return rc;
           if (ctx->profiling)
@@ -1385,7 +1394,7 @@ pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count)
 int
 pf_debug_set_variant (int variant)
 {
-  if (variant != 1 && variant != 2)
+  if (variant < 1 || variant > 7)
     return PF_BAD_ARG;
   g_apply_variant = variant;
   return PF_OK;

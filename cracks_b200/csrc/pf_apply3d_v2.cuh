@@ -26,7 +26,8 @@ template <int TX, int TY, int TZ> struct Tile3v2
   static constexpr int NXC = NX * TY * TZ; // (x-node, cell row, layer)
   static constexpr int NT = TX * TY * TZ;
   static constexpr int SY = NX, SZ = NX * NY;
-  static constexpr size_t smem_doubles = (size_t) 27 * NC2 + 7 * NC2 + 21 * NXC + 4 * NN;
+  static constexpr size_t dz_or_y = (7 * NC2 > 4 * NN) ? 7 * NC2 : 4 * NN; // DZ is dead once BZ exists
+  static constexpr size_t smem_doubles = (size_t) 27 * NC2 + 21 * NXC + dz_or_y;
   static constexpr size_t smem_bytes = smem_doubles * sizeof (double);
 };
 
@@ -41,9 +42,9 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
   constexpr int NN = T::NN, NT = T::NT, NX = T::NX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC;
   extern __shared__ __align__ (16) unsigned char smem_raw[];
   double *AZ = reinterpret_cast<double *> (smem_raw); // [3][9][NC2]
-  double *DZ = AZ + 27 * NC2;                         // [7][NC2]
-  double *BZ = DZ + 7 * NC2;                          // [7][3][NXC]
-  double *ys = BZ + 21 * NXC;                         // [4][NN]
+  double *BZ = AZ + 27 * NC2;                         // [7][3][NXC]
+  double *DZ = BZ + 21 * NXC;                         // [7][NC2], stage 1 -> 2 only
+  double *ys = DZ;                                    // [4][NN], aliases DZ
 
   const int tid = threadIdx.x;
   int b = blockIdx.x;
@@ -97,8 +98,6 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
             DZ[f * NC2 + i] = r * ((f == 3) ? k.gp[2] : k.gu[2]);
         }
     }
-  for (int i = tid; i < 4 * NN; i += NT)
-    ys[i] = 0;
   __syncthreads ();
   // ---- stage 2: y-collapse of the z-derivative chain ------------------------
   for (int i = tid; i < NXC; i += NT)
@@ -115,6 +114,9 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
           BZ[(f * 3 + 2) * NXC + i] = fma (S, R, P);
         }
     }
+  __syncthreads ();
+  for (int i = tid; i < 4 * NN; i += NT)
+    ys[i] = 0;
   __syncthreads ();
 
   // ---- stage 3: one thread per cell -----------------------------------------
@@ -269,41 +271,47 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
                 }
             }
         }
-      // ---- stage 4: plane -> shared y tile, 8 conflict-free phases -----------
+      // ---- stage 4: plane -> shared y tile.  Two cells hit the same node only
+      // if they are neighbours: x-neighbours are lanes of one warp (TX == 16 or
+      // 32), so the two vx phases are ordered with __syncwarp; y- and z-
+      // neighbours may sit in other warps, so vy (and vz when TZ > 1) phases
+      // are separated by block barriers.
 #pragma unroll
       for (int vy = 0; vy < 2; ++vy)
+        {
 #pragma unroll
-        for (int vx = 0; vx < 2; ++vx)
-          {
-            double lo[4], hi[4]; // vz = 0 / 1
+          for (int vz = 0; vz < 2; ++vz)
+            {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              {
-                const double gys = (c == 3) ? k.gp[1] : k.gu[1];
-                const double gzs = (c == 3) ? k.gp[2] : k.gu[2];
-                const double yv = (vx == 0 ? YP[c] - YR[c] : YP[c] + YR[c]) * gys;
-                const double a = (vy == 0) ? VP[c][vx] - VR[c][vx] - yv : VP[c][vx] + VR[c][vx] + yv;
-                const double d = ((vy == 0) ? DP[c][vx] - DR[c][vx] : DP[c][vx] + DR[c][vx]) * gzs;
-                const double sc = (c == 3) ? 0.125 : 1.0;
-                lo[c] = sc * (fma (-ez, a, a) - d);
-                hi[c] = sc * (fma (ez, a, a) + d);
-              }
-            const int n0 = nbase + vx + T::SY * vy;
-            if (valid)
-              {
+              for (int vx = 0; vx < 2; ++vx)
+                {
+                  double val[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                  ys[c * NN + n0] += lo[c];
-              }
+                  for (int c = 0; c < 4; ++c)
+                    {
+                      const double gys = (c == 3) ? k.gp[1] : k.gu[1];
+                      const double gzs = (c == 3) ? k.gp[2] : k.gu[2];
+                      const double yv = (vx == 0 ? YP[c] - YR[c] : YP[c] + YR[c]) * gys;
+                      const double a = (vy == 0) ? VP[c][vx] - VR[c][vx] - yv : VP[c][vx] + VR[c][vx] + yv;
+                      const double d = ((vy == 0) ? DP[c][vx] - DR[c][vx] : DP[c][vx] + DR[c][vx]) * gzs;
+                      const double sc = (c == 3) ? 0.125 : 1.0;
+                      val[c] = (vz == 0) ? sc * (fma (-ez, a, a) - d) : sc * (fma (ez, a, a) + d);
+                    }
+                  const int n0 = nbase + vx + T::SY * vy + T::SZ * vz;
+                  if (valid)
+                    {
+#pragma unroll
+                      for (int c = 0; c < 4; ++c)
+                        ys[c * NN + n0] += val[c];
+                    }
+                  __syncwarp ();
+                }
+              if (TZ > 1)
+                __syncthreads ();
+            }
+          if (TZ == 1)
             __syncthreads ();
-            if (valid)
-              {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                  ys[c * NN + n0 + T::SZ] += hi[c];
-              }
-            __syncthreads ();
-          }
+        }
     }
 
   // ---- flush the y tile ---------------------------------------------------------

@@ -81,13 +81,15 @@ def test_apply_jacobian_3d(oracle, pf, n, h):
         ctx.lib.pf_debug_force_generic(0)
     assert _relerr(ctx.to_nodal(y2), y_ref) <= TOL
     # the first-generation tiled kernel stays available for A/B measurements
-    ctx.lib.pf_debug_set_variant(1)
-    try:
-        y3 = np.zeros(prob.n_dofs)
-        ctx.vmult(y3, ctx.to_block(x))
-    finally:
-        ctx.lib.pf_debug_set_variant(2)
-    assert _relerr(ctx.to_nodal(y3), y_ref) <= TOL
+    # variant 1 = first-generation kernel, 3..7 = other tile shapes of v2
+    for variant in (1, 2, 4, 5, 6, 7):
+        ctx.lib.pf_debug_set_variant(variant)
+        try:
+            y3 = np.zeros(prob.n_dofs)
+            ctx.vmult(y3, ctx.to_block(x))
+        finally:
+            ctx.lib.pf_debug_set_variant(3)
+        assert _relerr(ctx.to_nodal(y3), y_ref) <= TOL, variant
     ctx.close()
 
 
