@@ -1,0 +1,380 @@
+#include "fracture_problem.h"
+
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <sys/stat.h>
+
+namespace cracks {
+
+double
+BlockVector::l2_norm () const
+{
+  double s = 0;
+  for (double v : data)
+    s += v * v;
+  return std::sqrt (s);
+}
+
+using P = ParameterHandler::Pattern;
+
+// the 32 entries of cracks.cc:1307-1405, same names, defaults and patterns
+void
+FracturePhaseFieldProblem::declare_parameters (ParameterHandler &prm)
+{
+  prm.enter_subsection ("Global parameters");
+  prm.declare_entry ("Dimension", "2", P::Integer, "", 0);
+  prm.declare_entry ("FE degree", "1", P::Integer, "", 1);
+  prm.declare_entry ("Global pre-refinement steps", "1", P::Integer, "", 0);
+  prm.declare_entry ("Local pre-refinement steps", "0", P::Integer, "", 0);
+  prm.declare_entry ("Adaptive refinement cycles", "0", P::Integer, "", 0);
+  prm.declare_entry ("Max No of timesteps", "1", P::Integer, "", 0);
+  prm.declare_entry ("Timestep size", "1.0", P::Double, "", 0);
+  prm.declare_entry ("Timestep size to switch to", "1.0", P::Double, "", 0);
+  prm.declare_entry ("Switch timestep after steps", "0", P::Integer, "", 0);
+  prm.declare_entry ("outer solver", "active set", P::Selection, "active set|simple monolithic");
+  prm.declare_entry ("test case", "sneddon", P::Selection,
+                     "sneddon|miehe tension|miehe shear|multiple homo|multiple het|three point bending");
+  prm.declare_entry ("ref strategy", "phase field", P::Selection,
+                     "phase field|fixed preref sneddon|fixed preref miehe tension|fixed preref miehe shear|"
+                     "fixed preref multiple homo|fixed preref multiple het|global|mix|phase field three point top");
+  prm.declare_entry ("value phase field for refinement", "0.0", P::Double, "", 0);
+  prm.declare_entry ("Output directory", "output", P::Anything);
+  prm.declare_entry ("Output filename", "solution_", P::Anything);
+  prm.leave_subsection ();
+
+  prm.enter_subsection ("Problem dependent parameters");
+  prm.declare_entry ("K reg", "1.0 * h", P::Anything);
+  prm.declare_entry ("Eps reg", "1.0 * h", P::Anything);
+  prm.declare_entry ("Gamma penalization", "0.0", P::Double, "", 0);
+  prm.declare_entry ("Pressure", "0.0", P::Anything);
+  prm.declare_entry ("Fracture toughness G_c", "0.0", P::Double, "", 0);
+  prm.declare_entry ("Poisson ratio nu", "0.0", P::Double, "", 0);
+  prm.declare_entry ("E modulus", "0.0", P::Double, "", 0);
+  prm.declare_entry ("Lame mu", "0.0", P::Double, "", 0);
+  prm.declare_entry ("Lame lambda", "0.0", P::Double, "", 0);
+  prm.leave_subsection ();
+
+  prm.enter_subsection ("Solver parameters");
+  prm.declare_entry ("Use Direct Inner Solver", "false", P::Bool);
+  prm.declare_entry ("Newton lower bound", "1.0e-10", P::Double, "", 0);
+  prm.declare_entry ("Newton maximum steps", "10", P::Integer, "", 0);
+  prm.declare_entry ("Upper Newton rho", "0.999", P::Double, "", 0);
+  prm.declare_entry ("Line search maximum steps", "5", P::Integer, "", 0);
+  prm.declare_entry ("Line search damping", "0.5", P::Double, "", 0);
+  prm.declare_entry ("Decompose stress in rhs", "0.0", P::Double, "", 0);
+  prm.declare_entry ("Decompose stress in matrix", "0.0", P::Double, "", 0);
+  prm.leave_subsection ();
+}
+
+FracturePhaseFieldProblem::FracturePhaseFieldProblem (ParameterHandler &prm, int dim, std::ostream &out)
+  : prm_ (prm), dim_ (dim), pcout_ (out)
+{
+  if (dim != 2 && dim != 3)
+    throw NotImplemented ("Dimension must be 2 or 3");
+}
+
+FracturePhaseFieldProblem::~FracturePhaseFieldProblem ()
+{
+  if (ctx_)
+    pf_destroy (ctx_);
+}
+
+// cracks.cc:1411-1575
+void
+FracturePhaseFieldProblem::set_runtime_parameters ()
+{
+  prm_.enter_subsection ("Global parameters");
+  if (prm_.get_integer ("FE degree") != 1)
+    throw NotImplemented ("only FE degree = 1 is available on the GPU path");
+  n_global_pre_refine = (unsigned) prm_.get_integer ("Global pre-refinement steps");
+  n_local_pre_refine = (unsigned) prm_.get_integer ("Local pre-refinement steps");
+  n_refinement_cycles = (unsigned) prm_.get_integer ("Adaptive refinement cycles");
+  max_no_timesteps = (unsigned) prm_.get_integer ("Max No of timesteps");
+  timestep = prm_.get_double ("Timestep size");
+  timestep_size_2 = prm_.get_double ("Timestep size to switch to");
+  switch_timestep = (unsigned) prm_.get_integer ("Switch timestep after steps");
+  outer_solver = prm_.get ("outer solver");
+  test_case = prm_.get ("test case");
+  output_folder = prm_.get ("Output directory");
+  prm_.leave_subsection ();
+
+  if (outer_solver != "active set")
+    throw NotImplemented ("outer solver = simple monolithic is not part of the GPU hot path");
+  if (test_case != "sneddon")
+    throw NotImplemented ("test case <" + test_case + "> needs meshes / boundary data outside this round's scope");
+  if (n_local_pre_refine != 0 || n_refinement_cycles != 0)
+    throw NotImplemented ("local / adaptive refinement (hanging nodes) is not available: use global refinement");
+
+  prm_.enter_subsection ("Problem dependent parameters");
+  func_pressure.initialize ("time", prm_.get ("Pressure"));
+  G_c = prm_.get_double ("Fracture toughness G_c");
+  poisson_ratio_nu = prm_.get_double ("Poisson ratio nu");
+  E_modulus = prm_.get_double ("E modulus");
+  lame_coefficient_mu = E_modulus / (2.0 * (1 + poisson_ratio_nu));
+  lame_coefficient_lambda = (2 * poisson_ratio_nu * lame_coefficient_mu) / (1.0 - 2 * poisson_ratio_nu);
+  prm_.leave_subsection ();
+
+  timestep_number = 0;
+  time = 0;
+
+  // setup_mesh(): "rect -10 -10 [-10] 10 10 [10]", 10 cells per direction,
+  // then refine_global (cracks.cc:1207-1253, 1534)
+  mesh_.dim = dim_;
+  const int n = 10 << n_global_pre_refine;
+  for (int d = 0; d < 3; ++d)
+    {
+      mesh_.n[d] = d < dim_ ? n : 1;
+      mesh_.h[d] = d < dim_ ? 20.0 / n : 1.0;
+      mesh_.origin[d] = d < dim_ ? -10.0 : 0.0;
+    }
+  long long cells = 1;
+  for (int d = 0; d < dim_; ++d)
+    cells *= n;
+  pcout_ << "Cells:\t" << cells << std::endl;
+
+  prm_.enter_subsection ("Solver parameters");
+  direct_solver = prm_.get_bool ("Use Direct Inner Solver");
+  lower_bound_newton_residual = prm_.get_double ("Newton lower bound");
+  max_no_newton_steps = (unsigned) prm_.get_integer ("Newton maximum steps");
+  max_no_line_search_steps = (unsigned) prm_.get_integer ("Line search maximum steps");
+  line_search_damping = prm_.get_double ("Line search damping");
+  decompose_stress_rhs = prm_.get_double ("Decompose stress in rhs");
+  decompose_stress_matrix = prm_.get_double ("Decompose stress in matrix");
+  prm_.leave_subsection ();
+  if (decompose_stress_rhs > 0 || decompose_stress_matrix > 0)
+    throw NotImplemented ("the Miehe stress split (2-D only in the reference) is not available yet");
+  if (direct_solver)
+    pcout_ << "note: 'Use Direct Inner Solver' is ignored, the GPU path always solves matrix-free" << std::endl;
+  use_old_timestep_pf = false;
+}
+
+// cracks.cc:3820-3892 (uniform mesh: every cell has the same diameter)
+void
+FracturePhaseFieldProblem::determine_mesh_dependent_parameters ()
+{
+  double d2 = 0;
+  for (int d = 0; d < dim_; ++d)
+    d2 += mesh_.h[d] * mesh_.h[d];
+  min_cell_diameter = std::sqrt (d2);
+  FunctionParser func;
+  prm_.enter_subsection ("Problem dependent parameters");
+  func.initialize ("h", prm_.get ("K reg"));
+  constant_k = func.value (min_cell_diameter);
+  func.initialize ("h", prm_.get ("Eps reg"));
+  alpha_eps = func.value (min_cell_diameter);
+  prm_.leave_subsection ();
+}
+
+// cracks.cc:1579-1680 without the sparse matrix
+void
+FracturePhaseFieldProblem::setup_system ()
+{
+  determine_mesh_dependent_parameters ();
+  params_.lambda = lame_coefficient_lambda;
+  params_.mu = lame_coefficient_mu;
+  params_.G_c = G_c;
+  params_.kappa = constant_k;
+  params_.eps = alpha_eps;
+  params_.alpha_biot = 0.0; // cracks.cc:1497
+  const int rc = pf_create (&mesh_, &params_, device, 0, 1, nullptr, &ctx_);
+  pf_check (ctx_, rc);
+  pf_check (ctx_, pf_set_dirichlet_all_faces (ctx_)); // set_newton_bc, cracks.cc:2575-2583 / 2686-2694
+  long long nodes = 1;
+  for (int d = 0; d < dim_; ++d)
+    nodes *= mesh_.n[d] + 1;
+  pcout_ << std::endl;
+  pcout_ << "DoFs: " << nodes * dim_ << " solid + " << nodes << " phase"
+         << " = " << nodes * (dim_ + 1) << std::endl;
+}
+
+// cracks.cc:2780-2994
+double
+FracturePhaseFieldProblem::newton_active_set ()
+{
+  pcout_ << "It.\t#A.Set\t#CycDoF\tResidual\tReduction\tLSrch\t#LinIts" << std::endl;
+  double newton_residual = 0;
+  pf_check (ctx_, pf_residual (ctx_, nullptr, nullptr, &newton_residual));
+  double old_newton_residual = newton_residual;
+  unsigned newton_step = 0;
+  char buf[256];
+  std::snprintf (buf, sizeof buf, "0\t\t\t%e", newton_residual);
+  pcout_ << buf << std::endl;
+  pf_check (ctx_, pf_active_set_reset (ctx_)); // active_set.clear(), fresh cycle_counter
+  unsigned sum_lin_it = 0;
+  double new_newton_residual = 0.0;
+  while (true)
+    {
+      int64_t n_active = 0, n_cycling = 0;
+      int changed = 0;
+      pf_check (ctx_, pf_active_set_update (ctx_, 1e+1 * E_modulus, nullptr, &n_active, &n_cycling, &changed));
+      pf_check (ctx_, pf_setup_jacobian (ctx_));                       // assemble_system()
+      pf_check (ctx_, pf_residual (ctx_, nullptr, nullptr, nullptr));  // its rhs + set_zero
+      int no_linear_iterations = 0;
+      pf_check (ctx_, pf_solve (ctx_, gmres_tolerance, gmres_max_iterations, nullptr, &no_linear_iterations));
+      sum_lin_it += (unsigned) no_linear_iterations;
+      pf_check (ctx_, pf_save_solution (ctx_));
+      unsigned line_search_step = 0;
+      for (; line_search_step < max_no_line_search_steps; ++line_search_step)
+        {
+          pf_check (ctx_, pf_update_solution (ctx_, 1.0));
+          pf_check (ctx_, pf_residual (ctx_, nullptr, nullptr, &new_newton_residual));
+          if (new_newton_residual < newton_residual)
+            break;
+          pf_check (ctx_, pf_restore_saved_solution (ctx_));
+          pf_check (ctx_, pf_scale_update (ctx_, line_search_damping));
+        }
+      std::snprintf (buf, sizeof buf, "%u\t%lld\t%lld\t%e\t%e\t%u\t%d", newton_step + 1, (long long) n_active,
+                     (long long) n_cycling, new_newton_residual, new_newton_residual / newton_residual,
+                     line_search_step, no_linear_iterations);
+      pcout_ << buf << std::endl;
+      old_newton_residual = newton_residual;
+      newton_residual = new_newton_residual;
+      ++newton_step;
+      if (newton_residual < lower_bound_newton_residual && changed == 0)
+        {
+          pcout_ << "\tNewton iterations: " << newton_step << " total linear iterations: " << sum_lin_it
+                 << std::endl;
+          break;
+        }
+      if (newton_step >= max_no_newton_steps)
+        {
+          pcout_ << "Newton iteration did not converge in " << newton_step << " steps." << std::endl;
+          total_newton_its_ += newton_step;
+          total_linear_its_ += sum_lin_it;
+          throw NoConvergence ("Newton iteration did not converge");
+        }
+    }
+  total_newton_its_ += newton_step;
+  total_linear_its_ += sum_lin_it;
+  return new_newton_residual / old_newton_residual;
+}
+
+// TableHandler::write_text(simple_table_with_separate_column_description), cracks.cc:4469-4475
+void
+FracturePhaseFieldProblem::write_statistics () const
+{
+  ::mkdir (output_folder.c_str (), 0755);
+  std::ofstream f ((output_folder + "/statistics").c_str ());
+  f << "# 1: Timestep No\n# 2: Time\n# 3: DoFs\n# 4: minimum cell diameter\n# 5: Bulk Energy\n# 6: Crack Energy\n";
+  char buf[256];
+  for (const auto &r : statistics_)
+    {
+      std::snprintf (buf, sizeof buf, "%u %.4f %lld %.8e %.8e %.8e ", r.timestep_no, r.time, r.dofs, r.h_min,
+                     r.bulk_energy, r.crack_energy);
+      f << buf << "\n";
+    }
+}
+
+// cracks.cc:4166-4581, Sneddon branch
+void
+FracturePhaseFieldProblem::run ()
+{
+  pcout_ << "Running on 1 GPU" << std::endl;
+  set_runtime_parameters ();
+  setup_system ();
+  if (!(alpha_eps >= min_cell_diameter))
+    throw ParameterError ("You need to pick eps >= h");
+  if (!(constant_k < 1.0))
+    throw ParameterError ("You need to pick K < 1");
+
+  pcout_ << "\n==============================" << "=====================================" << std::endl;
+  pcout_ << "Parameters\n" << "==========\n" << "h (min):           " << min_cell_diameter << "\n"
+         << "k:                 " << constant_k << "\n" << "eps:               " << alpha_eps << "\n"
+         << "G_c:               " << G_c << "\n" << "gamma penal:       " << 0 << "\n"
+         << "Poisson nu:        " << poisson_ratio_nu << "\n" << "E modulus:         " << E_modulus << "\n"
+         << "Lame mu:           " << lame_coefficient_mu << "\n" << "Lame lambda:       " << lame_coefficient_lambda
+         << "\n" << std::endl;
+
+  // initial condition, project_back_phase_field, old = old_old = solution (4233-4277)
+  pf_check (ctx_, pf_interpolate_sneddon (ctx_, min_cell_diameter));
+  pf_check (ctx_, pf_project_phase_field (ctx_));
+  old_timestep = timestep;
+  old_old_timestep = timestep;
+  long long nodes = 1, cells = 1;
+  for (int d = 0; d < dim_; ++d)
+    {
+      nodes *= mesh_.n[d] + 1;
+      cells *= mesh_.n[d];
+    }
+  double finishing_timestep_loop = 0;
+
+  do
+    {
+      if (timestep_number > switch_timestep && switch_timestep > 0)
+        timestep = timestep_size_2;
+      const double tmp_timestep = timestep;
+      old_old_timestep = old_timestep;
+      old_timestep = timestep;
+      pf_check (ctx_, pf_advance_timestep (ctx_)); // old_old = old; old = solution
+
+      pcout_ << std::endl;
+      pcout_ << "\n==============================" << "=========================================" << std::endl;
+      pcout_ << "Timestep " << timestep_number << ": " << time << " (" << timestep << ")"
+             << "   " << "Cells: " << cells << "   " << "DoFs: " << nodes * (dim_ + 1);
+      pcout_ << "\n--------------------------------" << "---------------------------------------" << std::endl;
+      pcout_ << std::endl;
+
+      time += timestep;
+      do
+        {
+          // catch NoConvergence, retry with a tenth of the step and old_timestep_pf (4320-4358)
+          use_old_timestep_pf = false;
+          pf_check (ctx_, pf_set_time_parameters (ctx_, old_timestep, old_old_timestep, 0, func_pressure.value (time)));
+          try
+            {
+              newton_active_set ();
+              break;
+            }
+          catch (NoConvergence &)
+            {
+              pcout_ << "Solver did not converge! Adjusting time step to " << timestep / 10 << std::endl;
+            }
+          pcout_ << "Taking old_timestep_pf" << std::endl;
+          use_old_timestep_pf = true;
+          pf_check (ctx_, pf_restore_old_solution (ctx_));
+          time -= timestep;
+          timestep = timestep / 10.0;
+          time += timestep;
+          if (timestep < 1e-12)
+            throw NoConvergence ("time step underflow");
+          // NB: the reference resets use_old_timestep_pf to false at the top of the retry
+          // loop (cracks.cc:4325), so the flag never reaches assemble_system; kept as is.
+        }
+      while (true);
+
+      pf_check (ctx_, pf_project_phase_field (ctx_));
+      timestep = tmp_timestep;
+
+      double bulk = 0, crack = 0;
+      pf_check (ctx_, pf_energy (ctx_, &bulk, &crack));
+      pcout_ << std::endl;
+      pcout_ << "No " << timestep_number << " time " << time << " bulk energy: " << bulk
+             << " crack energy: " << crack << std::endl;
+      statistics_.push_back ({timestep_number, time, nodes * (dim_ + 1), min_cell_diameter, bulk, crack});
+      write_statistics ();
+
+      pf_check (ctx_, pf_timestep_difference (ctx_, &finishing_timestep_loop));
+      pcout_ << "Timestep difference linfty: " << finishing_timestep_loop << std::endl;
+      ++timestep_number;
+
+      if (finishing_timestep_loop < 1.0e-5)
+        {
+          pf_check (ctx_, pf_tcv (ctx_, &tcv_));
+          const double p = func_pressure.value (time), nu = poisson_ratio_nu, E = 1.0, l_0 = 1.0;
+          const double ref = dim_ == 2 ? 2.0 * p * l_0 * l_0 * (1.0 - nu * nu) * M_PI / E
+                                       : 16.0 * p * l_0 * l_0 * l_0 * (1.0 - nu * nu) / E / 3.0;
+          pcout_ << "TCV: value= " << tcv_ << " exact= " << ref << " error= " << std::abs (tcv_ - ref) << std::endl;
+          break; // n_refinement_cycles == 0
+        }
+    }
+  while (timestep_number <= max_no_timesteps);
+
+  pcout_ << std::endl;
+  pcout_ << "Finishing time step loop: " << finishing_timestep_loop << std::endl;
+}
+
+} // namespace cracks

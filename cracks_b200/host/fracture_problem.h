@@ -1,0 +1,86 @@
+// fracture_problem.h -- host driver mirroring FracturePhaseFieldProblem<dim>
+// (cracks.cc:1024-1170) for the part of the program that sits on the hot path:
+// parameter handling, the time-step loop of run() (4166-4581) and the
+// primal-dual active-set Newton iteration (2780-2994).  All vectors live on
+// the GPU behind the C ABI; this class only sequences calls and keeps the
+// reference's screen / statistics output format.
+//
+// Supported here: `test case = sneddon` on the uniform (globally refined)
+// box, dim 2 or 3, `outer solver = active set`.  Everything else the .prm
+// surface can express is parsed and rejected with ExcNotImplemented-style
+// errors (SURVEY.md section 8f lists it as "next").
+#pragma once
+#include <iosfwd>
+#include <string>
+#include <vector>
+
+#include "function_parser.h"
+#include "matrix_free_jacobian.h"
+#include "parameter_handler.h"
+
+namespace cracks {
+
+struct NotImplemented : std::runtime_error
+{
+  using std::runtime_error::runtime_error;
+};
+
+struct StatisticsRow
+{
+  unsigned timestep_no;
+  double time;
+  long long dofs;
+  double h_min, bulk_energy, crack_energy;
+};
+
+class FracturePhaseFieldProblem
+{
+public:
+  FracturePhaseFieldProblem (ParameterHandler &prm, int dim, std::ostream &out);
+  ~FracturePhaseFieldProblem ();
+  static void declare_parameters (ParameterHandler &prm);
+  void run ();
+
+  const std::vector<StatisticsRow> &statistics () const { return statistics_; }
+  double tcv () const { return tcv_; }
+  unsigned total_newton_iterations () const { return total_newton_its_; }
+  unsigned total_linear_iterations () const { return total_linear_its_; }
+  // knobs that are not part of the reference's .prm surface
+  int device = 0;
+  int gmres_max_iterations = 200; // SolverControl(200, ...) at cracks.cc:2762
+  double gmres_tolerance = 1e-8;
+
+private:
+  void set_runtime_parameters ();
+  void setup_system ();
+  void determine_mesh_dependent_parameters ();
+  double newton_active_set ();
+  void write_statistics () const;
+
+  ParameterHandler &prm_;
+  int dim_;
+  std::ostream &pcout_;
+  pf_ctx *ctx_ = nullptr;
+  pf_mesh mesh_{};
+  pf_params params_{};
+
+  // run-time parameters, names as in the reference (cracks.cc:1111-1166)
+  unsigned n_global_pre_refine = 0, n_local_pre_refine = 0, n_refinement_cycles = 0;
+  unsigned max_no_timesteps = 0, switch_timestep = 0;
+  double timestep = 1, timestep_size_2 = 1, time = 0, old_timestep = 1, old_old_timestep = 1;
+  unsigned timestep_number = 0;
+  std::string outer_solver, test_case, output_folder;
+  double G_c = 0, poisson_ratio_nu = 0, E_modulus = 0, lame_coefficient_mu = 0, lame_coefficient_lambda = 0;
+  double constant_k = 0, alpha_eps = 0, min_cell_diameter = 0;
+  bool direct_solver = false, use_old_timestep_pf = false;
+  double lower_bound_newton_residual = 1e-10, line_search_damping = 0.5;
+  unsigned max_no_newton_steps = 10, max_no_line_search_steps = 5;
+  double decompose_stress_rhs = 0, decompose_stress_matrix = 0;
+  FunctionParser func_pressure;
+
+  std::vector<StatisticsRow> statistics_;
+  double tcv_ = 0;
+  unsigned total_newton_its_ = 0, total_linear_its_ = 0;
+};
+
+} // namespace cracks
