@@ -68,6 +68,8 @@ _SIGS = {
     "pf_destroy": [C.c_void_p],
     "pf_nccl_unique_id": [C.c_void_p],
     "pf_get_layout": [C.c_void_p, C.POINTER(Layout)],
+    "pf_slab_layout": [C.POINTER(Mesh), C.c_int, C.c_int, C.POINTER(Layout), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                       C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "pf_synchronize": [C.c_void_p],
     "pf_set_state": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double],
     "pf_get_solution": [C.c_void_p, C.c_void_p],
@@ -139,6 +141,19 @@ def exported_symbols_in_header() -> list:
     hdr = open(os.path.join(_HERE, "..", "include", "cracks_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(pf_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def slab_layout(mesh: Mesh, rank: int, nranks: int) -> dict:
+    """The library's z-slab decomposition for (rank, nranks); pure host code, no GPU needed."""
+    lay = Layout()
+    cb, ce, ocb, oce = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rc = load_library().pf_slab_layout(C.byref(mesh), rank, nranks, C.byref(lay), C.byref(cb), C.byref(ce),
+                                       C.byref(ocb), C.byref(oce))
+    if rc != PF_OK:
+        raise PFError(rc, "pf_slab_layout: bad arguments")
+    return dict(plane_begin=lay.plane_begin, plane_end=lay.plane_end, owned_begin=lay.owned_begin,
+                owned_end=lay.owned_end, cell_begin=cb.value, cell_end=ce.value, own_cell_begin=ocb.value,
+                own_cell_end=oce.value, nodes_per_plane=lay.n_nodes_plane, n_nodes_global=lay.n_nodes_global)
 
 
 def sneddon_mesh(dim: int, refine: int) -> Mesh:

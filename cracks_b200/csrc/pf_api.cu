@@ -475,6 +475,47 @@ residual_dev (pf_ctx *ctx, double *l2)
 // ===========================================================================
 extern "C" {
 
+// Pure host function (no CUDA call): the z-slab decomposition pf_create uses.
+// Cell layers of the slowest coordinate are cut into nranks contiguous ranges
+// (the uniform-mesh image of p4est's space-filling-curve partition); a node
+// plane belongs to the lowest rank whose cells touch it (deal.II convention);
+// every rank also evaluates the first cell layer of the rank above, so owned
+// planes receive complete sums without a reverse exchange.
+int
+pf_slab_layout (const pf_mesh *mesh, int rank, int nranks, pf_local_layout *out, int *cell_begin, int *cell_end,
+                int *own_cell_begin, int *own_cell_end)
+{
+  if (!mesh || !out || (mesh->dim != 2 && mesh->dim != 3) || nranks < 1 || rank < 0 || rank >= nranks
+      || nranks > mesh->n[mesh->dim - 1])
+    return PF_BAD_ARG;
+  const int dim = mesh->dim;
+  const int ncl = mesh->n[dim - 1];
+  const int cb = (int) ((long long) ncl * rank / nranks), ce = (int) ((long long) ncl * (rank + 1) / nranks);
+  out->n_nodes_global = 1;
+  out->n_nodes_plane = 1;
+  for (int d = 0; d < dim; ++d)
+    {
+      out->n_nodes_global *= mesh->n[d] + 1;
+      if (d < dim - 1)
+        out->n_nodes_plane *= mesh->n[d] + 1;
+    }
+  out->owned_begin = rank == 0 ? 0 : cb + 1;
+  out->owned_end = ce + 1;
+  const int cend = rank == nranks - 1 ? ce : ce + 1;
+  out->plane_begin = cb;
+  out->plane_end = cend + 1;
+  out->ncomp = dim + 1;
+  if (cell_begin)
+    *cell_begin = cb;
+  if (cell_end)
+    *cell_end = cend;
+  if (own_cell_begin)
+    *own_cell_begin = cb;
+  if (own_cell_end)
+    *own_cell_end = ce;
+  return PF_OK;
+}
+
 int
 pf_nccl_unique_id (void *id128)
 {
@@ -522,16 +563,14 @@ pf_create (const pf_mesh *mesh, const pf_params *params, int device, int rank, i
       if (d < dim - 1)
         g.nodes_per_plane *= g.nn[d];
     }
-  const int ncl = g.n[dim - 1];
-  const int cb = (int) ((long long) ncl * rank / nranks), ce = (int) ((long long) ncl * (rank + 1) / nranks);
-  ctx->own_cell_begin = cb;
-  ctx->own_cell_end = ce;
-  g.owned_begin = rank == 0 ? 0 : cb + 1;
-  g.owned_end = ce + 1;
-  g.cell_begin = cb;
-  g.cell_end = rank == nranks - 1 ? ce : ce + 1;
-  g.plane_begin = cb;
-  g.plane_end = g.cell_end + 1;
+  {
+    pf_local_layout lay;
+    pf_slab_layout (mesh, rank, nranks, &lay, &g.cell_begin, &g.cell_end, &ctx->own_cell_begin, &ctx->own_cell_end);
+    g.owned_begin = lay.owned_begin;
+    g.owned_end = lay.owned_end;
+    g.plane_begin = lay.plane_begin;
+    g.plane_end = lay.plane_end;
+  }
   g.n_local_nodes = g.nodes_per_plane * (g.plane_end - g.plane_begin);
   long long cells_per_layer = 1;
   for (int d = 0; d < dim - 1; ++d)

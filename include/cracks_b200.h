@@ -90,6 +90,12 @@ int pf_destroy (pf_ctx *ctx);
 const char *pf_last_error (const pf_ctx *ctx);
 int pf_nccl_unique_id (void *id128);
 int pf_get_layout (const pf_ctx *ctx, pf_local_layout *out);
+/* The slab decomposition itself, without touching a GPU (pure host): which
+ * node planes / cell layers `rank` of `nranks` holds, owns and evaluates.
+ * Stands in for the p4est partition of the uniform forest (cracks.cc:1083,
+ * 1180); cell_* pointers may be NULL. */
+int pf_slab_layout (const pf_mesh *mesh, int rank, int nranks, pf_local_layout *out, int *cell_begin,
+                    int *cell_end, int *own_cell_begin, int *own_cell_end);
 int64_t pf_n_dofs (const pf_ctx *ctx);
 /* the CUDA stream all work of this context is enqueued on (a cudaStream_t) */
 void *pf_stream (const pf_ctx *ctx);
