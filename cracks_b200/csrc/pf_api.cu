@@ -18,6 +18,7 @@
 #include "../../include/cracks_b200.h"
 #include "pf_apply3d.cuh"
 #include "pf_apply3d_v2.cuh"
+#include "pf_apply3d_v3.cuh"
 #include "pf_common.cuh"
 #include "pf_generic.cuh"
 #include "pf_vector.cuh"
@@ -105,6 +106,9 @@ struct pf_ctx
   double *diag = nullptr, *mass = nullptr, *r_total = nullptr, *r_pde = nullptr, *dx = nullptr;
   double *stage = nullptr, *xa = nullptr, *ya = nullptr, *saved = nullptr;
   uint8_t *mask = nullptr, *stage8 = nullptr;
+  double2 *aux = nullptr; // {phi~, mask} records for the TMA path
+  unsigned long long *tile_counter = nullptr, tile_epoch = 0;
+  int sm_count = 148;
   int *cycle = nullptr;
   void *fetab = nullptr;
   double *red = nullptr, *partial = nullptr; // reduction scratch
@@ -346,7 +350,7 @@ launch_apply3d (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
-template <int TX, int TY, int TZ>
+template <int TX, int TY, int TZ, int MINB = 2>
 int
 launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
 {
@@ -357,17 +361,84 @@ launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
   static bool attr_set = false;
   if (!attr_set)
     {
-      CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
       attr_set = true;
     }
-  k_apply3d_v2<TX, TY, TZ><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes, ctx->stream>>> (
+  k_apply3d_v2<TX, TY, TZ, MINB><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes, ctx->stream>>> (
     g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
   KCHECK ();
   return PF_OK;
 }
 
 int g_apply_variant = 3;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
+typedef CUresult (*pfn_encode_tiled) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+
+int
+make_nodal_tmap (pf_ctx *ctx, const void *base, int ncomp, int bx, int by, int bz, CUtensorMap *out)
+{
+  static pfn_encode_tiled encode = nullptr;
+  if (!encode)
+    {
+      void *fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      CU (cudaGetDriverEntryPoint ("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess)
+        return fail (ctx, PF_CUDA_ERROR, "cuTensorMapEncodeTiled is not available");
+      encode = reinterpret_cast<pfn_encode_tiled> (fn);
+    }
+  const Grid &g = ctx->g;
+  const cuuint64_t nplanes = (cuuint64_t) (g.plane_end - g.plane_begin);
+  const cuuint64_t dims[4] = {(cuuint64_t) ncomp, (cuuint64_t) g.nn[0], (cuuint64_t) g.nn[1], nplanes};
+  const cuuint64_t node_bytes = (cuuint64_t) ncomp * sizeof (double);
+  const cuuint64_t strides[3] = {node_bytes, node_bytes * g.nn[0], node_bytes * g.nn[0] * g.nn[1]};
+  const cuuint32_t box[4] = {(cuuint32_t) ncomp, (cuuint32_t) bx, (cuuint32_t) by, (cuuint32_t) bz};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode (out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *> (base), dims, strides, box,
+                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail (ctx, PF_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", (int) r);
+  return PF_OK;
+}
+
+template <int TX, int TY, int TZ, int MINB>
+int
+launch_apply3d_v3 (pf_ctx *ctx, const double *x, double *y)
+{
+  using T = Tile3v2<TX, TY, TZ>;
+  using L = Tile3v3<TX, TY, TZ>;
+  const Grid &g = ctx->g;
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+  const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  const int n_tiles = tiles_x * tiles_y * tiles_z;
+  static bool attr_set = false;
+  if (!attr_set)
+    {
+      CU (cudaFuncSetAttribute (k_apply3d_v3<TX, TY, TZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) L::smem_bytes));
+      attr_set = true;
+    }
+  CUtensorMap tm_x, tm_s, tm_a;
+  int rc;
+  if ((rc = make_nodal_tmap (ctx, x, 4, T::NX, T::NY, T::NZ, &tm_x)))
+    return rc;
+  if ((rc = make_nodal_tmap (ctx, ctx->sol, 4, T::NX, T::NY, T::NZ, &tm_s)))
+    return rc;
+  if ((rc = make_nodal_tmap (ctx, ctx->aux, 2, T::NX, T::NY, T::NZ, &tm_a)))
+    return rc;
+  const int grid = std::min (n_tiles, ctx->sm_count * MINB);
+  k_apply3d_v3<TX, TY, TZ, MINB><<<grid, T::NT, L::smem_bytes, ctx->stream>>> (
+    g, ctx->p, ctx->k3, tiles_x, tiles_y, n_tiles, ctx->tile_counter, ctx->tile_epoch, tm_x, tm_s, tm_a, y);
+  KCHECK ();
+  ctx->tile_epoch += (unsigned long long) n_tiles + (unsigned long long) grid;
+  return PF_OK;
+}
 int g_force_generic = 0;
 
 int
@@ -415,6 +486,14 @@ apply_dev (pf_ctx *ctx, double *x, double *y)
             case 5: rc = launch_apply3d_v2<32, 2, 1> (ctx, x, y); break;
             case 6: rc = launch_apply3d_v2<32, 4, 1> (ctx, x, y); break;
             case 7: rc = launch_apply3d_v2<16, 2, 2> (ctx, x, y); break;
+            case 8: rc = launch_apply3d_v2<16, 4, 1, 5> (ctx, x, y); break;
+            case 9: rc = launch_apply3d_v2<16, 2, 1, 8> (ctx, x, y); break;
+            case 10: rc = launch_apply3d_v2<32, 1, 1, 8> (ctx, x, y); break;
+            case 11: rc = launch_apply3d_v2<16, 4, 1, 6> (ctx, x, y); break;
+            case 12: rc = launch_apply3d_v3<16, 4, 1, 4> (ctx, x, y); break;
+            case 13: rc = launch_apply3d_v3<16, 4, 2, 2> (ctx, x, y); break;
+            case 14: rc = launch_apply3d_v3<16, 8, 1, 2> (ctx, x, y); break;
+            case 15: rc = launch_apply3d_v3<32, 2, 1, 4> (ctx, x, y); break;
             default: rc = launch_apply3d_v2<16, 4, 1> (ctx, x, y); break; // variant 3: fastest measured
             }
           if (rc)
@@ -605,6 +684,10 @@ pf_create (const pf_mesh *mesh, const pf_params *params, int device, int rank, i
   CU (cudaMalloc (&ctx->pt, nn * sizeof (double)));
   CU (cudaMalloc (&ctx->mass, nn * sizeof (double)));
   CU (cudaMalloc (&ctx->mask, nn));
+  CU (cudaMalloc (&ctx->aux, nn * sizeof (double2)));
+  CU (cudaMalloc (&ctx->tile_counter, sizeof (unsigned long long)));
+  CU (cudaMemsetAsync (ctx->tile_counter, 0, sizeof (unsigned long long), ctx->stream));
+  CU (cudaDeviceGetAttribute (&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   CU (cudaMalloc (&ctx->stage8, nd));
   CU (cudaMalloc (&ctx->cycle, nn * sizeof (int)));
   CU (cudaMemsetAsync (ctx->pt, 0, nn * sizeof (double), ctx->stream));
@@ -659,7 +742,7 @@ pf_destroy (pf_ctx *ctx)
     g_nccl.CommDestroy (ctx->comm);
   void *ptrs[] = {ctx->sol,   ctx->old,  ctx->oldold, ctx->pt,     ctx->diag,  ctx->mass, ctx->r_total,
                   ctx->r_pde, ctx->dx,   ctx->stage,  ctx->xa,     ctx->ya,    ctx->zvec, ctx->mask,
-                  ctx->saved, ctx->stage8, ctx->cycle, ctx->fetab, ctx->red,   ctx->hdev,  ctx->partial, ctx->counts,
+                  ctx->saved, ctx->aux, ctx->tile_counter, ctx->stage8, ctx->cycle, ctx->fetab, ctx->red,   ctx->hdev,  ctx->partial, ctx->counts,
                   ctx->V};
   for (void *p : ptrs)
     if (p)
@@ -861,6 +944,11 @@ pf_setup_jacobian (pf_ctx *ctx)
   int rc = halo_exchange (ctx, ctx->diag, ctx->nc);
   if (rc)
     return rc;
+  if (ctx->dim == 3)
+    {
+      k_pack_aux<<<nblk (g.n_local_nodes, 256), 256, 0, ctx->stream>>> (g.n_local_nodes, ctx->pt, ctx->mask, ctx->aux);
+      KCHECK ();
+    }
   ctx->jac_ready = true;
   return PF_OK;
 }
@@ -1433,7 +1521,7 @@ pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count)
 int
 pf_debug_set_variant (int variant)
 {
-  if (variant < 1 || variant > 7)
+  if (variant < 1 || variant > 15)
     return PF_BAD_ARG;
   g_apply_variant = variant;
   return PF_OK;

@@ -31,93 +31,19 @@ template <int TX, int TY, int TZ> struct Tile3v2
   static constexpr size_t smem_bytes = smem_doubles * sizeof (double);
 };
 
+// Stages 3 and 4 for one tile: every thread walks its cell through the 27 Gauss
+// points (plane -> row -> point) reading the staged arrays AZ / BZ, and adds
+// its nodal contributions to the shared y tile `ys`.  Contains block barriers:
+// must be called by all threads of the CTA.
 template <int TX, int TY, int TZ>
-__global__ void __launch_bounds__ (TX * TY * TZ, 2)
-k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
-              const double *__restrict__ x, const double *__restrict__ sol,
-              const double *__restrict__ pt, const uint8_t *__restrict__ mask,
-              double *__restrict__ y)
+__device__ __forceinline__ void
+tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const int cx0, const int cy0,
+               const int cz0, const double *__restrict__ AZ, const double *__restrict__ BZ,
+               double *__restrict__ ys)
 {
   using T = Tile3v2<TX, TY, TZ>;
-  constexpr int NN = T::NN, NT = T::NT, NX = T::NX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC;
-  extern __shared__ __align__ (16) unsigned char smem_raw[];
-  double *AZ = reinterpret_cast<double *> (smem_raw); // [3][9][NC2]
-  double *BZ = AZ + 27 * NC2;                         // [7][3][NXC]
-  double *DZ = BZ + 21 * NXC;                         // [7][NC2], stage 1 -> 2 only
-  double *ys = DZ;                                    // [4][NN], aliases DZ
-
-  const int tid = threadIdx.x;
-  int b = blockIdx.x;
-  const int bx = b % tiles_x;
-  b /= tiles_x;
-  const int by = b % tiles_y;
-  const int bz = b / tiles_y;
-  const int cx0 = bx * TX, cy0 = by * TY, cz0 = g.cell_begin + bz * TZ;
-  const int nnx = g.nn[0], nny = g.nn[1];
-  const int lz_off = g.plane_begin;
-  const long long pstride = g.nodes_per_plane;
+  constexpr int NN = T::NN, NX = T::NX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC;
   const double S = k.s;
-
-  // ---- stage 1: z-collapse per node column --------------------------------
-  for (int i = tid; i < NC2; i += NT)
-    {
-      const int ix = i % NX, iy = (i / NX) % NY, tz = i / (NX * NY);
-      const int gx = cx0 + ix, gy = cy0 + iy, gz = cz0 + tz;
-      double f0[9], f1[9];
-#pragma unroll
-      for (int f = 0; f < 9; ++f)
-        f0[f] = f1[f] = 0;
-      if (gx < nnx && gy < nny && gz < g.cell_end)
-        {
-          const long long n0 = gx + (long long) nnx * gy + pstride * (gz - lz_off);
-          const long long n1 = n0 + pstride;
-          const double4 xa = *reinterpret_cast<const double4 *> (x + 4 * n0);
-          const double4 xb = *reinterpret_cast<const double4 *> (x + 4 * n1);
-          const double4 sa = *reinterpret_cast<const double4 *> (sol + 4 * n0);
-          const double4 sb = *reinterpret_cast<const double4 *> (sol + 4 * n1);
-          const uint8_t m0 = mask[n0], m1 = mask[n1];
-          f0[0] = (m0 & 1) ? 0.0 : xa.x;
-          f0[1] = (m0 & 2) ? 0.0 : xa.y;
-          f0[2] = (m0 & 4) ? 0.0 : xa.z;
-          f0[3] = (m0 & 8) ? 0.0 : 0.125 * xa.w;
-          f1[0] = (m1 & 1) ? 0.0 : xb.x;
-          f1[1] = (m1 & 2) ? 0.0 : xb.y;
-          f1[2] = (m1 & 4) ? 0.0 : xb.z;
-          f1[3] = (m1 & 8) ? 0.0 : 0.125 * xb.w;
-          f0[4] = sa.x, f0[5] = sa.y, f0[6] = sa.z, f0[7] = 0.125 * sa.w, f0[8] = 0.125 * pt[n0];
-          f1[4] = sb.x, f1[5] = sb.y, f1[6] = sb.z, f1[7] = 0.125 * sb.w, f1[8] = 0.125 * pt[n1];
-        }
-#pragma unroll
-      for (int f = 0; f < 9; ++f)
-        {
-          const double s = f0[f] + f1[f], r = f1[f] - f0[f];
-          AZ[(0 * 9 + f) * NC2 + i] = fma (-S, r, s);
-          AZ[(1 * 9 + f) * NC2 + i] = s;
-          AZ[(2 * 9 + f) * NC2 + i] = fma (S, r, s);
-          if (f < 7)
-            DZ[f * NC2 + i] = r * ((f == 3) ? k.gp[2] : k.gu[2]);
-        }
-    }
-  __syncthreads ();
-  // ---- stage 2: y-collapse of the z-derivative chain ------------------------
-  for (int i = tid; i < NXC; i += NT)
-    {
-      const int ix = i % NX, cy = (i / NX) % TY, tz = i / (NX * TY);
-      const int c0 = ix + NX * (cy + NY * tz);
-#pragma unroll
-      for (int f = 0; f < 7; ++f)
-        {
-          const double d0 = DZ[f * NC2 + c0], d1 = DZ[f * NC2 + c0 + NX];
-          const double P = d0 + d1, R = d1 - d0;
-          BZ[(f * 3 + 0) * NXC + i] = fma (-S, R, P);
-          BZ[(f * 3 + 1) * NXC + i] = P;
-          BZ[(f * 3 + 2) * NXC + i] = fma (S, R, P);
-        }
-    }
-  __syncthreads ();
-  for (int i = tid; i < 4 * NN; i += NT)
-    ys[i] = 0;
-  __syncthreads ();
 
   // ---- stage 3: one thread per cell -----------------------------------------
   const int tx = tid % TX, ty = (tid / TX) % TY, tz = tid / (TX * TY);
@@ -313,6 +239,98 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
             __syncthreads ();
         }
     }
+
+}
+
+template <int TX, int TY, int TZ, int MINB>
+__global__ void __launch_bounds__ (TX * TY * TZ, MINB)
+k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
+              const double *__restrict__ x, const double *__restrict__ sol,
+              const double *__restrict__ pt, const uint8_t *__restrict__ mask,
+              double *__restrict__ y)
+{
+  using T = Tile3v2<TX, TY, TZ>;
+  constexpr int NN = T::NN, NT = T::NT, NX = T::NX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC;
+  extern __shared__ __align__ (16) unsigned char smem_raw[];
+  double *AZ = reinterpret_cast<double *> (smem_raw); // [3][9][NC2]
+  double *BZ = AZ + 27 * NC2;                         // [7][3][NXC]
+  double *DZ = BZ + 21 * NXC;                         // [7][NC2], stage 1 -> 2 only
+  double *ys = DZ;                                    // [4][NN], aliases DZ
+
+  const int tid = threadIdx.x;
+  int b = blockIdx.x;
+  const int bx = b % tiles_x;
+  b /= tiles_x;
+  const int by = b % tiles_y;
+  const int bz = b / tiles_y;
+  const int cx0 = bx * TX, cy0 = by * TY, cz0 = g.cell_begin + bz * TZ;
+  const int nnx = g.nn[0], nny = g.nn[1];
+  const int lz_off = g.plane_begin;
+  const long long pstride = g.nodes_per_plane;
+  const double S = k.s;
+
+  // ---- stage 1: z-collapse per node column --------------------------------
+  for (int i = tid; i < NC2; i += NT)
+    {
+      const int ix = i % NX, iy = (i / NX) % NY, tz = i / (NX * NY);
+      const int gx = cx0 + ix, gy = cy0 + iy, gz = cz0 + tz;
+      double f0[9], f1[9];
+#pragma unroll
+      for (int f = 0; f < 9; ++f)
+        f0[f] = f1[f] = 0;
+      if (gx < nnx && gy < nny && gz < g.cell_end)
+        {
+          const long long n0 = gx + (long long) nnx * gy + pstride * (gz - lz_off);
+          const long long n1 = n0 + pstride;
+          const double4 xa = *reinterpret_cast<const double4 *> (x + 4 * n0);
+          const double4 xb = *reinterpret_cast<const double4 *> (x + 4 * n1);
+          const double4 sa = *reinterpret_cast<const double4 *> (sol + 4 * n0);
+          const double4 sb = *reinterpret_cast<const double4 *> (sol + 4 * n1);
+          const uint8_t m0 = mask[n0], m1 = mask[n1];
+          f0[0] = (m0 & 1) ? 0.0 : xa.x;
+          f0[1] = (m0 & 2) ? 0.0 : xa.y;
+          f0[2] = (m0 & 4) ? 0.0 : xa.z;
+          f0[3] = (m0 & 8) ? 0.0 : 0.125 * xa.w;
+          f1[0] = (m1 & 1) ? 0.0 : xb.x;
+          f1[1] = (m1 & 2) ? 0.0 : xb.y;
+          f1[2] = (m1 & 4) ? 0.0 : xb.z;
+          f1[3] = (m1 & 8) ? 0.0 : 0.125 * xb.w;
+          f0[4] = sa.x, f0[5] = sa.y, f0[6] = sa.z, f0[7] = 0.125 * sa.w, f0[8] = 0.125 * pt[n0];
+          f1[4] = sb.x, f1[5] = sb.y, f1[6] = sb.z, f1[7] = 0.125 * sb.w, f1[8] = 0.125 * pt[n1];
+        }
+#pragma unroll
+      for (int f = 0; f < 9; ++f)
+        {
+          const double s = f0[f] + f1[f], r = f1[f] - f0[f];
+          AZ[(0 * 9 + f) * NC2 + i] = fma (-S, r, s);
+          AZ[(1 * 9 + f) * NC2 + i] = s;
+          AZ[(2 * 9 + f) * NC2 + i] = fma (S, r, s);
+          if (f < 7)
+            DZ[f * NC2 + i] = r * ((f == 3) ? k.gp[2] : k.gu[2]);
+        }
+    }
+  __syncthreads ();
+  // ---- stage 2: y-collapse of the z-derivative chain ------------------------
+  for (int i = tid; i < NXC; i += NT)
+    {
+      const int ix = i % NX, cy = (i / NX) % TY, tz = i / (NX * TY);
+      const int c0 = ix + NX * (cy + NY * tz);
+#pragma unroll
+      for (int f = 0; f < 7; ++f)
+        {
+          const double d0 = DZ[f * NC2 + c0], d1 = DZ[f * NC2 + c0 + NX];
+          const double P = d0 + d1, R = d1 - d0;
+          BZ[(f * 3 + 0) * NXC + i] = fma (-S, R, P);
+          BZ[(f * 3 + 1) * NXC + i] = P;
+          BZ[(f * 3 + 2) * NXC + i] = fma (S, R, P);
+        }
+    }
+  __syncthreads ();
+  for (int i = tid; i < 4 * NN; i += NT)
+    ys[i] = 0;
+  __syncthreads ();
+
+  tile_cells_v2<TX, TY, TZ> (g, p, k, tid, cx0, cy0, cz0, AZ, BZ, ys);
 
   // ---- flush the y tile ---------------------------------------------------------
   for (int i = tid; i < NN; i += NT)

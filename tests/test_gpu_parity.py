@@ -82,7 +82,8 @@ def test_apply_jacobian_3d(oracle, pf, n, h):
     assert _relerr(ctx.to_nodal(y2), y_ref) <= TOL
     # the first-generation tiled kernel stays available for A/B measurements
     # variant 1 = first-generation kernel, 3..7 = other tile shapes of v2
-    for variant in (1, 2, 4, 5, 6, 7):
+    # 12..15 = persistent TMA-fed kernel (v3)
+    for variant in (1, 2, 4, 5, 6, 7, 12, 13, 14, 15):
         ctx.lib.pf_debug_set_variant(variant)
         try:
             y3 = np.zeros(prob.n_dofs)
