@@ -79,6 +79,7 @@ _SIGS = {
     "pf_set_dirichlet_all_faces": [C.c_void_p],
     "pf_residual": [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)],
     "pf_setup_jacobian": [C.c_void_p],
+    "pf_set_preconditioner": [C.c_void_p, C.c_int, C.c_int, C.c_double],
     "pf_apply_jacobian": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_apply_jacobian_dev": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_jacobian_diagonal": [C.c_void_p, C.c_void_p],
@@ -291,6 +292,10 @@ class PhaseFieldContext:
             return r_pde, r_tot, nrm.value
         self._check(self.lib.pf_residual(self.h, None, None, C.byref(nrm)))
         return None, None, nrm.value
+
+    def set_preconditioner(self, kind=1, cheb_degree=3, cheb_ratio=20.0):
+        """0 = Jacobi, 1 = geometric multigrid (stand-in for the reference's ML AMG)"""
+        self._check(self.lib.pf_set_preconditioner(self.h, kind, cheb_degree, cheb_ratio))
 
     def setup_jacobian(self):
         self._check(self.lib.pf_setup_jacobian(self.h))

@@ -21,6 +21,7 @@
 #include "pf_apply3d_v3.cuh"
 #include "pf_common.cuh"
 #include "pf_generic.cuh"
+#include "pf_multigrid.cuh"
 #include "pf_vector.cuh"
 
 using namespace pf;
@@ -119,6 +120,15 @@ struct pf_ctx
   int krylov_m = 30;
   double *V = nullptr, *zvec = nullptr, *hdev = nullptr;
   bool jac_ready = false, have_r = false;
+  // multigrid preconditioner (single rank, dim 3): coarser level, work vectors, Chebyshev data
+  pf_ctx *coarse = nullptr;
+  bool owns_stream = true;
+  int precond = 1;          // 0 = Jacobi, 1 = geometric multigrid V-cycle (falls back to Jacobi if unavailable)
+  int cheb_degree = 3;
+  double cheb_ratio = 20.0; // smoothing range lambda_max / lambda_min targeted by the smoother
+  double lam_max = 0;
+  double *mg_b = nullptr, *mg_x = nullptr, *mg_y = nullptr, *mg_d = nullptr, *mg_r = nullptr;
+  bool mg_ready = false;
   double last_rnorm = 0;
   long long launches = 0;
   bool profiling = false;
@@ -549,6 +559,218 @@ residual_dev (pf_ctx *ctx, double *l2)
   return PF_OK;
 }
 
+
+// ---- geometric multigrid preconditioner ----------------------------------------
+int
+norm2_dev (pf_ctx *ctx, const double *v, double *out)
+{
+  const long long lo = ctx->owned_lo * ctx->nc, hi = ctx->owned_hi * ctx->nc;
+  k_multi_dot<8><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (lo, hi, 0, 0, v, 0, v, 1, ctx->partial);
+  KCHECK ();
+  k_reduce_partials<<<1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, 1, ctx->partial, ctx->red);
+  KCHECK ();
+  CU (cudaMemcpyAsync (ctx->h_red, ctx->red, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  *out = std::sqrt (ctx->h_red[0]);
+  return PF_OK;
+}
+
+bool
+mg_possible (const pf_ctx *ctx)
+{
+  if (ctx->dim != 3 || ctx->nranks != 1)
+    return false;
+  for (int d = 0; d < 3; ++d)
+    if (ctx->g.n[d] % 2 != 0 || ctx->g.n[d] / 2 < 4)
+      return false;
+  return true;
+}
+
+int diag_and_aux (pf_ctx *ctx);
+
+// (re)builds the level below ctx and transfers state, constraints and parameters to it
+int
+mg_setup_level (pf_ctx *ctx)
+{
+  const long long nd = ctx->n_local_dofs;
+  if (!ctx->mg_b)
+    {
+      double **vecs[] = {&ctx->mg_b, &ctx->mg_x, &ctx->mg_y, &ctx->mg_d, &ctx->mg_r};
+      for (double **v : vecs)
+        CU (cudaMalloc (v, sizeof (double) * nd));
+    }
+  // lambda_max of D^-1 J by a few power iterations (norm ratio)
+  {
+    double *v = ctx->mg_x, *w = ctx->mg_y;
+    k_fill_hash<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, v);
+    KCHECK ();
+    double lam = 1.0, nv = 0, nw = 0;
+    int rc;
+    for (int it = 0; it < 12; ++it)
+      {
+        if ((rc = apply_dev (ctx, v, w)))
+          return rc;
+        k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->diag, w, w);
+        KCHECK ();
+        if ((rc = norm2_dev (ctx, v, &nv)) || (rc = norm2_dev (ctx, w, &nw)))
+          return rc;
+        if (!(nv > 0) || !std::isfinite (nw))
+          return fail (ctx, PF_NUMERIC, "multigrid: power iteration broke down");
+        lam = nw / nv;
+        k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->red, 1.0 / nw, 0, w, v);
+        KCHECK ();
+      }
+    ctx->lam_max = 1.2 * lam;
+  }
+  if (!mg_possible (ctx))
+    {
+      ctx->mg_ready = true;
+      return PF_OK;
+    }
+  if (!ctx->coarse)
+    {
+      pf_mesh cm;
+      cm.dim = 3;
+      for (int d = 0; d < 3; ++d)
+        {
+          cm.n[d] = ctx->g.n[d] / 2;
+          cm.h[d] = ctx->g.h[d] * 2.0;
+          cm.origin[d] = ctx->g.origin[d];
+        }
+      int rc = pf_create (&cm, &ctx->prm, ctx->device, 0, 1, nullptr, &ctx->coarse);
+      if (rc)
+        return fail (ctx, rc, "multigrid: cannot create the coarse level: %s", pf_last_error (ctx->coarse));
+      cudaStreamDestroy (ctx->coarse->stream);
+      ctx->coarse->stream = ctx->stream;
+      ctx->coarse->owns_stream = false;
+    }
+  pf_ctx *c = ctx->coarse;
+  c->prm = ctx->prm;
+  c->p = ctx->p;
+  c->precond = ctx->precond;
+  c->cheb_degree = ctx->cheb_degree;
+  c->cheb_ratio = ctx->cheb_ratio;
+  Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}}, df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}};
+  const long long ncn = c->g.n_local_nodes;
+  k_inject<4, double><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->sol, c->sol);
+  KCHECK ();
+  k_inject<1, double><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->pt, c->pt);
+  KCHECK ();
+  k_inject<1, uint8_t><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->mask, c->mask);
+  KCHECK ();
+  int rc = diag_and_aux (c);
+  if (rc)
+    return fail (ctx, rc, "multigrid: coarse diagonal: %s", pf_last_error (c));
+  c->jac_ready = true;
+  if ((rc = mg_setup_level (c)))
+    return fail (ctx, rc, "multigrid: %s", pf_last_error (c));
+  ctx->mg_ready = true;
+  return PF_OK;
+}
+
+// Chebyshev-Jacobi smoother on J x = b; zero_guess: x is ignored on entry
+int
+mg_smooth (pf_ctx *ctx, const double *b, double *x, bool zero_guess, int degree, double ratio)
+{
+  const long long nd = ctx->n_local_dofs;
+  const double lmax = ctx->lam_max, lmin = lmax / ratio;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  int rc;
+  for (int kk = 0; kk < degree; ++kk)
+    {
+      const bool first = kk == 0;
+      if (!(first && zero_guess))
+        if ((rc = apply_dev (ctx, x, ctx->mg_y)))
+          return rc;
+      double c1 = 0, c2 = 1.0 / theta;
+      if (!first)
+        {
+          const double rho_new = 1.0 / (2.0 * sigma - rho);
+          c1 = rho_new * rho;
+          c2 = 2.0 * rho_new / delta;
+          rho = rho_new;
+        }
+      if (first && !zero_guess)
+        {
+          // d = (1/theta) D^-1 (b - A x); x += d
+          k_sub<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, b, ctx->mg_y, ctx->mg_r);
+          KCHECK ();
+          k_cheb_step<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, 1, 0.0, c2, ctx->mg_r, ctx->mg_y, ctx->diag,
+                                                                    ctx->mg_d, ctx->mg_r);
+          KCHECK ();
+          k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, 1.0, ctx->mg_d, x);
+          KCHECK ();
+        }
+      else
+        {
+          k_cheb_step<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, first ? 1 : 0, c1, c2, b, ctx->mg_y, ctx->diag,
+                                                                    ctx->mg_d, x);
+          KCHECK ();
+        }
+    }
+  return PF_OK;
+}
+
+int
+mg_vcycle (pf_ctx *ctx, const double *b, double *x)
+{
+  int rc;
+  pf_ctx *c = ctx->coarse;
+  if (!c)
+    return mg_smooth (ctx, b, x, true, 40, 400.0); // coarsest level: long Chebyshev run
+  if ((rc = mg_smooth (ctx, b, x, true, ctx->cheb_degree, ctx->cheb_ratio)))
+    return rc;
+  const long long nd = ctx->n_local_dofs;
+  if ((rc = apply_dev (ctx, x, ctx->mg_y)))
+    return rc;
+  k_sub<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, b, ctx->mg_y, ctx->mg_r);
+  KCHECK ();
+  Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}}, df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}};
+  k_restrict<<<nblk (c->g.n_local_nodes, 128), 128, 0, ctx->stream>>> (dc, df, ctx->mg_r, ctx->mask, c->mask, c->mg_b);
+  KCHECK ();
+  if ((rc = mg_vcycle (c, c->mg_b, c->mg_x)))
+    return rc;
+  k_prolong_add<<<nblk (ctx->g.n_local_nodes, 256), 256, 0, ctx->stream>>> (dc, df, c->mg_x, ctx->mask, x);
+  KCHECK ();
+  return mg_smooth (ctx, b, x, false, ctx->cheb_degree, ctx->cheb_ratio);
+}
+
+// z = M^-1 v
+int
+precond_apply (pf_ctx *ctx, const double *v, double *z)
+{
+  if (ctx->precond == 1 && ctx->mg_ready && ctx->coarse)
+    return mg_vcycle (ctx, v, z);
+  k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->n_local_dofs, ctx->diag, v, z);
+  KCHECK ();
+  return PF_OK;
+}
+
+int
+diag_and_aux (pf_ctx *ctx)
+{
+  const Grid &g = ctx->g;
+  CU (cudaMemsetAsync (ctx->diag, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
+  if (ctx->dim == 2)
+    k_diag_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+      g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
+  else
+    k_diag_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+      g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
+  KCHECK ();
+  // complete the diagonal on the ghost planes (their cells are only partly local)
+  int rc = halo_exchange (ctx, ctx->diag, ctx->nc);
+  if (rc)
+    return rc;
+  if (ctx->dim == 3)
+    {
+      k_pack_aux<<<nblk (g.n_local_nodes, 256), 256, 0, ctx->stream>>> (g.n_local_nodes, ctx->pt, ctx->mask, ctx->aux);
+      KCHECK ();
+    }
+  return PF_OK;
+}
+
 } // namespace
 
 // ===========================================================================
@@ -740,6 +962,11 @@ pf_destroy (pf_ctx *ctx)
     cudaStreamSynchronize (ctx->stream);
   if (ctx->comm)
     g_nccl.CommDestroy (ctx->comm);
+  if (ctx->coarse)
+    pf_destroy (ctx->coarse);
+  for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r})
+    if (v)
+      cudaFree (v);
   void *ptrs[] = {ctx->sol,   ctx->old,  ctx->oldold, ctx->pt,     ctx->diag,  ctx->mass, ctx->r_total,
                   ctx->r_pde, ctx->dx,   ctx->stage,  ctx->xa,     ctx->ya,    ctx->zvec, ctx->mask,
                   ctx->saved, ctx->aux, ctx->tile_counter, ctx->stage8, ctx->cycle, ctx->fetab, ctx->red,   ctx->hdev,  ctx->partial, ctx->counts,
@@ -751,7 +978,7 @@ pf_destroy (pf_ctx *ctx)
     cudaFreeHost (ctx->h_red);
   if (ctx->h_counts)
     cudaFreeHost (ctx->h_counts);
-  if (ctx->stream)
+  if (ctx->stream && ctx->owns_stream)
     cudaStreamDestroy (ctx->stream);
   delete ctx;
   return PF_OK;
@@ -931,25 +1158,25 @@ pf_setup_jacobian (pf_ctx *ctx)
   if (!ctx)
     return PF_BAD_ARG;
   CU (cudaSetDevice (ctx->device));
-  const Grid &g = ctx->g;
-  CU (cudaMemsetAsync (ctx->diag, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
-  if (ctx->dim == 2)
-    k_diag_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-      g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
-  else
-    k_diag_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-      g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
-  KCHECK ();
-  // complete the diagonal on the ghost planes (their cells are only partly local)
-  int rc = halo_exchange (ctx, ctx->diag, ctx->nc);
+  int rc = diag_and_aux (ctx);
   if (rc)
     return rc;
-  if (ctx->dim == 3)
-    {
-      k_pack_aux<<<nblk (g.n_local_nodes, 256), 256, 0, ctx->stream>>> (g.n_local_nodes, ctx->pt, ctx->mask, ctx->aux);
-      KCHECK ();
-    }
   ctx->jac_ready = true;
+  ctx->mg_ready = false;
+  if (ctx->precond == 1 && ctx->dim == 3 && ctx->nranks == 1)
+    return mg_setup_level (ctx);
+  return PF_OK;
+}
+
+int
+pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio)
+{
+  if (!ctx || kind < 0 || kind > 1 || cheb_degree < 1 || !(cheb_ratio > 1.0))
+    return PF_BAD_ARG;
+  ctx->precond = kind;
+  ctx->cheb_degree = cheb_degree;
+  ctx->cheb_ratio = cheb_ratio;
+  ctx->jac_ready = false;
   return PF_OK;
 }
 
@@ -1179,8 +1406,8 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
         {
           double *vk = V + (size_t) k * nd, *vk1 = V + (size_t) (k + 1) * nd;
           // z = M^{-1} v_k ; w = J z
-          k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->diag, vk, z);
-          KCHECK ();
+          if ((rc = precond_apply (ctx, vk, z)))
+            return rc;
           if ((rc = apply_dev (ctx, z, w)))
             return rc;
           // CGS2: two passes of classical Gram-Schmidt, fused multi-dot / multi-axpy
@@ -1243,8 +1470,8 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
       CU (cudaMemsetAsync (w, 0, sizeof (double) * nd, ctx->stream));
       k_combine<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k, V, nd, ctx->hdev, w);
       KCHECK ();
-      k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->diag, w, z);
-      KCHECK ();
+      if ((rc = precond_apply (ctx, w, z)))
+        return rc;
       k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, 1.0, z, x);
       KCHECK ();
       CU (cudaStreamSynchronize (ctx->stream));

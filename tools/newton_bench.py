@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Newton-its/s of the device-resident active-set Newton loop (cracks.cc:2780-2994)
+on Sneddon-3D (parameters_sneddon_3d.prm values) at a given global refinement.
+
+  python tools/newton_bench.py --refine 3 --steps 2 [--precond 1 --degree 3 --ratio 20]
+
+Prints the reference-style Newton table and one JSON line with Newton
+iterations per second, total linear iterations and the energies.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--refine", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2, help="time steps to run")
+    ap.add_argument("--precond", type=int, default=1)
+    ap.add_argument("--degree", type=int, default=3)
+    ap.add_argument("--ratio", type=float, default=20.0)
+    ap.add_argument("--gmres-max-it", type=int, default=200)
+    ap.add_argument("--quiet", action="store_true")
+    args = ap.parse_args()
+    import cracks_b200 as pf
+    from cracks_b200.api import mesh_diameter
+
+    mesh = pf.sneddon_mesh(3, args.refine)
+    ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh))           # K reg = 1e-8*h, Eps reg = 2h
+    ctx.set_preconditioner(args.precond, args.degree, args.ratio)
+    log = (lambda s: None) if args.quiet else (lambda s: print(s, flush=True))
+    # parameters_sneddon_3d.prm: Newton lower bound 1e-7, max 50 steps, line search 10 x 0.5
+    drv = pf.SneddonDriver(ctx, pressure=lambda t: 1e-3, max_no_timesteps=args.steps - 1, newton_lower_bound=1e-7,
+                           max_newton=50, max_line_search=10, gmres_max_it=args.gmres_max_it, log=log)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    try:
+        stats = drv.run(mesh_diameter(mesh))
+        err = None
+    except pf.PFError as e:
+        stats, err = drv.statistics, str(e)
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    print(json.dumps({"refine": args.refine, "n_dofs": ctx.n_dofs, "time_steps": len(stats),
+                      "newton_its": drv.newton_its, "linear_its": drv.lin_its, "wall_s": dt,
+                      "newton_its_per_s": drv.newton_its / dt if dt > 0 else None,
+                      "precond": args.precond, "cheb_degree": args.degree, "cheb_ratio": args.ratio,
+                      "statistics": stats, "error": err}))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
