@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--cpu-refine", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-newton", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="debug: apply-kernel variant (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -327,6 +328,23 @@ def main():
                          "kernel_share_of_step": kern_ms / ms_total, "algorithmic_bytes": b_alg, "peak_source": peak_src,
                          "note": "FP64-pipe bound: exact 27-point FP64 quadrature, no f64 tensor path (DESIGN.md)"},
         }
+        if world == 1 and not args.no_newton:
+            # second half of BASELINE.json's metric: Newton-its/s of the device-resident
+            # active-set Newton loop (cracks.cc:2780-2994) on the same mesh, real time
+            # steps 0..1 of parameters_sneddon_3d.prm from the interpolated initial condition
+            nctx = pf.PhaseFieldContext(mesh, params, device=local_rank)
+            drv = pf.SneddonDriver(nctx, pressure=lambda t: 1e-3, max_no_timesteps=1, newton_lower_bound=1e-7,
+                                   max_newton=50, max_line_search=10, gmres_max_it=200)
+            nctx.synchronize()
+            t0 = time.perf_counter()
+            nstats = drv.run(mesh_diameter(mesh))
+            nctx.synchronize()
+            dt = time.perf_counter() - t0
+            line["newton"] = {"newton_its_per_s": drv.newton_its / dt, "newton_its": drv.newton_its,
+                              "linear_its": drv.lin_its, "time_steps": len(nstats), "wall_s": dt,
+                              "crack_energy": nstats[-1]["crack"], "bulk_energy": nstats[-1]["bulk"],
+                              "preconditioner": "matrix-free geometric multigrid V-cycle, Chebyshev(3)-Jacobi"}
+            nctx.close()
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_sample(10, 2, refine=args.cpu_refine)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

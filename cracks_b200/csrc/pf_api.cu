@@ -124,7 +124,9 @@ struct pf_ctx
   pf_ctx *coarse = nullptr;
   bool owns_stream = true;
   int precond = 1;          // 0 = Jacobi, 1 = geometric multigrid V-cycle (falls back to Jacobi if unavailable)
-  int cheb_degree = 3;
+  int cheb_degree = 2;
+  int coarsest_degree = 16;
+  bool mg_approx = true;    // smoother / coarse operators use the 2-point Gauss rule (preconditioner only)
   double cheb_ratio = 20.0; // smoothing range lambda_max / lambda_min targeted by the smoother
   double lam_max = 0;
   double *mg_b = nullptr, *mg_x = nullptr, *mg_y = nullptr, *mg_d = nullptr, *mg_r = nullptr;
@@ -360,7 +362,7 @@ launch_apply3d (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
-template <int TX, int TY, int TZ, int MINB = 2>
+template <int TX, int TY, int TZ, int MINB = 2, int NQ = 3>
 int
 launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
 {
@@ -371,11 +373,11 @@ launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
   static bool attr_set = false;
   if (!attr_set)
     {
-      CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ, MINB, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
       attr_set = true;
     }
-  k_apply3d_v2<TX, TY, TZ, MINB><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes, ctx->stream>>> (
+  k_apply3d_v2<TX, TY, TZ, MINB, NQ><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes, ctx->stream>>> (
     g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
   KCHECK ();
   return PF_OK;
@@ -451,8 +453,10 @@ launch_apply3d_v3 (pf_ctx *ctx, const double *x, double *y)
 }
 int g_force_generic = 0;
 
+// approx = true: the under-integrated (2-point Gauss) operator used only inside the
+// multigrid preconditioner, whose arithmetic is unpinned
 int
-apply_dev (pf_ctx *ctx, double *x, double *y)
+apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
 {
   if (!ctx->jac_ready)
     return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must be called before applying the Jacobian");
@@ -487,6 +491,13 @@ apply_dev (pf_ctx *ctx, double *x, double *y)
               CU (cudaEventCreate (&e0));
               CU (cudaEventCreate (&e1));
               CU (cudaEventRecord (e0, ctx->stream));
+            }
+          if (approx)
+            {
+              rc = launch_apply3d_v2<16, 4, 1, 2, 2> (ctx, x, y);
+              if (rc)
+                return rc;
+              return PF_OK;
             }
           switch (g_apply_variant)
             {
@@ -606,9 +617,9 @@ mg_setup_level (pf_ctx *ctx)
     KCHECK ();
     double lam = 1.0, nv = 0, nw = 0;
     int rc;
-    for (int it = 0; it < 12; ++it)
+    for (int it = 0; it < 8; ++it)
       {
-        if ((rc = apply_dev (ctx, v, w)))
+        if ((rc = apply_dev (ctx, v, w, ctx->mg_approx)))
           return rc;
         k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->diag, w, w);
         KCHECK ();
@@ -650,6 +661,8 @@ mg_setup_level (pf_ctx *ctx)
   c->precond = ctx->precond;
   c->cheb_degree = ctx->cheb_degree;
   c->cheb_ratio = ctx->cheb_ratio;
+  c->mg_approx = ctx->mg_approx;
+  c->coarsest_degree = ctx->coarsest_degree;
   Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}}, df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}};
   const long long ncn = c->g.n_local_nodes;
   k_inject<4, double><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->sol, c->sol);
@@ -681,7 +694,7 @@ mg_smooth (pf_ctx *ctx, const double *b, double *x, bool zero_guess, int degree,
     {
       const bool first = kk == 0;
       if (!(first && zero_guess))
-        if ((rc = apply_dev (ctx, x, ctx->mg_y)))
+        if ((rc = apply_dev (ctx, x, ctx->mg_y, ctx->mg_approx)))
           return rc;
       double c1 = 0, c2 = 1.0 / theta;
       if (!first)
@@ -718,11 +731,11 @@ mg_vcycle (pf_ctx *ctx, const double *b, double *x)
   int rc;
   pf_ctx *c = ctx->coarse;
   if (!c)
-    return mg_smooth (ctx, b, x, true, 40, 400.0); // coarsest level: long Chebyshev run
+    return mg_smooth (ctx, b, x, true, ctx->coarsest_degree, 100.0); // coarsest level (5^3 cells for Sneddon): long Chebyshev run
   if ((rc = mg_smooth (ctx, b, x, true, ctx->cheb_degree, ctx->cheb_ratio)))
     return rc;
   const long long nd = ctx->n_local_dofs;
-  if ((rc = apply_dev (ctx, x, ctx->mg_y)))
+  if ((rc = apply_dev (ctx, x, ctx->mg_y, ctx->mg_approx)))
     return rc;
   k_sub<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, b, ctx->mg_y, ctx->mg_r);
   KCHECK ();
@@ -883,6 +896,7 @@ pf_create (const pf_mesh *mesh, const pf_params *params, int device, int rank, i
 
   const double s = std::sqrt (3.0 / 5.0);
   ctx->k3.s = s;
+  ctx->k3.s2 = std::sqrt (1.0 / 3.0);
   ctx->k3.wvol = 1.0;
   for (int d = 0; d < 3; ++d)
     {
@@ -1171,9 +1185,10 @@ pf_setup_jacobian (pf_ctx *ctx)
 int
 pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio)
 {
-  if (!ctx || kind < 0 || kind > 1 || cheb_degree < 1 || !(cheb_ratio > 1.0))
+  if (!ctx || kind < 0 || kind > 2 || cheb_degree < 1 || !(cheb_ratio > 1.0))
     return PF_BAD_ARG;
-  ctx->precond = kind;
+  ctx->precond = kind ? 1 : 0;
+  ctx->mg_approx = kind != 2; // kind 2: smoother with the exact 27-point operator (for comparisons)
   ctx->cheb_degree = cheb_degree;
   ctx->cheb_ratio = cheb_ratio;
   ctx->jac_ready = false;

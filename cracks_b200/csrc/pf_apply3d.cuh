@@ -25,6 +25,7 @@ namespace pf {
 struct K3
 {
   double s;          // sqrt(3/5): Gauss abscissa on [-1,1]
+  double s2;         // sqrt(1/3): abscissa of the 2-point rule (preconditioner-only operator)
   double gu[3];      // 1/(4 h_d): gradient scale of an unscaled nodal field
   double gp[3];      // 2/h_d:     gradient scale of a field pre-scaled by 1/8
   double wq[3];      // per-direction Gauss weights (5/9, 8/9, 5/9)

@@ -35,7 +35,7 @@ template <int TX, int TY, int TZ> struct Tile3v2
 // points (plane -> row -> point) reading the staged arrays AZ / BZ, and adds
 // its nodal contributions to the shared y tile `ys`.  Contains block barriers:
 // must be called by all threads of the CTA.
-template <int TX, int TY, int TZ>
+template <int TX, int TY, int TZ, int NQ = 3>
 __device__ __forceinline__ void
 tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const int cx0, const int cy0,
                const int cz0, const double *__restrict__ AZ, const double *__restrict__ BZ,
@@ -43,7 +43,8 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
 {
   using T = Tile3v2<TX, TY, TZ>;
   constexpr int NN = T::NN, NX = T::NX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC;
-  const double S = k.s;
+  constexpr bool CEN = (NQ == 3); // the 3-point rule has a centre point (xi = 0), the 2-point rule has not
+  const double S = CEN ? k.s : k.s2;
 
   // ---- stage 3: one thread per cell -----------------------------------------
   const int tx = tid % TX, ty = (tid / TX) % TY, tz = tid / (TX * TY);
@@ -56,12 +57,12 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
   const double c_gce = p.G_c / p.eps;
   const double c_gceps = p.G_c * p.eps;
   const double two_mu = 2.0 * p.mu;
-  const double es[3] = {-S, 0.0, S};
+  const double es[3] = {-S, CEN ? 0.0 : S, S};
 
 #pragma unroll 1
-  for (int qz = 0; qz < 3; ++qz)
+  for (int qz = 0; qz < NQ; ++qz)
     {
-      const double ez = (qz == 0) ? -S : (qz == 1 ? 0.0 : S);
+      const double ez = (qz == 0) ? -S : ((CEN && qz == 1) ? 0.0 : S);
       const double *Aq = AZ + qz * 9 * NC2 + c00;
       double VP[4][2], VR[4][2], DP[4][2], DR[4][2], YP[4], YR[4];
 #pragma unroll
@@ -75,7 +76,7 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
       if (valid)
         {
 #pragma unroll
-          for (int qy = 0; qy < 3; ++qy)
+          for (int qy = 0; qy < NQ; ++qy)
             {
               const double ey = es[qy];
               double PxB[9], RxB[9], PxBz[7], RxBz[7], dx[7], PxDy[7], RxDy[7];
@@ -85,8 +86,8 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                   const double a00 = Aq[f * NC2], a10 = Aq[f * NC2 + 1];
                   const double a01 = Aq[f * NC2 + NX], a11 = Aq[f * NC2 + NX + 1];
                   const double r0 = a01 - a00, r1 = a11 - a10;
-                  const double b0 = (qy == 1) ? a00 + a01 : fma (ey, r0, a00 + a01);
-                  const double b1 = (qy == 1) ? a10 + a11 : fma (ey, r1, a10 + a11);
+                  const double b0 = (CEN && qy == 1) ? a00 + a01 : fma (ey, r0, a00 + a01);
+                  const double b1 = (CEN && qy == 1) ? a10 + a11 : fma (ey, r1, a10 + a11);
                   PxB[f] = b0 + b1;
                   RxB[f] = b1 - b0;
                   if (f < 7)
@@ -95,7 +96,7 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                       dx[f] = RxB[f] * ((f == 3) ? k.gp[0] : k.gu[0]);
                       PxDy[f] = (r0 + r1) * gys;
                       RxDy[f] = (r1 - r0) * gys;
-                      const double z0 = BZ[(f * 3 + qy) * NXC + it0], z1 = BZ[(f * 3 + qy) * NXC + it0 + 1];
+                      const double z0 = BZ[(f * NQ + qy) * NXC + it0], z1 = BZ[(f * NQ + qy) * NXC + it0 + 1];
                       PxBz[f] = z0 + z1;
                       RxBz[f] = z1 - z0;
                     }
@@ -107,7 +108,7 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                 XS[c] = ZP[c] = ZR[c] = yP[c] = yR[c] = 0;
 
 #pragma unroll
-              for (int qx = 0; qx < 3; ++qx)
+              for (int qx = 0; qx < NQ; ++qx)
                 {
                   const double ex = es[qx];
                   double G[3][3], U[3][3], gph[3];
@@ -115,18 +116,18 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                   for (int c = 0; c < 3; ++c)
                     {
                       G[c][0] = dx[c];
-                      G[c][1] = (qx == 1) ? PxDy[c] : fma (ex, RxDy[c], PxDy[c]);
-                      G[c][2] = (qx == 1) ? PxBz[c] : fma (ex, RxBz[c], PxBz[c]);
+                      G[c][1] = (CEN && qx == 1) ? PxDy[c] : fma (ex, RxDy[c], PxDy[c]);
+                      G[c][2] = (CEN && qx == 1) ? PxBz[c] : fma (ex, RxBz[c], PxBz[c]);
                       U[c][0] = dx[4 + c];
-                      U[c][1] = (qx == 1) ? PxDy[4 + c] : fma (ex, RxDy[4 + c], PxDy[4 + c]);
-                      U[c][2] = (qx == 1) ? PxBz[4 + c] : fma (ex, RxBz[4 + c], PxBz[4 + c]);
+                      U[c][1] = (CEN && qx == 1) ? PxDy[4 + c] : fma (ex, RxDy[4 + c], PxDy[4 + c]);
+                      U[c][2] = (CEN && qx == 1) ? PxBz[4 + c] : fma (ex, RxBz[4 + c], PxBz[4 + c]);
                     }
                   gph[0] = dx[3];
-                  gph[1] = (qx == 1) ? PxDy[3] : fma (ex, RxDy[3], PxDy[3]);
-                  gph[2] = (qx == 1) ? PxBz[3] : fma (ex, RxBz[3], PxBz[3]);
-                  const double dphi = (qx == 1) ? PxB[3] : fma (ex, RxB[3], PxB[3]);
-                  const double pf = (qx == 1) ? PxB[7] : fma (ex, RxB[7], PxB[7]);
-                  double pte = (qx == 1) ? PxB[8] : fma (ex, RxB[8], PxB[8]);
+                  gph[1] = (CEN && qx == 1) ? PxDy[3] : fma (ex, RxDy[3], PxDy[3]);
+                  gph[2] = (CEN && qx == 1) ? PxBz[3] : fma (ex, RxBz[3], PxBz[3]);
+                  const double dphi = (CEN && qx == 1) ? PxB[3] : fma (ex, RxB[3], PxB[3]);
+                  const double pf = (CEN && qx == 1) ? PxB[7] : fma (ex, RxB[7], PxB[7]);
+                  double pte = (CEN && qx == 1) ? PxB[8] : fma (ex, RxB[8], PxB[8]);
                   if (p.clamp_extra)
                     pte = fmin (fmax (pte, 0.0), 1.0);
 
@@ -143,7 +144,7 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                   const double spE = fma (p.lambda * trU, trU, two_mu * fma (0.5, od2, dd2));
                   const double a_val = pf * (2.0 * omk * spG - 2.0 * p.P1 * trG)
                                        + dphi * (fma (omk, spE, c_gce) - 2.0 * p.P1 * trU);
-                  const double w = k.wvol * k.wq[qx] * k.wq[qy] * k.wq[qz];
+                  const double w = CEN ? k.wvol * k.wq[qx] * k.wq[qy] * k.wq[qz] : k.wvol;
                   const double wg = w * gdeg;
                   const double wgl = wg * p.lambda * trG, wgm = wg * p.mu, wg2m = wg * two_mu;
                   const double S00 = fma (wg2m, G[0][0], wgl), S11 = fma (wg2m, G[1][1], wgl),
@@ -159,14 +160,14 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                       XS[c] += fx[c];
                       yP[c] += fy[c];
                       ZP[c] += fz[c];
-                      if (qx != 1)
+                      if (!(CEN && qx == 1))
                         {
                           yR[c] = fma (ex, fy[c], yR[c]);
                           ZR[c] = fma (ex, fz[c], ZR[c]);
                         }
                     }
                   AP += wa;
-                  if (qx != 1)
+                  if (!(CEN && qx == 1))
                     AR = fma (ex, wa, AR);
                 }
 #pragma unroll
@@ -185,7 +186,7 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                   const double z0 = ZP[c] - ZR[c], z1 = ZP[c] + ZR[c];
                   DP[c][0] += z0;
                   DP[c][1] += z1;
-                  if (qy != 1)
+                  if (!(CEN && qy == 1))
                     {
                       VR[c][0] = fma (ey, v0, VR[c][0]);
                       VR[c][1] = fma (ey, v1, VR[c][1]);
@@ -242,7 +243,7 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
 
 }
 
-template <int TX, int TY, int TZ, int MINB>
+template <int TX, int TY, int TZ, int MINB, int NQ = 3>
 __global__ void __launch_bounds__ (TX * TY * TZ, MINB)
 k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
               const double *__restrict__ x, const double *__restrict__ sol,
@@ -267,7 +268,7 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
   const int nnx = g.nn[0], nny = g.nn[1];
   const int lz_off = g.plane_begin;
   const long long pstride = g.nodes_per_plane;
-  const double S = k.s;
+  const double S = (NQ == 3) ? k.s : k.s2;
 
   // ---- stage 1: z-collapse per node column --------------------------------
   for (int i = tid; i < NC2; i += NT)
@@ -303,8 +304,9 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
         {
           const double s = f0[f] + f1[f], r = f1[f] - f0[f];
           AZ[(0 * 9 + f) * NC2 + i] = fma (-S, r, s);
-          AZ[(1 * 9 + f) * NC2 + i] = s;
-          AZ[(2 * 9 + f) * NC2 + i] = fma (S, r, s);
+          AZ[(1 * 9 + f) * NC2 + i] = (NQ == 3) ? s : fma (S, r, s);
+          if (NQ == 3)
+            AZ[(2 * 9 + f) * NC2 + i] = fma (S, r, s);
           if (f < 7)
             DZ[f * NC2 + i] = r * ((f == 3) ? k.gp[2] : k.gu[2]);
         }
@@ -320,9 +322,10 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
         {
           const double d0 = DZ[f * NC2 + c0], d1 = DZ[f * NC2 + c0 + NX];
           const double P = d0 + d1, R = d1 - d0;
-          BZ[(f * 3 + 0) * NXC + i] = fma (-S, R, P);
-          BZ[(f * 3 + 1) * NXC + i] = P;
-          BZ[(f * 3 + 2) * NXC + i] = fma (S, R, P);
+          BZ[(f * NQ + 0) * NXC + i] = fma (-S, R, P);
+          BZ[(f * NQ + 1) * NXC + i] = (NQ == 3) ? P : fma (S, R, P);
+          if (NQ == 3)
+            BZ[(f * NQ + 2) * NXC + i] = fma (S, R, P);
         }
     }
   __syncthreads ();
@@ -330,7 +333,7 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
     ys[i] = 0;
   __syncthreads ();
 
-  tile_cells_v2<TX, TY, TZ> (g, p, k, tid, cx0, cy0, cz0, AZ, BZ, ys);
+  tile_cells_v2<TX, TY, TZ, NQ> (g, p, k, tid, cx0, cy0, cz0, AZ, BZ, ys);
 
   // ---- flush the y tile ---------------------------------------------------------
   for (int i = tid; i < NN; i += NT)

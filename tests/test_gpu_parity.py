@@ -199,3 +199,28 @@ def test_errors_are_loud(pf):
     with pytest.raises(pf.PFError):
         ctx.active_set_update(10.0)     # no residual yet
     ctx.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_preconditioners_give_the_same_newton_update(oracle, pf, kind):
+    """Jacobi, multigrid with the under-integrated smoother operator (default) and
+    multigrid with the exact operator are only preconditioners: the solution of
+    J dx = r must not depend on them (the reference's ML AMG is unpinned too)."""
+    import scipy.sparse.linalg as spla
+    prob, ctx, sol, old, oo, con, rng = _case(oracle, pf, 3, (16, 16, 16), (1.0, 1.0, 1.0), seed=9, clamp_active=False)
+    r_pde_ref, _ = prob.residual(sol, old, oo, con)
+    J = prob.jacobian(sol, old, oo, con).tocsc()
+    dx_ref = spla.spsolve(J, r_pde_ref)
+    dx_ref[con == 1] = 0.0
+    ctx.set_preconditioner(kind)
+    ctx.residual(want_vectors=False)
+    ctx.setup_jacobian()
+    dx, its = ctx.solve(1e-10, 2000, want_dx=True)
+    assert _relerr(ctx.to_nodal(dx), dx_ref) <= 1e-7
+    if kind:
+        assert its <= 40          # multigrid: a few dozen at most on this random state
+    with pytest.raises(pf.PFError):
+        ctx.set_preconditioner(3)
+    with pytest.raises(pf.PFError):
+        ctx.set_preconditioner(1, cheb_degree=0)
+    ctx.close()

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--refine", type=int, default=3)
     ap.add_argument("--steps", type=int, default=2, help="time steps to run")
     ap.add_argument("--precond", type=int, default=1)
-    ap.add_argument("--degree", type=int, default=3)
+    ap.add_argument("--degree", type=int, default=2)
     ap.add_argument("--ratio", type=float, default=20.0)
     ap.add_argument("--gmres-max-it", type=int, default=200)
     ap.add_argument("--quiet", action="store_true")
