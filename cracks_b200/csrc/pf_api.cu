@@ -22,6 +22,7 @@
 #include "pf_common.cuh"
 #include "pf_generic.cuh"
 #include "pf_multigrid.cuh"
+#include "pf_residual3d.cuh"
 #include "pf_vector.cuh"
 
 using namespace pf;
@@ -546,8 +547,23 @@ residual_dev (pf_ctx *ctx, double *l2)
     }
   else
     {
-      k_residual_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-        g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
+      if (g_force_generic)
+        k_residual_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+          g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
+      else
+        {
+          using TR = TileR3<16, 4, 1>;
+          const int tiles_x = (g.n[0] + 15) / 16, tiles_y = (g.n[1] + 3) / 4, tiles_z = g.cell_end - g.cell_begin;
+          static bool attr_set = false;
+          if (!attr_set)
+            {
+              CU (cudaFuncSetAttribute (k_residual3d<16, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int) TR::smem_bytes));
+              attr_set = true;
+            }
+          k_residual3d<16, 4, 1, 2><<<(unsigned) tiles_x * tiles_y * tiles_z, TR::NT, TR::smem_bytes, ctx->stream>>> (
+            g, ctx->p, ctx->k3, tiles_x, tiles_y, ctx->sol, ctx->pt, ctx->r_total);
+        }
       KCHECK ();
       k_residual_finish<3><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi,
                                                                         ctx->r_total, ctx->mask, ctx->r_pde,

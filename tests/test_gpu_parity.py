@@ -143,6 +143,13 @@ def test_residual_diag_energy(oracle, pf, dim, n, h):
     assert _relerr(ctx.to_nodal(r_tot), r_tot_ref) <= TOL
     assert _relerr(ctx.to_nodal(r_pde), r_pde_ref) <= TOL
     assert nrm == pytest.approx(np.linalg.norm(r_pde_ref), rel=1e-12)
+    # 3-D has a tiled residual kernel; the generic one is the independent second implementation
+    ctx.lib.pf_debug_force_generic(1)
+    try:
+        r_pde2, r_tot2, nrm2 = ctx.residual()
+    finally:
+        ctx.lib.pf_debug_force_generic(0)
+    assert _relerr(ctx.to_nodal(r_tot2), r_tot_ref) <= TOL and nrm2 == pytest.approx(nrm, rel=1e-12)
     ctx.setup_jacobian()
     d_ref = prob.jacobian(sol, old, oo, None).diagonal()
     assert np.all(d_ref > 0)
