@@ -100,7 +100,9 @@ struct pf_ctx
   int use_old_timestep_pf = 0;
   int device = 0, rank = 0, nranks = 1;
   int own_cell_begin = 0, own_cell_end = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
+  int range_begin = -1, range_end = -1; // cell-layer sub-range override for the tiled apply (halo overlap)
   ncclComm_t comm = nullptr;
   long long n_local_dofs = 0, owned_lo = 0, owned_hi = 0; // node ranges (local indices)
   // device state
@@ -242,10 +244,11 @@ update_phys (pf_ctx *c)
 
 // ghost planes of a local nodal vector <- owners (ncomp doubles per node)
 int
-halo_exchange (pf_ctx *ctx, double *v, int ncomp)
+halo_exchange (pf_ctx *ctx, double *v, int ncomp, cudaStream_t on = nullptr)
 {
   if (ctx->nranks == 1)
     return PF_OK;
+  const cudaStream_t st = on ? on : ctx->stream;
   const Grid &g = ctx->g;
   const size_t cnt = (size_t) g.nodes_per_plane * ncomp;
   auto plane = [&](int gp) { return v + (size_t) (gp - g.plane_begin) * cnt; };
@@ -253,13 +256,13 @@ halo_exchange (pf_ctx *ctx, double *v, int ncomp)
   if (ctx->rank > 0)
     {
       // lower ghost = plane_begin (owned by rank-1); send my first owned plane down
-      NC_ (g_nccl.Recv (plane (g.plane_begin), cnt, ncclFloat64, ctx->rank - 1, ctx->comm, ctx->stream));
-      NC_ (g_nccl.Send (plane (g.owned_begin), cnt, ncclFloat64, ctx->rank - 1, ctx->comm, ctx->stream));
+      NC_ (g_nccl.Recv (plane (g.plane_begin), cnt, ncclFloat64, ctx->rank - 1, ctx->comm, st));
+      NC_ (g_nccl.Send (plane (g.owned_begin), cnt, ncclFloat64, ctx->rank - 1, ctx->comm, st));
     }
   if (ctx->rank < ctx->nranks - 1)
     {
-      NC_ (g_nccl.Recv (plane (g.plane_end - 1), cnt, ncclFloat64, ctx->rank + 1, ctx->comm, ctx->stream));
-      NC_ (g_nccl.Send (plane (g.owned_end - 1), cnt, ncclFloat64, ctx->rank + 1, ctx->comm, ctx->stream));
+      NC_ (g_nccl.Recv (plane (g.plane_end - 1), cnt, ncclFloat64, ctx->rank + 1, ctx->comm, st));
+      NC_ (g_nccl.Send (plane (g.owned_end - 1), cnt, ncclFloat64, ctx->rank + 1, ctx->comm, st));
     }
   NC_ (g_nccl.GroupEnd ());
   return PF_OK;
@@ -368,7 +371,12 @@ int
 launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
 {
   using T = Tile3v2<TX, TY, TZ>;
-  const Grid &g = ctx->g;
+  Grid g = ctx->g;
+  if (ctx->range_begin >= 0)
+    {
+      g.cell_begin = ctx->range_begin;
+      g.cell_end = ctx->range_end;
+    }
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
   static bool attr_set = false;
@@ -461,11 +469,27 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
 {
   if (!ctx->jac_ready)
     return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must be called before applying the Jacobian");
-  int rc = halo_exchange (ctx, x, ctx->nc);
-  if (rc)
-    return rc;
+  int rc;
   const Grid &g = ctx->g;
   const long long nl = g.n_local_nodes;
+  // Multi-rank 3-D: the halo exchange of x runs on its own stream while the
+  // cell layers that do not touch a ghost plane are evaluated; the (at most
+  // two) boundary layers follow once the planes have arrived.
+  const int lo_b = g.cell_begin + (ctx->rank > 0 ? 1 : 0);
+  const int hi_b = g.cell_end - (ctx->rank < ctx->nranks - 1 ? 1 : 0);
+  static const bool no_overlap = getenv ("PF_NO_OVERLAP") != nullptr; // A/B switch for measurements
+  const bool overlap = !no_overlap && ctx->nranks > 1 && ctx->dim == 3 && !g_force_generic
+                       && (approx || g_apply_variant == 3) && hi_b > lo_b;
+  if (overlap)
+    {
+      CU (cudaEventRecord (ctx->ev_x, ctx->stream));
+      CU (cudaStreamWaitEvent (ctx->comm_stream, ctx->ev_x, 0));
+      if ((rc = halo_exchange (ctx, x, ctx->nc, ctx->comm_stream)))
+        return rc;
+      CU (cudaEventRecord (ctx->ev_halo, ctx->comm_stream));
+    }
+  else if ((rc = halo_exchange (ctx, x, ctx->nc)))
+    return rc;
   if (ctx->dim == 2)
     {
       k_apply_init<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
@@ -492,6 +516,30 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
               CU (cudaEventCreate (&e0));
               CU (cudaEventCreate (&e1));
               CU (cudaEventRecord (e0, ctx->stream));
+            }
+          if (overlap)
+            {
+              auto run = [&](int c0, int c1) -> int {
+                ctx->range_begin = c0;
+                ctx->range_end = c1;
+                const int r = approx ? launch_apply3d_v2<16, 4, 1, 2, 2> (ctx, x, y)
+                                     : launch_apply3d_v2<16, 4, 1> (ctx, x, y);
+                ctx->range_begin = ctx->range_end = -1;
+                return r;
+              };
+              if ((rc = run (lo_b, hi_b)))
+                return rc;
+              CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
+              if (ctx->rank > 0 && (rc = run (g.cell_begin, lo_b)))
+                return rc;
+              if (ctx->rank < ctx->nranks - 1 && (rc = run (hi_b, g.cell_end)))
+                return rc;
+              if (ctx->profiling)
+                {
+                  CU (cudaEventRecord (e1, ctx->stream));
+                  ctx->prof_events.emplace_back (e0, e1);
+                }
+              return PF_OK;
             }
           if (approx)
             {
@@ -878,6 +926,9 @@ pf_create (const pf_mesh *mesh, const pf_params *params, int device, int rank, i
   ctx->prm = *params;
   CU (cudaSetDevice (device));
   CU (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
+  CU (cudaStreamCreateWithFlags (&ctx->comm_stream, cudaStreamNonBlocking));
+  CU (cudaEventCreateWithFlags (&ctx->ev_x, cudaEventDisableTiming));
+  CU (cudaEventCreateWithFlags (&ctx->ev_halo, cudaEventDisableTiming));
 
   Grid &g = ctx->g;
   g.dim = dim;
@@ -1008,6 +1059,12 @@ pf_destroy (pf_ctx *ctx)
     cudaFreeHost (ctx->h_red);
   if (ctx->h_counts)
     cudaFreeHost (ctx->h_counts);
+  if (ctx->comm_stream)
+    cudaStreamDestroy (ctx->comm_stream);
+  if (ctx->ev_x)
+    cudaEventDestroy (ctx->ev_x);
+  if (ctx->ev_halo)
+    cudaEventDestroy (ctx->ev_halo);
   if (ctx->stream && ctx->owns_stream)
     cudaStreamDestroy (ctx->stream);
   delete ctx;
