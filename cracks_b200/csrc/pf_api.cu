@@ -102,6 +102,9 @@ struct pf_ctx
   int own_cell_begin = 0, own_cell_end = 0;
   cudaStream_t stream = nullptr, comm_stream = nullptr;
   cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_up[8] = {}, ev_done[8] = {};
+  double *stage2 = nullptr;
   int range_begin = -1, range_end = -1; // cell-layer sub-range override for the tiled apply (halo overlap)
   ncclComm_t comm = nullptr;
   long long n_local_dofs = 0, owned_lo = 0, owned_hi = 0; // node ranges (local indices)
@@ -848,6 +851,75 @@ diag_and_aux (pf_ctx *ctx)
   return PF_OK;
 }
 
+
+// Host-buffer apply (block layout in, block layout out) as a three-stage
+// pipeline over chunks of cell layers: PCIe upload of chunk c+1, permute +
+// operator on chunk c and PCIe download of the finished planes of chunk c-1
+// run concurrently on three streams.  Single rank, dim 3.
+int
+apply_host_pipelined (pf_ctx *ctx, const double *xh, double *yh)
+{
+  if (!ctx->jac_ready)
+    return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must be called before applying the Jacobian");
+  const Grid &g = ctx->g;
+  const long long npp = g.nodes_per_plane, nn = g.n_global_nodes;
+  const int layers = g.n[2];
+  const int n_chunks = std::min (8, layers / 2);
+  if (!ctx->h2d_stream)
+    {
+      CU (cudaStreamCreateWithFlags (&ctx->h2d_stream, cudaStreamNonBlocking));
+      CU (cudaStreamCreateWithFlags (&ctx->d2h_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 8; ++i)
+        {
+          CU (cudaEventCreateWithFlags (&ctx->ev_up[i], cudaEventDisableTiming));
+          CU (cudaEventCreateWithFlags (&ctx->ev_done[i], cudaEventDisableTiming));
+        }
+      CU (cudaMalloc (&ctx->stage2, sizeof (double) * ctx->n_local_dofs));
+    }
+  double *ub = ctx->stage, *pb = ctx->stage + nn * 3;     // upload staging, block layout
+  double *ub2 = ctx->stage2, *pb2 = ctx->stage2 + nn * 3; // download staging
+  double *x = ctx->xa, *y = ctx->ya;
+  // the upload stream must not overwrite staging still in use by earlier work on the compute stream
+  CU (cudaEventRecord (ctx->ev_x, ctx->stream));
+  CU (cudaStreamWaitEvent (ctx->h2d_stream, ctx->ev_x, 0));
+  CU (cudaStreamWaitEvent (ctx->d2h_stream, ctx->ev_x, 0));
+  int rc = PF_OK;
+  for (int c = 0; c < n_chunks; ++c)
+    {
+      const int c0 = (int) ((long long) layers * c / n_chunks), c1 = (int) ((long long) layers * (c + 1) / n_chunks);
+      // node planes first needed by this chunk: (c0, c1], plus plane 0 for the first chunk
+      const long long pa = c == 0 ? 0 : c0 + 1, pe = c1 + 1;
+      const long long na = pa * npp, cnt = (pe - pa) * npp;
+      CU (cudaMemcpyAsync (ub + na * 3, xh + na * 3, sizeof (double) * cnt * 3, cudaMemcpyHostToDevice, ctx->h2d_stream));
+      CU (cudaMemcpyAsync (pb + na, xh + nn * 3 + na, sizeof (double) * cnt, cudaMemcpyHostToDevice, ctx->h2d_stream));
+      CU (cudaEventRecord (ctx->ev_up[c], ctx->h2d_stream));
+      CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_up[c], 0));
+      k_block_to_nodal<3><<<nblk (cnt, 256), 256, 0, ctx->stream>>> (cnt, ub + na * 3, pb + na, x + na * 4);
+      KCHECK ();
+      k_apply_init<3><<<nblk (cnt, 256), 256, 0, ctx->stream>>> (cnt, x + na * 4, ctx->diag + na * 4, ctx->mask + na,
+                                                                 y + na * 4);
+      KCHECK ();
+      ctx->range_begin = c0;
+      ctx->range_end = c1;
+      rc = launch_apply3d_v2<16, 4, 1> (ctx, x, y);
+      ctx->range_begin = ctx->range_end = -1;
+      if (rc)
+        return rc;
+      // planes [c0, c1) are complete now (plane c1 still misses the next chunk), the last chunk completes c1 too
+      const long long qa = c0, qe = c == n_chunks - 1 ? c1 + 1 : c1;
+      const long long ma = qa * npp, mcnt = (qe - qa) * npp;
+      k_nodal_to_block<3><<<nblk (mcnt, 256), 256, 0, ctx->stream>>> (mcnt, y + ma * 4, ub2 + ma * 3, pb2 + ma);
+      KCHECK ();
+      CU (cudaEventRecord (ctx->ev_done[c], ctx->stream));
+      CU (cudaStreamWaitEvent (ctx->d2h_stream, ctx->ev_done[c], 0));
+      CU (cudaMemcpyAsync (yh + ma * 3, ub2 + ma * 3, sizeof (double) * mcnt * 3, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+      CU (cudaMemcpyAsync (yh + nn * 3 + ma, pb2 + ma, sizeof (double) * mcnt, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+  CU (cudaStreamSynchronize (ctx->d2h_stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  return PF_OK;
+}
+
 } // namespace
 
 // ===========================================================================
@@ -1061,6 +1133,17 @@ pf_destroy (pf_ctx *ctx)
     cudaFreeHost (ctx->h_counts);
   if (ctx->comm_stream)
     cudaStreamDestroy (ctx->comm_stream);
+  if (ctx->h2d_stream)
+    {
+      cudaStreamDestroy (ctx->h2d_stream);
+      cudaStreamDestroy (ctx->d2h_stream);
+      for (int i = 0; i < 8; ++i)
+        {
+          cudaEventDestroy (ctx->ev_up[i]);
+          cudaEventDestroy (ctx->ev_done[i]);
+        }
+      cudaFree (ctx->stage2);
+    }
   if (ctx->ev_x)
     cudaEventDestroy (ctx->ev_x);
   if (ctx->ev_halo)
@@ -1282,8 +1365,10 @@ pf_apply_jacobian (pf_ctx *ctx, const double *x, double *y)
   if (!ctx || !x || !y)
     return PF_BAD_ARG;
   CU (cudaSetDevice (ctx->device));
-  int rc = upload_block (ctx, x, ctx->xa);
-  if (rc)
+  int rc;
+  if (ctx->dim == 3 && ctx->nranks == 1 && !g_force_generic && g_apply_variant == 3 && ctx->g.n[2] >= 16)
+    return apply_host_pipelined (ctx, x, y);
+  if ((rc = upload_block (ctx, x, ctx->xa)))
     return rc;
   if ((rc = apply_dev (ctx, ctx->xa, ctx->ya)))
     return rc;

@@ -60,7 +60,8 @@ CASES_3D = [((10, 10, 10), (2.0, 2.0, 2.0)),      # the KAT-1 mesh
             ((16, 4, 2), (0.5, 0.5, 0.5)),        # exactly one tile
             ((19, 7, 5), (0.3, 0.45, 0.7)),       # ragged tiles, anisotropic cells
             ((1, 1, 1), (1.0, 1.0, 1.0)),         # a single cell
-            ((33, 9, 3), (0.25, 0.25, 0.25))]
+            ((33, 9, 3), (0.25, 0.25, 0.25)),
+            ((12, 6, 21), (0.4, 0.5, 0.3))]       # >= 16 layers: the host call takes the chunk-pipelined path
 
 
 @pytest.mark.parametrize("n,h", CASES_3D)
