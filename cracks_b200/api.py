@@ -90,6 +90,7 @@ _SIGS = {
     "pf_solve": [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_int)],
     "pf_energy": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "pf_tcv": [C.c_void_p, C.POINTER(C.c_double)],
+    "pf_cod": [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
     "pf_project_phase_field": [C.c_void_p],
     "pf_interpolate_sneddon": [C.c_void_p, C.c_double],
     "pf_advance_timestep": [C.c_void_p],
@@ -106,6 +107,7 @@ _SIGS = {
     "pf_host_alloc": [C.POINTER(C.c_void_p), C.c_size_t],
     "pf_host_free": [C.c_void_p],
     "pf_debug_force_generic": [C.c_int],
+    "pf_debug_disable_iso": [C.c_int],
     "pf_debug_set_variant": [C.c_int],
     "pf_profile_enable": [C.c_void_p, C.c_int],
     "pf_profile_read": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
@@ -356,6 +358,12 @@ class PhaseFieldContext:
         self._check(self.lib.pf_tcv(self.h, C.byref(t)))
         return t.value
 
+    def cod(self, eval_line: float):
+        """(value, n_faces) of compute_cod(eval_line), cracks.cc:3452-3549"""
+        v, nf = C.c_double(), C.c_int64()
+        self._check(self.lib.pf_cod(self.h, eval_line, C.byref(v), C.byref(nf)))
+        return v.value, nf.value
+
     def project_phase_field(self):
         self._check(self.lib.pf_project_phase_field(self.h))
 
@@ -494,6 +502,11 @@ class SneddonDriver:
             step_no += 1
             if diff < 1.0e-5:
                 self.tcv = c.tcv()
+                # compute_functional_values(), cracks.cc:3704-3725: x = -1.5 + i/256, i = 0..768
+                h0, x0 = c.mesh.h[0], c.mesh.origin[0]
+                on_plane = lambda x: abs((x - x0) / h0 - round((x - x0) / h0)) * h0 <= 1e-8
+                self.cod = [(x, v) for x in (-1.5 + i / 256.0 for i in range(3 * 256 + 1)) if on_plane(x)
+                            for v, nf in [c.cod(x)] if nf > 0]
                 break
             if step_no > self.max_steps:
                 break

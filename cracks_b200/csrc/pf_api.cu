@@ -369,6 +369,8 @@ launch_apply3d (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
+int g_no_iso = 0;
+
 template <int TX, int TY, int TZ, int MINB = 2, int NQ = 3>
 int
 launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
@@ -385,12 +387,21 @@ launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
   static bool attr_set = false;
   if (!attr_set)
     {
-      CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ, MINB, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ, MINB, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes));
+      CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ, MINB, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
       attr_set = true;
     }
-  k_apply3d_v2<TX, TY, TZ, MINB, NQ><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes, ctx->stream>>> (
-    g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  // cubic cells (every mesh the reference's 3-D cases use): gradient scales folded into constants
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
+  if (iso)
+    k_apply3d_v2<TX, TY, TZ, MINB, NQ, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  else
+    k_apply3d_v2<TX, TY, TZ, MINB, NQ, false><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
   KCHECK ();
   return PF_OK;
 }
@@ -1709,6 +1720,32 @@ pf_tcv (pf_ctx *ctx, double *tcv)
 }
 
 int
+pf_cod (pf_ctx *ctx, double eval_line, double *value, int64_t *n_faces)
+{
+  if (!ctx || !value)
+    return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
+  const Grid &g = ctx->g;
+  CU (cudaMemsetAsync (ctx->red, 0, 2 * sizeof (double), ctx->stream));
+  if (ctx->dim == 2)
+    k_cod_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (g, ctx->sol, eval_line, ctx->own_cell_begin,
+                                                                           ctx->own_cell_end, ctx->red);
+  else
+    k_cod_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (g, ctx->sol, eval_line, ctx->own_cell_begin,
+                                                                           ctx->own_cell_end, ctx->red);
+  KCHECK ();
+  int rc = allreduce_sum (ctx, ctx->red, 2);
+  if (rc)
+    return rc;
+  CU (cudaMemcpyAsync (ctx->h_red, ctx->red, 2 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  *value = ctx->h_red[0] / 2.0; // each face is visited from both neighbouring cells (cracks.cc:3537-3538)
+  if (n_faces)
+    *n_faces = (int64_t) std::llround (ctx->h_red[1]);
+  return PF_OK;
+}
+
+int
 pf_project_phase_field (pf_ctx *ctx)
 {
   if (!ctx)
@@ -1924,6 +1961,13 @@ pf_debug_set_variant (int variant)
   if (variant < 1 || variant > 15)
     return PF_BAD_ARG;
   g_apply_variant = variant;
+  return PF_OK;
+}
+
+int
+pf_debug_disable_iso (int on)
+{
+  g_no_iso = on;
   return PF_OK;
 }
 

@@ -35,7 +35,7 @@ template <int TX, int TY, int TZ> struct Tile3v2
 // points (plane -> row -> point) reading the staged arrays AZ / BZ, and adds
 // its nodal contributions to the shared y tile `ys`.  Contains block barriers:
 // must be called by all threads of the CTA.
-template <int TX, int TY, int TZ, int NQ = 3>
+template <int TX, int TY, int TZ, int NQ = 3, bool ISO = false>
 __device__ __forceinline__ void
 tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const int cx0, const int cy0,
                const int cz0, const double *__restrict__ AZ, const double *__restrict__ BZ,
@@ -55,8 +55,16 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
 
   const double omk = 1.0 - p.kappa;
   const double c_gce = p.G_c / p.eps;
-  const double c_gceps = p.G_c * p.eps;
-  const double two_mu = 2.0 * p.mu;
+  // ISO (hx == hy == hz): the 1/(4h) gradient scales of input and output sides are
+  // folded into the material constants instead of being applied per row / plane
+  const double gam = k.gu[0];
+  const double lamq = ISO ? p.lambda * gam * gam : p.lambda;
+  const double muq = ISO ? p.mu * gam * gam : p.mu;
+  const double p1g = ISO ? p.P1 * gam : p.P1;
+  const double vs = ISO ? 0.125 : 1.0; // 1/8 of the phi value weights, folded into a_val when ISO
+  const double c_gceps = ISO ? p.G_c * p.eps * 8.0 * gam * gam : p.G_c * p.eps;
+  const double two_mu = 2.0 * muq;
+  const double ca1 = 2.0 * omk * vs, ca2 = 2.0 * p1g * vs, ca3 = omk * vs, ca4 = c_gce * vs;
   const double es[3] = {-S, CEN ? 0.0 : S, S};
 
 #pragma unroll 1
@@ -93,9 +101,9 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                   if (f < 7)
                     {
                       const double gys = (f == 3) ? k.gp[1] : k.gu[1];
-                      dx[f] = RxB[f] * ((f == 3) ? k.gp[0] : k.gu[0]);
-                      PxDy[f] = (r0 + r1) * gys;
-                      RxDy[f] = (r1 - r0) * gys;
+                      dx[f] = ISO ? RxB[f] : RxB[f] * ((f == 3) ? k.gp[0] : k.gu[0]);
+                      PxDy[f] = ISO ? r0 + r1 : (r0 + r1) * gys;
+                      RxDy[f] = ISO ? r1 - r0 : (r1 - r0) * gys;
                       const double z0 = BZ[(f * NQ + qy) * NXC + it0], z1 = BZ[(f * NQ + qy) * NXC + it0 + 1];
                       PxBz[f] = z0 + z1;
                       RxBz[f] = z1 - z0;
@@ -138,15 +146,14 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                   const double u01 = U[0][1] + U[1][0], u02 = U[0][2] + U[2][0], u12 = U[1][2] + U[2][1];
                   const double ddot = fma (U[0][0], G[0][0], fma (U[1][1], G[1][1], U[2][2] * G[2][2]));
                   const double odot = fma (u01, o01, fma (u02, o02, u12 * o12));
-                  const double spG = fma (p.lambda * trU, trG, two_mu * fma (0.5, odot, ddot));
+                  const double spG = fma (lamq * trU, trG, two_mu * fma (0.5, odot, ddot));
                   const double dd2 = fma (U[0][0], U[0][0], fma (U[1][1], U[1][1], U[2][2] * U[2][2]));
                   const double od2 = fma (u01, u01, fma (u02, u02, u12 * u12));
-                  const double spE = fma (p.lambda * trU, trU, two_mu * fma (0.5, od2, dd2));
-                  const double a_val = pf * (2.0 * omk * spG - 2.0 * p.P1 * trG)
-                                       + dphi * (fma (omk, spE, c_gce) - 2.0 * p.P1 * trU);
+                  const double spE = fma (lamq * trU, trU, two_mu * fma (0.5, od2, dd2));
+                  const double a_val = pf * (ca1 * spG - ca2 * trG) + dphi * (fma (ca3, spE, ca4) - ca2 * trU);
                   const double w = CEN ? k.wvol * k.wq[qx] * k.wq[qy] * k.wq[qz] : k.wvol;
                   const double wg = w * gdeg;
-                  const double wgl = wg * p.lambda * trG, wgm = wg * p.mu, wg2m = wg * two_mu;
+                  const double wgl = wg * lamq * trG, wgm = wg * muq, wg2m = wg * two_mu;
                   const double S00 = fma (wg2m, G[0][0], wgl), S11 = fma (wg2m, G[1][1], wgl),
                                S22 = fma (wg2m, G[2][2], wgl);
                   const double S01 = wgm * o01, S02 = wgm * o02, S12 = wgm * o12;
@@ -174,7 +181,7 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
               for (int c = 0; c < 4; ++c)
                 {
                   const double gxs = (c == 3) ? k.gp[0] : k.gu[0];
-                  const double xv = XS[c] * gxs;
+                  const double xv = ISO ? XS[c] : XS[c] * gxs;
                   double v0 = -xv, v1 = xv;
                   if (c == 3)
                     {
@@ -218,11 +225,13 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
                     {
                       const double gys = (c == 3) ? k.gp[1] : k.gu[1];
                       const double gzs = (c == 3) ? k.gp[2] : k.gu[2];
-                      const double yv = (vx == 0 ? YP[c] - YR[c] : YP[c] + YR[c]) * gys;
+                      const double yv0 = vx == 0 ? YP[c] - YR[c] : YP[c] + YR[c];
+                      const double yv = ISO ? yv0 : yv0 * gys;
                       const double a = (vy == 0) ? VP[c][vx] - VR[c][vx] - yv : VP[c][vx] + VR[c][vx] + yv;
-                      const double d = ((vy == 0) ? DP[c][vx] - DR[c][vx] : DP[c][vx] + DR[c][vx]) * gzs;
-                      const double sc = (c == 3) ? 0.125 : 1.0;
-                      val[c] = (vz == 0) ? sc * (fma (-ez, a, a) - d) : sc * (fma (ez, a, a) + d);
+                      const double d0 = (vy == 0) ? DP[c][vx] - DR[c][vx] : DP[c][vx] + DR[c][vx];
+                      const double d = ISO ? d0 : d0 * gzs;
+                      const double v = (vz == 0) ? fma (-ez, a, a) - d : fma (ez, a, a) + d;
+                      val[c] = (c == 3 && !ISO) ? 0.125 * v : v;
                     }
                   const int n0 = nbase + vx + T::SY * vy + T::SZ * vz;
                   if (valid)
@@ -243,7 +252,7 @@ tile_cells_v2 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
 
 }
 
-template <int TX, int TY, int TZ, int MINB, int NQ = 3>
+template <int TX, int TY, int TZ, int MINB, int NQ = 3, bool ISO = false>
 __global__ void __launch_bounds__ (TX * TY * TZ, MINB)
 k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
               const double *__restrict__ x, const double *__restrict__ sol,
@@ -308,7 +317,7 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
           if (NQ == 3)
             AZ[(2 * 9 + f) * NC2 + i] = fma (S, r, s);
           if (f < 7)
-            DZ[f * NC2 + i] = r * ((f == 3) ? k.gp[2] : k.gu[2]);
+            DZ[f * NC2 + i] = ISO ? r : r * ((f == 3) ? k.gp[2] : k.gu[2]);
         }
     }
   __syncthreads ();
@@ -333,7 +342,7 @@ k_apply3d_v2 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
     ys[i] = 0;
   __syncthreads ();
 
-  tile_cells_v2<TX, TY, TZ, NQ> (g, p, k, tid, cx0, cy0, cz0, AZ, BZ, ys);
+  tile_cells_v2<TX, TY, TZ, NQ, ISO> (g, p, k, tid, cx0, cy0, cz0, AZ, BZ, ys);
 
   // ---- flush the y tile ---------------------------------------------------------
   for (int i = tid; i < NN; i += NT)

@@ -382,4 +382,101 @@ k_functionals_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
     }
 }
 
+// ---- crack opening displacement on the plane x = eval_line, cracks.cc:3452-3549:
+// every cell face on that plane (visited from both sides; the caller halves the
+// sum), QGauss<dim-1>(3), sum of 0.5 u . grad(phi) JxW.  out2[0] += value,
+// out2[1] += number of faces.  Cells of layers [own_begin, own_end) only.
+template <int DIM>
+__global__ void __launch_bounds__ (128)
+k_cod_generic (Grid g, const double *__restrict__ sol, double eval_line, int own_begin, int own_end,
+               double *__restrict__ out2)
+{
+  constexpr int NC = DIM + 1, NV = 1 << DIM;
+  const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  double cod = 0, faces = 0;
+  bool active = lc < g.n_local_cells;
+  int cx = 0;
+  if (active)
+    {
+      long long per_layer = g.n[0];
+      if (DIM == 3)
+        per_layer *= g.n[1];
+      const int layer = (int) (lc / per_layer) + g.cell_begin;
+      active = layer >= own_begin && layer < own_end;
+      cx = (int) (lc % g.n[0]);
+    }
+  if (active)
+    {
+      const double gq = 0.5 * sqrt (3.0 / 5.0);
+      const double xi[3] = {0.5 - gq, 0.5, 0.5 + gq};
+      const double w[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+      for (int side = 0; side < 2; ++side)
+        {
+          const double fx = g.origin[0] + (cx + side) * g.h[0];
+          if (!(fx < eval_line + 1e-8 && fx > eval_line - 1e-8))
+            continue;
+          faces += 1.0;
+          long long node[NV];
+          cell_nodes<DIM> (g, lc, node);
+          double ls[NV][NC];
+          for (int v = 0; v < NV; ++v)
+            for (int c = 0; c < NC; ++c)
+              ls[v][c] = sol[node[v] * NC + c];
+          for (int qz = 0; qz < (DIM == 3 ? 3 : 1); ++qz)
+            for (int qy = 0; qy < 3; ++qy)
+              {
+                const double pt[3] = {(double) side, xi[qy], xi[qz]};
+                double JxW = g.h[1] * w[qy];
+                if (DIM == 3)
+                  JxW *= g.h[2] * w[qz];
+                double u[DIM], gpf[DIM];
+                for (int e = 0; e < DIM; ++e)
+                  u[e] = gpf[e] = 0;
+                for (int v = 0; v < NV; ++v)
+                  {
+                    double N = 1.0;
+                    for (int d = 0; d < DIM; ++d)
+                      N *= ((v >> d) & 1) ? pt[d] : 1.0 - pt[d];
+                    for (int e = 0; e < DIM; ++e)
+                      {
+                        double gr = 1.0;
+                        for (int d = 0; d < DIM; ++d)
+                          {
+                            const int b = (v >> d) & 1;
+                            gr *= (d == e) ? (b ? 1.0 : -1.0) / g.h[d] : (b ? pt[d] : 1.0 - pt[d]);
+                          }
+                        u[e] += N * ls[v][e];
+                        gpf[e] += gr * ls[v][DIM];
+                      }
+                  }
+                double dot = 0;
+                for (int e = 0; e < DIM; ++e)
+                  dot += u[e] * gpf[e];
+                cod += 0.5 * dot * JxW;
+              }
+        }
+    }
+  __shared__ double red[2][4];
+  for (int o = 16; o > 0; o >>= 1)
+    {
+      cod += __shfl_down_sync (0xffffffffu, cod, o);
+      faces += __shfl_down_sync (0xffffffffu, faces, o);
+    }
+  const int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0)
+    {
+      red[0][wi] = cod;
+      red[1][wi] = faces;
+    }
+  __syncthreads ();
+  if (threadIdx.x < 2)
+    {
+      double s = 0;
+      for (int i = 0; i < (int) (blockDim.x >> 5); ++i)
+        s += red[threadIdx.x][i];
+      if (s != 0.0)
+        atomicAdd (&out2[threadIdx.x], s);
+    }
+}
+
 } // namespace pf

@@ -368,6 +368,24 @@ FracturePhaseFieldProblem::run ()
           const double ref = dim_ == 2 ? 2.0 * p * l_0 * l_0 * (1.0 - nu * nu) * M_PI / E
                                        : 16.0 * p * l_0 * l_0 * l_0 * (1.0 - nu * nu) / E / 3.0;
           pcout_ << "TCV: value= " << tcv_ << " exact= " << ref << " error= " << std::abs (tcv_ - ref) << std::endl;
+          // compute_functional_values(), cracks.cc:3704-3725: COD on the lines x = -1.5 + i/256;
+          // lines that carry no mesh face print nothing (compute_cod returns -1e300 there)
+          const unsigned N = 16 * 16;
+          for (unsigned i = 0; i <= 3 * N; ++i)
+            {
+              const double x = -1.5 + i * (1.0 / N);
+              const double t = (x - mesh_.origin[0]) / mesh_.h[0];
+              if (std::abs (t - std::round (t)) * mesh_.h[0] > 1e-8)
+                continue;
+              double cod = 0;
+              int64_t n_faces = 0;
+              pf_check (ctx_, pf_cod (ctx_, x, &cod, &n_faces));
+              if (n_faces > 0)
+                {
+                  pcout_ << x << "  " << cod << std::endl;
+                  cod_.push_back ({x, cod});
+                }
+            }
           break; // n_refinement_cycles == 0
         }
     }

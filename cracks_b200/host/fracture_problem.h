@@ -43,6 +43,7 @@ public:
 
   const std::vector<StatisticsRow> &statistics () const { return statistics_; }
   double tcv () const { return tcv_; }
+  const std::vector<std::pair<double, double>> &cod () const { return cod_; }
   unsigned total_newton_iterations () const { return total_newton_its_; }
   unsigned total_linear_iterations () const { return total_linear_its_; }
   // knobs that are not part of the reference's .prm surface
@@ -80,6 +81,7 @@ private:
 
   std::vector<StatisticsRow> statistics_;
   double tcv_ = 0;
+  std::vector<std::pair<double, double>> cod_; // (x, COD(x)) lines of compute_functional_values
   unsigned total_newton_its_ = 0, total_linear_its_ = 0;
 };
 

@@ -178,6 +178,9 @@ int pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it);
 /* ---- functionals (parity metrics) --------------------------------------- */
 int pf_energy (pf_ctx *ctx, double *bulk, double *crack);   /* cracks.cc:3615-3701 */
 int pf_tcv (pf_ctx *ctx, double *tcv);                      /* cracks.cc:3553-3589 */
+/* compute_cod(eval_line), cracks.cc:3452-3549: 0.5 int u.grad(phi) over the mesh faces on the plane
+ * x = eval_line; n_faces = 0 means no mesh face lies on that plane (the reference returns -1e300). */
+int pf_cod (pf_ctx *ctx, double eval_line, double *value, int64_t *n_faces);
 int pf_project_phase_field (pf_ctx *ctx);                   /* cracks.cc:3109-3137 */
 int pf_interpolate_sneddon (pf_ctx *ctx, double h_diam);    /* InitialValuesSneddon, cracks.cc:381-406 */
 /* time-step bookkeeping on the device: oldold <- old <- sol (cracks.cc:4302-4303);
@@ -210,6 +213,8 @@ int pf_host_alloc (void **out, size_t bytes);
 int pf_host_free (void *p);
 /* testing aid: route the 3-D apply through the dimension-generic kernel */
 int pf_debug_force_generic (int on);
+/* testing aid: do not use the cubic-cell (isotropic scale) specialisation of the tiled apply */
+int pf_debug_disable_iso (int on);
 /* testing aid: select the generation of the tiled 3-D apply kernel (1 or 2, default 2) */
 int pf_debug_set_variant (int variant);
 

@@ -65,6 +65,8 @@ def lib():
             f = getattr(_LIB, f"pfo_energy_{d}"); f.restype = None
             f.argtypes = [MP, PP, dp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
             f = getattr(_LIB, f"pfo_tcv_{d}"); f.restype = C.c_double; f.argtypes = [MP, dp]
+            f = getattr(_LIB, f"pfo_cod_{d}"); f.restype = C.c_double
+            f.argtypes = [MP, dp, C.c_double, C.POINTER(C.c_long)]
             f = getattr(_LIB, f"pfo_active_set_{d}"); f.restype = C.c_long
             f.argtypes = [MP, C.c_double, dp, dp, dp, dp, C.c_void_p, u8, C.POINTER(C.c_long)]
             f = getattr(_LIB, f"pfo_spmv_{d}"); f.restype = None
@@ -180,6 +182,12 @@ class Problem:
     def tcv(self, sol):
         return getattr(lib(), f"pfo_tcv_{self.sfx}")(C.byref(self.mesh), sol)
 
+    def cod(self, sol, eval_line):
+        """(value, n_faces) of compute_cod(eval_line), cracks.cc:3452-3549"""
+        nf = C.c_long(0)
+        v = getattr(lib(), f"pfo_cod_{self.sfx}")(C.byref(self.mesh), sol, eval_line, C.byref(nf))
+        return v, nf.value
+
     def active_set(self, c_scale, r_total, mass, old, sol, cycle):
         act = np.zeros(self.n_nodes, dtype=np.uint8)
         ncyc = C.c_long(0)
@@ -293,6 +301,9 @@ class SneddonRun:
             step_no += 1
             if diff < 1.0e-5:
                 self.tcv = p.tcv(sol)
+                # compute_functional_values(): x = -1.5 + i/256, i = 0..768; lines without faces print nothing
+                self.cod = [(x, v) for x in (-1.5 + i / 256.0 for i in range(3 * 256 + 1))
+                            for v, nf in [p.cod(sol, x)] if nf > 0]
                 break
             if step_no > self.max_steps:
                 break

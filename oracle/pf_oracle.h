@@ -53,6 +53,7 @@ typedef struct
   void pfo_lumped_mass_##D (const pfo_mesh *, double *mass); \
   void pfo_energy_##D (const pfo_mesh *, const pfo_params *, const double *sol, double *bulk, double *crack); \
   double pfo_tcv_##D (const pfo_mesh *, const double *sol); \
+  double pfo_cod_##D (const pfo_mesh *, const double *sol, double eval_line, long *n_faces); \
   long pfo_active_set_##D (const pfo_mesh *, double c_scale, const double *r_total, const double *mass, \
                            const double *old, double *sol, const int *cycle, unsigned char *active, long *n_cycling); \
   void pfo_spmv_##D (long nrows, const long *rowptr, const int *col, const double *val, const double *x, double *y);

@@ -695,6 +695,76 @@ SUF (pfo_active_set) (const pfo_mesh * m, double c_scale, const double *r_total,
   return cnt;
 }
 
+/* ---- crack opening displacement on the plane x = eval_line,
+ * cracks.cc:3452-3549: over every cell face lying on that plane (visited from
+ * both neighbouring cells, hence the final / 2), QGauss<dim-1>(3),
+ * sum of 0.5 * u . grad(phi) * JxW.  *n_faces counts the visited faces. */
+double
+SUF (pfo_cod) (const pfo_mesh * m, const double *sol, double eval_line, long *n_faces)
+{
+  const double gq = 0.5 * sqrt (3.0 / 5.0);
+  const double xi[3] = { 0.5 - gq, 0.5, 0.5 + gq };
+  const double w[3] = { 5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0 };
+  const long ncell = SUF (n_cells) (m);
+  double cod = 0;
+  long faces = 0;
+  for (long c = 0; c < ncell; ++c)
+    {
+      const long cx = c % m->n[0];
+      for (int side = 0; side < 2; ++side)
+        {
+          const double fx = m->origin[0] + (cx + side) * m->h[0];
+          if (!(fx < eval_line + 1e-8 && fx > eval_line - 1e-8))
+            continue;
+          ++faces;
+          long nodes[NV];
+          double ls[NDPC];
+          SUF (cell_nodes) (m, c, nodes);
+          SUF (gather) (nodes, sol, ls);
+#if DIM == 3
+          for (int qz = 0; qz < 3; ++qz)
+#else
+          const int qz = 0;
+#endif
+            for (int qy = 0; qy < 3; ++qy)
+              {
+                const double pt[3] = { (double) side, xi[qy], xi[qz] };
+                double JxW = m->h[1] * w[qy];
+#if DIM == 3
+                JxW *= m->h[2] * w[qz];
+#endif
+                double u[DIM], gpf[DIM];
+                memset (u, 0, sizeof (u));
+                memset (gpf, 0, sizeof (gpf));
+                for (int v = 0; v < NV; ++v)
+                  {
+                    double N = 1.0;
+                    for (int d = 0; d < DIM; ++d)
+                      N *= ((v >> d) & 1) ? pt[d] : 1.0 - pt[d];
+                    for (int e = 0; e < DIM; ++e)
+                      {
+                        double gr = 1.0;
+                        for (int d = 0; d < DIM; ++d)
+                          {
+                            const int b = (v >> d) & 1;
+                            gr *= (d == e) ? (b ? 1.0 : -1.0) / m->h[d] : (b ? pt[d] : 1.0 - pt[d]);
+                          }
+                        u[e] += N * ls[v * NC + e];
+                        gpf[e] += gr * ls[v * NC + DIM];
+                      }
+                  }
+                double dot = 0;
+                for (int e = 0; e < DIM; ++e)
+                  dot += u[e] * gpf[e];
+                cod += 0.5 * dot * JxW;
+              }
+        }
+    }
+  if (n_faces)
+    *n_faces = faces;
+  return cod / 2.0;
+}
+
 void
 SUF (pfo_spmv) (long nrows, const long *rowptr, const int *col, const double *val,
                 const double *x, double *y)

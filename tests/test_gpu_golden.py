@@ -34,6 +34,8 @@ def test_sneddon_3d_golden(pf):
         assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-6)
     assert stats[0]["diff"] == pytest.approx(golden["timestep_difference_linfty"][0], rel=1e-5)
     assert drv.tcv == pytest.approx(golden["tcv"], rel=1e-5)
+    assert len(drv.cod) == 1 and drv.cod[0][0] == 0.0
+    assert drv.cod[0][1] == pytest.approx(golden["cod"][0][1], rel=1e-5)
     ctx.close()
 
 

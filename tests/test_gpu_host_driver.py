@@ -32,6 +32,7 @@ def test_cli_reproduces_golden_statistics(pf, tmp_path):
         assert float(row[4]) == pytest.approx(ref["bulk"], rel=1e-6)
     assert float(rows[0][4]) == pytest.approx(golden["statistics"][0]["bulk"], rel=1e-7)
     assert "TCV: value= 0.0399535" in r.stdout
+    assert "\n0  0.00441323\n" in r.stdout                      # the COD line of the golden output
 
 
 def test_cli_rejects_unsupported_cases(pf, tmp_path):

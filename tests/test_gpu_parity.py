@@ -82,6 +82,14 @@ def test_apply_jacobian_3d(oracle, pf, n, h):
         ctx.lib.pf_debug_force_generic(0)
     assert _relerr(ctx.to_nodal(y2), y_ref) <= TOL
     # the first-generation tiled kernel stays available for A/B measurements
+    # cubic cells use a specialisation with the gradient scales folded into constants
+    ctx.lib.pf_debug_disable_iso(1)
+    try:
+        y4 = np.zeros(prob.n_dofs)
+        ctx.vmult(y4, ctx.to_block(x))
+    finally:
+        ctx.lib.pf_debug_disable_iso(0)
+    assert _relerr(ctx.to_nodal(y4), y_ref) <= TOL
     # variant 1 = first-generation kernel, 3..7 = other tile shapes of v2
     # 12..15 = persistent TMA-fed kernel (v3)
     for variant in (1, 2, 4, 5, 6, 7, 12, 13, 14, 15):
@@ -160,6 +168,12 @@ def test_residual_diag_energy(oracle, pf, dim, n, h):
     assert b == pytest.approx(b_ref, rel=1e-12) and c == pytest.approx(c_ref, rel=1e-12)
     assert ctx.tcv() == pytest.approx(prob.tcv(sol), rel=1e-11, abs=1e-15)
     assert np.allclose(ctx.lumped_mass(), prob.lumped_mass(), rtol=1e-15)
+    # crack opening displacement on a mesh plane and off the mesh planes
+    x_plane = prob.lo[0] + prob.mesh.h[0] * (n[0] // 2)
+    v_ref, nf_ref = prob.cod(sol, x_plane)
+    v, nf = ctx.cod(x_plane)
+    assert nf == nf_ref and nf > 0 and v == pytest.approx(v_ref, rel=1e-11, abs=1e-16)
+    assert ctx.cod(x_plane + 0.37 * prob.mesh.h[0])[1] == 0
     ctx.close()
 
 

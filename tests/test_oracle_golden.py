@@ -62,6 +62,9 @@ def test_timestep_difference_and_tcv(run, golden):
     assert run.statistics[1]["diff"] == pytest.approx(golden["timestep_difference_linfty"][1], rel=2e-5)
     assert run.tcv == pytest.approx(golden["tcv"], rel=2e-6)
     assert run.statistics[0]["n_active"] == golden["final_active_set"][0]
+    # compute_functional_values prints one line on this mesh: "0  0.00441323" (output:100)
+    assert len(run.cod) == 1 and run.cod[0][0] == 0.0
+    assert run.cod[0][1] == pytest.approx(golden["cod"][0][1], rel=2e-6)
 
 
 def test_csr_matches_matrix_free(oracle):
