@@ -202,14 +202,18 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    nccl_id = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def fresh_nccl_id():
+        if world == 1:
+            return None
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.frombuffer(bytearray(pf.PhaseFieldContext.nccl_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().numpy().tobytes())
+        return bytes(idt.cpu().numpy().tobytes())
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nccl_id = fresh_nccl_id()
 
     mesh = pf.sneddon_mesh(3, args.refine)
     params = pf.sneddon_params(mesh)
@@ -298,6 +302,31 @@ def main():
     local_nodes = (lay.plane_end - lay.plane_begin) * lay.n_nodes_plane
     owned_nodes = (lay.owned_end - lay.owned_begin) * lay.n_nodes_plane
 
+    newton = None
+    if not args.no_newton:
+        # second half of BASELINE.json's metric: Newton-its/s of the device-resident
+        # active-set Newton loop (cracks.cc:2780-2994) on the same mesh (all ranks, same
+        # z-slab decomposition), real time steps 0..1 of parameters_sneddon_3d.prm from the
+        # interpolated initial condition
+        nctx = pf.PhaseFieldContext(mesh, params, device=local_rank, rank=rank, nranks=world, nccl_id=fresh_nccl_id())
+        drv = pf.SneddonDriver(nctx, pressure=lambda t: 1e-3, max_no_timesteps=1, newton_lower_bound=1e-7,
+                               max_newton=50, max_line_search=10, gmres_max_it=200)
+        barrier()
+        t0 = time.perf_counter()
+        nstats = drv.run(mesh_diameter(mesh))
+        nctx.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        newton = {"newton_its_per_s": drv.newton_its / dt, "newton_its": drv.newton_its,
+                  "linear_its": drv.lin_its, "time_steps": len(nstats), "wall_s": dt,
+                  "crack_energy": nstats[-1]["crack"], "bulk_energy": nstats[-1]["bulk"],
+                  "preconditioner": "matrix-free geometric multigrid V-cycle (z-slab levels, replicated below), "
+                                    "Chebyshev-Jacobi smoothing"}
+        nctx.close()
+
     if rank == 0:
         peak, peak_src = load_peaks()
         # algorithmic bytes of one launch of the dominant kernel on this rank
@@ -328,23 +357,8 @@ def main():
                          "kernel_share_of_step": kern_ms / ms_total, "algorithmic_bytes": b_alg, "peak_source": peak_src,
                          "note": "FP64-pipe bound: exact 27-point FP64 quadrature, no f64 tensor path (DESIGN.md)"},
         }
-        if world == 1 and not args.no_newton:
-            # second half of BASELINE.json's metric: Newton-its/s of the device-resident
-            # active-set Newton loop (cracks.cc:2780-2994) on the same mesh, real time
-            # steps 0..1 of parameters_sneddon_3d.prm from the interpolated initial condition
-            nctx = pf.PhaseFieldContext(mesh, params, device=local_rank)
-            drv = pf.SneddonDriver(nctx, pressure=lambda t: 1e-3, max_no_timesteps=1, newton_lower_bound=1e-7,
-                                   max_newton=50, max_line_search=10, gmres_max_it=200)
-            nctx.synchronize()
-            t0 = time.perf_counter()
-            nstats = drv.run(mesh_diameter(mesh))
-            nctx.synchronize()
-            dt = time.perf_counter() - t0
-            line["newton"] = {"newton_its_per_s": drv.newton_its / dt, "newton_its": drv.newton_its,
-                              "linear_its": drv.lin_its, "time_steps": len(nstats), "wall_s": dt,
-                              "crack_energy": nstats[-1]["crack"], "bulk_energy": nstats[-1]["bulk"],
-                              "preconditioner": "matrix-free geometric multigrid V-cycle, Chebyshev(3)-Jacobi"}
-            nctx.close()
+        if newton is not None:
+            line["newton"] = newton
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_sample(10, 2, refine=args.cpu_refine)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

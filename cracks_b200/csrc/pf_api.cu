@@ -19,6 +19,7 @@
 #include "pf_apply3d.cuh"
 #include "pf_apply3d_v2.cuh"
 #include "pf_apply3d_v3.cuh"
+#include "pf_apply3d_v4.cuh"
 #include "pf_common.cuh"
 #include "pf_generic.cuh"
 #include "pf_multigrid.cuh"
@@ -35,7 +36,7 @@ namespace {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat64 = 8, ncclUint64 = 5 };
+enum { ncclFloat64 = 8, ncclUint64 = 5, ncclUint8 = 1 };
 enum { ncclSum = 0, ncclMax = 2 };
 struct NcclApi
 {
@@ -126,9 +127,12 @@ struct pf_ctx
   int krylov_m = 30;
   double *V = nullptr, *zvec = nullptr, *hdev = nullptr;
   bool jac_ready = false, have_r = false;
-  // multigrid preconditioner (single rank, dim 3): coarser level, work vectors, Chebyshev data
+  // multigrid preconditioner (dim 3): coarser level, work vectors, Chebyshev data.
+  // mg_mode of the level BELOW this one: 1 = same z-slab decomposition (shares the
+  // communicator), 2 = replicated on every rank (single-rank context, gathered by all-reduce)
   pf_ctx *coarse = nullptr;
-  bool owns_stream = true;
+  int mg_mode = 0;
+  bool owns_stream = true, owns_comm = true;
   int precond = 1;          // 0 = Jacobi, 1 = geometric multigrid V-cycle (falls back to Jacobi if unavailable)
   int cheb_degree = 2;
   int coarsest_degree = 16;
@@ -271,6 +275,30 @@ halo_exchange (pf_ctx *ctx, double *v, int ncomp, cudaStream_t on = nullptr)
   return PF_OK;
 }
 
+// same for a byte field (the constraint mask)
+int
+halo_exchange_bytes (pf_ctx *ctx, uint8_t *v)
+{
+  if (ctx->nranks == 1)
+    return PF_OK;
+  const Grid &g = ctx->g;
+  const size_t cnt = (size_t) g.nodes_per_plane;
+  auto plane = [&](int gp) { return v + (size_t) (gp - g.plane_begin) * cnt; };
+  NC_ (g_nccl.GroupStart ());
+  if (ctx->rank > 0)
+    {
+      NC_ (g_nccl.Recv (plane (g.plane_begin), cnt, ncclUint8, ctx->rank - 1, ctx->comm, ctx->stream));
+      NC_ (g_nccl.Send (plane (g.owned_begin), cnt, ncclUint8, ctx->rank - 1, ctx->comm, ctx->stream));
+    }
+  if (ctx->rank < ctx->nranks - 1)
+    {
+      NC_ (g_nccl.Recv (plane (g.plane_end - 1), cnt, ncclUint8, ctx->rank + 1, ctx->comm, ctx->stream));
+      NC_ (g_nccl.Send (plane (g.owned_end - 1), cnt, ncclUint8, ctx->rank + 1, ctx->comm, ctx->stream));
+    }
+  NC_ (g_nccl.GroupEnd ());
+  return PF_OK;
+}
+
 int
 allreduce_sum (pf_ctx *ctx, double *dev, int n)
 {
@@ -406,7 +434,51 @@ launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
-int g_apply_variant = 3;
+int g_apply_variant = getenv ("PF_APPLY_VARIANT") ? atoi (getenv ("PF_APPLY_VARIANT")) : 3;
+
+template <int TX, int TY, int TZ, int MINB = 2, int NQ = 3>
+int
+launch_apply3d_v4 (pf_ctx *ctx, const double *x, double *y)
+{
+  using T = Tile3v4<TX, TY, TZ>;
+  Grid g = ctx->g;
+  if (ctx->range_begin >= 0)
+    {
+      g.cell_begin = ctx->range_begin;
+      g.cell_end = ctx->range_end;
+    }
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+  const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  static bool attr_set = false;
+  if (!attr_set)
+    {
+      CU (cudaFuncSetAttribute (k_apply3d_v4<TX, TY, TZ, MINB, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes));
+      CU (cudaFuncSetAttribute (k_apply3d_v4<TX, TY, TZ, MINB, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes));
+      attr_set = true;
+    }
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
+  if (iso)
+    k_apply3d_v4<TX, TY, TZ, MINB, NQ, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  else
+    k_apply3d_v4<TX, TY, TZ, MINB, NQ, false><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  KCHECK ();
+  return PF_OK;
+}
+
+// the tiled kernel the library uses by default (exact 27-point rule, or the
+// 2-point rule of the preconditioner-only operator)
+int
+launch_tiled_default (pf_ctx *ctx, const double *x, double *y, bool approx)
+{
+  if (g_apply_variant == 16)
+    return approx ? launch_apply3d_v4<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v4<16, 4, 1> (ctx, x, y);
+  return approx ? launch_apply3d_v2<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v2<16, 4, 1> (ctx, x, y);
+}
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
 typedef CUresult (*pfn_encode_tiled) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -493,7 +565,7 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
   const int hi_b = g.cell_end - (ctx->rank < ctx->nranks - 1 ? 1 : 0);
   static const bool no_overlap = getenv ("PF_NO_OVERLAP") != nullptr; // A/B switch for measurements
   const bool overlap = !no_overlap && ctx->nranks > 1 && ctx->dim == 3 && !g_force_generic
-                       && (approx || g_apply_variant == 3) && hi_b > lo_b;
+                       && (approx || g_apply_variant == 3 || g_apply_variant == 16) && hi_b > lo_b;
   if (overlap)
     {
       CU (cudaEventRecord (ctx->ev_x, ctx->stream));
@@ -536,8 +608,7 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
               auto run = [&](int c0, int c1) -> int {
                 ctx->range_begin = c0;
                 ctx->range_end = c1;
-                const int r = approx ? launch_apply3d_v2<16, 4, 1, 2, 2> (ctx, x, y)
-                                     : launch_apply3d_v2<16, 4, 1> (ctx, x, y);
+                const int r = launch_tiled_default (ctx, x, y, approx);
                 ctx->range_begin = ctx->range_end = -1;
                 return r;
               };
@@ -557,7 +628,7 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
             }
           if (approx)
             {
-              rc = launch_apply3d_v2<16, 4, 1, 2, 2> (ctx, x, y);
+              rc = launch_tiled_default (ctx, x, y, true);
               if (rc)
                 return rc;
               return PF_OK;
@@ -578,6 +649,7 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
             case 13: rc = launch_apply3d_v3<16, 4, 2, 2> (ctx, x, y); break;
             case 14: rc = launch_apply3d_v3<16, 8, 1, 2> (ctx, x, y); break;
             case 15: rc = launch_apply3d_v3<32, 2, 1, 4> (ctx, x, y); break;
+            case 16: rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y); break;
             default: rc = launch_apply3d_v2<16, 4, 1> (ctx, x, y); break; // variant 3: fastest measured
             }
           if (rc)
@@ -658,6 +730,9 @@ norm2_dev (pf_ctx *ctx, const double *v, double *out)
   KCHECK ();
   k_reduce_partials<<<1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, 1, ctx->partial, ctx->red);
   KCHECK ();
+  int rc = allreduce_sum (ctx, ctx->red, 1);
+  if (rc)
+    return rc;
   CU (cudaMemcpyAsync (ctx->h_red, ctx->red, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
   CU (cudaStreamSynchronize (ctx->stream));
   *out = std::sqrt (ctx->h_red[0]);
@@ -667,13 +742,25 @@ norm2_dev (pf_ctx *ctx, const double *v, double *out)
 bool
 mg_possible (const pf_ctx *ctx)
 {
-  if (ctx->dim != 3 || ctx->nranks != 1)
+  if (ctx->dim != 3)
     return false;
   for (int d = 0; d < 3; ++d)
     if (ctx->g.n[d] % 2 != 0 || ctx->g.n[d] / 2 < 4)
       return false;
   return true;
 }
+
+// The level below keeps the z-slab decomposition while every rank's range of
+// cell layers stays aligned with the coarse cells (and at least 2 coarse
+// layers per rank remain); otherwise it is replicated on every rank.
+bool
+mg_coarse_distributed (const pf_ctx *ctx)
+{
+  return ctx->nranks > 1 && ctx->g.n[2] % (2 * ctx->nranks) == 0 && ctx->g.n[2] / (2 * ctx->nranks) >= 2;
+}
+
+int create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank, int nranks,
+                 const void *nccl_id, ncclComm_t shared_comm, pf_ctx **out);
 
 int diag_and_aux (pf_ctx *ctx);
 
@@ -726,7 +813,10 @@ mg_setup_level (pf_ctx *ctx)
           cm.h[d] = ctx->g.h[d] * 2.0;
           cm.origin[d] = ctx->g.origin[d];
         }
-      int rc = pf_create (&cm, &ctx->prm, ctx->device, 0, 1, nullptr, &ctx->coarse);
+      ctx->mg_mode = ctx->nranks == 1 ? 1 : (mg_coarse_distributed (ctx) ? 1 : 2);
+      int rc = ctx->mg_mode == 1 && ctx->nranks > 1
+                 ? create_impl (&cm, &ctx->prm, ctx->device, ctx->rank, ctx->nranks, nullptr, ctx->comm, &ctx->coarse)
+                 : create_impl (&cm, &ctx->prm, ctx->device, 0, 1, nullptr, nullptr, &ctx->coarse);
       if (rc)
         return fail (ctx, rc, "multigrid: cannot create the coarse level: %s", pf_last_error (ctx->coarse));
       cudaStreamDestroy (ctx->coarse->stream);
@@ -741,15 +831,46 @@ mg_setup_level (pf_ctx *ctx)
   c->cheb_ratio = ctx->cheb_ratio;
   c->mg_approx = ctx->mg_approx;
   c->coarsest_degree = ctx->coarsest_degree;
-  Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}}, df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}};
-  const long long ncn = c->g.n_local_nodes;
-  k_inject<4, double><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->sol, c->sol);
-  KCHECK ();
-  k_inject<1, double><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->pt, c->pt);
-  KCHECK ();
-  k_inject<1, uint8_t><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->mask, c->mask);
-  KCHECK ();
-  int rc = diag_and_aux (c);
+  Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}, c->g.plane_begin},
+    df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}, ctx->g.plane_begin};
+  int rc;
+  {
+    // coarse planes whose fine plane 2K this rank can read: all local fine planes when the
+    // coarse level keeps the decomposition (its missing upper ghost plane comes from the
+    // neighbour), the owned ones when it is replicated (every plane filled by exactly one rank)
+    const int fa = ctx->mg_mode == 2 ? ctx->g.owned_begin : ctx->g.plane_begin;
+    const int fe = ctx->mg_mode == 2 ? ctx->g.owned_end : ctx->g.plane_end;
+    const int Ka = std::max ((fa + 1) / 2, c->g.plane_begin), Ke = std::min ((fe - 1) / 2 + 1, c->g.plane_end);
+    const long long cnt = (long long) c->g.nodes_per_plane * std::max (Ke - Ka, 0);
+    if (ctx->mg_mode == 2)
+      {
+        CU (cudaMemsetAsync (c->sol, 0, sizeof (double) * c->n_local_dofs, ctx->stream));
+        CU (cudaMemsetAsync (c->pt, 0, sizeof (double) * c->g.n_local_nodes, ctx->stream));
+        CU (cudaMemsetAsync (c->mask, 0, (size_t) c->g.n_local_nodes, ctx->stream));
+      }
+    if (cnt > 0)
+      {
+        k_inject<4, double><<<nblk (cnt, 256), 256, 0, ctx->stream>>> (dc, df, Ka, Ke, ctx->sol, c->sol);
+        KCHECK ();
+        k_inject<1, double><<<nblk (cnt, 256), 256, 0, ctx->stream>>> (dc, df, Ka, Ke, ctx->pt, c->pt);
+        KCHECK ();
+        k_inject<1, uint8_t><<<nblk (cnt, 256), 256, 0, ctx->stream>>> (dc, df, Ka, Ke, ctx->mask, c->mask);
+        KCHECK ();
+      }
+    if (ctx->mg_mode == 2)
+      {
+        NC_ (g_nccl.AllReduce (c->sol, c->sol, (size_t) c->n_local_dofs, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+        NC_ (g_nccl.AllReduce (c->pt, c->pt, (size_t) c->g.n_local_nodes, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+        NC_ (g_nccl.AllReduce (c->mask, c->mask, (size_t) c->g.n_local_nodes, ncclUint8, ncclMax, ctx->comm, ctx->stream));
+      }
+    else if (c->nranks > 1)
+      {
+        if ((rc = halo_exchange (c, c->sol, 4)) || (rc = halo_exchange (c, c->pt, 1))
+            || (rc = halo_exchange_bytes (c, c->mask)))
+          return fail (ctx, rc, "multigrid: coarse halo: %s", pf_last_error (c));
+      }
+  }
+  rc = diag_and_aux (c);
   if (rc)
     return fail (ctx, rc, "multigrid: coarse diagonal: %s", pf_last_error (c));
   c->jac_ready = true;
@@ -817,12 +938,34 @@ mg_vcycle (pf_ctx *ctx, const double *b, double *x)
     return rc;
   k_sub<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, b, ctx->mg_y, ctx->mg_r);
   KCHECK ();
-  Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}}, df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}};
-  k_restrict<<<nblk (c->g.n_local_nodes, 128), 128, 0, ctx->stream>>> (dc, df, ctx->mg_r, ctx->mask, c->mask, c->mg_b);
-  KCHECK ();
+  Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}, c->g.plane_begin},
+    df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}, ctx->g.plane_begin};
+  {
+    // the restriction reads the fine residual one plane either side of an owned plane
+    if ((rc = halo_exchange (ctx, ctx->mg_r, 4)))
+      return rc;
+    int Ka = c->g.owned_begin, Ke = c->g.owned_end;
+    if (ctx->mg_mode == 2)
+      {
+        Ka = (ctx->g.owned_begin + 1) / 2;
+        Ke = (ctx->g.owned_end - 1) / 2 + 1;
+        CU (cudaMemsetAsync (c->mg_b, 0, sizeof (double) * c->n_local_dofs, ctx->stream));
+      }
+    const long long cnt = (long long) c->g.nodes_per_plane * std::max (Ke - Ka, 0);
+    if (cnt > 0)
+      {
+        k_restrict<<<nblk (cnt, 128), 128, 0, ctx->stream>>> (dc, df, Ka, Ke, ctx->mg_r, ctx->mask, c->mask, c->mg_b);
+        KCHECK ();
+      }
+    if (ctx->mg_mode == 2)
+      NC_ (g_nccl.AllReduce (c->mg_b, c->mg_b, (size_t) c->n_local_dofs, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+  }
   if ((rc = mg_vcycle (c, c->mg_b, c->mg_x)))
     return rc;
-  k_prolong_add<<<nblk (ctx->g.n_local_nodes, 256), 256, 0, ctx->stream>>> (dc, df, c->mg_x, ctx->mask, x);
+  if (c->nranks > 1 && (rc = halo_exchange (c, c->mg_x, 4)))
+    return rc;
+  k_prolong_add<<<nblk (ctx->g.n_local_nodes, 256), 256, 0, ctx->stream>>> (dc, df, ctx->g.plane_begin, ctx->g.plane_end,
+                                                                           c->mg_x, ctx->mask, x);
   KCHECK ();
   return mg_smooth (ctx, b, x, false, ctx->cheb_degree, ctx->cheb_ratio);
 }
@@ -912,7 +1055,7 @@ apply_host_pipelined (pf_ctx *ctx, const double *xh, double *yh)
       KCHECK ();
       ctx->range_begin = c0;
       ctx->range_end = c1;
-      rc = launch_apply3d_v2<16, 4, 1> (ctx, x, y);
+      rc = launch_tiled_default (ctx, x, y, false);
       ctx->range_begin = ctx->range_end = -1;
       if (rc)
         return rc;
@@ -989,6 +1132,17 @@ pf_nccl_unique_id (void *id128)
 int
 pf_create (const pf_mesh *mesh, const pf_params *params, int device, int rank, int nranks,
            const void *nccl_id, pf_ctx **out)
+{
+  return create_impl (mesh, params, device, rank, nranks, nccl_id, nullptr, out);
+}
+
+} // extern "C"
+
+namespace {
+// shared_comm != nullptr: a multigrid level that borrows its parent's communicator
+int
+create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank, int nranks,
+             const void *nccl_id, ncclComm_t shared_comm, pf_ctx **out)
 {
   if (!mesh || !params || !out || (mesh->dim != 2 && mesh->dim != 3) || nranks < 1 || rank < 0
       || rank >= nranks)
@@ -1102,7 +1256,12 @@ pf_create (const pf_mesh *mesh, const pf_params *params, int device, int rank, i
       k_lumped_mass<3><<<nblk (nn, 256), 256, 0, ctx->stream>>> (g, ctx->mass);
     }
   KCHECK ();
-  if (nranks > 1)
+  if (nranks > 1 && shared_comm)
+    {
+      ctx->comm = shared_comm;
+      ctx->owns_comm = false;
+    }
+  else if (nranks > 1)
     {
       if (!nccl_id)
         return fail (ctx, PF_BAD_ARG, "nranks > 1 needs an ncclUniqueId");
@@ -1115,6 +1274,9 @@ pf_create (const pf_mesh *mesh, const pf_params *params, int device, int rank, i
   CU (cudaStreamSynchronize (ctx->stream));
   return PF_OK;
 }
+} // namespace
+
+extern "C" {
 
 int
 pf_destroy (pf_ctx *ctx)
@@ -1124,10 +1286,10 @@ pf_destroy (pf_ctx *ctx)
   cudaSetDevice (ctx->device);
   if (ctx->stream)
     cudaStreamSynchronize (ctx->stream);
-  if (ctx->comm)
-    g_nccl.CommDestroy (ctx->comm);
   if (ctx->coarse)
     pf_destroy (ctx->coarse);
+  if (ctx->comm && ctx->owns_comm)
+    g_nccl.CommDestroy (ctx->comm);
   for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r})
     if (v)
       cudaFree (v);
@@ -1344,7 +1506,7 @@ pf_setup_jacobian (pf_ctx *ctx)
     return rc;
   ctx->jac_ready = true;
   ctx->mg_ready = false;
-  if (ctx->precond == 1 && ctx->dim == 3 && ctx->nranks == 1)
+  if (ctx->precond == 1 && ctx->dim == 3)
     return mg_setup_level (ctx);
   return PF_OK;
 }
@@ -1377,7 +1539,8 @@ pf_apply_jacobian (pf_ctx *ctx, const double *x, double *y)
     return PF_BAD_ARG;
   CU (cudaSetDevice (ctx->device));
   int rc;
-  if (ctx->dim == 3 && ctx->nranks == 1 && !g_force_generic && g_apply_variant == 3 && ctx->g.n[2] >= 16)
+  if (ctx->dim == 3 && ctx->nranks == 1 && !g_force_generic && (g_apply_variant == 3 || g_apply_variant == 16)
+      && ctx->g.n[2] >= 16)
     return apply_host_pipelined (ctx, x, y);
   if ((rc = upload_block (ctx, x, ctx->xa)))
     return rc;
@@ -1958,7 +2121,7 @@ pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count)
 int
 pf_debug_set_variant (int variant)
 {
-  if (variant < 1 || variant > 15)
+  if (variant < 1 || variant > 16)
     return PF_BAD_ARG;
   g_apply_variant = variant;
   return PF_OK;

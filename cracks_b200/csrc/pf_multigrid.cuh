@@ -13,25 +13,29 @@ namespace pf {
 
 struct Dims3
 {
-  int n[3]; // nodes per direction
+  int n[3]; // global nodes per direction
+  int kb;   // first node plane of the slowest coordinate held locally (z-slab decomposition)
 };
 
+// local index of global node (i,j,k); the caller guarantees that plane k is local
 __device__ __forceinline__ long long
 node_id (const Dims3 &d, int i, int j, int k)
 {
-  return i + (long long) d.n[0] * (j + (long long) d.n[1] * k);
+  return i + (long long) d.n[0] * (j + (long long) d.n[1] * (k - d.kb));
 }
 
 // coarse node (I,J,K) <- fine node (2I,2J,2K)
 template <int NCOMP, typename T>
 __global__ void
-k_inject (Dims3 dc, Dims3 df, const T *__restrict__ src, T *__restrict__ dst)
+k_inject (Dims3 dc, Dims3 df, int Ka, int Ke, const T *__restrict__ src, T *__restrict__ dst)
 {
-  const long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long) dc.n[0] * dc.n[1] * dc.n[2];
-  if (n >= total)
+  // coarse planes [Ka, Ke): the caller picks those whose fine plane 2K is local
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long) dc.n[0] * dc.n[1] * (Ke - Ka);
+  if (t >= total)
     return;
-  const int i = (int) (n % dc.n[0]), j = (int) ((n / dc.n[0]) % dc.n[1]), k = (int) (n / ((long long) dc.n[0] * dc.n[1]));
+  const int i = (int) (t % dc.n[0]), j = (int) ((t / dc.n[0]) % dc.n[1]), k = Ka + (int) (t / ((long long) dc.n[0] * dc.n[1]));
+  const long long n = node_id (dc, i, j, k);
   const long long f = node_id (df, 2 * i, 2 * j, 2 * k);
   for (int c = 0; c < NCOMP; ++c)
     dst[n * NCOMP + c] = src[f * NCOMP + c];
@@ -39,14 +43,16 @@ k_inject (Dims3 dc, Dims3 df, const T *__restrict__ src, T *__restrict__ dst)
 
 // xf += P xc (trilinear), constrained fine dofs receive nothing
 __global__ void
-k_prolong_add (Dims3 dc, Dims3 df, const double *__restrict__ xc, const uint8_t *__restrict__ fmask,
-               double *__restrict__ xf)
+k_prolong_add (Dims3 dc, Dims3 df, int ka, int ke, const double *__restrict__ xc,
+               const uint8_t *__restrict__ fmask, double *__restrict__ xf)
 {
-  const long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long) df.n[0] * df.n[1] * df.n[2];
-  if (n >= total)
+  // fine planes [ka, ke); the coarse planes k/2 and (k+1)/2 must be local
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long) df.n[0] * df.n[1] * (ke - ka);
+  if (t >= total)
     return;
-  const int i = (int) (n % df.n[0]), j = (int) ((n / df.n[0]) % df.n[1]), k = (int) (n / ((long long) df.n[0] * df.n[1]));
+  const int i = (int) (t % df.n[0]), j = (int) ((t / df.n[0]) % df.n[1]), k = ka + (int) (t / ((long long) df.n[0] * df.n[1]));
+  const long long n = node_id (df, i, j, k);
   const int i0 = i >> 1, j0 = j >> 1, k0 = k >> 1;
   const int ni = i & 1, nj = j & 1, nk = k & 1; // odd -> average of two coarse neighbours
   double acc[4] = {0, 0, 0, 0};
@@ -70,14 +76,16 @@ k_prolong_add (Dims3 dc, Dims3 df, const double *__restrict__ xc, const uint8_t 
 
 // rc = P^T rf with constrained fine rows treated as zero; constrained coarse rows get zero
 __global__ void
-k_restrict (Dims3 dc, Dims3 df, const double *__restrict__ rf, const uint8_t *__restrict__ fmask,
+k_restrict (Dims3 dc, Dims3 df, int Ka, int Ke, const double *__restrict__ rf, const uint8_t *__restrict__ fmask,
             const uint8_t *__restrict__ cmask, double *__restrict__ rc)
 {
-  const long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long) dc.n[0] * dc.n[1] * dc.n[2];
-  if (n >= total)
+  // coarse planes [Ka, Ke); the fine planes 2K-1 .. 2K+1 (where they exist) must be local
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long) dc.n[0] * dc.n[1] * (Ke - Ka);
+  if (t >= total)
     return;
-  const int I = (int) (n % dc.n[0]), J = (int) ((n / dc.n[0]) % dc.n[1]), K = (int) (n / ((long long) dc.n[0] * dc.n[1]));
+  const int I = (int) (t % dc.n[0]), J = (int) ((t / dc.n[0]) % dc.n[1]), K = Ka + (int) (t / ((long long) dc.n[0] * dc.n[1]));
+  const long long n = node_id (dc, I, J, K);
   double acc[4] = {0, 0, 0, 0};
   for (int dk = -1; dk <= 1; ++dk)
     for (int dj = -1; dj <= 1; ++dj)

@@ -98,8 +98,28 @@ def main():
             assert abs(got["bulk"] - ref["bulk"]) <= 1e-6 * ref["bulk"], (got, ref)
         assert abs(drv.tcv - golden["tcv"]) <= 1e-5 * golden["tcv"]
         print("KAT-1 on %d GPUs:" % world, [(s["bulk"], s["crack"]) for s in stats], "tcv", drv.tcv, flush=True)
-        print("MGPU_OK", flush=True)
     ctx.close()
+
+    # multigrid across ranks (z-slab levels 40 -> 20 -> 10, replicated 5^3 below): one time
+    # step at 2 refinements must converge like the single-GPU hierarchy and give its energies
+    mesh = pf.sneddon_mesh(3, 2)
+    ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh), device=local, rank=rank, nranks=world,
+                               nccl_id=None if world == 1 else _fresh_id(pf, dist, torch, rank))
+    drv = pf.SneddonDriver(ctx, pressure=lambda t: 1e-3, max_no_timesteps=0, newton_lower_bound=1e-7, gmres_max_it=60)
+    st = drv.run(mesh_diameter(mesh))[-1]
+    ctx.close()
+    if rank == 0:
+        ctx1 = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh), device=local)
+        drv1 = pf.SneddonDriver(ctx1, pressure=lambda t: 1e-3, max_no_timesteps=0, newton_lower_bound=1e-7, gmres_max_it=60)
+        st1 = drv1.run(mesh_diameter(mesh))[-1]
+        ctx1.close()
+        print("multigrid on %d ranks: newton %d linear %d | single GPU: newton %d linear %d | crack %.10e vs %.10e"
+              % (world, drv.newton_its, drv.lin_its, drv1.newton_its, drv1.lin_its, st["crack"], st1["crack"]), flush=True)
+        assert abs(st["crack"] - st1["crack"]) <= 1e-8 * st1["crack"], (st, st1)
+        assert abs(st["bulk"] - st1["bulk"]) <= 1e-6 * st1["bulk"], (st, st1)
+        assert drv.lin_its <= 1.5 * drv1.lin_its + 10, (drv.lin_its, drv1.lin_its)
+        print("MGPU_OK", flush=True)
+    dist.barrier()
     dist.destroy_process_group()
 
 
