@@ -134,8 +134,28 @@ def load_library():
         lib.pf_stream.restype = C.c_void_p
         lib.pf_launch_count.argtypes = [C.c_void_p]
         lib.pf_launch_count.restype = C.c_int64
-        _LIB = lib
+        _LIB = _TracedLib(lib) if os.environ.get("PF_PY_TRACE") else lib
     return _LIB
+
+
+class _TracedLib:
+    """Diagnostics (PF_PY_TRACE=1): host wall time and call count per C-ABI entry point."""
+
+    def __init__(self, lib):
+        self._lib, self.calls = lib, {}
+
+    def __getattr__(self, name):
+        import time
+        fn = getattr(self._lib, name)
+
+        def timed(*a):
+            t0 = time.perf_counter()
+            r = fn(*a)
+            e = self.calls.setdefault(name, [0, 0.0])
+            e[0] += 1
+            e[1] += time.perf_counter() - t0
+            return r
+        return timed
 
 
 def exported_symbols_in_header() -> list:
@@ -436,6 +456,14 @@ class SneddonDriver:
         self.newton_its = 0
         self.lin_its = 0
         self.tcv = None
+        self.phase_s = {}          # host wall time per phase of the Newton loop (diagnostics)
+
+    def _timed(self, name, fn, *a, **k):
+        import time as _t
+        t0 = _t.perf_counter()
+        r = fn(*a, **k)
+        self.phase_s[name] = self.phase_s.get(name, 0.0) + _t.perf_counter() - t0
+        return r
 
     def newton_active_set(self):
         c = self.ctx
@@ -449,16 +477,17 @@ class SneddonDriver:
         rows = []
         step = 0
         while True:
-            _, n_act, n_cyc, changed = c.active_set_update(10.0 * self.E, want_mask=False)
-            c.setup_jacobian()
-            c._check(c.lib.pf_residual(c.h, None, None, None))   # rhs with the new constraints (cracks.cc:2917-2918)
-            _, n_lin = c.solve(self.gmres_tol, self.gmres_max_it)
+            _, n_act, n_cyc, changed = self._timed("active_set", c.active_set_update, 10.0 * self.E, want_mask=False)
+            self._timed("setup_jacobian", c.setup_jacobian)
+            # rhs with the new constraints (cracks.cc:2917-2918)
+            self._timed("residual", lambda: c._check(c.lib.pf_residual(c.h, None, None, None)))
+            _, n_lin = self._timed("solve", c.solve, self.gmres_tol, self.gmres_max_it)
             c.save_solution()
             ls = 0
             new_res = 0.0
             while ls < self.max_ls:
                 c.update_solution(1.0)
-                _, _, new_res = c.residual(want_vectors=False)
+                _, _, new_res = self._timed("residual", c.residual, want_vectors=False)
                 if new_res < res:
                     break
                 c.restore_saved_solution()

@@ -6,7 +6,9 @@
 // redundant layer above, so the only data-path collective per operator
 // application is one halo exchange of two node planes of x (NCCL send/recv
 // over NVLink), and one small all-reduce per Krylov orthogonalisation.
+#include <chrono>
 #include <cmath>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -139,7 +141,8 @@ struct pf_ctx
   bool mg_approx = true;    // smoother / coarse operators use the 2-point Gauss rule (preconditioner only)
   double cheb_ratio = 20.0; // smoothing range lambda_max / lambda_min targeted by the smoother
   double lam_max = 0;
-  double *mg_b = nullptr, *mg_x = nullptr, *mg_y = nullptr, *mg_d = nullptr, *mg_r = nullptr;
+  double *mg_b = nullptr, *mg_x = nullptr, *mg_y = nullptr, *mg_d = nullptr, *mg_r = nullptr, *mg_ev = nullptr;
+  bool mg_ev_valid = false; // mg_ev holds the eigenvector estimate of the previous set-up
   bool mg_ready = false;
   double last_rnorm = 0;
   long long launches = 0;
@@ -193,6 +196,44 @@ fail (pf_ctx *c, int code, const char *fmt, ...)
                      cudaGetErrorString (e_));                                             \
     }                                                                                      \
   while (0)
+
+// PF_TRACE=1: synchronising host timers per labelled segment, printed by pf_destroy (diagnostics only)
+struct Trace
+{
+  bool on = getenv ("PF_TRACE") != nullptr;
+  std::map<std::string, std::pair<long, double>> acc;
+  std::chrono::steady_clock::time_point t0;
+  void begin (cudaStream_t st)
+  {
+    if (!on)
+      return;
+    cudaStreamSynchronize (st);
+    t0 = std::chrono::steady_clock::now ();
+  }
+  void mark (cudaStream_t st, const char *label)
+  {
+    if (!on)
+      return;
+    cudaStreamSynchronize (st);
+    const auto t1 = std::chrono::steady_clock::now ();
+    auto &e = acc[label];
+    e.first += 1;
+    const double dt = std::chrono::duration<double> (t1 - t0).count ();
+    e.second += dt;
+    if (dt > 2e-3)
+      fprintf (stderr, "[pf trace] slow %s #%ld: %.2f ms\n", label, e.first, dt * 1e3);
+    t0 = t1;
+  }
+  void dump (int rank)
+  {
+    if (!on || acc.empty ())
+      return;
+    for (auto &kv : acc)
+      fprintf (stderr, "[pf trace r%d] %-28s n=%6ld  %.4f s\n", rank, kv.first.c_str (), kv.second.first, kv.second.second);
+    acc.clear ();
+  }
+};
+Trace g_trace;
 
 inline unsigned
 nblk (long long n, int t)
@@ -434,7 +475,8 @@ launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
-int g_apply_variant = getenv ("PF_APPLY_VARIANT") ? atoi (getenv ("PF_APPLY_VARIANT")) : 3;
+// 16 = k_apply3d_v4<16,4,1> (default); 3 = k_apply3d_v2<16,4,1>; others: tuning variants kept for A/B runs
+int g_apply_variant = getenv ("PF_APPLY_VARIANT") ? atoi (getenv ("PF_APPLY_VARIANT")) : 16;
 
 template <int TX, int TY, int TZ, int MINB = 2, int NQ = 3>
 int
@@ -649,8 +691,8 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
             case 13: rc = launch_apply3d_v3<16, 4, 2, 2> (ctx, x, y); break;
             case 14: rc = launch_apply3d_v3<16, 8, 1, 2> (ctx, x, y); break;
             case 15: rc = launch_apply3d_v3<32, 2, 1, 4> (ctx, x, y); break;
-            case 16: rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y); break;
-            default: rc = launch_apply3d_v2<16, 4, 1> (ctx, x, y); break; // variant 3: fastest measured
+            case 3: rc = launch_apply3d_v2<16, 4, 1> (ctx, x, y); break;
+            default: rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y); break; // variant 16: fastest measured
             }
           if (rc)
             return rc;
@@ -669,6 +711,7 @@ residual_dev (pf_ctx *ctx, double *l2)
 {
   const Grid &g = ctx->g;
   const long long nl = g.n_local_nodes;
+  g_trace.begin (ctx->stream);
   CU (cudaMemsetAsync (ctx->r_total, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
   if (ctx->dim == 2)
     {
@@ -706,11 +749,14 @@ residual_dev (pf_ctx *ctx, double *l2)
   KCHECK ();
   k_reduce_partials<<<1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, 1, ctx->partial, ctx->red);
   KCHECK ();
+  g_trace.mark (ctx->stream, "residual:kernels");
   int rc = allreduce_sum (ctx, ctx->red, 1);
   if (rc)
     return rc;
+  g_trace.mark (ctx->stream, "residual:allreduce");
   CU (cudaMemcpyAsync (ctx->h_red, ctx->red, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
   CU (cudaStreamSynchronize (ctx->stream));
+  g_trace.mark (ctx->stream, "residual:d2h");
   ctx->last_rnorm = std::sqrt (ctx->h_red[0]);
   ctx->have_r = true;
   if (!std::isfinite (ctx->last_rnorm))
@@ -771,31 +817,55 @@ mg_setup_level (pf_ctx *ctx)
   const long long nd = ctx->n_local_dofs;
   if (!ctx->mg_b)
     {
-      double **vecs[] = {&ctx->mg_b, &ctx->mg_x, &ctx->mg_y, &ctx->mg_d, &ctx->mg_r};
+      double **vecs[] = {&ctx->mg_b, &ctx->mg_x, &ctx->mg_y, &ctx->mg_d, &ctx->mg_r, &ctx->mg_ev};
       for (double **v : vecs)
         CU (cudaMalloc (v, sizeof (double) * nd));
     }
-  // lambda_max of D^-1 J by a few power iterations (norm ratio)
+  // lambda_max of D^-1 J by power iterations.  The iterate stays on the device and is
+  // normalised there (one host read per level, not two per iteration); later Newton steps
+  // restart from the previous eigenvector estimate and need fewer iterations.
   {
-    double *v = ctx->mg_x, *w = ctx->mg_y;
-    k_fill_hash<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, v);
-    KCHECK ();
-    double lam = 1.0, nv = 0, nw = 0;
+    double *v = ctx->mg_ev, *w = ctx->mg_y;
+    const long long lo = ctx->owned_lo * ctx->nc, hi = ctx->owned_hi * ctx->nc;
     int rc;
-    for (int it = 0; it < 8; ++it)
+    auto norm2_to_red = [&](const double *u) -> int {
+      k_multi_dot<8><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (lo, hi, 0, 0, u, 0, u, 1, ctx->partial);
+      KCHECK ();
+      k_reduce_partials<<<1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, 1, ctx->partial, ctx->red);
+      KCHECK ();
+      return allreduce_sum (ctx, ctx->red, 1);
+    };
+    int n_it = 4;
+    if (!ctx->mg_ev_valid)
+      {
+        k_fill_hash<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, v);
+        KCHECK ();
+        n_it = 8;
+      }
+    if ((rc = norm2_to_red (v)))
+      return rc;
+    k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->red, 1.0, 1, v, v);
+    KCHECK ();
+    for (int it = 0; it < n_it; ++it)
       {
         if ((rc = apply_dev (ctx, v, w, ctx->mg_approx)))
           return rc;
         k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->diag, w, w);
         KCHECK ();
-        if ((rc = norm2_dev (ctx, v, &nv)) || (rc = norm2_dev (ctx, w, &nw)))
+        if ((rc = norm2_to_red (w)))
           return rc;
-        if (!(nv > 0) || !std::isfinite (nw))
-          return fail (ctx, PF_NUMERIC, "multigrid: power iteration broke down");
-        lam = nw / nv;
-        k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->red, 1.0 / nw, 0, w, v);
+        k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->red, 1.0, 1, w, v);
         KCHECK ();
       }
+    CU (cudaMemcpyAsync (ctx->h_red, ctx->red, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU (cudaStreamSynchronize (ctx->stream));
+    const double lam = std::sqrt (ctx->h_red[0]); // |D^-1 J v| with |v| = 1
+    if (!(lam > 0) || !std::isfinite (lam))
+      {
+        ctx->mg_ev_valid = false;
+        return fail (ctx, PF_NUMERIC, "multigrid: power iteration broke down");
+      }
+    ctx->mg_ev_valid = true;
     ctx->lam_max = 1.2 * lam;
   }
   if (!mg_possible (ctx))
@@ -1270,6 +1340,15 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
       ncclUniqueId id;
       memcpy (&id, nccl_id, sizeof id);
       NC_ (g_nccl.CommInitRank (&ctx->comm, nranks, id, rank));
+      // NCCL connects lazily: the first all-reduce and the first send/recv between two
+      // neighbours cost 0.3-0.8 s (measured).  Pay that here, not inside the first solve.
+      int rc;
+      if ((rc = allreduce_sum (ctx, ctx->red, 1)) || (rc = halo_exchange (ctx, ctx->zvec, ctx->nc))
+          || (rc = halo_exchange (ctx, ctx->zvec, ctx->nc, ctx->comm_stream)) || (rc = halo_exchange_bytes (ctx, ctx->mask)))
+        return rc;
+      NC_ (g_nccl.AllReduce (ctx->counts, ctx->counts, 3, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+      NC_ (g_nccl.AllReduce (ctx->stage8, ctx->stage8, 8, ncclUint8, ncclMax, ctx->comm, ctx->stream));
+      CU (cudaStreamSynchronize (ctx->comm_stream));
     }
   CU (cudaStreamSynchronize (ctx->stream));
   return PF_OK;
@@ -1286,11 +1365,13 @@ pf_destroy (pf_ctx *ctx)
   cudaSetDevice (ctx->device);
   if (ctx->stream)
     cudaStreamSynchronize (ctx->stream);
+  if (ctx->owns_stream)
+    g_trace.dump (ctx->rank);
   if (ctx->coarse)
     pf_destroy (ctx->coarse);
   if (ctx->comm && ctx->owns_comm)
     g_nccl.CommDestroy (ctx->comm);
-  for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r})
+  for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r, ctx->mg_ev})
     if (v)
       cudaFree (v);
   void *ptrs[] = {ctx->sol,   ctx->old,  ctx->oldold, ctx->pt,     ctx->diag,  ctx->mass, ctx->r_total,
@@ -1595,6 +1676,7 @@ pf_active_set_update (pf_ctx *ctx, double c, uint8_t *active_mask, int64_t *n_ac
     return fail (ctx, PF_BAD_ARG, "pf_active_set_update needs the r_total of a preceding pf_residual");
   CU (cudaSetDevice (ctx->device));
   const long long nl = ctx->g.n_local_nodes;
+  g_trace.begin (ctx->stream);
   CU (cudaMemsetAsync (ctx->counts, 0, 4 * sizeof (unsigned long long), ctx->stream));
   if (ctx->dim == 2)
     k_active_set<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi, c, ctx->r_total,
@@ -1605,13 +1687,16 @@ pf_active_set_update (pf_ctx *ctx, double c, uint8_t *active_mask, int64_t *n_ac
                                                              ctx->mass, ctx->old, ctx->sol, ctx->cycle,
                                                              ctx->mask, ctx->counts);
   KCHECK ();
+  g_trace.mark (ctx->stream, "active_set:kernel");
   if (ctx->nranks > 1)
     {
       NC_ (g_nccl.AllReduce (ctx->counts, ctx->counts, 3, ncclUint64, ncclSum, ctx->comm, ctx->stream));
+      g_trace.mark (ctx->stream, "active_set:allreduce");
       // ghost copies of phi and of the mask follow their owners
       int rc = halo_exchange (ctx, ctx->sol, ctx->nc);
       if (rc)
         return rc;
+      g_trace.mark (ctx->stream, "active_set:halo_sol");
       // the mask is one byte per node: exchange through the double staging path
       // is overkill; recompute is impossible (needs r_total), so send bytes.
       const Grid &g = ctx->g;
@@ -1629,6 +1714,7 @@ pf_active_set_update (pf_ctx *ctx, double c, uint8_t *active_mask, int64_t *n_ac
           NC_ (g_nccl.Send (plane (g.owned_end - 1), cnt, 1, ctx->rank + 1, ctx->comm, ctx->stream));
         }
       NC_ (g_nccl.GroupEnd ());
+      g_trace.mark (ctx->stream, "active_set:halo_mask");
     }
   CU (cudaMemcpyAsync (ctx->h_counts, ctx->counts, 4 * sizeof (unsigned long long), cudaMemcpyDeviceToHost,
                        ctx->stream));

@@ -24,7 +24,8 @@ _LIB = None
 
 
 class Mesh(C.Structure):
-    _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("h", C.c_double * 3), ("origin", C.c_double * 3)]
+    _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("h", C.c_double * 3), ("origin", C.c_double * 3),
+                ("slit", C.c_int)]
 
 
 class Params(C.Structure):
@@ -32,6 +33,7 @@ class Params(C.Structure):
         ("lam", C.c_double), ("mu", C.c_double), ("G_c", C.c_double), ("kappa", C.c_double),
         ("eps", C.c_double), ("pressure", C.c_double), ("alpha_biot", C.c_double),
         ("dt_old", C.c_double), ("dt_oldold", C.c_double), ("use_old_timestep_pf", C.c_int),
+        ("split", C.c_int), ("d_rhs", C.c_double), ("d_mat", C.c_double),
     ]
 
 
@@ -71,6 +73,15 @@ def lib():
             f.argtypes = [MP, C.c_double, dp, dp, dp, dp, C.c_void_p, u8, C.POINTER(C.c_long)]
             f = getattr(_LIB, f"pfo_spmv_{d}"); f.restype = None
             f.argtypes = [C.c_long, lp, ip, dp, dp, dp]
+            f = getattr(_LIB, f"pfo_n_nodes_{d}"); f.restype = C.c_long; f.argtypes = [MP]
+            f = getattr(_LIB, f"pfo_cell_nodes_{d}"); f.restype = None; f.argtypes = [MP, lp]
+            f = getattr(_LIB, f"pfo_node_coords_{d}"); f.restype = None; f.argtypes = [MP, dp]
+        _LIB.pfo_eigen_2x2.restype = None
+        _LIB.pfo_eigen_2x2.argtypes = [dp, C.POINTER(C.c_double), C.POINTER(C.c_double), dp]
+        _LIB.pfo_decompose_stress_2d.restype = None
+        _LIB.pfo_decompose_stress_2d.argtypes = [dp, dp, C.c_double, C.c_double, C.c_int, dp, dp]
+        _LIB.pfo_load_2d.restype = None
+        _LIB.pfo_load_2d.argtypes = [MP, PP, dp, dp]
         _LIB.pfo_num_threads.restype = C.c_int
     return _LIB
 
@@ -93,6 +104,9 @@ class Problem:
     pressure: float = 1e-3
     kappa_of_h: object = lambda h: 0.0
     eps_of_h: object = lambda h: 2.0 * h
+    slit: bool = False              # unit_slit.inp topology (2-D, Miehe tests)
+    lame: object = None             # (lambda, mu) given directly (Miehe prms, cracks.cc:1512-1521)
+    h_param: object = None          # h used for K reg / Eps reg if not the cell diameter (cracks.cc:3839-3854)
     mesh: Mesh = field(init=False)
     prm: Params = field(init=False)
 
@@ -106,16 +120,31 @@ class Problem:
         self.hdiam = math.sqrt(sum(self.mesh.h[d] ** 2 for d in range(self.dim)))  # cell->diameter()
         mu = self.E / (2.0 * (1 + self.nu))
         lam = (2 * self.nu * mu) / (1.0 - 2 * self.nu)
-        self.prm = Params(lam, mu, self.G_c, self.kappa_of_h(self.hdiam), self.eps_of_h(self.hdiam),
-                          self.pressure, 0.0, 1.0, 1.0, 0)
+        if self.lame is not None:
+            lam, mu = self.lame
+        self.mesh.slit = 1 if self.slit else 0
+        hp = self.hdiam if self.h_param is None else self.h_param
+        self.prm = Params(lam, mu, self.G_c, self.kappa_of_h(hp), self.eps_of_h(hp),
+                          self.pressure, 0.0, 1.0, 1.0, 0, 0, 0.0, 0.0)
         self.nc = self.dim + 1
         self.nnode_dir = tuple(self.n[d] + 1 for d in range(self.dim))
-        self.n_nodes = int(np.prod(self.nnode_dir))
+        self.sfx = f"{self.dim}d"
+        self.n_nodes = int(getattr(lib(), f"pfo_n_nodes_{self.sfx}")(C.byref(self.mesh)))
         self.n_dofs = self.n_nodes * self.nc
         self.sfx = f"{self.dim}d"
 
     # -- geometry ----------------------------------------------------------
+    def cells(self):
+        nv = 1 << self.dim
+        out = np.empty((int(np.prod(self.n[: self.dim])), nv), dtype=np.int64)
+        getattr(lib(), f"pfo_cell_nodes_{self.sfx}")(C.byref(self.mesh), out)
+        return out
+
     def node_coords(self):
+        if self.slit:
+            xyz = np.empty((self.n_nodes, self.dim))
+            getattr(lib(), f"pfo_node_coords_{self.sfx}")(C.byref(self.mesh), xyz)
+            return [np.ascontiguousarray(xyz[:, d]) for d in range(self.dim)]
         axes = [self.lo[d] + self.mesh.h[d] * np.arange(self.nnode_dir[d]) for d in range(self.dim)]
         grids = np.meshgrid(*axes[::-1], indexing="ij")[::-1]   # x fastest
         return [g.reshape(-1) for g in grids]
@@ -148,6 +177,17 @@ class Problem:
         return r_pde, r_tot
 
     def csr_pattern(self):
+        if not hasattr(self, "_pattern") and self.slit:
+            # node graph from the cell connectivity (the structured stencil does not know the slit)
+            import scipy.sparse as sp
+            cells, nv, nc = self.cells(), 1 << self.dim, self.nc
+            rows = np.repeat(cells, nv, axis=1).reshape(-1)
+            cols = np.tile(cells, (1, nv)).reshape(-1)
+            g = sp.coo_matrix((np.ones(rows.shape[0]), (rows, cols)), shape=(self.n_nodes,) * 2).tocsr()
+            g.sort_indices()
+            blk = sp.kron(g, np.ones((nc, nc)), format="csr")
+            blk.sort_indices()
+            self._pattern = (blk.indptr.astype(np.int64), blk.indices.astype(np.int32))
         if not hasattr(self, "_pattern"):
             nnz = getattr(lib(), f"pfo_csr_nnz_{self.sfx}")(C.byref(self.mesh))
             rowptr = np.empty(self.n_dofs + 1, dtype=np.int64); col = np.empty(nnz, dtype=np.int32)
@@ -187,6 +227,12 @@ class Problem:
         nf = C.c_long(0)
         v = getattr(lib(), f"pfo_cod_{self.sfx}")(C.byref(self.mesh), sol, eval_line, C.byref(nf))
         return v, nf.value
+
+    def load(self, sol):
+        """compute_load(), cracks.cc:3728-3816: (load_x, load_y) on boundary id 3"""
+        out = np.zeros(2)
+        lib().pfo_load_2d(C.byref(self.mesh), C.byref(self.prm), sol, out)
+        return out
 
     def active_set(self, c_scale, r_total, mass, old, sol, cycle):
         act = np.zeros(self.n_nodes, dtype=np.uint8)
@@ -307,6 +353,115 @@ class SneddonRun:
                 break
             if step_no > self.max_steps:
                 break
+        return self.statistics
+
+
+class MeshWouldRefine(Exception):
+    """refine_mesh() of the reference would change the mesh (cracks.cc:3971-3995, 4108-4133):
+    the uniform-mesh oracle stops here."""
+
+
+class MieheRun(SneddonRun):
+    """Time loop of the reference for `test case = miehe tension / miehe shear` on the
+    uniformly refined unit_slit.inp mesh (cracks.cc:4166-4581 with the Dirichlet data of
+    2584-2625, the load functional 3728-3816 and, for d_mat > 0, the stress split)."""
+
+    def __init__(self, test: str, refine: int, timestep, lam, mu, E, G_c=2.7, kappa_of_h=lambda h: 0.0,
+                 eps_of_h=lambda h: 2.0 * h, cycles=0, max_no_timesteps=24, timestep_2=None, switch_timestep=0,
+                 newton_lower_bound=1e-6, max_newton=100, max_line_search=10, line_search_damping=0.6,
+                 d_rhs=0.0, d_mat=0.0, refine_threshold=0.8):
+        assert test in ("miehe tension", "miehe shear")
+        n = 2 * 2 ** refine
+        # determine_mesh_dependent_parameters: h of the FINAL level (cracks.cc:3839-3854)
+        h_final = 0.5 * math.sqrt(2.0) * 2.0 ** (-(refine + cycles))
+        prob = Problem(2, (n, n), (0.0, 0.0), (1.0, 1.0), E=E, G_c=G_c, pressure=0.0, kappa_of_h=kappa_of_h,
+                       eps_of_h=eps_of_h, slit=True, lame=(lam, mu), h_param=h_final)
+        self.test, self.cycles, self.threshold = test, cycles, refine_threshold
+        self.h_final = h_final
+        self.d_rhs, self.d_mat = d_rhs, d_mat
+        self.dt2, self.switch = timestep_2, switch_timestep
+        self.p = prob
+        self.lower, self.max_newton = newton_lower_bound, max_newton
+        self.max_ls, self.damp = max_line_search, line_search_damping
+        self.dt, self.max_steps = timestep, max_no_timesteps
+        self.mass = prob.lumped_mass()
+        self.dirichlet, self._bc_nodes = self._dirichlet()
+        self.constrained = self.dirichlet.copy()
+        sol = np.zeros((prob.n_nodes, 3))
+        sol[:, 2] = 1.0                          # InitialValuesTensionOrShear, cracks.cc:679-691
+        self.solution = sol.reshape(-1)
+        self.statistics, self.logs = [], []
+
+    def _dirichlet(self):
+        """Constrained displacement dofs (cracks.cc:2584-2625) and the top-edge nodes."""
+        p = self.p
+        x, y = p.node_coords()
+        nreg = (p.n[0] + 1) * (p.n[1] + 1)
+        m = np.zeros((p.n_nodes, 3), dtype=np.uint8)
+        top, bottom = y == 1.0, y == 0.0
+        left, right = x == 0.0, x == 1.0
+        if self.test == "miehe tension":
+            m[bottom, 1] = 1                     # id 2: u_y = 0
+            m[top, 0] = m[top, 1] = 1            # id 3: u = (0, t)
+        else:
+            m[left, 1] = m[right, 1] = 1         # ids 0, 1: u_y = 0
+            m[bottom, 0] = m[bottom, 1] = 1      # id 2: u = 0
+            m[top, 0] = m[top, 1] = 1            # id 3: u = (-t, 0)
+            # id 4 = lower face of the slit: the original (not the doubled) nodes on y = 1/2, x >= 1/2
+            lower = (np.arange(p.n_nodes) < nreg) & (y == 0.5) & (x >= 0.5)
+            m[lower, 1] = 1
+        return m.reshape(-1), np.where(top)[0]
+
+    def set_initial_bc(self, time):
+        sol = self.solution.reshape(-1, 3)
+        con = self.dirichlet.reshape(-1, 3)
+        for c in range(2):
+            sol[con[:, c] == 1, c] = 0.0
+        if self.test == "miehe tension":
+            sol[self._bc_nodes, 1] = time        # BoundaryTensionTest, cracks.cc:780-797
+        else:
+            sol[self._bc_nodes, 0] = -time       # BoundaryShearTest, cracks.cc:845-861
+
+    def run(self):
+        p = self.p
+        sol = self.solution
+        self.oldold = sol.copy()
+        old = sol.copy()
+        dt = self.dt
+        dt_old = dt_oldold = dt
+        time, step_no = 0.0, 0
+        while step_no <= self.max_steps:
+            if self.switch > 0 and step_no > self.switch:
+                dt = self.dt2
+            tmp_dt = dt
+            dt_oldold, dt_old = dt_old, dt
+            self.oldold = old
+            old = sol.copy()
+            p.prm.dt_old, p.prm.dt_oldold = dt_old, dt_oldold
+            p.prm.use_old_timestep_pf = 0
+            p.prm.split = 1 if (self.d_mat > 0 and step_no > 0) else 0
+            p.prm.d_rhs, p.prm.d_mat = self.d_rhs, self.d_mat
+            time += dt
+            while True:
+                try:
+                    self.set_initial_bc(time)
+                    self.newton_active_set(old)
+                    break
+                except NoConvergence:
+                    sol[:] = old                 # time-step cut, cracks.cc:4333-4355
+                    time -= dt
+                    dt /= 10.0
+                    time += dt
+            phi = sol.reshape(-1, 3)[:, 2]
+            np.clip(phi, 0.0, 1.0, out=phi)
+            if self.cycles > 0 and phi.min() < self.threshold:
+                raise MeshWouldRefine(step_no)
+            dt = tmp_dt
+            bulk, crack = p.energy(sol)
+            load = p.load(sol)
+            self.statistics.append(dict(step=step_no, time=time, dofs=p.n_dofs, h=self.h_final, bulk=bulk, crack=crack,
+                                        load=float(load[1] if self.test == "miehe tension" else load[0])))
+            step_no += 1
         return self.statistics
 
 

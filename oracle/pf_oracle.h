@@ -27,6 +27,10 @@ typedef struct
   int n[3];         /* cells per direction (subdivided_hyper_rectangle + refine_global) */
   double h[3];      /* cell edge lengths */
   double origin[3]; /* lower corner */
+  int slit;         /* 2-D only: 1 = the unit_slit.inp topology (meshes/unit_slit.inp, cracks.cc:1202-1205):
+                       the nodes on the line y = origin + h*n[1]/2 with x-index > n[0]/2 are doubled; the cells
+                       above the line use the copies (appended after the regular nodes), the cells below the
+                       originals.  The two sides are not connected: that is the pre-existing crack. */
 } pfo_mesh;
 
 typedef struct
@@ -38,6 +42,8 @@ typedef struct
   double alpha_biot;       /* 0 in the reference (cracks.cc:1497) */
   double dt_old, dt_oldold;/* old_timestep, old_old_timestep */
   int use_old_timestep_pf; /* cracks.cc:2276 */
+  int split;               /* decompose_stress_matrix > 0 && timestep_number > 0 (cracks.cc:2294, 2338); 2-D only */
+  double d_rhs, d_mat;     /* decompose_stress_rhs / decompose_stress_matrix (cracks.cc:1568-1569) */
 } pfo_params;
 
 #define PFO_DECL(D) \
@@ -56,10 +62,19 @@ typedef struct
   double pfo_cod_##D (const pfo_mesh *, const double *sol, double eval_line, long *n_faces); \
   long pfo_active_set_##D (const pfo_mesh *, double c_scale, const double *r_total, const double *mass, \
                            const double *old, double *sol, const int *cycle, unsigned char *active, long *n_cycling); \
+  long pfo_n_nodes_##D (const pfo_mesh *); \
+  void pfo_cell_nodes_##D (const pfo_mesh *, long *cells /* [n_cells][2^dim] */); \
+  void pfo_node_coords_##D (const pfo_mesh *, double *xyz /* [n_nodes][dim] */); \
   void pfo_spmv_##D (long nrows, const long *rowptr, const int *col, const double *val, const double *x, double *y);
 
 PFO_DECL (2d)
 PFO_DECL (3d)
+
+/* 2-D only (the reference's split and load functional are 2-D, cracks.cc:1923-2120, 3728-3816) */
+void pfo_eigen_2x2 (const double *m /* row-major 2x2 */, double *ev1, double *ev2, double *P /* row-major */);
+void pfo_decompose_stress_2d (const double *E, const double *E_lin, double lambda, double mu, int derivative,
+                              double *s_plus, double *s_minus);
+void pfo_load_2d (const pfo_mesh *, const pfo_params *, const double *sol, double *load /* [2] */);
 
 int pfo_num_threads (void);
 

@@ -81,6 +81,10 @@ static inline long SUF (n_nodes) (const pfo_mesh * m)
   long n = 1;
   for (int d = 0; d < DIM; ++d)
     n *= (long) m->n[d] + 1;
+#if DIM == 2
+  if (m->slit)
+    n += m->n[0] / 2;           /* the doubled nodes of the slit, appended */
+#endif
   return n;
 }
 
@@ -114,7 +118,159 @@ static inline void SUF (cell_nodes) (const pfo_mesh * m, long c, long *nodes)
 #endif
       nodes[v] = id;
     }
+#if DIM == 2
+  /* unit_slit.inp (see pf_oracle.h): the row of cells above the slit line uses the doubled nodes */
+  if (m->slit && ci[1] == m->n[1] / 2)
+    for (int v = 0; v < 2; ++v)
+      {
+        const long ix = ci[0] + (v & 1);
+        if (ix > m->n[0] / 2)
+          nodes[v] = ((long) m->n[0] + 1) * ((long) m->n[1] + 1) + (ix - m->n[0] / 2 - 1);
+      }
+#endif
 }
+
+long
+SUF (pfo_n_nodes) (const pfo_mesh * m)
+{
+  return SUF (n_nodes) (m);
+}
+
+void
+SUF (pfo_cell_nodes) (const pfo_mesh * m, long *cells)
+{
+  const long ncell = SUF (n_cells) (m);
+  for (long c = 0; c < ncell; ++c)
+    SUF (cell_nodes) (m, c, cells + c * NV);
+}
+
+void
+SUF (pfo_node_coords) (const pfo_mesh * m, double *xyz)
+{
+  const long ncell = SUF (n_cells) (m);
+  for (long c = 0; c < ncell; ++c)
+    {
+      long nodes[NV], ci[3] = { 0, 0, 0 }, rem = c;
+      for (int d = 0; d < DIM; ++d)
+        {
+          ci[d] = rem % m->n[d];
+          rem /= m->n[d];
+        }
+      SUF (cell_nodes) (m, c, nodes);
+      for (int v = 0; v < NV; ++v)
+        for (int d = 0; d < DIM; ++d)
+          xyz[nodes[v] * DIM + d] = m->origin[d] + m->h[d] * (double) (ci[d] + ((v >> d) & 1));
+    }
+}
+
+#if DIM == 2
+/* ---- closed-form 2x2 symmetric eigen-decomposition, cracks.cc:1691-1737 ----
+ * P = [v1 v2] (columns).  The reference abort()s if the vectors are not
+ * orthogonal (1732-1736); here P is filled with NaN in that case. */
+void
+pfo_eigen_2x2 (const double *m, double *ev1, double *ev2, double *P)
+{
+  const double m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+  double v1[2], v2[2];
+  if (fabs (m01) < 1e-10 * fabs (m00) || fabs (m01) < 1e-10 * fabs (m11))
+    {
+      *ev1 = m00;
+      v1[0] = 1;
+      v1[1] = 0;
+      *ev2 = m11;
+      v2[0] = 0;
+      v2[1] = 1;
+    }
+  else
+    {
+      const double sq = sqrt ((m00 - m11) * (m00 - m11) + 4.0 * m01 * m10);
+      *ev1 = 0.5 * ((m00 + m11) + sq);
+      *ev2 = 0.5 * ((m00 + m11) - sq);
+      v1[0] = 1.0 / (sqrt (1 + (*ev1 - m00) / m01 * (*ev1 - m00) / m01));
+      v1[1] = (*ev1 - m00) / (m01 * (sqrt (1 + (*ev1 - m00) / m01 * (*ev1 - m00) / m01)));
+      v2[0] = 1.0 / (sqrt (1 + (*ev2 - m00) / m01 * (*ev2 - m00) / m01));
+      v2[1] = (*ev2 - m00) / (m01 * (sqrt (1 + (*ev2 - m00) / m01 * (*ev2 - m00) / m01)));
+    }
+  P[0] = v1[0];
+  P[1] = v2[0];
+  P[2] = v1[1];
+  P[3] = v2[1];
+  if (v1[0] * v2[0] + v1[1] * v2[1] > 1.0e-6)
+    P[0] = P[1] = P[2] = P[3] = NAN;
+}
+
+static inline void
+SUF (mat2_mul3) (const double *A, const double *B, const double *C, int transpose_c, double *out)
+{
+  /* out = A * B * (transpose_c ? C^T : C), row-major 2x2 */
+  double AB[4];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j)
+      AB[i * 2 + j] = A[i * 2] * B[j] + A[i * 2 + 1] * B[2 + j];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j)
+      out[i * 2 + j] = transpose_c ? AB[i * 2] * C[j * 2] + AB[i * 2 + 1] * C[j * 2 + 1]
+                                   : AB[i * 2] * C[j] + AB[i * 2 + 1] * C[2 + j];
+}
+
+/* ---- Miehe tensile/compressive split and its linearisation, cracks.cc:1923-2120.
+ * E, E_lin row-major 2x2.  The derivative branch divides by E[0][1] and by the
+ * discriminant without guards, exactly like the reference (1992-2006). */
+void
+pfo_decompose_stress_2d (const double *E, const double *EL, double lambda, double mu, int derivative,
+                         double *sp, double *sm)
+{
+  const double tr_E = E[0] + E[3], tr_EL = EL[0] + EL[3];
+  double e1, e2, P[4];
+  pfo_eigen_2x2 (E, &e1, &e2, P);
+  const double e1p = fmax (0.0, e1), e2p = fmax (0.0, e2);
+  const double Lp[4] = { e1p, 0.0, 0.0, e2p };
+  if (!derivative)
+    {
+      double Ep[4];
+      SUF (mat2_mul3) (P, Lp, P, 1, Ep);
+      const double trp = fmax (0.0, tr_E);
+      for (int i = 0; i < 4; ++i)
+        {
+          const double id = (i == 0 || i == 3) ? 1.0 : 0.0;
+          sp[i] = lambda * trp * id + 2 * mu * Ep[i];
+          sm[i] = lambda * (tr_E - trp) * id + 2 * mu * (E[i] - Ep[i]);
+        }
+      return;
+    }
+  const double E00 = E[0], E01 = E[1], E10 = E[2], E11 = E[3];
+  const double L00 = EL[0], L01 = EL[1], L10 = EL[2], L11 = EL[3];
+  const double disk = sqrt (E01 * E10 + (E00 - E11) * (E00 - E11) / 4.0);
+  const double e1L = 0.5 * tr_EL + 1.0 / (2.0 * disk) * (L01 * E10 + E01 * L10 + (E00 - E11) * (L00 - L11) / 2.0);
+  const double e2L = 0.5 * tr_EL - 1.0 / (2.0 * disk) * (L01 * E10 + E01 * L10 + (E00 - E11) * (L00 - L11) / 2.0);
+  const double q1 = (e1 - E00) / E01, q2 = (e2 - E00) / E01;
+  const double n1 = 1.0 / (sqrt (1 + q1 * q1)), n2 = 1.0 / (sqrt (1 + q2 * q2));
+  const double dq1 = ((e1L - L00) * E01 - (e1 - E00) * L01) / (E01 * E01);
+  const double dq2 = ((e2L - L00) * E01 - (e2 - E00) * L01) / (E01 * E01);
+  const double n1L = -1.0 * (1.0 / (1.0 + q1 * q1) * 1.0 / (2.0 * sqrt (1.0 + q1 * q1)) * (2.0 * q1) * dq1);
+  const double n2L = -1.0 * (1.0 / (1.0 + q2 * q2) * 1.0 / (2.0 * sqrt (1.0 + q2 * q2)) * (2.0 * q2) * dq2);
+  /* product rule on normalisation and vector entries (2031-2063) */
+  const double v1L[2] = { n1 * 0.0 + n1L * 1.0, n1 * dq1 + n1L * q1 };
+  const double v2L[2] = { n2 * 0.0 + n2L * 1.0, n2 * dq2 + n2L * q2 };
+  const double PL[4] = { v1L[0], v2L[0], v1L[1], v2L[1] };
+  const double e1pL = (e1 < 0.0) ? 0.0 : e1L;   /* 2080-2094: keyed on the sign of the eigenvalue of E */
+  const double e2pL = (e2 < 0.0) ? 0.0 : e2L;
+  const double LpL[4] = { e1pL, 0.0, 0.0, e2pL };
+  double T1[4], T2[4], T3[4], EpL[4];
+  SUF (mat2_mul3) (PL, Lp, P, 1, T1);
+  SUF (mat2_mul3) (P, LpL, P, 1, T2);
+  SUF (mat2_mul3) (P, Lp, PL, 1, T3);
+  for (int i = 0; i < 4; ++i)
+    EpL[i] = T1[i] + T2[i] + T3[i];
+  const double trpL = (tr_E < 0.0) ? 0.0 : tr_EL;
+  for (int i = 0; i < 4; ++i)
+    {
+      const double id = (i == 0 || i == 3) ? 1.0 : 0.0;
+      sp[i] = lambda * trpL * id + 2 * mu * EpL[i];
+      sm[i] = lambda * (tr_EL - trpL) * id + 2 * mu * (EL[i] - EpL[i]);
+    }
+}
+#endif
 
 /* quadrature-point state shared by residual and Jacobian; restates
  * cracks.cc:2222-2306 (no stress split: sigma+ = sigma, sigma- = 0). */
@@ -123,6 +279,7 @@ typedef struct
   double pf, pf_extra, grad_pf[DIM];
   double grad_u[DIM][DIM], E[DIM][DIM], tr_E, div_u;
   double sp[DIM][DIM];          /* stress_term_plus */
+  double sm[DIM][DIM];          /* stress_term_minus (zero without the split) */
 } SUF (qstate);
 
 static void
@@ -167,6 +324,13 @@ SUF (eval_state) (const SUF (fe_tab) * t, int q, const pfo_params * p,
   for (int a = 0; a < DIM; ++a)
     for (int b = 0; b < DIM; ++b)
       s->sp[a][b] = (a == b ? p->lambda * s->tr_E : 0.0) + 2 * p->mu * s->E[a][b];
+#if DIM == 2
+  if (p->split)                  /* cracks.cc:2294-2300 */
+    {
+      const double zero[4] = { 0, 0, 0, 0 };
+      pfo_decompose_stress_2d (&s->E[0][0], zero, p->lambda, p->mu, 0, &s->sp[0][0], &s->sm[0][0]);
+    }
+#endif
 }
 
 static void
@@ -204,6 +368,9 @@ SUF (cell_rhs) (const SUF (fe_tab) * t, const pfo_params * p,
               double sc = 0;
               for (int e = 0; e < DIM; ++e)
                 sc += g * s.sp[c][e] * t->dN[q][v][e];
+              if (p->split)      /* + decompose_stress_rhs * sigma^- : grad(phi_i), cracks.cc:2407 */
+                for (int e = 0; e < DIM; ++e)
+                  sc += p->d_rhs * s.sm[c][e] * t->dN[q][v][e];
               const double div_lin = t->dN[q][v][c];
               local_rhs[v * NC + c] -=
                 (sc - (ab - 1.0) * pr * s.pf_extra * s.pf_extra * div_lin) * t->JxW[q];
@@ -265,9 +432,17 @@ SUF (cell_matrix) (const SUF (fe_tab) * t, const pfo_params * p,
               divL += gu[a][a];
             }
           double spL[DIM][DIM];  /* stress_term_plus_LinU */
+          double smL[DIM][DIM];  /* stress_term_minus_LinU */
           for (int a = 0; a < DIM; ++a)
             for (int b = 0; b < DIM; ++b)
-              spL[a][b] = (ci < DIM) ? ((a == b ? p->lambda * trEL : 0.0) + 2 * p->mu * EL[a][b]) : 0.0;
+              {
+                spL[a][b] = (ci < DIM) ? ((a == b ? p->lambda * trEL : 0.0) + 2 * p->mu * EL[a][b]) : 0.0;
+                smL[a][b] = 0.0;
+              }
+#if DIM == 2
+          if (p->split && ci < DIM)   /* cracks.cc:2338-2345 */
+            pfo_decompose_stress_2d (&s.E[0][0], &EL[0][0], p->lambda, p->mu, 1, &spL[0][0], &smL[0][0]);
+#endif
           double spL_E = 0, sp_EL = 0;
           for (int a = 0; a < DIM; ++a)
             for (int b = 0; b < DIM; ++b)
@@ -283,6 +458,9 @@ SUF (cell_matrix) (const SUF (fe_tab) * t, const pfo_params * p,
                   double sc = 0;
                   for (int e = 0; e < DIM; ++e)
                     sc += g * spL[cj][e] * t->dN[q][vj][e];
+                  if (p->split)  /* + decompose_stress_matrix * sigma^-_LinU : grad(phi_j), cracks.cc:2362 */
+                    for (int e = 0; e < DIM; ++e)
+                      sc += p->d_mat * smL[cj][e] * t->dN[q][vj][e];
                   local_matrix[j * NDPC + i] += 1.0 * sc * t->JxW[q];
                 }
               else
@@ -764,6 +942,53 @@ SUF (pfo_cod) (const pfo_mesh * m, const double *sol, double eval_line, long *n_
     *n_faces = faces;
   return cod / 2.0;
 }
+
+#if DIM == 2
+/* ---- load on boundary id 3 (the top edge y = max of unit_slit.inp),
+ * cracks.cc:3728-3816: int sigma(u) n ds with QGauss<1>(3), sigma undegraded;
+ * load[0] *= -1 (3789). */
+void
+pfo_load_2d (const pfo_mesh * m, const pfo_params * p, const double *sol, double *load)
+{
+  const double gq = 0.5 * sqrt (3.0 / 5.0);
+  const double xi[3] = { 0.5 - gq, 0.5, 0.5 + gq };
+  const double w[3] = { 5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0 };
+  double lv[2] = { 0, 0 };
+  const long cy = m->n[1] - 1;
+  for (long cx = 0; cx < m->n[0]; ++cx)
+    {
+      long nodes[NV];
+      double ls[NDPC];
+      SUF (cell_nodes) (m, cx + cy * m->n[0], nodes);
+      SUF (gather) (nodes, sol, ls);
+      for (int q = 0; q < 3; ++q)
+        {
+          const double pt[2] = { xi[q], 1.0 };
+          double gu[2][2] = { {0, 0}, {0, 0} };
+          for (int v = 0; v < NV; ++v)
+            for (int e = 0; e < 2; ++e)
+              {
+                double gr = 1.0;
+                for (int d = 0; d < 2; ++d)
+                  {
+                    const int b = (v >> d) & 1;
+                    gr *= (d == e) ? (b ? 1.0 : -1.0) / m->h[d] : (b ? pt[d] : 1.0 - pt[d]);
+                  }
+                for (int c = 0; c < 2; ++c)
+                  gu[c][e] += gr * ls[v * NC + c];
+              }
+          const double E01 = 0.5 * (gu[0][1] + gu[1][0]), tr = gu[0][0] + gu[1][1];
+          const double s01 = 2 * p->mu * E01, s11 = p->lambda * tr + 2 * p->mu * gu[1][1];
+          const double JxW = m->h[0] * w[q];
+          /* stress * normal with n = (0, 1) */
+          lv[0] += s01 * JxW;
+          lv[1] += s11 * JxW;
+        }
+    }
+  load[0] = -1.0 * lv[0];
+  load[1] = lv[1];
+}
+#endif
 
 void
 SUF (pfo_spmv) (long nrows, const long *rowptr, const int *col, const double *val,

@@ -30,8 +30,23 @@ def main():
     import cracks_b200 as pf
     from cracks_b200.api import mesh_diameter
 
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    nccl_id = None
+    if world > 1:                                                        # torchrun: one rank per GPU
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(pf.PhaseFieldContext.nccl_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        nccl_id = idt.cpu().numpy().tobytes()
+        if rank != 0:
+            args.quiet = True
     mesh = pf.sneddon_mesh(3, args.refine)
-    ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh))           # K reg = 1e-8*h, Eps reg = 2h
+    ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh), device=local, rank=rank, nranks=world,
+                               nccl_id=nccl_id)                          # K reg = 1e-8*h, Eps reg = 2h
     ctx.set_preconditioner(args.precond, args.degree, args.ratio)
     log = (lambda s: None) if args.quiet else (lambda s: print(s, flush=True))
     # parameters_sneddon_3d.prm: Newton lower bound 1e-7, max 50 steps, line search 10 x 0.5
@@ -46,12 +61,18 @@ def main():
         stats, err = drv.statistics, str(e)
     ctx.synchronize()
     dt = time.perf_counter() - t0
-    print(json.dumps({"refine": args.refine, "n_dofs": ctx.n_dofs, "time_steps": len(stats),
-                      "newton_its": drv.newton_its, "linear_its": drv.lin_its, "wall_s": dt,
-                      "newton_its_per_s": drv.newton_its / dt if dt > 0 else None,
-                      "precond": args.precond, "cheb_degree": args.degree, "cheb_ratio": args.ratio,
-                      "statistics": stats, "error": err}))
+    if rank == 0 and hasattr(ctx.lib, "calls"):
+        print(json.dumps({k: [v[0], round(v[1], 4)] for k, v in sorted(ctx.lib.calls.items(), key=lambda kv: -kv[1][1])}))
+    if rank == 0:
+      print(json.dumps({"refine": args.refine, "n_gpus": world, "phase_s": drv.phase_s, "n_dofs": ctx.n_dofs, "time_steps": len(stats),
+                        "newton_its": drv.newton_its, "linear_its": drv.lin_its, "wall_s": dt,
+                        "newton_its_per_s": drv.newton_its / dt if dt > 0 else None,
+                        "precond": args.precond, "cheb_degree": args.degree, "cheb_ratio": args.ratio,
+                        "statistics": stats, "error": err}))
     ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
