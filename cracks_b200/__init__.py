@@ -17,4 +17,8 @@ from .api import (  # noqa: F401
     sneddon_mesh,
     sneddon_params,
     SneddonDriver,
+    MieheDriver,
+    MeshWouldRefine,
+    miehe_mesh,
+    miehe_final_h,
 )

@@ -35,7 +35,8 @@ class NoConvergence(PFError):
 
 
 class Mesh(C.Structure):
-    _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("h", C.c_double * 3), ("origin", C.c_double * 3)]
+    _fields_ = [("dim", C.c_int), ("n", C.c_int * 3), ("h", C.c_double * 3), ("origin", C.c_double * 3),
+                ("slit", C.c_int)]
 
 
 class Params(C.Structure):
@@ -80,6 +81,7 @@ _SIGS = {
     "pf_residual": [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)],
     "pf_setup_jacobian": [C.c_void_p],
     "pf_set_preconditioner": [C.c_void_p, C.c_int, C.c_int, C.c_double],
+    "pf_set_krylov_dim": [C.c_void_p, C.c_int],
     "pf_apply_jacobian": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_apply_jacobian_dev": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_jacobian_diagonal": [C.c_void_p, C.c_void_p],
@@ -93,6 +95,11 @@ _SIGS = {
     "pf_cod": [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
     "pf_project_phase_field": [C.c_void_p],
     "pf_interpolate_sneddon": [C.c_void_p, C.c_double],
+    "pf_set_stress_split": [C.c_void_p, C.c_int, C.c_double, C.c_double],
+    "pf_dirichlet_miehe": [C.c_void_p, C.c_int, C.c_double, C.c_int],
+    "pf_interpolate_unbroken": [C.c_void_p],
+    "pf_load": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "pf_phase_field_min": [C.c_void_p, C.POINTER(C.c_double)],
     "pf_advance_timestep": [C.c_void_p],
     "pf_set_time_parameters": [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double],
     "pf_timestep_difference": [C.c_void_p, C.POINTER(C.c_double)],
@@ -225,13 +232,11 @@ class PhaseFieldContext:
         rc = self.lib.pf_create(C.byref(mesh), C.byref(params), device, rank, nranks, idbuf, C.byref(h))
         self.h = h
         self._check(rc)
-        self.n_nodes = 1
-        for d in range(self.dim):
-            self.n_nodes *= mesh.n[d] + 1
-        self.n_dofs = self.n_nodes * self.nc
         lay = Layout()
         self._check(self.lib.pf_get_layout(self.h, C.byref(lay)))
         self.layout = lay
+        self.n_nodes = int(lay.n_nodes_global)      # includes the doubled nodes of a slit mesh
+        self.n_dofs = self.n_nodes * self.nc
         self.n_local_dofs = (lay.plane_end - lay.plane_begin) * lay.n_nodes_plane * self.nc
 
     # -- plumbing ---------------------------------------------------------
@@ -355,6 +360,28 @@ class PhaseFieldContext:
         self._check(rc)
         return dx, n_it.value
 
+    def set_krylov_dim(self, m: int):
+        self._check(self.lib.pf_set_krylov_dim(self.h, m))
+
+    def set_stress_split(self, active: bool, d_rhs: float, d_mat: float):
+        self._check(self.lib.pf_set_stress_split(self.h, int(active), d_rhs, d_mat))
+
+    def dirichlet_miehe(self, kind: int, time: float, set_values: bool = True):
+        self._check(self.lib.pf_dirichlet_miehe(self.h, kind, time, int(set_values)))
+
+    def interpolate_unbroken(self):
+        self._check(self.lib.pf_interpolate_unbroken(self.h))
+
+    def load(self):
+        lx, ly = C.c_double(), C.c_double()
+        self._check(self.lib.pf_load(self.h, C.byref(lx), C.byref(ly)))
+        return lx.value, ly.value
+
+    def phase_field_min(self) -> float:
+        v = C.c_double()
+        self._check(self.lib.pf_phase_field_min(self.h, C.byref(v)))
+        return v.value
+
     def update_solution(self, alpha=1.0):
         self._check(self.lib.pf_update_solution(self.h, alpha))
 
@@ -426,6 +453,25 @@ class PhaseFieldContext:
         out = np.zeros(self.n_dofs)
         self._check(self.lib.pf_download(self.h, C.c_void_p(dev), _ptr(out)))
         return out
+
+
+def miehe_mesh(refine: int) -> Mesh:
+    """meshes/unit_slit.inp (2 x 2 cells on the unit square, slit from the centre to the right
+    edge) after `refine` global refinements (cracks.cc:1202-1205, 1534)."""
+    m = Mesh()
+    m.dim = 2
+    n = 2 * 2 ** refine
+    for d in range(2):
+        m.n[d], m.h[d], m.origin[d] = n, 1.0 / n, 0.0
+    m.n[2], m.h[2], m.origin[2] = 1, 1.0, 0.0
+    m.slit = 1
+    return m
+
+
+def miehe_final_h(refine: int, cycles: int = 0) -> float:
+    """determine_mesh_dependent_parameters() for the Miehe tests: the diameter the cells will
+    have on the FINAL level (cracks.cc:3839-3854), coarse diameter sqrt(2)/2."""
+    return 0.5 * math.sqrt(2.0) * 2.0 ** (-(refine + cycles))
 
 
 @dataclass
@@ -539,4 +585,68 @@ class SneddonDriver:
                 break
             if step_no > self.max_steps:
                 break
+        return self.statistics
+
+
+class MeshWouldRefine(PFError):
+    """refine_mesh() of the reference would change the mesh here (cracks.cc:3971-3995, 4108-4133);
+    predictor-corrector refinement is outside this library's scope."""
+
+    def __init__(self, step):
+        super().__init__(PF_UNSUPPORTED, "phase field below the refinement threshold at time step %d" % step)
+        self.step = step
+
+
+class MieheDriver(SneddonDriver):
+    """Host-side restatement of run() for `test case = miehe tension / miehe shear` on the
+    uniformly refined slit mesh (cracks.cc:4166-4581): time-dependent Dirichlet data, stress
+    split from the second time step on, load functional, time-step cut on NoConvergence."""
+
+    def __init__(self, ctx: PhaseFieldContext, test: str, E, timestep, max_no_timesteps, timestep_2=None,
+                 switch_timestep=0, d_rhs=0.0, d_mat=0.0, cycles=0, refine_threshold=0.8, **kw):
+        super().__init__(ctx, E=E, timestep=timestep, max_no_timesteps=max_no_timesteps, **kw)
+        self.kind = {"miehe tension": 1, "miehe shear": 2}[test]
+        self.dt2, self.switch = timestep_2, switch_timestep
+        self.d_rhs, self.d_mat = d_rhs, d_mat
+        self.cycles, self.threshold = cycles, refine_threshold
+
+    def run(self):
+        c = self.ctx
+        c.interpolate_unbroken()
+        c.project_phase_field()
+        dt = self.dt
+        dt_old = dt_oldold = dt
+        time, step_no = 0.0, 0
+        while step_no <= self.max_steps:
+            if self.switch > 0 and step_no > self.switch:
+                dt = self.dt2
+            tmp_dt = dt
+            dt_oldold, dt_old = dt_old, dt
+            c.advance_timestep()
+            c.set_time_parameters(dt_old, dt_oldold, False, 0.0)
+            c.set_stress_split(self.d_mat > 0 and step_no > 0, self.d_rhs, self.d_mat)
+            time += dt
+            self.log("Timestep %d: %g (%g)" % (step_no, time - dt, dt))
+            while True:
+                try:
+                    c.dirichlet_miehe(self.kind, time, True)      # set_initial_bc(time), cracks.cc:2787
+                    self.newton_active_set()
+                    break
+                except NoConvergence:
+                    self.log("Solver did not converge! Adjusting time step to %g" % (dt / 10))
+                    c._check(c.lib.pf_restore_old_solution(c.h))  # cracks.cc:4333-4355
+                    time -= dt
+                    dt /= 10.0
+                    time += dt
+            c.project_phase_field()
+            if self.cycles > 0 and c.phase_field_min() < self.threshold:
+                raise MeshWouldRefine(step_no)
+            dt = tmp_dt
+            bulk, crack = c.energy()
+            lx, ly = c.load()
+            self.statistics.append(dict(step=step_no, time=time, bulk=bulk, crack=crack,
+                                        load=ly if self.kind == 1 else lx))
+            self.log("No %d time %g bulk energy: %.8e crack energy: %.8e  load %.8e"
+                     % (step_no, time, bulk, crack, self.statistics[-1]["load"]))
+            step_no += 1
         return self.statistics

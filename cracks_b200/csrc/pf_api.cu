@@ -101,6 +101,8 @@ struct pf_ctx
   K3 k3{};
   double pressure = 0, dt_old = 1, dt_oldold = 1;
   int use_old_timestep_pf = 0;
+  int split = 0;              // Miehe stress split (2-D), see pf_set_stress_split
+  double d_rhs = 0, d_mat = 0;
   int device = 0, rank = 0, nranks = 1;
   int own_cell_begin = 0, own_cell_end = 0;
   cudaStream_t stream = nullptr, comm_stream = nullptr;
@@ -124,6 +126,7 @@ struct pf_ctx
   double *red = nullptr, *partial = nullptr; // reduction scratch
   unsigned long long *counts = nullptr;
   double *h_red = nullptr; // pinned mirror
+  double *h_gs = nullptr;  // pinned: the two Gram-Schmidt coefficient sets and the norm of one Arnoldi step
   unsigned long long *h_counts = nullptr;
   // Krylov workspace
   int krylov_m = 30;
@@ -288,6 +291,9 @@ update_phys (pf_ctx *c)
   c->p.eps = c->prm.eps;
   c->p.P1 = (c->prm.alpha_biot - 1.0) * c->pressure;
   c->p.clamp_extra = c->use_old_timestep_pf ? 0 : 1;
+  c->p.split = c->split;
+  c->p.d_rhs = c->d_rhs;
+  c->p.d_mat = c->d_mat;
 }
 
 // ghost planes of a local nodal vector <- owners (ncomp doubles per node)
@@ -1223,6 +1229,8 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
       return PF_BAD_ARG;
   if (nranks > mesh->n[dim - 1])
     return PF_BAD_ARG;
+  if (mesh->slit && (dim != 2 || nranks != 1 || mesh->n[0] % 2 || mesh->n[1] % 2))
+    return PF_BAD_ARG;
   pf_ctx *ctx = new pf_ctx ();
   *out = ctx;
   ctx->dim = dim;
@@ -1260,6 +1268,18 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
     g.plane_end = lay.plane_end;
   }
   g.n_local_nodes = g.nodes_per_plane * (g.plane_end - g.plane_begin);
+  g.slit_row = -1;
+  g.slit_i0 = 0;
+  g.slit_base = 0;
+  if (mesh->slit)
+    {
+      // the doubled nodes of the slit line are appended after the regular ones (single rank)
+      g.slit_row = g.n[1] / 2;
+      g.slit_i0 = g.n[0] / 2 + 1;
+      g.slit_base = g.n_local_nodes;
+      g.n_local_nodes += g.n[0] / 2;
+      g.n_global_nodes += g.n[0] / 2;
+    }
   long long cells_per_layer = 1;
   for (int d = 0; d < dim - 1; ++d)
     cells_per_layer *= g.n[d];
@@ -1267,6 +1287,8 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
   ctx->n_local_dofs = g.n_local_nodes * ctx->nc;
   ctx->owned_lo = (long long) (g.owned_begin - g.plane_begin) * g.nodes_per_plane;
   ctx->owned_hi = (long long) (g.owned_end - g.plane_begin) * g.nodes_per_plane;
+  if (mesh->slit)
+    ctx->owned_hi = g.n_local_nodes;
 
   const double s = std::sqrt (3.0 / 5.0);
   ctx->k3.s = s;
@@ -1304,8 +1326,9 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
   CU (cudaMemsetAsync (ctx->mask, 0, nn, ctx->stream));
   CU (cudaMemsetAsync (ctx->cycle, 0, nn * sizeof (int), ctx->stream));
   CU (cudaMalloc (&ctx->red, 64 * sizeof (double)));
-  CU (cudaMalloc (&ctx->hdev, 128 * sizeof (double)));
-  CU (cudaMalloc (&ctx->partial, (size_t) RED_BLOCKS * 64 * sizeof (double)));
+  CU (cudaMalloc (&ctx->hdev, (size_t) (ctx->krylov_m + 2) * sizeof (double)));
+  CU (cudaMalloc (&ctx->partial, (size_t) RED_BLOCKS * (ctx->krylov_m + 2) * sizeof (double)));
+  CU (cudaMallocHost (&ctx->h_gs, (size_t) 3 * (ctx->krylov_m + 2) * sizeof (double)));
   CU (cudaMalloc (&ctx->counts, 4 * sizeof (unsigned long long)));
   CU (cudaMallocHost (&ctx->h_red, 128 * sizeof (double)));
   CU (cudaMallocHost (&ctx->h_counts, 4 * sizeof (unsigned long long)));
@@ -1315,7 +1338,13 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
       fill_fetab<2> (t, g.h);
       CU (cudaMalloc (&ctx->fetab, sizeof t));
       CU (cudaMemcpy (ctx->fetab, &t, sizeof t, cudaMemcpyHostToDevice));
-      k_lumped_mass<2><<<nblk (nn, 256), 256, 0, ctx->stream>>> (g, ctx->mass);
+      if (mesh->slit)
+        {
+          CU (cudaMemsetAsync (ctx->mass, 0, nn * sizeof (double), ctx->stream));
+          k_lumped_mass_cells<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (g, ctx->mass);
+        }
+      else
+        k_lumped_mass<2><<<nblk (nn, 256), 256, 0, ctx->stream>>> (g, ctx->mass);
     }
   else
     {
@@ -1383,6 +1412,8 @@ pf_destroy (pf_ctx *ctx)
       cudaFree (p);
   if (ctx->h_red)
     cudaFreeHost (ctx->h_red);
+  if (ctx->h_gs)
+    cudaFreeHost (ctx->h_gs);
   if (ctx->h_counts)
     cudaFreeHost (ctx->h_counts);
   if (ctx->comm_stream)
@@ -1602,6 +1633,28 @@ pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio
   ctx->cheb_degree = cheb_degree;
   ctx->cheb_ratio = cheb_ratio;
   ctx->jac_ready = false;
+  return PF_OK;
+}
+
+int
+pf_set_krylov_dim (pf_ctx *ctx, int m)
+{
+  if (!ctx || m < 2 || m > 2000)
+    return PF_BAD_ARG;
+  if (m == ctx->krylov_m)
+    return PF_OK;
+  CU (cudaSetDevice (ctx->device));
+  CU (cudaStreamSynchronize (ctx->stream));
+  if (ctx->V)
+    CU (cudaFree (ctx->V));
+  ctx->V = nullptr; // pf_solve allocates (m + 1) vectors on first use
+  CU (cudaFree (ctx->hdev));
+  CU (cudaFree (ctx->partial));
+  CU (cudaFreeHost (ctx->h_gs));
+  ctx->krylov_m = m;
+  CU (cudaMalloc (&ctx->hdev, (size_t) (m + 2) * sizeof (double)));
+  CU (cudaMalloc (&ctx->partial, (size_t) RED_BLOCKS * (m + 2) * sizeof (double)));
+  CU (cudaMallocHost (&ctx->h_gs, (size_t) 3 * (m + 2) * sizeof (double)));
   return PF_OK;
 }
 
@@ -1846,26 +1899,27 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
           // CGS2: two passes of classical Gram-Schmidt, fused multi-dot / multi-axpy
           if ((rc = dots (k + 1, w, 0)))
             return rc;
-          CU (cudaMemcpyAsync (ctx->h_red, ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToHost,
+          double *gs0 = ctx->h_gs, *gs1 = ctx->h_gs + (m + 2), *gs2 = ctx->h_gs + 2 * (m + 2);
+          CU (cudaMemcpyAsync (gs0, ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToHost,
                                ctx->stream));
           k_multi_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w);
           KCHECK ();
           if ((rc = dots (k + 1, w, 0)))
             return rc;
-          CU (cudaMemcpyAsync (ctx->h_red + 40, ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToHost,
+          CU (cudaMemcpyAsync (gs1, ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToHost,
                                ctx->stream));
           k_multi_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w);
           KCHECK ();
           if ((rc = dots (0, w, 1)))
             return rc;
-          CU (cudaMemcpyAsync (ctx->h_red + 80, ctx->hdev, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+          CU (cudaMemcpyAsync (gs2, ctx->hdev, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
           k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, 1.0, 1, w, vk1);
           KCHECK ();
           CU (cudaStreamSynchronize (ctx->stream));
           ++its;
           for (int j = 0; j <= k; ++j)
-            H[(size_t) j * m + k] = ctx->h_red[j] + ctx->h_red[40 + j];
-          const double hk1 = std::sqrt (ctx->h_red[80]);
+            H[(size_t) j * m + k] = gs0[j] + gs1[j];
+          const double hk1 = std::sqrt (gs2[0]);
           H[(size_t) (k + 1) * m + k] = hk1;
           // Givens rotations
           for (int j = 0; j < k; ++j)
@@ -1991,6 +2045,96 @@ pf_cod (pf_ctx *ctx, double eval_line, double *value, int64_t *n_faces)
   *value = ctx->h_red[0] / 2.0; // each face is visited from both neighbouring cells (cracks.cc:3537-3538)
   if (n_faces)
     *n_faces = (int64_t) std::llround (ctx->h_red[1]);
+  return PF_OK;
+}
+
+int
+pf_set_stress_split (pf_ctx *ctx, int active, double decompose_rhs, double decompose_matrix)
+{
+  if (!ctx || decompose_rhs < 0 || decompose_matrix < 0)
+    return PF_BAD_ARG;
+  if (active && ctx->dim != 2)
+    return fail (ctx, PF_UNSUPPORTED, "the stress split of the reference is 2-D only (cracks.cc:1923-2120)");
+  ctx->split = active ? 1 : 0;
+  ctx->d_rhs = decompose_rhs;
+  ctx->d_mat = decompose_matrix;
+  update_phys (ctx);
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return PF_OK;
+}
+
+int
+pf_dirichlet_miehe (pf_ctx *ctx, int kind, double time, int set_values)
+{
+  if (!ctx || (kind != 1 && kind != 2))
+    return PF_BAD_ARG;
+  if (ctx->dim != 2 || ctx->g.slit_row < 0)
+    return fail (ctx, PF_UNSUPPORTED, "the Miehe boundary data need the 2-D slit mesh");
+  const long long nl = ctx->g.n_local_nodes;
+  k_dirichlet_miehe<<<nblk (nl, 256), 256, 0, ctx->stream>>> (ctx->g, kind, time, set_values, ctx->mask, ctx->sol);
+  KCHECK ();
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return PF_OK;
+}
+
+int
+pf_interpolate_unbroken (pf_ctx *ctx)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  // InitialValuesTensionOrShear / InitialValuesNoCrack: u = 0, phi = 1 (cracks.cc:679-691, 727-737)
+  const long long nl = ctx->g.n_local_nodes;
+  CU (cudaMemsetAsync (ctx->sol, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
+  if (ctx->dim == 2)
+    k_set_component<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, 2, 1.0, ctx->sol);
+  else
+    k_set_component<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, 3, 1.0, ctx->sol);
+  KCHECK ();
+  const size_t bytes = sizeof (double) * ctx->n_local_dofs;
+  CU (cudaMemcpyAsync (ctx->old, ctx->sol, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU (cudaMemcpyAsync (ctx->oldold, ctx->sol, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return refresh_extrapolation (ctx);
+}
+
+int
+pf_load (pf_ctx *ctx, double *load_x, double *load_y)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  if (ctx->dim != 2 || ctx->nranks != 1)
+    return fail (ctx, PF_UNSUPPORTED, "pf_load: 2-D, single rank (the reference's load tests are 2-D)");
+  CU (cudaMemsetAsync (ctx->red, 0, 2 * sizeof (double), ctx->stream));
+  k_load_top_2d<<<nblk (ctx->g.n[0], 128), 128, 0, ctx->stream>>> (ctx->g, ctx->p, ctx->sol, ctx->red);
+  KCHECK ();
+  CU (cudaMemcpyAsync (ctx->h_red, ctx->red, 2 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  if (load_x)
+    *load_x = -1.0 * ctx->h_red[0]; // load_value[0] *= -1.0, cracks.cc:3789
+  if (load_y)
+    *load_y = ctx->h_red[1];
+  return PF_OK;
+}
+
+int
+pf_phase_field_min (pf_ctx *ctx, double *phi_min)
+{
+  if (!ctx || !phi_min)
+    return PF_BAD_ARG;
+  k_one_minus_phi_max<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->owned_lo, ctx->owned_hi, ctx->nc, ctx->sol,
+                                                                    ctx->partial);
+  KCHECK ();
+  k_reduce_partials_max<<<1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, ctx->partial, ctx->red);
+  KCHECK ();
+  int rc = allreduce_max (ctx, ctx->red, 1);
+  if (rc)
+    return rc;
+  CU (cudaMemcpyAsync (ctx->h_red, ctx->red, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  *phi_min = 1.0 - ctx->h_red[0];
   return PF_OK;
 }
 

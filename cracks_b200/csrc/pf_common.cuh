@@ -26,6 +26,12 @@ struct Grid
   long long n_local_nodes;
   long long n_local_cells;
   long long n_global_nodes;
+  // unit_slit.inp topology (2-D Miehe tests, cracks.cc:1202-1205): the nodes on the line
+  // y = origin + h * n[1]/2 with x-index >= slit_i0 are doubled; the cell row slit_row
+  // (just above the line) uses the copies stored from slit_base on.  slit_row < 0: no slit.
+  int slit_row;
+  int slit_i0;
+  long long slit_base;
 };
 
 // quantities that change per Newton step / time step
@@ -34,6 +40,8 @@ struct Phys
   double lambda, mu, G_c, kappa, eps;
   double P1;        // (alpha_biot - 1) * pressure   (cracks.cc:2381, 2409, 2428)
   int clamp_extra;  // 1: pf_extra = clamp01(interp(pt)); 0: use_old_timestep_pf (cracks.cc:2276)
+  int split;        // Miehe stress split active: decompose_stress_matrix > 0 && timestep_number > 0 (2294, 2338); 2-D
+  double d_rhs, d_mat; // decompose_stress_rhs / decompose_stress_matrix (cracks.cc:1568-1569)
 };
 
 template <int DIM> struct FeTab

@@ -6,6 +6,7 @@
 // Weak form restated from cracks.cc:2235-2432 (no stress split: sigma+ = sigma).
 #pragma once
 #include "pf_common.cuh"
+#include "pf_split2d.cuh"
 
 namespace pf {
 
@@ -31,6 +32,13 @@ cell_nodes (const Grid &g, long long lc, long long *node)
         id += (ci[2] + ((v >> 2) & 1)) * sz;
       node[v] = id;
     }
+  if (DIM == 2 && g.slit_row >= 0 && ci[1] == g.slit_row)
+    for (int v = 0; v < 2; ++v) // bottom vertices of the cell row above the slit: doubled nodes
+      {
+        const int ix = ci[0] + (v & 1);
+        if (ix >= g.slit_i0)
+          node[v] = g.slit_base + (ix - g.slit_i0);
+      }
 }
 
 // q-point state for the no-split constitutive law
@@ -40,6 +48,9 @@ template <int DIM> struct QState
   double gpf[DIM];
   double gu[DIM][DIM];
   double sp[DIM][DIM];
+  double sm[DIM][DIM]; // sigma^- (zero without the split)
+  Sym2 E2;             // 2-D: strain and its eigen-decomposition, reused by the linearisation
+  Eig2 eig;
 };
 
 template <int DIM>
@@ -82,8 +93,21 @@ eval_qstate (const FeTab<DIM> &t, int q, const Phys &p, const double (*ls)[DIM +
       {
         const double E = 0.5 * (s.gu[a][b] + s.gu[b][a]);
         s.sp[a][b] = (a == b ? p.lambda * tr : 0.0) + 2 * p.mu * E;
+        s.sm[a][b] = 0.0;
         spE += s.sp[a][b] * E;
       }
+  if (DIM == 2 && p.split) // cracks.cc:2294-2300
+    {
+      s.E2.xx = s.gu[0][0];
+      s.E2.yy = s.gu[1][1];
+      s.E2.xy = 0.5 * (s.gu[0][1] + s.gu[1][0]);
+      s.eig = eig_sym2 (s.E2);
+      Sym2 sp, sm;
+      split_stress (s.E2, s.eig, p.lambda, p.mu, sp, sm);
+      s.sp[0][0] = sp.xx, s.sp[0][1] = s.sp[1][0] = sp.xy, s.sp[1][1] = sp.yy;
+      s.sm[0][0] = sm.xx, s.sm[0][1] = s.sm[1][0] = sm.xy, s.sm[1][1] = sm.yy;
+      spE = sp.xx * s.E2.xx + 2.0 * sp.xy * s.E2.xy + sp.yy * s.E2.yy;
+    }
   s.spE = spE;
 }
 
@@ -146,12 +170,26 @@ k_apply_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
         }
       const double gdeg = (1.0 - p.kappa) * s.pf_extra * s.pf_extra + p.kappa;
       double Sig[DIM][DIM];
-      for (int a = 0; a < DIM; ++a)
-        for (int b = 0; b < DIM; ++b)
-          Sig[a][b] = gdeg * ((a == b ? p.lambda * trG : 0.0) + p.mu * (G[a][b] + G[b][a]));
-      // (phi,u) + (phi,phi) value coefficient, cracks.cc:2375-2382 with
-      // sigma(du):E(u) == sigma(u):E(du) for the unsplit law
-      const double a_val = s.pf * (2.0 * (1.0 - p.kappa) * spG - 2.0 * p.P1 * trG)
+      // sigma+'(u; du):E(u) + sigma+(u):E(du); equal for the unsplit law
+      double cross = 2.0 * spG;
+      if (DIM == 2 && p.split)
+        {
+          // the linearisation is linear in E(du), so it is applied to the interpolated
+          // direction instead of once per trial function (cracks.cc:2338-2345, 2359-2364)
+          Sym2 L, spL, smL;
+          L.xx = G[0][0], L.yy = G[1][1], L.xy = 0.5 * (G[0][1] + G[1][0]);
+          split_stress_lin (s.E2, s.eig, L, p.lambda, p.mu, spL, smL);
+          Sig[0][0] = gdeg * spL.xx + p.d_mat * smL.xx;
+          Sig[1][1] = gdeg * spL.yy + p.d_mat * smL.yy;
+          Sig[0][1] = Sig[1][0] = gdeg * spL.xy + p.d_mat * smL.xy;
+          cross = (spL.xx * s.E2.xx + 2.0 * spL.xy * s.E2.xy + spL.yy * s.E2.yy) + spG;
+        }
+      else
+        for (int a = 0; a < DIM; ++a)
+          for (int b = 0; b < DIM; ++b)
+            Sig[a][b] = gdeg * ((a == b ? p.lambda * trG : 0.0) + p.mu * (G[a][b] + G[b][a]));
+      // (phi,u) + (phi,phi) value coefficient, cracks.cc:2375-2382
+      const double a_val = s.pf * ((1.0 - p.kappa) * cross - 2.0 * p.P1 * trG)
                            + dphi * ((1.0 - p.kappa) * s.spE + p.G_c / p.eps - 2.0 * p.P1 * s.div_u);
       const double w = t.JxW[q];
       for (int v = 0; v < NV; ++v)
@@ -215,7 +253,7 @@ k_residual_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
             {
               double sc = 0;
               for (int e = 0; e < DIM; ++e)
-                sc += gdeg * s.sp[c][e] * t.dN[q][v][e];
+                sc += (gdeg * s.sp[c][e] + p.d_rhs * s.sm[c][e]) * t.dN[q][v][e]; // sm = 0 without the split
               out[v][c] -= w * (sc - pe2 * t.dN[q][v][c]);
             }
           out[v][DIM] -= w * (cphi * t.N[q][v] + p.G_c * p.eps * gg);
@@ -267,6 +305,20 @@ k_diag_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
           for (int c = 0; c < DIM; ++c)
             {
               const double d = t.dN[q][v][c];
+              if (DIM == 2 && p.split)
+                {
+                  // trial = test = e_c N_v: E_lin = sym(e_c (x) grad N_v)
+                  Sym2 L, spL, smL;
+                  const double dx = t.dN[q][v][0], dy = t.dN[q][v][1];
+                  L.xx = c == 0 ? dx : 0.0;
+                  L.yy = c == 1 ? dy : 0.0;
+                  L.xy = 0.5 * (c == 0 ? dy : dx);
+                  split_stress_lin (s.E2, s.eig, L, p.lambda, p.mu, spL, smL);
+                  const double sx = c == 0 ? gdeg * spL.xx + p.d_mat * smL.xx : gdeg * spL.xy + p.d_mat * smL.xy;
+                  const double sy = c == 0 ? gdeg * spL.xy + p.d_mat * smL.xy : gdeg * spL.yy + p.d_mat * smL.yy;
+                  out[v][c] += w * (sx * dx + sy * dy);
+                  continue;
+                }
               // g * (lambda d_c^2 + mu (|grad N|^2 + d_c^2))
               out[v][c] += w * gdeg * (p.lambda * d * d + p.mu * (g2 + d * d));
             }
@@ -476,6 +528,122 @@ k_cod_generic (Grid g, const double *__restrict__ sol, double eval_line, int own
         s += red[threadIdx.x][i];
       if (s != 0.0)
         atomicAdd (&out2[threadIdx.x], s);
+    }
+}
+
+// ---- phi-block lumped mass by a cell loop (cracks.cc:2514-2562: vertex quadrature,
+// vol / 2^dim per cell vertex); used where the node -> cells count is not implied
+// by the node index (slit meshes)
+template <int DIM>
+__global__ void __launch_bounds__ (128)
+k_lumped_mass_cells (Grid g, double *__restrict__ mass)
+{
+  const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (lc >= g.n_local_cells)
+    return;
+  long long node[1 << DIM];
+  cell_nodes<DIM> (g, lc, node);
+  double vol = 1;
+  for (int d = 0; d < DIM; ++d)
+    vol *= g.h[d];
+  for (int v = 0; v < (1 << DIM); ++v)
+    atomicAdd (&mass[node[v]], vol / (1 << DIM));
+}
+
+// ---- load on boundary id 3 = the top edge (cracks.cc:3728-3816): int sigma(u) n ds,
+// n = (0,1), QGauss<1>(3), undegraded stress.  out2 += (sigma_xy, sigma_yy) integrals.
+__global__ void __launch_bounds__ (128)
+k_load_top_2d (Grid g, Phys p, const double *__restrict__ sol, double *__restrict__ out2)
+{
+  const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+  double lx = 0, ly = 0;
+  if (cx < g.n[0])
+    {
+      long long node[4];
+      cell_nodes<2> (g, cx + (long long) (g.n[1] - 1) * g.n[0], node);
+      const double gq = 0.5 * sqrt (3.0 / 5.0);
+      const double xi[3] = {0.5 - gq, 0.5, 0.5 + gq};
+      const double wq[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+      for (int q = 0; q < 3; ++q)
+        {
+          const double pt[2] = {xi[q], 1.0};
+          double gu[2][2] = {{0, 0}, {0, 0}};
+          for (int v = 0; v < 4; ++v)
+            for (int e = 0; e < 2; ++e)
+              {
+                double gr = 1.0;
+                for (int d = 0; d < 2; ++d)
+                  {
+                    const int b = (v >> d) & 1;
+                    gr *= (d == e) ? (b ? 1.0 : -1.0) / g.h[d] : (b ? pt[d] : 1.0 - pt[d]);
+                  }
+                for (int c = 0; c < 2; ++c)
+                  gu[c][e] += gr * sol[node[v] * 3 + c];
+              }
+          const double tr = gu[0][0] + gu[1][1];
+          const double JxW = g.h[0] * wq[q];
+          lx += p.mu * (gu[0][1] + gu[1][0]) * JxW;
+          ly += (p.lambda * tr + 2.0 * p.mu * gu[1][1]) * JxW;
+        }
+    }
+  for (int o = 16; o > 0; o >>= 1)
+    {
+      lx += __shfl_down_sync (0xffffffffu, lx, o);
+      ly += __shfl_down_sync (0xffffffffu, ly, o);
+    }
+  if ((threadIdx.x & 31) == 0)
+    {
+      atomicAdd (&out2[0], lx);
+      atomicAdd (&out2[1], ly);
+    }
+}
+
+// ---- Dirichlet rows and values of the Miehe tests on the unit square with slit
+// (cracks.cc:2584-2625 with BoundaryTensionTest 780-797 / BoundaryShearTest 845-861).
+// kind 1 = tension: u_y = 0 on y = 0, u = (0, t) on y = 1;
+// kind 2 = shear:   u_y = 0 on x = 0 and x = 1, u = 0 on y = 0, u = (-t, 0) on y = 1,
+//                   u_y = 0 on the lower face of the slit (boundary id 4).
+// set_values = 0: only (re)build the mask bits; 1: also write the values into sol.
+__global__ void
+k_dirichlet_miehe (Grid g, int kind, double time, int set_values, uint8_t *__restrict__ mask,
+                   double *__restrict__ sol)
+{
+  const long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= g.n_local_nodes)
+    return;
+  const bool dup = g.slit_row >= 0 && n >= g.slit_base;
+  const int i = dup ? (int) (n - g.slit_base) + g.slit_i0 : (int) (n % g.nn[0]);
+  const int j = dup ? g.slit_row : (int) (n / g.nn[0]);
+  const bool top = j == g.nn[1] - 1, bottom = j == 0, left = i == 0, right = i == g.nn[0] - 1;
+  bool cx = false, cy = false;
+  double vx = 0, vy = 0;
+  if (kind == 1)
+    {
+      cy = bottom || top;
+      cx = top;
+      if (top)
+        vy = time;
+    }
+  else
+    {
+      const bool lower_slit = !dup && g.slit_row >= 0 && j == g.slit_row && i >= g.slit_i0 - 1;
+      cy = left || right || bottom || top || lower_slit;
+      cx = bottom || top;
+      if (top)
+        vx = -time;
+    }
+  uint8_t m = mask[n] & (uint8_t) 4u; // keep the active-set bit of phi
+  if (cx)
+    m |= 1u;
+  if (cy)
+    m |= 2u;
+  mask[n] = m;
+  if (set_values)
+    {
+      if (cx)
+        sol[n * 3 + 0] = vx;
+      if (cy)
+        sol[n * 3 + 1] = vy;
     }
 }
 

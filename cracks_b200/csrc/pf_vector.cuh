@@ -460,4 +460,29 @@ k_absdiff_max (long long lo, long long hi, const double *__restrict__ a, const d
     partial[blockIdx.x] = s;
 }
 
+template <int DIM>
+__global__ void
+k_set_component (long long n_nodes, int c, double value, double *__restrict__ v)
+{
+  const long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < n_nodes)
+    v[n * (DIM + 1) + c] = value;
+}
+
+// partial[b] = max over the block's nodes in [lo, hi) of (1 - phi): the refinement
+// indicator of refine_mesh() looks for phi below a threshold (cracks.cc:3971-3995)
+__global__ void __launch_bounds__ (RED_THREADS)
+k_one_minus_phi_max (long long lo, long long hi, int ncomp, const double *__restrict__ sol,
+                     double *__restrict__ partial)
+{
+  __shared__ double sh[RED_THREADS / 32];
+  double acc = -1e300;
+  for (long long n = lo + (long long) blockIdx.x * blockDim.x + threadIdx.x; n < hi;
+       n += (long long) gridDim.x * blockDim.x)
+    acc = fmax (acc, 1.0 - sol[n * ncomp + ncomp - 1]);
+  const double s = block_reduce_max (acc, sh);
+  if (threadIdx.x == 0)
+    partial[blockIdx.x] = s;
+}
+
 } // namespace pf

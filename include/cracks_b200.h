@@ -56,6 +56,10 @@ typedef struct
   int n[3];         /* cells per direction: 10 * 2^(global pre-refinement) for Sneddon */
   double h[3];      /* cell edge lengths */
   double origin[3]; /* lower corner of the box */
+  int slit;         /* 2-D, single rank: 1 = the topology of meshes/unit_slit.inp after refine_global
+                       (Miehe tests, cracks.cc:1202-1205): the nodes on the line y = origin + h n[1]/2 with
+                       x-index > n[0]/2 are doubled, the cells above the line use the copies, which are
+                       numbered after the (n[0]+1)(n[1]+1) regular nodes.  0 for the box meshes. */
 } pf_mesh;
 
 typedef struct
@@ -152,6 +156,11 @@ int pf_apply_jacobian_dev (pf_ctx *ctx, double *x_dev, double *y_dev);
  * rank only, otherwise Jacobi is used).  Takes effect at the next
  * pf_setup_jacobian. */
 int pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio);
+/* Restart length of GMRES (deal.II's SolverGMRES default keeps 28 basis vectors,
+ * cracks.cc:2764; this library's default is 30).  Ill-conditioned small 2-D
+ * problems, which the reference hands to a sparse direct solver (2750-2759),
+ * want a basis as large as the iteration count. */
+int pf_set_krylov_dim (pf_ctx *ctx, int m);
 
 /* diag(J) as used for constrained rows and the Jacobi/Chebyshev smoother */
 int pf_jacobian_diagonal (pf_ctx *ctx, double *diag);
@@ -183,6 +192,29 @@ int pf_tcv (pf_ctx *ctx, double *tcv);                      /* cracks.cc:3553-35
 int pf_cod (pf_ctx *ctx, double eval_line, double *value, int64_t *n_faces);
 int pf_project_phase_field (pf_ctx *ctx);                   /* cracks.cc:3109-3137 */
 int pf_interpolate_sneddon (pf_ctx *ctx, double h_diam);    /* InitialValuesSneddon, cracks.cc:381-406 */
+
+/* ---- 2-D Miehe tests (configs 2 and 4): slit mesh, stress split, load ------ */
+
+/* decompose_stress(): Miehe's tensile/compressive split and its linearisation
+ * (cracks.cc:1923-2120, 1691-1737).  active = (decompose_stress_matrix > 0 &&
+ * timestep_number > 0), the condition of cracks.cc:2294 and 2338; the two
+ * factors are "Decompose stress in rhs / matrix" (1568-1569).  2-D only, like
+ * the reference. */
+int pf_set_stress_split (pf_ctx *ctx, int active, double decompose_rhs, double decompose_matrix);
+/* set_boundary_conditions() for `miehe tension` (kind 1) and `miehe shear`
+ * (kind 2), cracks.cc:2584-2625: rebuilds the Dirichlet bits of the constraint
+ * mask on the device and, if set_values != 0, writes the boundary values at
+ * `time` into the solution (set_initial_bc, 2700-2707).  Needs mesh.slit. */
+int pf_dirichlet_miehe (pf_ctx *ctx, int kind, double time, int set_values);
+/* InitialValuesTensionOrShear / InitialValuesNoCrack (cracks.cc:679-691, 727-737):
+ * u = 0, phi = 1; old = oldold = solution. */
+int pf_interpolate_unbroken (pf_ctx *ctx);
+/* compute_load(), cracks.cc:3728-3816: traction integral over boundary id 3
+ * (top edge), undegraded stress, load_x already multiplied by -1 (3789). */
+int pf_load (pf_ctx *ctx, double *load_x, double *load_y);
+/* min over the owned phase-field dofs: the indicator refine_mesh() tests
+ * against "value phase field for refinement" (cracks.cc:3971-3995).  [collective] */
+int pf_phase_field_min (pf_ctx *ctx, double *phi_min);
 /* time-step bookkeeping on the device: oldold <- old <- sol (cracks.cc:4302-4303);
  * returns ||old - sol||_inf of the step just finished (4478-4483) */
 int pf_advance_timestep (pf_ctx *ctx);

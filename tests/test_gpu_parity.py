@@ -90,15 +90,15 @@ def test_apply_jacobian_3d(oracle, pf, n, h):
     finally:
         ctx.lib.pf_debug_disable_iso(0)
     assert _relerr(ctx.to_nodal(y4), y_ref) <= TOL
-    # variant 1 = first-generation kernel, 3..7 = other tile shapes of v2
-    # 12..15 = persistent TMA-fed kernel (v3)
-    for variant in (1, 2, 4, 5, 6, 7, 12, 13, 14, 15):
+    # variant 1 = first-generation kernel, 2..7 = tile shapes of v2, 12..15 = persistent
+    # TMA-fed kernel (v3); 16 = v4 (symmetric strain sums, closed-form phi Laplacian) is the default
+    for variant in (1, 2, 3, 4, 5, 6, 7, 12, 13, 14, 15):
         ctx.lib.pf_debug_set_variant(variant)
         try:
             y3 = np.zeros(prob.n_dofs)
             ctx.vmult(y3, ctx.to_block(x))
         finally:
-            ctx.lib.pf_debug_set_variant(3)
+            ctx.lib.pf_debug_set_variant(16)
         assert _relerr(ctx.to_nodal(y3), y_ref) <= TOL, variant
     ctx.close()
 
