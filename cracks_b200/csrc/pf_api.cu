@@ -881,7 +881,7 @@ mg_setup_level (pf_ctx *ctx)
     }
   if (!ctx->coarse)
     {
-      pf_mesh cm;
+      pf_mesh cm{};
       cm.dim = 3;
       for (int d = 0; d < 3; ++d)
         {

@@ -100,14 +100,20 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
   outer_solver = prm_.get ("outer solver");
   test_case = prm_.get ("test case");
   output_folder = prm_.get ("Output directory");
+  refinement_strategy = prm_.get ("ref strategy");
+  value_phase_field_for_refinement = prm_.get_double ("value phase field for refinement");
   prm_.leave_subsection ();
 
   if (outer_solver != "active set")
     throw NotImplemented ("outer solver = simple monolithic is not part of the GPU hot path");
-  if (test_case != "sneddon")
+  if (test_case != "sneddon" && !miehe ())
     throw NotImplemented ("test case <" + test_case + "> needs meshes / boundary data outside this round's scope");
-  if (n_local_pre_refine != 0 || n_refinement_cycles != 0)
-    throw NotImplemented ("local / adaptive refinement (hanging nodes) is not available: use global refinement");
+  if (miehe () && dim_ != 2)
+    throw NotImplemented ("the Miehe tests are 2-D (meshes/unit_slit.inp)");
+  if (n_local_pre_refine != 0)
+    throw NotImplemented ("local pre-refinement (hanging nodes) is not available: use global refinement");
+  if (n_refinement_cycles != 0 && !(miehe () && refinement_strategy == "phase field"))
+    throw NotImplemented ("adaptive refinement (hanging nodes) is not available: use global refinement");
 
   prm_.enter_subsection ("Problem dependent parameters");
   func_pressure.initialize ("time", prm_.get ("Pressure"));
@@ -116,6 +122,12 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
   E_modulus = prm_.get_double ("E modulus");
   lame_coefficient_mu = E_modulus / (2.0 * (1 + poisson_ratio_nu));
   lame_coefficient_lambda = (2 * poisson_ratio_nu * lame_coefficient_mu) / (1.0 - 2 * poisson_ratio_nu);
+  if (miehe ())
+    {
+      // Miehe 2010: the Lame coefficients are given directly (cracks.cc:1512-1521)
+      lame_coefficient_mu = prm_.get_double ("Lame mu");
+      lame_coefficient_lambda = prm_.get_double ("Lame lambda");
+    }
   prm_.leave_subsection ();
 
   timestep_number = 0;
@@ -123,13 +135,16 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
 
   // setup_mesh(): "rect -10 -10 [-10] 10 10 [10]", 10 cells per direction,
   // then refine_global (cracks.cc:1207-1253, 1534)
+  // Miehe tests: meshes/unit_slit.inp, 2 x 2 cells on the unit square with the slit (1202-1205)
   mesh_.dim = dim_;
-  const int n = 10 << n_global_pre_refine;
+  mesh_.slit = miehe () ? 1 : 0;
+  const int n = (miehe () ? 2 : 10) << n_global_pre_refine;
+  const double length = miehe () ? 1.0 : 20.0, lower = miehe () ? 0.0 : -10.0;
   for (int d = 0; d < 3; ++d)
     {
       mesh_.n[d] = d < dim_ ? n : 1;
-      mesh_.h[d] = d < dim_ ? 20.0 / n : 1.0;
-      mesh_.origin[d] = d < dim_ ? -10.0 : 0.0;
+      mesh_.h[d] = d < dim_ ? length / n : 1.0;
+      mesh_.origin[d] = d < dim_ ? lower : 0.0;
     }
   long long cells = 1;
   for (int d = 0; d < dim_; ++d)
@@ -145,8 +160,8 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
   decompose_stress_rhs = prm_.get_double ("Decompose stress in rhs");
   decompose_stress_matrix = prm_.get_double ("Decompose stress in matrix");
   prm_.leave_subsection ();
-  if (decompose_stress_rhs > 0 || decompose_stress_matrix > 0)
-    throw NotImplemented ("the Miehe stress split (2-D only in the reference) is not available yet");
+  if ((decompose_stress_rhs > 0 || decompose_stress_matrix > 0) && dim_ != 2)
+    throw NotImplemented ("the Miehe stress split is 2-D only (cracks.cc:1923-2120)");
   if (direct_solver)
     pcout_ << "note: 'Use Direct Inner Solver' is ignored, the GPU path always solves matrix-free" << std::endl;
   use_old_timestep_pf = false;
@@ -160,6 +175,11 @@ FracturePhaseFieldProblem::determine_mesh_dependent_parameters ()
   for (int d = 0; d < dim_; ++d)
     d2 += mesh_.h[d] * mesh_.h[d];
   min_cell_diameter = std::sqrt (d2);
+  // the Miehe tests use the h the mesh will have on its final level (cracks.cc:3839-3854);
+  // the coarse cells of unit_slit.inp have diameter sqrt(2)/2
+  if (miehe ())
+    min_cell_diameter = 0.5 * std::sqrt (2.0)
+                        * std::pow (2.0, -1.0 * (n_global_pre_refine + n_refinement_cycles + n_local_pre_refine));
   FunctionParser func;
   prm_.enter_subsection ("Problem dependent parameters");
   func.initialize ("h", prm_.get ("K reg"));
@@ -182,10 +202,17 @@ FracturePhaseFieldProblem::setup_system ()
   params_.alpha_biot = 0.0; // cracks.cc:1497
   const int rc = pf_create (&mesh_, &params_, device, 0, 1, nullptr, &ctx_);
   pf_check (ctx_, rc);
-  pf_check (ctx_, pf_set_dirichlet_all_faces (ctx_)); // set_newton_bc, cracks.cc:2575-2583 / 2686-2694
-  long long nodes = 1;
-  for (int d = 0; d < dim_; ++d)
-    nodes *= mesh_.n[d] + 1;
+  if (miehe ())
+    {
+      pf_check (ctx_, pf_dirichlet_miehe (ctx_, miehe_kind (), 0.0, 0)); // set_newton_bc, cracks.cc:2584-2625
+      // the reference solves these small, ill-conditioned systems with a sparse direct solver or
+      // AMG (2750-2771); Jacobi-GMRES needs a basis as long as its iteration count
+      pf_check (ctx_, pf_set_krylov_dim (ctx_, 300));
+      gmres_max_iterations = std::max (gmres_max_iterations, 3000);
+    }
+  else
+    pf_check (ctx_, pf_set_dirichlet_all_faces (ctx_)); // set_newton_bc, cracks.cc:2575-2583 / 2686-2694
+  long long nodes = pf_n_dofs (ctx_) / (dim_ + 1);
   pcout_ << std::endl;
   pcout_ << "DoFs: " << nodes * dim_ << " solid + " << nodes << " phase"
          << " = " << nodes * (dim_ + 1) << std::endl;
@@ -260,12 +287,20 @@ FracturePhaseFieldProblem::write_statistics () const
   ::mkdir (output_folder.c_str (), 0755);
   std::ofstream f ((output_folder + "/statistics").c_str ());
   f << "# 1: Timestep No\n# 2: Time\n# 3: DoFs\n# 4: minimum cell diameter\n# 5: Bulk Energy\n# 6: Crack Energy\n";
+  if (miehe ())
+    f << (miehe_kind () == 1 ? "# 7: Load y\n" : "# 7: Load x\n");
   char buf[256];
   for (const auto &r : statistics_)
     {
       std::snprintf (buf, sizeof buf, "%u %.4f %lld %.8e %.8e %.8e ", r.timestep_no, r.time, r.dofs, r.h_min,
                      r.bulk_energy, r.crack_energy);
-      f << buf << "\n";
+      f << buf;
+      if (miehe ())
+        {
+          std::snprintf (buf, sizeof buf, "%.8e ", r.load);
+          f << buf;
+        }
+      f << "\n";
     }
 }
 
@@ -290,16 +325,16 @@ FracturePhaseFieldProblem::run ()
          << "\n" << std::endl;
 
   // initial condition, project_back_phase_field, old = old_old = solution (4233-4277)
-  pf_check (ctx_, pf_interpolate_sneddon (ctx_, min_cell_diameter));
+  if (miehe ())
+    pf_check (ctx_, pf_interpolate_unbroken (ctx_)); // InitialValuesTensionOrShear, cracks.cc:679-691
+  else
+    pf_check (ctx_, pf_interpolate_sneddon (ctx_, min_cell_diameter));
   pf_check (ctx_, pf_project_phase_field (ctx_));
   old_timestep = timestep;
   old_old_timestep = timestep;
-  long long nodes = 1, cells = 1;
+  long long nodes = pf_n_dofs (ctx_) / (dim_ + 1), cells = 1;
   for (int d = 0; d < dim_; ++d)
-    {
-      nodes *= mesh_.n[d] + 1;
-      cells *= mesh_.n[d];
-    }
+    cells *= mesh_.n[d];
   double finishing_timestep_loop = 0;
 
   do
@@ -324,6 +359,11 @@ FracturePhaseFieldProblem::run ()
           // catch NoConvergence, retry with a tenth of the step and old_timestep_pf (4320-4358)
           use_old_timestep_pf = false;
           pf_check (ctx_, pf_set_time_parameters (ctx_, old_timestep, old_old_timestep, 0, func_pressure.value (time)));
+          // the split is active from the second time step on (cracks.cc:2294, 2338)
+          pf_check (ctx_, pf_set_stress_split (ctx_, decompose_stress_matrix > 0 && timestep_number > 0,
+                                               decompose_stress_rhs, decompose_stress_matrix));
+          if (miehe ())
+            pf_check (ctx_, pf_dirichlet_miehe (ctx_, miehe_kind (), time, 1)); // set_initial_bc(time), 2787
           try
             {
               newton_active_set ();
@@ -347,21 +387,41 @@ FracturePhaseFieldProblem::run ()
       while (true);
 
       pf_check (ctx_, pf_project_phase_field (ctx_));
+      if (miehe () && n_refinement_cycles > 0)
+        {
+          // refine_mesh(), strategy "phase field" (cracks.cc:3971-3995): cells with a phase-field dof
+          // below the threshold would be refined and the step redone.  Hanging nodes are out of scope.
+          double phi_min = 1.0;
+          pf_check (ctx_, pf_phase_field_min (ctx_, &phi_min));
+          if (phi_min < value_phase_field_for_refinement)
+            throw NotImplemented ("refine_mesh() would refine the mesh in time step "
+                                  + std::to_string (timestep_number)
+                                  + " (predictor-corrector refinement with hanging nodes is not available)");
+        }
       timestep = tmp_timestep;
 
-      double bulk = 0, crack = 0;
+      double bulk = 0, crack = 0, load = 0;
       pf_check (ctx_, pf_energy (ctx_, &bulk, &crack));
       pcout_ << std::endl;
       pcout_ << "No " << timestep_number << " time " << time << " bulk energy: " << bulk
-             << " crack energy: " << crack << std::endl;
-      statistics_.push_back ({timestep_number, time, nodes * (dim_ + 1), min_cell_diameter, bulk, crack});
+             << " crack energy: " << crack;
+      if (miehe ())
+        {
+          double lx = 0, ly = 0;
+          pf_check (ctx_, pf_load (ctx_, &lx, &ly)); // compute_load(), cracks.cc:3728-3816
+          load = miehe_kind () == 1 ? ly : lx;
+          pcout_ << (miehe_kind () == 1 ? "  Load y: " : "  Load x: ") << load;
+        }
+      pcout_ << std::endl;
+      statistics_.push_back ({timestep_number, time, nodes * (dim_ + 1), min_cell_diameter, bulk, crack, load});
       write_statistics ();
 
       pf_check (ctx_, pf_timestep_difference (ctx_, &finishing_timestep_loop));
-      pcout_ << "Timestep difference linfty: " << finishing_timestep_loop << std::endl;
+      if (!miehe ())
+        pcout_ << "Timestep difference linfty: " << finishing_timestep_loop << std::endl;
       ++timestep_number;
 
-      if (finishing_timestep_loop < 1.0e-5)
+      if (!miehe () && finishing_timestep_loop < 1.0e-5)
         {
           pf_check (ctx_, pf_tcv (ctx_, &tcv_));
           const double p = func_pressure.value (time), nu = poisson_ratio_nu, E = 1.0, l_0 = 1.0;

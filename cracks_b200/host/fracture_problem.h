@@ -5,10 +5,13 @@
 // the GPU behind the C ABI; this class only sequences calls and keeps the
 // reference's screen / statistics output format.
 //
-// Supported here: `test case = sneddon` on the uniform (globally refined)
-// box, dim 2 or 3, `outer solver = active set`.  Everything else the .prm
-// surface can express is parsed and rejected with ExcNotImplemented-style
-// errors (SURVEY.md section 8f lists it as "next").
+// Supported here, `outer solver = active set`:
+//   `test case = sneddon` on the uniform (globally refined) box, dim 2 or 3;
+//   `test case = miehe tension / miehe shear` (dim 2) on the globally refined
+//   meshes/unit_slit.inp topology, with the stress split and the load
+//   functional, for as long as refine_mesh() would not change the mesh.
+// Everything else the .prm surface can express is parsed and rejected with
+// ExcNotImplemented-style errors (SURVEY.md section 8f lists it as "next").
 #pragma once
 #include <iosfwd>
 #include <string>
@@ -31,6 +34,7 @@ struct StatisticsRow
   double time;
   long long dofs;
   double h_min, bulk_energy, crack_energy;
+  double load = 0; // "Load y" (miehe tension) / "Load x" (miehe shear), cracks.cc:3791-3804
 };
 
 class FracturePhaseFieldProblem
@@ -57,6 +61,8 @@ private:
   void determine_mesh_dependent_parameters ();
   double newton_active_set ();
   void write_statistics () const;
+  bool miehe () const { return test_case == "miehe tension" || test_case == "miehe shear"; }
+  int miehe_kind () const { return test_case == "miehe tension" ? 1 : 2; }
 
   ParameterHandler &prm_;
   int dim_;
@@ -77,6 +83,8 @@ private:
   double lower_bound_newton_residual = 1e-10, line_search_damping = 0.5;
   unsigned max_no_newton_steps = 10, max_no_line_search_steps = 5;
   double decompose_stress_rhs = 0, decompose_stress_matrix = 0;
+  double value_phase_field_for_refinement = 0;
+  std::string refinement_strategy;
   FunctionParser func_pressure;
 
   std::vector<StatisticsRow> statistics_;

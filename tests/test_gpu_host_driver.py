@@ -37,7 +37,62 @@ def test_cli_reproduces_golden_statistics(pf, tmp_path):
 
 def test_cli_rejects_unsupported_cases(pf, tmp_path):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "cracks_b200", "host"), "-s"])
-    (tmp_path / "m.prm").write_text("subsection Global parameters\n set test case = miehe shear\nend\n")
+    (tmp_path / "m.prm").write_text("subsection Global parameters\n set test case = three point bending\nend\n")
     r = subprocess.run([os.path.join(ROOT, "cracks_b200", "cracks_b200_run"), str(tmp_path / "m.prm")],
                        capture_output=True, text=True)
-    assert r.returncode == 1 and "miehe shear" in r.stderr
+    assert r.returncode == 1 and "three point bending" in r.stderr
+
+
+SECTIONS = {
+    "Global parameters": ["Global pre-refinement steps", "Local pre-refinement steps", "Adaptive refinement cycles",
+                          "Max No of timesteps", "Timestep size", "Timestep size to switch to",
+                          "Switch timestep after steps", "outer solver", "test case", "ref strategy",
+                          "value phase field for refinement", "Output filename"],
+    "Problem dependent parameters": ["K reg", "Eps reg", "Gamma penalization", "Pressure", "Fracture toughness G_c",
+                                     "Poisson ratio nu", "E modulus", "Lame mu", "Lame lambda"],
+    "Solver parameters": ["Use Direct Inner Solver", "Newton lower bound", "Newton maximum steps", "Upper Newton rho",
+                          "Line search maximum steps", "Line search damping", "Decompose stress in rhs",
+                          "Decompose stress in matrix"],
+}
+
+
+def _write_prm(path, values, outdir):
+    """A .prm file with the values the golden fixture transcribed from the reference's test prm."""
+    lines = []
+    for sec, keys in SECTIONS.items():
+        lines.append("subsection " + sec)
+        if sec == "Global parameters":
+            lines.append("  set Dimension = 2")
+            lines.append("  set Output directory = " + str(outdir))
+        for k in keys:
+            if k in values:
+                lines.append("  set %s = %s" % (k, values[k]))
+        lines.append("end")
+    path.write_text("\n".join(lines) + "\n")
+
+
+@pytest.mark.parametrize("name,rows,stops", [("miehe_shear_2", 25, False), ("miehe_tension_adaptive_1", 25, True)])
+def test_cli_miehe_goldens(pf, tmp_path, name, rows, stops):
+    """KAT-4 / KAT-3 through `cracks_b200_run file.prm`: the statistics file has the reference's
+    columns (incl. Load x / Load y) and values; the adaptive case stops where refine_mesh() would fire."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "cracks_b200", "host"), "-s"])
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", name + ".json")))
+    _write_prm(tmp_path / "t.prm", g["prm"], tmp_path / "out")
+    r = subprocess.run([os.path.join(ROOT, "cracks_b200", "cracks_b200_run"), str(tmp_path / "t.prm")],
+                       capture_output=True, text=True, timeout=900)
+    print(r.stdout[-2000:], r.stderr[-1000:])
+    assert "DoFs: 594 solid + 297 phase = 891" in r.stdout            # tests/miehe_shear_2.output
+    if stops:
+        assert r.returncode == 1 and "refine_mesh() would refine the mesh in time step 25" in r.stderr
+    else:
+        assert r.returncode == 0, r.stderr
+    text = open(tmp_path / "out" / "statistics").read()
+    assert ("# 7: Load x" if "shear" in name else "# 7: Load y") in text
+    got = [l.split() for l in text.splitlines() if not l.startswith("#")]
+    assert len(got) == rows
+    for row, ref in zip(got, g["statistics"]):
+        assert int(row[0]) == ref["step"] and int(row[2]) == 891
+        assert float(row[3]) == pytest.approx(ref["h"], rel=1e-8)
+        tol = 1e-6 if ref["step"] <= 18 else 1e-3
+        for col, k in ((4, "bulk"), (5, "crack"), (6, "load")):
+            assert float(row[col]) == pytest.approx(ref[k], rel=tol), (ref["step"], k)
