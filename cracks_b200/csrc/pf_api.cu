@@ -147,6 +147,14 @@ struct pf_ctx
   double *mg_b = nullptr, *mg_x = nullptr, *mg_y = nullptr, *mg_d = nullptr, *mg_r = nullptr, *mg_ev = nullptr;
   bool mg_ev_valid = false; // mg_ev holds the eigenvector estimate of the previous set-up
   bool mg_ready = false;
+  // the V-cycle as a CUDA graph (top level only): ~200 small launches and, with several ranks,
+  // ~30 NCCL calls per application collapse into one cudaGraphLaunch.  Re-captured after
+  // every pf_setup_jacobian (the Chebyshev coefficients are kernel arguments).
+  cudaGraphExec_t mg_graph = nullptr;
+  bool mg_graph_valid = false;
+  long long mg_graph_launches = 0;
+  double *mg_in = nullptr;  // fixed input buffer of the captured V-cycle
+  double *mg_out = nullptr; // output buffer it was captured with
   double last_rnorm = 0;
   long long launches = 0;
   bool profiling = false;
@@ -1050,6 +1058,59 @@ mg_vcycle (pf_ctx *ctx, const double *b, double *x)
 int
 precond_apply (pf_ctx *ctx, const double *v, double *z)
 {
+  // Opt-in (PF_MG_GRAPH=1), single rank only.  Measured on B200 at 16.7 M DoF: 9.27 vs 9.26
+  // Newton-its/s, i.e. the V-cycle is not launch-bound on one GPU; with NCCL nodes in the graph
+  // (2 and 4 ranks) the solve ran but the processes hung at tear-down, so it stays off there.
+  static const bool use_graph = getenv ("PF_MG_GRAPH") && atoi (getenv ("PF_MG_GRAPH")) == 1;
+  if (ctx->precond == 1 && ctx->mg_ready && ctx->coarse && use_graph && ctx->nranks == 1 && !ctx->profiling
+      && !g_trace.on)
+    {
+      if (!ctx->mg_in)
+        CU (cudaMalloc (&ctx->mg_in, sizeof (double) * ctx->n_local_dofs));
+      CU (cudaMemcpyAsync (ctx->mg_in, v, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (!ctx->mg_graph_valid || ctx->mg_out != z)
+        {
+          // capture one V-cycle (all levels, halo exchanges on the second stream included)
+          const long long l0 = ctx->launches;
+          cudaGraph_t graph = nullptr;
+          CU (cudaStreamBeginCapture (ctx->stream, cudaStreamCaptureModeThreadLocal));
+          const int rc = mg_vcycle (ctx, ctx->mg_in, z);
+          const cudaError_t ce = cudaStreamEndCapture (ctx->stream, &graph);
+          if (rc || ce != cudaSuccess || !graph)
+            {
+              if (graph)
+                cudaGraphDestroy (graph);
+              cudaGetLastError ();
+              return fail (ctx, rc ? rc : PF_CUDA_ERROR, "multigrid: capturing the V-cycle failed (%s); PF_MG_GRAPH=0 disables it",
+                           rc ? ctx->err.c_str () : cudaGetErrorString (ce));
+            }
+          ctx->mg_graph_launches = ctx->launches - l0;
+          ctx->launches = l0;
+          cudaError_t ie = cudaSuccess;
+          if (ctx->mg_graph)
+            {
+              // same topology as before: update the executable graph in place, re-instantiate if refused
+              cudaGraphExecUpdateResultInfo info;
+              ie = cudaGraphExecUpdate (ctx->mg_graph, graph, &info);
+              if (ie != cudaSuccess)
+                {
+                  cudaGetLastError ();
+                  cudaGraphExecDestroy (ctx->mg_graph);
+                  ctx->mg_graph = nullptr;
+                }
+            }
+          if (!ctx->mg_graph)
+            ie = cudaGraphInstantiate (&ctx->mg_graph, graph, 0);
+          cudaGraphDestroy (graph);
+          if (ie != cudaSuccess)
+            return fail (ctx, PF_CUDA_ERROR, "multigrid: cudaGraphInstantiate: %s", cudaGetErrorString (ie));
+          ctx->mg_graph_valid = true;
+          ctx->mg_out = z;
+        }
+      CU (cudaGraphLaunch (ctx->mg_graph, ctx->stream));
+      ctx->launches += ctx->mg_graph_launches;
+      return PF_OK;
+    }
   if (ctx->precond == 1 && ctx->mg_ready && ctx->coarse)
     return mg_vcycle (ctx, v, z);
   k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->n_local_dofs, ctx->diag, v, z);
@@ -1400,7 +1461,9 @@ pf_destroy (pf_ctx *ctx)
     pf_destroy (ctx->coarse);
   if (ctx->comm && ctx->owns_comm)
     g_nccl.CommDestroy (ctx->comm);
-  for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r, ctx->mg_ev})
+  if (ctx->mg_graph)
+    cudaGraphExecDestroy (ctx->mg_graph);
+  for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r, ctx->mg_ev, ctx->mg_in})
     if (v)
       cudaFree (v);
   void *ptrs[] = {ctx->sol,   ctx->old,  ctx->oldold, ctx->pt,     ctx->diag,  ctx->mass, ctx->r_total,
@@ -1618,6 +1681,7 @@ pf_setup_jacobian (pf_ctx *ctx)
     return rc;
   ctx->jac_ready = true;
   ctx->mg_ready = false;
+  ctx->mg_graph_valid = false;
   if (ctx->precond == 1 && ctx->dim == 3)
     return mg_setup_level (ctx);
   return PF_OK;
