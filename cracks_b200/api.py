@@ -49,6 +49,12 @@ class Layout(C.Structure):
                 ("plane_end", C.c_int), ("owned_begin", C.c_int), ("owned_end", C.c_int), ("ncomp", C.c_int)]
 
 
+class MgLevel(C.Structure):
+    _fields_ = [("n", C.c_int * 3), ("replicated", C.c_int), ("mode_below", C.c_int), ("layout", Layout),
+                ("inject_begin", C.c_int), ("inject_end", C.c_int), ("restrict_begin", C.c_int),
+                ("restrict_end", C.c_int)]
+
+
 def library_path() -> str:
     return os.path.join(_HERE, "libcracks_b200.so")
 
@@ -71,6 +77,7 @@ _SIGS = {
     "pf_get_layout": [C.c_void_p, C.POINTER(Layout)],
     "pf_slab_layout": [C.POINTER(Mesh), C.c_int, C.c_int, C.POINTER(Layout), C.POINTER(C.c_int), C.POINTER(C.c_int),
                        C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "pf_mg_hierarchy": [C.POINTER(Mesh), C.c_int, C.c_int, C.POINTER(MgLevel), C.c_int, C.POINTER(C.c_int)],
     "pf_synchronize": [C.c_void_p],
     "pf_set_state": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double],
     "pf_get_solution": [C.c_void_p, C.c_void_p],
@@ -171,6 +178,23 @@ def exported_symbols_in_header() -> list:
     hdr = open(os.path.join(_HERE, "..", "include", "cracks_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     return sorted(set(re.findall(r"\b(pf_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def mg_hierarchy(mesh: Mesh, rank: int, nranks: int) -> list:
+    """The multigrid levels (fine to coarse) `rank` of `nranks` builds; pure host code, no GPU needed."""
+    levels = (MgLevel * 16)()
+    n = C.c_int()
+    rc = load_library().pf_mg_hierarchy(C.byref(mesh), rank, nranks, levels, 16, C.byref(n))
+    if rc != PF_OK:
+        raise PFError(rc, "pf_mg_hierarchy: bad arguments")
+    out = []
+    for L in levels[: n.value]:
+        lay = L.layout
+        out.append(dict(n=tuple(L.n), replicated=bool(L.replicated), mode_below=L.mode_below,
+                        plane_begin=lay.plane_begin, plane_end=lay.plane_end, owned_begin=lay.owned_begin,
+                        owned_end=lay.owned_end, inject=(L.inject_begin, L.inject_end),
+                        restrict=(L.restrict_begin, L.restrict_end)))
+    return out
 
 
 def slab_layout(mesh: Mesh, rank: int, nranks: int) -> dict:

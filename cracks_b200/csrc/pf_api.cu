@@ -799,15 +799,56 @@ norm2_dev (pf_ctx *ctx, const double *v, double *out)
   return PF_OK;
 }
 
+// ---- hierarchy rules, pure host arithmetic shared with pf_mg_hierarchy() ------
+// a level can be coarsened while every direction stays even and keeps >= 4 cells
+bool
+mg_possible_n (int dim, const int *n)
+{
+  if (dim != 3)
+    return false;
+  for (int d = 0; d < 3; ++d)
+    if (n[d] % 2 != 0 || n[d] / 2 < 4)
+      return false;
+  return true;
+}
+
+bool
+mg_coarse_distributed_n (int nz, int nranks)
+{
+  return nranks > 1 && nz % (2 * nranks) == 0 && nz / (2 * nranks) >= 2;
+}
+
+struct MgRange
+{
+  int a, e;
+};
+
+// coarse planes a rank fills by injection.  mode 1 (coarse level keeps the decomposition): from every
+// local fine plane, its missing upper ghost plane comes from the neighbour; mode 2 (replicated coarse
+// level): from the owned fine planes, so that every coarse plane is filled by exactly one rank
+MgRange
+mg_inject_range (int mode, int f_plane_begin, int f_plane_end, int f_owned_begin, int f_owned_end,
+                 int c_plane_begin, int c_plane_end)
+{
+  const int fa = mode == 2 ? f_owned_begin : f_plane_begin;
+  const int fe = mode == 2 ? f_owned_end : f_plane_end;
+  return {std::max ((fa + 1) / 2, c_plane_begin), std::min ((fe - 1) / 2 + 1, c_plane_end)};
+}
+
+// coarse planes a rank restricts into: its owned coarse planes (mode 1) or the coarse planes whose
+// fine plane 2K it owns (mode 2)
+MgRange
+mg_restrict_range (int mode, int f_owned_begin, int f_owned_end, int c_owned_begin, int c_owned_end)
+{
+  if (mode == 2)
+    return {(f_owned_begin + 1) / 2, (f_owned_end - 1) / 2 + 1};
+  return {c_owned_begin, c_owned_end};
+}
+
 bool
 mg_possible (const pf_ctx *ctx)
 {
-  if (ctx->dim != 3)
-    return false;
-  for (int d = 0; d < 3; ++d)
-    if (ctx->g.n[d] % 2 != 0 || ctx->g.n[d] / 2 < 4)
-      return false;
-  return true;
+  return mg_possible_n (ctx->dim, ctx->g.n);
 }
 
 // The level below keeps the z-slab decomposition while every rank's range of
@@ -816,7 +857,7 @@ mg_possible (const pf_ctx *ctx)
 bool
 mg_coarse_distributed (const pf_ctx *ctx)
 {
-  return ctx->nranks > 1 && ctx->g.n[2] % (2 * ctx->nranks) == 0 && ctx->g.n[2] / (2 * ctx->nranks) >= 2;
+  return mg_coarse_distributed_n (ctx->g.n[2], ctx->nranks);
 }
 
 int create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank, int nranks,
@@ -922,9 +963,9 @@ mg_setup_level (pf_ctx *ctx)
     // coarse planes whose fine plane 2K this rank can read: all local fine planes when the
     // coarse level keeps the decomposition (its missing upper ghost plane comes from the
     // neighbour), the owned ones when it is replicated (every plane filled by exactly one rank)
-    const int fa = ctx->mg_mode == 2 ? ctx->g.owned_begin : ctx->g.plane_begin;
-    const int fe = ctx->mg_mode == 2 ? ctx->g.owned_end : ctx->g.plane_end;
-    const int Ka = std::max ((fa + 1) / 2, c->g.plane_begin), Ke = std::min ((fe - 1) / 2 + 1, c->g.plane_end);
+    const MgRange inj = mg_inject_range (ctx->mg_mode, ctx->g.plane_begin, ctx->g.plane_end, ctx->g.owned_begin,
+                                         ctx->g.owned_end, c->g.plane_begin, c->g.plane_end);
+    const int Ka = inj.a, Ke = inj.e;
     const long long cnt = (long long) c->g.nodes_per_plane * std::max (Ke - Ka, 0);
     if (ctx->mg_mode == 2)
       {
@@ -1028,13 +1069,11 @@ mg_vcycle (pf_ctx *ctx, const double *b, double *x)
     // the restriction reads the fine residual one plane either side of an owned plane
     if ((rc = halo_exchange (ctx, ctx->mg_r, 4)))
       return rc;
-    int Ka = c->g.owned_begin, Ke = c->g.owned_end;
+    const MgRange res = mg_restrict_range (ctx->mg_mode, ctx->g.owned_begin, ctx->g.owned_end, c->g.owned_begin,
+                                           c->g.owned_end);
+    const int Ka = res.a, Ke = res.e;
     if (ctx->mg_mode == 2)
-      {
-        Ka = (ctx->g.owned_begin + 1) / 2;
-        Ke = (ctx->g.owned_end - 1) / 2 + 1;
-        CU (cudaMemsetAsync (c->mg_b, 0, sizeof (double) * c->n_local_dofs, ctx->stream));
-      }
+      CU (cudaMemsetAsync (c->mg_b, 0, sizeof (double) * c->n_local_dofs, ctx->stream));
     const long long cnt = (long long) c->g.nodes_per_plane * std::max (Ke - Ka, 0);
     if (cnt > 0)
       {
@@ -1254,6 +1293,56 @@ pf_slab_layout (const pf_mesh *mesh, int rank, int nranks, pf_local_layout *out,
     *own_cell_begin = cb;
   if (own_cell_end)
     *own_cell_end = ce;
+  return PF_OK;
+}
+
+// Pure host function: the multigrid hierarchy pf_setup_jacobian builds for (rank, nranks) and the
+// plane ranges of its inter-grid transfers, from the same rules the device code uses.
+int
+pf_mg_hierarchy (const pf_mesh *mesh, int rank, int nranks, pf_mg_level *levels, int max_levels, int *n_levels)
+{
+  if (!mesh || !levels || !n_levels || max_levels < 1 || mesh->dim != 3)
+    return PF_BAD_ARG;
+  pf_mesh m = *mesh;
+  int r = rank, nr = nranks, l = 0;
+  for (;; ++l)
+    {
+      if (l >= max_levels)
+        return PF_BAD_ARG;
+      pf_mg_level &L = levels[l];
+      memset (&L, 0, sizeof L);
+      for (int d = 0; d < 3; ++d)
+        L.n[d] = m.n[d];
+      L.replicated = (nranks > 1 && nr == 1) ? 1 : 0;
+      int cb, ce;
+      const int rc = pf_slab_layout (&m, r, nr, &L.layout, &cb, &ce, nullptr, nullptr);
+      if (rc)
+        return rc;
+      if (l > 0)
+        {
+          const pf_mg_level &F = levels[l - 1];
+          const MgRange inj = mg_inject_range (F.mode_below, F.layout.plane_begin, F.layout.plane_end, F.layout.owned_begin,
+                                               F.layout.owned_end, L.layout.plane_begin, L.layout.plane_end);
+          const MgRange res = mg_restrict_range (F.mode_below, F.layout.owned_begin, F.layout.owned_end,
+                                                 L.layout.owned_begin, L.layout.owned_end);
+          L.inject_begin = inj.a, L.inject_end = inj.e;
+          L.restrict_begin = res.a, L.restrict_end = res.e;
+        }
+      if (!mg_possible_n (3, m.n))
+        {
+          L.mode_below = 0;
+          break;
+        }
+      L.mode_below = nr == 1 ? 1 : (mg_coarse_distributed_n (m.n[2], nr) ? 1 : 2);
+      if (L.mode_below == 2)
+        r = 0, nr = 1;
+      for (int d = 0; d < 3; ++d)
+        {
+          m.n[d] /= 2;
+          m.h[d] *= 2.0;
+        }
+    }
+  *n_levels = l + 1;
   return PF_OK;
 }
 

@@ -100,6 +100,20 @@ int pf_get_layout (const pf_ctx *ctx, pf_local_layout *out);
  * 1180); cell_* pointers may be NULL. */
 int pf_slab_layout (const pf_mesh *mesh, int rank, int nranks, pf_local_layout *out, int *cell_begin,
                     int *cell_end, int *own_cell_begin, int *own_cell_end);
+/* One level of the geometric multigrid hierarchy that replaces the reference's ML AMG set-up
+ * (cracks.cc:2477-2497) as `rank` of `nranks` sees it. */
+typedef struct
+{
+  int n[3];                /* cells per direction of this level */
+  int replicated;          /* 1: this level is held completely by every rank (no decomposition) */
+  int mode_below;          /* level below: 0 = none (coarsest), 1 = same z-slab decomposition, 2 = replicated */
+  pf_local_layout layout;  /* node planes this rank holds / owns on this level */
+  int inject_begin, inject_end;     /* coarse planes this rank fills when the state is injected from the level above */
+  int restrict_begin, restrict_end; /* coarse planes this rank restricts the residual of the level above into */
+} pf_mg_level;
+/* Pure host function (no GPU): the hierarchy and transfer ranges pf_setup_jacobian uses, dim 3.
+ * Levels are ordered fine to coarse; *n_levels <= max_levels. */
+int pf_mg_hierarchy (const pf_mesh *mesh, int rank, int nranks, pf_mg_level *levels, int max_levels, int *n_levels);
 int64_t pf_n_dofs (const pf_ctx *ctx);
 /* the CUDA stream all work of this context is enqueued on (a cudaStream_t) */
 void *pf_stream (const pf_ctx *ctx);
