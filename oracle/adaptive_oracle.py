@@ -1,0 +1,373 @@
+"""CPU oracle for locally refined meshes with hanging nodes (TEST INFRASTRUCTURE ONLY --
+never imported by cracks_b200/).
+
+Restates, in numpy/scipy on top of oracle/libpf_oracle.so's raw cell sums, what the
+reference does once `Local pre-refinement steps` / `Adaptive refinement cycles` are
+non-zero (2-D):
+
+  * refine_mesh(), strategy `fixed preref sneddon` (cracks.cc:3901-3923) on the forest of
+    the box mesh, with p4est's 2:1 balance across faces and corners;
+  * DoFTools::make_hanging_node_constraints (1630-1634): an edge midpoint that is a vertex of
+    the refined neighbour but not of the coarse cell is constrained to the mean of the edge ends;
+  * AffineConstraints::distribute_local_to_global / set_zero / distribute for the two
+    constraint sets of the reference: hanging nodes only (system_total_residual, 2446-2456)
+    and hanging nodes + Dirichlet + active set (constraints_update, 2909-2911).  In exact
+    arithmetic these are the congruence C^T J C, C^T r with the interpolation matrix C;
+  * the active-set loop skipping hanging nodes (2855-2857) and re-distributing them (2887-2890);
+  * compute_cod on a line x = const of a non-uniform mesh (3452-3549).
+
+Parity status: PINNED by tests/test_oracle_adaptive.py against the reference's golden
+tests/sneddon_2d_1.{statistics,output} (KAT-2: 124 cells, 453 DoFs incl. 12 hanging nodes).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+import newton_oracle as orc
+
+
+class GMesh(C.Structure):
+    _fields_ = [("n_cells", C.c_long), ("n_nodes", C.c_long), ("cells", C.c_void_p), ("cell_h", C.c_void_p)]
+
+
+def _lib():
+    lib = orc.lib()
+    if not hasattr(lib, "_g_ready"):
+        dp = np.ctypeslib.ndpointer(np.float64, flags="C")
+        GP, PP = C.POINTER(GMesh), C.POINTER(orc.Params)
+        for d in ("2d", "3d"):
+            f = getattr(lib, f"pfo_g_residual_{d}"); f.restype = None; f.argtypes = [GP, PP, dp, dp, dp, dp]
+            f = getattr(lib, f"pfo_g_cell_matrices_{d}"); f.restype = None; f.argtypes = [GP, PP, dp, dp, dp, dp]
+            f = getattr(lib, f"pfo_g_lumped_mass_{d}"); f.restype = None; f.argtypes = [GP, dp]
+            f = getattr(lib, f"pfo_g_functionals_{d}"); f.restype = None; f.argtypes = [GP, PP, dp, dp]
+        lib._g_ready = True
+    return lib
+
+
+class QuadForest:
+    """Forest of quadtrees over an nx x ny box mesh; a cell is (level, i, j) with (i, j) counted in
+    cells of its own level.  refine() splits flagged cells and restores the 2:1 balance across
+    faces and corners the way p4est does for deal.II's parallel::distributed::Triangulation."""
+
+    def __init__(self, nx, ny, lo, hi):
+        self.nx, self.ny, self.lo, self.hi = nx, ny, lo, hi
+        self.cells = {(0, i, j) for j in range(ny) for i in range(nx)}
+
+    # -- geometry ---------------------------------------------------------------
+    def max_level(self):
+        return max(c[0] for c in self.cells)
+
+    def cell_box(self, c):
+        L, i, j = c
+        hx = (self.hi[0] - self.lo[0]) / (self.nx << L)
+        hy = (self.hi[1] - self.lo[1]) / (self.ny << L)
+        return self.lo[0] + i * hx, self.lo[1] + j * hy, hx, hy
+
+    def vertices(self, c):
+        x, y, hx, hy = self.cell_box(c)
+        return [(x, y), (x + hx, y), (x, y + hy), (x + hx, y + hy)]
+
+    # -- refinement -------------------------------------------------------------
+    def _leaf_containing(self, L, i, j):
+        """the active cell covering cell (L, i, j) or None if outside / finer cells cover it"""
+        if i < 0 or j < 0 or i >= (self.nx << L) or j >= (self.ny << L):
+            return None
+        while L >= 0:
+            if (L, i, j) in self.cells:
+                return (L, i, j)
+            L, i, j = L - 1, i >> 1, j >> 1
+        return None
+
+    def refine(self, flagged):
+        for c in list(flagged):
+            self._split(c)
+
+    def _split(self, c):
+        if c not in self.cells:
+            return
+        L, i, j = c
+        # 2:1 balance: before c gets level L + 1 children, no face / corner neighbour may be coarser than L
+        for di in (-1, 0, 1):
+            for dj in (-1, 0, 1):
+                if (di, dj) == (0, 0):
+                    continue
+                nb = self._leaf_containing(L, i + di, j + dj)
+                if nb is not None and nb[0] < L:
+                    self._split(nb)
+        self.cells.discard(c)
+        for b in (0, 1):
+            for a in (0, 1):
+                self.cells.add((L + 1, 2 * i + a, 2 * j + b))
+
+    # -- numbering ---------------------------------------------------------------
+    def build(self):
+        """-> (cells [n][4] node ids, cell_h [n][2], node coordinates [m][2], hanging {node: (a, b)})"""
+        Lm = self.max_level()
+        order = sorted(self.cells, key=lambda c: (c[2] << (Lm - c[0]), c[1] << (Lm - c[0]), c[0]))
+        node_of, coords, cells, hs = {}, [], [], []
+        hx0 = (self.hi[0] - self.lo[0]) / (self.nx << Lm)
+        hy0 = (self.hi[1] - self.lo[1]) / (self.ny << Lm)
+
+        def node(p):
+            if p not in node_of:
+                node_of[p] = len(coords)
+                coords.append((self.lo[0] + p[0] * hx0, self.lo[1] + p[1] * hy0))
+            return node_of[p]
+
+        lattice = []
+        for (L, i, j) in order:
+            s = 1 << (Lm - L)
+            pts = [(i * s, j * s), ((i + 1) * s, j * s), (i * s, (j + 1) * s), ((i + 1) * s, (j + 1) * s)]
+            lattice.append(pts)
+            cells.append([node(p) for p in pts])
+            hs.append((s * hx0, s * hy0))
+        hanging = {}
+        for pts in lattice:
+            for a, b in ((0, 1), (2, 3), (0, 2), (1, 3)):       # the four edges
+                p, q = pts[a], pts[b]
+                if (p[0] + q[0]) % 2 or (p[1] + q[1]) % 2:
+                    continue
+                mid = ((p[0] + q[0]) // 2, (p[1] + q[1]) // 2)
+                if mid in node_of:
+                    hanging[node_of[mid]] = (node_of[p], node_of[q])
+        return (np.array(cells, dtype=np.int64), np.array(hs, dtype=np.float64), np.array(coords, dtype=np.float64),
+                hanging)
+
+
+class AdaptiveProblem:
+    """(u, phi) problem on a QuadForest mesh: raw cell sums from the C oracle, constraints here."""
+
+    def __init__(self, forest: QuadForest, prm: orc.Params):
+        import scipy.sparse as sp
+        self.forest, self.prm = forest, prm
+        self.cells, self.cell_h, self.xy, self.hanging = forest.build()
+        self.n_cells, self.n_nodes = self.cells.shape[0], self.xy.shape[0]
+        self.nc, self.dim = 3, 2
+        self.n_dofs = self.n_nodes * 3
+        self.gm = GMesh(self.n_cells, self.n_nodes, self.cells.ctypes.data, self.cell_h.ctypes.data)
+        self.h_min = float(np.min(np.sqrt((self.cell_h ** 2).sum(axis=1))))
+        # H: hanging-node interpolation (identity on regular dofs), cracks.cc:1630-1634
+        rows, cols, vals = [], [], []
+        is_h = np.zeros(self.n_nodes, dtype=bool)
+        for h in self.hanging:
+            is_h[h] = True
+        for n in range(self.n_nodes):
+            for c in range(3):
+                if is_h[n]:
+                    a, b = self.hanging[n]
+                    assert not is_h[a] and not is_h[b]
+                    rows += [n * 3 + c] * 2
+                    cols += [a * 3 + c, b * 3 + c]
+                    vals += [0.5, 0.5]
+                else:
+                    rows.append(n * 3 + c); cols.append(n * 3 + c); vals.append(1.0)
+        self.H = sp.csr_matrix((vals, (rows, cols)), shape=(self.n_dofs,) * 2)
+        self.is_hanging_node = is_h
+        self.is_hanging_dof = np.repeat(is_h, 3)
+        x, y = self.xy[:, 0], self.xy[:, 1]
+        on_b = (x == forest.lo[0]) | (x == forest.hi[0]) | (y == forest.lo[1]) | (y == forest.hi[1])
+        m = np.zeros((self.n_nodes, 3), dtype=bool)
+        m[on_b, :2] = True                                  # u = 0 on boundary ids 0..3, cracks.cc:2575-2583
+        self.dirichlet = m.reshape(-1)
+        # dof indices of the cell matrices
+        dofs = (self.cells[:, :, None] * 3 + np.arange(3)[None, None, :]).reshape(self.n_cells, 12)
+        self._rows = np.repeat(dofs, 12, axis=1).reshape(-1)      # row = test function j
+        self._cols = np.tile(dofs, (1, 12)).reshape(-1)
+
+    def raw_residual(self, sol, old, oldold):
+        r = np.empty(self.n_dofs)
+        _lib().pfo_g_residual_2d(C.byref(self.gm), C.byref(self.prm), sol, old, oldold, r)
+        return r
+
+    def raw_jacobian(self, sol, old, oldold):
+        import scipy.sparse as sp
+        mats = np.empty(self.n_cells * 144)
+        _lib().pfo_g_cell_matrices_2d(C.byref(self.gm), C.byref(self.prm), sol, old, oldold, mats)
+        return sp.coo_matrix((mats, (self._rows, self._cols)), shape=(self.n_dofs,) * 2).tocsr()
+
+    def lumped_mass(self):
+        m = np.empty(self.n_nodes)
+        _lib().pfo_g_lumped_mass_2d(C.byref(self.gm), m)
+        return m
+
+    def functionals(self, sol):
+        out = np.zeros(3)
+        _lib().pfo_g_functionals_2d(C.byref(self.gm), C.byref(self.prm), sol, out)
+        return out                                            # bulk, crack, tcv
+
+    def distribute_hanging(self, v):
+        return self.H @ v
+
+    def cod(self, sol, eval_line):
+        """compute_cod(eval_line), cracks.cc:3452-3549, on a mesh whose cells differ in size"""
+        gq = 0.5 * math.sqrt(3.0 / 5.0)
+        xi, w = (0.5 - gq, 0.5, 0.5 + gq), (5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0)
+        s = sol.reshape(-1, 3)
+        total, faces = 0.0, 0
+        for c in range(self.n_cells):
+            nodes, (hx, hy) = self.cells[c], self.cell_h[c]
+            x0 = self.xy[nodes[0], 0]
+            for side in (0, 1):
+                fx = x0 + side * hx
+                if not (eval_line - 1e-8 < fx < eval_line + 1e-8):
+                    continue
+                faces += 1
+                for q in range(3):
+                    pt = (float(side), xi[q])
+                    u, g = np.zeros(2), np.zeros(2)
+                    for v in range(4):
+                        bx, by = v & 1, (v >> 1) & 1
+                        Nx = pt[0] if bx else 1.0 - pt[0]
+                        Ny = pt[1] if by else 1.0 - pt[1]
+                        u += Nx * Ny * s[nodes[v], :2]
+                        g += np.array([(1.0 if bx else -1.0) / hx * Ny, Nx * (1.0 if by else -1.0) / hy]) * s[nodes[v], 2]
+                    total += 0.5 * float(u @ g) * hy * w[q]
+        return total / 2.0, faces
+
+
+def flag_fixed_preref_sneddon(forest: QuadForest):
+    """cells with a vertex in [-2.5, 2.5] x [-1.25, 1.25] (cracks.cc:3901-3923)"""
+    return [c for c in forest.cells
+            if any(-2.5 <= x <= 2.5 and -1.25 <= y <= 1.25 for x, y in forest.vertices(c))]
+
+
+class AdaptiveSneddonRun:
+    """run() of the reference for `test case = sneddon`, dim 2, `ref strategy = fixed preref sneddon`
+    with local pre-refinement (cracks.cc:4166-4581), up to the first adaptive refinement cycle."""
+
+    def __init__(self, global_refine=0, local_pre_refine=1, E=1.0, nu=0.2, G_c=1.0, pressure=1e-3,
+                 kappa_of_h=lambda h: 1e-8 * h, eps_of_h=lambda h: 2.0 * h, newton_lower_bound=1e-7, max_newton=50,
+                 max_line_search=10, line_search_damping=0.5, timestep=1.0, max_no_timesteps=3):
+        n = 10 << global_refine
+        self.forest = QuadForest(n, n, (-10.0, -10.0), (10.0, 10.0))
+        self.prerefinement_h = []
+        for _ in range(local_pre_refine):
+            self.prerefinement_h.append(AdaptiveProblem(self.forest, orc.Params()).h_min)
+            self.forest.refine(flag_fixed_preref_sneddon(self.forest))
+        mu = E / (2.0 * (1 + nu))
+        lam = (2 * nu * mu) / (1.0 - 2 * nu)
+        self.prm = orc.Params(lam, mu, G_c, 0.0, 1.0, pressure, 0.0, 1.0, 1.0, 0, 0, 0.0, 0.0)
+        self.p = AdaptiveProblem(self.forest, self.prm)
+        self.prm.kappa, self.prm.eps = kappa_of_h(self.p.h_min), eps_of_h(self.p.h_min)
+        self.E = E
+        self.lower, self.max_newton = newton_lower_bound, max_newton
+        self.max_ls, self.damp = max_line_search, line_search_damping
+        self.dt, self.max_steps = timestep, max_no_timesteps
+        self.statistics, self.logs, self.diffs = [], [], []
+
+    def initial(self):
+        p = self.p
+        x, y = p.xy[:, 0], p.xy[:, 1]
+        broken = (x * x <= 1.0) & (np.abs(2.0 * y) <= 2.0 * p.h_min)   # InitialValuesSneddon, cracks.cc:381-406
+        sol = np.zeros((p.n_nodes, 3))
+        sol[:, 2] = np.where(broken, 0.0, 1.0)
+        return sol.reshape(-1)
+
+    def newton_active_set(self, sol, old, oldold):
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        p = self.p
+        log = orc.NewtonLog()
+        sol[p.dirichlet] = 0.0                                 # set_initial_bc
+        sol[:] = p.distribute_hanging(sol)
+        # constraints_update still holds the active set of the previous solve (cracks.cc:2790-2794)
+        constrained = self.constrained
+
+        def residuals():
+            raw = p.raw_residual(sol, old, oldold)
+            r_total = p.H.T @ raw                              # hanging-node constraints only
+            r_pde = r_total.copy()
+            r_pde[constrained] = 0.0
+            return r_pde, r_total
+
+        r_pde, r_total = residuals()
+        res = float(np.linalg.norm(r_pde))
+        log.initial_residual = res
+        old_res = res
+        active = np.zeros(p.n_nodes, dtype=bool)
+        cycle = np.zeros(p.n_nodes, dtype=np.int32)
+        mass = self.mass
+        step = 0
+        while True:
+            active_old = active
+            phi, phi_old = sol.reshape(-1, 3)[:, 2], old.reshape(-1, 3)[:, 2]
+            crit = r_total.reshape(-1, 3)[:, 2] / mass + 10.0 * self.E * (phi - phi_old)
+            active = (~p.is_hanging_node) & (~((crit <= 0.0) & (cycle < 5)))
+            n_cyc = int(np.sum(active & (cycle >= 5)))
+            phi[active] = phi_old[active]
+            sol[:] = p.distribute_hanging(sol)
+            cycle[active_old & ~active] += 1
+            con = p.dirichlet.reshape(-1, 3).copy()
+            con[:, 2] |= active
+            constrained = self.constrained = con.reshape(-1)
+            changed = bool(np.any(active != active_old))
+            free = ~(constrained | p.is_hanging_dof)
+            Cm = p.H @ sp.diags(free.astype(float))          # interpolation matrix of constraints_update
+            J = p.raw_jacobian(sol, old, oldold)
+            r_pde, _ = residuals()
+            A = (Cm.T @ J @ Cm + sp.diags((~free).astype(float))).tocsc()
+            update = Cm @ spla.spsolve(A, r_pde)
+            saved = sol.copy()
+            ls, new_res = 0, 0.0
+            while ls < self.max_ls:
+                sol += update
+                r_pde, r_total = residuals()
+                new_res = float(np.linalg.norm(r_pde))
+                if new_res < res:
+                    break
+                sol[:] = saved
+                update *= self.damp
+                ls += 1
+            log.rows.append((step + 1, int(active.sum()), n_cyc, new_res, new_res / res, ls))
+            old_res, res = res, new_res
+            step += 1
+            if res < self.lower and not changed:
+                break
+            if step >= self.max_newton:
+                raise orc.NoConvergence()
+        self.logs.append(log)
+        return res / old_res
+
+    def run(self):
+        p = self.p
+        self.mass = p.lumped_mass()
+        self.constrained = p.dirichlet.copy()                  # constraints_update after setup_system (1637-1641)
+        sol = self.initial()
+        phi = sol.reshape(-1, 3)[:, 2]
+        np.clip(phi, 0.0, 1.0, out=phi)
+        oldold, old = sol.copy(), sol.copy()
+        self.prm.dt_old = self.prm.dt_oldold = self.dt
+        time, step_no = 0.0, 0
+        self.tcv, self.cod = None, None
+        while step_no <= self.max_steps:
+            oldold, old = old, sol.copy()
+            time += self.dt
+            self.newton_active_set(sol, old, oldold)
+            np.clip(phi, 0.0, 1.0, out=phi)
+            sol[:] = p.distribute_hanging(sol)                 # cracks.cc:4416-4417
+            bulk, crack, tcv = p.functionals(sol)
+            diff = float(np.max(np.abs(old - sol)))
+            self.statistics.append(dict(step=step_no, time=time, dofs=p.n_dofs, h=p.h_min, bulk=bulk, crack=crack))
+            self.diffs.append(diff)
+            step_no += 1
+            if diff < 1.0e-5:
+                self.tcv = tcv
+                # compute_functional_values(), cracks.cc:3704-3725: x = -1.5 + i/256; only lines that carry
+                # mesh faces print a value (all vertex abscissae of these meshes are multiples of 1/256)
+                xs_mesh = set(np.round(p.xy[:, 0] * 256.0).astype(int).tolist())
+                self.cod = [(x, v) for i in range(3 * 256 + 1) for x in [-1.5 + i / 256.0]
+                            if int(round(x * 256.0)) in xs_mesh
+                            for v, nf in [p.cod(sol, x)] if nf > 0]
+                break
+        self.solution = sol
+        return self.statistics
+
+    def refined_once_more(self):
+        """DoFs after `Refinement cycle 0` (cracks.cc:4525-4560): same strategy on the current forest"""
+        f = QuadForest(self.forest.nx, self.forest.ny, self.forest.lo, self.forest.hi)
+        f.cells = set(self.forest.cells)
+        f.refine(flag_fixed_preref_sneddon(f))
+        return AdaptiveProblem(f, self.prm)

@@ -46,7 +46,24 @@ typedef struct
   double d_rhs, d_mat;     /* decompose_stress_rhs / decompose_stress_matrix (cracks.cc:1568-1569) */
 } pfo_params;
 
+/* General (locally refined) mesh of axis-aligned Q1 cells, as produced by the reference's
+ * refine_mesh() on the box meshes (cracks.cc:3895-4163): explicit connectivity, one edge-length
+ * vector per cell.  Hanging-node constraints are resolved by the caller (oracle/newton_oracle.py),
+ * these functions return the raw, unconstrained cell sums. */
+typedef struct
+{
+  long n_cells, n_nodes;
+  const long *cells;     /* [n_cells][2^dim] node numbers, vertex order lexicographic (x fastest) */
+  const double *cell_h;  /* [n_cells][dim] edge lengths */
+} pfo_gmesh;
+
 #define PFO_DECL(D) \
+  void pfo_g_residual_##D (const pfo_gmesh *, const pfo_params *, const double *sol, const double *old, \
+                           const double *oldold, double *r_raw); \
+  void pfo_g_cell_matrices_##D (const pfo_gmesh *, const pfo_params *, const double *sol, const double *old, \
+                                const double *oldold, double *mats /* [n_cells][ndpc][ndpc], row = test */); \
+  void pfo_g_lumped_mass_##D (const pfo_gmesh *, double *mass); \
+  void pfo_g_functionals_##D (const pfo_gmesh *, const pfo_params *, const double *sol, double *bulk_crack_tcv); \
   void pfo_residual_##D (const pfo_mesh *, const pfo_params *, const double *sol, const double *old, \
                          const double *oldold, const unsigned char *constrained, double *r_pde, double *r_total); \
   long pfo_csr_nnz_##D (const pfo_mesh *); \

@@ -990,6 +990,113 @@ pfo_load_2d (const pfo_mesh * m, const pfo_params * p, const double *sol, double
 }
 #endif
 
+/* ---- general (locally refined) meshes: raw cell sums, constraints resolved by the caller ---- */
+void
+SUF (pfo_g_residual) (const pfo_gmesh * m, const pfo_params * p, const double *sol, const double *old,
+                      const double *oldold, double *r_raw)
+{
+  for (long i = 0; i < m->n_nodes * NC; ++i)
+    r_raw[i] = 0;
+  for (long c = 0; c < m->n_cells; ++c)
+    {
+      SUF (fe_tab) t;
+      SUF (fe_init) (&t, m->cell_h + c * DIM);
+      const long *nodes = m->cells + c * NV;
+      double ls[NDPC], lo[NDPC], loo[NDPC], rhs[NDPC];
+      SUF (gather) (nodes, sol, ls);
+      SUF (gather) (nodes, old, lo);
+      SUF (gather) (nodes, oldold, loo);
+      SUF (cell_rhs) (&t, p, ls, lo, loo, rhs);
+      for (int v = 0; v < NV; ++v)
+        for (int cc = 0; cc < NC; ++cc)
+          r_raw[nodes[v] * NC + cc] += rhs[v * NC + cc];
+    }
+}
+
+void
+SUF (pfo_g_cell_matrices) (const pfo_gmesh * m, const pfo_params * p, const double *sol, const double *old,
+                           const double *oldold, double *mats)
+{
+#pragma omp parallel for schedule(static)
+  for (long c = 0; c < m->n_cells; ++c)
+    {
+      SUF (fe_tab) t;
+      SUF (fe_init) (&t, m->cell_h + c * DIM);
+      const long *nodes = m->cells + c * NV;
+      double ls[NDPC], lo[NDPC], loo[NDPC];
+      SUF (gather) (nodes, sol, ls);
+      SUF (gather) (nodes, old, lo);
+      SUF (gather) (nodes, oldold, loo);
+      SUF (cell_matrix) (&t, p, ls, lo, loo, mats + c * NDPC * NDPC);
+    }
+}
+
+void
+SUF (pfo_g_lumped_mass) (const pfo_gmesh * m, double *mass)
+{
+  for (long i = 0; i < m->n_nodes; ++i)
+    mass[i] = 0;
+  for (long c = 0; c < m->n_cells; ++c)
+    {
+      double vol = 1;
+      for (int d = 0; d < DIM; ++d)
+        vol *= m->cell_h[c * DIM + d];
+      for (int v = 0; v < NV; ++v)
+        mass[m->cells[c * NV + v]] += 1.0 * 1.0 * (vol / NV);
+    }
+}
+
+/* bulk energy, crack energy (cracks.cc:3663-3681) and TCV (3585-3586) */
+void
+SUF (pfo_g_functionals) (const pfo_gmesh * m, const pfo_params * p, const double *sol, double *out)
+{
+  double eb = 0, ec = 0, tcv = 0;
+  for (long c = 0; c < m->n_cells; ++c)
+    {
+      SUF (fe_tab) t;
+      SUF (fe_init) (&t, m->cell_h + c * DIM);
+      double ls[NDPC];
+      SUF (gather) (m->cells + c * NV, sol, ls);
+      for (int q = 0; q < NQ; ++q)
+        {
+          double pf = 0, gpf[DIM], u[DIM], gu[DIM][DIM];
+          memset (gpf, 0, sizeof (gpf));
+          memset (u, 0, sizeof (u));
+          memset (gu, 0, sizeof (gu));
+          for (int v = 0; v < NV; ++v)
+            {
+              pf += t.N[q][v] * ls[v * NC + DIM];
+              for (int e = 0; e < DIM; ++e)
+                {
+                  u[e] += t.N[q][v] * ls[v * NC + e];
+                  gpf[e] += t.dN[q][v][e] * ls[v * NC + DIM];
+                  for (int cc = 0; cc < DIM; ++cc)
+                    gu[cc][e] += t.dN[q][v][e] * ls[v * NC + cc];
+                }
+            }
+          double trE = 0, trE2 = 0, gg = 0, ug = 0;
+          for (int a = 0; a < DIM; ++a)
+            {
+              trE += gu[a][a];
+              gg += gpf[a] * gpf[a];
+              ug += u[a] * gpf[a];
+              for (int b = 0; b < DIM; ++b)
+                {
+                  const double E = 0.5 * (gu[a][b] + gu[b][a]);
+                  trE2 += E * E;
+                }
+            }
+          const double psi = 0.5 * p->lambda * trE * trE + p->mu * trE2;
+          eb += ((1 + p->kappa) * pf * pf + p->kappa) * psi * t.JxW[q];
+          ec += p->G_c / 2.0 * ((pf - 1) * (pf - 1) / p->eps + p->eps * gg) * t.JxW[q];
+          tcv += ug * t.JxW[q];
+        }
+    }
+  out[0] = eb;
+  out[1] = ec;
+  out[2] = tcv;
+}
+
 void
 SUF (pfo_spmv) (long nrows, const long *rowptr, const int *col, const double *val,
                 const double *x, double *y)

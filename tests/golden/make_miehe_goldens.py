@@ -6,6 +6,7 @@ fixtures travel, the reference does not):
   tests/miehe_shear_2.{prm,statistics,output}            -> miehe_shear_2.json            (KAT-4)
   tests/miehe_tension_adaptive_1.{prm,statistics}        -> miehe_tension_adaptive_1.json (KAT-3)
   the six Catch TEST_CASEs of cracks.cc:1740-1919        -> eigen_2x2.json                (KAT-6)
+  tests/sneddon_2d_1.{prm,statistics,output}             -> sneddon_2d_1.json             (KAT-2, hanging nodes)
 """
 import json
 import math
@@ -37,11 +38,34 @@ def statistics(path):
     return rows
 
 
+def sneddon_2d_1():
+    out = open(f"{REF}/tests/sneddon_2d_1.output").read()
+    rows = []
+    for line in open(f"{REF}/tests/sneddon_2d_1.statistics"):
+        if line.startswith("#") or not line.strip():
+            continue
+        f = line.split()
+        rows.append(dict(step=int(f[0]), time=float(f[1]), dofs=int(f[2]), h=float(f[3]), bulk=float(f[4]),
+                         crack=float(f[5])))
+    tcv = re.search(r"TCV: value= (\S+) exact= (\S+)", out)
+    cod = [(float(a), float(b)) for a, b in re.findall(r"^(-?\d+)  (\S+)$", out, flags=re.M)]
+    d = dict(_source="tjhei/cracks tests/sneddon_2d_1.prm, .statistics, .output (transcribed by make_miehe_goldens.py)",
+             prm=prm_values(f"{REF}/tests/sneddon_2d_1.prm"), statistics=rows,
+             initial_newton_residual=initial_residuals(f"{REF}/tests/sneddon_2d_1.output"),
+             timestep_difference_linfty=[float(x) for x in re.findall(r"Timestep difference linfty: (\S+)", out)],
+             cells=int(re.search(r"Timestep 0: .*Cells: (\d+)", out).group(1)),
+             prerefinement_h=float(re.search(r"Prerefinement step with h= (\S+)", out).group(1)),
+             tcv=float(tcv.group(1)), cod=cod,
+             dofs_after_refinement_cycle_0=int(re.search(r"Refinement cycle 0\s*\n-+\s*\n\s*\nDoFs: .* = (\d+)", out).group(1)))
+    json.dump(d, open(os.path.join(HERE, "sneddon_2d_1.json"), "w"), indent=1)
+
+
 def initial_residuals(path):
     return [float(m.group(1)) for m in re.finditer(r"^0\t\t\t(\S+)$", open(path).read(), flags=re.M)]
 
 
 def main():
+    sneddon_2d_1()
     for name in ("miehe_shear_2", "miehe_tension_adaptive_1"):
         d = dict(_source=f"tjhei/cracks tests/{name}.prm, .statistics, .output (transcribed by make_miehe_goldens.py)",
                  prm=prm_values(f"{REF}/tests/{name}.prm"), statistics=statistics(f"{REF}/tests/{name}.statistics"),

@@ -1,0 +1,93 @@
+"""Pins the hanging-node oracle (oracle/adaptive_oracle.py) against the reference's golden
+tests/sneddon_2d_1.{statistics,output} (KAT-2): Sneddon 2-D with one local
+pre-refinement step -> 124 cells, 453 DoFs of which 12 x 3 sit on hanging nodes.
+This is the oracle for SURVEY 8f rank 3 (hanging nodes / AMR), which the CUDA path does not cover yet."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return json.load(open(os.path.join(HERE, "golden", "sneddon_2d_1.json")))
+
+
+@pytest.fixture(scope="module")
+def run(oracle, golden):
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import adaptive_oracle as ao
+    p = golden["prm"]
+    r = ao.AdaptiveSneddonRun(global_refine=int(p["Global pre-refinement steps"]),
+                              local_pre_refine=int(p["Local pre-refinement steps"]), E=float(p["E modulus"]),
+                              nu=float(p["Poisson ratio nu"]), G_c=float(p["Fracture toughness G_c"]),
+                              pressure=float(p["Pressure"]), newton_lower_bound=float(p["Newton lower bound"]),
+                              max_newton=int(p["Newton maximum steps"]),
+                              max_line_search=int(p["Line search maximum steps"]), timestep=float(p["Timestep size"]),
+                              max_no_timesteps=int(p["Max No of timesteps"]))
+    r.run()
+    return r
+
+
+def test_mesh_with_hanging_nodes(run, golden):
+    p = run.p
+    assert p.n_cells == golden["cells"] == 124
+    assert p.n_dofs == golden["statistics"][0]["dofs"] == 453
+    assert len(p.hanging) == 12                                  # perimeter of the 4 x 2 refined patch
+    assert run.prerefinement_h[0] == pytest.approx(golden["prerefinement_h"], rel=1e-5)
+    assert p.h_min == pytest.approx(golden["statistics"][0]["h"], rel=1e-8)
+    # a hanging node sits in the middle of its two parents
+    for h, (a, b) in p.hanging.items():
+        assert np.allclose(p.xy[h], 0.5 * (p.xy[a] + p.xy[b]))
+    # the mesh after `Refinement cycle 0` of the golden output
+    assert run.refined_once_more().n_dofs == golden["dofs_after_refinement_cycle_0"] == 777
+
+
+def test_kat2_statistics(run, golden):
+    assert len(run.statistics) == len(golden["statistics"]) == 4
+    for got, ref in zip(run.statistics, golden["statistics"]):
+        assert got["time"] == ref["time"]
+        assert got["crack"] == pytest.approx(ref["crack"], rel=1e-8)
+        # row 0 to all printed digits; later rows stop at |r| < 1e-7 with a round-off-determined
+        # active set (top): the reference's own harness accepts 1e-6 absolute
+        assert got["bulk"] == pytest.approx(ref["bulk"], rel=2e-9 if got["step"] == 0 else 5e-8)
+
+
+def test_kat2_newton_and_functionals(run, golden):
+    for lg, ref in zip(run.logs[:3], golden["initial_newton_residual"]):
+        assert lg.initial_residual == pytest.approx(ref, rel=2e-7)           # 7 printed digits
+    for got, ref in zip(run.diffs[:3], golden["timestep_difference_linfty"]):
+        assert got == pytest.approx(ref, rel=2e-6)
+    assert run.diffs[3] < 1e-5                                                # the loop ends at step 3, like the golden
+    assert run.tcv == pytest.approx(golden["tcv"], rel=2e-6)
+    assert [x for x, _ in run.cod] == [x for x, _ in golden["cod"]]
+    for (_, v), (_, ref) in zip(run.cod, golden["cod"]):
+        assert v == pytest.approx(ref, rel=2e-6)
+
+
+def test_constraint_congruence_matches_elimination(run):
+    """C^T J C on the free dofs equals eliminating the hanging rows by hand on one state."""
+    import scipy.sparse as sp
+    p = run.p
+    rng = np.random.default_rng(0)
+    sol = run.solution + 1e-3 * rng.standard_normal(p.n_dofs)
+    sol = p.distribute_hanging(sol)
+    J = p.raw_jacobian(sol, sol, sol).toarray()
+    free = ~(p.dirichlet | p.is_hanging_dof)
+    Cm = (p.H @ sp.diags(free.astype(float))).toarray()
+    A = Cm.T @ J @ Cm
+    x = np.where(free, rng.standard_normal(p.n_dofs), 0.0)
+    full = p.distribute_hanging(x)                       # hanging values follow their parents
+    y = J @ full
+    # fold the hanging rows onto their parents
+    for h, (a, b) in p.hanging.items():
+        for c in range(3):
+            y[a * 3 + c] += 0.5 * y[h * 3 + c]
+            y[b * 3 + c] += 0.5 * y[h * 3 + c]
+            y[h * 3 + c] = 0.0
+    y[~free] = 0.0
+    assert np.allclose(A @ x, y, rtol=1e-12, atol=1e-12 * np.abs(y).max())
