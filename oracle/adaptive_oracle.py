@@ -52,9 +52,30 @@ class QuadForest:
     cells of its own level.  refine() splits flagged cells and restores the 2:1 balance across
     faces and corners the way p4est does for deal.II's parallel::distributed::Triangulation."""
 
-    def __init__(self, nx, ny, lo, hi):
-        self.nx, self.ny, self.lo, self.hi = nx, ny, lo, hi
+    def __init__(self, nx, ny, lo, hi, slit=False):
+        """slit: the topology of meshes/unit_slit.inp -- the line y = mid, x > mid is an internal boundary;
+        the cells above it own doubled nodes, and only the tip (mid, mid) connects the two sides."""
+        self.nx, self.ny, self.lo, self.hi, self.slit = nx, ny, lo, hi, slit
+        assert not slit or (nx % 2 == 0 and ny % 2 == 0)
         self.cells = {(0, i, j) for j in range(ny) for i in range(nx)}
+
+    def copy(self):
+        f = QuadForest(self.nx, self.ny, self.lo, self.hi, self.slit)
+        f.cells = set(self.cells)
+        return f
+
+    def _connected(self, L, i, j, di, dj):
+        """is the level-L position (i + di, j + dj) a face / corner neighbour of (i, j) in the coarse-mesh
+        connectivity?  Across the slit only through points with x <= mid (the tip is a shared vertex)."""
+        if not self.slit or dj == 0:
+            return True
+        half_y, half_x = (self.ny << L) // 2, (self.nx << L) // 2
+        j2 = j + dj
+        if (j < half_y) == (j2 < half_y):
+            return True                                    # same side of the slit line
+        if di == 0:
+            return i <= half_x                             # shared segment [i, i+1] reaches x <= mid
+        return (i + 1 if di > 0 else i) <= half_x          # shared corner point
 
     # -- geometry ---------------------------------------------------------------
     def max_level(self):
@@ -94,6 +115,8 @@ class QuadForest:
             for dj in (-1, 0, 1):
                 if (di, dj) == (0, 0):
                     continue
+                if not self._connected(L, i, j, di, dj):
+                    continue
                 nb = self._leaf_containing(L, i + di, j + dj)
                 if nb is not None and nb[0] < L:
                     self._split(nb)
@@ -111,28 +134,37 @@ class QuadForest:
         hx0 = (self.hi[0] - self.lo[0]) / (self.nx << Lm)
         hy0 = (self.hi[1] - self.lo[1]) / (self.ny << Lm)
 
-        def node(p):
-            if p not in node_of:
-                node_of[p] = len(coords)
-                coords.append((self.lo[0] + p[0] * hx0, self.lo[1] + p[1] * hy0))
-            return node_of[p]
+        xm, ym = (self.nx << Lm) // 2, (self.ny << Lm) // 2
+
+        def key(p, upper):
+            # nodes on the slit line right of the tip exist twice: flag 1 = the copy of the upper side
+            return (p[0], p[1], 1 if (self.slit and upper and p[1] == ym and p[0] > xm) else 0)
+
+        def node(k):
+            if k not in node_of:
+                node_of[k] = len(coords)
+                coords.append((self.lo[0] + k[0] * hx0, self.lo[1] + k[1] * hy0))
+            return node_of[k]
 
         lattice = []
         for (L, i, j) in order:
             s = 1 << (Lm - L)
-            pts = [(i * s, j * s), ((i + 1) * s, j * s), (i * s, (j + 1) * s), ((i + 1) * s, (j + 1) * s)]
-            lattice.append(pts)
-            cells.append([node(p) for p in pts])
+            upper = j * s >= ym
+            pts = [key(p, upper) for p in ((i * s, j * s), ((i + 1) * s, j * s), (i * s, (j + 1) * s),
+                                           ((i + 1) * s, (j + 1) * s))]
+            lattice.append((pts, upper))
+            cells.append([node(k) for k in pts])
             hs.append((s * hx0, s * hy0))
         hanging = {}
-        for pts in lattice:
+        for pts, upper in lattice:
             for a, b in ((0, 1), (2, 3), (0, 2), (1, 3)):       # the four edges
                 p, q = pts[a], pts[b]
                 if (p[0] + q[0]) % 2 or (p[1] + q[1]) % 2:
                     continue
-                mid = ((p[0] + q[0]) // 2, (p[1] + q[1]) // 2)
+                mid = key(((p[0] + q[0]) // 2, (p[1] + q[1]) // 2), upper)
                 if mid in node_of:
                     hanging[node_of[mid]] = (node_of[p], node_of[q])
+        self.order, self.node_of, self.lattice_level = order, node_of, Lm
         return (np.array(cells, dtype=np.int64), np.array(hs, dtype=np.float64), np.array(coords, dtype=np.float64),
                 hanging)
 
@@ -266,12 +298,15 @@ class AdaptiveSneddonRun:
         sol[:, 2] = np.where(broken, 0.0, 1.0)
         return sol.reshape(-1)
 
+    def set_initial_bc(self, sol):
+        sol[self.p.dirichlet] = 0.0                            # u = 0 on the boundary, cracks.cc:2575-2583
+
     def newton_active_set(self, sol, old, oldold):
         import scipy.sparse as sp
         import scipy.sparse.linalg as spla
         p = self.p
         log = orc.NewtonLog()
-        sol[p.dirichlet] = 0.0                                 # set_initial_bc
+        self.set_initial_bc(sol)
         sol[:] = p.distribute_hanging(sol)
         # constraints_update still holds the active set of the previous solve (cracks.cc:2790-2794)
         constrained = self.constrained
@@ -371,3 +406,181 @@ class AdaptiveSneddonRun:
         f.cells = set(self.forest.cells)
         f.refine(flag_fixed_preref_sneddon(f))
         return AdaptiveProblem(f, self.prm)
+
+
+def transfer(old_forest: QuadForest, old_prob: AdaptiveProblem, new_forest: QuadForest, new_prob: AdaptiveProblem,
+             vectors):
+    """SolutionTransfer::interpolate after refinement (cracks.cc:4137-4159): every new cell lies inside one
+    old cell; its vertex values are the bilinear interpolant of that cell's four nodal values."""
+    old_index = {c: k for k, c in enumerate(old_forest.order)}
+    outs = [np.zeros(new_prob.n_dofs) for _ in vectors]
+    done = np.zeros(new_prob.n_nodes, dtype=bool)
+    for k, (L, i, j) in enumerate(new_forest.order):
+        # the old leaf covering this cell
+        l, a, b = L, i, j
+        while (l, a, b) not in old_index:
+            l, a, b = l - 1, a >> 1, b >> 1
+            assert l >= 0, "coarsening is not part of the reference's refinement strategies used here"
+        oc = old_index[(l, a, b)]
+        s = 1 << (L - l)                                   # new cells per old cell edge
+        onodes = old_prob.cells[oc]
+        for v in range(4):
+            n = new_prob.cells[k, v]
+            if done[n]:
+                continue
+            xi = ((i - a * s) + (v & 1)) / s
+            eta = ((j - b * s) + ((v >> 1) & 1)) / s
+            w = ((1 - xi) * (1 - eta), xi * (1 - eta), (1 - xi) * eta, xi * eta)
+            for vec, out in zip(vectors, outs):
+                vv = vec.reshape(-1, 3)
+                out.reshape(-1, 3)[n] = sum(w[q] * vv[onodes[q]] for q in range(4))
+            done[n] = True
+    assert done.all()
+    return outs
+
+
+class AdaptiveMieheRun(AdaptiveSneddonRun):
+    """run() of the reference for `test case = miehe tension / miehe shear` with the predictor-corrector
+    refinement `ref strategy = phase field` (cracks.cc:4166-4581, 3971-3995, 4108-4159): after every
+    converged step cells holding a phase-field dof below the threshold are refined (up to the level cap,
+    2:1 balanced), the three solution vectors are interpolated to the new mesh and the step is redone."""
+
+    def __init__(self, test, refine, timestep, lam, mu, E, G_c=2.7, kappa_of_h=lambda h: 0.0, eps_of_h=lambda h: 2.0 * h,
+                 cycles=1, max_no_timesteps=32, timestep_2=None, switch_timestep=0, newton_lower_bound=1e-6,
+                 max_newton=50, max_line_search=10, line_search_damping=0.6, d_rhs=0.0, d_mat=0.0,
+                 refine_threshold=0.5):
+        assert test in ("miehe tension", "miehe shear")
+        self.test = test
+        self.forest = QuadForest(2, 2, (0.0, 0.0), (1.0, 1.0), slit=True)
+        for _ in range(refine):
+            self.forest.refine(list(self.forest.cells))                       # refine_global
+        self.level_cap = refine + cycles
+        self.h_final = 0.5 * math.sqrt(2.0) * 2.0 ** (-(refine + cycles))    # cracks.cc:3839-3854
+        self.prm = orc.Params(lam, mu, G_c, kappa_of_h(self.h_final), eps_of_h(self.h_final), 0.0, 0.0, 1.0, 1.0, 0,
+                              0, d_rhs, d_mat)
+        self.E, self.d_rhs, self.d_mat = E, d_rhs, d_mat
+        self.lower, self.max_newton = newton_lower_bound, max_newton
+        self.max_ls, self.damp = max_line_search, line_search_damping
+        self.dt, self.max_steps = timestep, max_no_timesteps
+        self.dt2, self.switch, self.threshold = timestep_2, switch_timestep, refine_threshold
+        self.statistics, self.logs, self.diffs = [], [], []
+        self._setup_system()
+
+    def _setup_system(self):
+        """setup_system() on the current forest (cracks.cc:1579-1680)"""
+        self.p = p = AdaptiveProblem(self.forest, self.prm)
+        x, y = p.xy[:, 0], p.xy[:, 1]
+        m = np.zeros((p.n_nodes, 3), dtype=bool)
+        top, bottom, left, right = y == 1.0, y == 0.0, x == 0.0, x == 1.0
+        if self.test == "miehe tension":
+            m[bottom, 1] = True
+            m[top, 0] = m[top, 1] = True
+        else:
+            m[left, 1] = m[right, 1] = True
+            m[bottom, 0] = m[bottom, 1] = True
+            m[top, 0] = m[top, 1] = True
+            upper_copy = np.zeros(p.n_nodes, dtype=bool)
+            for k, n in self.forest.node_of.items():
+                upper_copy[n] = k[2] == 1
+            m[(y == 0.5) & (x >= 0.5) & ~upper_copy, 1] = True                # boundary id 4: lower slit face
+        p.dirichlet = m.reshape(-1)
+        self._top = np.where(top)[0]
+        self.mass = p.lumped_mass()
+        self.constrained = p.dirichlet.copy()
+
+    def set_initial_bc(self, sol):
+        time = self._time
+        s = sol.reshape(-1, 3)
+        con = self.p.dirichlet.reshape(-1, 3)
+        for c in range(2):
+            s[con[:, c], c] = 0.0
+        if self.test == "miehe tension":
+            s[self._top, 1] = time
+        else:
+            s[self._top, 0] = -time
+
+    def load(self, sol):
+        """compute_load() on the top edge (cracks.cc:3728-3816)"""
+        p = self.p
+        gq = 0.5 * math.sqrt(3.0 / 5.0)
+        xi, w = (0.5 - gq, 0.5, 0.5 + gq), (5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0)
+        s = sol.reshape(-1, 3)
+        lx = ly = 0.0
+        for c in range(p.n_cells):
+            nodes, (hx, hy) = p.cells[c], p.cell_h[c]
+            if p.xy[nodes[2], 1] != 1.0:
+                continue
+            for q in range(3):
+                gu = np.zeros((2, 2))
+                for v in range(4):
+                    bx, by = v & 1, (v >> 1) & 1
+                    Nx, Ny = (xi[q] if bx else 1.0 - xi[q]), (1.0 if by else 0.0)
+                    g = np.array([(1.0 if bx else -1.0) / hx * Ny, Nx * (1.0 if by else -1.0) / hy])
+                    gu += np.outer(s[nodes[v], :2], g)
+                tr = gu[0, 0] + gu[1, 1]
+                lx += self.prm.mu * (gu[0, 1] + gu[1, 0]) * hx * w[q]
+                ly += (self.prm.lam * tr + 2 * self.prm.mu * gu[1, 1]) * hx * w[q]
+        return -lx, ly
+
+    def refine_mesh(self, vectors):
+        """-> (changed, transferred vectors).  Strategy `phase field` + level cap + 2:1 balance."""
+        p = self.p
+        phi = vectors[0].reshape(-1, 3)[:, 2]
+        flagged = [c for k, c in enumerate(self.forest.order)
+                   if c[0] < self.level_cap and np.any(phi[p.cells[k]] < self.threshold)]
+        if not flagged:
+            return False, vectors
+        old_forest, old_prob = self.forest, p
+        self.forest = old_forest.copy()
+        self.forest.refine(flagged)
+        self._setup_system()
+        return True, transfer(old_forest, old_prob, self.forest, self.p, vectors)
+
+    def run(self):
+        sol = np.zeros((self.p.n_nodes, 3))
+        sol[:, 2] = 1.0
+        sol = sol.reshape(-1)
+        oldold, old = sol.copy(), sol.copy()
+        dt = self.dt
+        dt_old = dt_oldold = dt
+        time, step_no = 0.0, 0
+        self.redone = []
+        while step_no <= self.max_steps:
+            if self.switch > 0 and step_no > self.switch:
+                dt = self.dt2
+            tmp_dt = dt
+            dt_oldold, dt_old = dt_old, dt
+            oldold, old = old, sol.copy()
+            while True:                                                       # redo_step
+                self.prm.dt_old, self.prm.dt_oldold = dt_old, dt_oldold
+                self.prm.split = 1 if (self.d_mat > 0 and step_no > 0) else 0
+                time += dt
+                while True:
+                    try:
+                        self._time = time
+                        self.newton_active_set(sol, old, oldold)
+                        break
+                    except orc.NoConvergence:
+                        sol[:] = old
+                        time -= dt
+                        dt /= 10.0
+                        time += dt
+                        if dt < 1e-6 * tmp_dt:
+                            raise                                         # the reference would cut for ever
+                phi = sol.reshape(-1, 3)[:, 2]
+                np.clip(phi, 0.0, 1.0, out=phi)
+                sol[:] = self.p.distribute_hanging(sol)
+                changed, (sol, old, oldold) = self.refine_mesh([sol, old, oldold])
+                if not changed:
+                    break
+                self.redone.append(step_no)                                   # "MESH CHANGED!", cracks.cc:4421-4431
+                time -= dt
+                sol = old.copy()
+            dt = tmp_dt
+            bulk, crack, _ = self.p.functionals(sol)
+            lx, ly = self.load(sol)
+            self.statistics.append(dict(step=step_no, time=time, dofs=self.p.n_dofs, h=self.h_final, bulk=bulk,
+                                        crack=crack, load=ly if self.test == "miehe tension" else lx))
+            step_no += 1
+        self.solution = sol
+        return self.statistics
