@@ -5,6 +5,7 @@ fixtures travel, the reference does not):
 
   tests/miehe_shear_2.{prm,statistics,output}            -> miehe_shear_2.json            (KAT-4)
   tests/miehe_tension_adaptive_1.{prm,statistics}        -> miehe_tension_adaptive_1.json (KAT-3)
+  tests/miehe_shear_1.{prm,statistics,output}            -> miehe_shear_1.json            (adaptive shear, split)
   the six Catch TEST_CASEs of cracks.cc:1740-1919        -> eigen_2x2.json                (KAT-6)
   tests/sneddon_2d_1.{prm,statistics,output}             -> sneddon_2d_1.json             (KAT-2, hanging nodes)
 """
@@ -66,7 +67,7 @@ def initial_residuals(path):
 
 def main():
     sneddon_2d_1()
-    for name in ("miehe_shear_2", "miehe_tension_adaptive_1"):
+    for name in ("miehe_shear_2", "miehe_tension_adaptive_1", "miehe_shear_1"):
         d = dict(_source=f"tjhei/cracks tests/{name}.prm, .statistics, .output (transcribed by make_miehe_goldens.py)",
                  prm=prm_values(f"{REF}/tests/{name}.prm"), statistics=statistics(f"{REF}/tests/{name}.statistics"),
                  initial_newton_residual=initial_residuals(f"{REF}/tests/{name}.output"))

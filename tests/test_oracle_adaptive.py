@@ -124,3 +124,33 @@ def test_kat3_miehe_tension_with_predictor_corrector_refinement(oracle):
             if k == 31 and key == "bulk":
                 continue                                              # fully broken specimen: 5 % spread
             assert got[key] == pytest.approx(ref[key], rel=tol), (k, key)
+
+
+def test_miehe_shear_1_adaptive_with_split(oracle):
+    """tests/miehe_shear_1.statistics: stress split + predictor-corrector refinement + hanging nodes
+    (DoFs 891 -> 918 -> 984 -> 1068 -> 1173 -> 1506).  All 9 printed digits on rows 0-9."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import adaptive_oracle as ao
+    g = json.load(open(os.path.join(HERE, "golden", "miehe_shear_1.json")))
+    p = g["prm"]
+    fh = lambda expr: (lambda h: eval(expr, {"h": h, "pow": pow}))
+    run = ao.AdaptiveMieheRun(p["test case"], int(p["Global pre-refinement steps"]), float(p["Timestep size"]),
+                              float(p["Lame lambda"]), float(p["Lame mu"]), float(p["E modulus"]),
+                              G_c=float(p["Fracture toughness G_c"]), kappa_of_h=fh(p["K reg"]), eps_of_h=fh(p["Eps reg"]),
+                              cycles=int(p["Adaptive refinement cycles"]), max_no_timesteps=int(p["Max No of timesteps"]),
+                              timestep_2=float(p["Timestep size to switch to"]),
+                              switch_timestep=int(p["Switch timestep after steps"]),
+                              newton_lower_bound=float(p["Newton lower bound"]), max_newton=int(p["Newton maximum steps"]),
+                              max_line_search=int(p["Line search maximum steps"]),
+                              line_search_damping=float(p["Line search damping"]),
+                              d_rhs=float(p["Decompose stress in rhs"]), d_mat=float(p["Decompose stress in matrix"]),
+                              refine_threshold=float(p["value phase field for refinement"]))
+    stats = run.run()
+    assert [r["dofs"] for r in stats] == [r["dofs"] for r in g["statistics"]]
+    assert [r["dofs"] for r in stats[5:]] == [891, 918, 984, 1068, 1173, 1506]
+    for got, ref in zip(stats, g["statistics"]):
+        tol = 2e-8 if got["step"] <= 9 else 1e-5
+        for key in ("bulk", "crack", "load"):
+            assert got[key] == pytest.approx(ref[key], rel=tol), (got["step"], key)
+    for lg_first, ref in zip([run.logs[0]], g["initial_newton_residual"]):
+        assert lg_first.initial_residual == pytest.approx(ref, rel=2e-6)
