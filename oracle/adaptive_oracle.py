@@ -30,7 +30,8 @@ import newton_oracle as orc
 
 
 class GMesh(C.Structure):
-    _fields_ = [("n_cells", C.c_long), ("n_nodes", C.c_long), ("cells", C.c_void_p), ("cell_h", C.c_void_p)]
+    _fields_ = [("n_cells", C.c_long), ("n_nodes", C.c_long), ("cells", C.c_void_p), ("cell_h", C.c_void_p),
+                ("cell_lame", C.c_void_p)]
 
 
 def _lib():
@@ -170,16 +171,20 @@ class QuadForest:
 
 
 class AdaptiveProblem:
-    """(u, phi) problem on a QuadForest mesh: raw cell sums from the C oracle, constraints here."""
+    """(u, phi) problem on a forest mesh (QuadForest / OctForest): raw cell sums from the C oracle,
+    constraints here.  hanging = {node: (parents...)} with equal weights 1/len(parents)."""
 
-    def __init__(self, forest: QuadForest, prm: orc.Params):
+    def __init__(self, forest, prm: orc.Params):
         import scipy.sparse as sp
         self.forest, self.prm = forest, prm
         self.cells, self.cell_h, self.xy, self.hanging = forest.build()
+        self.dim = dim = self.cell_h.shape[1]
+        self.nc = nc = dim + 1
+        self.sfx = f"{dim}d"
         self.n_cells, self.n_nodes = self.cells.shape[0], self.xy.shape[0]
-        self.nc, self.dim = 3, 2
-        self.n_dofs = self.n_nodes * 3
-        self.gm = GMesh(self.n_cells, self.n_nodes, self.cells.ctypes.data, self.cell_h.ctypes.data)
+        self.n_dofs = self.n_nodes * nc
+        self.cell_lame = None                                # set_cell_lame() for heterogeneous materials
+        self.gm = GMesh(self.n_cells, self.n_nodes, self.cells.ctypes.data, self.cell_h.ctypes.data, None)
         self.h_min = float(np.min(np.sqrt((self.cell_h ** 2).sum(axis=1))))
         # H: hanging-node interpolation (identity on regular dofs), cracks.cc:1630-1634
         rows, cols, vals = [], [], []
@@ -187,47 +192,60 @@ class AdaptiveProblem:
         for h in self.hanging:
             is_h[h] = True
         for n in range(self.n_nodes):
-            for c in range(3):
+            for c in range(nc):
                 if is_h[n]:
-                    a, b = self.hanging[n]
-                    assert not is_h[a] and not is_h[b]
-                    rows += [n * 3 + c] * 2
-                    cols += [a * 3 + c, b * 3 + c]
-                    vals += [0.5, 0.5]
+                    parents = self.hanging[n]
+                    assert not any(is_h[q] for q in parents)
+                    rows += [n * nc + c] * len(parents)
+                    cols += [q * nc + c for q in parents]
+                    vals += [1.0 / len(parents)] * len(parents)
                 else:
-                    rows.append(n * 3 + c); cols.append(n * 3 + c); vals.append(1.0)
+                    rows.append(n * nc + c); cols.append(n * nc + c); vals.append(1.0)
         self.H = sp.csr_matrix((vals, (rows, cols)), shape=(self.n_dofs,) * 2)
         self.is_hanging_node = is_h
-        self.is_hanging_dof = np.repeat(is_h, 3)
-        x, y = self.xy[:, 0], self.xy[:, 1]
-        on_b = (x == forest.lo[0]) | (x == forest.hi[0]) | (y == forest.lo[1]) | (y == forest.hi[1])
-        m = np.zeros((self.n_nodes, 3), dtype=bool)
-        m[on_b, :2] = True                                  # u = 0 on boundary ids 0..3, cracks.cc:2575-2583
+        self.is_hanging_dof = np.repeat(is_h, nc)
+        on_b = np.zeros(self.n_nodes, dtype=bool)
+        for d in range(dim):
+            on_b |= (self.xy[:, d] == forest.lo[d]) | (self.xy[:, d] == forest.hi[d])
+        m = np.zeros((self.n_nodes, nc), dtype=bool)
+        m[on_b, :dim] = True                                # u = 0 on every face, cracks.cc:2575-2583, 2686-2694
         self.dirichlet = m.reshape(-1)
         # dof indices of the cell matrices
-        dofs = (self.cells[:, :, None] * 3 + np.arange(3)[None, None, :]).reshape(self.n_cells, 12)
-        self._rows = np.repeat(dofs, 12, axis=1).reshape(-1)      # row = test function j
-        self._cols = np.tile(dofs, (1, 12)).reshape(-1)
+        ndpc = self.cells.shape[1] * nc
+        self.ndpc = ndpc
+        dofs = (self.cells[:, :, None] * nc + np.arange(nc)[None, None, :]).reshape(self.n_cells, ndpc)
+        self._rows = np.repeat(dofs, ndpc, axis=1).reshape(-1)    # row = test function j
+        self._cols = np.tile(dofs, (1, ndpc)).reshape(-1)
+
+    def set_cell_lame(self, lame_assembly, lame_energy):
+        """per-cell (lambda, mu): the values assemble_system uses and the ones compute_energy uses"""
+        self._lame_a = np.ascontiguousarray(lame_assembly, dtype=np.float64)
+        self._lame_e = np.ascontiguousarray(lame_energy, dtype=np.float64)
+        self.gm.cell_lame = self._lame_a.ctypes.data
 
     def raw_residual(self, sol, old, oldold):
         r = np.empty(self.n_dofs)
-        _lib().pfo_g_residual_2d(C.byref(self.gm), C.byref(self.prm), sol, old, oldold, r)
+        getattr(_lib(), f"pfo_g_residual_{self.sfx}")(C.byref(self.gm), C.byref(self.prm), sol, old, oldold, r)
         return r
 
     def raw_jacobian(self, sol, old, oldold):
         import scipy.sparse as sp
-        mats = np.empty(self.n_cells * 144)
-        _lib().pfo_g_cell_matrices_2d(C.byref(self.gm), C.byref(self.prm), sol, old, oldold, mats)
+        mats = np.empty(self.n_cells * self.ndpc * self.ndpc)
+        getattr(_lib(), f"pfo_g_cell_matrices_{self.sfx}")(C.byref(self.gm), C.byref(self.prm), sol, old, oldold, mats)
         return sp.coo_matrix((mats, (self._rows, self._cols)), shape=(self.n_dofs,) * 2).tocsr()
 
     def lumped_mass(self):
         m = np.empty(self.n_nodes)
-        _lib().pfo_g_lumped_mass_2d(C.byref(self.gm), m)
+        getattr(_lib(), f"pfo_g_lumped_mass_{self.sfx}")(C.byref(self.gm), m)
         return m
 
     def functionals(self, sol):
         out = np.zeros(3)
-        _lib().pfo_g_functionals_2d(C.byref(self.gm), C.byref(self.prm), sol, out)
+        if self.cell_lame is None and hasattr(self, "_lame_e"):
+            self.gm.cell_lame = self._lame_e.ctypes.data      # compute_energy's coefficients (cracks.cc:3651)
+        getattr(_lib(), f"pfo_g_functionals_{self.sfx}")(C.byref(self.gm), C.byref(self.prm), sol, out)
+        if hasattr(self, "_lame_a"):
+            self.gm.cell_lame = self._lame_a.ctypes.data
         return out                                            # bulk, crack, tcv
 
     def distribute_hanging(self, v):
@@ -328,15 +346,16 @@ class AdaptiveSneddonRun:
         step = 0
         while True:
             active_old = active
-            phi, phi_old = sol.reshape(-1, 3)[:, 2], old.reshape(-1, 3)[:, 2]
-            crit = r_total.reshape(-1, 3)[:, 2] / mass + 10.0 * self.E * (phi - phi_old)
+            nc, dim = p.nc, p.dim
+            phi, phi_old = sol.reshape(-1, nc)[:, dim], old.reshape(-1, nc)[:, dim]
+            crit = r_total.reshape(-1, nc)[:, dim] / mass + 10.0 * self.E * (phi - phi_old)
             active = (~p.is_hanging_node) & (~((crit <= 0.0) & (cycle < 5)))
             n_cyc = int(np.sum(active & (cycle >= 5)))
             phi[active] = phi_old[active]
             sol[:] = p.distribute_hanging(sol)
             cycle[active_old & ~active] += 1
-            con = p.dirichlet.reshape(-1, 3).copy()
-            con[:, 2] |= active
+            con = p.dirichlet.reshape(-1, nc).copy()
+            con[:, dim] |= active
             constrained = self.constrained = con.reshape(-1)
             changed = bool(np.any(active != active_old))
             free = ~(constrained | p.is_hanging_dof)
@@ -581,6 +600,179 @@ class AdaptiveMieheRun(AdaptiveSneddonRun):
             lx, ly = self.load(sol)
             self.statistics.append(dict(step=step_no, time=time, dofs=self.p.n_dofs, h=self.h_final, bulk=bulk,
                                         crack=crack, load=ly if self.test == "miehe tension" else lx))
+            step_no += 1
+        self.solution = sol
+        return self.statistics
+
+
+
+class OctForest:
+    """3-D counterpart of QuadForest (no slit): forest of octrees over an nx x ny x nz box mesh with
+    p4est's full 2:1 balance (faces, edges, corners).  Hanging nodes: edge midpoints (two parents) and
+    face centres (four parents) of cells whose neighbour is one level finer."""
+
+    def __init__(self, n, lo, hi):
+        self.n, self.lo, self.hi = tuple(n), tuple(lo), tuple(hi)
+        self.cells = {(0, i, j, k) for k in range(n[2]) for j in range(n[1]) for i in range(n[0])}
+
+    def copy(self):
+        f = OctForest(self.n, self.lo, self.hi)
+        f.cells = set(self.cells)
+        return f
+
+    def cell_size(self, L):
+        return tuple((self.hi[d] - self.lo[d]) / (self.n[d] << L) for d in range(3))
+
+    def centre(self, c):
+        h = self.cell_size(c[0])
+        return tuple(self.lo[d] + (c[1 + d] + 0.5) * h[d] for d in range(3))
+
+    def vertices(self, c):
+        h = self.cell_size(c[0])
+        return [tuple(self.lo[d] + (c[1 + d] + ((v >> d) & 1)) * h[d] for d in range(3)) for v in range(8)]
+
+    def _leaf_containing(self, L, idx):
+        if any(idx[d] < 0 or idx[d] >= (self.n[d] << L) for d in range(3)):
+            return None
+        i, j, k = idx
+        while L >= 0:
+            if (L, i, j, k) in self.cells:
+                return (L, i, j, k)
+            L, i, j, k = L - 1, i >> 1, j >> 1, k >> 1
+        return None
+
+    def refine(self, flagged):
+        for c in list(flagged):
+            self._split(c)
+
+    def _split(self, c):
+        if c not in self.cells:
+            return
+        L, i, j, k = c
+        for di in (-1, 0, 1):
+            for dj in (-1, 0, 1):
+                for dk in (-1, 0, 1):
+                    if (di, dj, dk) == (0, 0, 0):
+                        continue
+                    nb = self._leaf_containing(L, (i + di, j + dj, k + dk))
+                    if nb is not None and nb[0] < L:
+                        self._split(nb)
+        self.cells.discard(c)
+        for v in range(8):
+            self.cells.add((L + 1, 2 * i + (v & 1), 2 * j + ((v >> 1) & 1), 2 * k + ((v >> 2) & 1)))
+
+    def build(self):
+        Lm = max(c[0] for c in self.cells)
+        order = sorted(self.cells, key=lambda c: (c[3] << (Lm - c[0]), c[2] << (Lm - c[0]), c[1] << (Lm - c[0]), c[0]))
+        h0 = self.cell_size(Lm)
+        node_of, coords, cells, hs, lattice = {}, [], [], [], []
+
+        def node(pt):
+            if pt not in node_of:
+                node_of[pt] = len(coords)
+                coords.append(tuple(self.lo[d] + pt[d] * h0[d] for d in range(3)))
+            return node_of[pt]
+
+        for c in order:
+            s = 1 << (Lm - c[0])
+            pts = [tuple((c[1 + d] + ((v >> d) & 1)) * s for d in range(3)) for v in range(8)]
+            lattice.append(pts)
+            cells.append([node(pt) for pt in pts])
+            hs.append(tuple(s * h0[d] for d in range(3)))
+        hanging = {}
+        edges = [(a, a | (1 << d)) for d in range(3) for a in range(8) if not a & (1 << d)]
+        faces = [[a for a in range(8) if ((a >> d) & 1) == side] for d in range(3) for side in (0, 1)]
+        for pts in lattice:
+            for group in edges + faces:
+                ps = [pts[a] for a in group]
+                ssum = [sum(q[d] for q in ps) for d in range(3)]
+                if any(v % len(ps) for v in ssum):
+                    continue
+                mid = tuple(v // len(ps) for v in ssum)
+                if mid in node_of:
+                    hanging[node_of[mid]] = tuple(node_of[q] for q in ps)
+        self.order, self.node_of, self.lattice_level = order, node_of, Lm
+        return (np.array(cells, dtype=np.int64), np.array(hs, dtype=np.float64), np.array(coords, dtype=np.float64),
+                hanging)
+
+
+def initial_multiple_het_3d(xyz, width):
+    """InitialValuesMultipleHet<3>, cracks.cc:595-610: two plate-shaped cracks, width = min cell diameter"""
+    x, y, z = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    w = width / 2.0
+    c1 = (x >= 2.6 - w) & (x <= 2.6 + w) & (y >= 3.8 - w) & (y <= 5.5 + w) & (z >= 4.0 - w) & (z <= 4.0 + w)
+    c2 = (x >= 5.5 - w) & (x <= 7.0 + w) & (y >= 4.0 - w) & (y <= 4.0 + w) & (z >= 6.0 - w) & (z <= 6.0 + w)
+    return np.where(c1 | c2, 0.0, 1.0)
+
+
+class HeteroRun3D(AdaptiveSneddonRun):
+    """run() of the reference for `test case = multiple het`, dim 3 (cracks.cc:4166-4581): single-tree
+    cube [0,10]^3, global refinement, local pre-refinement with `ref strategy = phase field` on the
+    interpolated initial cracks, per-cell Lame coefficients from the E-modulus field, pressure(time)."""
+
+    def __init__(self, e_modulus_of_cell, global_refine=3, local_pre_refine=1, nu=0.2, G_c=1.0,
+                 pressure=lambda t: 1e3 * t, kappa_of_h=lambda h: 0.0, eps_of_h=lambda h: 1.5, E_active_set=1e4,
+                 newton_lower_bound=1e-6, max_newton=20, max_line_search=8, line_search_damping=0.5, timestep=0.01,
+                 max_no_timesteps=1, refine_threshold=0.4):
+        self.forest = OctForest((1, 1, 1), (0.0,) * 3, (10.0,) * 3)
+        for _ in range(global_refine):
+            self.forest.refine(list(self.forest.cells))
+        self.level_cap = global_refine + local_pre_refine
+        self.prerefinement_h, self.prerefinement_dofs = [], []
+        dummy = orc.Params(1.0, 1.0, G_c, 0.0, 1.0, 0.0, 0.0, 1.0, 1.0, 0, 0, 0.0, 0.0)
+        for _ in range(local_pre_refine):
+            p = AdaptiveProblem(self.forest, dummy)
+            self.prerefinement_h.append(p.h_min)
+            self.prerefinement_dofs.append(p.n_dofs)
+            phi = initial_multiple_het_3d(p.xy, p.h_min)
+            flagged = [c for k, c in enumerate(self.forest.order)
+                       if c[0] < self.level_cap and np.any(phi[p.cells[k]] < refine_threshold)]
+            self.forest.refine(flagged)
+        self.prm = orc.Params(1.0, 1.0, G_c, 0.0, 1.0, 0.0, 0.0, 1.0, 1.0, 0, 0, 0.0, 0.0)
+        self.p = AdaptiveProblem(self.forest, self.prm)
+        self.prm.kappa, self.prm.eps = kappa_of_h(self.p.h_min), eps_of_h(self.p.h_min)
+        # E(cell centre); assembly adds 1.0 to it (cracks.cc:2209-2210), compute_energy does not (3651)
+        E = np.array([e_modulus_of_cell(c, self.forest.centre(c)) for c in self.forest.order], dtype=np.float64)
+
+        def lame(Ev):
+            mu = Ev / (2.0 * (1 + nu))
+            return np.stack([(2 * nu * mu) / (1.0 - 2 * nu), mu], axis=1)
+
+        self.p.set_cell_lame(lame(E + 1.0), lame(E))
+        self.E_cells = E
+        self.E = E_active_set          # c = 10 E_modulus with whatever value the member holds (cracks.cc:2859)
+        self.pressure = pressure
+        self.lower, self.max_newton = newton_lower_bound, max_newton
+        self.max_ls, self.damp = max_line_search, line_search_damping
+        self.dt, self.max_steps = timestep, max_no_timesteps
+        self.statistics, self.logs, self.diffs = [], [], []
+
+    def initial(self):
+        p = self.p
+        sol = np.zeros((p.n_nodes, 4))
+        sol[:, 3] = initial_multiple_het_3d(p.xy, p.h_min)
+        return sol.reshape(-1)
+
+    def run(self):
+        p = self.p
+        self.mass = p.lumped_mass()
+        self.constrained = p.dirichlet.copy()
+        sol = self.initial()
+        phi = sol.reshape(-1, 4)[:, 3]
+        np.clip(phi, 0.0, 1.0, out=phi)
+        oldold, old = sol.copy(), sol.copy()
+        self.prm.dt_old = self.prm.dt_oldold = self.dt
+        time, step_no = 0.0, 0
+        while step_no <= self.max_steps:
+            oldold, old = old, sol.copy()
+            time += self.dt
+            self.prm.pressure = self.pressure(time)
+            self.newton_active_set(sol, old, oldold)
+            np.clip(phi, 0.0, 1.0, out=phi)
+            sol[:] = p.distribute_hanging(sol)
+            bulk, crack, _ = p.functionals(sol)
+            self.statistics.append(dict(step=step_no, time=time, dofs=p.n_dofs, h=p.h_min, bulk=bulk, crack=crack))
+            self.diffs.append(float(np.max(np.abs(old - sol))))
             step_no += 1
         self.solution = sol
         return self.statistics

@@ -55,6 +55,9 @@ typedef struct
   long n_cells, n_nodes;
   const long *cells;     /* [n_cells][2^dim] node numbers, vertex order lexicographic (x fastest) */
   const double *cell_h;  /* [n_cells][dim] edge lengths */
+  const double *cell_lame; /* NULL, or [n_cells][2] = (lambda, mu) per cell: `test case = multiple het`
+                              recomputes the Lame coefficients from E(cell centre) in every cell
+                              (cracks.cc:2207-2216; compute_energy uses other values, 3646-3656) */
 } pfo_gmesh;
 
 #define PFO_DECL(D) \

@@ -991,6 +991,18 @@ pfo_load_2d (const pfo_mesh * m, const pfo_params * p, const double *sol, double
 #endif
 
 /* ---- general (locally refined) meshes: raw cell sums, constraints resolved by the caller ---- */
+static inline pfo_params
+SUF (cell_params) (const pfo_gmesh * m, const pfo_params * p, long c)
+{
+  pfo_params q = *p;
+  if (m->cell_lame)
+    {
+      q.lambda = m->cell_lame[2 * c];
+      q.mu = m->cell_lame[2 * c + 1];
+    }
+  return q;
+}
+
 void
 SUF (pfo_g_residual) (const pfo_gmesh * m, const pfo_params * p, const double *sol, const double *old,
                       const double *oldold, double *r_raw)
@@ -1006,7 +1018,8 @@ SUF (pfo_g_residual) (const pfo_gmesh * m, const pfo_params * p, const double *s
       SUF (gather) (nodes, sol, ls);
       SUF (gather) (nodes, old, lo);
       SUF (gather) (nodes, oldold, loo);
-      SUF (cell_rhs) (&t, p, ls, lo, loo, rhs);
+      const pfo_params pc = SUF (cell_params) (m, p, c);
+      SUF (cell_rhs) (&t, &pc, ls, lo, loo, rhs);
       for (int v = 0; v < NV; ++v)
         for (int cc = 0; cc < NC; ++cc)
           r_raw[nodes[v] * NC + cc] += rhs[v * NC + cc];
@@ -1027,7 +1040,8 @@ SUF (pfo_g_cell_matrices) (const pfo_gmesh * m, const pfo_params * p, const doub
       SUF (gather) (nodes, sol, ls);
       SUF (gather) (nodes, old, lo);
       SUF (gather) (nodes, oldold, loo);
-      SUF (cell_matrix) (&t, p, ls, lo, loo, mats + c * NDPC * NDPC);
+      const pfo_params pc = SUF (cell_params) (m, p, c);
+      SUF (cell_matrix) (&t, &pc, ls, lo, loo, mats + c * NDPC * NDPC);
     }
 }
 
@@ -1057,6 +1071,7 @@ SUF (pfo_g_functionals) (const pfo_gmesh * m, const pfo_params * p, const double
       SUF (fe_init) (&t, m->cell_h + c * DIM);
       double ls[NDPC];
       SUF (gather) (m->cells + c * NV, sol, ls);
+      const pfo_params pc = SUF (cell_params) (m, p, c);
       for (int q = 0; q < NQ; ++q)
         {
           double pf = 0, gpf[DIM], u[DIM], gu[DIM][DIM];
@@ -1086,7 +1101,7 @@ SUF (pfo_g_functionals) (const pfo_gmesh * m, const pfo_params * p, const double
                   trE2 += E * E;
                 }
             }
-          const double psi = 0.5 * p->lambda * trE * trE + p->mu * trE2;
+          const double psi = 0.5 * pc.lambda * trE * trE + pc.mu * trE2;
           eb += ((1 + p->kappa) * pf * pf + p->kappa) * psi * t.JxW[q];
           ec += p->G_c / 2.0 * ((pf - 1) * (pf - 1) / p->eps + p->eps * gg) * t.JxW[q];
           tcv += ug * t.JxW[q];

@@ -154,3 +154,26 @@ def test_miehe_shear_1_adaptive_with_split(oracle):
             assert got[key] == pytest.approx(ref[key], rel=tol), (got["step"], key)
     for lg_first, ref in zip([run.logs[0]], g["initial_newton_residual"]):
         assert lg_first.initial_residual == pytest.approx(ref, rel=2e-6)
+
+
+def test_kat5_hetero_3d(oracle):
+    """tests/hetero_3d_1.mpirun-4.statistics (BASELINE config 5 in small): octree with edge / face hanging
+    nodes from the phase-field pre-refinement (932 cells, 5288 DoFs), per-cell Lame coefficients from the
+    bitmap E-modulus field (sampled into the fixture by tests/golden/make_hetero_golden.py), the `+ 1.0`
+    of the assembly that compute_energy does not have (cracks.cc:2209-2210 vs 3651), pressure(time)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import adaptive_oracle as ao
+    g = json.load(open(os.path.join(HERE, "golden", "hetero_3d_1.json")))
+    field = {tuple(k): e for k, e in zip(g["cell_keys"], g["e_modulus"])}
+    run = ao.HeteroRun3D(lambda cell, centre: field[cell])
+    assert run.prerefinement_dofs == [g["dofs_before_prerefinement"]] == [2916]
+    assert run.prerefinement_h[0] == pytest.approx(g["prerefinement_h"], rel=1e-5)
+    assert run.p.n_cells == g["cells"] == 932 and run.p.n_dofs == g["statistics"][0]["dofs"] == 5288
+    assert set(len(v) for v in run.p.hanging.values()) == {2, 4}          # edge midpoints and face centres
+    stats = run.run()
+    for got, ref in zip(stats, g["statistics"]):
+        assert got["h"] == pytest.approx(ref["h"], rel=1e-8)
+        assert got["bulk"] == pytest.approx(ref["bulk"], rel=2e-8)
+        assert got["crack"] == pytest.approx(ref["crack"], rel=2e-8)
+    for lg, ref in zip(run.logs, g["initial_newton_residual"]):
+        assert lg.initial_residual == pytest.approx(ref, rel=2e-7)
