@@ -23,6 +23,7 @@
 #include "pf_apply3d_v3.cuh"
 #include "pf_apply3d_v4.cuh"
 #include "pf_common.cuh"
+#include "pf_forest.cuh"
 #include "pf_generic.cuh"
 #include "pf_multigrid.cuh"
 #include "pf_residual3d.cuh"
@@ -155,6 +156,15 @@ struct pf_ctx
   long long mg_graph_launches = 0;
   double *mg_in = nullptr;  // fixed input buffer of the captured V-cycle
   double *mg_out = nullptr; // output buffer it was captured with
+  // forest (locally refined) mesh, see pf_create_forest -- EXPERIMENTAL, not yet run on a GPU
+  bool forest = false;
+  long long n_hanging = 0;
+  long long *hang = nullptr;          // [n_hanging][5]: node, parents (-1 = unused)
+  long long *conn_dev = nullptr;
+  unsigned char *level_dev = nullptr;
+  double *lame_dev = nullptr, *lame_energy_dev = nullptr;
+  double *fx = nullptr;               // distributed copy of the input vector of an apply
+  uint8_t *zero_mask = nullptr;       // "nothing constrained", for the hanging-node-only constraint set
   double last_rnorm = 0;
   long long launches = 0;
   bool profiling = false;
@@ -604,6 +614,77 @@ launch_apply3d_v3 (pf_ctx *ctx, const double *x, double *y)
 }
 int g_force_generic = 0;
 
+// ---- hanging nodes of forest meshes (no-ops on box meshes) -------------------------------
+int
+hanging_distribute (pf_ctx *ctx, double *v, int zero_constrained)
+{
+  if (!ctx->forest || ctx->n_hanging == 0)
+    return PF_OK;
+  const long long n = ctx->n_hanging;
+  if (ctx->dim == 2)
+    k_hanging_distribute<3><<<nblk (n * 3, 256), 256, 0, ctx->stream>>> (n, ctx->hang, ctx->mask, zero_constrained, v);
+  else
+    k_hanging_distribute<4><<<nblk (n * 4, 256), 256, 0, ctx->stream>>> (n, ctx->hang, ctx->mask, zero_constrained, v);
+  KCHECK ();
+  return PF_OK;
+}
+
+// respect_mask: rows of constrained parents are dropped (operator, r_pde); otherwise every parent
+// receives its share (r_total of the hanging-node-only constraint set, cracks.cc:2446-2456)
+int
+hanging_fold (pf_ctx *ctx, const double *diag, const double *x, double *y, bool respect_mask)
+{
+  if (!ctx->forest || ctx->n_hanging == 0)
+    return PF_OK;
+  const long long n = ctx->n_hanging;
+  const uint8_t *m = respect_mask ? ctx->mask : ctx->zero_mask;
+  if (ctx->dim == 2)
+    k_hanging_fold<3><<<nblk (n * 3, 256), 256, 0, ctx->stream>>> (n, ctx->hang, m, diag, x, y);
+  else
+    k_hanging_fold<4><<<nblk (n * 4, 256), 256, 0, ctx->stream>>> (n, ctx->hang, m, diag, x, y);
+  KCHECK ();
+  return PF_OK;
+}
+
+int
+mark_hanging (pf_ctx *ctx)
+{
+  if (!ctx->forest || ctx->n_hanging == 0)
+    return PF_OK;
+  k_mark_hanging<<<nblk (ctx->n_hanging, 256), 256, 0, ctx->stream>>> (ctx->n_hanging, ctx->hang, ctx->mask);
+  KCHECK ();
+  return PF_OK;
+}
+
+// y = (H F)^T J (H F) x + D x on a forest mesh (F drops the constrained columns, D is the decoupled
+// diagonal of constrained and hanging rows): generic cell kernels between a distribute and a fold
+int
+apply_forest_dev (pf_ctx *ctx, const double *x, double *y)
+{
+  const Grid &g = ctx->g;
+  const long long nl = g.n_local_nodes;
+  int rc;
+  CU (cudaMemcpyAsync (ctx->fx, x, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice, ctx->stream));
+  if ((rc = hanging_distribute (ctx, ctx->fx, 1)))
+    return rc;
+  if (ctx->dim == 2)
+    {
+      k_apply_init<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
+      KCHECK ();
+      k_apply_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+        g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->fx, ctx->sol, ctx->pt, ctx->mask, y);
+    }
+  else
+    {
+      k_apply_init<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
+      KCHECK ();
+      k_apply_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+        g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->fx, ctx->sol, ctx->pt, ctx->mask, y);
+    }
+  KCHECK ();
+  return hanging_fold (ctx, ctx->diag, x, y, true);
+}
+
 // approx = true: the under-integrated (2-point Gauss) operator used only inside the
 // multigrid preconditioner, whose arithmetic is unpinned
 int
@@ -611,6 +692,8 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
 {
   if (!ctx->jac_ready)
     return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must be called before applying the Jacobian");
+  if (ctx->forest)
+    return apply_forest_dev (ctx, x, y);
   int rc;
   const Grid &g = ctx->g;
   const long long nl = g.n_local_nodes;
@@ -732,13 +815,15 @@ residual_dev (pf_ctx *ctx, double *l2)
       k_residual_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
         g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
       KCHECK ();
+      if (int rcf = hanging_fold (ctx, nullptr, nullptr, ctx->r_total, false))
+        return rcf;
       k_residual_finish<2><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi,
                                                                         ctx->r_total, ctx->mask, ctx->r_pde,
                                                                         ctx->partial);
     }
   else
     {
-      if (g_force_generic)
+      if (g_force_generic || ctx->forest)
         k_residual_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
           g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
       else
@@ -756,6 +841,8 @@ residual_dev (pf_ctx *ctx, double *l2)
             g, ctx->p, ctx->k3, tiles_x, tiles_y, ctx->sol, ctx->pt, ctx->r_total);
         }
       KCHECK ();
+      if (int rcf = hanging_fold (ctx, nullptr, nullptr, ctx->r_total, false))
+        return rcf;
       k_residual_finish<3><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi,
                                                                         ctx->r_total, ctx->mask, ctx->r_pde,
                                                                         ctx->partial);
@@ -1169,6 +1256,14 @@ diag_and_aux (pf_ctx *ctx)
     k_diag_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
       g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
   KCHECK ();
+  if (ctx->forest && ctx->n_hanging > 0)
+    {
+      if (ctx->dim == 2)
+        k_hanging_fold_diag<3><<<nblk (ctx->n_hanging * 3, 256), 256, 0, ctx->stream>>> (ctx->n_hanging, ctx->hang, ctx->diag);
+      else
+        k_hanging_fold_diag<4><<<nblk (ctx->n_hanging * 4, 256), 256, 0, ctx->stream>>> (ctx->n_hanging, ctx->hang, ctx->diag);
+      KCHECK ();
+    }
   // complete the diagonal on the ghost planes (their cells are only partly local)
   int rc = halo_exchange (ctx, ctx->diag, ctx->nc);
   if (rc)
@@ -1532,9 +1627,158 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
   CU (cudaStreamSynchronize (ctx->stream));
   return PF_OK;
 }
+// EXPERIMENTAL (not yet run on a GPU): context on a locally refined mesh given by flat tables
+int
+create_forest_impl (const pf_forest_mesh *fm, const pf_params *params, int device, pf_ctx **out)
+{
+  if (!fm || !params || !out || (fm->dim != 2 && fm->dim != 3) || fm->n_cells < 1 || fm->n_nodes < 1 || !fm->conn
+      || !fm->cell_level || fm->n_levels < 1 || fm->n_levels > 32 || !fm->level_h || fm->n_hanging < 0
+      || (fm->n_hanging > 0 && !fm->hanging) || fm->n_cells > 2000000000ll)
+    return PF_BAD_ARG;
+  pf_ctx *ctx = new pf_ctx ();
+  *out = ctx;
+  const int dim = fm->dim;
+  ctx->dim = dim;
+  ctx->nc = dim + 1;
+  ctx->device = device;
+  ctx->rank = 0;
+  ctx->nranks = 1;
+  ctx->prm = *params;
+  ctx->forest = true;
+  ctx->precond = 0; // Jacobi; the geometric multigrid needs the box hierarchy
+  CU (cudaSetDevice (device));
+  CU (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
+  CU (cudaStreamCreateWithFlags (&ctx->comm_stream, cudaStreamNonBlocking));
+  CU (cudaEventCreateWithFlags (&ctx->ev_x, cudaEventDisableTiming));
+  CU (cudaEventCreateWithFlags (&ctx->ev_halo, cudaEventDisableTiming));
+  Grid &g = ctx->g;
+  g.dim = dim;
+  // one "plane" holding every node, one "layer" holding every cell: the slab bookkeeping of the
+  // box meshes degenerates to "everything is local and owned"
+  g.n[0] = (int) fm->n_cells;
+  g.n[1] = g.n[2] = 1;
+  g.nn[0] = g.nn[1] = g.nn[2] = 1;
+  for (int d = 0; d < 3; ++d)
+    {
+      g.h[d] = d < dim ? fm->level_h[d] : 1.0;
+      g.origin[d] = 0.0;
+    }
+  g.plane_begin = g.owned_begin = 0;
+  g.plane_end = g.owned_end = 1;
+  g.cell_begin = 0;
+  g.cell_end = 1;
+  ctx->own_cell_begin = 0;
+  ctx->own_cell_end = 1;
+  g.nodes_per_plane = fm->n_nodes;
+  g.n_local_nodes = g.n_global_nodes = fm->n_nodes;
+  g.n_local_cells = fm->n_cells;
+  g.slit_row = -1;
+  ctx->n_local_dofs = g.n_local_nodes * ctx->nc;
+  ctx->owned_lo = 0;
+  ctx->owned_hi = g.n_local_nodes;
+  update_phys (ctx);
+  const size_t nd = (size_t) ctx->n_local_dofs, nn = (size_t) g.n_local_nodes, ncell = (size_t) fm->n_cells;
+  const int nv = 1 << dim;
+  double **vecs[] = {&ctx->sol, &ctx->old, &ctx->oldold, &ctx->diag, &ctx->r_total, &ctx->r_pde, &ctx->dx,
+                     &ctx->stage, &ctx->xa, &ctx->ya, &ctx->zvec, &ctx->saved, &ctx->fx};
+  for (double **v : vecs)
+    {
+      CU (cudaMalloc (v, nd * sizeof (double)));
+      CU (cudaMemsetAsync (*v, 0, nd * sizeof (double), ctx->stream));
+    }
+  CU (cudaMalloc (&ctx->pt, nn * sizeof (double)));
+  CU (cudaMalloc (&ctx->mass, nn * sizeof (double)));
+  CU (cudaMalloc (&ctx->mask, nn));
+  CU (cudaMalloc (&ctx->zero_mask, nn));
+  CU (cudaMalloc (&ctx->aux, nn * sizeof (double2)));
+  CU (cudaMalloc (&ctx->tile_counter, sizeof (unsigned long long)));
+  CU (cudaDeviceGetAttribute (&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CU (cudaMalloc (&ctx->stage8, nd));
+  CU (cudaMalloc (&ctx->cycle, nn * sizeof (int)));
+  CU (cudaMemsetAsync (ctx->pt, 0, nn * sizeof (double), ctx->stream));
+  CU (cudaMemsetAsync (ctx->mass, 0, nn * sizeof (double), ctx->stream));
+  CU (cudaMemsetAsync (ctx->mask, 0, nn, ctx->stream));
+  CU (cudaMemsetAsync (ctx->zero_mask, 0, nn, ctx->stream));
+  CU (cudaMemsetAsync (ctx->cycle, 0, nn * sizeof (int), ctx->stream));
+  CU (cudaMalloc (&ctx->red, 64 * sizeof (double)));
+  CU (cudaMalloc (&ctx->hdev, (size_t) (ctx->krylov_m + 2) * sizeof (double)));
+  CU (cudaMalloc (&ctx->partial, (size_t) RED_BLOCKS * (ctx->krylov_m + 2) * sizeof (double)));
+  CU (cudaMallocHost (&ctx->h_gs, (size_t) 3 * (ctx->krylov_m + 2) * sizeof (double)));
+  CU (cudaMalloc (&ctx->counts, 4 * sizeof (unsigned long long)));
+  CU (cudaMallocHost (&ctx->h_red, 128 * sizeof (double)));
+  CU (cudaMallocHost (&ctx->h_counts, 4 * sizeof (unsigned long long)));
+  // mesh tables
+  CU (cudaMalloc (&ctx->conn_dev, ncell * nv * sizeof (long long)));
+  CU (cudaMemcpy (ctx->conn_dev, fm->conn, ncell * nv * sizeof (long long), cudaMemcpyHostToDevice));
+  CU (cudaMalloc (&ctx->level_dev, ncell));
+  CU (cudaMemcpy (ctx->level_dev, fm->cell_level, ncell, cudaMemcpyHostToDevice));
+  for (size_t c = 0; c < ncell; ++c)
+    if (fm->cell_level[c] >= fm->n_levels)
+      return fail (ctx, PF_BAD_ARG, "cell %zu has level %d >= n_levels %d", c, (int) fm->cell_level[c], fm->n_levels);
+  for (size_t i = 0; i < ncell * nv; ++i)
+    if (fm->conn[i] < 0 || fm->conn[i] >= fm->n_nodes)
+      return fail (ctx, PF_BAD_ARG, "connectivity entry %zu out of range", i);
+  if (fm->n_hanging > 0)
+    {
+      ctx->n_hanging = fm->n_hanging;
+      for (long long h = 0; h < fm->n_hanging; ++h)
+        for (int q = 0; q < 5; ++q)
+          {
+            const long long v = fm->hanging[5 * h + q];
+            if (v >= fm->n_nodes || (q < 3 && v < 0))
+              return fail (ctx, PF_BAD_ARG, "hanging-node table row %lld is malformed", h);
+          }
+      CU (cudaMalloc (&ctx->hang, (size_t) fm->n_hanging * 5 * sizeof (long long)));
+      CU (cudaMemcpy (ctx->hang, fm->hanging, (size_t) fm->n_hanging * 5 * sizeof (long long), cudaMemcpyHostToDevice));
+    }
+  if (fm->cell_lame)
+    {
+      CU (cudaMalloc (&ctx->lame_dev, ncell * 2 * sizeof (double)));
+      CU (cudaMemcpy (ctx->lame_dev, fm->cell_lame, ncell * 2 * sizeof (double), cudaMemcpyHostToDevice));
+      const double *le = fm->cell_lame_energy ? fm->cell_lame_energy : fm->cell_lame;
+      CU (cudaMalloc (&ctx->lame_energy_dev, ncell * 2 * sizeof (double)));
+      CU (cudaMemcpy (ctx->lame_energy_dev, le, ncell * 2 * sizeof (double), cudaMemcpyHostToDevice));
+    }
+  g.conn = ctx->conn_dev;
+  g.cell_level = ctx->level_dev;
+  g.cell_lame = ctx->lame_dev;
+  // one shape table per level
+  if (dim == 2)
+    {
+      std::vector<FeTab<2>> tabs ((size_t) fm->n_levels);
+      for (int l = 0; l < fm->n_levels; ++l)
+        fill_fetab<2> (tabs[(size_t) l], fm->level_h + l * dim);
+      CU (cudaMalloc (&ctx->fetab, tabs.size () * sizeof (FeTab<2>)));
+      CU (cudaMemcpy (ctx->fetab, tabs.data (), tabs.size () * sizeof (FeTab<2>), cudaMemcpyHostToDevice));
+      k_lumped_mass_forest<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (g, (const FeTab<2> *) ctx->fetab,
+                                                                                     ctx->mass);
+    }
+  else
+    {
+      std::vector<FeTab<3>> tabs ((size_t) fm->n_levels);
+      for (int l = 0; l < fm->n_levels; ++l)
+        fill_fetab<3> (tabs[(size_t) l], fm->level_h + l * dim);
+      CU (cudaMalloc (&ctx->fetab, tabs.size () * sizeof (FeTab<3>)));
+      CU (cudaMemcpy (ctx->fetab, tabs.data (), tabs.size () * sizeof (FeTab<3>), cudaMemcpyHostToDevice));
+      k_lumped_mass_forest<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (g, (const FeTab<3> *) ctx->fetab,
+                                                                                     ctx->mass);
+    }
+  KCHECK ();
+  int rc = mark_hanging (ctx);
+  if (rc)
+    return rc;
+  CU (cudaStreamSynchronize (ctx->stream));
+  return PF_OK;
+}
 } // namespace
 
 extern "C" {
+
+int
+pf_create_forest (const pf_forest_mesh *mesh, const pf_params *params, int device, pf_ctx **out)
+{
+  return create_forest_impl (mesh, params, device, out);
+}
 
 int
 pf_destroy (pf_ctx *ctx)
@@ -1558,7 +1802,8 @@ pf_destroy (pf_ctx *ctx)
   void *ptrs[] = {ctx->sol,   ctx->old,  ctx->oldold, ctx->pt,     ctx->diag,  ctx->mass, ctx->r_total,
                   ctx->r_pde, ctx->dx,   ctx->stage,  ctx->xa,     ctx->ya,    ctx->zvec, ctx->mask,
                   ctx->saved, ctx->aux, ctx->tile_counter, ctx->stage8, ctx->cycle, ctx->fetab, ctx->red,   ctx->hdev,  ctx->partial, ctx->counts,
-                  ctx->V};
+                  ctx->V, ctx->hang, ctx->conn_dev, ctx->level_dev, ctx->lame_dev, ctx->lame_energy_dev, ctx->fx,
+                  ctx->zero_mask};
   for (void *p : ptrs)
     if (p)
       cudaFree (p);
@@ -1721,6 +1966,8 @@ pf_set_constraints (pf_ctx *ctx, const uint8_t *dirichlet_mask, const uint8_t *a
         k_mask_from_block<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ub, pb, dirichlet_mask != nullptr,
                                                                       active_mask != nullptr, ctx->mask);
       KCHECK ();
+      if (int rch = mark_hanging (ctx))
+        return rch;
     }
   ctx->jac_ready = false;
   ctx->have_r = false;
@@ -1732,6 +1979,8 @@ pf_set_dirichlet_all_faces (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  if (ctx->forest)
+    return fail (ctx, PF_UNSUPPORTED, "forest meshes take their Dirichlet rows from pf_set_constraints");
   const long long nl = ctx->g.n_local_nodes;
   if (ctx->dim == 2)
     k_mask_dirichlet_faces<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (ctx->g, ctx->mask);
@@ -1771,7 +2020,7 @@ pf_setup_jacobian (pf_ctx *ctx)
   ctx->jac_ready = true;
   ctx->mg_ready = false;
   ctx->mg_graph_valid = false;
-  if (ctx->precond == 1 && ctx->dim == 3)
+  if (ctx->precond == 1 && ctx->dim == 3 && !ctx->forest)
     return mg_setup_level (ctx);
   return PF_OK;
 }
@@ -1826,8 +2075,8 @@ pf_apply_jacobian (pf_ctx *ctx, const double *x, double *y)
     return PF_BAD_ARG;
   CU (cudaSetDevice (ctx->device));
   int rc;
-  if (ctx->dim == 3 && ctx->nranks == 1 && !g_force_generic && (g_apply_variant == 3 || g_apply_variant == 16)
-      && ctx->g.n[2] >= 16)
+  if (ctx->dim == 3 && ctx->nranks == 1 && !g_force_generic && !ctx->forest
+      && (g_apply_variant == 3 || g_apply_variant == 16) && ctx->g.n[2] >= 16)
     return apply_host_pipelined (ctx, x, y);
   if ((rc = upload_block (ctx, x, ctx->xa)))
     return rc;
@@ -1893,6 +2142,8 @@ pf_active_set_update (pf_ctx *ctx, double c, uint8_t *active_mask, int64_t *n_ac
                                                              ctx->mass, ctx->old, ctx->sol, ctx->cycle,
                                                              ctx->mask, ctx->counts);
   KCHECK ();
+  if (int rch = hanging_distribute (ctx, ctx->sol, 0)) // constraints_hanging_nodes.distribute(solution), cracks.cc:2887-2890
+    return rch;
   g_trace.mark (ctx->stream, "active_set:kernel");
   if (ctx->nranks > 1)
     {
@@ -2125,6 +2376,8 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
   KCHECK ();
   if ((rc = halo_exchange (ctx, x, ctx->nc)))
     return rc;
+  if ((rc = hanging_distribute (ctx, x, 0))) // constraints_update.distribute(newton_update), cracks.cc:2773
+    return rc;
   if (n_it)
     *n_it = its;
   if (dx && (rc = download_block (ctx, x, dx)))
@@ -2141,7 +2394,9 @@ pf_energy (pf_ctx *ctx, double *bulk, double *crack)
   if (!ctx)
     return PF_BAD_ARG;
   CU (cudaSetDevice (ctx->device));
-  const Grid &g = ctx->g;
+  Grid g = ctx->g;
+  if (ctx->lame_energy_dev)
+    g.cell_lame = ctx->lame_energy_dev; // compute_energy's coefficients differ from the assembly's (cracks.cc:3651)
   CU (cudaMemsetAsync (ctx->red, 0, 4 * sizeof (double), ctx->stream));
   if (ctx->dim == 2)
     k_functionals_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
@@ -2180,6 +2435,8 @@ pf_cod (pf_ctx *ctx, double eval_line, double *value, int64_t *n_faces)
 {
   if (!ctx || !value)
     return PF_BAD_ARG;
+  if (ctx->forest)
+    return fail (ctx, PF_UNSUPPORTED, "pf_cod is not available on forest meshes yet");
   CU (cudaSetDevice (ctx->device));
   const Grid &g = ctx->g;
   CU (cudaMemsetAsync (ctx->red, 0, 2 * sizeof (double), ctx->stream));
@@ -2222,7 +2479,7 @@ pf_dirichlet_miehe (pf_ctx *ctx, int kind, double time, int set_values)
 {
   if (!ctx || (kind != 1 && kind != 2))
     return PF_BAD_ARG;
-  if (ctx->dim != 2 || ctx->g.slit_row < 0)
+  if (ctx->dim != 2 || ctx->g.slit_row < 0 || ctx->forest)
     return fail (ctx, PF_UNSUPPORTED, "the Miehe boundary data need the 2-D slit mesh");
   const long long nl = ctx->g.n_local_nodes;
   k_dirichlet_miehe<<<nblk (nl, 256), 256, 0, ctx->stream>>> (ctx->g, kind, time, set_values, ctx->mask, ctx->sol);
@@ -2258,8 +2515,8 @@ pf_load (pf_ctx *ctx, double *load_x, double *load_y)
 {
   if (!ctx)
     return PF_BAD_ARG;
-  if (ctx->dim != 2 || ctx->nranks != 1)
-    return fail (ctx, PF_UNSUPPORTED, "pf_load: 2-D, single rank (the reference's load tests are 2-D)");
+  if (ctx->dim != 2 || ctx->nranks != 1 || ctx->forest)
+    return fail (ctx, PF_UNSUPPORTED, "pf_load: 2-D box / slit mesh, single rank (the reference's load tests are 2-D)");
   CU (cudaMemsetAsync (ctx->red, 0, 2 * sizeof (double), ctx->stream));
   k_load_top_2d<<<nblk (ctx->g.n[0], 128), 128, 0, ctx->stream>>> (ctx->g, ctx->p, ctx->sol, ctx->red);
   KCHECK ();
@@ -2302,6 +2559,8 @@ pf_project_phase_field (pf_ctx *ctx)
   else
     k_project_phi<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->sol);
   KCHECK ();
+  if (int rch = hanging_distribute (ctx, ctx->sol, 0)) // cracks.cc:4416-4417
+    return rch;
   ctx->jac_ready = false;
   ctx->have_r = false;
   return PF_OK;
@@ -2312,6 +2571,8 @@ pf_interpolate_sneddon (pf_ctx *ctx, double h_diam)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  if (ctx->forest)
+    return fail (ctx, PF_UNSUPPORTED, "the initial condition of a forest mesh is interpolated by the host (pf_set_state)");
   const long long nl = ctx->g.n_local_nodes;
   if (ctx->dim == 2)
     k_interpolate_sneddon<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (ctx->g, h_diam, ctx->sol);

@@ -32,6 +32,11 @@ struct Grid
   int slit_row;
   int slit_i0;
   long long slit_base;
+  // forest (locally refined) meshes, see pf_create_forest: explicit connectivity, one shape table per
+  // refinement level, optional per-cell Lame coefficients.  All null on the box meshes.
+  const long long *conn;           // [n_local_cells][2^dim] node numbers
+  const unsigned char *cell_level; // [n_local_cells] index into the FeTab array
+  const double *cell_lame;         // [n_local_cells][2] = (lambda, mu) or null
 };
 
 // quantities that change per Newton step / time step
@@ -58,5 +63,7 @@ template <int DIM> struct FeTab
 __host__ __device__ inline bool is_constrained (uint8_t m, int c) { return (m >> c) & 1u; }
 
 #define PF_ACTIVE_BIT(DIM) (1u << (DIM))
+// forest meshes: the node is a hanging node (all its components are constrained to its parents)
+#define PF_HANGING_BIT 0x80u
 
 } // namespace pf

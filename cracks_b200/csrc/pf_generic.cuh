@@ -14,6 +14,12 @@ template <int DIM>
 __device__ __forceinline__ void
 cell_nodes (const Grid &g, long long lc, long long *node)
 {
+  if (g.conn) // forest mesh: explicit connectivity
+    {
+      for (int v = 0; v < (1 << DIM); ++v)
+        node[v] = g.conn[lc * (1 << DIM) + v];
+      return;
+    }
   // lc = local cell index within [cell_begin, cell_end) layers, x fastest
   long long rem = lc;
   int ci[3] = {0, 0, 0};
@@ -39,6 +45,26 @@ cell_nodes (const Grid &g, long long lc, long long *node)
         if (ix >= g.slit_i0)
           node[v] = g.slit_base + (ix - g.slit_i0);
       }
+}
+
+// shape table of the cell (one per refinement level on forest meshes) and its material constants
+template <int DIM>
+__device__ __forceinline__ const FeTab<DIM> &
+cell_table (const Grid &g, const FeTab<DIM> *tab, long long lc)
+{
+  return g.cell_level ? tab[g.cell_level[lc]] : *tab;
+}
+
+__device__ __forceinline__ Phys
+cell_phys (const Grid &g, const Phys &p, long long lc)
+{
+  Phys q = p;
+  if (g.cell_lame) // `test case = multiple het`: Lame coefficients per cell (cracks.cc:2207-2216)
+    {
+      q.lambda = g.cell_lame[2 * lc];
+      q.mu = g.cell_lame[2 * lc + 1];
+    }
+  return q;
 }
 
 // q-point state for the no-split constitutive law
@@ -114,7 +140,7 @@ eval_qstate (const FeTab<DIM> &t, int q, const Phys &p, const double (*ls)[DIM +
 // ---- y += J x on the cells of this rank (rows/cols of constrained dofs dropped)
 template <int DIM>
 __global__ void __launch_bounds__ (128)
-k_apply_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
+k_apply_generic (Grid g, Phys p_in, const FeTab<DIM> *__restrict__ tab,
                  const double *__restrict__ x, const double *__restrict__ sol,
                  const double *__restrict__ pt, const uint8_t *__restrict__ mask,
                  double *__restrict__ y)
@@ -123,7 +149,8 @@ k_apply_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
   const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (lc >= g.n_local_cells)
     return;
-  const FeTab<DIM> &t = *tab;
+  const FeTab<DIM> &t = cell_table<DIM> (g, tab, lc);
+  const Phys p = cell_phys (g, p_in, lc);
   long long node[NV];
   cell_nodes<DIM> (g, lc, node);
   double lx[NV][NC], ls[NV][NC], lpt[NV], out[NV][NC];
@@ -214,7 +241,7 @@ k_apply_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
 // ---- r_total += local_rhs (cracks.cc:2393-2432); constraints applied later
 template <int DIM>
 __global__ void __launch_bounds__ (128)
-k_residual_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
+k_residual_generic (Grid g, Phys p_in, const FeTab<DIM> *__restrict__ tab,
                     const double *__restrict__ sol, const double *__restrict__ pt,
                     double *__restrict__ r)
 {
@@ -222,7 +249,8 @@ k_residual_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
   const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (lc >= g.n_local_cells)
     return;
-  const FeTab<DIM> &t = *tab;
+  const FeTab<DIM> &t = cell_table<DIM> (g, tab, lc);
+  const Phys p = cell_phys (g, p_in, lc);
   long long node[NV];
   cell_nodes<DIM> (g, lc, node);
   double ls[NV][NC], lpt[NV], out[NV][NC];
@@ -268,7 +296,7 @@ k_residual_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
 // AffineConstraints::distribute_local_to_global leaves on constrained rows.
 template <int DIM>
 __global__ void __launch_bounds__ (128)
-k_diag_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
+k_diag_generic (Grid g, Phys p_in, const FeTab<DIM> *__restrict__ tab,
                 const double *__restrict__ sol, const double *__restrict__ pt,
                 double *__restrict__ diag)
 {
@@ -276,7 +304,8 @@ k_diag_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
   const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
   if (lc >= g.n_local_cells)
     return;
-  const FeTab<DIM> &t = *tab;
+  const FeTab<DIM> &t = cell_table<DIM> (g, tab, lc);
+  const Phys p = cell_phys (g, p_in, lc);
   long long node[NV];
   cell_nodes<DIM> (g, lc, node);
   double ls[NV][NC], lpt[NV], out[NV][NC];
@@ -342,7 +371,7 @@ k_diag_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
 // block-reduced, one atomicAdd per block into out[0..2]
 template <int DIM>
 __global__ void __launch_bounds__ (128)
-k_functionals_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
+k_functionals_generic (Grid g, Phys p_in, const FeTab<DIM> *__restrict__ tab,
                        const double *__restrict__ sol, int owned_cells_only_begin,
                        int owned_cells_only_end, double *__restrict__ out3)
 {
@@ -361,7 +390,8 @@ k_functionals_generic (Grid g, Phys p, const FeTab<DIM> *__restrict__ tab,
     }
   if (active)
     {
-      const FeTab<DIM> &t = *tab;
+      const FeTab<DIM> &t = cell_table<DIM> (g, tab, lc);
+      const Phys p = cell_phys (g, p_in, lc);
       long long node[NV];
       cell_nodes<DIM> (g, lc, node);
       double ls[NV][NC];

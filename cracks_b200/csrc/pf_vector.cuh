@@ -258,6 +258,8 @@ k_active_set (long long n_nodes, long long owned_lo, long long owned_hi, double 
   const double old_value = old[i], new_value = sol[i];
   const double gap = new_value - old_value;
   const uint8_t m = mask[n];
+  if (m & PF_HANGING_BIT) // hanging nodes are skipped (cracks.cc:2855-2857); forest meshes only
+    return;
   const bool was = (m >> DIM) & 1;
   int cyc = cycle[n];
   const bool inactive = (r_total[i] / mass[n] + c_scale * gap <= 0.0) && (cyc < 5);

@@ -329,3 +329,123 @@ initial_multiple_het_3d (const double *p, double min_cell_diameter)
 }
 
 } // namespace cracks
+
+// ---- C binding (ctypes mirror: cracks_b200/forest.py) ---------------------------------------------
+extern "C" {
+
+void *
+pfh_forest_create (int dim, const int *n, const double *lo, const double *hi, int slit)
+{
+  try
+    {
+      return new cracks::Forest (dim, n, lo, hi, slit != 0);
+    }
+  catch (std::exception &)
+    {
+      return nullptr;
+    }
+}
+
+void *
+pfh_forest_clone (const void *f)
+{
+  return new cracks::Forest (*static_cast<const cracks::Forest *> (f));
+}
+
+void
+pfh_forest_destroy (void *f)
+{
+  delete static_cast<cracks::Forest *> (f);
+}
+
+void
+pfh_forest_refine_global (void *f, int times)
+{
+  static_cast<cracks::Forest *> (f)->refine_global (times);
+}
+
+int
+pfh_forest_refine (void *f, const unsigned char *flags, long long n)
+{
+  cracks::Forest *F = static_cast<cracks::Forest *> (f);
+  if (n != F->n_cells ())
+    return -1;
+  F->refine (std::vector<char> (flags, flags + n));
+  return 0;
+}
+
+long long
+pfh_forest_n_cells (const void *f)
+{
+  return static_cast<const cracks::Forest *> (f)->n_cells ();
+}
+
+long long
+pfh_forest_n_nodes (const void *f)
+{
+  return static_cast<const cracks::Forest *> (f)->n_nodes ();
+}
+
+long long
+pfh_forest_n_hanging (const void *f)
+{
+  return (long long) static_cast<const cracks::Forest *> (f)->hanging_nodes ().size ();
+}
+
+int
+pfh_forest_max_level (const void *f)
+{
+  return static_cast<const cracks::Forest *> (f)->max_level ();
+}
+
+double
+pfh_forest_min_cell_diameter (const void *f)
+{
+  return static_cast<const cracks::Forest *> (f)->min_cell_diameter ();
+}
+
+// conn [n_cells][2^dim], level [n_cells], coords [n_nodes][dim], hanging [n_hanging][5] (node, parents,
+// -1 = unused), level_h [(max_level + 1)][dim], upper_copy [n_nodes] (doubled slit nodes); any may be null
+void
+pfh_forest_tables (const void *f, long long *conn, unsigned char *level, double *coords, long long *hanging,
+                   double *level_h, unsigned char *upper_copy)
+{
+  const cracks::Forest &F = *static_cast<const cracks::Forest *> (f);
+  if (conn)
+    std::copy (F.connectivity ().begin (), F.connectivity ().end (), conn);
+  if (level)
+    for (long long c = 0; c < F.n_cells (); ++c)
+      level[c] = (unsigned char) F.cells ()[(size_t) c].level;
+  if (coords)
+    std::copy (F.coordinates ().begin (), F.coordinates ().end (), coords);
+  if (hanging)
+    for (size_t h = 0; h < F.hanging_nodes ().size (); ++h)
+      {
+        const cracks::HangingNode &hn = F.hanging_nodes ()[h];
+        hanging[5 * h] = hn.node;
+        for (int q = 0; q < 4; ++q)
+          hanging[5 * h + 1 + q] = q < hn.n_parents ? hn.parents[q] : -1;
+      }
+  if (level_h)
+    for (int l = 0; l <= F.max_level (); ++l)
+      F.cell_size (l, level_h + l * F.dim ());
+  if (upper_copy)
+    for (long long n = 0; n < F.n_nodes (); ++n)
+      upper_copy[n] = F.is_upper_slit_copy (n) ? 1 : 0;
+}
+
+int
+pfh_forest_transfer (const void *to, const void *from, const double *v_from, double *v_to, int ncomp)
+{
+  try
+    {
+      static_cast<const cracks::Forest *> (to)->transfer (*static_cast<const cracks::Forest *> (from), v_from, v_to, ncomp);
+      return 0;
+    }
+  catch (std::exception &)
+    {
+      return -1;
+    }
+}
+
+} // extern "C"

@@ -100,6 +100,27 @@ int pf_get_layout (const pf_ctx *ctx, pf_local_layout *out);
  * 1180); cell_* pointers may be NULL. */
 int pf_slab_layout (const pf_mesh *mesh, int rank, int nranks, pf_local_layout *out, int *cell_begin,
                     int *cell_end, int *own_cell_begin, int *own_cell_end);
+/* EXPERIMENTAL (written against the hanging-node oracle, not yet run on a GPU): a locally refined
+ * mesh as flat tables, the output of the host forest (cracks_b200/host/forest.h) that stands in for
+ * the reference's p4est triangulation after refine_mesh() (cracks.cc:3895-4163).  All cells are
+ * axis-aligned; a cell's level selects its edge lengths.  Hanging nodes (make_hanging_node_constraints,
+ * 1630-1634) are constrained to the mean of their 2 (edge) or 4 (face) parents.  Single rank, Jacobi
+ * preconditioner; Dirichlet rows come from pf_set_constraints, initial values from pf_set_state. */
+typedef struct
+{
+  int dim;
+  int64_t n_cells, n_nodes;
+  const int64_t *conn;        /* [n_cells][2^dim] node numbers, vertex order lexicographic (x fastest) */
+  const uint8_t *cell_level;  /* [n_cells] */
+  int n_levels;
+  const double *level_h;      /* [n_levels][dim] edge lengths of the cells of each level */
+  int64_t n_hanging;
+  const int64_t *hanging;     /* [n_hanging][5]: node, parent 0..3 (-1 = unused) */
+  const double *cell_lame;        /* NULL, or [n_cells][2] = (lambda, mu) used by the assembly (cracks.cc:2207-2216) */
+  const double *cell_lame_energy; /* NULL (= cell_lame), or the values compute_energy uses (3646-3656) */
+} pf_forest_mesh;
+int pf_create_forest (const pf_forest_mesh *mesh, const pf_params *params, int device, pf_ctx **out);
+
 /* One level of the geometric multigrid hierarchy that replaces the reference's ML AMG set-up
  * (cracks.cc:2477-2497) as `rank` of `nranks` sees it. */
 typedef struct

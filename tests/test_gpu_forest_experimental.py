@@ -1,0 +1,89 @@
+"""OPT-IN (PF_EXPERIMENTAL=1): the device path for locally refined meshes with hanging nodes
+(pf_create_forest, cracks_b200/csrc/pf_forest.cuh) against the hanging-node oracle and the KAT-2 golden.
+This code was written after the round's GPU budget was spent and has not been run on a GPU yet, so it
+does not gate the suite; the box-mesh paths do not touch it."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PF_EXPERIMENTAL") != "1", reason="experimental forest path: set PF_EXPERIMENTAL=1")]
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def ao(oracle):
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import adaptive_oracle
+    return adaptive_oracle
+
+
+def _relerr(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+def test_forest_kernels_match_the_hanging_node_oracle(oracle, ao, pf):
+    import scipy.sparse as sp
+    from cracks_b200.forest import ForestContext, ForestSneddonDriver
+    run = ao.AdaptiveSneddonRun()                       # KAT-2 mesh: 124 cells, 12 hanging nodes
+    p = run.p
+    f = ForestSneddonDriver.prerefined_forest()
+    assert np.array_equal(f.tables()["conn"], p.cells)  # same numbering as the oracle forest
+    prm = run.prm
+    ctx = ForestContext(f, pf.Params(prm.lam, prm.mu, prm.G_c, prm.kappa, prm.eps, 0.0))
+    rng = np.random.default_rng(1)
+    nn = p.n_nodes
+    sol = np.zeros((nn, 3)); sol[:, :2] = 1e-2 * rng.standard_normal((nn, 2)); sol[:, 2] = rng.random(nn)
+    old = sol.copy(); old[:, 2] = rng.random(nn)
+    oo = old.copy(); oo[:, 2] += 0.5 * (rng.random(nn) - 0.5)
+    sol, old, oo = (p.distribute_hanging(v.reshape(-1)) for v in (sol, old, oo))
+    prm.dt_old, prm.dt_oldold = 1.0, 0.5
+    active = (rng.random(nn) < 0.2) & ~p.is_hanging_node
+    con = p.dirichlet.reshape(nn, 3).copy(); con[:, 2] |= active
+    con = con.reshape(-1)
+    ctx.set_state(ctx.to_block(sol), ctx.to_block(old), ctx.to_block(oo), 1.0, 0.5, False, prm.pressure)
+    cb = ctx.to_block(con.astype(np.uint8)).astype(np.uint8)
+    ctx.set_constraints(cb, cb)
+    raw = p.raw_residual(sol, old, oo)
+    r_total_ref = p.H.T @ raw
+    r_pde_ref = np.where(con, 0.0, r_total_ref)
+    r_pde, r_tot, nrm = ctx.residual()
+    assert _relerr(ctx.to_nodal(r_tot), r_total_ref) <= 1e-12
+    assert _relerr(ctx.to_nodal(r_pde), r_pde_ref) <= 1e-12
+    assert nrm == pytest.approx(np.linalg.norm(r_pde_ref), rel=1e-11)
+    ctx.setup_jacobian()
+    free = ~(con | p.is_hanging_dof)
+    Cm = p.H @ sp.diags(free.astype(float))
+    A = (Cm.T @ p.raw_jacobian(sol, old, oo) @ Cm).tocsr()
+    x = np.where(free, rng.standard_normal(p.n_dofs), 0.0)
+    y = np.zeros(p.n_dofs)
+    ctx.vmult(y, ctx.to_block(x))
+    assert _relerr(ctx.to_nodal(y)[free], (A @ x)[free]) <= 1e-12
+    assert _relerr(ctx.lumped_mass(), p.lumped_mass()) <= 1e-14
+    bulk, crack = ctx.energy()
+    b_ref, c_ref, tcv_ref = p.functionals(sol)
+    assert bulk == pytest.approx(b_ref, rel=1e-12) and crack == pytest.approx(c_ref, rel=1e-12)
+    ctx.close()
+
+
+def test_kat2_golden_on_the_gpu(pf):
+    from cracks_b200.forest import ForestContext, ForestSneddonDriver
+    g = json.load(open(os.path.join(HERE, "golden", "sneddon_2d_1.json")))
+    f = ForestSneddonDriver.prerefined_forest()
+    h = f.min_cell_diameter
+    mu = 1.0 / (2.0 * 1.2)
+    lam = 0.4 * mu / 0.6
+    ctx = ForestContext(f, pf.Params(lam, mu, 1.0, 1e-8 * h, 2.0 * h, 0.0))
+    ctx.set_krylov_dim(300)
+    drv = ForestSneddonDriver(ctx, pressure=lambda t: 1e-3, max_no_timesteps=3, newton_lower_bound=1e-7, max_newton=50,
+                              max_line_search=10, gmres_max_it=3000)
+    stats = drv.run_on_forest()
+    assert ctx.n_dofs == 453 and len(stats) == 4
+    for got, ref in zip(stats, g["statistics"]):
+        assert got["crack"] == pytest.approx(ref["crack"], rel=1e-8)
+        assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-6)
+    assert drv.tcv == pytest.approx(g["tcv"], rel=1e-5)
+    ctx.close()

@@ -95,3 +95,23 @@ def test_solution_transfer_reproduces_linear_fields(dump):
     d = dump("transfer")
     assert d["fine_cells"] > d["coarse_cells"] and d["fine_hanging"] > 0
     assert d["max_error"] <= 1e-14
+
+
+def test_ctypes_mirror_of_the_host_forest(dump, pf):
+    """cracks_b200/forest.py (HostForest) hands out the same tables as the C++ class"""
+    from cracks_b200.forest import ForestSneddonDriver
+    f = ForestSneddonDriver.prerefined_forest()            # the KAT-2 recipe through the C binding
+    d = dump("kat2")
+    t = f.tables()
+    assert (f.n_cells, f.n_nodes, f.n_hanging) == (d["n_cells"], d["n_nodes"], len(d["hanging"])) == (124, 151, 12)
+    assert np.array_equal(t["conn"].reshape(-1), np.array(d["conn"]))
+    assert np.allclose(t["coords"].reshape(-1), np.array(d["coords"]), rtol=0, atol=0)
+    assert [[v for v in row if v >= 0] for row in t["hanging"].tolist()] == d["hanging"]
+    assert np.allclose(t["level_h"], [[2.0, 2.0], [1.0, 1.0]])
+    finer = f.clone()
+    flags = np.zeros(finer.n_cells, dtype=np.uint8)
+    flags[::7] = 1
+    finer.refine(flags)
+    xy0, xy1 = t["coords"], finer.tables()["coords"]
+    lin = lambda xy: np.stack([1 + 2 * xy[:, 0] - xy[:, 1], 3 - xy[:, 0]], axis=1).reshape(-1)
+    assert np.allclose(finer.transfer_from(f, lin(xy0), 2), lin(xy1), rtol=0, atol=1e-13)
