@@ -143,12 +143,18 @@ def cpu_reference_sample(steps, warmup, refine=2):
         spmv(prob.n_dofs, rowptr, col, val, x, y)
     t = (time.perf_counter() - t0) / steps
     cores = orc.lib().pfo_num_threads()
+    # the reference assembles the Jacobian once per Newton step (cracks.cc:2917) and then needs one
+    # vmult per GMRES iteration (about 12 per step with a multigrid-quality preconditioner): an upper
+    # bound on its Newton-its/s that ignores the AMG set-up, the V-cycles and the residual assemblies
+    newton_bound = 1.0 / (t_asm + 12.0 * t)
     return {
         "value": prob.n_dofs / t / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": (f"CSR SpMV (the reference's vmult) on Sneddon-3D at {refine} global refinements: "
                    f"{prob.n_dofs} DoF, {col.shape[0]} nnz, {steps} applies after {warmup} warm-ups; "
                    f"Jacobian assembly (needed once per Newton step by the reference) took {t_asm:.2f} s "
-                   f"= {prob.n_dofs / t_asm / 1e6:.3f} MDoF/s"),
+                   f"= {prob.n_dofs / t_asm / 1e6:.3f} MDoF/s; assembly + 12 vmults bound the CPU path to "
+                   f"{newton_bound:.2f} Newton-its/s at this size"),
+        "newton_its_per_s_upper_bound": newton_bound,
         "ms_per_apply": t * 1e3, "assembly_s": t_asm, "n_dofs": prob.n_dofs,
     }
 

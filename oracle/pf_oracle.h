@@ -5,12 +5,14 @@
  * bench.py's cpu_baseline / --impl reference legs may load this library.
  * The product (cracks_b200/) never links or calls it.
  *
- * Parity status: PINNED.  oracle/newton_oracle.py drives these functions
- * through the reference's active-set Newton loop (cracks.cc:2780-2994) and
- * reproduces tests/sneddon_3d_1.mpirun=4.statistics (all four rows, bulk and
- * crack energy, <= 1e-8 relative), the initial residual 6.744161e+01 and the
- * TCV 0.0399535 of tests/sneddon_3d_1.mpirun=4.output; see
- * tests/test_oracle_golden.py and tests/golden/sneddon_3d_1.json.
+ * Parity status: PINNED against every golden the reference ships for this path except the
+ * gmsh three-point case (tests/test_oracle_golden.py, test_oracle_miehe.py, test_oracle_adaptive.py;
+ * fixtures under tests/golden/ with the scripts that transcribed them):
+ *   sneddon_3d_1 (uniform 3-D), sneddon_2d_1 (hanging nodes), miehe_shear_2 + its 2-rank variant
+ *   (stress split), miehe_shear_1 and miehe_tension_adaptive_1 (split / predictor-corrector
+ *   refinement), hetero_3d_1 (3-D hanging nodes, bitmap coefficient), the Catch cases of the
+ *   2x2 eigen routine.  oracle/newton_oracle.py and oracle/adaptive_oracle.py drive these C
+ *   functions through the reference's time loop and active-set Newton iteration.
  * The reference itself cannot be compiled here (needs deal.II, Trilinos,
  * p4est, MPI), so there is no oracle/_ref.
  */
