@@ -177,3 +177,59 @@ def test_kat5_hetero_3d(oracle):
         assert got["crack"] == pytest.approx(ref["crack"], rel=2e-8)
     for lg, ref in zip(run.logs, g["initial_newton_residual"]):
         assert lg.initial_residual == pytest.approx(ref, rel=2e-7)
+
+
+def test_distribute_fold_formulation_equals_the_congruence(run):
+    """The device path for hanging nodes (cracks_b200/csrc/pf_forest.cuh, pf_api.cu::apply_forest_dev)
+    does not form C^T J C; it runs the unconstrained cell kernel between a `distribute` (hanging values
+    from their parents, constrained parents counting as zero) and a `fold` (hanging rows added to their
+    unconstrained parents, then decoupled).  Emulated here in numpy, step for step, on the KAT-2 mesh:
+    it must equal the congruence the oracle pins to the goldens."""
+    import scipy.sparse as sp
+    p = run.p
+    rng = np.random.default_rng(5)
+    sol = p.distribute_hanging(run.solution + 1e-3 * rng.standard_normal(p.n_dofs))
+    nn = p.n_nodes
+    active = (rng.random(nn) < 0.3) & ~p.is_hanging_node
+    con = p.dirichlet.reshape(nn, 3).copy()
+    con[:, 2] |= active
+    con = con.reshape(-1)                                   # mask bits of Dirichlet / active dofs
+    J = p.raw_jacobian(sol, sol, sol).tocsr()
+    diag = np.abs(J.diagonal()) + 1.0                       # any positive decoupling diagonal
+    free = ~(con | p.is_hanging_dof)
+    x = np.where(free, rng.standard_normal(p.n_dofs), 0.0)
+    x[p.is_hanging_dof] = 0.0                               # Krylov vectors carry zeros on hanging rows
+
+    def distribute(v, zero_constrained):
+        v = v.copy()
+        for h, parents in p.hanging.items():
+            for c in range(3):
+                vals = [0.0 if (zero_constrained and con[q * 3 + c]) else v[q * 3 + c] for q in parents]
+                v[h * 3 + c] = sum(vals) / len(parents)
+        return v
+
+    def fold(y, respect_mask, x_orig=None):
+        y = y.copy()
+        for h, parents in p.hanging.items():
+            for c in range(3):
+                val = y[h * 3 + c] / len(parents)
+                for q in parents:
+                    if not (respect_mask and con[q * 3 + c]):
+                        y[q * 3 + c] += val
+                y[h * 3 + c] = diag[h * 3 + c] * x_orig[h * 3 + c] if x_orig is not None else 0.0
+        return y
+
+    # k_apply_init, then the cell kernel with constrained columns zeroed on load and constrained rows skipped
+    fx = distribute(x, True)
+    y = np.where(con, diag * x, 0.0)
+    fx_cols = np.where(con, 0.0, fx)
+    y += np.where(con, 0.0, J @ fx_cols)
+    y = fold(y, True, x)
+    Cm = p.H @ sp.diags(free.astype(float))
+    ref = Cm.T @ (J @ (Cm @ x))
+    assert np.allclose(y[free], ref[free], rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    assert np.all(y[p.is_hanging_dof] == 0.0)               # decoupled rows: diag * 0
+    # residual: r_total folds into every parent, r_pde drops the constrained rows afterwards
+    raw = p.raw_residual(sol, sol, sol)
+    r_total = fold(raw, False)
+    assert np.allclose(r_total, p.H.T @ raw, rtol=1e-13, atol=1e-13 * np.abs(raw).max())

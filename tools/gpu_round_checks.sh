@@ -1,0 +1,34 @@
+#!/bin/bash
+# What to run on a GPU box (gpurun -- 'bash tools/gpu_round_checks.sh [step ...]'), cheapest first.
+# Every step is wrapped in `timeout`; a multi-rank hang must never eat the budget again
+# (round 1 lost 53 GPU-minutes to two 300 s tear-down hangs on a 4-GPU box).
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
+mkdir -p gpurun_out
+N=$(nvidia-smi -L | wc -l)
+steps=${*:-"tests bench"}
+for s in $steps; do
+  case $s in
+    tests)        # the gating suite
+      timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 ;;
+    experimental) # forest / hanging-node device path, written in round 1 without a GPU at hand
+      PF_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_forest_experimental.py -x -q 2>&1 | tail -30 ;;
+    bench)
+      timeout 600 python bench.py --steps 50 --warmup 10 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+      cat gpurun_out/bench_n1.json ;;
+    bench_multi)  # only on a multi-GPU box; 120 s cap per rank count
+      for n in 2 4 8; do
+        [ "$n" -le "$N" ] || continue
+        timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
+          --master-port 29617 bench.py --gpus $n --steps 50 --warmup 10 2> gpurun_out/bench_n$n.err | tail -1 | tee gpurun_out/bench_n$n.json
+      done ;;
+    graph)        # PF_MG_GRAPH=1: V-cycle as a CUDA graph; hung at tear-down with NCCL nodes (2 ranks) in round 1
+      PF_MG_GRAPH=1 timeout 120 python tools/newton_bench.py --refine 4 --steps 2 --quiet | cut -c1-300 ;;
+    ncu)          # full capture of the default apply kernel (full grid, deterministic launch index)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_apply3d -s 3 -c 2 \
+        -o gpurun_out/prof_apply -f python tools/profile_apply.py --refine 4 --applies 6 > gpurun_out/ncu.log 2>&1
+      ls -la gpurun_out/prof_apply.ncu-rep ;;
+    trace)        # per-entry-point host time of the Newton loop (PF_PY_TRACE) and NCCL segment timers (PF_TRACE)
+      PF_PY_TRACE=1 timeout 120 python tools/newton_bench.py --refine 4 --steps 2 --quiet | cut -c1-1200 ;;
+    *) echo "unknown step $s" ;;
+  esac
+done
