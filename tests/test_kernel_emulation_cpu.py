@@ -1,0 +1,157 @@
+"""The CUDA kernel SOURCES for locally refined meshes, executed on the CPU.
+
+tests/emu/emu_kernels.cc compiles cracks_b200/csrc/{pf_generic,pf_forest,pf_vector,pf_split2d}.cuh with g++
+against a shim of <cuda_runtime.h> and runs the thread-per-item kernels one emulated thread at a time, in
+the order pf_api.cu launches them on a forest mesh (mark hanging, lumped mass, residual + fold, diagonal +
+fold, distribute -> init -> cell kernel -> fold).  That holds the kernel logic of the hanging-node device
+path against the oracle -- which reproduces the reference's sneddon_2d_1 and hetero_3d_1 goldens -- without
+a GPU.  It is test infrastructure, not a CPU fallback: nothing under cracks_b200/ links it, and the launch
+plumbing of pf_api.cu itself still needs its first GPU run (tests/test_gpu_forest_experimental.py)."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    d = os.path.join(HERE, "emu")
+    so = os.path.join(d, "libemu_kernels.so")
+    srcs = [os.path.join(d, "emu_kernels.cc"), os.path.join(d, "cuda_shim", "cuda_runtime.h")] + \
+           [os.path.join(ROOT, "cracks_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "cracks_b200", "csrc"))
+            if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(d, "cuda_shim"),
+                               "-o", so, os.path.join(d, "emu_kernels.cc")])
+    return C.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def ao(oracle):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import adaptive_oracle
+    return adaptive_oracle
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _run_emulation(emu, p, prm, sol, old, oo, con, x, cell_lame=None):
+    """p: oracle AdaptiveProblem (mesh tables + reference results), returns the emulated kernel outputs"""
+    nc, nn = p.nc, p.n_nodes
+    level_h, inv = np.unique(np.round(p.cell_h, 12), axis=0, return_inverse=True)
+    level = np.ascontiguousarray(inv.reshape(-1).astype(np.uint8))
+    hang = np.full((len(p.hanging), 5), -1, dtype=np.int64)
+    for k, (h, parents) in enumerate(sorted(p.hanging.items())):
+        hang[k, 0] = h
+        hang[k, 1:1 + len(parents)] = parents
+    ct = (prm.dt_old + prm.dt_oldold) / prm.dt_oldold
+    pt = np.ascontiguousarray(oo.reshape(nn, nc)[:, -1] + ct * (old.reshape(nn, nc)[:, -1] - oo.reshape(nn, nc)[:, -1]))
+    mask = np.zeros(nn, dtype=np.uint8)
+    for c in range(nc):
+        mask |= (con.reshape(nn, nc)[:, c].astype(np.uint8) << c)
+    phys = np.array([prm.lam, prm.mu, prm.G_c, prm.kappa, prm.eps, (prm.alpha_biot - 1.0) * prm.pressure, 1.0])
+    out = {k: np.zeros(nn * nc) for k in ("r_total", "r_pde", "diag", "y")}
+    out["mass"] = np.zeros(nn)
+    cells = np.ascontiguousarray(p.cells)
+    emu.emu_forest(C.c_int(p.dim), C.c_longlong(p.n_cells), C.c_longlong(nn), _ptr(cells), _ptr(level),
+                   C.c_int(level_h.shape[0]), _ptr(np.ascontiguousarray(level_h)), C.c_longlong(hang.shape[0]), _ptr(hang),
+                   _ptr(cell_lame), _ptr(phys), _ptr(sol), _ptr(pt), _ptr(mask), _ptr(x), _ptr(out["r_total"]),
+                   _ptr(out["r_pde"]), _ptr(out["diag"]), _ptr(out["y"]), _ptr(out["mass"]))
+    return out
+
+
+def _check(p, prm, out, sol, old, oo, con, x):
+    import scipy.sparse as sp
+    rel = lambda a, b: np.max(np.abs(a - b)) / np.max(np.abs(b))
+    raw = p.raw_residual(sol, old, oo)
+    r_total_ref = p.H.T @ raw
+    assert rel(out["r_total"], r_total_ref) <= 1e-12
+    assert rel(out["r_pde"], np.where(con, 0.0, r_total_ref)) <= 1e-12
+    assert rel(out["mass"], p.lumped_mass()) <= 1e-14
+    free = ~(con | p.is_hanging_dof)
+    Cm = p.H @ sp.diags(free.astype(float))
+    J = p.raw_jacobian(sol, old, oo)
+    ref = Cm.T @ (J @ (Cm @ x))
+    assert rel(out["y"][free], ref[free]) <= 1e-12
+    assert np.all(out["y"][p.is_hanging_dof] == 0.0)                       # decoupled rows times x_h = 0
+    assert np.allclose(out["y"][con & ~p.is_hanging_dof], (out["diag"] * x)[con & ~p.is_hanging_dof])
+    assert np.all(out["diag"] > 0)
+    # Jacobi diagonal: the raw diagonal on regular dofs plus the folded share of the hanging ones
+    d_raw = np.abs(J.diagonal())
+    reg = ~p.is_hanging_dof
+    assert np.all(out["diag"][reg] >= d_raw[reg] * (1 - 1e-12))
+
+
+def test_forest_kernels_2d_on_the_kat2_mesh(emu, ao):
+    run = ao.AdaptiveSneddonRun()
+    p, prm = run.p, run.prm
+    rng = np.random.default_rng(2)
+    nn = p.n_nodes
+    sol = np.zeros((nn, 3)); sol[:, :2] = 1e-2 * rng.standard_normal((nn, 2)); sol[:, 2] = rng.random(nn)
+    old = sol.copy(); old[:, 2] = rng.random(nn)
+    oo = old.copy(); oo[:, 2] += 0.5 * (rng.random(nn) - 0.5)        # extrapolation leaves [0, 1]: the clamp is exercised
+    sol, old, oo = (np.ascontiguousarray(p.distribute_hanging(v.reshape(-1))) for v in (sol, old, oo))
+    prm.dt_old, prm.dt_oldold = 1.0, 0.5
+    con = p.dirichlet.reshape(nn, 3).copy()
+    con[:, 2] |= (rng.random(nn) < 0.25) & ~p.is_hanging_node
+    con = con.reshape(-1)
+    free = ~(con | p.is_hanging_dof)
+    x = np.where(free, rng.standard_normal(p.n_dofs), 0.0)
+    x[con] = rng.standard_normal(int(con.sum()))                     # constrained entries must not leak into free rows
+    x[p.is_hanging_dof] = 0.0
+    out = _run_emulation(emu, p, prm, sol, old, oo, con, x)
+    _check(p, prm, out, sol, old, oo, con, x)                         # free rows only see free columns
+
+
+def test_forest_kernels_3d_hetero_on_the_kat5_mesh(emu, ao):
+    g = json.load(open(os.path.join(HERE, "golden", "hetero_3d_1.json")))
+    field = {tuple(k): e for k, e in zip(g["cell_keys"], g["e_modulus"])}
+    run = ao.HeteroRun3D(lambda cell, centre: field[cell])
+    p, prm = run.p, run.prm
+    prm.pressure = 10.0
+    rng = np.random.default_rng(3)
+    nn = p.n_nodes
+    sol = np.zeros((nn, 4)); sol[:, :3] = 1e-4 * rng.standard_normal((nn, 3)); sol[:, 3] = rng.random(nn)
+    sol = np.ascontiguousarray(p.distribute_hanging(sol.reshape(-1)))
+    prm.dt_old = prm.dt_oldold = 0.01
+    con = p.dirichlet.reshape(nn, 4).copy()
+    con[:, 3] |= (rng.random(nn) < 0.25) & ~p.is_hanging_node
+    con = con.reshape(-1)
+    free = ~(con | p.is_hanging_dof)
+    x = np.where(free, rng.standard_normal(p.n_dofs), 0.0)
+    out = _run_emulation(emu, p, prm, sol, sol, sol, con, x, cell_lame=p._lame_a)
+    _check(p, prm, out, sol, sol, sol, con, x)
+    assert {len(v) for v in p.hanging.values()} == {2, 4}             # edge and face hanging nodes were exercised
+
+
+def test_active_set_kernel_skips_hanging_nodes(emu, ao):
+    run = ao.AdaptiveSneddonRun()
+    p = run.p
+    rng = np.random.default_rng(4)
+    nn = p.n_nodes
+    r_total = rng.standard_normal(nn * 3)
+    mass = p.lumped_mass()
+    old = rng.random(nn * 3)
+    sol = old + 0.1 * rng.standard_normal(nn * 3)
+    sol0 = sol.copy()
+    cycle = np.zeros(nn, dtype=np.int32)
+    mask = np.where(p.is_hanging_node, 0x80, 0).astype(np.uint8)
+    counts = np.zeros(3, dtype=np.uint64)
+    emu.emu_active_set(C.c_int(2), C.c_longlong(nn), C.c_double(10.0), _ptr(r_total), _ptr(mass), _ptr(old), _ptr(sol),
+                       _ptr(cycle), _ptr(mask), _ptr(counts))
+    crit = r_total.reshape(nn, 3)[:, 2] / mass + 10.0 * (sol0.reshape(nn, 3)[:, 2] - old.reshape(nn, 3)[:, 2])
+    active_ref = (~p.is_hanging_node) & (crit > 0.0)                       # cracks.cc:2855-2881
+    assert np.array_equal((mask & 4) != 0, active_ref)
+    assert np.all((mask & 0x80) == np.where(p.is_hanging_node, 0x80, 0))   # hanging bit untouched
+    assert int(counts[0]) == int(active_ref.sum())
+    phi, phi_old = sol.reshape(nn, 3)[:, 2], old.reshape(nn, 3)[:, 2]
+    assert np.array_equal(phi[active_ref], phi_old[active_ref]) and np.array_equal(phi[~active_ref], sol0.reshape(nn, 3)[~active_ref, 2])
