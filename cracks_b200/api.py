@@ -82,6 +82,7 @@ _SIGS = {
     "pf_synchronize": [C.c_void_p],
     "pf_set_state": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double],
     "pf_get_solution": [C.c_void_p, C.c_void_p],
+    "pf_get_state": [C.c_void_p, C.c_int, C.c_void_p],
     "pf_update_solution": [C.c_void_p, C.c_double],
     "pf_set_params": [C.c_void_p, C.POINTER(Params)],
     "pf_set_constraints": [C.c_void_p, C.c_void_p, C.c_void_p],
@@ -322,6 +323,12 @@ class PhaseFieldContext:
 
     def set_time_parameters(self, dt_old, dt_oldold, use_old_timestep_pf, pressure):
         self._check(self.lib.pf_set_time_parameters(self.h, dt_old, dt_oldold, int(use_old_timestep_pf), pressure))
+
+    def get_state(self, which: int) -> np.ndarray:
+        """0: solution, 1: old_solution, 2: old_old_solution (block layout)"""
+        out = np.zeros(self.n_dofs)
+        self._check(self.lib.pf_get_state(self.h, which, _ptr(out)))
+        return out
 
     def get_solution(self) -> np.ndarray:
         out = np.zeros(self.n_dofs)

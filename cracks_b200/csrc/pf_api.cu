@@ -1928,6 +1928,14 @@ pf_get_solution (pf_ctx *ctx, double *sol)
 }
 
 int
+pf_get_state (pf_ctx *ctx, int which, double *out)
+{
+  if (!ctx || !out || which < 0 || which > 2)
+    return PF_BAD_ARG;
+  return download_block (ctx, which == 0 ? ctx->sol : (which == 1 ? ctx->old : ctx->oldold), out);
+}
+
+int
 pf_update_solution (pf_ctx *ctx, double alpha)
 {
   if (!ctx)

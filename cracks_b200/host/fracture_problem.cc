@@ -110,9 +110,12 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
     throw NotImplemented ("test case <" + test_case + "> needs meshes / boundary data outside this round's scope");
   if (miehe () && dim_ != 2)
     throw NotImplemented ("the Miehe tests are 2-D (meshes/unit_slit.inp)");
-  if (n_local_pre_refine != 0)
-    throw NotImplemented ("local pre-refinement (hanging nodes) is not available: use global refinement");
-  if (n_refinement_cycles != 0 && !(miehe () && refinement_strategy == "phase field"))
+  const bool forest_case = test_case == "sneddon" && dim_ == 2 && refinement_strategy == "fixed preref sneddon"
+                           && (n_local_pre_refine != 0 || n_refinement_cycles != 0);
+  if (n_local_pre_refine != 0 && !forest_case)
+    throw NotImplemented ("local pre-refinement (hanging nodes) is only available for sneddon, dim 2, "
+                          "ref strategy = fixed preref sneddon");
+  if (n_refinement_cycles != 0 && !forest_case && !(miehe () && refinement_strategy == "phase field"))
     throw NotImplemented ("adaptive refinement (hanging nodes) is not available: use global refinement");
 
   prm_.enter_subsection ("Problem dependent parameters");
@@ -150,6 +153,12 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
   for (int d = 0; d < dim_; ++d)
     cells *= n;
   pcout_ << "Cells:\t" << cells << std::endl;
+  if (forest_case)
+    {
+      const int nc[3] = {n, n, 1};
+      const double lo[3] = {-10.0, -10.0, 0.0}, hi[3] = {10.0, 10.0, 0.0};
+      forest_.reset (new Forest (2, nc, lo, hi));
+    }
 
   prm_.enter_subsection ("Solver parameters");
   direct_solver = prm_.get_bool ("Use Direct Inner Solver");
@@ -175,6 +184,8 @@ FracturePhaseFieldProblem::determine_mesh_dependent_parameters ()
   for (int d = 0; d < dim_; ++d)
     d2 += mesh_.h[d] * mesh_.h[d];
   min_cell_diameter = std::sqrt (d2);
+  if (use_forest ())
+    min_cell_diameter = forest_->min_cell_diameter ();
   // the Miehe tests use the h the mesh will have on its final level (cracks.cc:3839-3854);
   // the coarse cells of unit_slit.inp have diameter sqrt(2)/2
   if (miehe ())
@@ -200,6 +211,14 @@ FracturePhaseFieldProblem::setup_system ()
   params_.kappa = constant_k;
   params_.eps = alpha_eps;
   params_.alpha_biot = 0.0; // cracks.cc:1497
+  if (use_forest ())
+    {
+      forest_create_context ();
+      pcout_ << std::endl;
+      pcout_ << "DoFs: " << n_nodes () * dim_ << " solid + " << n_nodes () << " phase"
+             << " = " << n_nodes () * (dim_ + 1) << std::endl;
+      return;
+    }
   const int rc = pf_create (&mesh_, &params_, device, 0, 1, nullptr, &ctx_);
   pf_check (ctx_, rc);
   if (miehe ())
@@ -311,6 +330,13 @@ FracturePhaseFieldProblem::run ()
   pcout_ << "Running on 1 GPU" << std::endl;
   set_runtime_parameters ();
   setup_system ();
+  // local pre-refinement (cracks.cc:4177-4211): interpolate the initial condition, refine, set up again
+  for (unsigned i = 0; i < n_local_pre_refine; ++i)
+    {
+      pcout_ << "Prerefinement step with h= " << min_cell_diameter << std::endl;
+      forest_refine_fixed_preref_sneddon ();
+      setup_system ();
+    }
   if (!(alpha_eps >= min_cell_diameter))
     throw ParameterError ("You need to pick eps >= h");
   if (!(constant_k < 1.0))
@@ -327,6 +353,11 @@ FracturePhaseFieldProblem::run ()
   // initial condition, project_back_phase_field, old = old_old = solution (4233-4277)
   if (miehe ())
     pf_check (ctx_, pf_interpolate_unbroken (ctx_)); // InitialValuesTensionOrShear, cracks.cc:679-691
+  else if (use_forest ())
+    {
+      const std::vector<double> ic = forest_initial_sneddon ();
+      pf_check (ctx_, pf_set_state (ctx_, ic.data (), ic.data (), ic.data (), timestep, timestep, 0, func_pressure.value (0.0)));
+    }
   else
     pf_check (ctx_, pf_interpolate_sneddon (ctx_, min_cell_diameter));
   pf_check (ctx_, pf_project_phase_field (ctx_));
@@ -335,6 +366,9 @@ FracturePhaseFieldProblem::run ()
   long long nodes = pf_n_dofs (ctx_) / (dim_ + 1), cells = 1;
   for (int d = 0; d < dim_; ++d)
     cells *= mesh_.n[d];
+  if (use_forest ())
+    cells = n_cells ();
+  unsigned refinement_cycle = 0;
   double finishing_timestep_loop = 0;
 
   do
@@ -431,7 +465,7 @@ FracturePhaseFieldProblem::run ()
           // compute_functional_values(), cracks.cc:3704-3725: COD on the lines x = -1.5 + i/256;
           // lines that carry no mesh face print nothing (compute_cod returns -1e300 there)
           const unsigned N = 16 * 16;
-          for (unsigned i = 0; i <= 3 * N; ++i)
+          for (unsigned i = 0; i <= 3 * N && !use_forest (); ++i) // pf_cod: box meshes only so far
             {
               const double x = -1.5 + i * (1.0 / N);
               const double t = (x - mesh_.origin[0]) / mesh_.h[0];
@@ -446,13 +480,164 @@ FracturePhaseFieldProblem::run ()
                   cod_.push_back ({x, cod});
                 }
             }
-          break; // n_refinement_cycles == 0
+          if (n_refinement_cycles == 0)
+            break;
+          // refinement cycle (cracks.cc:4525-4560): refine, carry old / old_old over, restart from the
+          // re-interpolated initial condition
+          --n_refinement_cycles;
+          pcout_ << std::endl;
+          pcout_ << "\n================== " << std::endl;
+          pcout_ << "Refinement cycle " << refinement_cycle << "\n------------------ " << std::endl;
+          if (!use_forest ())
+            throw NotImplemented ("refinement cycles need the forest path (sneddon, dim 2, fixed preref sneddon)");
+          {
+            const Forest coarse = *forest_;
+            const long long nd_old = pf_n_dofs (ctx_), nn_old = nd_old / 3;
+            std::vector<double> old_b ((size_t) nd_old), oldold_b ((size_t) nd_old);
+            pf_check (ctx_, pf_get_state (ctx_, 1, old_b.data ()));
+            pf_check (ctx_, pf_get_state (ctx_, 2, oldold_b.data ()));
+            forest_refine_fixed_preref_sneddon ();
+            setup_system ();
+            const long long nn_new = n_nodes ();
+            // block layout [u | phi] <-> nodal interleaved for the transfer
+            auto to_nodal = [](const std::vector<double> &b, long long nn) {
+              std::vector<double> v ((size_t) nn * 3);
+              for (long long i = 0; i < nn; ++i)
+                {
+                  v[(size_t) (3 * i)] = b[(size_t) (2 * i)];
+                  v[(size_t) (3 * i + 1)] = b[(size_t) (2 * i + 1)];
+                  v[(size_t) (3 * i + 2)] = b[(size_t) (2 * nn + i)];
+                }
+              return v;
+            };
+            auto to_block = [](const std::vector<double> &v, long long nn) {
+              std::vector<double> b ((size_t) nn * 3);
+              for (long long i = 0; i < nn; ++i)
+                {
+                  b[(size_t) (2 * i)] = v[(size_t) (3 * i)];
+                  b[(size_t) (2 * i + 1)] = v[(size_t) (3 * i + 1)];
+                  b[(size_t) (2 * nn + i)] = v[(size_t) (3 * i + 2)];
+                }
+              return b;
+            };
+            std::vector<double> tmp ((size_t) nn_new * 3);
+            forest_->transfer (coarse, to_nodal (old_b, nn_old).data (), tmp.data (), 3);
+            const std::vector<double> old_new = to_block (tmp, nn_new);
+            forest_->transfer (coarse, to_nodal (oldold_b, nn_old).data (), tmp.data (), 3);
+            const std::vector<double> oldold_new = to_block (tmp, nn_new);
+            const std::vector<double> ic = forest_initial_sneddon ();
+            pf_check (ctx_, pf_set_state (ctx_, ic.data (), old_new.data (), oldold_new.data (), old_timestep,
+                                          old_old_timestep, 0, func_pressure.value (time)));
+            nodes = nn_new;
+            cells = n_cells ();
+            ++refinement_cycle;
+          }
         }
     }
   while (timestep_number <= max_no_timesteps);
 
   pcout_ << std::endl;
   pcout_ << "Finishing time step loop: " << finishing_timestep_loop << std::endl;
+}
+
+// ---- forest path (EXPERIMENTAL: device side not yet run on a GPU) ---------------------------------
+
+long long
+FracturePhaseFieldProblem::n_nodes () const
+{
+  return use_forest () ? forest_->n_nodes () : pf_n_dofs (ctx_) / (dim_ + 1);
+}
+
+long long
+FracturePhaseFieldProblem::n_cells () const
+{
+  return forest_->n_cells ();
+}
+
+// refine_mesh(), strategy `fixed preref sneddon` (cracks.cc:3901-3923): cells with a vertex in
+// [-2.5, 2.5] x [-1.25, 1.25]
+void
+FracturePhaseFieldProblem::forest_refine_fixed_preref_sneddon ()
+{
+  const Forest &f = *forest_;
+  std::vector<char> flags ((size_t) f.n_cells (), 0);
+  for (long long c = 0; c < f.n_cells (); ++c)
+    for (int v = 0; v < 4; ++v)
+      {
+        const long long n = f.connectivity ()[(size_t) (c * 4 + v)];
+        const double x = f.coordinates ()[(size_t) (2 * n)], y = f.coordinates ()[(size_t) (2 * n + 1)];
+        if (x <= 2.5 && x >= -2.5 && y <= 1.25 && y >= -1.25)
+          flags[(size_t) c] = 1;
+      }
+  forest_->refine (flags);
+}
+
+// setup_system() on the forest: flat tables -> pf_create_forest, Dirichlet rows u = 0 on the boundary
+void
+FracturePhaseFieldProblem::forest_create_context ()
+{
+  if (ctx_)
+    {
+      pf_destroy (ctx_);
+      ctx_ = nullptr;
+    }
+  const Forest &f = *forest_;
+  const long long nn = f.n_nodes (), nc = f.n_cells ();
+  std::vector<int64_t> conn (f.connectivity ().begin (), f.connectivity ().end ());
+  std::vector<uint8_t> level ((size_t) nc);
+  for (long long c = 0; c < nc; ++c)
+    level[(size_t) c] = (uint8_t) f.cells ()[(size_t) c].level;
+  std::vector<double> level_h ((size_t) (f.max_level () + 1) * 2);
+  for (int l = 0; l <= f.max_level (); ++l)
+    f.cell_size (l, &level_h[(size_t) (2 * l)]);
+  std::vector<int64_t> hang (f.hanging_nodes ().size () * 5);
+  for (size_t h = 0; h < f.hanging_nodes ().size (); ++h)
+    {
+      const HangingNode &hn = f.hanging_nodes ()[h];
+      hang[5 * h] = hn.node;
+      for (int q = 0; q < 4; ++q)
+        hang[5 * h + 1 + (size_t) q] = q < hn.n_parents ? hn.parents[q] : -1;
+    }
+  pf_forest_mesh fm{};
+  fm.dim = 2;
+  fm.n_cells = nc;
+  fm.n_nodes = nn;
+  fm.conn = conn.data ();
+  fm.cell_level = level.data ();
+  fm.n_levels = f.max_level () + 1;
+  fm.level_h = level_h.data ();
+  fm.n_hanging = (int64_t) f.hanging_nodes ().size ();
+  fm.hanging = hang.empty () ? nullptr : hang.data ();
+  const int rc = pf_create_forest (&fm, &params_, device, &ctx_);
+  pf_check (ctx_, rc);
+  // set_newton_bc(): u = 0 on boundary ids 0..3 (cracks.cc:2575-2583); block layout [u | phi]
+  std::vector<uint8_t> dirichlet ((size_t) nn * 3, 0), none ((size_t) nn * 3, 0);
+  for (long long n = 0; n < nn; ++n)
+    {
+      const double x = f.coordinates ()[(size_t) (2 * n)], y = f.coordinates ()[(size_t) (2 * n + 1)];
+      if (x == -10.0 || x == 10.0 || y == -10.0 || y == 10.0)
+        dirichlet[(size_t) (2 * n)] = dirichlet[(size_t) (2 * n + 1)] = 1;
+    }
+  pf_check (ctx_, pf_set_constraints (ctx_, dirichlet.data (), none.data ()));
+  // the reference hands these small systems to AMG; Jacobi-GMRES wants a long basis
+  pf_check (ctx_, pf_set_krylov_dim (ctx_, 300));
+  gmres_max_iterations = std::max (gmres_max_iterations, 3000);
+}
+
+// InitialValuesSneddon<2> (cracks.cc:381-406) at the forest's nodes, block layout
+std::vector<double>
+FracturePhaseFieldProblem::forest_initial_sneddon () const
+{
+  const Forest &f = *forest_;
+  const long long nn = f.n_nodes ();
+  std::vector<double> b ((size_t) nn * 3, 0.0);
+  for (long long n = 0; n < nn; ++n)
+    {
+      const double x = f.coordinates ()[(size_t) (2 * n)], y = f.coordinates ()[(size_t) (2 * n + 1)];
+      const bool broken = (x * x <= 1.0) && (std::abs (2.0 * y) <= 2.0 * min_cell_diameter);
+      b[(size_t) (2 * nn + n)] = broken ? 0.0 : 1.0;
+    }
+  return b;
 }
 
 } // namespace cracks

@@ -17,6 +17,9 @@
 #include <string>
 #include <vector>
 
+#include <memory>
+
+#include "forest.h"
 #include "function_parser.h"
 #include "matrix_free_jacobian.h"
 #include "parameter_handler.h"
@@ -62,12 +65,21 @@ private:
   double newton_active_set ();
   void write_statistics () const;
   bool miehe () const { return test_case == "miehe tension" || test_case == "miehe shear"; }
+  // EXPERIMENTAL (device side not yet run on a GPU): Sneddon 2-D with local pre-refinement
+  // / refinement cycles on the host forest, strategy `fixed preref sneddon`
+  bool use_forest () const { return forest_ != nullptr; }
+  void forest_refine_fixed_preref_sneddon ();
+  void forest_create_context ();
+  std::vector<double> forest_initial_sneddon () const;
+  long long n_nodes () const;
+  long long n_cells () const;
   int miehe_kind () const { return test_case == "miehe tension" ? 1 : 2; }
 
   ParameterHandler &prm_;
   int dim_;
   std::ostream &pcout_;
   pf_ctx *ctx_ = nullptr;
+  std::unique_ptr<Forest> forest_;
   pf_mesh mesh_{};
   pf_params params_{};
 

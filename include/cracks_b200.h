@@ -149,6 +149,9 @@ int pf_synchronize (pf_ctx *ctx);
 int pf_set_state (pf_ctx *ctx, const double *sol, const double *old, const double *oldold,
                   double dt_old, double dt_oldold, int use_old_timestep_pf, double pressure);
 int pf_get_solution (pf_ctx *ctx, double *sol);
+/* which = 0: solution, 1: old_solution, 2: old_old_solution (what SolutionTransfer carries to a refined
+ * mesh, cracks.cc:4137-4159); host buffer in block layout */
+int pf_get_state (pf_ctx *ctx, int which, double *out);
 /* in-place update of the linearisation point: sol += alpha * dx (line search, cracks.cc:2944) */
 int pf_update_solution (pf_ctx *ctx, double alpha);
 int pf_set_params (pf_ctx *ctx, const pf_params *params);

@@ -87,3 +87,40 @@ def test_kat2_golden_on_the_gpu(pf):
         assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-6)
     assert drv.tcv == pytest.approx(g["tcv"], rel=1e-5)
     ctx.close()
+
+
+def test_kat2_through_the_cli(pf, tmp_path):
+    """tests/sneddon_2d_1.prm through cracks_b200_run: local pre-refinement on the host forest, hanging nodes
+    on the device, the refinement cycle at the end (777 DoFs) like the golden output."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    subprocess.check_call(["make", "-C", os.path.join(root, "cracks_b200", "host"), "-s"])
+    g = json.load(open(os.path.join(HERE, "golden", "sneddon_2d_1.json")))
+    sections = {"Global parameters": ["Global pre-refinement steps", "Local pre-refinement steps", "Adaptive refinement cycles",
+                                      "Max No of timesteps", "Timestep size", "outer solver", "test case", "ref strategy",
+                                      "value phase field for refinement"],
+                "Problem dependent parameters": ["K reg", "Eps reg", "Gamma penalization", "Pressure", "Fracture toughness G_c",
+                                                 "Poisson ratio nu", "E modulus"],
+                "Solver parameters": ["Use Direct Inner Solver", "Newton lower bound", "Newton maximum steps",
+                                      "Decompose stress in rhs", "Decompose stress in matrix", "Line search maximum steps"]}
+    lines = []
+    for sec, keys in sections.items():
+        lines.append("subsection " + sec)
+        if sec == "Global parameters":
+            lines += ["  set Dimension = 2", "  set Output directory = " + str(tmp_path / "out")]
+        lines += ["  set %s = %s" % (k, g["prm"][k]) for k in keys if k in g["prm"]]
+        lines.append("end")
+    (tmp_path / "t.prm").write_text("\n".join(lines) + "\n")
+    r = subprocess.run([os.path.join(root, "cracks_b200", "cracks_b200_run"), str(tmp_path / "t.prm")],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-1000:])
+    assert r.returncode == 0, r.stderr
+    assert "Prerefinement step with h= 2.82843" in r.stdout
+    assert "DoFs: 302 solid + 151 phase = 453" in r.stdout and "DoFs: 518 solid + 259 phase = 777" in r.stdout
+    assert "0\t\t\t1.491639e+01" in r.stdout
+    rows = [l.split() for l in open(tmp_path / "out" / "statistics") if not l.startswith("#")]
+    assert len(rows) == 4
+    for row, ref in zip(rows, g["statistics"]):
+        assert int(row[2]) == 453
+        assert float(row[5]) == pytest.approx(ref["crack"], rel=1e-8)
+        assert float(row[4]) == pytest.approx(ref["bulk"], rel=1e-6)
