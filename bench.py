@@ -319,7 +319,11 @@ def main():
                                max_newton=50, max_line_search=10, gmres_max_it=200)
         barrier()
         t0 = time.perf_counter()
-        nstats = drv.run(mesh_diameter(mesh))
+        try:
+            # every decision in the loop is taken on all-reduced values, so a failure is raised on all ranks alike
+            nstats, nerr = drv.run(mesh_diameter(mesh)), None
+        except pf.PFError as exc:
+            nstats, nerr = drv.statistics, str(exc)
         nctx.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -328,9 +332,12 @@ def main():
             dt = float(t[0])
         newton = {"newton_its_per_s": drv.newton_its / dt, "newton_its": drv.newton_its,
                   "linear_its": drv.lin_its, "time_steps": len(nstats), "wall_s": dt,
-                  "crack_energy": nstats[-1]["crack"], "bulk_energy": nstats[-1]["bulk"],
+                  "crack_energy": nstats[-1]["crack"] if nstats else None,
+                  "bulk_energy": nstats[-1]["bulk"] if nstats else None,
                   "preconditioner": "matrix-free geometric multigrid V-cycle (z-slab levels, replicated below), "
                                     "Chebyshev-Jacobi smoothing"}
+        if nerr:
+            newton["error"] = nerr
         nctx.close()
 
     if rank == 0:
