@@ -155,3 +155,73 @@ def test_active_set_kernel_skips_hanging_nodes(emu, ao):
     assert int(counts[0]) == int(active_ref.sum())
     phi, phi_old = sol.reshape(nn, 3)[:, 2], old.reshape(nn, 3)[:, 2]
     assert np.array_equal(phi[active_ref], phi_old[active_ref]) and np.array_equal(phi[~active_ref], sol0.reshape(nn, 3)[~active_ref, 2])
+
+
+# ---- the tiled 3-D hot kernels, one OS thread per CUDA thread -----------------------------------------
+
+@pytest.fixture(scope="module")
+def emu_tiled():
+    d = os.path.join(HERE, "emu")
+    so = os.path.join(d, "libemu_tiled.so")
+    srcs = [os.path.join(d, "emu_tiled.cc"), os.path.join(d, "cuda_shim_block", "cuda_runtime.h")] + \
+           [os.path.join(ROOT, "cracks_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "cracks_b200", "csrc"))
+            if f.endswith(".cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-I",
+                               os.path.join(d, "cuda_shim_block"), "-o", so, os.path.join(d, "emu_tiled.cc")])
+    return C.CDLL(so)
+
+
+def _box_case(oracle, n, h, seed):
+    rng = np.random.default_rng(seed)
+    lo = tuple(-0.5 * n[d] * h[d] for d in range(3))
+    hi = tuple(0.5 * n[d] * h[d] for d in range(3))
+    prob = oracle.Problem(3, tuple(n), lo, hi, kappa_of_h=lambda hh: 1e-3, eps_of_h=lambda hh: 2.0 * hh, pressure=1e-3)
+    nn = prob.n_nodes
+    sol = np.zeros((nn, 4)); sol[:, :3] = 1e-2 * rng.standard_normal((nn, 3)); sol[:, 3] = rng.random(nn)
+    old = sol.copy(); old[:, 3] = rng.random(nn)
+    oo = old.copy(); oo[:, 3] = old[:, 3] + 0.5 * (rng.random(nn) - 0.5)
+    sol, old, oo = sol.reshape(-1), old.reshape(-1), oo.reshape(-1)
+    prob.prm.dt_old, prob.prm.dt_oldold = 1.0, 0.5
+    con = prob.dirichlet_mask().reshape(nn, 4); con[rng.random(nn) < 0.2, 3] = 1
+    con = np.ascontiguousarray(con.reshape(-1))
+    x = rng.standard_normal(nn * 4)
+    pt = np.ascontiguousarray(oo.reshape(nn, 4)[:, 3] + 3.0 * (old.reshape(nn, 4)[:, 3] - oo.reshape(nn, 4)[:, 3]))
+    mask = np.zeros(nn, dtype=np.uint8)
+    for c in range(4):
+        mask |= (con.reshape(nn, 4)[:, c].astype(np.uint8) << c)
+    phys = np.array([prob.prm.lam, prob.prm.mu, prob.prm.G_c, prob.prm.kappa, prob.prm.eps, -prob.prm.pressure, 1.0])
+    return prob, sol, old, oo, con, x, pt, mask, phys
+
+
+@pytest.mark.parametrize("n,h", [((17, 5, 2), (0.5, 0.5, 0.5)),      # cubic cells: the ISO specialisation, ragged tiles
+                                 ((7, 6, 3), (0.3, 0.45, 0.7))])     # anisotropic cells: the general variant
+def test_tiled_apply_kernel_sources_match_the_oracle(oracle, emu_tiled, n, h):
+    prob, sol, old, oo, con, x, pt, mask, phys = _box_case(oracle, n, h, seed=sum(n))
+    y_ref = prob.apply_jacobian(sol, old, oo, con, x)
+    free = con == 0
+    diag = np.ones(prob.n_dofs)
+    nv, hv = (C.c_int * 3)(*n), (C.c_double * 3)(*h)
+    for variant in (16, 3):                                           # v4 (default) and v2
+        y = np.zeros(prob.n_dofs)
+        emu_tiled.emu_apply3d(C.c_int(variant), C.c_int(3), nv, hv, _ptr(phys), _ptr(x), _ptr(sol), _ptr(pt), _ptr(mask),
+                              _ptr(diag), _ptr(y))
+        assert np.max(np.abs(y[free] - y_ref[free])) / np.max(np.abs(y_ref[free])) <= 1e-12, variant
+        assert np.array_equal(y[~free], x[~free])                     # constrained rows: diag * x, untouched by the tiles
+    # the 2-point-rule operator of the multigrid smoother: v4 and v2 must agree with each other
+    y2 = [np.zeros(prob.n_dofs), np.zeros(prob.n_dofs)]
+    for out, variant in zip(y2, (16, 3)):
+        emu_tiled.emu_apply3d(C.c_int(variant), C.c_int(2), nv, hv, _ptr(phys), _ptr(x), _ptr(sol), _ptr(pt), _ptr(mask),
+                              _ptr(diag), _ptr(out))
+    assert np.max(np.abs(y2[0] - y2[1])) / np.max(np.abs(y2[1])) <= 1e-12
+    # and it is a different (under-integrated) operator, close to the exact one
+    assert 1e-6 < np.max(np.abs(y2[0][free] - y_ref[free])) / np.max(np.abs(y_ref[free])) < 0.5
+
+
+def test_tiled_residual_kernel_source_matches_the_oracle(oracle, emu_tiled):
+    n, h = (18, 5, 2), (0.5, 0.4, 0.3)
+    prob, sol, old, oo, con, x, pt, mask, phys = _box_case(oracle, n, h, seed=9)
+    _, r_tot_ref = prob.residual(sol, old, oo, con)
+    r = np.zeros(prob.n_dofs)
+    emu_tiled.emu_residual3d((C.c_int * 3)(*n), (C.c_double * 3)(*h), _ptr(phys), _ptr(sol), _ptr(pt), _ptr(r))
+    assert np.max(np.abs(r - r_tot_ref)) / np.max(np.abs(r_tot_ref)) <= 1e-12
