@@ -789,6 +789,10 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
             case 14: rc = launch_apply3d_v3<16, 8, 1, 2> (ctx, x, y); break;
             case 15: rc = launch_apply3d_v3<32, 2, 1, 4> (ctx, x, y); break;
             case 3: rc = launch_apply3d_v2<16, 4, 1> (ctx, x, y); break;
+            // v4 at 12 / 10 warps per SM: ptxas caps it at 168 registers and spills 164 / 256 bytes
+            // (vs 222 registers, no spills, 8 warps per SM); prepared offline, to be measured
+            case 17: rc = launch_apply3d_v4<16, 4, 1, 6> (ctx, x, y); break;
+            case 18: rc = launch_apply3d_v4<16, 4, 1, 5> (ctx, x, y); break;
             default: rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y); break; // variant 16: fastest measured
             }
           if (rc)
@@ -2773,7 +2777,7 @@ pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count)
 int
 pf_debug_set_variant (int variant)
 {
-  if (variant < 1 || variant > 16)
+  if (variant < 1 || variant > 18)
     return PF_BAD_ARG;
   g_apply_variant = variant;
   return PF_OK;

@@ -21,6 +21,11 @@ for s in $steps; do
         timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
           --master-port 29617 bench.py --gpus $n --steps 50 --warmup 10 2> gpurun_out/bench_n$n.err | tail -1 | tee gpurun_out/bench_n$n.json
       done ;;
+    variants)     # A/B of apply-kernel variants prepared offline: 16 = v4 default (222 regs, 8 warps/SM),
+                  # 17 / 18 = v4 capped at 168 registers (12 / 10 warps/SM, 164 / 256 B spills)
+      for v in 16 17 18; do
+        echo "variant $v"; timeout 300 python bench.py --variant $v --steps 50 --warmup 10 --no-cpu-baseline --no-newton --e2e-steps 1 | cut -c1-330
+      done ;;
     graph)        # PF_MG_GRAPH=1: V-cycle as a CUDA graph; hung at tear-down with NCCL nodes (2 ranks) in round 1
       PF_MG_GRAPH=1 timeout 120 python tools/newton_bench.py --refine 4 --steps 2 --quiet | cut -c1-300 ;;
     ncu)          # full capture of the default apply kernel (full grid, deterministic launch index)
