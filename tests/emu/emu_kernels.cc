@@ -162,6 +162,59 @@ emu_forest (int dim, long long n_cells, long long n_nodes, const long long *conn
     run<3> (f, p, sol, pt, mask, x, r_total, r_pde, diag, y, mass);
 }
 
+// the generic kernels on a 2-D box / slit mesh (implicit connectivity), with or without the Miehe split,
+// in the order residual_dev / diag_and_aux / apply_dev launch them
+void
+emu_box2d (const int *n, const double *h, int slit, const double *phys /* lambda, mu, G_c, kappa, eps, P1, clamp, split,
+           d_rhs, d_mat */, const double *sol, const double *pt, const unsigned char *mask, const double *x,
+           double *r_total, double *diag, double *y, double *mass)
+{
+  Grid g;
+  std::memset (&g, 0, sizeof g);
+  g.dim = 2;
+  g.nodes_per_plane = 1;
+  g.n_global_nodes = 1;
+  for (int d = 0; d < 3; ++d)
+    {
+      g.n[d] = d < 2 ? n[d] : 1;
+      g.nn[d] = d < 2 ? n[d] + 1 : 1;
+      g.h[d] = d < 2 ? h[d] : 1.0;
+      g.n_global_nodes *= g.nn[d];
+    }
+  g.nodes_per_plane = g.nn[0];
+  g.plane_end = g.owned_end = g.nn[1];
+  g.cell_end = n[1];
+  g.n_local_nodes = g.n_global_nodes;
+  g.n_local_cells = (long long) n[0] * n[1];
+  g.slit_row = -1;
+  if (slit)
+    {
+      g.slit_row = n[1] / 2;
+      g.slit_i0 = n[0] / 2 + 1;
+      g.slit_base = g.n_local_nodes;
+      g.n_local_nodes += n[0] / 2;
+      g.n_global_nodes += n[0] / 2;
+    }
+  Phys p;
+  std::memset (&p, 0, sizeof p);
+  p.lambda = phys[0], p.mu = phys[1], p.G_c = phys[2], p.kappa = phys[3], p.eps = phys[4], p.P1 = phys[5];
+  p.clamp_extra = (int) phys[6];
+  p.split = (int) phys[7];
+  p.d_rhs = phys[8];
+  p.d_mat = phys[9];
+  FeTab<2> tab;
+  fill_tab<2> (tab, h);
+  const long long nn = g.n_local_nodes, nd = nn * 3;
+  std::fill (mass, mass + nn, 0.0);
+  launch (k_lumped_mass_cells<2>, g.n_local_cells, 128, g, mass);
+  std::fill (r_total, r_total + nd, 0.0);
+  launch (k_residual_generic<2>, g.n_local_cells, 128, g, p, (const FeTab<2> *) &tab, sol, pt, r_total);
+  std::fill (diag, diag + nd, 0.0);
+  launch (k_diag_generic<2>, g.n_local_cells, 128, g, p, (const FeTab<2> *) &tab, sol, pt, diag);
+  launch (k_apply_init<2>, nn, 256, nn, x, (const double *) diag, mask, y);
+  launch (k_apply_generic<2>, g.n_local_cells, 128, g, p, (const FeTab<2> *) &tab, x, sol, pt, mask, y);
+}
+
 // active-set kernel on a forest: returns counts {active, cycling, changed}
 void
 emu_active_set (int dim, long long n_nodes, double c_scale, const double *r_total, const double *mass, const double *old,

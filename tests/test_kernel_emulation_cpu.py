@@ -225,3 +225,41 @@ def test_tiled_residual_kernel_source_matches_the_oracle(oracle, emu_tiled):
     r = np.zeros(prob.n_dofs)
     emu_tiled.emu_residual3d((C.c_int * 3)(*n), (C.c_double * 3)(*h), _ptr(phys), _ptr(sol), _ptr(pt), _ptr(r))
     assert np.max(np.abs(r - r_tot_ref)) / np.max(np.abs(r_tot_ref)) <= 1e-12
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_generic_2d_kernel_sources_on_the_slit_mesh(oracle, emu, split):
+    """The 2-D path the GPU suite covers (tests/test_gpu_miehe.py) once more in the CPU suite: slit
+    connectivity, Miehe split and its linearisation, diagonal, lumped mass -- kernel sources vs oracle."""
+    lam, mu = 121.15e3, 80.77e3
+    n = 8
+    prob = oracle.Problem(2, (n, n), (0.0, 0.0), (1.0, 1.0), G_c=2.7, pressure=0.0, kappa_of_h=lambda h: 1e-6,
+                          eps_of_h=lambda h: 2.0 * h, slit=True, lame=(lam, mu))
+    prob.prm.split, prob.prm.d_rhs, prob.prm.d_mat = int(split), 1.0, 1.0
+    prob.prm.dt_old, prob.prm.dt_oldold = 1.0, 0.5
+    rng = np.random.default_rng(8)
+    nn = prob.n_nodes
+    sol = np.zeros((nn, 3)); sol[:, :2] = 1e-3 * rng.standard_normal((nn, 2)); sol[:, 2] = rng.random(nn)
+    old = sol.copy(); old[:, 2] = rng.random(nn)
+    oo = old.copy(); oo[:, 2] += 0.5 * (rng.random(nn) - 0.5)
+    sol, old, oo = sol.reshape(-1), old.reshape(-1), oo.reshape(-1)
+    run = oracle.MieheRun("miehe shear", 2, 5e-4, lam, mu, 1e3)
+    con = run.dirichlet.reshape(nn, 3).copy(); con[rng.random(nn) < 0.2, 2] = 1
+    con = np.ascontiguousarray(con.reshape(-1))
+    x = rng.standard_normal(nn * 3)
+    pt = np.ascontiguousarray(oo.reshape(nn, 3)[:, 2] + 3.0 * (old.reshape(nn, 3)[:, 2] - oo.reshape(nn, 3)[:, 2]))
+    mask = np.zeros(nn, dtype=np.uint8)
+    for c in range(3):
+        mask |= (con.reshape(nn, 3)[:, c].astype(np.uint8) << c)
+    phys = np.array([lam, mu, 2.7, prob.prm.kappa, prob.prm.eps, 0.0, 1.0, float(split), 1.0, 1.0])
+    out = {k: np.zeros(nn * 3) for k in ("r", "diag", "y")}
+    mass = np.zeros(nn)
+    emu.emu_box2d((C.c_int * 2)(n, n), (C.c_double * 2)(1.0 / n, 1.0 / n), C.c_int(1), _ptr(phys), _ptr(sol), _ptr(pt),
+                  _ptr(mask), _ptr(x), _ptr(out["r"]), _ptr(out["diag"]), _ptr(out["y"]), _ptr(mass))
+    rel = lambda a, b: np.max(np.abs(a - b)) / np.max(np.abs(b))
+    _, r_tot_ref = prob.residual(sol, old, oo, con)
+    assert rel(out["r"], r_tot_ref) <= (1e-12 if not split else 1e-11)
+    y_ref = prob.apply_jacobian(sol, old, oo, con, x)
+    assert rel(out["y"], y_ref) <= (1e-12 if not split else 1e-10)    # constrained rows: the same deal.II-style diagonal
+    assert rel(out["diag"], np.abs(prob.jacobian(sol, old, oo, None).diagonal())) <= (1e-12 if not split else 1e-10)
+    assert rel(mass, prob.lumped_mass()) <= 1e-14
