@@ -190,9 +190,12 @@ int pf_apply_jacobian_dev (pf_ctx *ctx, double *x_dev, double *y_dev);
 /* Preconditioner of pf_solve, the stand-in for the two ML AMG hierarchies of
  * cracks.cc:2477-2497: kind 0 = Jacobi, kind 1 = matrix-free geometric
  * multigrid V-cycle on the 10*2^l mesh family with Chebyshev-Jacobi smoothing
- * of the given degree and smoothing range (default 1, 2, 20; kind 2 = same with the exact 27-point operator in the smoother; dim 3 and one
- * rank only, otherwise Jacobi is used).  Takes effect at the next
- * pf_setup_jacobian. */
+ * of the given degree and smoothing range (default 1, 2, 20; kind 2 = same with
+ * the exact 27-point operator in the smoother).  Dim 3 box meshes, any number of
+ * ranks: a level keeps the z-slab decomposition while the slabs stay aligned with
+ * the coarse cells and is replicated on every rank below that (pf_mg_hierarchy
+ * describes the levels).  2-D and forest meshes use Jacobi.  Takes effect at the
+ * next pf_setup_jacobian. */
 int pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio);
 /* Restart length of GMRES (deal.II's SolverGMRES default keeps 28 basis vectors,
  * cracks.cc:2764; this library's default is 30).  Ill-conditioned small 2-D
