@@ -109,6 +109,8 @@ _SIGS = {
     "pf_interpolate_unbroken": [C.c_void_p],
     "pf_load": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "pf_phase_field_min": [C.c_void_p, C.POINTER(C.c_double)],
+    "pf_set_dirichlet_values": [C.c_void_p, C.c_void_p],
+    "pf_load_cells": [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "pf_advance_timestep": [C.c_void_p],
     "pf_set_time_parameters": [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_double],
     "pf_timestep_difference": [C.c_void_p, C.POINTER(C.c_double)],
@@ -407,6 +409,15 @@ class PhaseFieldContext:
     def load(self):
         lx, ly = C.c_double(), C.c_double()
         self._check(self.lib.pf_load(self.h, C.byref(lx), C.byref(ly)))
+        return lx.value, ly.value
+
+    def set_dirichlet_values(self, values_block: np.ndarray):
+        self._check(self.lib.pf_set_dirichlet_values(self.h, _ptr(np.ascontiguousarray(values_block, dtype=np.float64))))
+
+    def load_cells(self, cells: np.ndarray):
+        cells = np.ascontiguousarray(cells, dtype=np.int64)
+        lx, ly = C.c_double(), C.c_double()
+        self._check(self.lib.pf_load_cells(self.h, _ptr(cells), cells.shape[0], C.byref(lx), C.byref(ly)))
         return lx.value, ly.value
 
     def phase_field_min(self) -> float:

@@ -162,7 +162,7 @@ struct pf_ctx
   long long *hang = nullptr;          // [n_hanging][5]: node, parents (-1 = unused)
   long long *conn_dev = nullptr;
   unsigned char *level_dev = nullptr;
-  double *lame_dev = nullptr, *lame_energy_dev = nullptr;
+  double *lame_dev = nullptr, *lame_energy_dev = nullptr, *level_h_dev = nullptr;
   double *fx = nullptr;               // distributed copy of the input vector of an apply
   uint8_t *zero_mask = nullptr;       // "nothing constrained", for the hanging-node-only constraint set
   double last_rnorm = 0;
@@ -1743,6 +1743,8 @@ create_forest_impl (const pf_forest_mesh *fm, const pf_params *params, int devic
       CU (cudaMalloc (&ctx->lame_energy_dev, ncell * 2 * sizeof (double)));
       CU (cudaMemcpy (ctx->lame_energy_dev, le, ncell * 2 * sizeof (double), cudaMemcpyHostToDevice));
     }
+  CU (cudaMalloc (&ctx->level_h_dev, (size_t) fm->n_levels * dim * sizeof (double)));
+  CU (cudaMemcpy (ctx->level_h_dev, fm->level_h, (size_t) fm->n_levels * dim * sizeof (double), cudaMemcpyHostToDevice));
   g.conn = ctx->conn_dev;
   g.cell_level = ctx->level_dev;
   g.cell_lame = ctx->lame_dev;
@@ -1807,7 +1809,7 @@ pf_destroy (pf_ctx *ctx)
                   ctx->r_pde, ctx->dx,   ctx->stage,  ctx->xa,     ctx->ya,    ctx->zvec, ctx->mask,
                   ctx->saved, ctx->aux, ctx->tile_counter, ctx->stage8, ctx->cycle, ctx->fetab, ctx->red,   ctx->hdev,  ctx->partial, ctx->counts,
                   ctx->V, ctx->hang, ctx->conn_dev, ctx->level_dev, ctx->lame_dev, ctx->lame_energy_dev, ctx->fx,
-                  ctx->zero_mask};
+                  ctx->zero_mask, ctx->level_h_dev};
   for (void *p : ptrs)
     if (p)
       cudaFree (p);
@@ -2532,6 +2534,59 @@ pf_load (pf_ctx *ctx, double *load_x, double *load_y)
   CU (cudaMemsetAsync (ctx->red, 0, 2 * sizeof (double), ctx->stream));
   k_load_top_2d<<<nblk (ctx->g.n[0], 128), 128, 0, ctx->stream>>> (ctx->g, ctx->p, ctx->sol, ctx->red);
   KCHECK ();
+  CU (cudaMemcpyAsync (ctx->h_red, ctx->red, 2 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  if (load_x)
+    *load_x = -1.0 * ctx->h_red[0]; // load_value[0] *= -1.0, cracks.cc:3789
+  if (load_y)
+    *load_y = ctx->h_red[1];
+  return PF_OK;
+}
+
+int
+pf_set_dirichlet_values (pf_ctx *ctx, const double *values)
+{
+  if (!ctx || !values)
+    return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
+  int rc = upload_block (ctx, values, ctx->xa);
+  if (rc)
+    return rc;
+  const long long nl = ctx->g.n_local_nodes;
+  if (ctx->dim == 2)
+    k_set_dirichlet_values<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, ctx->xa, ctx->sol);
+  else
+    k_set_dirichlet_values<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, ctx->xa, ctx->sol);
+  KCHECK ();
+  if ((rc = hanging_distribute (ctx, ctx->sol, 0)))
+    return rc;
+  ctx->jac_ready = false;
+  ctx->have_r = false;
+  return PF_OK;
+}
+
+int
+pf_load_cells (pf_ctx *ctx, const int64_t *cells, int64_t n_cells, double *load_x, double *load_y)
+{
+  if (!ctx || !cells || n_cells < 0)
+    return PF_BAD_ARG;
+  if (!ctx->forest || ctx->dim != 2)
+    return fail (ctx, PF_UNSUPPORTED, "pf_load_cells: 2-D forest meshes (use pf_load on the box / slit mesh)");
+  CU (cudaSetDevice (ctx->device));
+  for (int64_t i = 0; i < n_cells; ++i)
+    if (cells[i] < 0 || cells[i] >= ctx->g.n_local_cells)
+      return fail (ctx, PF_BAD_ARG, "pf_load_cells: cell index out of range");
+  CU (cudaMemsetAsync (ctx->red, 0, 2 * sizeof (double), ctx->stream));
+  if (n_cells > 0)
+    {
+      // the list is small (the cells along one edge): staged through the byte staging buffer
+      if ((size_t) n_cells * sizeof (long long) > (size_t) ctx->n_local_dofs)
+        return fail (ctx, PF_BAD_ARG, "pf_load_cells: list longer than the staging buffer");
+      CU (cudaMemcpyAsync (ctx->stage8, cells, (size_t) n_cells * sizeof (long long), cudaMemcpyHostToDevice, ctx->stream));
+      k_load_top_forest<<<nblk (n_cells, 128), 128, 0, ctx->stream>>> (ctx->g, ctx->p, ctx->level_h_dev, n_cells,
+                                                                       (const long long *) ctx->stage8, ctx->sol, ctx->red);
+      KCHECK ();
+    }
   CU (cudaMemcpyAsync (ctx->h_red, ctx->red, 2 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
   CU (cudaStreamSynchronize (ctx->stream));
   if (load_x)

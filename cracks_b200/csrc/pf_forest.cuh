@@ -114,4 +114,65 @@ k_lumped_mass_forest (Grid g, const FeTab<DIM> *__restrict__ tab, double *__rest
     atomicAdd (&mass[g.conn[lc * (1 << DIM) + v]], vol / (1 << DIM));
 }
 
+// set_initial_bc(): constraints.distribute(solution) for inhomogeneous Dirichlet data (cracks.cc:2700-2707):
+// sol = vals on the displacement dofs whose Dirichlet bit is set
+template <int DIM>
+__global__ void
+k_set_dirichlet_values (long long n_nodes, const uint8_t *__restrict__ mask, const double *__restrict__ vals,
+                        double *__restrict__ sol)
+{
+  const long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes)
+    return;
+  const uint8_t m = mask[n];
+  for (int c = 0; c < DIM; ++c)
+    if ((m >> c) & 1)
+      sol[n * (DIM + 1) + c] = vals[n * (DIM + 1) + c];
+}
+
+// compute_load() (cracks.cc:3728-3816) on a forest: the listed cells have their top edge (vertices 2, 3)
+// on boundary id 3; int sigma(u) n ds with n = (0, 1), QGauss<1>(3), undegraded stress.
+// out2 += (integral of sigma_xy, integral of sigma_yy); one thread per listed cell, atomics.
+__global__ void __launch_bounds__ (128)
+k_load_top_forest (Grid g, Phys p_in, const double *__restrict__ level_h, long long n_list,
+                   const long long *__restrict__ list, const double *__restrict__ sol, double *__restrict__ out2)
+{
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_list)
+    return;
+  const long long lc = list[t];
+  Phys p = p_in;
+  if (g.cell_lame)
+    {
+      p.lambda = g.cell_lame[2 * lc];
+      p.mu = g.cell_lame[2 * lc + 1];
+    }
+  const double hx = level_h[2 * g.cell_level[lc]], hy = level_h[2 * g.cell_level[lc] + 1];
+  const double gq = 0.5 * sqrt (3.0 / 5.0);
+  const double xi[3] = {0.5 - gq, 0.5, 0.5 + gq};
+  const double wq[3] = {5.0 / 18.0, 8.0 / 18.0, 5.0 / 18.0};
+  double lx = 0, ly = 0;
+  for (int q = 0; q < 3; ++q)
+    {
+      double gu[2][2] = {{0, 0}, {0, 0}};
+      for (int v = 0; v < 4; ++v)
+        {
+          const int bx = v & 1, by = (v >> 1) & 1;
+          const double Nx = bx ? xi[q] : 1.0 - xi[q], Ny = by ? 1.0 : 0.0; // on the edge eta = 1
+          const double gx = (bx ? 1.0 : -1.0) / hx * Ny, gy = Nx * (by ? 1.0 : -1.0) / hy;
+          const long long n = g.conn[lc * 4 + v];
+          for (int c = 0; c < 2; ++c)
+            {
+              gu[c][0] += gx * sol[n * 3 + c];
+              gu[c][1] += gy * sol[n * 3 + c];
+            }
+        }
+      const double tr = gu[0][0] + gu[1][1];
+      lx += p.mu * (gu[0][1] + gu[1][0]) * hx * wq[q];
+      ly += (p.lambda * tr + 2.0 * p.mu * gu[1][1]) * hx * wq[q];
+    }
+  atomicAdd (&out2[0], lx);
+  atomicAdd (&out2[1], ly);
+}
+
 } // namespace pf

@@ -216,3 +216,121 @@ class ForestSneddonDriver(api.SneddonDriver):
             if step_no > self.max_steps:
                 break
         return self.statistics
+
+
+class ForestMieheDriver(api.SneddonDriver):
+    """run() for `test case = miehe tension / miehe shear` WITH the predictor-corrector refinement
+    (`ref strategy = phase field`, cracks.cc:4166-4581, 3971-3995, 4108-4159, 4419-4431) on a HostForest:
+    after every converged step the cells holding a phase-field dof below the threshold are refined (level
+    cap, 2:1 balance), solution / old / old_old are interpolated to the new forest, a new device context
+    is built and the step is redone.  EXPERIMENTAL like the rest of the forest device path."""
+
+    def __init__(self, test, refine, params_of_h, E, timestep, max_no_timesteps, cycles=1, timestep_2=None,
+                 switch_timestep=0, d_rhs=0.0, d_mat=0.0, refine_threshold=0.8, device=0, krylov_dim=300, **kw):
+        self.kind = {"miehe tension": 1, "miehe shear": 2}[test]
+        self.forest = HostForest(2, (2, 2), (0.0, 0.0), (1.0, 1.0), slit=True)
+        self.forest.refine_global(refine)
+        self.level_cap = refine + cycles
+        self.h_final = api.miehe_final_h(refine, cycles)
+        self.params = params_of_h(self.h_final)                  # api.Params with K reg / Eps reg at the final h
+        self.device, self.krylov_dim = device, krylov_dim
+        self.dt2, self.switch = timestep_2, switch_timestep
+        self.d_rhs, self.d_mat, self.threshold = d_rhs, d_mat, refine_threshold
+        self.redone = []
+        super().__init__(self._new_context(), E=E, timestep=timestep, max_no_timesteps=max_no_timesteps, **kw)
+
+    def _new_context(self):
+        """setup_system() on the current forest: tables -> device, Dirichlet rows of set_newton_bc (2584-2625)"""
+        f = self.forest
+        ctx = ForestContext(f, self.params, device=self.device)
+        ctx.set_krylov_dim(self.krylov_dim)
+        t = ctx.tables
+        x, y = t["coords"][:, 0], t["coords"][:, 1]
+        top, bottom, left, right = y == 1.0, y == 0.0, x == 0.0, x == 1.0
+        m = np.zeros((ctx.n_nodes, 3), dtype=np.uint8)
+        if self.kind == 1:
+            m[bottom, 1] = 1
+            m[top, 0] = m[top, 1] = 1
+        else:
+            m[left, 1] = m[right, 1] = 1
+            m[bottom, 0] = m[bottom, 1] = 1
+            m[top, 0] = m[top, 1] = 1
+            m[(y == 0.5) & (x >= 0.5) & (t["upper_copy"] == 0), 1] = 1      # boundary id 4: lower face of the slit
+        self._top_nodes = np.where(top)[0]
+        self._top_cells = np.where(t["coords"][t["conn"][:, 2], 1] == 1.0)[0].astype(np.int64)
+        none = np.zeros(ctx.n_dofs, dtype=np.uint8)
+        ctx.set_constraints(ctx.to_block(m.reshape(-1)).astype(np.uint8), none)
+        return ctx
+
+    def _bc_values(self, time):
+        v = np.zeros((self.ctx.n_nodes, 3))
+        if self.kind == 1:
+            v[self._top_nodes, 1] = time                              # BoundaryTensionTest
+        else:
+            v[self._top_nodes, 0] = -time                             # BoundaryShearTest
+        return self.ctx.to_block(v.reshape(-1))
+
+    def _refine_mesh(self):
+        """-> True if the mesh changed; the three vectors are carried over (SolutionTransfer)"""
+        c = self.ctx
+        t = c.tables
+        phi = c.to_nodal(c.get_state(0)).reshape(-1, 3)[:, 2]
+        flags = (t["level"] < self.level_cap) & (phi[t["conn"]] < self.threshold).any(axis=1)
+        if not flags.any():
+            return False
+        vecs = [c.to_nodal(c.get_state(w)) for w in (0, 1, 2)]
+        coarse = self.forest
+        self.forest = coarse.clone()
+        self.forest.refine(flags)
+        new = [self.forest.transfer_from(coarse, v, 3) for v in vecs]
+        c.close()
+        self.ctx = c = self._new_context()
+        c.set_state(c.to_block(new[0]), c.to_block(new[1]), c.to_block(new[2]), self._dt_old, self._dt_oldold, False, 0.0)
+        return True
+
+    def run(self):
+        c = self.ctx
+        sol = np.zeros((c.n_nodes, 3))
+        sol[:, 2] = 1.0                                               # InitialValuesTensionOrShear
+        blk = c.to_block(sol.reshape(-1))
+        c.set_state(blk, blk, blk, self.dt, self.dt, False, 0.0)
+        dt = self.dt
+        self._dt_old = self._dt_oldold = dt
+        time, step_no = 0.0, 0
+        while step_no <= self.max_steps:
+            if self.switch > 0 and step_no > self.switch:
+                dt = self.dt2
+            tmp_dt = dt
+            self._dt_oldold, self._dt_old = self._dt_old, dt
+            self.ctx.advance_timestep()
+            while True:                                               # redo_step
+                c = self.ctx
+                c.set_time_parameters(self._dt_old, self._dt_oldold, False, 0.0)
+                c.set_stress_split(self.d_mat > 0 and step_no > 0, self.d_rhs, self.d_mat)
+                time += dt
+                while True:
+                    try:
+                        c.set_dirichlet_values(self._bc_values(time))   # set_initial_bc(time)
+                        self.newton_active_set()
+                        break
+                    except api.NoConvergence:
+                        c._check(c.lib.pf_restore_old_solution(c.h))
+                        time -= dt
+                        dt /= 10.0
+                        time += dt
+                        if dt < 1e-6 * tmp_dt:
+                            raise
+                c.project_phase_field()
+                if not self._refine_mesh():
+                    break
+                self.redone.append(step_no)                           # "MESH CHANGED!": redo the step from old_solution
+                time -= dt
+                self.ctx._check(self.ctx.lib.pf_restore_old_solution(self.ctx.h))
+            dt = tmp_dt
+            c = self.ctx
+            bulk, crack = c.energy()
+            lx, ly = c.load_cells(self._top_cells)
+            self.statistics.append(dict(step=step_no, time=time, dofs=c.n_dofs, bulk=bulk, crack=crack,
+                                        load=ly if self.kind == 1 else lx))
+            step_no += 1
+        return self.statistics

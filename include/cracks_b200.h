@@ -253,6 +253,12 @@ int pf_interpolate_unbroken (pf_ctx *ctx);
 /* compute_load(), cracks.cc:3728-3816: traction integral over boundary id 3
  * (top edge), undegraded stress, load_x already multiplied by -1 (3789). */
 int pf_load (pf_ctx *ctx, double *load_x, double *load_y);
+/* set_initial_bc() for arbitrary Dirichlet data (cracks.cc:2700-2707): writes values[dof] (host, block
+ * layout) into the solution on every displacement dof whose Dirichlet bit is set (pf_set_constraints). */
+int pf_set_dirichlet_values (pf_ctx *ctx, const double *values);
+/* compute_load() on a forest mesh (EXPERIMENTAL, see pf_create_forest): `cells` lists the cells whose top
+ * edge lies on boundary id 3. */
+int pf_load_cells (pf_ctx *ctx, const int64_t *cells, int64_t n_cells, double *load_x, double *load_y);
 /* min over the owned phase-field dofs: the indicator refine_mesh() tests
  * against "value phase field for refinement" (cracks.cc:3971-3995).  [collective] */
 int pf_phase_field_min (pf_ctx *ctx, double *phi_min);

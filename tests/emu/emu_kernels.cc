@@ -215,6 +215,31 @@ emu_box2d (const int *n, const double *h, int slit, const double *phys /* lambda
   launch (k_apply_generic<2>, g.n_local_cells, 128, g, p, (const FeTab<2> *) &tab, x, sol, pt, mask, y);
 }
 
+// compute_load on a 2-D forest (k_load_top_forest) and the Dirichlet-value kernel
+void
+emu_load_forest (long long n_cells, long long n_nodes, const long long *conn, const unsigned char *level,
+                 const double *level_h, double lambda, double mu, long long n_list, const long long *list,
+                 const double *sol, double *out2)
+{
+  EmuForest f{2, n_cells, n_nodes, 0, conn, level, 0, level_h, nullptr, nullptr};
+  Grid g = make_grid<2> (f);
+  Phys p;
+  std::memset (&p, 0, sizeof p);
+  p.lambda = lambda;
+  p.mu = mu;
+  out2[0] = out2[1] = 0.0;
+  launch (k_load_top_forest, n_list, 128, g, p, level_h, n_list, list, sol, out2);
+}
+
+void
+emu_set_dirichlet_values (int dim, long long n_nodes, const unsigned char *mask, const double *vals, double *sol)
+{
+  if (dim == 2)
+    launch (k_set_dirichlet_values<2>, n_nodes, 256, n_nodes, mask, vals, sol);
+  else
+    launch (k_set_dirichlet_values<3>, n_nodes, 256, n_nodes, mask, vals, sol);
+}
+
 // active-set kernel on a forest: returns counts {active, cycling, changed}
 void
 emu_active_set (int dim, long long n_nodes, double c_scale, const double *r_total, const double *mass, const double *old,

@@ -124,3 +124,49 @@ def test_kat2_through_the_cli(pf, tmp_path):
         assert int(row[2]) == 453
         assert float(row[5]) == pytest.approx(ref["crack"], rel=1e-8)
         assert float(row[4]) == pytest.approx(ref["bulk"], rel=1e-6)
+
+
+def _miehe_forest_driver(pf, g, max_steps=None):
+    from cracks_b200.forest import ForestMieheDriver
+    p = g["prm"]
+    num = lambda k: float(p[k])
+    fh = lambda expr: (lambda h: eval(expr, {"h": h, "pow": pow}))
+    params_of_h = lambda h: pf.Params(num("Lame lambda"), num("Lame mu"), num("Fracture toughness G_c"), fh(p["K reg"])(h),
+                                      fh(p["Eps reg"])(h), 0.0)
+    return ForestMieheDriver(p["test case"], int(p["Global pre-refinement steps"]), params_of_h, E=num("E modulus"),
+                             timestep=num("Timestep size"),
+                             max_no_timesteps=int(p["Max No of timesteps"]) if max_steps is None else max_steps,
+                             cycles=int(p["Adaptive refinement cycles"]), timestep_2=num("Timestep size to switch to"),
+                             switch_timestep=int(p["Switch timestep after steps"]),
+                             d_rhs=float(p.get("Decompose stress in rhs", 0.0)), d_mat=float(p.get("Decompose stress in matrix", 0.0)),
+                             refine_threshold=num("value phase field for refinement"),
+                             newton_lower_bound=num("Newton lower bound"), max_newton=int(p["Newton maximum steps"]),
+                             max_line_search=int(p["Line search maximum steps"]), line_search_damping=num("Line search damping"),
+                             gmres_max_it=3000)
+
+
+def test_miehe_shear_1_adaptive_on_the_gpu(pf):
+    """BASELINE config 4 in small: stress split + predictor-corrector refinement, tests/miehe_shear_1.statistics"""
+    g = json.load(open(os.path.join(HERE, "golden", "miehe_shear_1.json")))
+    drv = _miehe_forest_driver(pf, g)
+    stats = drv.run()
+    assert [r["dofs"] for r in stats] == [r["dofs"] for r in g["statistics"]]
+    for got, ref in zip(stats, g["statistics"]):
+        tol = 1e-6 if got["step"] <= 9 else 1e-4
+        for k in ("bulk", "crack", "load"):
+            assert got[k] == pytest.approx(ref[k], rel=tol), (got["step"], k)
+    drv.ctx.close()
+
+
+def test_miehe_tension_adaptive_on_the_gpu(pf):
+    """BASELINE config 2 in small: tests/miehe_tension_adaptive_1.statistics through its adaptive rows (25-31)"""
+    g = json.load(open(os.path.join(HERE, "golden", "miehe_tension_adaptive_1.json")))
+    drv = _miehe_forest_driver(pf, g, max_steps=31)
+    stats = drv.run()
+    assert [r["dofs"] for r in stats] == [r["dofs"] for r in g["statistics"][:32]]
+    for got, ref in zip(stats, g["statistics"]):
+        k = got["step"]
+        tol = 1e-6 if k <= 21 else 1e-3 if k <= 26 else 1e-2
+        for key in ("crack", "load"):
+            assert got[key] == pytest.approx(ref[key], rel=tol), (k, key)
+    drv.ctx.close()

@@ -263,3 +263,38 @@ def test_generic_2d_kernel_sources_on_the_slit_mesh(oracle, emu, split):
     assert rel(out["y"], y_ref) <= (1e-12 if not split else 1e-10)    # constrained rows: the same deal.II-style diagonal
     assert rel(out["diag"], np.abs(prob.jacobian(sol, old, oo, None).diagonal())) <= (1e-12 if not split else 1e-10)
     assert rel(mass, prob.lumped_mass()) <= 1e-14
+
+
+def test_forest_load_and_dirichlet_value_kernels(emu, ao):
+    """k_load_top_forest / k_set_dirichlet_values (Miehe tests on a refined slit forest) vs the adaptive oracle"""
+    lam, mu = 121.15e3, 80.77e3
+    run = ao.AdaptiveMieheRun("miehe shear", 2, 1e-3, lam, mu, 1e3, cycles=1)
+    # refine the cells right of the crack tip once so that the top edge and the mesh carry several levels
+    flagged = [c for c in run.forest.order if run.forest.cell_box(c)[0] >= 0.5]
+    run.forest = run.forest.copy(); run.forest.refine(flagged); run._setup_system()
+    p = run.p
+    rng = np.random.default_rng(6)
+    sol = np.ascontiguousarray(p.distribute_hanging(rng.standard_normal(p.n_dofs)))
+    level_h, inv = np.unique(np.round(p.cell_h, 12), axis=0, return_inverse=True)
+    level = np.ascontiguousarray(inv.reshape(-1).astype(np.uint8))
+    top = np.ascontiguousarray(np.where(p.xy[p.cells[:, 2], 1] == 1.0)[0].astype(np.int64))
+    assert len(set(p.cell_h[top, 0])) == 2                                   # two cell sizes along the top edge
+    out = np.zeros(2)
+    cells = np.ascontiguousarray(p.cells)
+    emu.emu_load_forest(C.c_longlong(p.n_cells), C.c_longlong(p.n_nodes), _ptr(cells), _ptr(level),
+                        _ptr(np.ascontiguousarray(level_h)), C.c_double(lam), C.c_double(mu), C.c_longlong(top.shape[0]),
+                        _ptr(top), _ptr(sol), _ptr(out))
+    lx_ref, ly_ref = run.load(sol)
+    assert -out[0] == pytest.approx(lx_ref, rel=1e-12) and out[1] == pytest.approx(ly_ref, rel=1e-12)
+    # set_initial_bc(time)
+    run._time = 0.0125
+    ref = sol.copy()
+    run.set_initial_bc(ref)
+    vals = np.zeros((p.n_nodes, 3)); vals[run._top, 0] = -0.0125
+    mask = np.zeros(p.n_nodes, dtype=np.uint8)
+    for c in range(3):
+        mask |= (p.dirichlet.reshape(-1, 3)[:, c].astype(np.uint8) << c)
+    got = sol.copy()
+    emu.emu_set_dirichlet_values(C.c_int(2), C.c_longlong(p.n_nodes), _ptr(mask), _ptr(np.ascontiguousarray(vals.reshape(-1))),
+                                 _ptr(got))
+    assert np.array_equal(got, ref)
