@@ -1,0 +1,27 @@
+"""Runs the opt-in suite of the forest / hanging-node device path (tests/test_gpu_forest_experimental.py) in a
+SUBPROCESS, last in the GPU suite, and does not gate on it: that path was written after the round's GPU
+budget was spent; its kernel sources and the library plumbing pass on the CPU emulation
+(tests/test_emulated_library_cpu.py) but it has not met a real GPU yet.  Isolation keeps a device fault or
+a hang (600 s cap) from touching the gating tests; the outcome is printed either way and reported as
+passed / xfailed."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_forest_device_path_first_gpu_run(pf):
+    env = dict(os.environ, PF_EXPERIMENTAL="1")
+    try:
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_forest_experimental.py"),
+                            "-q", "-rA", "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        out, rc = r.stdout[-4000:] + r.stderr[-1500:], r.returncode
+    except subprocess.TimeoutExpired as exc:
+        out, rc = "TIMEOUT after 600 s\n" + str(exc.stdout)[-2000:], -1
+    print(out)
+    if rc != 0:
+        pytest.xfail("forest device path failed on its first GPU run (non-gating, see the captured output)")
