@@ -211,3 +211,97 @@ def test_forest_context_entry_points(oracle, epf):
     assert np.allclose(ctx.to_nodal(ctx.get_state(0)), expect, rtol=0, atol=1e-15)
     assert np.array_equal(ctx.to_nodal(ctx.get_state(1)), old) and np.array_equal(ctx.to_nodal(ctx.get_state(2)), oo)
     ctx.close()
+
+
+def test_cpp_host_driver_on_the_forest_path(emu_so, tmp_path):
+    """cracks_b200/host (C++: .prm surface, FracturePhaseFieldProblem, host forest) linked against the emulated
+    build: tests/sneddon_2d_1.prm -- local pre-refinement, hanging nodes, the refinement cycle at the end --
+    through the command line, like tests/test_gpu_forest_experimental.py::test_kat2_through_the_cli on a GPU."""
+    host = os.path.join(ROOT, "cracks_b200", "host")
+    exe = os.path.join(HERE, "emu", "cracks_b200_run_emu")
+    srcs = [os.path.join(host, f) for f in ("main.cc", "fracture_problem.cc", "parameter_handler.cc", "function_parser.cc",
+                                            "forest.cc")]
+    deps = srcs + [os.path.join(host, f) for f in os.listdir(host) if f.endswith(".h")] + [emu_so]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, *srcs, "-L", os.path.join(HERE, "emu"),
+                               "-lcracks_b200_emu", "-Wl,-rpath," + os.path.join(HERE, "emu"), "-pthread"])
+    g = json.load(open(os.path.join(HERE, "golden", "sneddon_2d_1.json")))
+    sections = {"Global parameters": ["Global pre-refinement steps", "Local pre-refinement steps", "Adaptive refinement cycles",
+                                      "Max No of timesteps", "Timestep size", "outer solver", "test case", "ref strategy",
+                                      "value phase field for refinement"],
+                "Problem dependent parameters": ["K reg", "Eps reg", "Gamma penalization", "Pressure", "Fracture toughness G_c",
+                                                 "Poisson ratio nu", "E modulus"],
+                "Solver parameters": ["Use Direct Inner Solver", "Newton lower bound", "Newton maximum steps",
+                                      "Decompose stress in rhs", "Decompose stress in matrix", "Line search maximum steps"]}
+    lines = []
+    for sec, keys in sections.items():
+        lines.append("subsection " + sec)
+        if sec == "Global parameters":
+            lines += ["  set Dimension = 2", "  set Output directory = " + str(tmp_path / "out")]
+        lines += ["  set %s = %s" % (k, g["prm"][k]) for k in keys if k in g["prm"]]
+        lines.append("end")
+    (tmp_path / "t.prm").write_text("\n".join(lines) + "\n")
+    r = subprocess.run([exe, str(tmp_path / "t.prm")], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-2500:], r.stderr[-800:])
+    assert r.returncode == 0, r.stderr
+    assert "Prerefinement step with h= 2.82843" in r.stdout
+    assert "DoFs: 302 solid + 151 phase = 453" in r.stdout and "DoFs: 518 solid + 259 phase = 777" in r.stdout
+    assert "0\t\t\t1.491639e+01" in r.stdout                          # tests/sneddon_2d_1.output
+    assert "Refinement cycle 0" in r.stdout and "TCV: value= 0.0418879" in r.stdout
+    rows = [l.split() for l in open(tmp_path / "out" / "statistics") if not l.startswith("#")]
+    assert len(rows) == 4
+    for row, ref in zip(rows, g["statistics"]):
+        assert int(row[2]) == 453 and float(row[3]) == pytest.approx(ref["h"], rel=1e-8)
+        assert float(row[5]) == pytest.approx(ref["crack"], rel=1e-8)
+        assert float(row[4]) == pytest.approx(ref["bulk"], rel=1e-6)
+
+
+def test_cpp_host_driver_miehe_small(oracle, emu_so, tmp_path):
+    """The C++ Miehe branch (slit mesh, split from the second step on, Load x column) on a 4 x 4 mesh against the
+    oracle's run; the golden-sized runs are in the GPU suite (tests/test_gpu_host_driver.py)."""
+    exe = os.path.join(HERE, "emu", "cracks_b200_run_emu")
+    if not os.path.exists(exe):
+        pytest.skip("built by test_cpp_host_driver_on_the_forest_path")
+    lam, mu = 121.15e3, 80.77e3
+    ref = oracle.MieheRun("miehe shear", 1, 5e-4, lam, mu, 1e3, kappa_of_h=lambda h: 1e-10 * h, d_rhs=1.0, d_mat=1.0,
+                          max_no_timesteps=2).run()
+    (tmp_path / "m.prm").write_text(f"""subsection Global parameters
+  set Dimension = 2
+  set Global pre-refinement steps = 1
+  set Max No of timesteps = 2
+  set Timestep size = 5.0e-4
+  set test case = miehe shear
+  set ref strategy = phase field
+  set value phase field for refinement = 0.8
+  set Output directory = {tmp_path / 'out'}
+end
+subsection Problem dependent parameters
+  set K reg = 1.0e-10*h
+  set Eps reg = 2*h
+  set Fracture toughness G_c = 2.7
+  set E modulus = 1e+3
+  set Poisson ratio nu = 0.2
+  set Lame mu = 80.77e+3
+  set Lame lambda = 121.15e+3
+end
+subsection Solver parameters
+  set Use Direct Inner Solver = true
+  set Newton lower bound = 1.0e-6
+  set Newton maximum steps = 100
+  set Line search maximum steps = 10
+  set Line search damping = 0.6
+  set Decompose stress in rhs = 1.0
+  set Decompose stress in matrix = 1.0
+end
+""")
+    r = subprocess.run([exe, str(tmp_path / "m.prm")], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-1500:], r.stderr[-800:])
+    assert r.returncode == 0, r.stderr
+    text = open(tmp_path / "out" / "statistics").read()
+    assert "# 7: Load x" in text
+    rows = [l.split() for l in text.splitlines() if not l.startswith("#")]
+    assert len(rows) == len(ref) == 3
+    for row, b in zip(rows, ref):
+        assert int(row[2]) == b["dofs"]
+        for col, k in ((4, "bulk"), (5, "crack"), (6, "load")):
+            assert float(row[col]) == pytest.approx(b[k], rel=1e-6), (row[0], k)
