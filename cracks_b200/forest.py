@@ -334,3 +334,73 @@ class ForestMieheDriver(api.SneddonDriver):
                                         load=ly if self.kind == 1 else lx))
             step_no += 1
         return self.statistics
+
+
+def initial_multiple_het_3d(xyz: np.ndarray, width: float) -> np.ndarray:
+    """InitialValuesMultipleHet<3> for the phase-field component (cracks.cc:595-610): two plate-shaped cracks"""
+    x, y, z = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    w = width / 2.0
+    c1 = (x >= 2.6 - w) & (x <= 2.6 + w) & (y >= 3.8 - w) & (y <= 5.5 + w) & (z >= 4.0 - w) & (z <= 4.0 + w)
+    c2 = (x >= 5.5 - w) & (x <= 7.0 + w) & (y >= 4.0 - w) & (y <= 4.0 + w) & (z >= 6.0 - w) & (z <= 6.0 + w)
+    return np.where(c1 | c2, 0.0, 1.0)
+
+
+class ForestHeteroDriver(api.SneddonDriver):
+    """run() for `test case = multiple het`, dim 3 (BASELINE config 5; cracks.cc:4166-4581): the single-tree cube
+    [0,10]^3 of meshes/unit_cube_10.inp, global refinement, local pre-refinement with `ref strategy = phase field`
+    on the interpolated initial cracks, Lame coefficients per cell from an E-modulus field (the reference's
+    BitmapFunction; `e_modulus_of_cells(centres) -> E`), `E + 1` in the assembly but not in compute_energy
+    (2209-2210 vs 3651), pressure as a function of time.  EXPERIMENTAL like the rest of the forest device path."""
+
+    def __init__(self, e_modulus_of_cells, global_refine=3, local_pre_refine=1, nu=0.2, G_c=1.0, pressure=lambda t: 1e3 * t,
+                 kappa_of_h=lambda h: 0.0, eps_of_h=lambda h: 1.5, E_active_set=1e4, refine_threshold=0.4, timestep=0.01,
+                 max_no_timesteps=1, device=0, krylov_dim=300, **kw):
+        f = HostForest(3, (1, 1, 1), (0.0,) * 3, (10.0,) * 3)
+        f.refine_global(global_refine)
+        cap = global_refine + local_pre_refine
+        self.prerefinement = []
+        for _ in range(local_pre_refine):
+            t = f.tables()
+            self.prerefinement.append((f.min_cell_diameter, int(f.n_nodes) * 4))
+            phi = initial_multiple_het_3d(t["coords"], f.min_cell_diameter)
+            f.refine((t["level"] < cap) & (phi[t["conn"]] < refine_threshold).any(axis=1))
+        self.forest = f
+        t = f.tables()
+        h = f.min_cell_diameter
+        centres = t["coords"][t["conn"]].mean(axis=1)
+        E = np.asarray(e_modulus_of_cells(centres), dtype=np.float64)
+
+        def lame(Ev):
+            mu = Ev / (2.0 * (1 + nu))
+            return np.stack([(2 * nu * mu) / (1.0 - 2 * nu), mu], axis=1)
+
+        params = api.Params(1.0, 1.0, G_c, kappa_of_h(h), eps_of_h(h), 0.0)     # lambda, mu come per cell
+        ctx = ForestContext(f, params, device=device, cell_lame=lame(E + 1.0), cell_lame_energy=lame(E))
+        ctx.set_krylov_dim(krylov_dim)
+        xyz = t["coords"]
+        on_b = ((xyz == 0.0) | (xyz == 10.0)).any(axis=1)
+        m = np.zeros((ctx.n_nodes, 4), dtype=np.uint8)
+        m[on_b, :3] = 1                                                        # u = 0 on the six faces, cracks.cc:2686-2694
+        ctx.set_constraints(ctx.to_block(m.reshape(-1)).astype(np.uint8), np.zeros(ctx.n_dofs, dtype=np.uint8))
+        super().__init__(ctx, E=E_active_set, pressure=pressure, timestep=timestep, max_no_timesteps=max_no_timesteps, **kw)
+
+    def run(self):
+        c = self.ctx
+        sol = np.zeros((c.n_nodes, 4))
+        sol[:, 3] = initial_multiple_het_3d(c.tables["coords"], c.forest.min_cell_diameter)
+        blk = c.to_block(sol.reshape(-1))
+        c.set_state(blk, blk, blk, self.dt, self.dt, False, self.pressure(0.0))
+        c.project_phase_field()
+        dt_old = dt_oldold = self.dt
+        time, step_no = 0.0, 0
+        while step_no <= self.max_steps:
+            dt_oldold, dt_old = dt_old, self.dt
+            c.advance_timestep()
+            time += self.dt
+            c.set_time_parameters(dt_old, dt_oldold, False, self.pressure(time))
+            self.newton_active_set()
+            c.project_phase_field()
+            bulk, crack = c.energy()
+            self.statistics.append(dict(step=step_no, time=time, dofs=c.n_dofs, bulk=bulk, crack=crack))
+            step_no += 1
+        return self.statistics

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <vector>
 
+#include "bitmap_function.h"
 #include "forest.h"
 
 using namespace cracks;
@@ -127,6 +128,30 @@ main (int argc, char **argv)
           err = std::fmax (err, std::fabs (v1[(size_t) (i * 2 + c)] - field (&fine.coordinates ()[(size_t) (i * 3)], c)));
       std::printf ("{\"coarse_cells\": %lld, \"fine_cells\": %lld, \"fine_hanging\": %zu, \"max_error\": %.3e}\n",
                    coarse.n_cells (), fine.n_cells (), fine.hanging_nodes ().size (), err);
+    }
+  else if (!std::strcmp (argv[1], "bitmap") && argc > 2)
+    {
+      // E-modulus field of tests/hetero_3d_1.prm at the cell centres of the KAT-5 mesh: argv[2] = PGM file
+      const int n[3] = {1, 1, 1};
+      const double lo[3] = {0, 0, 0}, hi[3] = {10, 10, 10};
+      Forest f (3, n, lo, hi);
+      f.refine_global (3);
+      const double h = f.min_cell_diameter ();
+      std::vector<char> flags ((size_t) f.n_cells (), 0);
+      for (long long c = 0; c < f.n_cells (); ++c)
+        for (int v = 0; v < 8; ++v)
+          if (initial_multiple_het_3d (&f.coordinates ()[(size_t) (f.connectivity ()[(size_t) (c * 8 + v)] * 3)], h) < 0.4)
+            flags[(size_t) c] = 1;
+      f.refine (flags);
+      const BitmapFunction E (argv[2], 0, 10, 0, 10, 1e4, 1e5); // BitmapFunction(filename,0,10,0,10,E,10 E), cracks.cc:1543
+      std::printf ("[");
+      for (long long c = 0; c < f.n_cells (); ++c)
+        {
+          double x[3];
+          f.cell_centre (c, x);
+          std::printf ("%s%.17g", c ? "," : "", E.value (x, 3));
+        }
+      std::printf ("]\n");
     }
   else
     return 2;

@@ -305,3 +305,34 @@ end
         assert int(row[2]) == b["dofs"]
         for col, k in ((4, "bulk"), (5, "crack"), (6, "load")):
             assert float(row[col]) == pytest.approx(b[k], rel=1e-6), (row[0], k)
+
+
+def test_forest_hetero_3d_kat5_end_to_end(epf):
+    """BASELINE config 5 in small through the library (emulated): octree with edge / face hanging nodes from the
+    phase-field pre-refinement, per-cell Lame coefficients (both sets), pressure(time): tests/hetero_3d_1 golden."""
+    pf = epf
+    from cracks_b200.forest import ForestHeteroDriver
+    g = json.load(open(os.path.join(HERE, "golden", "hetero_3d_1.json")))
+    field = {tuple(k): e for k, e in zip(g["cell_keys"], g["e_modulus"])}
+
+    def e_of(centres):
+        # the fixture is keyed by (level, i, j, k); recover the key from the centre and the cell size
+        out = np.empty(centres.shape[0])
+        for n, c in enumerate(centres):
+            for level in (3, 4):
+                h = 10.0 / (1 << level)
+                idx = tuple(int(round(v / h - 0.5)) for v in c)
+                if abs((idx[0] + 0.5) * h - c[0]) < 1e-9 and (level,) + idx in field:
+                    out[n] = field[(level,) + idx]
+                    break
+            else:
+                raise KeyError(c)
+        return out
+
+    drv = ForestHeteroDriver(e_of, newton_lower_bound=1e-6, max_newton=20, max_line_search=8, gmres_max_it=3000)
+    assert drv.prerefinement[0][1] == g["dofs_before_prerefinement"]
+    assert drv.ctx.n_dofs == g["statistics"][0]["dofs"] == 5288
+    for got, ref in zip(drv.run(), g["statistics"]):
+        assert got["crack"] == pytest.approx(ref["crack"], rel=1e-7)
+        assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-6)
+    drv.ctx.close()

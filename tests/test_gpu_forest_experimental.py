@@ -170,3 +170,28 @@ def test_miehe_tension_adaptive_on_the_gpu(pf):
         for key in ("crack", "load"):
             assert got[key] == pytest.approx(ref[key], rel=tol), (k, key)
     drv.ctx.close()
+
+
+def test_hetero_3d_kat5_on_the_gpu(pf):
+    """BASELINE config 5 in small: tests/hetero_3d_1.mpirun-4.statistics on the 3-D forest path"""
+    from cracks_b200.forest import ForestHeteroDriver
+    g = json.load(open(os.path.join(HERE, "golden", "hetero_3d_1.json")))
+    field = {tuple(k): e for k, e in zip(g["cell_keys"], g["e_modulus"])}
+
+    def e_of(centres):
+        out = np.empty(centres.shape[0])
+        for n, c in enumerate(centres):
+            for level in (3, 4):
+                h = 10.0 / (1 << level)
+                idx = tuple(int(round(v / h - 0.5)) for v in c)
+                if abs((idx[0] + 0.5) * h - c[0]) < 1e-9 and (level,) + idx in field:
+                    out[n] = field[(level,) + idx]
+                    break
+        return out
+
+    drv = ForestHeteroDriver(e_of, newton_lower_bound=1e-6, max_newton=20, max_line_search=8, gmres_max_it=3000)
+    assert drv.ctx.n_dofs == 5288
+    for got, ref in zip(drv.run(), g["statistics"]):
+        assert got["crack"] == pytest.approx(ref["crack"], rel=1e-7)
+        assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-6)
+    drv.ctx.close()

@@ -115,3 +115,17 @@ def test_ctypes_mirror_of_the_host_forest(dump, pf):
     xy0, xy1 = t["coords"], finer.tables()["coords"]
     lin = lambda xy: np.stack([1 + 2 * xy[:, 0] - xy[:, 1], 3 - xy[:, 0]], axis=1).reshape(-1)
     assert np.allclose(finer.transfer_from(f, lin(xy0), 2), lin(xy1), rtol=0, atol=1e-13)
+
+
+def test_cpp_bitmap_function_reproduces_the_fixture_field(dump):
+    """cracks_b200/host/bitmap_function.{h,cc} (BitmapFile / BitmapFunction<3> of cracks.cc:118-241 with its
+    quirks) evaluated on the reference's test.pgm at the KAT-5 cell centres equals the field the hetero_3d_1
+    fixture carries (which reproduces the golden).  Needs the reference tree: skipped where it is absent."""
+    pgm = "/root/reference/test.pgm"
+    if not os.path.exists(pgm):
+        pytest.skip("the reference's test.pgm is only present in the build container")
+    exe = os.path.join(ROOT, "cracks_b200", "forest_dump")
+    got = np.array(json.loads(subprocess.check_output([exe, "bitmap", pgm], text=True)))
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "hetero_3d_1.json")))
+    assert got.shape[0] == 932
+    assert np.allclose(got, np.array(g["e_modulus"]), rtol=1e-14, atol=0)
