@@ -3,63 +3,63 @@
 #include <algorithm>
 #include <cmath>
 #include <fstream>
+#include <sstream>
 #include <stdexcept>
 
 namespace cracks {
 
-BitmapFile::BitmapFile (const std::string &name)
+PgmImage::PgmImage (const std::string &path)
 {
-  std::ifstream in (name.c_str ());
+  std::ifstream in (path.c_str ());
   if (!in)
-    throw std::runtime_error ("Can't read from file <" + name + ">!");
-  std::string temp;
-  std::getline (in, temp); // magic number
-  in >> temp;
-  if (!temp.empty () && temp[0] == '#')
-    std::getline (in, temp); // comment line; otherwise the token just read was nx -- not handled by the reference either
-  in >> nx >> ny;
-  if (!(nx > 0 && ny > 0))
-    throw std::runtime_error ("Invalid file format.");
-  image_data.reserve ((size_t) nx * ny);
-  for (int k = 0; k < nx * ny; ++k)
+    throw std::runtime_error ("cannot read the bitmap <" + path + ">");
+  std::string line, token;
+  std::getline (in, line);          // "P2"
+  in >> token;                      // either the creator comment or already the width
+  if (!token.empty () && token[0] == '#')
     {
-      unsigned int val = 0;
-      in >> val; // the first value read is the max-value token of the header, like the reference
-      image_data.push_back (val / 255.0);
+      std::getline (in, line);
+      in >> nx_;
     }
-  hx = 1.0 / (nx - 1);
-  hy = 1.0 / (ny - 1);
+  else
+    nx_ = std::atoi (token.c_str ());
+  in >> ny_;
+  if (nx_ < 2 || ny_ < 2)
+    throw std::runtime_error ("bitmap <" + path + ">: bad header");
+  // nx * ny tokens follow the size; the first of them is the header's max-value (cracks.cc:150-155)
+  grey_.resize ((size_t) nx_ * ny_);
+  for (double &g : grey_)
+    {
+      unsigned v = 0;
+      in >> v;
+      g = v / 255.0;
+    }
 }
 
 double
-BitmapFile::get_pixel_value (int i, int j) const
+PgmImage::sample (double x, double y) const
 {
-  return image_data[(size_t) (nx * (ny - 1 - j) + i)];
+  const double hx = 1.0 / (nx_ - 1), hy = 1.0 / (ny_ - 1);
+  const int i = std::clamp ((int) (x / hx), 0, nx_ - 2);
+  const int j = std::clamp ((int) (y / hy), 0, ny_ - 2);
+  // the reference clamps the in-pixel offsets to min(max(t, 1), 0) = 0: no interpolation takes place
+  const double tx = std::min (std::max ((x - i * hx) / hx, 1.0), 0.0);
+  const double ty = std::min (std::max ((y - j * hy) / hy, 1.0), 0.0);
+  const double bottom = (1 - tx) * pixel (i, j) + tx * pixel (i + 1, j);
+  const double top = (1 - tx) * pixel (i, j + 1) + tx * pixel (i + 1, j + 1);
+  return (1 - ty) * bottom + ty * top;
 }
 
 double
-BitmapFile::get_value (double x, double y) const
+BitmapFunction::value (const double *point, int dim) const
 {
-  const int ix = std::min (std::max ((int) (x / hx), 0), nx - 2);
-  const int iy = std::min (std::max ((int) (y / hy), 0), ny - 2);
-  const double xi = std::min (std::max ((x - ix * hx) / hx, 1.), 0.);
-  const double eta = std::min (std::max ((y - iy * hy) / hy, 1.), 0.);
-  return ((1 - xi) * (1 - eta) * get_pixel_value (ix, iy) + xi * (1 - eta) * get_pixel_value (ix + 1, iy)
-          + (1 - xi) * eta * get_pixel_value (ix, iy + 1) + xi * eta * get_pixel_value (ix + 1, iy + 1));
-}
-
-double
-BitmapFunction::value (const double *p, int dim) const
-{
-  const double x = (p[0] - x1) / (x2 - x1);
-  const double y = (p[1] - y1) / (y2 - y1);
+  const double u = (point[0] - x1_) / (x2_ - x1_), v = (point[1] - y1_) / (y2_ - y1_);
   if (dim == 2)
-    return minvalue + f.get_value (x, y) * (maxvalue - minvalue);
-  const double z = (p[2] - y1) / (y2 - y1);
-  return minvalue
-         + (f.get_value (x / 10.0, (y - z) / 10.0) + 0.5 * f.get_value ((x + y) / 2.0, (z + x) / 2.0)
-            + 0.25 * f.get_value (std::fmod (z + x - y, 10.0), std::fmod (y + x, 10.0)))
-             * (maxvalue - minvalue) / 2.25;
+    return lo_ + image_.sample (u, v) * (hi_ - lo_);
+  const double w = (point[2] - y1_) / (y2_ - y1_);
+  const double mix = image_.sample (u / 10.0, (v - w) / 10.0) + 0.5 * image_.sample ((u + v) / 2.0, (w + u) / 2.0)
+                     + 0.25 * image_.sample (std::fmod (w + u - v, 10.0), std::fmod (v + u, 10.0));
+  return lo_ + mix * (hi_ - lo_) / 2.25;
 }
 
 } // namespace cracks
