@@ -1,0 +1,74 @@
+"""Several ranks of the library WITHOUT GPUs: every rank is a process running the CPU emulation of the library
+(tests/emu/libcracks_b200_emu.so); "NCCL" is tests/emu/fake_nccl (Unix sockets), found by the library's own
+dlopen("libnccl.so.2") through LD_LIBRARY_PATH.  What this exercises is the multi-rank host logic that only a
+multi-GPU box runs otherwise: z-slab layout, halo exchanges, the multigrid hierarchy across ranks (levels that
+keep the decomposition and levels replicated by all-reduce), all-reduced Krylov / active-set decisions.
+The result must not depend on the number of ranks (up to FP reassociation)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+
+
+@pytest.fixture(scope="module")
+def built():
+    sys.path.insert(0, EMU)
+    import build_emulated_library as b
+    so = os.path.join(EMU, "libcracks_b200_emu.so")
+    if not os.path.exists(so):
+        b.build()
+    fake = os.path.join(EMU, "fake_nccl", "libnccl.so.2")
+    src = os.path.join(EMU, "fake_nccl", "fake_nccl.cc")
+    if not os.path.exists(fake) or os.path.getmtime(src) > os.path.getmtime(fake):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", fake, src])
+    return so
+
+
+def _run(nranks, n, steps, tmp_path, timeout):
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(EMU, "fake_nccl") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    tag = "%d_%s" % (nranks, "x".join(map(str, n)))
+    id_file, out_file = str(tmp_path / ("id_" + tag)), str(tmp_path / ("out_" + tag + ".json"))
+    procs = [subprocess.Popen([sys.executable, os.path.join(EMU, "multirank_worker.py"), str(r), str(nranks), id_file, out_file,
+                               *map(str, n), str(steps)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(nranks)]
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=timeout)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-1500:] for o in outs)
+    return json.load(open(out_file))
+
+
+def test_two_ranks_give_the_single_rank_result(built, tmp_path):
+    n = (8, 8, 8)
+    one = _run(1, n, 1, tmp_path, 600)
+    two = _run(2, n, 1, tmp_path, 600)
+    # 8 layers on 2 ranks: the 4 x 4 x 4 level keeps the z-slabs (mode 1, 2 layers per rank)
+    assert [tuple(L[0]) for L in two["levels"]] == [(8, 8, 8), (4, 4, 4)] and two["levels"][0][2] == 1
+    for a, b in zip(two["statistics"], one["statistics"]):
+        assert a["crack"] == pytest.approx(b["crack"], rel=1e-10)
+        assert a["bulk"] == pytest.approx(b["bulk"], rel=1e-7)
+    assert two["newton_its"] == one["newton_its"]
+    assert abs(two["linear_its"] - one["linear_its"]) <= 0.2 * one["linear_its"] + 3
+
+
+@pytest.mark.skipif(os.environ.get("PF_SLOW_TESTS") != "1", reason="8 emulated ranks take several minutes: PF_SLOW_TESTS=1")
+def test_eight_ranks_distributed_and_replicated_levels(built, tmp_path):
+    n = (16, 16, 32)
+    one = _run(1, n, 1, tmp_path, 3000)
+    eight = _run(8, n, 1, tmp_path, 3000)
+    # 32 layers on 8 ranks: 8 x 8 x 16 keeps the slabs (2 layers per rank), 4 x 4 x 8 is replicated
+    assert [(tuple(L[0]), L[1]) for L in eight["levels"]] == [((16, 16, 32), False), ((8, 8, 16), False), ((4, 4, 8), True)]
+    for a, b in zip(eight["statistics"], one["statistics"]):
+        assert a["crack"] == pytest.approx(b["crack"], rel=1e-10)
+        assert a["bulk"] == pytest.approx(b["bulk"], rel=1e-7)
+    assert eight["newton_its"] == one["newton_its"]
