@@ -1,5 +1,7 @@
 #include "fracture_problem.h"
 
+#include "bitmap_function.h"
+
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -106,12 +108,17 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
 
   if (outer_solver != "active set")
     throw NotImplemented ("outer solver = simple monolithic is not part of the GPU hot path");
-  if (test_case != "sneddon" && !miehe ())
+  if (test_case != "sneddon" && !miehe () && !hetero ())
     throw NotImplemented ("test case <" + test_case + "> needs meshes / boundary data outside this round's scope");
+  if (hetero () && (dim_ != 3 || refinement_strategy != "phase field"))
+    throw NotImplemented ("test case = multiple het is available for dim 3 with ref strategy = phase field");
   if (miehe () && dim_ != 2)
     throw NotImplemented ("the Miehe tests are 2-D (meshes/unit_slit.inp)");
-  const bool forest_case = test_case == "sneddon" && dim_ == 2 && refinement_strategy == "fixed preref sneddon"
-                           && (n_local_pre_refine != 0 || n_refinement_cycles != 0);
+  const bool forest_case = (test_case == "sneddon" && dim_ == 2 && refinement_strategy == "fixed preref sneddon"
+                            && (n_local_pre_refine != 0 || n_refinement_cycles != 0))
+                           || hetero ();
+  if (hetero () && n_refinement_cycles != 0)
+    throw NotImplemented ("multiple het: adaptive refinement cycles during the run are not available");
   if (n_local_pre_refine != 0 && !forest_case)
     throw NotImplemented ("local pre-refinement (hanging nodes) is only available for sneddon, dim 2, "
                           "ref strategy = fixed preref sneddon");
@@ -152,8 +159,18 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
   long long cells = 1;
   for (int d = 0; d < dim_; ++d)
     cells *= n;
+  if (hetero ())
+    cells = 1ll << (3 * n_global_pre_refine); // one coarse hexahedron
   pcout_ << "Cells:\t" << cells << std::endl;
-  if (forest_case)
+  if (forest_case && hetero ())
+    {
+      // meshes/unit_cube_10.inp: one hexahedron [0,10]^3 (cracks.cc:1216-1222), then refine_global
+      const int nc[3] = {1, 1, 1};
+      const double lo[3] = {0.0, 0.0, 0.0}, hi[3] = {10.0, 10.0, 10.0};
+      forest_.reset (new Forest (3, nc, lo, hi));
+      forest_->refine_global ((int) n_global_pre_refine);
+    }
+  else if (forest_case)
     {
       const int nc[3] = {n, n, 1};
       const double lo[3] = {-10.0, -10.0, 0.0}, hi[3] = {10.0, 10.0, 0.0};
@@ -334,7 +351,7 @@ FracturePhaseFieldProblem::run ()
   for (unsigned i = 0; i < n_local_pre_refine; ++i)
     {
       pcout_ << "Prerefinement step with h= " << min_cell_diameter << std::endl;
-      forest_refine_fixed_preref_sneddon ();
+      forest_prerefine ();
       setup_system ();
     }
   if (!(alpha_eps >= min_cell_diameter))
@@ -355,7 +372,7 @@ FracturePhaseFieldProblem::run ()
     pf_check (ctx_, pf_interpolate_unbroken (ctx_)); // InitialValuesTensionOrShear, cracks.cc:679-691
   else if (use_forest ())
     {
-      const std::vector<double> ic = forest_initial_sneddon ();
+      const std::vector<double> ic = forest_initial_values ();
       pf_check (ctx_, pf_set_state (ctx_, ic.data (), ic.data (), ic.data (), timestep, timestep, 0, func_pressure.value (0.0)));
     }
   else
@@ -451,11 +468,11 @@ FracturePhaseFieldProblem::run ()
       write_statistics ();
 
       pf_check (ctx_, pf_timestep_difference (ctx_, &finishing_timestep_loop));
-      if (!miehe ())
+      if (test_case == "sneddon")
         pcout_ << "Timestep difference linfty: " << finishing_timestep_loop << std::endl;
       ++timestep_number;
 
-      if (!miehe () && finishing_timestep_loop < 1.0e-5)
+      if (test_case == "sneddon" && finishing_timestep_loop < 1.0e-5)
         {
           pf_check (ctx_, pf_tcv (ctx_, &tcv_));
           const double p = func_pressure.value (time), nu = poisson_ratio_nu, E = 1.0, l_0 = 1.0;
@@ -582,14 +599,15 @@ FracturePhaseFieldProblem::forest_create_context ()
       ctx_ = nullptr;
     }
   const Forest &f = *forest_;
+  const int dim = f.dim (), nv = 1 << dim, ncomp = dim + 1;
   const long long nn = f.n_nodes (), nc = f.n_cells ();
   std::vector<int64_t> conn (f.connectivity ().begin (), f.connectivity ().end ());
   std::vector<uint8_t> level ((size_t) nc);
   for (long long c = 0; c < nc; ++c)
     level[(size_t) c] = (uint8_t) f.cells ()[(size_t) c].level;
-  std::vector<double> level_h ((size_t) (f.max_level () + 1) * 2);
+  std::vector<double> level_h ((size_t) (f.max_level () + 1) * dim);
   for (int l = 0; l <= f.max_level (); ++l)
-    f.cell_size (l, &level_h[(size_t) (2 * l)]);
+    f.cell_size (l, &level_h[(size_t) (dim * l)]);
   std::vector<int64_t> hang (f.hanging_nodes ().size () * 5);
   for (size_t h = 0; h < f.hanging_nodes ().size (); ++h)
     {
@@ -599,7 +617,7 @@ FracturePhaseFieldProblem::forest_create_context ()
         hang[5 * h + 1 + (size_t) q] = q < hn.n_parents ? hn.parents[q] : -1;
     }
   pf_forest_mesh fm{};
-  fm.dim = 2;
+  fm.dim = dim;
   fm.n_cells = nc;
   fm.n_nodes = nn;
   fm.conn = conn.data ();
@@ -608,20 +626,105 @@ FracturePhaseFieldProblem::forest_create_context ()
   fm.level_h = level_h.data ();
   fm.n_hanging = (int64_t) f.hanging_nodes ().size ();
   fm.hanging = hang.empty () ? nullptr : hang.data ();
+  // heterogeneous material: Lame coefficients per cell from E(cell centre) (cracks.cc:2207-2216); the assembly
+  // uses E + 1, compute_energy uses E (3646-3656)
+  std::vector<double> lame_assembly, lame_energy;
+  if (hetero ())
+    {
+      const BitmapFunction func_emodulus (source_dir + "/test.pgm", 0, 10, 0, 10, E_modulus, 10.0 * E_modulus); // 1543
+      lame_assembly.resize ((size_t) nc * 2);
+      lame_energy.resize ((size_t) nc * 2);
+      const double nu = poisson_ratio_nu;
+      for (long long c = 0; c < nc; ++c)
+        {
+          double x[3];
+          f.cell_centre (c, x);
+          const double E = func_emodulus.value (x, 3);
+          for (int which = 0; which < 2; ++which)
+            {
+              const double Ev = which == 0 ? E + 1.0 : E;
+              const double mu = Ev / (2.0 * (1 + nu)), lambda = (2 * nu * mu) / (1.0 - 2 * nu);
+              std::vector<double> &out = which == 0 ? lame_assembly : lame_energy;
+              out[(size_t) (2 * c)] = lambda;
+              out[(size_t) (2 * c + 1)] = mu;
+            }
+        }
+      fm.cell_lame = lame_assembly.data ();
+      fm.cell_lame_energy = lame_energy.data ();
+    }
   const int rc = pf_create_forest (&fm, &params_, device, &ctx_);
   pf_check (ctx_, rc);
-  // set_newton_bc(): u = 0 on boundary ids 0..3 (cracks.cc:2575-2583); block layout [u | phi]
-  std::vector<uint8_t> dirichlet ((size_t) nn * 3, 0), none ((size_t) nn * 3, 0);
+  // set_newton_bc(): u = 0 on every boundary face (cracks.cc:2575-2583, 2686-2694); block layout [u | phi]
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (long long n = 0; n < nn; ++n)
+    for (int d = 0; d < dim; ++d)
+      {
+        lo[d] = std::min (lo[d], f.coordinates ()[(size_t) (dim * n + d)]);
+        hi[d] = std::max (hi[d], f.coordinates ()[(size_t) (dim * n + d)]);
+      }
+  std::vector<uint8_t> dirichlet ((size_t) nn * ncomp, 0), none ((size_t) nn * ncomp, 0);
   for (long long n = 0; n < nn; ++n)
     {
-      const double x = f.coordinates ()[(size_t) (2 * n)], y = f.coordinates ()[(size_t) (2 * n + 1)];
-      if (x == -10.0 || x == 10.0 || y == -10.0 || y == 10.0)
-        dirichlet[(size_t) (2 * n)] = dirichlet[(size_t) (2 * n + 1)] = 1;
+      bool on_boundary = false;
+      for (int d = 0; d < dim; ++d)
+        {
+          const double x = f.coordinates ()[(size_t) (dim * n + d)];
+          on_boundary = on_boundary || x == lo[d] || x == hi[d];
+        }
+      if (on_boundary)
+        for (int d = 0; d < dim; ++d)
+          dirichlet[(size_t) (dim * n + d)] = 1;
     }
+  (void) nv;
   pf_check (ctx_, pf_set_constraints (ctx_, dirichlet.data (), none.data ()));
-  // the reference hands these small systems to AMG; Jacobi-GMRES wants a long basis
+  // the reference hands these systems to AMG; Jacobi-GMRES wants a long basis
   pf_check (ctx_, pf_set_krylov_dim (ctx_, 300));
   gmres_max_iterations = std::max (gmres_max_iterations, 3000);
+}
+
+// refine_mesh(), strategy `phase field` during the local pre-refinement (cracks.cc:3971-3995, 4108-4116): cells that
+// hold an initial phase-field value below the threshold, up to the level cap
+void
+FracturePhaseFieldProblem::forest_refine_phase_field_on_initial_values ()
+{
+  const Forest &f = *forest_;
+  const int dim = f.dim (), nv = 1 << dim;
+  const int cap = (int) (n_global_pre_refine + n_refinement_cycles + n_local_pre_refine);
+  const std::vector<double> ic = forest_initial_values ();
+  const long long nn = f.n_nodes ();
+  std::vector<char> flags ((size_t) f.n_cells (), 0);
+  for (long long c = 0; c < f.n_cells (); ++c)
+    {
+      if (f.cells ()[(size_t) c].level >= cap)
+        continue;
+      for (int v = 0; v < nv; ++v)
+        if (ic[(size_t) (dim * nn + f.connectivity ()[(size_t) (c * nv + v)])] < value_phase_field_for_refinement)
+          flags[(size_t) c] = 1;
+    }
+  forest_->refine (flags);
+}
+
+void
+FracturePhaseFieldProblem::forest_prerefine ()
+{
+  if (hetero ())
+    forest_refine_phase_field_on_initial_values ();
+  else
+    forest_refine_fixed_preref_sneddon ();
+}
+
+// the initial values of the test case at the forest's nodes, block layout [u | phi]
+std::vector<double>
+FracturePhaseFieldProblem::forest_initial_values () const
+{
+  if (!hetero ())
+    return forest_initial_sneddon ();
+  const Forest &f = *forest_;
+  const long long nn = f.n_nodes ();
+  std::vector<double> b ((size_t) nn * 4, 0.0);
+  for (long long n = 0; n < nn; ++n)
+    b[(size_t) (3 * nn + n)] = initial_multiple_het_3d (&f.coordinates ()[(size_t) (3 * n)], min_cell_diameter);
+  return b;
 }
 
 // InitialValuesSneddon<2> (cracks.cc:381-406) at the forest's nodes, block layout

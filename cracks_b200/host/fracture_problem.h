@@ -9,7 +9,11 @@
 //   `test case = sneddon` on the uniform (globally refined) box, dim 2 or 3;
 //   `test case = miehe tension / miehe shear` (dim 2) on the globally refined
 //   meshes/unit_slit.inp topology, with the stress split and the load
-//   functional, for as long as refine_mesh() would not change the mesh.
+//   functional, for as long as refine_mesh() would not change the mesh;
+//   on the host forest (forest.h; device side verified on the CPU emulation,
+//   first GPU run pending): `sneddon`, dim 2, with local pre-refinement and
+//   refinement cycles (`fixed preref sneddon`), and `multiple het`, dim 3,
+//   with the phase-field pre-refinement and the bitmap E-modulus field.
 // Everything else the .prm surface can express is parsed and rejected with
 // ExcNotImplemented-style errors (SURVEY.md section 8f lists it as "next").
 #pragma once
@@ -55,6 +59,7 @@ public:
   unsigned total_linear_iterations () const { return total_linear_its_; }
   // knobs that are not part of the reference's .prm surface
   int device = 0;
+  std::string source_dir = ".";   // where test.pgm lives ($SRC of cracks.cc:1541, a compile-time path in the reference)
   int gmres_max_iterations = 200; // SolverControl(200, ...) at cracks.cc:2762
   double gmres_tolerance = 1e-8;
 
@@ -68,9 +73,13 @@ private:
   // EXPERIMENTAL (device side not yet run on a GPU): Sneddon 2-D with local pre-refinement
   // / refinement cycles on the host forest, strategy `fixed preref sneddon`
   bool use_forest () const { return forest_ != nullptr; }
+  bool hetero () const { return test_case == "multiple het"; }
   void forest_refine_fixed_preref_sneddon ();
+  void forest_refine_phase_field_on_initial_values ();
+  void forest_prerefine ();
   void forest_create_context ();
   std::vector<double> forest_initial_sneddon () const;
+  std::vector<double> forest_initial_values () const;
   long long n_nodes () const;
   long long n_cells () const;
   int miehe_kind () const { return test_case == "miehe tension" ? 1 : 2; }

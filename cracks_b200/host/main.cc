@@ -20,12 +20,15 @@ main (int argc, char *argv[])
       FracturePhaseFieldProblem::declare_parameters (prm);
       const char *file = nullptr;
       int device = 0, gmres_max_it = 200;
+      std::string source_dir = ".";
       for (int i = 1; i < argc; ++i)
         {
           if (!std::strcmp (argv[i], "--device") && i + 1 < argc)
             device = std::atoi (argv[++i]);
           else if (!std::strcmp (argv[i], "--gmres-max-it") && i + 1 < argc)
             gmres_max_it = std::atoi (argv[++i]);
+          else if (!std::strcmp (argv[i], "--source-dir") && i + 1 < argc)
+            source_dir = argv[++i]; // where test.pgm lives (multiple het)
           else
             file = argv[i];
         }
@@ -33,7 +36,7 @@ main (int argc, char *argv[])
         {
           std::ofstream out ("default.prm");
           out << prm.print_parameters ();
-          std::cout << "usage: ./cracks_b200 <parameter_file> [--device N] [--gmres-max-it K]" << std::endl
+          std::cout << "usage: ./cracks_b200 <parameter_file> [--device N] [--gmres-max-it K] [--source-dir DIR]" << std::endl
                     << " (created default.prm)" << std::endl;
           return 0;
         }
@@ -51,6 +54,7 @@ main (int argc, char *argv[])
       FracturePhaseFieldProblem problem (prm, dim, std::cout);
       problem.device = device;
       problem.gmres_max_iterations = gmres_max_it;
+      problem.source_dir = source_dir;
       problem.run ();
     }
   catch (std::exception &exc)

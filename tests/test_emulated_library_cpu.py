@@ -220,7 +220,7 @@ def test_cpp_host_driver_on_the_forest_path(emu_so, tmp_path):
     host = os.path.join(ROOT, "cracks_b200", "host")
     exe = os.path.join(HERE, "emu", "cracks_b200_run_emu")
     srcs = [os.path.join(host, f) for f in ("main.cc", "fracture_problem.cc", "parameter_handler.cc", "function_parser.cc",
-                                            "forest.cc")]
+                                            "forest.cc", "bitmap_function.cc")]
     deps = srcs + [os.path.join(host, f) for f in os.listdir(host) if f.endswith(".h")] + [emu_so]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, *srcs, "-L", os.path.join(HERE, "emu"),
@@ -336,3 +336,60 @@ def test_forest_hetero_3d_kat5_end_to_end(epf):
         assert got["crack"] == pytest.approx(ref["crack"], rel=1e-7)
         assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-6)
     drv.ctx.close()
+
+
+def test_cpp_host_driver_hetero_3d(emu_so, tmp_path):
+    """`test case = multiple het` (BASELINE config 5 in small) through the C++ command line on the emulated build:
+    single-tree cube, phase-field pre-refinement, E-modulus field read from the reference's test.pgm by the C++
+    BitmapFunction, hanging nodes in 3-D -- tests/hetero_3d_1.mpirun-4.statistics.  Needs the reference tree for
+    the bitmap (skipped elsewhere)."""
+    if not os.path.exists("/root/reference/test.pgm"):
+        pytest.skip("the reference's test.pgm is only present in the build container")
+    exe = os.path.join(HERE, "emu", "cracks_b200_run_emu")
+    host = os.path.join(ROOT, "cracks_b200", "host")
+    srcs = [os.path.join(host, f) for f in ("main.cc", "fracture_problem.cc", "parameter_handler.cc", "function_parser.cc",
+                                            "forest.cc", "bitmap_function.cc")]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, *srcs, "-L", os.path.join(HERE, "emu"),
+                           "-lcracks_b200_emu", "-Wl,-rpath," + os.path.join(HERE, "emu"), "-pthread"])
+    g = json.load(open(os.path.join(HERE, "golden", "hetero_3d_1.json")))
+    (tmp_path / "h.prm").write_text(f"""subsection Global parameters
+  set Dimension = 3
+  set Global pre-refinement steps = 3
+  set Local pre-refinement steps = 1
+  set Adaptive refinement cycles = 0
+  set Max No of timesteps = 1
+  set Timestep size = 0.01
+  set outer solver = active set
+  set test case = multiple het
+  set ref strategy = phase field
+  set value phase field for refinement = 0.4
+  set Output directory = {tmp_path / 'out'}
+end
+subsection Problem dependent parameters
+  set K reg = 0
+  set Eps reg = 1.5
+  set Pressure = 0 + time *1e3
+  set Fracture toughness G_c = 1.0
+  set Poisson ratio nu = 0.2
+  set E modulus = 1e4
+end
+subsection Solver parameters
+  set Newton lower bound = 1.0e-6
+  set Newton maximum steps = 20
+  set Line search maximum steps = 8
+  set Line search damping = 0.5
+end
+""")
+    r = subprocess.run([exe, str(tmp_path / "h.prm"), "--source-dir", "/root/reference"], capture_output=True, text=True,
+                       timeout=900)
+    print(r.stdout[-2500:], r.stderr[-800:])
+    assert r.returncode == 0, r.stderr
+    assert "Cells:\t512" in r.stdout and "DoFs: 2187 solid + 729 phase = 2916" in r.stdout   # tests/hetero_3d_1 output
+    assert "Prerefinement step with h= 2.16506" in r.stdout and "DoFs: 3966 solid + 1322 phase = 5288" in r.stdout
+    assert "0\t\t\t2.772590e+01" in r.stdout and "0\t\t\t9.870742e+01" in r.stdout
+    rows = [l.split() for l in open(tmp_path / "out" / "statistics") if not l.startswith("#")]
+    assert len(rows) == 2
+    for row, ref in zip(rows, g["statistics"]):
+        assert int(row[2]) == 5288 and float(row[3]) == pytest.approx(ref["h"], rel=1e-8)
+        assert float(row[5]) == pytest.approx(ref["crack"], rel=1e-7)
+        assert float(row[4]) == pytest.approx(ref["bulk"], rel=1e-6)
