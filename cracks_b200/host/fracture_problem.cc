@@ -116,7 +116,7 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
     throw NotImplemented ("the Miehe tests are 2-D (meshes/unit_slit.inp)");
   const bool forest_case = (test_case == "sneddon" && dim_ == 2 && refinement_strategy == "fixed preref sneddon"
                             && (n_local_pre_refine != 0 || n_refinement_cycles != 0))
-                           || hetero ();
+                           || hetero () || (miehe () && n_refinement_cycles != 0 && adaptive_forest);
   if (hetero () && n_refinement_cycles != 0)
     throw NotImplemented ("multiple het: adaptive refinement cycles during the run are not available");
   if (n_local_pre_refine != 0 && !forest_case)
@@ -168,6 +168,14 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
       const int nc[3] = {1, 1, 1};
       const double lo[3] = {0.0, 0.0, 0.0}, hi[3] = {10.0, 10.0, 10.0};
       forest_.reset (new Forest (3, nc, lo, hi));
+      forest_->refine_global ((int) n_global_pre_refine);
+    }
+  else if (forest_case && miehe ())
+    {
+      // meshes/unit_slit.inp: 2 x 2 cells with the slit (cracks.cc:1202-1205), then refine_global
+      const int nc[3] = {2, 2, 1};
+      const double lo[3] = {0.0, 0.0, 0.0}, hi[3] = {1.0, 1.0, 0.0};
+      forest_.reset (new Forest (2, nc, lo, hi, true));
       forest_->refine_global ((int) n_global_pre_refine);
     }
   else if (forest_case)
@@ -404,6 +412,7 @@ FracturePhaseFieldProblem::run ()
       pcout_ << "\n--------------------------------" << "---------------------------------------" << std::endl;
       pcout_ << std::endl;
 
+    redo_step: // cracks.cc:4307
       time += timestep;
       do
         {
@@ -413,7 +422,12 @@ FracturePhaseFieldProblem::run ()
           // the split is active from the second time step on (cracks.cc:2294, 2338)
           pf_check (ctx_, pf_set_stress_split (ctx_, decompose_stress_matrix > 0 && timestep_number > 0,
                                                decompose_stress_rhs, decompose_stress_matrix));
-          if (miehe ())
+          if (miehe () && use_forest ())
+            {
+              const std::vector<double> bc = forest_miehe_boundary_values (time);
+              pf_check (ctx_, pf_set_dirichlet_values (ctx_, bc.data ()));     // set_initial_bc(time), 2787
+            }
+          else if (miehe ())
             pf_check (ctx_, pf_dirichlet_miehe (ctx_, miehe_kind (), time, 1)); // set_initial_bc(time), 2787
           try
             {
@@ -438,7 +452,20 @@ FracturePhaseFieldProblem::run ()
       while (true);
 
       pf_check (ctx_, pf_project_phase_field (ctx_));
-      if (miehe () && n_refinement_cycles > 0)
+      if (miehe () && use_forest ())
+        {
+          // predictor-corrector refinement (cracks.cc:4419-4431): if refine_mesh() changed the mesh, redo the step
+          if (forest_refine_phase_field_and_transfer ())
+            {
+              pcout_ << "MESH CHANGED!" << std::endl;
+              time -= timestep;
+              pf_check (ctx_, pf_restore_old_solution (ctx_));
+              nodes = n_nodes ();
+              cells = n_cells ();
+              goto redo_step;
+            }
+        }
+      else if (miehe () && n_refinement_cycles > 0)
         {
           // refine_mesh(), strategy "phase field" (cracks.cc:3971-3995): cells with a phase-field dof
           // below the threshold would be refined and the step redone.  Hanging nodes are out of scope.
@@ -459,7 +486,10 @@ FracturePhaseFieldProblem::run ()
       if (miehe ())
         {
           double lx = 0, ly = 0;
-          pf_check (ctx_, pf_load (ctx_, &lx, &ly)); // compute_load(), cracks.cc:3728-3816
+          if (use_forest ())
+            pf_check (ctx_, pf_load_cells (ctx_, forest_top_cells_.data (), (int64_t) forest_top_cells_.size (), &lx, &ly));
+          else
+            pf_check (ctx_, pf_load (ctx_, &lx, &ly)); // compute_load(), cracks.cc:3728-3816
           load = miehe_kind () == 1 ? ly : lx;
           pcout_ << (miehe_kind () == 1 ? "  Load y: " : "  Load x: ") << load;
         }
@@ -671,11 +701,41 @@ FracturePhaseFieldProblem::forest_create_context ()
           const double x = f.coordinates ()[(size_t) (dim * n + d)];
           on_boundary = on_boundary || x == lo[d] || x == hi[d];
         }
-      if (on_boundary)
+      if (on_boundary && !miehe ())
         for (int d = 0; d < dim; ++d)
           dirichlet[(size_t) (dim * n + d)] = 1;
     }
   (void) nv;
+  if (miehe ())
+    {
+      // set_newton_bc() of the Miehe tests (cracks.cc:2584-2625) on the unit square with the slit
+      forest_top_nodes_.clear ();
+      forest_top_cells_.clear ();
+      for (long long n = 0; n < nn; ++n)
+        {
+          const double x = f.coordinates ()[(size_t) (2 * n)], y = f.coordinates ()[(size_t) (2 * n + 1)];
+          const bool top = y == 1.0, bottom = y == 0.0, left = x == 0.0, right = x == 1.0;
+          bool cx = false, cy = false;
+          if (miehe_kind () == 1)
+            {
+              cy = bottom || top;
+              cx = top;
+            }
+          else
+            {
+              const bool lower_slit = y == 0.5 && x >= 0.5 && !f.is_upper_slit_copy (n); // boundary id 4
+              cy = left || right || bottom || top || lower_slit;
+              cx = bottom || top;
+            }
+          dirichlet[(size_t) (2 * n)] = cx;
+          dirichlet[(size_t) (2 * n + 1)] = cy;
+          if (top)
+            forest_top_nodes_.push_back (n);
+        }
+      for (long long c = 0; c < nc; ++c)
+        if (f.coordinates ()[(size_t) (2 * f.connectivity ()[(size_t) (4 * c + 2)] + 1)] == 1.0)
+          forest_top_cells_.push_back (c);
+    }
   pf_check (ctx_, pf_set_constraints (ctx_, dirichlet.data (), none.data ()));
   // the reference hands these systems to AMG; Jacobi-GMRES wants a long basis
   pf_check (ctx_, pf_set_krylov_dim (ctx_, 300));
@@ -702,6 +762,77 @@ FracturePhaseFieldProblem::forest_refine_phase_field_on_initial_values ()
           flags[(size_t) c] = 1;
     }
   forest_->refine (flags);
+}
+
+// BoundaryTensionTest / BoundaryShearTest (cracks.cc:780-797, 845-861) on the forest's nodes, block layout
+std::vector<double>
+FracturePhaseFieldProblem::forest_miehe_boundary_values (double t) const
+{
+  const long long nn = forest_->n_nodes ();
+  std::vector<double> b ((size_t) nn * 3, 0.0);
+  for (const long long n : forest_top_nodes_)
+    {
+      if (miehe_kind () == 1)
+        b[(size_t) (2 * n + 1)] = t;
+      else
+        b[(size_t) (2 * n)] = -t;
+    }
+  return b;
+}
+
+// refine_mesh(), strategy `phase field` (cracks.cc:3971-3995, 4108-4159): flag cells holding a phase-field dof
+// below the threshold (not beyond the level cap), refine with 2:1 balance, interpolate solution / old / old_old
+// to the new forest and rebuild the device context.  Returns false if nothing was flagged.
+bool
+FracturePhaseFieldProblem::forest_refine_phase_field_and_transfer ()
+{
+  const Forest coarse = *forest_;
+  const long long nn_old = coarse.n_nodes (), nd_old = nn_old * 3;
+  std::vector<double> blk[3];
+  for (int w = 0; w < 3; ++w)
+    {
+      blk[w].resize ((size_t) nd_old);
+      pf_check (ctx_, pf_get_state (ctx_, w, blk[w].data ()));
+    }
+  const int cap = (int) (n_global_pre_refine + n_refinement_cycles + n_local_pre_refine);
+  std::vector<char> flags ((size_t) coarse.n_cells (), 0);
+  bool any = false;
+  for (long long c = 0; c < coarse.n_cells (); ++c)
+    {
+      if (coarse.cells ()[(size_t) c].level >= cap)
+        continue;
+      for (int v = 0; v < 4; ++v)
+        if (blk[0][(size_t) (2 * nn_old + coarse.connectivity ()[(size_t) (4 * c + v)])] < value_phase_field_for_refinement)
+          flags[(size_t) c] = 1;
+      any = any || flags[(size_t) c];
+    }
+  if (!any)
+    return false;
+  forest_->refine (flags);
+  setup_system ();
+  const long long nn_new = forest_->n_nodes ();
+  std::vector<double> out[3];
+  std::vector<double> nodal_old ((size_t) nd_old), nodal_new ((size_t) nn_new * 3);
+  for (int w = 0; w < 3; ++w)
+    {
+      for (long long i = 0; i < nn_old; ++i)
+        {
+          nodal_old[(size_t) (3 * i)] = blk[w][(size_t) (2 * i)];
+          nodal_old[(size_t) (3 * i + 1)] = blk[w][(size_t) (2 * i + 1)];
+          nodal_old[(size_t) (3 * i + 2)] = blk[w][(size_t) (2 * nn_old + i)];
+        }
+      forest_->transfer (coarse, nodal_old.data (), nodal_new.data (), 3);
+      out[w].resize ((size_t) nn_new * 3);
+      for (long long i = 0; i < nn_new; ++i)
+        {
+          out[w][(size_t) (2 * i)] = nodal_new[(size_t) (3 * i)];
+          out[w][(size_t) (2 * i + 1)] = nodal_new[(size_t) (3 * i + 1)];
+          out[w][(size_t) (2 * nn_new + i)] = nodal_new[(size_t) (3 * i + 2)];
+        }
+    }
+  pf_check (ctx_, pf_set_state (ctx_, out[0].data (), out[1].data (), out[2].data (), old_timestep, old_old_timestep, 0,
+                                func_pressure.value (time)));
+  return true;
 }
 
 void

@@ -59,6 +59,10 @@ public:
   unsigned total_linear_iterations () const { return total_linear_its_; }
   // knobs that are not part of the reference's .prm surface
   int device = 0;
+  // EXPERIMENTAL: run the Miehe tests with `Adaptive refinement cycles` > 0 on the host forest and follow
+  // refine_mesh() (phase-field flags, level cap, solution transfer, redo of the step) instead of stopping
+  // where the mesh would change
+  bool adaptive_forest = false;
   std::string source_dir = ".";   // where test.pgm lives ($SRC of cracks.cc:1541, a compile-time path in the reference)
   int gmres_max_iterations = 200; // SolverControl(200, ...) at cracks.cc:2762
   double gmres_tolerance = 1e-8;
@@ -80,6 +84,8 @@ private:
   void forest_create_context ();
   std::vector<double> forest_initial_sneddon () const;
   std::vector<double> forest_initial_values () const;
+  bool forest_refine_phase_field_and_transfer ();
+  std::vector<double> forest_miehe_boundary_values (double t) const;
   long long n_nodes () const;
   long long n_cells () const;
   int miehe_kind () const { return test_case == "miehe tension" ? 1 : 2; }
@@ -89,6 +95,8 @@ private:
   std::ostream &pcout_;
   pf_ctx *ctx_ = nullptr;
   std::unique_ptr<Forest> forest_;
+  std::vector<long long> forest_top_nodes_;  // nodes on boundary id 3 (y = 1) of the Miehe forest
+  std::vector<int64_t> forest_top_cells_;    // cells whose top edge lies on it (compute_load)
   pf_mesh mesh_{};
   pf_params params_{};
 

@@ -307,6 +307,30 @@ end
             assert float(row[col]) == pytest.approx(b[k], rel=1e-6), (row[0], k)
 
 
+def test_cpp_host_driver_miehe_adaptive(emu_so, tmp_path):
+    """tests/miehe_shear_1.prm through the C++ command line with --adaptive: predictor-corrector refinement on the
+    slit forest (phase-field flags, 2:1 balance across the slit, SolutionTransfer of the three vectors, redo of
+    the step) against the reference's golden statistics.  Steps 0-6 by default (the mesh changes in step 6:
+    891 -> 918 DoFs); PF_SLOW_TESTS=1 runs all 11 rows."""
+    from prm_from_golden import write_prm, read_statistics
+    exe = os.path.join(HERE, "emu", "cracks_b200_run_emu")
+    if not os.path.exists(exe):
+        pytest.skip("built by test_cpp_host_driver_on_the_forest_path")
+    g = json.load(open(os.path.join(HERE, "golden", "miehe_shear_1.json")))
+    last = 10 if os.environ.get("PF_SLOW_TESTS") == "1" else 6
+    write_prm(tmp_path / "a.prm", g["prm"], 2, tmp_path / "out", Max_No_of_timesteps=last)
+    r = subprocess.run([exe, str(tmp_path / "a.prm"), "--adaptive"], capture_output=True, text=True, timeout=3000)
+    print(r.stdout[-1500:], r.stderr[-800:])
+    assert r.returncode == 0, r.stderr
+    assert "MESH CHANGED!" in r.stdout
+    rows = read_statistics(tmp_path / "out" / "statistics")
+    assert len(rows) == last + 1
+    for row, ref in zip(rows, g["statistics"]):
+        assert int(row[2]) == ref["dofs"] and float(row[3]) == pytest.approx(ref["h"], rel=1e-8)
+        for col, k in ((4, "bulk"), (5, "crack"), (6, "load")):
+            assert float(row[col]) == pytest.approx(ref[k], rel=2e-7), (row[0], k)
+
+
 def test_forest_hetero_3d_kat5_end_to_end(epf):
     """BASELINE config 5 in small through the library (emulated): octree with edge / face hanging nodes from the
     phase-field pre-refinement, per-cell Lame coefficients (both sets), pressure(time): tests/hetero_3d_1 golden."""

@@ -172,6 +172,29 @@ def test_miehe_tension_adaptive_on_the_gpu(pf):
     drv.ctx.close()
 
 
+@pytest.mark.parametrize("name", ["miehe_shear_1", "miehe_tension_adaptive_1"])
+def test_adaptive_miehe_through_the_cli(pf, tmp_path, name):
+    """tests/miehe_shear_1.prm and tests/miehe_tension_adaptive_1.prm through `cracks_b200_run --adaptive`:
+    predictor-corrector refinement on the slit forest, every row of the golden statistics."""
+    import subprocess
+    from prm_from_golden import write_prm, read_statistics
+    root = os.path.dirname(HERE)
+    subprocess.check_call(["make", "-C", os.path.join(root, "cracks_b200", "host"), "-s"])
+    g = json.load(open(os.path.join(HERE, "golden", name + ".json")))
+    write_prm(tmp_path / "a.prm", g["prm"], 2, tmp_path / "out")
+    r = subprocess.run([os.path.join(root, "cracks_b200", "cracks_b200_run"), str(tmp_path / "a.prm"), "--adaptive"],
+                       capture_output=True, text=True, timeout=1200)
+    print(r.stdout[-3000:], r.stderr[-1000:])
+    assert r.returncode == 0, r.stderr
+    assert "MESH CHANGED!" in r.stdout
+    rows = read_statistics(tmp_path / "out" / "statistics")
+    assert len(rows) == len(g["statistics"])
+    for row, ref in zip(rows, g["statistics"]):
+        assert int(row[2]) == ref["dofs"]
+        for col, k in ((4, "bulk"), (5, "crack"), (6, "load")):
+            assert float(row[col]) == pytest.approx(ref[k], rel=1e-6), (row[0], k)
+
+
 def test_hetero_3d_kat5_on_the_gpu(pf):
     """BASELINE config 5 in small: tests/hetero_3d_1.mpirun-4.statistics on the 3-D forest path"""
     from cracks_b200.forest import ForestHeteroDriver
