@@ -522,6 +522,14 @@ launch_apply3d_v4 (pf_ctx *ctx, const double *x, double *y)
                                 (int) T::smem_bytes));
       CU (cudaFuncSetAttribute (k_apply3d_v4<TX, TY, TZ, MINB, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
+      if (MINB > 4)
+        {
+          // more than four resident CTAs only fit with the largest shared-memory carve-out
+          CU (cudaFuncSetAttribute (k_apply3d_v4<TX, TY, TZ, MINB, NQ, false>,
+                                    cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+          CU (cudaFuncSetAttribute (k_apply3d_v4<TX, TY, TZ, MINB, NQ, true>,
+                                    cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
       attr_set = true;
     }
   const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;

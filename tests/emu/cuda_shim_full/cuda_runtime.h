@@ -154,6 +154,7 @@ enum
   cudaEventDisableTiming = 2,
   cudaStreamCaptureModeThreadLocal = 1,
   cudaFuncAttributeMaxDynamicSharedMemorySize = 8,
+  cudaFuncAttributePreferredSharedMemoryCarveout = 9,
   cudaDevAttrMultiProcessorCount = 16
 };
 inline const char *
