@@ -90,6 +90,8 @@ _SIGS = {
     "pf_residual": [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)],
     "pf_setup_jacobian": [C.c_void_p],
     "pf_set_preconditioner": [C.c_void_p, C.c_int, C.c_int, C.c_double],
+    "pf_set_multigrid_precision": [C.c_void_p, C.c_int],
+    "pf_apply_preconditioner": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_set_krylov_dim": [C.c_void_p, C.c_int],
     "pf_apply_jacobian": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_apply_jacobian_dev": [C.c_void_p, C.c_void_p, C.c_void_p],
@@ -357,6 +359,17 @@ class PhaseFieldContext:
     def set_preconditioner(self, kind=1, cheb_degree=2, cheb_ratio=20.0):
         """0 = Jacobi, 1 = geometric multigrid (stand-in for the reference's ML AMG)"""
         self._check(self.lib.pf_set_preconditioner(self.h, kind, cheb_degree, cheb_ratio))
+
+    def set_multigrid_precision(self, bits=64):
+        """64 (default) or 32: run the V-cycle of the multigrid preconditioner in FP32 (outer GMRES stays FP64)"""
+        self._check(self.lib.pf_set_multigrid_precision(self.h, bits))
+
+    def apply_preconditioner(self, v):
+        """z = M^-1 v (one V-cycle, or Jacobi), block layout"""
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        z = np.empty_like(v)
+        self._check(self.lib.pf_apply_preconditioner(self.h, _ptr(v), _ptr(z)))
+        return z
 
     def setup_jacobian(self):
         self._check(self.lib.pf_setup_jacobian(self.h))

@@ -25,6 +25,7 @@
 #include "pf_common.cuh"
 #include "pf_forest.cuh"
 #include "pf_generic.cuh"
+#include "pf_mg_lowp.cuh"
 #include "pf_multigrid.cuh"
 #include "pf_residual3d.cuh"
 #include "pf_vector.cuh"
@@ -39,7 +40,7 @@ namespace {
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat64 = 8, ncclUint64 = 5, ncclUint8 = 1 };
+enum { ncclFloat64 = 8, ncclFloat32 = 7, ncclUint64 = 5, ncclUint8 = 1 };
 enum { ncclSum = 0, ncclMax = 2 };
 struct NcclApi
 {
@@ -154,6 +155,11 @@ struct pf_ctx
   cudaGraphExec_t mg_graph = nullptr;
   bool mg_graph_valid = false;
   long long mg_graph_launches = 0;
+  // the V-cycle in FP32 (pf_mg_lowp.cuh; opt-in, pf_set_multigrid_precision): per level the state, the inverse
+  // diagonal and the work vectors in float; set-up (diagonal, power iteration) stays FP64
+  int mg_fp32 = getenv ("PF_MG_FP32") ? atoi (getenv ("PF_MG_FP32")) : 0;
+  float *f_sol = nullptr, *f_pt = nullptr, *f_idiag = nullptr;
+  float *f_b = nullptr, *f_x = nullptr, *f_y = nullptr, *f_d = nullptr, *f_r = nullptr;
   double *mg_in = nullptr;  // fixed input buffer of the captured V-cycle
   double *mg_out = nullptr; // output buffer it was captured with
   // forest (locally refined) mesh, see pf_create_forest -- EXPERIMENTAL, not yet run on a GPU
@@ -314,9 +320,10 @@ update_phys (pf_ctx *c)
   c->p.d_mat = c->d_mat;
 }
 
-// ghost planes of a local nodal vector <- owners (ncomp doubles per node)
+// ghost planes of a local nodal vector <- owners (ncomp entries of type T per node)
+template <typename T>
 int
-halo_exchange (pf_ctx *ctx, double *v, int ncomp, cudaStream_t on = nullptr)
+halo_exchange_t (pf_ctx *ctx, T *v, int ncomp, int nccl_type, cudaStream_t on = nullptr)
 {
   if (ctx->nranks == 1)
     return PF_OK;
@@ -328,16 +335,28 @@ halo_exchange (pf_ctx *ctx, double *v, int ncomp, cudaStream_t on = nullptr)
   if (ctx->rank > 0)
     {
       // lower ghost = plane_begin (owned by rank-1); send my first owned plane down
-      NC_ (g_nccl.Recv (plane (g.plane_begin), cnt, ncclFloat64, ctx->rank - 1, ctx->comm, st));
-      NC_ (g_nccl.Send (plane (g.owned_begin), cnt, ncclFloat64, ctx->rank - 1, ctx->comm, st));
+      NC_ (g_nccl.Recv (plane (g.plane_begin), cnt, nccl_type, ctx->rank - 1, ctx->comm, st));
+      NC_ (g_nccl.Send (plane (g.owned_begin), cnt, nccl_type, ctx->rank - 1, ctx->comm, st));
     }
   if (ctx->rank < ctx->nranks - 1)
     {
-      NC_ (g_nccl.Recv (plane (g.plane_end - 1), cnt, ncclFloat64, ctx->rank + 1, ctx->comm, st));
-      NC_ (g_nccl.Send (plane (g.owned_end - 1), cnt, ncclFloat64, ctx->rank + 1, ctx->comm, st));
+      NC_ (g_nccl.Recv (plane (g.plane_end - 1), cnt, nccl_type, ctx->rank + 1, ctx->comm, st));
+      NC_ (g_nccl.Send (plane (g.owned_end - 1), cnt, nccl_type, ctx->rank + 1, ctx->comm, st));
     }
   NC_ (g_nccl.GroupEnd ());
   return PF_OK;
+}
+
+int
+halo_exchange (pf_ctx *ctx, double *v, int ncomp, cudaStream_t on = nullptr)
+{
+  return halo_exchange_t (ctx, v, ncomp, ncclFloat64, on);
+}
+
+int
+halo_exchange (pf_ctx *ctx, float *v, int ncomp, cudaStream_t on = nullptr)
+{
+  return halo_exchange_t (ctx, v, ncomp, ncclFloat32, on);
 }
 
 // same for a byte field (the constraint mask)
@@ -965,6 +984,8 @@ int create_impl (const pf_mesh *mesh, const pf_params *params, int device, int r
 int diag_and_aux (pf_ctx *ctx);
 
 // (re)builds the level below ctx and transfers state, constraints and parameters to it
+int mg_lowp_refresh (pf_ctx *ctx);
+
 int
 mg_setup_level (pf_ctx *ctx)
 {
@@ -1022,6 +1043,12 @@ mg_setup_level (pf_ctx *ctx)
     ctx->mg_ev_valid = true;
     ctx->lam_max = 1.2 * lam;
   }
+  if (ctx->mg_fp32)
+    {
+      const int rcl = mg_lowp_refresh (ctx);
+      if (rcl)
+        return rcl;
+    }
   if (!mg_possible (ctx))
     {
       ctx->mg_ready = true;
@@ -1055,6 +1082,7 @@ mg_setup_level (pf_ctx *ctx)
   c->cheb_ratio = ctx->cheb_ratio;
   c->mg_approx = ctx->mg_approx;
   c->coarsest_degree = ctx->coarsest_degree;
+  c->mg_fp32 = ctx->mg_fp32;
   Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}, c->g.plane_begin},
     df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}, ctx->g.plane_begin};
   int rc;
@@ -1192,10 +1220,185 @@ mg_vcycle (pf_ctx *ctx, const double *b, double *x)
   return mg_smooth (ctx, b, x, false, ctx->cheb_degree, ctx->cheb_ratio);
 }
 
+// ---- the V-cycle in FP32 (pf_mg_lowp.cuh) ---------------------------------------------------
+
+template <int TX, int TY, int TZ, int MINB>
+int
+launch_apply3d_mg (pf_ctx *ctx, const float *x, float *y)
+{
+  using T = Tile3mg<float, TX, TY, TZ>;
+  Grid g = ctx->g;
+  if (ctx->range_begin >= 0)
+    {
+      g.cell_begin = ctx->range_begin;
+      g.cell_end = ctx->range_end;
+    }
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+  const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
+  if (iso)
+    k_apply3d_mg<float, TX, TY, TZ, MINB, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->f_sol, ctx->f_pt, ctx->mask, y);
+  else
+    k_apply3d_mg<float, TX, TY, TZ, MINB, false><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->f_sol, ctx->f_pt, ctx->mask, y);
+  KCHECK ();
+  return PF_OK;
+}
+
+// y = J_2pt x in FP32; like apply_dev, the halo exchange of x overlaps the interior cell layers
+int
+apply_lowp (pf_ctx *ctx, float *x, float *y)
+{
+  int rc;
+  const Grid &g = ctx->g;
+  const int lo_b = g.cell_begin + (ctx->rank > 0 ? 1 : 0);
+  const int hi_b = g.cell_end - (ctx->rank < ctx->nranks - 1 ? 1 : 0);
+  static const bool no_overlap = getenv ("PF_NO_OVERLAP") != nullptr;
+  const bool overlap = !no_overlap && ctx->nranks > 1 && hi_b > lo_b;
+  if (overlap)
+    {
+      CU (cudaEventRecord (ctx->ev_x, ctx->stream));
+      CU (cudaStreamWaitEvent (ctx->comm_stream, ctx->ev_x, 0));
+      if ((rc = halo_exchange (ctx, x, 4, ctx->comm_stream)))
+        return rc;
+      CU (cudaEventRecord (ctx->ev_halo, ctx->comm_stream));
+    }
+  else if ((rc = halo_exchange (ctx, x, 4)))
+    return rc;
+  const long long nl = g.n_local_nodes;
+  k_apply_init_r<float><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->f_idiag, ctx->mask, y);
+  KCHECK ();
+  auto run = [&](int c0, int c1) -> int {
+    ctx->range_begin = c0;
+    ctx->range_end = c1;
+    const int r = launch_apply3d_mg<16, 4, 1, 8> (ctx, x, y);
+    ctx->range_begin = ctx->range_end = -1;
+    return r;
+  };
+  if (!overlap)
+    return launch_apply3d_mg<16, 4, 1, 8> (ctx, x, y);
+  if ((rc = run (lo_b, hi_b)))
+    return rc;
+  CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
+  if (ctx->rank > 0 && (rc = run (g.cell_begin, lo_b)))
+    return rc;
+  if (ctx->rank < ctx->nranks - 1 && (rc = run (hi_b, g.cell_end)))
+    return rc;
+  return PF_OK;
+}
+
+// float copies of what a level's V-cycle reads; called once per pf_setup_jacobian and level
+int
+mg_lowp_refresh (pf_ctx *ctx)
+{
+  const long long nd = ctx->n_local_dofs, nl = ctx->g.n_local_nodes;
+  if (!ctx->f_b)
+    {
+      float **vecs[] = {&ctx->f_sol, &ctx->f_idiag, &ctx->f_b, &ctx->f_x, &ctx->f_y, &ctx->f_d, &ctx->f_r};
+      for (float **v : vecs)
+        CU (cudaMalloc (v, sizeof (float) * nd));
+      CU (cudaMalloc (&ctx->f_pt, sizeof (float) * nl));
+    }
+  k_convert<double, float><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->sol, ctx->f_sol);
+  KCHECK ();
+  k_convert<double, float><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->pt, ctx->f_pt);
+  KCHECK ();
+  k_convert_inverse<double, float><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->diag, ctx->f_idiag);
+  KCHECK ();
+  return PF_OK;
+}
+
+int
+mg_smooth_lowp (pf_ctx *ctx, const float *b, float *x, bool zero_guess, int degree, double ratio)
+{
+  const long long nd = ctx->n_local_dofs;
+  const double lmax = ctx->lam_max, lmin = lmax / ratio;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  int rc;
+  for (int kk = 0; kk < degree; ++kk)
+    {
+      const bool first = kk == 0;
+      if (!(first && zero_guess))
+        if ((rc = apply_lowp (ctx, x, ctx->f_y)))
+          return rc;
+      double c1 = 0, c2 = 1.0 / theta;
+      if (!first)
+        {
+          const double rho_new = 1.0 / (2.0 * sigma - rho);
+          c1 = rho_new * rho;
+          c2 = 2.0 * rho_new / delta;
+          rho = rho_new;
+        }
+      const int mode = first ? (zero_guess ? 1 : 2) : 0;
+      k_cheb_step_r<float><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, mode, (float) c1, (float) c2, b, ctx->f_y,
+                                                                         ctx->f_idiag, ctx->f_d, x);
+      KCHECK ();
+    }
+  return PF_OK;
+}
+
+int
+mg_vcycle_lowp (pf_ctx *ctx, const float *b, float *x)
+{
+  int rc;
+  pf_ctx *c = ctx->coarse;
+  if (!c)
+    return mg_smooth_lowp (ctx, b, x, true, ctx->coarsest_degree, 100.0);
+  if ((rc = mg_smooth_lowp (ctx, b, x, true, ctx->cheb_degree, ctx->cheb_ratio)))
+    return rc;
+  const long long nd = ctx->n_local_dofs;
+  if ((rc = apply_lowp (ctx, x, ctx->f_y)))
+    return rc;
+  k_sub_r<float><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, b, ctx->f_y, ctx->f_r);
+  KCHECK ();
+  Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}, c->g.plane_begin},
+    df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}, ctx->g.plane_begin};
+  if ((rc = halo_exchange (ctx, ctx->f_r, 4)))
+    return rc;
+  const MgRange res = mg_restrict_range (ctx->mg_mode, ctx->g.owned_begin, ctx->g.owned_end, c->g.owned_begin,
+                                         c->g.owned_end);
+  if (ctx->mg_mode == 2)
+    CU (cudaMemsetAsync (c->f_b, 0, sizeof (float) * c->n_local_dofs, ctx->stream));
+  const long long cnt = (long long) c->g.nodes_per_plane * std::max (res.e - res.a, 0);
+  if (cnt > 0)
+    {
+      k_restrict_r<float><<<nblk (cnt, 128), 128, 0, ctx->stream>>> (dc, df, res.a, res.e, ctx->f_r, ctx->mask, c->mask,
+                                                                    c->f_b);
+      KCHECK ();
+    }
+  if (ctx->mg_mode == 2)
+    NC_ (g_nccl.AllReduce (c->f_b, c->f_b, (size_t) c->n_local_dofs, ncclFloat32, ncclSum, ctx->comm, ctx->stream));
+  if ((rc = mg_vcycle_lowp (c, c->f_b, c->f_x)))
+    return rc;
+  if (c->nranks > 1 && (rc = halo_exchange (c, c->f_x, 4)))
+    return rc;
+  const long long nfine = (long long) ctx->g.nodes_per_plane * (ctx->g.plane_end - ctx->g.plane_begin);
+  k_prolong_add_r<float><<<nblk (nfine, 256), 256, 0, ctx->stream>>> (dc, df, ctx->g.plane_begin, ctx->g.plane_end, c->f_x,
+                                                                     ctx->mask, x);
+  KCHECK ();
+  return mg_smooth_lowp (ctx, b, x, false, ctx->cheb_degree, ctx->cheb_ratio);
+}
+
 // z = M^-1 v
 int
 precond_apply (pf_ctx *ctx, const double *v, double *z)
 {
+  if (ctx->precond == 1 && ctx->mg_ready && ctx->coarse && ctx->mg_fp32 && ctx->f_b)
+    {
+      // FP64 Krylov vector -> FP32 V-cycle -> FP64 (right preconditioning: the outer iteration stays FP64)
+      const long long nd = ctx->n_local_dofs;
+      k_convert<double, float><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, v, ctx->f_b);
+      KCHECK ();
+      const int rc = mg_vcycle_lowp (ctx, ctx->f_b, ctx->f_x);
+      if (rc)
+        return rc;
+      k_convert<float, double><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->f_x, z);
+      KCHECK ();
+      return PF_OK;
+    }
   // Opt-in (PF_MG_GRAPH=1), single rank only.  Measured on B200 at 16.7 M DoF: 9.27 vs 9.26
   // Newton-its/s, i.e. the V-cycle is not launch-bound on one GPU; with NCCL nodes in the graph
   // (2 and 4 ranks) the solve ran but the processes hung at tear-down, so it stays off there.
@@ -1810,6 +2013,9 @@ pf_destroy (pf_ctx *ctx)
     g_nccl.CommDestroy (ctx->comm);
   if (ctx->mg_graph)
     cudaGraphExecDestroy (ctx->mg_graph);
+  for (float *v : {ctx->f_sol, ctx->f_pt, ctx->f_idiag, ctx->f_b, ctx->f_x, ctx->f_y, ctx->f_d, ctx->f_r})
+    if (v)
+      cudaFree (v);
   for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r, ctx->mg_ev, ctx->mg_in})
     if (v)
       cudaFree (v);
@@ -2061,6 +2267,17 @@ pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio
 }
 
 int
+pf_set_multigrid_precision (pf_ctx *ctx, int bits)
+{
+  if (!ctx || (bits != 32 && bits != 64))
+    return PF_BAD_ARG;
+  for (pf_ctx *c = ctx; c; c = c->coarse)
+    c->mg_fp32 = bits == 32;
+  ctx->jac_ready = false; // the float copies are made by pf_setup_jacobian
+  return PF_OK;
+}
+
+int
 pf_set_krylov_dim (pf_ctx *ctx, int m)
 {
   if (!ctx || m < 2 || m > 2000)
@@ -2105,6 +2322,22 @@ pf_apply_jacobian (pf_ctx *ctx, const double *x, double *y)
   if ((rc = apply_dev (ctx, ctx->xa, ctx->ya)))
     return rc;
   return download_block (ctx, ctx->ya, y);
+}
+
+int
+pf_apply_preconditioner (pf_ctx *ctx, const double *v, double *z)
+{
+  if (!ctx || !v || !z)
+    return PF_BAD_ARG;
+  if (!ctx->jac_ready)
+    return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must precede pf_apply_preconditioner");
+  CU (cudaSetDevice (ctx->device));
+  int rc;
+  if ((rc = upload_block (ctx, v, ctx->xa)))
+    return rc;
+  if ((rc = precond_apply (ctx, ctx->xa, ctx->ya)))
+    return rc;
+  return download_block (ctx, ctx->ya, z);
 }
 
 int

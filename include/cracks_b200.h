@@ -197,6 +197,19 @@ int pf_apply_jacobian_dev (pf_ctx *ctx, double *x_dev, double *y_dev);
  * describes the levels).  2-D and forest meshes use Jacobi.  Takes effect at the
  * next pf_setup_jacobian. */
 int pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio);
+/* Precision of the multigrid V-cycle: 64 (default) or 32.  With 32 the smoother
+ * operator, the Chebyshev steps and the grid transfers of every level run in
+ * FP32 on float copies of the linearisation state (made by pf_setup_jacobian);
+ * the Krylov vectors are converted at the preconditioner boundary and the outer
+ * GMRES, the Jacobian apply (pf_apply_jacobian) and all residuals stay FP64, so
+ * converged results are unchanged -- like the ML AMG of cracks.cc:2477-2497, the
+ * preconditioner only influences #LinIts.  Opt-in (also PF_MG_FP32=1 in the
+ * environment at pf_create); takes effect at the next pf_setup_jacobian. */
+int pf_set_multigrid_precision (pf_ctx *ctx, int bits);
+/* z = M^-1 v, one application of the preconditioner pf_solve uses (the vmult of
+ * BlockDiagonalPreconditioner, cracks.cc:2717-2740); host buffers, block layout,
+ * n_dofs doubles each.  pf_setup_jacobian must have been called. */
+int pf_apply_preconditioner (pf_ctx *ctx, const double *v, double *z);
 /* Restart length of GMRES (deal.II's SolverGMRES default keeps 28 basis vectors,
  * cracks.cc:2764; this library's default is 30).  Ill-conditioned small 2-D
  * problems, which the reference hands to a sparse direct solver (2750-2759),

@@ -43,6 +43,10 @@ struct double4
 {
   double x, y, z, w;
 };
+struct alignas (16) float4
+{
+  float x, y, z, w;
+};
 inline double4
 make_double4 (double x, double y, double z, double w)
 {
@@ -71,6 +75,16 @@ atomicAdd (double *p, double v)
 {
   std::atomic_ref<double> a (*p);
   double old = a.load (std::memory_order_relaxed);
+  while (!a.compare_exchange_weak (old, old + v, std::memory_order_relaxed))
+    {
+    }
+  return old;
+}
+inline float
+atomicAdd (float *p, float v)
+{
+  std::atomic_ref<float> a (*p);
+  float old = a.load (std::memory_order_relaxed);
   while (!a.compare_exchange_weak (old, old + v, std::memory_order_relaxed))
     {
     }

@@ -253,6 +253,8 @@ ncclAllReduce (const void *send, void *recv, size_t count, int type, int op, voi
             reduce_into (static_cast<double *> (recv), reinterpret_cast<const double *> (tmp.data ()), count, op);
           else if (type == 5)
             reduce_into (static_cast<uint64_t *> (recv), reinterpret_cast<const uint64_t *> (tmp.data ()), count, op);
+          else if (type == 7)
+            reduce_into (static_cast<float *> (recv), reinterpret_cast<const float *> (tmp.data ()), count, op);
           else if (type == 1)
             reduce_into (static_cast<uint8_t *> (recv), reinterpret_cast<const uint8_t *> (tmp.data ()), count, op);
           else

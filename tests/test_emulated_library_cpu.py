@@ -103,6 +103,40 @@ def test_kat1_first_time_steps_with_multigrid(epf):
     ctx.close()
 
 
+def test_fp32_vcycle_against_fp64(epf):
+    """pf_set_multigrid_precision(32): the V-cycle in float (pf_mg_lowp.cuh: smoother operator, Chebyshev steps,
+    transfers) returns the FP64 V-cycle's vector to single-precision accuracy on a two-level problem, and the
+    KAT-1 time step converges to the same golden energies with (nearly) the same number of GMRES iterations."""
+    pf = epf
+    from cracks_b200.api import mesh_diameter
+    g = json.load(open(os.path.join(HERE, "golden", "sneddon_3d_1.json")))
+    out = {}
+    for bits in (64, 32):
+        mesh = pf.sneddon_mesh(3, 0)
+        ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh, kappa_of_h=lambda hh: 0.0))
+        ctx.set_multigrid_precision(bits)
+        drv = pf.SneddonDriver(ctx, pressure=lambda t: g["prm"]["pressure"], max_no_timesteps=0,
+                               newton_lower_bound=g["prm"]["newton_lower_bound"], max_newton=g["prm"]["newton_max_steps"],
+                               max_line_search=g["prm"]["line_search_max_steps"], gmres_max_it=300)
+        stats = drv.run(mesh_diameter(mesh))
+        # one more V-cycle on a fixed vector, linearised at the converged state
+        ctx.setup_jacobian()
+        v = np.random.default_rng(7).standard_normal(ctx.n_dofs)
+        out[bits] = (stats, drv.lin_its, drv.newton_its, ctx.apply_preconditioner(v))
+        ctx.close()
+    s64, s32 = out[64][0], out[32][0]
+    assert s32[0]["crack"] == pytest.approx(g["statistics"][0]["crack"], rel=1e-8)
+    assert s32[0]["bulk"] == pytest.approx(g["statistics"][0]["bulk"], rel=1e-7)
+    assert s32[0]["bulk"] == pytest.approx(s64[0]["bulk"], rel=1e-7)
+    assert out[32][2] == out[64][2]                                  # same Newton history
+    assert abs(out[32][1] - out[64][1]) <= max(3, out[64][1] // 20)  # the preconditioner is as good
+    z64, z32 = out[64][3], out[32][3]
+    print("GMRES iterations fp64 / fp32:", out[64][1], out[32][1], " |z32 - z64| / |z64| =",
+          np.linalg.norm(z32 - z64) / np.linalg.norm(z64))
+    assert np.linalg.norm(z32 - z64) <= 2e-4 * np.linalg.norm(z64)
+    assert np.linalg.norm(z32 - z64) > 0                            # and really is another code path
+
+
 def test_miehe_shear_small(oracle, epf):
     """Miehe shear with the stress split on the 4 x 4 slit mesh, three time steps, against the oracle's run of the
     same mesh (the golden-sized run is part of the GPU suite; here the point is the library's plumbing)"""

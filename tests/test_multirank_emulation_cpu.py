@@ -29,9 +29,10 @@ def built():
     return so
 
 
-def _run(nranks, n, steps, tmp_path, timeout):
+def _run(nranks, n, steps, tmp_path, timeout, **extra_env):
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(EMU, "fake_nccl") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-    tag = "%d_%s" % (nranks, "x".join(map(str, n)))
+    env.update(extra_env)
+    tag = "%d_%s_%s" % (nranks, "x".join(map(str, n)), "_".join(extra_env.values()))
     id_file, out_file = str(tmp_path / ("id_" + tag)), str(tmp_path / ("out_" + tag + ".json"))
     procs = [subprocess.Popen([sys.executable, os.path.join(EMU, "multirank_worker.py"), str(r), str(nranks), id_file, out_file,
                                *map(str, n), str(steps)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -48,9 +49,25 @@ def _run(nranks, n, steps, tmp_path, timeout):
     return json.load(open(out_file))
 
 
-def test_two_ranks_give_the_single_rank_result(built, tmp_path):
+@pytest.fixture(scope="module")
+def one_rank_8(built, tmp_path_factory):
+    return _run(1, (8, 8, 8), 1, tmp_path_factory.mktemp("one"), 600)
+
+
+def test_two_ranks_with_the_fp32_vcycle(built, one_rank_8, tmp_path):
+    """PF_MG_FP32=1 on two ranks: float halo exchanges of the smoother input, the residual before the restriction
+    and the coarse correction; the converged step is the FP64 single-rank one."""
+    two = _run(2, (8, 8, 8), 1, tmp_path, 600, PF_MG_FP32="1")
+    for a, b in zip(two["statistics"], one_rank_8["statistics"]):
+        assert a["crack"] == pytest.approx(b["crack"], rel=1e-10)
+        assert a["bulk"] == pytest.approx(b["bulk"], rel=1e-7)
+    assert two["newton_its"] == one_rank_8["newton_its"]
+    assert abs(two["linear_its"] - one_rank_8["linear_its"]) <= 0.2 * one_rank_8["linear_its"] + 3
+
+
+def test_two_ranks_give_the_single_rank_result(built, one_rank_8, tmp_path):
     n = (8, 8, 8)
-    one = _run(1, n, 1, tmp_path, 600)
+    one = one_rank_8
     two = _run(2, n, 1, tmp_path, 600)
     # 8 layers on 2 ranks: the 4 x 4 x 4 level keeps the z-slabs (mode 1, 2 layers per rank)
     assert [tuple(L[0]) for L in two["levels"]] == [(8, 8, 8), (4, 4, 4)] and two["levels"][0][2] == 1
@@ -62,10 +79,11 @@ def test_two_ranks_give_the_single_rank_result(built, tmp_path):
 
 
 @pytest.mark.skipif(os.environ.get("PF_SLOW_TESTS") != "1", reason="8 emulated ranks take several minutes: PF_SLOW_TESTS=1")
-def test_eight_ranks_distributed_and_replicated_levels(built, tmp_path):
+@pytest.mark.parametrize("fp32", ["0", "1"])
+def test_eight_ranks_distributed_and_replicated_levels(built, tmp_path, fp32):
     n = (16, 16, 32)
     one = _run(1, n, 1, tmp_path, 3000)
-    eight = _run(8, n, 1, tmp_path, 3000)
+    eight = _run(8, n, 1, tmp_path, 3000, PF_MG_FP32=fp32)
     # 32 layers on 8 ranks: 8 x 8 x 16 keeps the slabs (2 layers per rank), 4 x 4 x 8 is replicated
     assert [(tuple(L[0]), L[1]) for L in eight["levels"]] == [((16, 16, 32), False), ((8, 8, 16), False), ((4, 4, 8), True)]
     for a, b in zip(eight["statistics"], one["statistics"]):

@@ -14,14 +14,25 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_forest_device_path_first_gpu_run(pf):
+def _first_run(test_file, cap):
     env = dict(os.environ, PF_EXPERIMENTAL="1")
     try:
-        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_forest_experimental.py"),
-                            "-q", "-rA", "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", test_file),
+                            "-q", "-rA", "-s", "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=cap, env=env,
+                           cwd=ROOT)
         out, rc = r.stdout[-4000:] + r.stderr[-1500:], r.returncode
     except subprocess.TimeoutExpired as exc:
-        out, rc = "TIMEOUT after 600 s\n" + str(exc.stdout)[-2000:], -1
+        out, rc = "TIMEOUT after %d s\n" % cap + str(exc.stdout)[-2000:], -1
     print(out)
-    if rc != 0:
+    return rc
+
+
+def test_forest_device_path_first_gpu_run(pf):
+    if _first_run("test_gpu_forest_experimental.py", 600) != 0:
         pytest.xfail("forest device path failed on its first GPU run (non-gating, see the captured output)")
+
+
+def test_fp32_vcycle_first_gpu_run(pf):
+    """same arrangement for the FP32 V-cycle (pf_mg_lowp.cuh, opt-in at run time)"""
+    if _first_run("test_gpu_fp32_vcycle_experimental.py", 300) != 0:
+        pytest.xfail("FP32 V-cycle failed on its first GPU run (non-gating, see the captured output)")

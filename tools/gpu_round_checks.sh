@@ -26,6 +26,18 @@ for s in $steps; do
       for v in 16 17 18; do
         echo "variant $v"; timeout 300 python bench.py --variant $v --steps 50 --warmup 10 --no-cpu-baseline --no-newton --e2e-steps 1 | cut -c1-330
       done ;;
+    fp32)         # A/B of the multigrid V-cycle precision (pf_mg_lowp.cuh, written in round 1 without a GPU):
+                  # Newton-its/s and #LinIts with the FP64 and the FP32 V-cycle; same energies expected
+      for f in 0 1; do
+        echo "PF_MG_FP32=$f"; PF_MG_FP32=$f timeout 180 python tools/newton_bench.py --refine 4 --steps 2 --quiet | cut -c1-600
+      done
+      if [ "$N" -ge 2 ]; then
+        for f in 0 1; do
+          echo "PF_MG_FP32=$f, 2 ranks"
+          PF_MG_FP32=$f timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+            --master-port 29618 tools/newton_bench.py --refine 4 --steps 2 --quiet | cut -c1-600
+        done
+      fi ;;
     graph)        # PF_MG_GRAPH=1: V-cycle as a CUDA graph; hung at tear-down with NCCL nodes (2 ranks) in round 1
       PF_MG_GRAPH=1 timeout 120 python tools/newton_bench.py --refine 4 --steps 2 --quiet | cut -c1-300 ;;
     ncu)          # full capture of the default apply kernel (full grid, deterministic launch index)
