@@ -113,6 +113,7 @@ struct pf_ctx
   cudaEvent_t ev_up[8] = {}, ev_done[8] = {};
   double *stage2 = nullptr;
   int range_begin = -1, range_end = -1; // cell-layer sub-range override for the tiled apply (halo overlap)
+  int range_stride = 1;                 // > 1: only the layers range_begin and range_end - 1 (Grid::layer_stride)
   ncclComm_t comm = nullptr;
   long long n_local_dofs = 0, owned_lo = 0, owned_hi = 0; // node ranges (local indices)
   // device state
@@ -482,6 +483,8 @@ launch_apply3d (pf_ctx *ctx, const double *x, double *y)
 }
 
 int g_no_iso = 0;
+// A/B switch: evaluate the two boundary layers of a middle slab in two launches (as before) instead of one
+const bool g_split_boundary = getenv ("PF_SPLIT_BOUNDARY") != nullptr;
 
 template <int TX, int TY, int TZ, int MINB = 2, int NQ = 3>
 int
@@ -493,9 +496,10 @@ launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
     {
       g.cell_begin = ctx->range_begin;
       g.cell_end = ctx->range_end;
+      g.layer_stride = ctx->range_stride;
     }
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
-  const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
   static bool attr_set = false;
   if (!attr_set)
     {
@@ -531,9 +535,10 @@ launch_apply3d_v4 (pf_ctx *ctx, const double *x, double *y)
     {
       g.cell_begin = ctx->range_begin;
       g.cell_end = ctx->range_end;
+      g.layer_stride = ctx->range_stride;
     }
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
-  const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
   static bool attr_set = false;
   if (!attr_set)
     {
@@ -771,20 +776,31 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
             }
           if (overlap)
             {
-              auto run = [&](int c0, int c1) -> int {
+              auto run = [&](int c0, int c1, int stride = 1) -> int {
                 ctx->range_begin = c0;
                 ctx->range_end = c1;
+                ctx->range_stride = stride;
                 const int r = launch_tiled_default (ctx, x, y, approx);
                 ctx->range_begin = ctx->range_end = -1;
+                ctx->range_stride = 1;
                 return r;
               };
               if ((rc = run (lo_b, hi_b)))
                 return rc;
               CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
-              if (ctx->rank > 0 && (rc = run (g.cell_begin, lo_b)))
-                return rc;
-              if (ctx->rank < ctx->nranks - 1 && (rc = run (hi_b, g.cell_end)))
-                return rc;
+              if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !g_split_boundary)
+                {
+                  // a slab in the middle: its two boundary layers in ONE launch (each alone is less than a wave)
+                  if ((rc = run (g.cell_begin, g.cell_end, g.cell_end - 1 - g.cell_begin)))
+                    return rc;
+                }
+              else
+                {
+                  if (ctx->rank > 0 && (rc = run (g.cell_begin, lo_b)))
+                    return rc;
+                  if (ctx->rank < ctx->nranks - 1 && (rc = run (hi_b, g.cell_end)))
+                    return rc;
+                }
               if (ctx->profiling)
                 {
                   CU (cudaEventRecord (e1, ctx->stream));
@@ -1232,9 +1248,10 @@ launch_apply3d_mg (pf_ctx *ctx, const float *x, float *y)
     {
       g.cell_begin = ctx->range_begin;
       g.cell_end = ctx->range_end;
+      g.layer_stride = ctx->range_stride;
     }
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
-  const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
   const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
   const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
   if (iso)
@@ -1270,11 +1287,13 @@ apply_lowp (pf_ctx *ctx, float *x, float *y)
   const long long nl = g.n_local_nodes;
   k_apply_init_r<float><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->f_idiag, ctx->mask, y);
   KCHECK ();
-  auto run = [&](int c0, int c1) -> int {
+  auto run = [&](int c0, int c1, int stride = 1) -> int {
     ctx->range_begin = c0;
     ctx->range_end = c1;
+    ctx->range_stride = stride;
     const int r = launch_apply3d_mg<16, 4, 1, 8> (ctx, x, y);
     ctx->range_begin = ctx->range_end = -1;
+    ctx->range_stride = 1;
     return r;
   };
   if (!overlap)
@@ -1282,6 +1301,8 @@ apply_lowp (pf_ctx *ctx, float *x, float *y)
   if ((rc = run (lo_b, hi_b)))
     return rc;
   CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
+  if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !g_split_boundary)
+    return run (g.cell_begin, g.cell_end, g.cell_end - 1 - g.cell_begin);
   if (ctx->rank > 0 && (rc = run (g.cell_begin, lo_b)))
     return rc;
   if (ctx->rank < ctx->nranks - 1 && (rc = run (hi_b, g.cell_end)))

@@ -22,6 +22,9 @@ struct Grid
   int owned_end;
   int cell_begin;  // cell layers [cell_begin, cell_end) evaluated by this rank
   int cell_end;
+  // tiled 3-D kernels with TZ == 1: tile layer b covers cell layer cell_begin + b * layer_stride.  A stride
+  // of cell_end - 1 - cell_begin with two tile layers evaluates the two boundary layers of a slab in one launch.
+  int layer_stride = 1;
   long long nodes_per_plane;
   long long n_local_nodes;
   long long n_local_cells;

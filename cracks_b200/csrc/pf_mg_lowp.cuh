@@ -55,7 +55,7 @@ k_apply3d_mg (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, const R *__restric
   b /= tiles_x;
   const int by = b % tiles_y;
   const int bz = b / tiles_y;
-  const int cx0 = bx * TX, cy0 = by * TY, cz0 = g.cell_begin + bz * TZ;
+  const int cx0 = bx * TX, cy0 = by * TY, cz0 = g.cell_begin + bz * TZ * g.layer_stride;
   const int nnx = g.nn[0], nny = g.nn[1];
   const int lz_off = g.plane_begin;
   const long long pstride = g.nodes_per_plane;

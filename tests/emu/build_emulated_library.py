@@ -5,7 +5,8 @@ compiled for the CPU against tests/emu/cuda_shim_full/cuda_runtime.h (TEST INFRA
 The sources are copied to tests/emu/_gen/ with three mechanical rewrites, nothing else:
   1. `kernel<<<grid, block, smem, stream>>> (args);`  ->  `pf_emu::launch (coop, (kernel), grid, block, smem, stream, args);`
      where coop says whether the kernel uses barriers / shared memory / shuffles (COOPERATIVE below);
-  2. `extern __shared__` -> `extern` (the dynamic shared-memory array is one global buffer, emu_runtime.cc);
+  2. `extern __shared__` -> `extern thread_local` (the dynamic shared-memory array is one buffer per OS thread,
+     i.e. per running block, emu_runtime.cc);
   3. the block reductions of pf_vector.cuh go through shared memory instead of warp shuffles (speed);
   4. the TMA variant (pf_apply3d_v3.cuh: inline PTX, CUtensorMap) is cut out and its launcher returns
      PF_UNSUPPORTED; the reduction grid is shrunk (RED_BLOCKS x RED_THREADS = 3 x 32) because every CUDA
@@ -93,14 +94,14 @@ def generate():
         if not name.endswith((".cu", ".cuh")) or name == "pf_apply3d_v3.cuh":
             continue
         text = open(os.path.join(SRC, name)).read()
-        text = text.replace("extern __shared__", "extern")
+        text = text.replace("extern __shared__", "extern thread_local")
         if name == "pf_vector.cuh":
             # the warp-shuffle stage of the block reductions costs ten block barriers per call when every
             # CUDA thread is an OS thread: here the reduction goes through shared memory instead (two barriers)
             for op, init, comb in (("sum", "0", "s += slots[i]"), ("max", "slots[0]", "s = fmax (s, slots[i])")):
                 a = text.index(f"block_reduce_{op} (double v, double *sh")
                 b = text.index("\n}\n", a) + 3
-                body = (f"block_reduce_{op} (double v, double *sh)\n{{\n  static double slots[1024];\n  (void) sh;\n"
+                body = (f"block_reduce_{op} (double v, double *sh)\n{{\n  static thread_local double slots[1024];\n  (void) sh;\n"
                         f"  slots[threadIdx.x] = v;\n  __syncthreads ();\n  double s = {init};\n  if (threadIdx.x == 0)\n"
                         f"    for (unsigned i = {'0' if op == 'sum' else '1'}; i < blockDim.x; ++i)\n      {comb};\n"
                         f"  __syncthreads ();\n  return s;\n}}\n")
@@ -124,7 +125,7 @@ def generate():
 def build():
     generate()
     so = os.path.join(HERE, "libcracks_b200_emu.so")
-    cmd = ["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-x", "c++", "-I", os.path.join(HERE, "cuda_shim_full"),
+    cmd = ["g++", "-O1", "-g", "-fno-extern-tls-init", "-std=c++20", "-fPIC", "-shared", "-pthread", "-x", "c++", "-I", os.path.join(HERE, "cuda_shim_full"),
            "-o", so, os.path.join(GEN, "pf_api.cu"), os.path.join(HERE, "emu_runtime.cc"), "-ldl"]
     subprocess.check_call(cmd)
     return so

@@ -1,14 +1,14 @@
 // cuda_runtime.h -- TEST SHIM (full): enough of the CUDA runtime API and of the device-side vocabulary
 // for g++ to compile a pre-processed copy of cracks_b200/csrc/pf_api.cu (tests/emu/build_emulated_library.py
 // rewrites the <<<...>>> launches into pf_emu::launch calls) and run the WHOLE library on the CPU:
-// "device" memory is host memory, streams and events are no-ops, a kernel launch executes its blocks one
-// after the other -- sequentially thread by thread for thread-per-item kernels, with one OS thread per CUDA
-// thread, a std::barrier for __syncthreads / __syncwarp / warp shuffles and std::atomic_ref for atomicAdd for
-// the cooperative ones.  Test infrastructure only (tests/test_emulated_library_cpu.py): it is a checker of
+// "device" memory is host memory, streams and events are no-ops, a kernel launch hands its blocks to a small
+// pool of OS threads.  Inside a block the CUDA threads run one after the other -- as plain calls for
+// thread-per-item kernels, as fibers (ucontext) that yield at __syncthreads / __syncwarp / warp shuffles for the
+// cooperative ones; shared memory is thread_local storage of the OS thread that runs the block, atomicAdd is
+// std::atomic_ref (blocks run concurrently).  Test infrastructure only (tests/test_emulated_library_cpu.py): it is a checker of
 // the library's host logic and kernel sources, never a fallback -- nothing under cracks_b200/ refers to it.
 #pragma once
 #include <atomic>
-#include <barrier>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -23,7 +23,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 #define __align__(n)
 #define __grid_constant__
 
@@ -57,17 +57,9 @@ extern thread_local uint3 threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
 
 namespace pf_emu {
-extern std::barrier<> *block_barrier; // null while a kernel runs in sequential mode
-extern double shfl_slots[1024];
+extern thread_local double shfl_slots[1024];
 [[noreturn]] void fail (const char *what);
-inline void
-sync ()
-{
-  if (!block_barrier)
-    fail ("a kernel launched in sequential mode reached a barrier / shuffle: add it to COOPERATIVE in "
-          "tests/emu/build_emulated_library.py");
-  block_barrier->arrive_and_wait ();
-}
+void sync (); // block barrier: the running fiber yields until every thread of the block has arrived
 } // namespace pf_emu
 
 inline double
@@ -275,65 +267,44 @@ inline cudaError_t cudaGraphExecDestroy (cudaGraphExec_t) { return cudaSuccess; 
 namespace pf_emu {
 extern long long launches_sequential, launches_cooperative;
 
-// persistent workers, one set per block size: a cooperative launch hands every block to the same OS
-// threads instead of spawning blockDim threads per block
-struct Pool
-{
-  explicit Pool (unsigned n);
-  ~Pool ();
-  void run_block (void (*trampoline) (void *, unsigned), void *job);
-  unsigned n;
-  std::barrier<> start, done, inner;
-  std::vector<std::thread> workers;
-  void (*fn) (void *, unsigned) = nullptr;
-  void *job = nullptr;
-  bool stop = false;
-};
-Pool &pool_for (unsigned block);
+// one block: run `body (job, t)` for t = 0 .. block-1 on the calling OS thread; cooperative blocks as fibers
+void run_block (bool cooperative, unsigned block, void (*body) (void *, unsigned), void *job);
+// all blocks of a launch on the worker pool; returns when the last one has finished
+void run_grid (unsigned grid, unsigned block, void (*per_block) (void *, unsigned), void *job);
 
 template <class K, class... A>
 void
 launch (bool cooperative, K kernel, unsigned grid, unsigned block, size_t /*smem*/, cudaStream_t, A... args)
 {
-  if (!cooperative)
-    {
-      ++launches_sequential;
-      block_barrier = nullptr;
-      gridDim.x = grid;
-      blockDim.x = block;
-      for (unsigned b = 0; b < grid; ++b)
-        for (unsigned t = 0; t < block; ++t)
-          {
-            blockIdx.x = b;
-            threadIdx.x = t;
-            kernel (args...);
-          }
-      return;
-    }
-  ++launches_cooperative;
   if (block > 1024)
     fail ("block too large for the emulation");
-  Pool &pool = pool_for (block);
-  block_barrier = &pool.inner;
+  ++(cooperative ? launches_cooperative : launches_sequential);
   struct Job
   {
-    unsigned grid, block, b;
+    unsigned grid, block;
+    bool cooperative;
     decltype (std::make_tuple (args...)) a;
     K k;
-  } job{grid, block, 0, std::make_tuple (args...), kernel};
-  auto trampoline = [](void *p, unsigned t) {
-    Job &j = *static_cast<Job *> (p);
-    gridDim.x = j.grid;
-    blockDim.x = j.block;
-    blockIdx.x = j.b;
-    threadIdx.x = t;
-    std::apply (j.k, j.a);
+  } job{grid, block, cooperative, std::make_tuple (args...), kernel};
+  struct BlockJob
+  {
+    Job *j;
+    unsigned b;
   };
-  for (unsigned b = 0; b < grid; ++b)
-    {
-      job.b = b;
-      pool.run_block (trampoline, &job);
-    }
-  block_barrier = nullptr;
+  auto per_block = [](void *p, unsigned b) {
+    Job &j = *static_cast<Job *> (p);
+    BlockJob bj{&j, b};
+    run_block (j.cooperative, j.block,
+               [](void *q, unsigned t) {
+                 BlockJob &x = *static_cast<BlockJob *> (q);
+                 gridDim.x = x.j->grid;
+                 blockDim.x = x.j->block;
+                 blockIdx.x = x.b;
+                 threadIdx.x = t;
+                 std::apply (x.j->k, x.j->a);
+               },
+               &bj);
+  };
+  run_grid (grid, block, per_block, &job);
 }
 } // namespace pf_emu

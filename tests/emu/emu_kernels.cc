@@ -89,8 +89,7 @@ template <int DIM>
 static Grid
 make_grid (const EmuForest &f)
 {
-  Grid g;
-  std::memset (&g, 0, sizeof g);
+  Grid g{};
   g.dim = DIM;
   g.n[0] = (int) f.n_cells;
   g.n[1] = g.n[2] = 1;
@@ -169,8 +168,7 @@ emu_box2d (const int *n, const double *h, int slit, const double *phys /* lambda
            d_rhs, d_mat */, const double *sol, const double *pt, const unsigned char *mask, const double *x,
            double *r_total, double *diag, double *y, double *mass)
 {
-  Grid g;
-  std::memset (&g, 0, sizeof g);
+  Grid g{};
   g.dim = 2;
   g.nodes_per_plane = 1;
   g.n_global_nodes = 1;

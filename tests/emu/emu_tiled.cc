@@ -48,8 +48,7 @@ launch_blocks (K kernel, unsigned grid, unsigned block, A... args)
 static Grid
 box_grid (const int *n, const double *h)
 {
-  Grid g;
-  std::memset (&g, 0, sizeof g);
+  Grid g{};
   g.dim = 3;
   g.nodes_per_plane = 1;
   g.n_global_nodes = 1;

@@ -65,6 +65,25 @@ def test_two_ranks_with_the_fp32_vcycle(built, one_rank_8, tmp_path):
     assert abs(two["linear_its"] - one_rank_8["linear_its"]) <= 0.2 * one_rank_8["linear_its"] + 3
 
 
+@pytest.fixture(scope="module")
+def one_rank_12(built, tmp_path_factory):
+    return _run(1, (8, 8, 12), 1, tmp_path_factory.mktemp("one12"), 900)
+
+
+@pytest.mark.parametrize("fp32", ["0", "1"])
+def test_four_ranks_middle_slabs(built, one_rank_12, tmp_path, fp32):
+    """12 cell layers on 4 ranks: ranks 1 and 2 own slabs with a neighbour on both sides, whose two boundary
+    layers are evaluated by ONE strided launch after the halo exchange (Grid::layer_stride) while the interior
+    layer overlaps it; the 4 x 4 x 6 level is replicated."""
+    four = _run(4, (8, 8, 12), 1, tmp_path, 900, PF_MG_FP32=fp32)
+    assert [(tuple(L[0]), L[1]) for L in four["levels"]] == [((8, 8, 12), False), ((4, 4, 6), True)]
+    for a, b in zip(four["statistics"], one_rank_12["statistics"]):
+        assert a["crack"] == pytest.approx(b["crack"], rel=1e-10)
+        assert a["bulk"] == pytest.approx(b["bulk"], rel=1e-7)
+    assert four["newton_its"] == one_rank_12["newton_its"]
+    assert abs(four["linear_its"] - one_rank_12["linear_its"]) <= 0.2 * one_rank_12["linear_its"] + 3
+
+
 def test_two_ranks_give_the_single_rank_result(built, one_rank_8, tmp_path):
     n = (8, 8, 8)
     one = one_rank_8
@@ -78,12 +97,16 @@ def test_two_ranks_give_the_single_rank_result(built, one_rank_8, tmp_path):
     assert abs(two["linear_its"] - one["linear_its"]) <= 0.2 * one["linear_its"] + 3
 
 
-@pytest.mark.skipif(os.environ.get("PF_SLOW_TESTS") != "1", reason="8 emulated ranks take several minutes: PF_SLOW_TESTS=1")
+@pytest.fixture(scope="module")
+def one_rank_32(built, tmp_path_factory):
+    return _run(1, (16, 16, 32), 1, tmp_path_factory.mktemp("one32"), 3000)
+
+
 @pytest.mark.parametrize("fp32", ["0", "1"])
-def test_eight_ranks_distributed_and_replicated_levels(built, tmp_path, fp32):
+def test_eight_ranks_distributed_and_replicated_levels(built, one_rank_32, tmp_path, fp32):
     n = (16, 16, 32)
-    one = _run(1, n, 1, tmp_path, 3000)
-    eight = _run(8, n, 1, tmp_path, 3000, PF_MG_FP32=fp32)
+    one = one_rank_32
+    eight = _run(8, n, 1, tmp_path, 3000, PF_MG_FP32=fp32, PF_EMU_THREADS="2")
     # 32 layers on 8 ranks: 8 x 8 x 16 keeps the slabs (2 layers per rank), 4 x 4 x 8 is replicated
     assert [(tuple(L[0]), L[1]) for L in eight["levels"]] == [((16, 16, 32), False), ((8, 8, 16), False), ((4, 4, 8), True)]
     for a, b in zip(eight["statistics"], one["statistics"]):
