@@ -110,7 +110,7 @@ struct pf_ctx
   cudaStream_t stream = nullptr, comm_stream = nullptr;
   cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-  cudaEvent_t ev_up[8] = {}, ev_done[8] = {};
+  cudaEvent_t ev_up[32] = {}, ev_done[32] = {};
   double *stage2 = nullptr;
   int range_begin = -1, range_end = -1; // cell-layer sub-range override for the tiled apply (halo overlap)
   int range_stride = 1;                 // > 1: only the layers range_begin and range_end - 1 (Grid::layer_stride)
@@ -1525,12 +1525,16 @@ apply_host_pipelined (pf_ctx *ctx, const double *xh, double *yh)
   const Grid &g = ctx->g;
   const long long npp = g.nodes_per_plane, nn = g.n_global_nodes;
   const int layers = g.n[2];
-  const int n_chunks = std::min (8, layers / 2);
+  // chunks of >= 2 cell layers; the first upload and the last download are not overlapped, so their share
+  // (1 / n_chunks each) is what the pipeline cannot hide.  Measured with 8 (3.75 ms at 16.7 M DoF, PCIe-bound);
+  // 16 is the default since (PF_E2E_CHUNKS for the A/B)
+  static const int max_chunks = std::max (1, std::min (32, getenv ("PF_E2E_CHUNKS") ? atoi (getenv ("PF_E2E_CHUNKS")) : 16));
+  const int n_chunks = std::max (1, std::min (max_chunks, layers / 2));
   if (!ctx->h2d_stream)
     {
       CU (cudaStreamCreateWithFlags (&ctx->h2d_stream, cudaStreamNonBlocking));
       CU (cudaStreamCreateWithFlags (&ctx->d2h_stream, cudaStreamNonBlocking));
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 32; ++i)
         {
           CU (cudaEventCreateWithFlags (&ctx->ev_up[i], cudaEventDisableTiming));
           CU (cudaEventCreateWithFlags (&ctx->ev_done[i], cudaEventDisableTiming));
@@ -2060,7 +2064,7 @@ pf_destroy (pf_ctx *ctx)
     {
       cudaStreamDestroy (ctx->h2d_stream);
       cudaStreamDestroy (ctx->d2h_stream);
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 32; ++i)
         {
           cudaEventDestroy (ctx->ev_up[i]);
           cudaEventDestroy (ctx->ev_done[i]);

@@ -85,6 +85,40 @@ def test_apply_residual_diag_3d(oracle, epf):
     ctx.close()
 
 
+@pytest.mark.parametrize("nz", [16, 45])
+def test_host_buffer_apply_pipeline(oracle, epf, nz):
+    """pf_apply_jacobian with n[2] >= 16 takes the three-stream pipeline over chunks of cell layers (upload,
+    permute + operator on a layer range, download of the finished planes): 8 chunks of 2 layers / 16 ragged
+    chunks of 2-3 layers, against the oracle."""
+    pf = epf
+    n, h = (5, 4, nz), (0.5, 0.5, 0.5)
+    rng = np.random.default_rng(5)
+    lo = tuple(-0.5 * n[d] * h[d] for d in range(3)); hi = tuple(0.5 * n[d] * h[d] for d in range(3))
+    prob = oracle.Problem(3, n, lo, hi, kappa_of_h=lambda hh: 1e-3, eps_of_h=lambda hh: 2.0 * hh, pressure=1e-3)
+    nn = prob.n_nodes
+    sol = np.zeros((nn, 4)); sol[:, :3] = 1e-2 * rng.standard_normal((nn, 3)); sol[:, 3] = rng.random(nn)
+    sol = sol.reshape(-1)
+    prob.prm.dt_old, prob.prm.dt_oldold = 1.0, 1.0
+    con = prob.dirichlet_mask().reshape(nn, 4); con[rng.random(nn) < 0.2, 3] = 1
+    con = np.ascontiguousarray(con.reshape(-1))
+    mesh = pf.Mesh(); mesh.dim = 3
+    for d in range(3):
+        mesh.n[d], mesh.h[d], mesh.origin[d] = n[d], h[d], lo[d]
+    ctx = pf.PhaseFieldContext(mesh, pf.Params(prob.prm.lam, prob.prm.mu, prob.prm.G_c, prob.prm.kappa, prob.prm.eps, 0.0))
+    blk = ctx.to_block(sol)
+    ctx.set_state(blk, blk, blk, 1.0, 1.0, False, prob.pressure)
+    cb = ctx.to_block(con).astype(np.uint8)
+    ctx.set_constraints(cb, cb)
+    ctx.set_preconditioner(0, 2, 20.0)
+    ctx.setup_jacobian()
+    for _ in range(2):                                              # twice: the staging buffers are reused
+        x = rng.standard_normal(prob.n_dofs)
+        y = np.zeros(prob.n_dofs)
+        ctx.vmult(y, ctx.to_block(x))
+        assert _relerr(ctx.to_nodal(y), prob.apply_jacobian(sol, sol, sol, con, x)) <= 1e-12
+    ctx.close()
+
+
 def test_kat1_first_time_steps_with_multigrid(epf):
     """sneddon_3d_1 golden through SneddonDriver: active-set Newton, GMRES, the multigrid V-cycle (10^3 -> 5^3)"""
     pf = epf

@@ -26,6 +26,10 @@ for s in $steps; do
       for v in 16 17 18; do
         echo "variant $v"; timeout 300 python bench.py --variant $v --steps 50 --warmup 10 --no-cpu-baseline --no-newton --e2e-steps 1 | cut -c1-330
       done ;;
+    chunks)       # host-buffer apply (the e2e number): chunks of the H2D / apply / D2H pipeline, 8 was measured (3.75 ms)
+      for c in 8 16 32; do
+        echo "PF_E2E_CHUNKS=$c"; PF_E2E_CHUNKS=$c timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-newton | cut -c1-400
+      done ;;
     fp32)         # A/B of the multigrid V-cycle precision (pf_mg_lowp.cuh, written in round 1 without a GPU):
                   # Newton-its/s and #LinIts with the FP64 and the FP32 V-cycle; same energies expected
       for f in 0 1; do
