@@ -22,6 +22,7 @@
 #include "pf_apply3d_v2.cuh"
 #include "pf_apply3d_v3.cuh"
 #include "pf_apply3d_v4.cuh"
+#include "pf_apply3d_v5.cuh"
 #include "pf_common.cuh"
 #include "pf_forest.cuh"
 #include "pf_generic.cuh"
@@ -568,6 +569,82 @@ launch_apply3d_v4 (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
+// v4 under an explicit register cap (k_apply3d_v4_maxr)
+template <int TX, int TY, int TZ, int MAXR>
+int
+launch_apply3d_v4_maxr (pf_ctx *ctx, const double *x, double *y)
+{
+  using T = Tile3v4<TX, TY, TZ>;
+  Grid g = ctx->g;
+  if (ctx->range_begin >= 0)
+    {
+      g.cell_begin = ctx->range_begin;
+      g.cell_end = ctx->range_end;
+      g.layer_stride = ctx->range_stride;
+    }
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+  const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  static bool attr_set = false;
+  if (!attr_set)
+    {
+      CU (cudaFuncSetAttribute (k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes));
+      CU (cudaFuncSetAttribute (k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes));
+      CU (cudaFuncSetAttribute (k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU (cudaFuncSetAttribute (k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      attr_set = true;
+    }
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
+  if (iso)
+    k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  else
+    k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, false><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  KCHECK ();
+  return PF_OK;
+}
+
+// v5 = v4 with the y-collapse staged in shared memory (54 KB per CTA: needs the largest carve-out for 4 CTAs / SM)
+template <int TX, int TY, int TZ, int MINB = 2>
+int
+launch_apply3d_v5 (pf_ctx *ctx, const double *x, double *y)
+{
+  using T = Tile3v5<TX, TY, TZ>;
+  Grid g = ctx->g;
+  if (ctx->range_begin >= 0)
+    {
+      g.cell_begin = ctx->range_begin;
+      g.cell_end = ctx->range_end;
+      g.layer_stride = ctx->range_stride;
+    }
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+  const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
+  static bool attr_set = false;
+  if (!attr_set)
+    {
+      CU (cudaFuncSetAttribute (k_apply3d_v5<TX, TY, TZ, MINB, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes));
+      CU (cudaFuncSetAttribute (k_apply3d_v5<TX, TY, TZ, MINB, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes));
+      CU (cudaFuncSetAttribute (k_apply3d_v5<TX, TY, TZ, MINB, 3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU (cudaFuncSetAttribute (k_apply3d_v5<TX, TY, TZ, MINB, 3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      attr_set = true;
+    }
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
+  if (iso)
+    k_apply3d_v5<TX, TY, TZ, MINB, 3, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  else
+    k_apply3d_v5<TX, TY, TZ, MINB, 3, false><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+  KCHECK ();
+  return PF_OK;
+}
+
 // the tiled kernel the library uses by default (exact 27-point rule, or the
 // 2-point rule of the preconditioner-only operator)
 int
@@ -836,6 +913,11 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
             // (vs 222 registers, no spills, 8 warps per SM); prepared offline, to be measured
             case 17: rc = launch_apply3d_v4<16, 4, 1, 6> (ctx, x, y); break;
             case 18: rc = launch_apply3d_v4<16, 4, 1, 5> (ctx, x, y); break;
+            // v5: y-collapse of the plane arrays staged in shared memory (-11 % FP64 instructions), to be measured
+            case 19: rc = launch_apply3d_v5<16, 4, 1> (ctx, x, y); break;
+            // v4 capped at exactly 200 / 184 registers (5 CTAs = 10 warps per SM), to be measured
+            case 20: rc = launch_apply3d_v4_maxr<16, 4, 1, 200> (ctx, x, y); break;
+            case 21: rc = launch_apply3d_v4_maxr<16, 4, 1, 184> (ctx, x, y); break;
             default: rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y); break; // variant 16: fastest measured
             }
           if (rc)
@@ -3098,7 +3180,7 @@ pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count)
 int
 pf_debug_set_variant (int variant)
 {
-  if (variant < 1 || variant > 18)
+  if (variant < 1 || variant > 21)
     return PF_BAD_ARG;
   g_apply_variant = variant;
   return PF_OK;

@@ -1,31 +1,22 @@
-// pf_apply3d_v4.cuh -- third tuning step of the hot kernel (same mapping as
-// pf_apply3d_v2.cuh: staged z-collapsed node columns, one thread per cell,
-// plane -> row -> point walk, transposed collapse into a shared y tile).
-// What changes is the FP64 instruction count per cell (the binding resource,
-// DESIGN.md 5.1):
-//   * the strain only enters through its symmetric part, so the off-diagonal
-//     sums G01+G10, G02+G20, G12+G21 (and the same for the state U) are formed
-//     from row-level combinations with ONE fma per point instead of two fmas
-//     and an add;
-//   * cubic cells, 3-point rule: the constant-coefficient term
-//     G_c eps grad(dphi).grad(psi) (cracks.cc:2378) is a polynomial that the
-//     Gauss rule integrates exactly, so it is applied in closed form: in the
-//     sum/difference (Walsh-Hadamard) basis of the 8 cell nodes the Q1
-//     Laplacian is diagonal (1-D mass: h/4, h/12; 1-D stiffness: 0, 1/h), the
-//     8 coefficients are by-products of the centre row of the centre plane and
-//     the result joins the plane accumulators there.  The phi-gradient leaves
-//     the 27-point loop altogether.  Differences to the quadrature are
-//     round-off (parity tests: 1e-12).
+// pf_apply3d_v5.cuh -- v4 with the y-collapse of the plane arrays staged in shared memory.
+//
+// In v4 every cell thread forms, per Gauss row and field, b = (a00 + a01) + ey (a01 - a00) for BOTH of its
+// node columns (4 loads, 6 FP64 instructions per field and row) although the right column of a cell is the
+// left column of its x-neighbour.  Here the CTA computes that collapse once per (x-node, cell row) and plane
+// into BY[f][qy] / DY[f] (one extra cooperative stage and barrier per plane, 18.5 KB more shared memory), and a
+// row only reads its two columns: 46 instead of 100 FP64 instructions per row, about 11 % of the kernel's
+// FP64 work (the binding resource).  Everything else is v4.  Prepared without a GPU at hand:
+// variant 19 of PF_APPLY_VARIANT, checked against the oracle on the CPU emulation, to be timed.
 #pragma once
-#include "pf_apply3d_v2.cuh"
+#include "pf_apply3d_v4.cuh"
 
 namespace pf {
 
-template <int TX, int TY, int TZ> struct Tile3v4 : Tile3v2<TX, TY, TZ>
+template <int TX, int TY, int TZ> struct Tile3v5 : Tile3v4<TX, TY, TZ>
 {
-  using B = Tile3v2<TX, TY, TZ>;
-  // + BR[NXC]: y-difference of the z-difference of the phi column of x (closed-form Laplacian)
-  static constexpr size_t smem_doubles = B::smem_doubles + B::NXC;
+  using B4 = Tile3v4<TX, TY, TZ>;
+  // + BY[9][3][NXC] (y-collapsed values of one plane) + DY[7][NXC] (their y-differences)
+  static constexpr size_t smem_doubles = B4::smem_doubles + (size_t) 34 * B4::NXC;
   static constexpr size_t smem_bytes = smem_doubles * sizeof (double);
 };
 
@@ -35,10 +26,12 @@ template <int TX, int TY, int TZ> struct Tile3v4 : Tile3v2<TX, TY, TZ>
 // must be called by all threads of the CTA.
 template <int TX, int TY, int TZ, int NQ = 3, bool ISO = false>
 __device__ __forceinline__ void
-tile_cells_v4 (const Grid &g, const Phys &p, const K3 &k, const int tid, const int cx0, const int cy0,
+tile_cells_v5 (const Grid &g, const Phys &p, const K3 &k, const int tid, const int cx0, const int cy0,
                const int cz0, const double *__restrict__ AZ, const double *__restrict__ BZ,
-               const double *__restrict__ BR, double *__restrict__ ys)
+               const double *__restrict__ BR, double *__restrict__ BY, double *__restrict__ DY,
+               double *__restrict__ ys)
 {
+  constexpr int NT5 = TX * TY * TZ;
   using T = Tile3v2<TX, TY, TZ>;
   constexpr int NN = T::NN, NX = T::NX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC;
   constexpr bool CEN = (NQ == 3); // the 3-point rule has a centre point (xi = 0), the 2-point rule has not
@@ -73,7 +66,28 @@ tile_cells_v4 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
   for (int qz = 0; qz < NQ; ++qz)
     {
       const double ez = (qz == 0) ? -S : ((CEN && qz == 1) ? 0.0 : S);
-      const double *Aq = AZ + qz * 9 * NC2 + c00;
+      // ---- stage 2b: y-collapse of this plane per (x-node, cell row), shared by the two cells beside it ----
+      {
+        const double *Ap = AZ + qz * 9 * NC2;
+        for (int i = tid; i < NXC; i += NT5)
+          {
+            const int ix = i % NX, cy = (i / NX) % TY, iz = i / (NX * TY);
+            const int c0 = ix + NX * (cy + NY * iz);
+#pragma unroll
+            for (int f = 0; f < 9; ++f)
+              {
+                const double a0 = Ap[f * NC2 + c0], a1 = Ap[f * NC2 + c0 + NX];
+                const double s = a0 + a1, r = a1 - a0;
+                BY[(f * NQ + 0) * NXC + i] = fma (-S, r, s);
+                BY[(f * NQ + 1) * NXC + i] = CEN ? s : fma (S, r, s);
+                if (CEN)
+                  BY[(f * NQ + 2) * NXC + i] = fma (S, r, s);
+                if (f < 7)
+                  DY[f * NXC + i] = ISO ? r : r * ((f == 3) ? k.gp[1] : k.gu[1]);
+              }
+          }
+        __syncthreads ();
+      }
       double VP[4][2], VR[4][2], DP[4][2], DR[4][2], YP[4], YR[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -93,19 +107,15 @@ tile_cells_v4 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
 #pragma unroll
               for (int f = 0; f < 9; ++f)
                 {
-                  const double a00 = Aq[f * NC2], a10 = Aq[f * NC2 + 1];
-                  const double a01 = Aq[f * NC2 + NX], a11 = Aq[f * NC2 + NX + 1];
-                  const double r0 = a01 - a00, r1 = a11 - a10;
-                  const double b0 = (CEN && qy == 1) ? a00 + a01 : fma (ey, r0, a00 + a01);
-                  const double b1 = (CEN && qy == 1) ? a10 + a11 : fma (ey, r1, a10 + a11);
+                  const double b0 = BY[(f * NQ + qy) * NXC + it0], b1 = BY[(f * NQ + qy) * NXC + it0 + 1];
                   PxB[f] = b0 + b1;
                   RxB[f] = b1 - b0;
                   if (f < 7)
                     {
-                      const double gys = (f == 3) ? k.gp[1] : k.gu[1];
+                      const double r0 = DY[f * NXC + it0], r1 = DY[f * NXC + it0 + 1];
                       dx[f] = ISO ? RxB[f] : RxB[f] * ((f == 3) ? k.gp[0] : k.gu[0]);
-                      PxDy[f] = ISO ? r0 + r1 : (r0 + r1) * gys;
-                      RxDy[f] = ISO ? r1 - r0 : (r1 - r0) * gys;
+                      PxDy[f] = r0 + r1;
+                      RxDy[f] = r1 - r0;
                       const double z0 = BZ[(f * NQ + qy) * NXC + it0], z1 = BZ[(f * NQ + qy) * NXC + it0 + 1];
                       PxBz[f] = z0 + z1;
                       RxBz[f] = z1 - z0;
@@ -294,13 +304,12 @@ tile_cells_v4 (const Grid &g, const Phys &p, const K3 &k, const int tid, const i
 
 }
 
-// the whole kernel: staging (stages 1 and 2), the cell walk, the flush of the y tile
-template <int TX, int TY, int TZ, int NQ, bool ISO>
-__device__ __forceinline__ void
-apply3d_v4_body (const Grid &g, const Phys &p, const K3 &k, int tiles_x, int tiles_y,
-                 const double *__restrict__ x, const double *__restrict__ sol,
-                 const double *__restrict__ pt, const uint8_t *__restrict__ mask,
-                 double *__restrict__ y)
+template <int TX, int TY, int TZ, int MINB, int NQ = 3, bool ISO = false>
+__global__ void __launch_bounds__ (TX * TY * TZ, MINB)
+k_apply3d_v5 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
+              const double *__restrict__ x, const double *__restrict__ sol,
+              const double *__restrict__ pt, const uint8_t *__restrict__ mask,
+              double *__restrict__ y)
 {
   using T = Tile3v2<TX, TY, TZ>;
   constexpr int NN = T::NN, NT = T::NT, NX = T::NX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC;
@@ -308,7 +317,9 @@ apply3d_v4_body (const Grid &g, const Phys &p, const K3 &k, int tiles_x, int til
   double *AZ = reinterpret_cast<double *> (smem_raw); // [3][9][NC2]
   double *BZ = AZ + 27 * NC2;                         // [7][3][NXC]
   double *BR = BZ + 21 * NXC;                         // [NXC]: y-difference of the z-difference of x's phi
-  double *DZ = BR + NXC;                              // [7][NC2], stage 1 -> 2 only
+  double *BY = BR + NXC;                              // [9][NQ][NXC], rebuilt for every plane
+  double *DY = BY + 27 * NXC;                         // [7][NXC]
+  double *DZ = DY + 7 * NXC;                          // [7][NC2], stage 1 -> 2 only
   double *ys = DZ;                                    // [4][NN], aliases DZ
 
   const int tid = threadIdx.x;
@@ -388,7 +399,7 @@ apply3d_v4_body (const Grid &g, const Phys &p, const K3 &k, int tiles_x, int til
     ys[i] = 0;
   __syncthreads ();
 
-  tile_cells_v4<TX, TY, TZ, NQ, ISO> (g, p, k, tid, cx0, cy0, cz0, AZ, BZ, BR, ys);
+  tile_cells_v5<TX, TY, TZ, NQ, ISO> (g, p, k, tid, cx0, cy0, cz0, AZ, BZ, BR, BY, DY, ys);
 
   // ---- flush the y tile ---------------------------------------------------------
   for (int i = tid; i < NN; i += NT)
@@ -405,28 +416,6 @@ apply3d_v4_body (const Grid &g, const Phys &p, const K3 &k, int tiles_x, int til
               atomicAdd (&y[4 * n + c], ys[c * NN + i]);
         }
     }
-}
-
-template <int TX, int TY, int TZ, int MINB, int NQ = 3, bool ISO = false>
-__global__ void __launch_bounds__ (TX * TY * TZ, MINB)
-k_apply3d_v4 (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
-              const double *__restrict__ x, const double *__restrict__ sol,
-              const double *__restrict__ pt, const uint8_t *__restrict__ mask,
-              double *__restrict__ y)
-{
-  apply3d_v4_body<TX, TY, TZ, NQ, ISO> (g, p, k, tiles_x, tiles_y, x, sol, pt, mask, y);
-}
-
-// the same kernel under an explicit register cap (tuning variants: 200 registers = 5 CTAs of 64 threads
-// per SM, 10 warps, where __launch_bounds__ (64, 5) makes ptxas go down to 168 and spill)
-template <int TX, int TY, int TZ, int MAXR, int NQ = 3, bool ISO = false>
-__global__ void __launch_bounds__ (TX * TY * TZ) __maxnreg__ (MAXR)
-k_apply3d_v4_maxr (Grid g, Phys p, K3 k, int tiles_x, int tiles_y,
-                   const double *__restrict__ x, const double *__restrict__ sol,
-                   const double *__restrict__ pt, const uint8_t *__restrict__ mask,
-                   double *__restrict__ y)
-{
-  apply3d_v4_body<TX, TY, TZ, NQ, ISO> (g, p, k, tiles_x, tiles_y, x, sol, pt, mask, y);
 }
 
 } // namespace pf

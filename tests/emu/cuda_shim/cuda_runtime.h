@@ -14,6 +14,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static
 #define __align__(n)
 

@@ -23,6 +23,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __shared__ static thread_local
 #define __align__(n)
 #define __grid_constant__

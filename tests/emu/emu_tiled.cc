@@ -18,6 +18,7 @@ alignas (16) unsigned char smem_raw[256 * 1024];
 #include <vector>
 
 #include "../../cracks_b200/csrc/pf_apply3d_v4.cuh"
+#include "../../cracks_b200/csrc/pf_apply3d_v5.cuh"
 #include "../../cracks_b200/csrc/pf_residual3d.cuh"
 #include "../../cracks_b200/csrc/pf_vector.cuh"
 
@@ -114,7 +115,9 @@ emu_apply3d (int variant, int nq, const int *n, const double *h, const double *p
   const unsigned grid = (unsigned) (tiles_x * tiles_y * tiles_z);
   const bool iso = h[0] == h[1] && h[1] == h[2];
 #define EMU_LAUNCH(KERNEL) launch_blocks (KERNEL, grid, (unsigned) (TX * TY * TZ), g, p, k, tiles_x, tiles_y, x, sol, pt, mask, y)
-  if (variant == 16 && nq == 3)
+  if (variant == 19)
+    iso ? EMU_LAUNCH ((k_apply3d_v5<TX, TY, TZ, 2, 3, true>) ) : EMU_LAUNCH ((k_apply3d_v5<TX, TY, TZ, 2, 3, false>) );
+  else if (variant == 16 && nq == 3)
     iso ? EMU_LAUNCH ((k_apply3d_v4<TX, TY, TZ, 2, 3, true>) ) : EMU_LAUNCH ((k_apply3d_v4<TX, TY, TZ, 2, 3, false>) );
   else if (variant == 16)
     iso ? EMU_LAUNCH ((k_apply3d_v4<TX, TY, TZ, 2, 2, true>) ) : EMU_LAUNCH ((k_apply3d_v4<TX, TY, TZ, 2, 2, false>) );

@@ -202,7 +202,7 @@ def test_tiled_apply_kernel_sources_match_the_oracle(oracle, emu_tiled, n, h):
     free = con == 0
     diag = np.ones(prob.n_dofs)
     nv, hv = (C.c_int * 3)(*n), (C.c_double * 3)(*h)
-    for variant in (16, 3):                                           # v4 (default) and v2
+    for variant in (16, 3, 19):                                       # v4 (default), v2 and v5 (y-collapse staged)
         y = np.zeros(prob.n_dofs)
         emu_tiled.emu_apply3d(C.c_int(variant), C.c_int(3), nv, hv, _ptr(phys), _ptr(x), _ptr(sol), _ptr(pt), _ptr(mask),
                               _ptr(diag), _ptr(y))

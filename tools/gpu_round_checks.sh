@@ -22,8 +22,10 @@ for s in $steps; do
           --master-port 29617 bench.py --gpus $n --steps 50 --warmup 10 2> gpurun_out/bench_n$n.err | tail -1 | tee gpurun_out/bench_n$n.json
       done ;;
     variants)     # A/B of apply-kernel variants prepared offline: 16 = v4 default (222 regs, 8 warps/SM),
-                  # 17 / 18 = v4 capped at 168 registers (12 / 10 warps/SM, 164 / 256 B spills)
-      for v in 16 17 18; do
+                  # 17 / 18 = v4 with __launch_bounds__ (64, 6 / 5): 168 registers (12 / 10 warps/SM, 164 / 256 B spills),
+                  # 20 / 21 = v4 with __maxnreg__ (200 / 184): 10 warps/SM, 56 / 176 B spills,
+                  # 19 = v5 (y-collapse staged in shared memory: 178 registers, no spills, 54 KB per CTA -> 8 warps/SM)
+      for v in 16 20 17 18 21 19; do
         echo "variant $v"; timeout 300 python bench.py --variant $v --steps 50 --warmup 10 --no-cpu-baseline --no-newton --e2e-steps 1 | cut -c1-330
       done ;;
     chunks)       # host-buffer apply (the e2e number): chunks of the H2D / apply / D2H pipeline, 8 was measured (3.75 ms)
