@@ -366,7 +366,7 @@ def main():
                     "note": "pf_apply_jacobian with pinned host buffers in the reference's block layout"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_apply3d_v4<16,4,1>" if os.environ.get("PF_APPLY_VARIANT", "16") == "16" else "variant " + os.environ["PF_APPLY_VARIANT"], "kernel_ms": k_ms,
+                         "traffic": traffic, "kernel": "k_apply3d_v4<16,4,1>" if str(args.variant or os.environ.get("PF_APPLY_VARIANT", "16")) == "16" else "variant %s" % (args.variant or os.environ["PF_APPLY_VARIANT"]), "kernel_ms": k_ms,
                          "kernel_share_of_step": kern_ms / ms_total, "algorithmic_bytes": b_alg, "peak_source": peak_src,
                          "note": "FP64-pipe bound: exact 27-point FP64 quadrature, no f64 tensor path (DESIGN.md)"},
         }
