@@ -24,5 +24,16 @@ def oracle():
 @pytest.fixture(scope="session")
 def pf():
     import cracks_b200
+    if os.environ.get("PF_EMULATED_LIBRARY") == "1":
+        # developer aid for a box without a GPU: `PF_EMULATED_LIBRARY=1 pytest tests/test_gpu_parity.py` runs the
+        # GPU parity tests through the CPU emulation of the library (tests/emu/, test infrastructure) to catch
+        # regressions of the host logic / kernel sources before GPU time is spent.  Never set by the suites.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emulated_library
+        so = build_emulated_library.build()
+        from cracks_b200 import api
+        api.library_path = lambda: so
+        api._LIB = None
+        return cracks_b200
     cracks_b200.build_library()
     return cracks_b200

@@ -2,6 +2,8 @@
 oracle on the same seeded inputs.  Bit-level agreement is not expected for
 FP64 sums in a different order; the tolerance is 1e-12 relative l-infinity
 (SURVEY.md 8c)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -92,8 +94,12 @@ def test_apply_jacobian_3d(oracle, pf, n, h):
     assert _relerr(ctx.to_nodal(y4), y_ref) <= TOL
     # variant 1 = first-generation kernel, 2..7 = tile shapes of v2, 12..15 = persistent
     # TMA-fed kernel (v3); 16 = v4 (symmetric strain sums, closed-form phi Laplacian) is the default
-    for variant in (1, 2, 3, 4, 5, 6, 7, 12, 13, 14, 15):
-        ctx.lib.pf_debug_set_variant(variant)
+    # 17 / 18 / 20 / 21 = v4 under register caps, 19 = v5 (y-collapse staged in shared memory): tuning variants
+    variants = (1, 2, 3, 4, 5, 6, 7, 12, 13, 14, 15, 17, 18, 19, 20, 21)
+    if os.environ.get("PF_EMULATED_LIBRARY") == "1":
+        variants = tuple(v for v in variants if not 12 <= v <= 15)   # the TMA kernel is not emulated
+    for variant in variants:
+        assert ctx.lib.pf_debug_set_variant(variant) == 0
         try:
             y3 = np.zeros(prob.n_dofs)
             ctx.vmult(y3, ctx.to_block(x))
