@@ -99,6 +99,7 @@ _SIGS = {
     "pf_lumped_mass": [C.c_void_p, C.c_void_p],
     "pf_active_set_update": [C.c_void_p, C.c_double, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                              C.POINTER(C.c_int)],
+    "pf_get_active_set": [C.c_void_p, C.c_void_p],
     "pf_active_set_reset": [C.c_void_p],
     "pf_solve": [C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.POINTER(C.c_int)],
     "pf_energy": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
@@ -370,6 +371,12 @@ class PhaseFieldContext:
         z = np.empty_like(v)
         self._check(self.lib.pf_apply_preconditioner(self.h, _ptr(v), _ptr(z)))
         return z
+
+    def get_active_set(self):
+        """one byte per node, 1 = in the active set (does not change it)"""
+        m = np.zeros(self.n_nodes, dtype=np.uint8)
+        self._check(self.lib.pf_get_active_set(self.h, _ptr(m)))
+        return m
 
     def setup_jacobian(self):
         self._check(self.lib.pf_setup_jacobian(self.h))

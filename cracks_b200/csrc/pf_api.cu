@@ -2469,6 +2469,26 @@ pf_lumped_mass (pf_ctx *ctx, double *mass)
 }
 
 int
+pf_get_active_set (pf_ctx *ctx, uint8_t *active_mask)
+{
+  if (!ctx || !active_mask)
+    return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
+  const Grid &g = ctx->g;
+  const long long nl = g.n_local_nodes;
+  if (ctx->dim == 2)
+    k_get_active<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, ctx->stage8);
+  else
+    k_get_active<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, ctx->stage8);
+  KCHECK ();
+  const long long lo = ctx->owned_lo, cnt = ctx->owned_hi - ctx->owned_lo;
+  CU (cudaMemcpyAsync (active_mask + (long long) g.plane_begin * g.nodes_per_plane + lo, ctx->stage8 + lo, (size_t) cnt,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CU (cudaStreamSynchronize (ctx->stream));
+  return PF_OK;
+}
+
+int
 pf_active_set_reset (pf_ctx *ctx)
 {
   if (!ctx)

@@ -1,4 +1,5 @@
 #include "fracture_problem.h"
+#include "vtu_writer.h"
 
 #include "bitmap_function.h"
 
@@ -102,6 +103,7 @@ FracturePhaseFieldProblem::set_runtime_parameters ()
   outer_solver = prm_.get ("outer solver");
   test_case = prm_.get ("test case");
   output_folder = prm_.get ("Output directory");
+  filename_base = prm_.get ("Output filename");
   refinement_strategy = prm_.get ("ref strategy");
   value_phase_field_for_refinement = prm_.get_double ("value phase field for refinement");
   prm_.leave_subsection ();
@@ -348,6 +350,118 @@ FracturePhaseFieldProblem::write_statistics () const
     }
 }
 
+// output_results(), cracks.cc:3142-3258: displacement, phasefield and active_set per node, subdomain (and
+// emodulus for `multiple het`) per cell; one .vtu piece (this driver runs one rank), the .pvtu / .visit / .pvd
+// records, and the two screen lines of the reference.  Not written: the SneddonExactPostProc fields (3164-3167).
+void
+FracturePhaseFieldProblem::output_results ()
+{
+  ++output_cycle_;
+  if (!write_output)
+    return;
+  const long long nn = n_nodes ();
+  std::vector<double> blk ((size_t) nn * (dim_ + 1));
+  pf_check (ctx_, pf_get_state (ctx_, 0, blk.data ()));
+  std::vector<uint8_t> active ((size_t) nn, 0);
+  pf_check (ctx_, pf_get_active_set (ctx_, active.data ()));
+  std::vector<VtuPointField> pfields (3);
+  pfields[0].name = "displacement";
+  pfields[0].n_components = 3;
+  pfields[0].values.assign ((size_t) nn * 3, 0.0);
+  pfields[1].name = "phasefield";
+  pfields[1].n_components = 1;
+  pfields[1].values.resize ((size_t) nn);
+  pfields[2].name = "active_set";
+  pfields[2].n_components = 1;
+  pfields[2].values.resize ((size_t) nn);
+  for (long long i = 0; i < nn; ++i)
+    {
+      for (int d = 0; d < dim_; ++d)
+        pfields[0].values[(size_t) (3 * i + d)] = blk[(size_t) (dim_ * i + d)];
+      pfields[1].values[(size_t) i] = blk[(size_t) (dim_ * nn + i)];
+      pfields[2].values[(size_t) i] = active[(size_t) i];
+    }
+  // mesh tables: the forest's, or the box (with the doubled nodes of the slit, include/cracks_b200.h pf_mesh.slit)
+  std::vector<double> coords;
+  std::vector<long long> conn;
+  long long nc = 0;
+  if (use_forest ())
+    {
+      coords = forest_->coordinates ();
+      conn = forest_->connectivity ();
+      nc = forest_->n_cells ();
+    }
+  else
+    {
+      const int *n = mesh_.n;
+      const int nx1 = n[0] + 1, ny1 = n[1] + 1, nz1 = dim_ == 3 ? n[2] + 1 : 1;
+      const long long regular = (long long) nx1 * ny1 * nz1;
+      coords.assign ((size_t) nn * dim_, 0.0);
+      for (long long p = 0; p < regular; ++p)
+        {
+          const long long ijk[3] = {p % nx1, (p / nx1) % ny1, p / ((long long) nx1 * ny1)};
+          for (int d = 0; d < dim_; ++d)
+            coords[(size_t) (dim_ * p + d)] = mesh_.origin[d] + mesh_.h[d] * ijk[d];
+        }
+      const int slit_row = mesh_.slit ? n[1] / 2 : -1, slit_i0 = n[0] / 2 + 1;
+      for (long long p = regular; p < nn; ++p) // copies of the nodes (slit_i0 + k, n[1]/2)
+        {
+          coords[(size_t) (2 * p)] = mesh_.origin[0] + mesh_.h[0] * (slit_i0 + (p - regular));
+          coords[(size_t) (2 * p + 1)] = mesh_.origin[1] + mesh_.h[1] * (n[1] / 2);
+        }
+      const int nv = 1 << dim_;
+      nc = (long long) n[0] * n[1] * (dim_ == 3 ? n[2] : 1);
+      conn.resize ((size_t) nc * nv);
+      for (long long c = 0; c < nc; ++c)
+        {
+          const long long ci = c % n[0], cj = (c / n[0]) % n[1], ck = c / ((long long) n[0] * n[1]);
+          for (int v = 0; v < nv; ++v)
+            {
+              const long long i = ci + (v & 1), j = cj + ((v >> 1) & 1), k = ck + ((v >> 2) & 1);
+              long long node = i + nx1 * (j + (long long) ny1 * k);
+              if (cj == slit_row && j == slit_row && i >= slit_i0)
+                node = regular + (i - slit_i0); // the cell row above the slit sees the upper copies
+              conn[(size_t) (nv * c + v)] = node;
+            }
+        }
+    }
+  std::vector<VtuCellField> cfields;
+  if (hetero ())
+    {
+      // e_mod(cell) = 1.0 + func_emodulus->value(cell->center()), cracks.cc:3170-3183
+      const BitmapFunction func_emodulus (source_dir + "/test.pgm", 0, 10, 0, 10, E_modulus, 10.0 * E_modulus);
+      VtuCellField e;
+      e.name = "emodulus";
+      e.values.resize ((size_t) nc);
+      for (long long c = 0; c < nc; ++c)
+        {
+          double x[3];
+          forest_->cell_centre (c, x);
+          e.values[(size_t) c] = (float) (1.0 + func_emodulus.value (x, 3));
+        }
+      cfields.push_back (e);
+    }
+  VtuCellField sub;
+  sub.name = "subdomain";
+  sub.values.assign ((size_t) nc, 0.0f);
+  cfields.push_back (sub);
+
+  pcout_ << "Write solution " << output_cycle_ << std::endl;
+  ::mkdir (output_folder.c_str (), 0755);
+  char num[16];
+  std::snprintf (num, sizeof num, "%05d", output_cycle_);
+  const std::string piece = filename_base + num + ".0000.vtu", master = filename_base + num + ".pvtu";
+  write_vtu (output_folder + "/" + piece, dim_, nn, coords.data (), nc, conn.data (), pfields, cfields);
+  write_pvtu_record (output_folder + "/" + master, {piece}, pfields, cfields);
+  const std::string visit = output_folder + "/" + filename_base + num + ".visit";
+  write_visit_record (visit, {{piece}});
+  output_file_names_by_timestep_.push_back ({piece});
+  write_visit_record (output_folder + "/solution.visit", output_file_names_by_timestep_);
+  pcout_ << "\tas " << visit << std::endl;
+  times_and_names_.emplace_back (time, master);
+  write_pvd_record (output_folder + "/solution.pvd", times_and_names_);
+}
+
 // cracks.cc:4166-4581, Sneddon branch
 void
 FracturePhaseFieldProblem::run ()
@@ -385,6 +499,7 @@ FracturePhaseFieldProblem::run ()
     }
   else
     pf_check (ctx_, pf_interpolate_sneddon (ctx_, min_cell_diameter));
+  output_results (); // cracks.cc:4263
   pf_check (ctx_, pf_project_phase_field (ctx_));
   old_timestep = timestep;
   old_old_timestep = timestep;
@@ -495,6 +610,7 @@ FracturePhaseFieldProblem::run ()
         }
       pcout_ << std::endl;
       statistics_.push_back ({timestep_number, time, nodes * (dim_ + 1), min_cell_diameter, bulk, crack, load});
+      output_results (); // cracks.cc:4466-4467
       write_statistics ();
 
       pf_check (ctx_, pf_timestep_difference (ctx_, &finishing_timestep_loop));

@@ -63,6 +63,9 @@ public:
   // refine_mesh() (phase-field flags, level cap, solution transfer, redo of the step) instead of stopping
   // where the mesh would change
   bool adaptive_forest = false;
+  // write the .vtu / .pvtu / .visit / .pvd files of output_results() (cracks.cc:3142-3258); the command line
+  // switches it off with --no-output (16.7 M DoF are 0.8 GB per time step)
+  bool write_output = true;
   std::string source_dir = ".";   // where test.pgm lives ($SRC of cracks.cc:1541, a compile-time path in the reference)
   int gmres_max_iterations = 200; // SolverControl(200, ...) at cracks.cc:2762
   double gmres_tolerance = 1e-8;
@@ -73,6 +76,7 @@ private:
   void determine_mesh_dependent_parameters ();
   double newton_active_set ();
   void write_statistics () const;
+  void output_results (); // cracks.cc:3142-3258
   bool miehe () const { return test_case == "miehe tension" || test_case == "miehe shear"; }
   // EXPERIMENTAL (device side not yet run on a GPU): Sneddon 2-D with local pre-refinement
   // / refinement cycles on the host forest, strategy `fixed preref sneddon`
@@ -117,6 +121,10 @@ private:
   FunctionParser func_pressure;
 
   std::vector<StatisticsRow> statistics_;
+  int output_cycle_ = -1; // `refinement_cycle` of output_results()
+  std::string filename_base;
+  std::vector<std::vector<std::string>> output_file_names_by_timestep_;
+  std::vector<std::pair<double, std::string>> times_and_names_;
   double tcv_ = 0;
   std::vector<std::pair<double, double>> cod_; // (x, COD(x)) lines of compute_functional_values
   unsigned total_newton_its_ = 0, total_linear_its_ = 0;

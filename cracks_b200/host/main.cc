@@ -21,13 +21,15 @@ main (int argc, char *argv[])
       const char *file = nullptr;
       int device = 0, gmres_max_it = 200;
       std::string source_dir = ".";
-      bool adaptive = false;
+      bool adaptive = false, write_output = true;
       for (int i = 1; i < argc; ++i)
         {
           if (!std::strcmp (argv[i], "--device") && i + 1 < argc)
             device = std::atoi (argv[++i]);
           else if (!std::strcmp (argv[i], "--gmres-max-it") && i + 1 < argc)
             gmres_max_it = std::atoi (argv[++i]);
+          else if (!std::strcmp (argv[i], "--no-output"))
+            write_output = false; // skip the .vtu files of output_results() (benchmark-sized runs)
           else if (!std::strcmp (argv[i], "--adaptive"))
             adaptive = true; // follow refine_mesh() on the host forest (experimental)
           else if (!std::strcmp (argv[i], "--source-dir") && i + 1 < argc)
@@ -39,7 +41,7 @@ main (int argc, char *argv[])
         {
           std::ofstream out ("default.prm");
           out << prm.print_parameters ();
-          std::cout << "usage: ./cracks_b200 <parameter_file> [--device N] [--gmres-max-it K] [--source-dir DIR] [--adaptive]" << std::endl
+          std::cout << "usage: ./cracks_b200 <parameter_file> [--device N] [--gmres-max-it K] [--source-dir DIR] [--adaptive] [--no-output]" << std::endl
                     << " (created default.prm)" << std::endl;
           return 0;
         }
@@ -59,6 +61,7 @@ main (int argc, char *argv[])
       problem.gmres_max_iterations = gmres_max_it;
       problem.source_dir = source_dir;
       problem.adaptive_forest = adaptive;
+      problem.write_output = write_output;
       problem.run ();
     }
   catch (std::exception &exc)

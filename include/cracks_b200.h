@@ -229,6 +229,9 @@ int pf_lumped_mass (pf_ctx *ctx, double *mass);
  * active_mask (one byte per node, may be NULL) receives the set.  [collective] */
 int pf_active_set_update (pf_ctx *ctx, double c, uint8_t *active_mask,
                           int64_t *n_active, int64_t *n_cycling, int *changed);
+/* The current active set without changing it (one byte per node, 1 = active): what
+ * output_results() writes as the "active_set" field, cracks.cc:3193-3208. */
+int pf_get_active_set (pf_ctx *ctx, uint8_t *active_mask);
 int pf_active_set_reset (pf_ctx *ctx);
 
 /* solve(): GMRES(<= max_it, tol_rel * ||r_pde||_2) on J dx = r_pde with the

@@ -288,7 +288,7 @@ def test_cpp_host_driver_on_the_forest_path(emu_so, tmp_path):
     host = os.path.join(ROOT, "cracks_b200", "host")
     exe = os.path.join(HERE, "emu", "cracks_b200_run_emu")
     srcs = [os.path.join(host, f) for f in ("main.cc", "fracture_problem.cc", "parameter_handler.cc", "function_parser.cc",
-                                            "forest.cc", "bitmap_function.cc")]
+                                            "forest.cc", "bitmap_function.cc", "vtu_writer.cc")]
     deps = srcs + [os.path.join(host, f) for f in os.listdir(host) if f.endswith(".h")] + [emu_so]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, *srcs, "-L", os.path.join(HERE, "emu"),
@@ -316,6 +316,23 @@ def test_cpp_host_driver_on_the_forest_path(emu_so, tmp_path):
     assert "DoFs: 302 solid + 151 phase = 453" in r.stdout and "DoFs: 518 solid + 259 phase = 777" in r.stdout
     assert "0\t\t\t1.491639e+01" in r.stdout                          # tests/sneddon_2d_1.output
     assert "Refinement cycle 0" in r.stdout and "TCV: value= 0.0418879" in r.stdout
+    # output_results(): the initial condition and the 4 time steps, like the golden's "Write solution 0..4"; the
+    # pieces are valid VTK XML with the forest's cells and the nodal fields
+    from vtu_reader import read_vtu
+    written = [l.strip() for l in r.stdout.splitlines() if l.startswith("Write solution")]
+    assert written[:5] == ["Write solution %d" % i for i in range(5)]
+    assert "\tas " + str(tmp_path / "out" / "solution_00003.visit") in r.stdout
+    v = read_vtu(tmp_path / "out" / "solution_00004.0000.vtu")
+    assert (v["n_points"], v["n_cells"]) == (151, 124) and v["point_data"] == ["displacement", "phasefield", "active_set"]
+    assert v["connectivity"].shape == (124 * 4,) and set(v["types"]) == {9} and v["offsets"][-1] == 124 * 4
+    assert v["phasefield"].min() == 0.0 and 0.9 < v["phasefield"].max() <= 1.0 and 0 < v["active_set"].sum() < 151
+    assert np.all(v["displacement"][:, 2] == 0.0) and np.abs(v["displacement"]).max() > 0
+    quad = v["points"][v["connectivity"].reshape(-1, 4)]                 # counter-clockwise quads: positive area
+    e1, e2 = quad[:, 1] - quad[:, 0], quad[:, 3] - quad[:, 0]
+    assert np.all(e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0] > 0)
+    pvd = open(tmp_path / "out" / "solution.pvd").read()
+    assert pvd.count("<DataSet") == len(written) and 'file="solution_00004.pvtu"' in pvd
+    assert open(tmp_path / "out" / "solution.visit").read().splitlines()[:2] == ["!NBLOCKS 1", "solution_00000.0000.vtu"]
     rows = [l.split() for l in open(tmp_path / "out" / "statistics") if not l.startswith("#")]
     assert len(rows) == 4
     for row, ref in zip(rows, g["statistics"]):
@@ -367,6 +384,14 @@ end
     assert r.returncode == 0, r.stderr
     text = open(tmp_path / "out" / "statistics").read()
     assert "# 7: Load x" in text
+    # the piece of the last step: 4 x 4 cells with the slit = 25 + 2 doubled nodes, the cell row above the slit
+    # is connected to the upper copies
+    from vtu_reader import read_vtu
+    v = read_vtu(tmp_path / "out" / "solution_00003.0000.vtu")
+    assert (v["n_points"], v["n_cells"]) == (27, 16)
+    cells = v["connectivity"].reshape(-1, 4)
+    assert {25, 26} <= set(cells[8:12].reshape(-1)) and not ({25, 26} & set(cells[:8].reshape(-1)))
+    assert np.allclose(v["points"][25:27, :2], [[0.75, 0.5], [1.0, 0.5]])
     rows = [l.split() for l in text.splitlines() if not l.startswith("#")]
     assert len(rows) == len(ref) == 3
     for row, b in zip(rows, ref):
@@ -440,7 +465,7 @@ def test_cpp_host_driver_hetero_3d(emu_so, tmp_path):
     exe = os.path.join(HERE, "emu", "cracks_b200_run_emu")
     host = os.path.join(ROOT, "cracks_b200", "host")
     srcs = [os.path.join(host, f) for f in ("main.cc", "fracture_problem.cc", "parameter_handler.cc", "function_parser.cc",
-                                            "forest.cc", "bitmap_function.cc")]
+                                            "forest.cc", "bitmap_function.cc", "vtu_writer.cc")]
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, *srcs, "-L", os.path.join(HERE, "emu"),
                            "-lcracks_b200_emu", "-Wl,-rpath," + os.path.join(HERE, "emu"), "-pthread"])
     g = json.load(open(os.path.join(HERE, "golden", "hetero_3d_1.json")))
@@ -485,3 +510,11 @@ end
         assert int(row[2]) == 5288 and float(row[3]) == pytest.approx(ref["h"], rel=1e-8)
         assert float(row[5]) == pytest.approx(ref["crack"], rel=1e-7)
         assert float(row[4]) == pytest.approx(ref["bulk"], rel=1e-6)
+    # output_results() of `multiple het`: hexahedra of the octree, the emodulus cell field (1 + E, cracks.cc:3179)
+    from vtu_reader import read_vtu
+    v = read_vtu(tmp_path / "out" / "solution_00002.0000.vtu")
+    assert v["n_points"] == 1322 and set(v["types"]) == {12} and v["cell_data"] == ["emodulus", "subdomain"]
+    assert v["emodulus"].min() >= 1.0 and v["emodulus"].max() > 2.0 * v["emodulus"].min()
+    hexa = v["points"][v["connectivity"].reshape(-1, 8)]
+    vol = np.einsum("ci,ci->c", np.cross(hexa[:, 1] - hexa[:, 0], hexa[:, 3] - hexa[:, 0]), hexa[:, 4] - hexa[:, 0])
+    assert np.all(vol > 0) and vol.sum() == pytest.approx(1000.0, rel=1e-12)      # [0,10]^3, right-handed cells
