@@ -159,6 +159,7 @@ struct pf_ctx
   long long mg_graph_launches = 0;
   // the V-cycle in FP32 (pf_mg_lowp.cuh; opt-in, pf_set_multigrid_precision): per level the state, the inverse
   // diagonal and the work vectors in float; set-up (diagonal, power iteration) stays FP64
+  bool mg2d = false; // multigrid also on 2-D box / slit meshes (pf_set_preconditioner kind 3), single rank
   int mg_fp32 = getenv ("PF_MG_FP32") ? atoi (getenv ("PF_MG_FP32")) : 0;
   float *f_sol = nullptr, *f_pt = nullptr, *f_idiag = nullptr;
   float *f_b = nullptr, *f_x = nullptr, *f_y = nullptr, *f_d = nullptr, *f_r = nullptr;
@@ -1083,6 +1084,7 @@ int diag_and_aux (pf_ctx *ctx);
 
 // (re)builds the level below ctx and transfers state, constraints and parameters to it
 int mg_lowp_refresh (pf_ctx *ctx);
+int mg2_setup_coarse (pf_ctx *ctx);
 
 int
 mg_setup_level (pf_ctx *ctx)
@@ -1141,6 +1143,8 @@ mg_setup_level (pf_ctx *ctx)
     ctx->mg_ev_valid = true;
     ctx->lam_max = 1.2 * lam;
   }
+  if (ctx->dim == 2)
+    return mg2_setup_coarse (ctx);
   if (ctx->mg_fp32)
     {
       const int rcl = mg_lowp_refresh (ctx);
@@ -1230,6 +1234,81 @@ mg_setup_level (pf_ctx *ctx)
   return PF_OK;
 }
 
+// ---- 2-D hierarchy: n -> n / 2 down to 2 x 2 (slit: the coarse mesh is the same square with the same slit) ----
+Dims2
+dims2_of (const pf_ctx *ctx)
+{
+  const Grid &g = ctx->g;
+  return Dims2{{g.nn[0], g.nn[1]}, g.slit_row, g.slit_i0, g.slit_base};
+}
+
+bool
+mg2_possible (const pf_ctx *ctx)
+{
+  if (ctx->dim != 2 || !ctx->mg2d || ctx->nranks != 1 || ctx->forest)
+    return false;
+  for (int d = 0; d < 2; ++d)
+    {
+      const int n = ctx->g.n[d];
+      if (n % 2 != 0 || n / 2 < 2 || (ctx->g.slit_row >= 0 && (n / 2) % 2 != 0))
+        return false;
+    }
+  return true;
+}
+
+int
+mg2_setup_coarse (pf_ctx *ctx)
+{
+  if (!mg2_possible (ctx))
+    {
+      ctx->mg_ready = true; // coarsest level: mg_vcycle runs the long Chebyshev iteration on it
+      return PF_OK;
+    }
+  if (!ctx->coarse)
+    {
+      pf_mesh cm{};
+      cm.dim = 2;
+      for (int d = 0; d < 2; ++d)
+        {
+          cm.n[d] = ctx->g.n[d] / 2;
+          cm.h[d] = ctx->g.h[d] * 2.0;
+          cm.origin[d] = ctx->g.origin[d];
+        }
+      cm.slit = ctx->g.slit_row >= 0;
+      const int rc = create_impl (&cm, &ctx->prm, ctx->device, 0, 1, nullptr, nullptr, &ctx->coarse);
+      if (rc)
+        return fail (ctx, rc, "multigrid: cannot create the coarse level: %s", pf_last_error (ctx->coarse));
+      cudaStreamDestroy (ctx->coarse->stream);
+      ctx->coarse->stream = ctx->stream;
+      ctx->coarse->owns_stream = false;
+    }
+  pf_ctx *c = ctx->coarse;
+  c->prm = ctx->prm;
+  c->p = ctx->p; // incl. the stress-split switches
+  c->precond = ctx->precond;
+  c->cheb_degree = ctx->cheb_degree;
+  c->cheb_ratio = ctx->cheb_ratio;
+  c->mg_approx = ctx->mg_approx;
+  c->coarsest_degree = ctx->coarsest_degree;
+  c->mg2d = true;
+  const Dims2 dc = dims2_of (c), df = dims2_of (ctx);
+  const long long ncn = c->g.n_local_nodes;
+  k_inject2d<3, double><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->sol, c->sol);
+  KCHECK ();
+  k_inject2d<1, double><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->pt, c->pt);
+  KCHECK ();
+  k_inject2d<1, uint8_t><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (dc, df, ctx->mask, c->mask);
+  KCHECK ();
+  int rc = diag_and_aux (c);
+  if (rc)
+    return fail (ctx, rc, "multigrid: coarse diagonal: %s", pf_last_error (c));
+  c->jac_ready = true;
+  if ((rc = mg_setup_level (c)))
+    return fail (ctx, rc, "multigrid: %s", pf_last_error (c));
+  ctx->mg_ready = true;
+  return PF_OK;
+}
+
 // Chebyshev-Jacobi smoother on J x = b; zero_guess: x is ignored on entry
 int
 mg_smooth (pf_ctx *ctx, const double *b, double *x, bool zero_guess, int degree, double ratio)
@@ -1288,6 +1367,21 @@ mg_vcycle (pf_ctx *ctx, const double *b, double *x)
     return rc;
   k_sub<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, b, ctx->mg_y, ctx->mg_r);
   KCHECK ();
+  if (ctx->dim == 2)
+    {
+      const Dims2 dc2 = dims2_of (c), df2 = dims2_of (ctx);
+      const long long nfn = ctx->g.n_local_nodes, ncn = c->g.n_local_nodes;
+      CU (cudaMemsetAsync (c->mg_b, 0, sizeof (double) * c->n_local_dofs, ctx->stream));
+      k_restrict_add2d<<<nblk (nfn, 256), 256, 0, ctx->stream>>> (dc2, df2, ctx->mg_r, ctx->mask, c->mg_b);
+      KCHECK ();
+      k_zero_constrained<2><<<nblk (ncn, 256), 256, 0, ctx->stream>>> (ncn, c->mask, c->mg_b);
+      KCHECK ();
+      if ((rc = mg_vcycle (c, c->mg_b, c->mg_x)))
+        return rc;
+      k_prolong_add2d<<<nblk (nfn, 256), 256, 0, ctx->stream>>> (dc2, df2, c->mg_x, ctx->mask, x);
+      KCHECK ();
+      return mg_smooth (ctx, b, x, false, ctx->cheb_degree, ctx->cheb_ratio);
+    }
   Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}, c->g.plane_begin},
     df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}, ctx->g.plane_begin};
   {
@@ -2355,7 +2449,7 @@ pf_setup_jacobian (pf_ctx *ctx)
   ctx->jac_ready = true;
   ctx->mg_ready = false;
   ctx->mg_graph_valid = false;
-  if (ctx->precond == 1 && ctx->dim == 3 && !ctx->forest)
+  if (ctx->precond == 1 && !ctx->forest && (ctx->dim == 3 || (ctx->mg2d && ctx->nranks == 1)))
     return mg_setup_level (ctx);
   return PF_OK;
 }
@@ -2363,10 +2457,11 @@ pf_setup_jacobian (pf_ctx *ctx)
 int
 pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio)
 {
-  if (!ctx || kind < 0 || kind > 2 || cheb_degree < 1 || !(cheb_ratio > 1.0))
+  if (!ctx || kind < 0 || kind > 3 || cheb_degree < 1 || !(cheb_ratio > 1.0))
     return PF_BAD_ARG;
   ctx->precond = kind ? 1 : 0;
   ctx->mg_approx = kind != 2; // kind 2: smoother with the exact 27-point operator (for comparisons)
+  ctx->mg2d = kind == 3;      // kind 3: the V-cycle also on 2-D box / slit meshes (otherwise Jacobi there)
   ctx->cheb_degree = cheb_degree;
   ctx->cheb_ratio = cheb_ratio;
   ctx->jac_ready = false;

@@ -108,6 +108,121 @@ k_restrict (Dims3 dc, Dims3 df, int Ka, int Ke, const double *__restrict__ rf, c
     rc[4 * n + c] = ((m >> c) & 1) ? 0.0 : acc[c];
 }
 
+// ---- 2-D hierarchy (box meshes and the unit square with the slit of the Miehe tests) -------------------
+// Nodes: the regular (n[0] x n[1]) grid, x fastest, followed by the upper copies of the slit nodes
+// (slit_i0 + k, slit_j) -- the layout of Grid::slit_* (pf_common.cuh).  slit_j < 0: no slit.
+struct Dims2
+{
+  int n[2];
+  int slit_j, slit_i0;
+  long long slit_base;
+};
+
+__device__ __forceinline__ long long
+n_nodes2 (const Dims2 &d)
+{
+  return (long long) d.n[0] * d.n[1] + (d.slit_j >= 0 ? d.n[0] - d.slit_i0 : 0);
+}
+
+// node (i, j) as seen from the upper (upper = true) or the lower side of the slit
+__device__ __forceinline__ long long
+node_id2 (const Dims2 &d, int i, int j, bool upper)
+{
+  if (upper && j == d.slit_j && i >= d.slit_i0)
+    return d.slit_base + (i - d.slit_i0);
+  return i + (long long) d.n[0] * j;
+}
+
+// t-th node -> (i, j, side)
+__device__ __forceinline__ void
+node_ij2 (const Dims2 &d, long long t, int &i, int &j, bool &upper)
+{
+  const long long regular = (long long) d.n[0] * d.n[1];
+  if (t < regular)
+    {
+      i = (int) (t % d.n[0]);
+      j = (int) (t / d.n[0]);
+      upper = d.slit_j >= 0 && j > d.slit_j;
+    }
+  else
+    {
+      i = d.slit_i0 + (int) (t - regular);
+      j = d.slit_j;
+      upper = true;
+    }
+}
+
+// coarse node <- the fine node at the same place (same side of the slit)
+template <int NCOMP, typename T>
+__global__ void
+k_inject2d (Dims2 dc, Dims2 df, const T *__restrict__ src, T *__restrict__ dst)
+{
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes2 (dc))
+    return;
+  int I, J;
+  bool upper;
+  node_ij2 (dc, t, I, J, upper);
+  const long long f = node_id2 (df, 2 * I, 2 * J, upper);
+  for (int c = 0; c < NCOMP; ++c)
+    dst[t * NCOMP + c] = src[f * NCOMP + c];
+}
+
+// xf += P xc (bilinear; a fine node above the slit takes the upper copies of its coarse parents on the slit
+// line, one below the lower ones), constrained fine dofs receive nothing.  3 components per node.
+__global__ void
+k_prolong_add2d (Dims2 dc, Dims2 df, const double *__restrict__ xc, const uint8_t *__restrict__ fmask,
+                 double *__restrict__ xf)
+{
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes2 (df))
+    return;
+  int i, j;
+  bool upper;
+  node_ij2 (df, t, i, j, upper);
+  const int i0 = i >> 1, j0 = j >> 1, ni = i & 1, nj = j & 1;
+  const double w = (ni ? 0.5 : 1.0) * (nj ? 0.5 : 1.0);
+  double acc[3] = {0, 0, 0};
+  for (int c2 = 0; c2 <= nj; ++c2)
+    for (int c1 = 0; c1 <= ni; ++c1)
+      {
+        const long long cn = node_id2 (dc, i0 + c1, j0 + c2, upper);
+        for (int c = 0; c < 3; ++c)
+          acc[c] += w * xc[3 * cn + c];
+      }
+  const uint8_t m = fmask[t];
+  for (int c = 0; c < 3; ++c)
+    if (!((m >> c) & 1))
+      xf[3 * t + c] += acc[c];
+}
+
+// rc += P^T rf (the transpose of k_prolong_add2d as a scatter; rc zeroed by the caller, constrained fine rows
+// count as zero; constrained coarse rows are zeroed afterwards with k_zero_constrained)
+__global__ void
+k_restrict_add2d (Dims2 dc, Dims2 df, const double *__restrict__ rf, const uint8_t *__restrict__ fmask,
+                  double *__restrict__ rc)
+{
+  const long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes2 (df))
+    return;
+  int i, j;
+  bool upper;
+  node_ij2 (df, t, i, j, upper);
+  const uint8_t m = fmask[t];
+  double r[3];
+  for (int c = 0; c < 3; ++c)
+    r[c] = ((m >> c) & 1) ? 0.0 : rf[3 * t + c];
+  const int i0 = i >> 1, j0 = j >> 1, ni = i & 1, nj = j & 1;
+  const double w = (ni ? 0.5 : 1.0) * (nj ? 0.5 : 1.0);
+  for (int c2 = 0; c2 <= nj; ++c2)
+    for (int c1 = 0; c1 <= ni; ++c1)
+      {
+        const long long cn = node_id2 (dc, i0 + c1, j0 + c2, upper);
+        for (int c = 0; c < 3; ++c)
+          atomicAdd (&rc[3 * cn + c], w * r[c]);
+      }
+}
+
 // one Chebyshev step, fused: r = b - y (y = A x, or r = b when first), d = c1 d + c2 r / diag, x += d
 __global__ void
 k_cheb_step (long long n, int first, double c1, double c2, const double *__restrict__ b,

@@ -255,6 +255,10 @@ FracturePhaseFieldProblem::setup_system ()
       // AMG (2750-2771); Jacobi-GMRES needs a basis as long as its iteration count
       pf_check (ctx_, pf_set_krylov_dim (ctx_, 300));
       gmres_max_iterations = std::max (gmres_max_iterations, 3000);
+      // from 64 x 64 cells on Jacobi-GMRES needs thousands of iterations per solve: geometric multigrid on the
+      // slit square (the golden-sized meshes stay on the Jacobi path their GPU runs were verified with)
+      if (mesh_.n[0] >= 64)
+        pf_check (ctx_, pf_set_preconditioner (ctx_, 3, 2, 8.0));
     }
   else
     pf_check (ctx_, pf_set_dirichlet_all_faces (ctx_)); // set_newton_bc, cracks.cc:2575-2583 / 2686-2694

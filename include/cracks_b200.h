@@ -194,8 +194,12 @@ int pf_apply_jacobian_dev (pf_ctx *ctx, double *x_dev, double *y_dev);
  * the exact 27-point operator in the smoother).  Dim 3 box meshes, any number of
  * ranks: a level keeps the z-slab decomposition while the slabs stay aligned with
  * the coarse cells and is replicated on every rank below that (pf_mg_hierarchy
- * describes the levels).  2-D and forest meshes use Jacobi.  Takes effect at the
- * next pf_setup_jacobian. */
+ * describes the levels).  kind 3 = kind 1, and the V-cycle also on 2-D box meshes
+ * and on the unit square with the slit of the Miehe tests (single rank; n -> n/2
+ * down to 2 x 2 cells, the slit is kept on every level; a smoothing range of 8 is
+ * the robust choice there, 20 stalls GMRES once the active set is irregular).
+ * With kinds 1 and 2, 2-D meshes use Jacobi; forest meshes always do.  Takes
+ * effect at the next pf_setup_jacobian. */
 int pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio);
 /* Precision of the multigrid V-cycle: 64 (default) or 32.  With 32 the smoother
  * operator, the Chebyshev steps and the grid transfers of every level run in

@@ -192,6 +192,31 @@ def test_miehe_shear_small(oracle, epf):
     ctx.close()
 
 
+def test_multigrid_2d_on_the_slit_mesh(epf):
+    """pf_set_preconditioner kind 3: geometric multigrid on the unit square with the slit (16 x 16 -> ... -> 2 x 2,
+    doubled slit nodes on every level, stress split from the second step on).  Same converged steps as with
+    Jacobi-GMRES, a small fraction of the iterations."""
+    pf = epf
+    lam, mu = 121.15e3, 80.77e3
+    out = {}
+    for kind in (1, 3):
+        hf = pf.miehe_final_h(3, 0)
+        ctx = pf.PhaseFieldContext(pf.miehe_mesh(3), pf.Params(lam, mu, 2.7, 1e-10 * hf, 2 * hf, 0.0))
+        ctx.set_krylov_dim(300 if kind == 1 else 40)
+        ctx.set_preconditioner(kind, 2, 8.0)
+        drv = pf.MieheDriver(ctx, "miehe shear", E=1e3, timestep=1e-3, max_no_timesteps=2, d_rhs=1.0, d_mat=1.0,
+                             newton_lower_bound=1e-6, max_newton=100, max_line_search=10, line_search_damping=0.6,
+                             gmres_max_it=3000)
+        out[kind] = (drv.run(), drv.newton_its, drv.lin_its)
+        ctx.close()
+    for a, b in zip(out[3][0], out[1][0]):
+        for k in ("bulk", "crack", "load"):
+            assert a[k] == pytest.approx(b[k], rel=1e-9), (a["step"], k)
+    assert out[3][1] == out[1][1]
+    assert out[3][2] * 4 < out[1][2] and out[3][2] / out[3][1] < 20
+    # with kind 1 a 2-D context keeps using Jacobi (the path the golden GPU runs were verified with)
+
+
 def test_forest_context_kat2_end_to_end(oracle, epf):
     """pf_create_forest and the hanging-node plumbing of pf_api.cu (apply_forest_dev, the fold / distribute hooks)
     through ForestSneddonDriver: the sneddon_2d_1 golden"""
