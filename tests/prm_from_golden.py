@@ -13,9 +13,14 @@ SECTIONS = {
 }
 
 
-def write_prm(path, prm, dim, output_dir, **overrides):
+def write_prm(path, prm, dim, output_dir, exact=None, **overrides):
+    """overrides: keyword = key with blanks replaced by underscores; `exact`: dict with the keys as they are
+    (for the ones that contain a hyphen)"""
     p = dict(prm)
     p.update({k.replace("_", " "): v for k, v in overrides.items()})
+    p.update(exact or {})
+    unknown = [k for k in p if not any(k in keys for keys in SECTIONS.values()) and k != "Output filename"]
+    assert not unknown, unknown
     lines = []
     for sec, keys in SECTIONS.items():
         lines.append("subsection " + sec)

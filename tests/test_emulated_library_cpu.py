@@ -449,6 +449,47 @@ def test_cpp_host_driver_miehe_adaptive(emu_so, tmp_path):
             assert float(row[col]) == pytest.approx(ref[k], rel=2e-7), (row[0], k)
 
 
+def test_cpp_host_driver_miehe_multigrid_from_64_cells(epf, emu_so, tmp_path):
+    """From 64 x 64 cells on the C++ driver preconditions the Miehe runs with the 2-D multigrid (kind 3): two time
+    steps of miehe shear at 5 global refinements through the command line = the Python driver with the same
+    preconditioner, a dozen GMRES iterations per Newton step."""
+    from prm_from_golden import write_prm, read_statistics
+    import re
+    pf = epf
+    exe = os.path.join(HERE, "emu", "cracks_b200_run_emu")
+    if not os.path.exists(exe):
+        pytest.skip("built by test_cpp_host_driver_on_the_forest_path")
+    g = json.load(open(os.path.join(HERE, "golden", "miehe_shear_2.json")))
+    write_prm(tmp_path / "m.prm", g["prm"], 2, tmp_path / "out", Max_No_of_timesteps=1,
+              exact={"Global pre-refinement steps": 5})
+    r = subprocess.run([exe, str(tmp_path / "m.prm"), "--no-output"], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-1500:], r.stderr[-800:])
+    assert r.returncode == 0, r.stderr
+    its = [tuple(map(int, m)) for m in re.findall(r"Newton iterations: (\d+) total linear iterations: (\d+)", r.stdout)]
+    assert len(its) == 2 and all(lin <= 20 * newton for newton, lin in its)
+    p = g["prm"]
+    lam, mu = float(p["Lame lambda"]), float(p["Lame mu"])
+    hf = pf.miehe_final_h(5, 0)
+    fh = lambda expr: eval(expr, {"h": hf, "pow": pow})
+    ctx = pf.PhaseFieldContext(pf.miehe_mesh(5), pf.Params(lam, mu, float(p["Fracture toughness G_c"]), fh(p["K reg"]),
+                                                           fh(p["Eps reg"]), 0.0))
+    ctx.set_krylov_dim(300)
+    ctx.set_preconditioner(3, 2, 8.0)
+    drv = pf.MieheDriver(ctx, p["test case"], E=float(p["E modulus"]), timestep=float(p["Timestep size"]), max_no_timesteps=1,
+                         d_rhs=float(p["Decompose stress in rhs"]), d_mat=float(p["Decompose stress in matrix"]),
+                         newton_lower_bound=float(p["Newton lower bound"]), max_newton=int(p["Newton maximum steps"]),
+                         max_line_search=int(p["Line search maximum steps"]), line_search_damping=float(p["Line search damping"]),
+                         gmres_max_it=3000)
+    ref = drv.run()
+    ctx.close()
+    rows = read_statistics(tmp_path / "out" / "statistics")
+    assert len(rows) == len(ref) == 2 and not os.path.exists(tmp_path / "out" / "solution_00000.0000.vtu")
+    for row, b in zip(rows, ref):
+        assert int(row[2]) == 12771
+        for col, k in ((4, "bulk"), (5, "crack"), (6, "load")):
+            assert float(row[col]) == pytest.approx(b[k], rel=1e-6), (row[0], k)
+
+
 def test_forest_hetero_3d_kat5_end_to_end(epf):
     """BASELINE config 5 in small through the library (emulated): octree with edge / face hanging nodes from the
     phase-field pre-refinement, per-cell Lame coefficients (both sets), pressure(time): tests/hetero_3d_1 golden."""
