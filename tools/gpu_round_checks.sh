@@ -32,6 +32,9 @@ for s in $steps; do
       for c in 8 16 32; do
         echo "PF_E2E_CHUNKS=$c"; PF_E2E_CHUNKS=$c timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-newton | cut -c1-400
       done ;;
+    miehe2d)      # BASELINE config 2 / 4 at ~2e5 DoF through the C++ command line with the 2-D multigrid (kind 3),
+                  # written in round 1 without a GPU; prints wall time and iteration counts
+      make -C cracks_b200/host -s && timeout 300 python tools/miehe_scale.py --refine 7 --steps 3 ;;
     fp32)         # A/B of the multigrid V-cycle precision (pf_mg_lowp.cuh, written in round 1 without a GPU):
                   # Newton-its/s and #LinIts with the FP64 and the FP32 V-cycle; same energies expected
       for f in 0 1; do
