@@ -2,6 +2,10 @@
 # What to run on a GPU box (gpurun -- 'bash tools/gpu_round_checks.sh [step ...]'), cheapest first.
 # Every step is wrapped in `timeout`; a multi-rank hang must never eat the budget again
 # (round 1 lost 53 GPU-minutes to two 300 s tear-down hangs on a 4-GPU box).
+# Suggested first call of a round (1 GPU, about 15 minutes of box time):
+#   bash tools/gpu_round_checks.sh tests bench variants fp32 chunks miehe2d ncu
+# then make the fastest apply variant / V-cycle precision / chunk count the default and re-run `tests bench`;
+# `bench_multi` and the 2-rank half of `fp32` need a multi-GPU box (gpurun --gpus 2|4|8).
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
