@@ -172,7 +172,7 @@ def test_miehe_tension_adaptive_on_the_gpu(pf):
     drv.ctx.close()
 
 
-@pytest.mark.parametrize("name", ["miehe_shear_1", "miehe_tension_adaptive_1"])
+@pytest.mark.parametrize("name", ["miehe_shear_1"] + (["miehe_tension_adaptive_1"] if os.environ.get("PF_SLOW_TESTS") == "1" else []))
 def test_adaptive_miehe_through_the_cli(pf, tmp_path, name):
     """tests/miehe_shear_1.prm and tests/miehe_tension_adaptive_1.prm through `cracks_b200_run --adaptive`:
     predictor-corrector refinement on the slit forest, every row of the golden statistics."""
