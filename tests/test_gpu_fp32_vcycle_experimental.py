@@ -33,7 +33,9 @@ def test_kat1_golden_with_the_fp32_vcycle(pf):
     g, stats, _, _, _ = _run(pf, 0, 32, steps=3)
     for got, ref in zip(stats, g["statistics"]):
         assert got["crack"] == pytest.approx(ref["crack"], rel=1e-8)
-        assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-7)
+        # the bulk energy of the later steps moves by 1e-7 with the Newton stopping point (FP64 cycle: 2e-8,
+        # FP32 cycle: 2e-7 on the emulated library); tests/test_gpu_host_driver.py uses the same 1e-6
+        assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-7 if got["step"] == 0 else 1e-6)
 
 
 @pytest.mark.parametrize("refine", [1, 2])
