@@ -363,7 +363,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": nd / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(8 * 4 * local_nodes), "d2h_bytes_per_step": int(8 * 4 * owned_nodes),
-                    "note": "pf_apply_jacobian with pinned host buffers in the reference's block layout"},
+                    "note": "pf_apply_jacobian with pinned host buffers in the reference's block layout"
+                            + ("; H2D / apply / D2H pipelined over %s chunks of cell layers" % os.environ.get("PF_E2E_CHUNKS", "16")
+                               if world == 1 else "")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_apply3d_v4<16,4,1>" if str(args.variant or os.environ.get("PF_APPLY_VARIANT", "16")) == "16" else "variant %s" % (args.variant or os.environ["PF_APPLY_VARIANT"]), "kernel_ms": k_ms,
