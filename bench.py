@@ -108,7 +108,26 @@ def pinned_array(lib, n, dtype=np.float64):
     return np.frombuffer(buf, dtype=dtype, count=n), p
 
 
-def cpu_reference_sample(steps, warmup, refine=2):
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_refine_for_this_host(requested):
+    """--cpu-refine auto: the BASELINE size (4 refinements: 1.8e9 nnz = 21.6 GB of CSR plus 14 GB of
+    assembly scratch) when the host has the memory for it, else 3 (2.8 GB); the rate is size-normalised."""
+    if requested != "auto":
+        return int(requested)
+    try:
+        avail_kb = next(int(l.split()[1]) for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+    except (OSError, StopIteration):
+        return 3
+    return 4 if avail_kb >= 96 * 1024 * 1024 else 3
+
+
+def cpu_reference_sample(steps, warmup, refine=2, newton=False):
     """The reference's CPU operator apply: assemble the Jacobian into CSR
     (cracks.cc:2200-2468) once, then time its vmult = CSR SpMV (cracks.cc:2770)
     with all host threads.  Bounded sample: Sneddon-3D at `refine` global
@@ -116,6 +135,8 @@ def cpu_reference_sample(steps, warmup, refine=2):
     in this image: no deal.II/Trilinos/p4est/MPI)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import newton_oracle as orc
+    # torchrun exports OMP_NUM_THREADS=1 to its ranks: ask for every core this process may run on
+    orc.lib().pfo_set_num_threads(host_cores())
     prob = orc.sneddon_3d(refine, kappa_of_h=lambda h: 1e-8 * h)
     n = 10 * 2 ** refine
     sol_b, act_b = sneddon_state(n, 20.0 / n)
@@ -147,7 +168,19 @@ def cpu_reference_sample(steps, warmup, refine=2):
     # vmult per GMRES iteration (about 12 per step with a multigrid-quality preconditioner): an upper
     # bound on its Newton-its/s that ignores the AMG set-up, the V-cycles and the residual assemblies
     newton_bound = 1.0 / (t_asm + 12.0 * t)
+    measured = None
+    if newton:
+        # a MEASURED active-set Newton step of the assembled-matrix path (SURVEY.md 8d iii): residual + active
+        # set + assembly + GMRES(1e-8) + one line-search residual, at 3 refinements (about 20 s of CPU work)
+        import cpu_newton
+        del val, col, rowptr
+        measured = cpu_newton.time_one_newton_step(refine=min(refine, 3), threads=host_cores())
     return {
+        "newton_its_per_s": measured["newton_its_per_s"] if measured else None,
+        "newton_sample": ("one active-set Newton step (cracks.cc:2780-2994) of the assembled-matrix CPU path at %d DoF: "
+                          "%.1f s = residual + active set + CSR assembly + %d GMRES iterations (%s) to 1e-8 + one "
+                          "line-search residual" % (measured["n_dofs"], measured["wall_s"], measured["linear_its"],
+                                                    measured["preconditioner"])) if measured else None,
         "value": prob.n_dofs / t / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": (f"CSR SpMV (the reference's vmult) on Sneddon-3D at {refine} global refinements: "
                    f"{prob.n_dofs} DoF, {col.shape[0]} nnz, {steps} applies after {warmup} warm-ups; "
@@ -159,18 +192,39 @@ def cpu_reference_sample(steps, warmup, refine=2):
     }
 
 
+def kernel_info(variant):
+    """name, FP64 instructions per cell and captured DRAM traffic of the apply kernel variant (profiles/kernels.json,
+    written from the SASS / ncu captures named there)"""
+    p = os.path.join(ROOT, "profiles", "kernels.json")
+    info = json.load(open(p)) if os.path.exists(p) else {}
+    k = dict(info.get("kernels", {}).get(str(variant), {"name": "apply variant %s" % variant}))
+    k.setdefault("fp64_peak_tinst_per_s", info.get("fp64_peak_tinst_per_s"))
+    if not k.get("fp64_peak_tinst_per_s"):
+        k.pop("fp64_inst_per_cell", None)
+    return k
+
+
+def workload_config(refine, world):
+    """`config` of both arms (identical by construction: the CPU arm times a bounded sample of this workload)"""
+    n = 10 * 2 ** refine
+    nn = (n + 1) ** 3
+    return {"workload": f"Sneddon-3D operator apply y=J(U)x (parameters_sneddon_3d.prm, Global pre-refinement "
+                        f"steps = {refine}): {n}^3 cells Q1, {nn} nodes, {4 * nn} DoF",
+            "parallelism": f"z-slab x{world}" if world > 1 else "single GPU"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    cb = cpu_reference_sample(args.steps, args.warmup, refine=args.cpu_refine)
-    n = 10 * 2 ** args.refine
+    refine = cpu_refine_for_this_host(args.cpu_refine)
+    cb = cpu_reference_sample(args.steps, args.warmup, refine=refine)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_apply"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Sneddon-3D operator apply (parameters_sneddon_3d.prm), {n}^3 cells Q1; CPU arm "
-                               f"timed on a bounded sample at {args.cpu_refine} refinements ({cb['n_dofs']} DoF)",
-                   "timing": "host wall clock around OpenMP CSR SpMV"},
+        "config": workload_config(args.refine, args.gpus),
+        "timing": f"host wall clock around the OpenMP CSR SpMV, {cb['cores']} threads; bounded sample of the workload at "
+                  f"{refine} refinements ({cb['n_dofs']} DoF), the rate is per DoF",
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -185,7 +239,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--refine", type=int, default=4, help="global pre-refinement steps (4 -> 16.7M DoF)")
-    ap.add_argument("--cpu-refine", type=int, default=3)
+    ap.add_argument("--cpu-refine", default="auto", help="refinements of the CPU arm's sample: 3, 4 or auto (4 if the host has >= 96 GB free)")
+    ap.add_argument("--no-cpu-newton", action="store_true", help="skip the measured CPU Newton step (about 20 s)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-newton", action="store_true")
@@ -221,13 +276,35 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     nccl_id = fresh_nccl_id()
 
+    parity = None
+    if world > 1:
+        # multi-GPU parity record (outside every timed region; the oracle is the checker): apply / residual /
+        # diagonal / functionals of the slab-decomposed path on `world` ranks against the single-domain CPU oracle
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import newton_oracle as orc
+        from mgpu_check import small_mesh_parity
+
+        def allsum(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+
+        errs = small_mesh_parity(pf, orc, rank, world, local_rank, nccl_id, allsum)
+        if rank == 0:
+            parity = {"n_ranks": world, "jv_relerr": errs["apply"], "residual_relerr": max(errs["r_pde"], errs["r_total"]),
+                      "diag_relerr": errs["diag"], "crack_energy_relerr": errs["crack"], "bulk_energy_relerr": errs["bulk"],
+                      "against": "single-domain CPU oracle, 12 x 9 x %d cells" % max(10, 3 * world),
+                      "ok": bool(all(v <= 1e-11 for v in errs.values()))}
+        nccl_id = fresh_nccl_id()
+
     mesh = pf.sneddon_mesh(3, args.refine)
     params = pf.sneddon_params(mesh)
     n = mesh.n[0]
     ctx = pf.PhaseFieldContext(mesh, params, device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id)
     lib = ctx.lib
     if args.variant:
-        lib.pf_debug_set_variant(args.variant)
+        lib.pf_debug_set_variant(ctx.h, args.variant)
     nd, nn = ctx.n_dofs, ctx.n_nodes
 
     sol, active = sneddon_state(n, mesh.h[0])
@@ -347,36 +424,48 @@ def main():
         b_alg = 24 * 4 * local_nodes + 9 * local_nodes
         k_ms = kern_ms / max(kern_cnt, 1)
         achieved = b_alg / (k_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        kinfo = kernel_info(args.variant or int(os.environ.get("PF_APPLY_VARIANT", "0")) or "default")
+        # DRAM bytes of one launch from the committed ncu capture of the same kernel at this size; only quoted
+        # for the launch it was captured on (one GPU, the whole mesh)
+        traffic = kinfo.get("dram_bytes_per_launch") if (world == 1 and args.refine == 4) else None
+        local_cells = (lay.plane_end - lay.plane_begin - 1) * n * n      # incl. the redundant layer of a slab
+        fp64 = None
+        if kinfo.get("fp64_inst_per_cell"):
+            # the resource that binds an exact FP64 evaluation: thread-level FP64 instructions (DFMA / DADD / DMUL share one
+            # pipe) per second against the DFMA issue rate measured on this pool (tools/fp64_peak.cu)
+            rate = kinfo["fp64_inst_per_cell"] * local_cells / (k_ms * 1e-3) / 1e12
+            fp64 = {"bound": "fp64", "achieved": rate, "peak": kinfo["fp64_peak_tinst_per_s"], "unit": "T FP64 inst/s",
+                    "frac": rate / kinfo["fp64_peak_tinst_per_s"], "fp64_inst_per_cell": kinfo["fp64_inst_per_cell"],
+                    "source": kinfo.get("source")}
         line = {
             "metric": METRIC, "value": nd / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Sneddon-3D operator apply y=J(U)x (parameters_sneddon_3d.prm, Global "
-                                   f"pre-refinement steps = {args.refine}): {n}^3 cells Q1, {nn} nodes, {nd} DoF",
-                       "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: x, y, U are 3 x %.0f MB per GPU vs 126 MB L2" % (8 * 4 * local_nodes / 1e6),
-                       "timing": "CUDA events on the library stream, max over ranks"},
+            "config": workload_config(args.refine, world),
+            "timing": "CUDA events on the library stream, max over ranks; inputs larger than L2: x, y, U are 3 x %.0f MB "
+                      "per GPU vs 126 MB L2" % (8 * 4 * local_nodes / 1e6),
             "clocks": clocks,
             "e2e": {"value": nd / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(8 * 4 * local_nodes), "d2h_bytes_per_step": int(8 * 4 * owned_nodes),
-                    "note": "pf_apply_jacobian with pinned host buffers in the reference's block layout"
-                            + ("; H2D / apply / D2H pipelined over %s chunks of cell layers" % os.environ.get("PF_E2E_CHUNKS", "16")
-                               if world == 1 else "")},
+                    "note": "pf_apply_jacobian with pinned host buffers in the reference's block layout; H2D / apply / D2H "
+                            "pipelined over chunks of cell layers"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_apply3d_v4<16,4,1>" if str(args.variant or os.environ.get("PF_APPLY_VARIANT", "16")) == "16" else "variant %s" % (args.variant or os.environ["PF_APPLY_VARIANT"]), "kernel_ms": k_ms,
+                         "traffic": traffic, "kernel": kinfo["name"], "kernel_ms": k_ms,
                          "kernel_share_of_step": kern_ms / ms_total, "algorithmic_bytes": b_alg, "peak_source": peak_src,
-                         "note": "FP64-pipe bound: exact 27-point FP64 quadrature, no f64 tensor path (DESIGN.md)"},
+                         "binding_resource": "fp64 pipe (see roofline_fp64): exact 27-point FP64 quadrature, no f64 tensor "
+                                             "path on sm_100a (DESIGN.md 5.1)"},
         }
+        if fp64:
+            line["roofline_fp64"] = fp64
+        if parity is not None:
+            line["parity"] = parity
         if newton is not None:
             line["newton"] = newton
-        if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference_sample(10, 2, refine=args.cpu_refine)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if not args.no_cpu_baseline:
+            cb = cpu_reference_sample(10, 2, refine=3, newton=not args.no_cpu_newton)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "newton_its_per_s",
+                                                       "newton_sample")}
         print(json.dumps(line))
     ctx.device_vector_free(x_dev)
     ctx.device_vector_free(y_dev)

@@ -127,9 +127,9 @@ _SIGS = {
     "pf_download": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_host_alloc": [C.POINTER(C.c_void_p), C.c_size_t],
     "pf_host_free": [C.c_void_p],
-    "pf_debug_force_generic": [C.c_int],
-    "pf_debug_disable_iso": [C.c_int],
-    "pf_debug_set_variant": [C.c_int],
+    "pf_debug_force_generic": [C.c_void_p, C.c_int],
+    "pf_debug_disable_iso": [C.c_void_p, C.c_int],
+    "pf_debug_set_variant": [C.c_void_p, C.c_int],
     "pf_profile_enable": [C.c_void_p, C.c_int],
     "pf_profile_read": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
 }

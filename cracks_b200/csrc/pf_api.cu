@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cmath>
 #include <map>
+#include <set>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -20,9 +21,11 @@
 #include "../../include/cracks_b200.h"
 #include "pf_apply3d.cuh"
 #include "pf_apply3d_v2.cuh"
-#include "pf_apply3d_v3.cuh"
 #include "pf_apply3d_v4.cuh"
+#ifdef PF_TUNING_VARIANTS // earlier generations and tuning experiments of the apply kernel: `make TUNING=1`, A/B runs only
+#include "pf_apply3d_v3.cuh"
 #include "pf_apply3d_v5.cuh"
+#endif
 #include "pf_common.cuh"
 #include "pf_forest.cuh"
 #include "pf_generic.cuh"
@@ -174,6 +177,14 @@ struct pf_ctx
   double *lame_dev = nullptr, *lame_energy_dev = nullptr, *level_h_dev = nullptr;
   double *fx = nullptr;               // distributed copy of the input vector of an apply
   uint8_t *zero_mask = nullptr;       // "nothing constrained", for the hanging-node-only constraint set
+  // tuning / debugging switches (per context; the environment is read once, by pf_create)
+  int apply_variant = 16;      // 16 = default exact kernel; other numbers only in a PF_TUNING_VARIANTS build
+  int force_generic = 0;       // pf_debug_force_generic: the thread-per-cell second implementation
+  int no_iso = 0;              // pf_debug_disable_iso: general (anisotropic) code path on cubic cells
+  bool no_overlap = false;     // PF_NO_OVERLAP: halo exchange not overlapped with the interior layers (A/B)
+  bool split_boundary = false; // PF_SPLIT_BOUNDARY: two boundary launches of a middle slab instead of one (A/B)
+  bool mg_use_graph = false;   // PF_MG_GRAPH=1
+  std::set<const void *> attr_done; // kernels whose per-device function attributes this context has set
   double last_rnorm = 0;
   long long launches = 0;
   bool profiling = false;
@@ -463,6 +474,7 @@ refresh_extrapolation (pf_ctx *ctx)
 }
 
 // ---- the operator application on device vectors (local slab) -------------
+#ifdef PF_TUNING_VARIANTS
 template <int TX, int TY, int TZ>
 int
 launch_apply3d (pf_ctx *ctx, const double *x, double *y)
@@ -471,12 +483,11 @@ launch_apply3d (pf_ctx *ctx, const double *x, double *y)
   const Grid &g = ctx->g;
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
-  static bool attr_set = false;
-  if (!attr_set)
+  static const char attr_tag = 0; // one address per template instantiation
+  if (ctx->attr_done.insert (&attr_tag).second)
     {
       CU (cudaFuncSetAttribute (k_apply3d<TX, TY, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
-      attr_set = true;
     }
   k_apply3d<TX, TY, TZ><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes, ctx->stream>>> (
     g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
@@ -484,9 +495,6 @@ launch_apply3d (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
-int g_no_iso = 0;
-// A/B switch: evaluate the two boundary layers of a middle slab in two launches (as before) instead of one
-const bool g_split_boundary = getenv ("PF_SPLIT_BOUNDARY") != nullptr;
 
 template <int TX, int TY, int TZ, int MINB = 2, int NQ = 3>
 int
@@ -502,17 +510,16 @@ launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
     }
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
-  static bool attr_set = false;
-  if (!attr_set)
+  static const char attr_tag = 0; // one address per template instantiation
+  if (ctx->attr_done.insert (&attr_tag).second)
     {
       CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ, MINB, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
       CU (cudaFuncSetAttribute (k_apply3d_v2<TX, TY, TZ, MINB, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
-      attr_set = true;
     }
   // cubic cells (every mesh the reference's 3-D cases use): gradient scales folded into constants
-  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
   const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
   if (iso)
     k_apply3d_v2<TX, TY, TZ, MINB, NQ, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
@@ -524,8 +531,8 @@ launch_apply3d_v2 (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
-// 16 = k_apply3d_v4<16,4,1> (default); 3 = k_apply3d_v2<16,4,1>; others: tuning variants kept for A/B runs
-int g_apply_variant = getenv ("PF_APPLY_VARIANT") ? atoi (getenv ("PF_APPLY_VARIANT")) : 16;
+
+#endif // PF_TUNING_VARIANTS
 
 template <int TX, int TY, int TZ, int MINB = 2, int NQ = 3>
 int
@@ -541,8 +548,8 @@ launch_apply3d_v4 (pf_ctx *ctx, const double *x, double *y)
     }
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
-  static bool attr_set = false;
-  if (!attr_set)
+  static const char attr_tag = 0; // one address per template instantiation
+  if (ctx->attr_done.insert (&attr_tag).second)
     {
       CU (cudaFuncSetAttribute (k_apply3d_v4<TX, TY, TZ, MINB, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
@@ -556,9 +563,8 @@ launch_apply3d_v4 (pf_ctx *ctx, const double *x, double *y)
           CU (cudaFuncSetAttribute (k_apply3d_v4<TX, TY, TZ, MINB, NQ, true>,
                                     cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         }
-      attr_set = true;
     }
-  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
   const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
   if (iso)
     k_apply3d_v4<TX, TY, TZ, MINB, NQ, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
@@ -570,6 +576,7 @@ launch_apply3d_v4 (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
+#ifdef PF_TUNING_VARIANTS
 // v4 under an explicit register cap (k_apply3d_v4_maxr)
 template <int TX, int TY, int TZ, int MAXR>
 int
@@ -585,8 +592,8 @@ launch_apply3d_v4_maxr (pf_ctx *ctx, const double *x, double *y)
     }
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
-  static bool attr_set = false;
-  if (!attr_set)
+  static const char attr_tag = 0; // one address per template instantiation
+  if (ctx->attr_done.insert (&attr_tag).second)
     {
       CU (cudaFuncSetAttribute (k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
@@ -594,9 +601,8 @@ launch_apply3d_v4_maxr (pf_ctx *ctx, const double *x, double *y)
                                 (int) T::smem_bytes));
       CU (cudaFuncSetAttribute (k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       CU (cudaFuncSetAttribute (k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      attr_set = true;
     }
-  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
   const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
   if (iso)
     k_apply3d_v4_maxr<TX, TY, TZ, MAXR, 3, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
@@ -623,8 +629,8 @@ launch_apply3d_v5 (pf_ctx *ctx, const double *x, double *y)
     }
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
-  static bool attr_set = false;
-  if (!attr_set)
+  static const char attr_tag = 0; // one address per template instantiation
+  if (ctx->attr_done.insert (&attr_tag).second)
     {
       CU (cudaFuncSetAttribute (k_apply3d_v5<TX, TY, TZ, MINB, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) T::smem_bytes));
@@ -632,9 +638,8 @@ launch_apply3d_v5 (pf_ctx *ctx, const double *x, double *y)
                                 (int) T::smem_bytes));
       CU (cudaFuncSetAttribute (k_apply3d_v5<TX, TY, TZ, MINB, 3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       CU (cudaFuncSetAttribute (k_apply3d_v5<TX, TY, TZ, MINB, 3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      attr_set = true;
     }
-  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
   const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
   if (iso)
     k_apply3d_v5<TX, TY, TZ, MINB, 3, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
@@ -646,16 +651,21 @@ launch_apply3d_v5 (pf_ctx *ctx, const double *x, double *y)
   return PF_OK;
 }
 
+#endif // PF_TUNING_VARIANTS
+
 // the tiled kernel the library uses by default (exact 27-point rule, or the
 // 2-point rule of the preconditioner-only operator)
 int
 launch_tiled_default (pf_ctx *ctx, const double *x, double *y, bool approx)
 {
-  if (g_apply_variant == 16)
-    return approx ? launch_apply3d_v4<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v4<16, 4, 1> (ctx, x, y);
-  return approx ? launch_apply3d_v2<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v2<16, 4, 1> (ctx, x, y);
+#ifdef PF_TUNING_VARIANTS
+  if (ctx->apply_variant == 3)
+    return approx ? launch_apply3d_v2<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v2<16, 4, 1> (ctx, x, y);
+#endif
+  return approx ? launch_apply3d_v4<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v4<16, 4, 1> (ctx, x, y);
 }
 
+#ifdef PF_TUNING_VARIANTS
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda)
 typedef CUresult (*pfn_encode_tiled) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                       const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -700,12 +710,11 @@ launch_apply3d_v3 (pf_ctx *ctx, const double *x, double *y)
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = (g.cell_end - g.cell_begin + TZ - 1) / TZ;
   const int n_tiles = tiles_x * tiles_y * tiles_z;
-  static bool attr_set = false;
-  if (!attr_set)
+  static const char attr_tag = 0; // one address per template instantiation
+  if (ctx->attr_done.insert (&attr_tag).second)
     {
       CU (cudaFuncSetAttribute (k_apply3d_v3<TX, TY, TZ, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) L::smem_bytes));
-      attr_set = true;
     }
   CUtensorMap tm_x, tm_s, tm_a;
   int rc;
@@ -722,7 +731,8 @@ launch_apply3d_v3 (pf_ctx *ctx, const double *x, double *y)
   ctx->tile_epoch += (unsigned long long) n_tiles + (unsigned long long) grid;
   return PF_OK;
 }
-int g_force_generic = 0;
+
+#endif // PF_TUNING_VARIANTS
 
 // ---- hanging nodes of forest meshes (no-ops on box meshes) -------------------------------
 int
@@ -812,9 +822,9 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
   // two) boundary layers follow once the planes have arrived.
   const int lo_b = g.cell_begin + (ctx->rank > 0 ? 1 : 0);
   const int hi_b = g.cell_end - (ctx->rank < ctx->nranks - 1 ? 1 : 0);
-  static const bool no_overlap = getenv ("PF_NO_OVERLAP") != nullptr; // A/B switch for measurements
-  const bool overlap = !no_overlap && ctx->nranks > 1 && ctx->dim == 3 && !g_force_generic
-                       && (approx || g_apply_variant == 3 || g_apply_variant == 16) && hi_b > lo_b;
+  const bool no_overlap = ctx->no_overlap;
+  const bool overlap = !no_overlap && ctx->nranks > 1 && ctx->dim == 3 && !ctx->force_generic
+                       && (approx || ctx->apply_variant == 3 || ctx->apply_variant == 16) && hi_b > lo_b;
   if (overlap)
     {
       CU (cudaEventRecord (ctx->ev_x, ctx->stream));
@@ -837,7 +847,7 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
     {
       k_apply_init<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
       KCHECK ();
-      if (g_force_generic)
+      if (ctx->force_generic)
         {
           k_apply_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
             g, ctx->p, (const FeTab<3> *) ctx->fetab, x, ctx->sol, ctx->pt, ctx->mask, y);
@@ -866,7 +876,7 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
               if ((rc = run (lo_b, hi_b)))
                 return rc;
               CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
-              if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !g_split_boundary)
+              if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !ctx->split_boundary)
                 {
                   // a slab in the middle: its two boundary layers in ONE launch (each alone is less than a wave)
                   if ((rc = run (g.cell_begin, g.cell_end, g.cell_end - 1 - g.cell_begin)))
@@ -893,7 +903,8 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
                 return rc;
               return PF_OK;
             }
-          switch (g_apply_variant)
+#ifdef PF_TUNING_VARIANTS
+          switch (ctx->apply_variant)
             {
             case 1: rc = launch_apply3d<16, 4, 2> (ctx, x, y); break;
             case 2: rc = launch_apply3d_v2<16, 4, 2> (ctx, x, y); break;
@@ -921,6 +932,9 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
             case 21: rc = launch_apply3d_v4_maxr<16, 4, 1, 184> (ctx, x, y); break;
             default: rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y); break; // variant 16: fastest measured
             }
+#else
+          rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y);
+#endif
           if (rc)
             return rc;
           if (ctx->profiling)
@@ -953,19 +967,18 @@ residual_dev (pf_ctx *ctx, double *l2)
     }
   else
     {
-      if (g_force_generic || ctx->forest)
+      if (ctx->force_generic || ctx->forest)
         k_residual_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
           g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
       else
         {
           using TR = TileR3<16, 4, 1>;
           const int tiles_x = (g.n[0] + 15) / 16, tiles_y = (g.n[1] + 3) / 4, tiles_z = g.cell_end - g.cell_begin;
-          static bool attr_set = false;
-          if (!attr_set)
+          static const char attr_tag = 0; // one address per template instantiation
+          if (ctx->attr_done.insert (&attr_tag).second)
             {
               CU (cudaFuncSetAttribute (k_residual3d<16, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int) TR::smem_bytes));
-              attr_set = true;
             }
           k_residual3d<16, 4, 1, 2><<<(unsigned) tiles_x * tiles_y * tiles_z, TR::NT, TR::smem_bytes, ctx->stream>>> (
             g, ctx->p, ctx->k3, tiles_x, tiles_y, ctx->sol, ctx->pt, ctx->r_total);
@@ -1185,6 +1198,9 @@ mg_setup_level (pf_ctx *ctx)
   c->mg_approx = ctx->mg_approx;
   c->coarsest_degree = ctx->coarsest_degree;
   c->mg_fp32 = ctx->mg_fp32;
+  c->apply_variant = ctx->apply_variant;
+  c->no_iso = ctx->no_iso;
+  c->force_generic = ctx->force_generic;
   Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}, c->g.plane_begin},
     df{{ctx->g.nn[0], ctx->g.nn[1], ctx->g.nn[2]}, ctx->g.plane_begin};
   int rc;
@@ -1428,7 +1444,7 @@ launch_apply3d_mg (pf_ctx *ctx, const float *x, float *y)
     }
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
-  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !g_no_iso;
+  const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
   const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
   if (iso)
     k_apply3d_mg<float, TX, TY, TZ, MINB, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
@@ -1448,7 +1464,7 @@ apply_lowp (pf_ctx *ctx, float *x, float *y)
   const Grid &g = ctx->g;
   const int lo_b = g.cell_begin + (ctx->rank > 0 ? 1 : 0);
   const int hi_b = g.cell_end - (ctx->rank < ctx->nranks - 1 ? 1 : 0);
-  static const bool no_overlap = getenv ("PF_NO_OVERLAP") != nullptr;
+  const bool no_overlap = ctx->no_overlap;
   const bool overlap = !no_overlap && ctx->nranks > 1 && hi_b > lo_b;
   if (overlap)
     {
@@ -1477,7 +1493,7 @@ apply_lowp (pf_ctx *ctx, float *x, float *y)
   if ((rc = run (lo_b, hi_b)))
     return rc;
   CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
-  if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !g_split_boundary)
+  if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !ctx->split_boundary)
     return run (g.cell_begin, g.cell_end, g.cell_end - 1 - g.cell_begin);
   if (ctx->rank > 0 && (rc = run (g.cell_begin, lo_b)))
     return rc;
@@ -1599,7 +1615,7 @@ precond_apply (pf_ctx *ctx, const double *v, double *z)
   // Opt-in (PF_MG_GRAPH=1), single rank only.  Measured on B200 at 16.7 M DoF: 9.27 vs 9.26
   // Newton-its/s, i.e. the V-cycle is not launch-bound on one GPU; with NCCL nodes in the graph
   // (2 and 4 ranks) the solve ran but the processes hung at tear-down, so it stays off there.
-  static const bool use_graph = getenv ("PF_MG_GRAPH") && atoi (getenv ("PF_MG_GRAPH")) == 1;
+  const bool use_graph = ctx->mg_use_graph;
   if (ctx->precond == 1 && ctx->mg_ready && ctx->coarse && use_graph && ctx->nranks == 1 && !ctx->profiling
       && !g_trace.on)
     {
@@ -1680,11 +1696,13 @@ diag_and_aux (pf_ctx *ctx)
   int rc = halo_exchange (ctx, ctx->diag, ctx->nc);
   if (rc)
     return rc;
+#ifdef PF_TUNING_VARIANTS
   if (ctx->dim == 3)
     {
       k_pack_aux<<<nblk (g.n_local_nodes, 256), 256, 0, ctx->stream>>> (g.n_local_nodes, ctx->pt, ctx->mask, ctx->aux);
       KCHECK ();
     }
+#endif
   return PF_OK;
 }
 
@@ -1900,6 +1918,14 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
   ctx->rank = rank;
   ctx->nranks = nranks;
   ctx->prm = *params;
+  // A/B switches for measurements: read once per context, here
+  ctx->no_overlap = getenv ("PF_NO_OVERLAP") != nullptr;
+  ctx->split_boundary = getenv ("PF_SPLIT_BOUNDARY") != nullptr;
+  ctx->mg_use_graph = getenv ("PF_MG_GRAPH") && atoi (getenv ("PF_MG_GRAPH")) == 1;
+#ifdef PF_TUNING_VARIANTS
+  if (getenv ("PF_APPLY_VARIANT"))
+    ctx->apply_variant = atoi (getenv ("PF_APPLY_VARIANT"));
+#endif
   CU (cudaSetDevice (device));
   CU (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
   CU (cudaStreamCreateWithFlags (&ctx->comm_stream, cudaStreamNonBlocking));
@@ -1977,9 +2003,13 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
   CU (cudaMalloc (&ctx->pt, nn * sizeof (double)));
   CU (cudaMalloc (&ctx->mass, nn * sizeof (double)));
   CU (cudaMalloc (&ctx->mask, nn));
+#ifdef PF_TUNING_VARIANTS
+#ifdef PF_TUNING_VARIANTS
   CU (cudaMalloc (&ctx->aux, nn * sizeof (double2)));
   CU (cudaMalloc (&ctx->tile_counter, sizeof (unsigned long long)));
+#endif
   CU (cudaMemsetAsync (ctx->tile_counter, 0, sizeof (unsigned long long), ctx->stream));
+#endif
   CU (cudaDeviceGetAttribute (&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   CU (cudaMalloc (&ctx->stage8, nd));
   CU (cudaMalloc (&ctx->cycle, nn * sizeof (int)));
@@ -2106,8 +2136,10 @@ create_forest_impl (const pf_forest_mesh *fm, const pf_params *params, int devic
   CU (cudaMalloc (&ctx->mass, nn * sizeof (double)));
   CU (cudaMalloc (&ctx->mask, nn));
   CU (cudaMalloc (&ctx->zero_mask, nn));
+#ifdef PF_TUNING_VARIANTS
   CU (cudaMalloc (&ctx->aux, nn * sizeof (double2)));
   CU (cudaMalloc (&ctx->tile_counter, sizeof (unsigned long long)));
+#endif
   CU (cudaDeviceGetAttribute (&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   CU (cudaMalloc (&ctx->stage8, nd));
   CU (cudaMalloc (&ctx->cycle, nn * sizeof (int)));
@@ -2295,6 +2327,7 @@ pf_synchronize (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   CU (cudaStreamSynchronize (ctx->stream));
   return PF_OK;
 }
@@ -2345,6 +2378,7 @@ pf_get_solution (pf_ctx *ctx, double *sol)
 {
   if (!ctx || !sol)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   return download_block (ctx, ctx->sol, sol);
 }
 
@@ -2353,6 +2387,7 @@ pf_get_state (pf_ctx *ctx, int which, double *out)
 {
   if (!ctx || !out || which < 0 || which > 2)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   return download_block (ctx, which == 0 ? ctx->sol : (which == 1 ? ctx->old : ctx->oldold), out);
 }
 
@@ -2361,6 +2396,7 @@ pf_update_solution (pf_ctx *ctx, double alpha)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->n_local_dofs, alpha, ctx->dx, ctx->sol);
   KCHECK ();
   ctx->jac_ready = false;
@@ -2373,6 +2409,7 @@ pf_set_constraints (pf_ctx *ctx, const uint8_t *dirichlet_mask, const uint8_t *a
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   const Grid &g = ctx->g;
   const int dim = ctx->dim;
   const long long n0 = (long long) g.plane_begin * g.nodes_per_plane, nl = g.n_local_nodes;
@@ -2408,6 +2445,7 @@ pf_set_dirichlet_all_faces (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   if (ctx->forest)
     return fail (ctx, PF_UNSUPPORTED, "forest meshes take their Dirichlet rows from pf_set_constraints");
   const long long nl = ctx->g.n_local_nodes;
@@ -2506,6 +2544,7 @@ pf_apply_jacobian_dev (pf_ctx *ctx, double *x_dev, double *y_dev)
 {
   if (!ctx || !x_dev || !y_dev)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   return apply_dev (ctx, x_dev, y_dev);
 }
 
@@ -2516,8 +2555,8 @@ pf_apply_jacobian (pf_ctx *ctx, const double *x, double *y)
     return PF_BAD_ARG;
   CU (cudaSetDevice (ctx->device));
   int rc;
-  if (ctx->dim == 3 && ctx->nranks == 1 && !g_force_generic && !ctx->forest
-      && (g_apply_variant == 3 || g_apply_variant == 16) && ctx->g.n[2] >= 16)
+  if (ctx->dim == 3 && ctx->nranks == 1 && !ctx->force_generic && !ctx->forest
+      && (ctx->apply_variant == 3 || ctx->apply_variant == 16) && ctx->g.n[2] >= 16)
     return apply_host_pipelined (ctx, x, y);
   if ((rc = upload_block (ctx, x, ctx->xa)))
     return rc;
@@ -2547,6 +2586,7 @@ pf_jacobian_diagonal (pf_ctx *ctx, double *diag)
 {
   if (!ctx || !diag || !ctx->jac_ready)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   return download_block (ctx, ctx->diag, diag);
 }
 
@@ -2555,6 +2595,7 @@ pf_lumped_mass (pf_ctx *ctx, double *mass)
 {
   if (!ctx || !mass)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   const Grid &g = ctx->g;
   const long long lo = ctx->owned_lo, cnt = ctx->owned_hi - ctx->owned_lo;
   CU (cudaMemcpyAsync (mass + (long long) g.plane_begin * g.nodes_per_plane + lo, ctx->mass + lo,
@@ -2588,6 +2629,7 @@ pf_active_set_reset (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   const long long nl = ctx->g.n_local_nodes;
   if (ctx->dim == 2)
     k_clear_active<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask, ctx->cycle);
@@ -2720,14 +2762,14 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
   int its = 0;
   if (n_it)
     *n_it = 0;
-  if (!(bnorm > 0))
+  if (!std::isfinite (bnorm))
+    return fail (ctx, PF_NUMERIC, "non-finite right-hand side in pf_solve");
+  if (bnorm == 0.0)
     {
       if (dx)
         return download_block (ctx, x, dx);
       return PF_OK;
     }
-  if (!std::isfinite (bnorm))
-    return fail (ctx, PF_NUMERIC, "non-finite right-hand side in pf_solve");
 
   std::vector<double> H ((size_t) (m + 1) * m), cs (m), sn (m), gvec (m + 1), yv (m);
   double res = bnorm;
@@ -2956,6 +2998,7 @@ pf_dirichlet_miehe (pf_ctx *ctx, int kind, double time, int set_values)
 {
   if (!ctx || (kind != 1 && kind != 2))
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   if (ctx->dim != 2 || ctx->g.slit_row < 0 || ctx->forest)
     return fail (ctx, PF_UNSUPPORTED, "the Miehe boundary data need the 2-D slit mesh");
   const long long nl = ctx->g.n_local_nodes;
@@ -2971,6 +3014,7 @@ pf_interpolate_unbroken (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   // InitialValuesTensionOrShear / InitialValuesNoCrack: u = 0, phi = 1 (cracks.cc:679-691, 727-737)
   const long long nl = ctx->g.n_local_nodes;
   CU (cudaMemsetAsync (ctx->sol, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
@@ -2992,6 +3036,7 @@ pf_load (pf_ctx *ctx, double *load_x, double *load_y)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   if (ctx->dim != 2 || ctx->nranks != 1 || ctx->forest)
     return fail (ctx, PF_UNSUPPORTED, "pf_load: 2-D box / slit mesh, single rank (the reference's load tests are 2-D)");
   CU (cudaMemsetAsync (ctx->red, 0, 2 * sizeof (double), ctx->stream));
@@ -3064,6 +3109,7 @@ pf_phase_field_min (pf_ctx *ctx, double *phi_min)
 {
   if (!ctx || !phi_min)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   k_one_minus_phi_max<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->owned_lo, ctx->owned_hi, ctx->nc, ctx->sol,
                                                                     ctx->partial);
   KCHECK ();
@@ -3083,6 +3129,7 @@ pf_project_phase_field (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   const long long nl = ctx->g.n_local_nodes;
   if (ctx->dim == 2)
     k_project_phi<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->sol);
@@ -3101,6 +3148,7 @@ pf_interpolate_sneddon (pf_ctx *ctx, double h_diam)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   if (ctx->forest)
     return fail (ctx, PF_UNSUPPORTED, "the initial condition of a forest mesh is interpolated by the host (pf_set_state)");
   const long long nl = ctx->g.n_local_nodes;
@@ -3122,6 +3170,7 @@ pf_advance_timestep (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   // old_old_solution = old_solution; old_solution = solution (cracks.cc:4302-4303)
   std::swap (ctx->old, ctx->oldold);
   CU (cudaMemcpyAsync (ctx->old, ctx->sol, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice,
@@ -3151,6 +3200,7 @@ pf_timestep_difference (pf_ctx *ctx, double *linfty)
 {
   if (!ctx || !linfty)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   const long long lo = ctx->owned_lo * ctx->nc, hi = ctx->owned_hi * ctx->nc;
   k_absdiff_max<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (lo, hi, ctx->old, ctx->sol, ctx->partial);
   KCHECK ();
@@ -3170,6 +3220,7 @@ pf_restore_old_solution (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   CU (cudaMemcpyAsync (ctx->sol, ctx->old, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice,
                        ctx->stream));
   ctx->jac_ready = false;
@@ -3183,6 +3234,7 @@ pf_save_solution (pf_ctx *ctx)
   // saved_solution = solution (cracks.cc:2922)
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   CU (cudaMemcpyAsync (ctx->saved, ctx->sol, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice,
                        ctx->stream));
   return PF_OK;
@@ -3193,6 +3245,7 @@ pf_restore_saved_solution (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   CU (cudaMemcpyAsync (ctx->sol, ctx->saved, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice,
                        ctx->stream));
   // r_total deliberately stays that of the rejected trial (cracks.cc:2947-2955)
@@ -3206,6 +3259,7 @@ pf_scale_update (pf_ctx *ctx, double factor)
   // newton_update *= line_search_damping (cracks.cc:2956)
   if (!ctx)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->n_local_dofs, ctx->hdev, factor, 0, ctx->dx,
                                                             ctx->dx);
   KCHECK ();
@@ -3237,6 +3291,7 @@ pf_upload (pf_ctx *ctx, const double *host_block, double *dev)
 {
   if (!ctx || !host_block || !dev)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   return upload_block (ctx, host_block, dev);
 }
 
@@ -3245,6 +3300,7 @@ pf_download (pf_ctx *ctx, const double *dev, double *host_block)
 {
   if (!ctx || !host_block || !dev)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   return download_block (ctx, dev, host_block);
 }
 
@@ -3276,6 +3332,7 @@ pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count)
   // the launches since the last read, on the launching stream
   if (!ctx || !total_ms || !count)
     return PF_BAD_ARG;
+  CU (cudaSetDevice (ctx->device));
   CU (cudaStreamSynchronize (ctx->stream));
   double tot = 0;
   for (auto &pr : ctx->prof_events)
@@ -3292,26 +3349,41 @@ pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count)
   return PF_OK;
 }
 
+// every level of the context's multigrid hierarchy follows the switch
 int
-pf_debug_set_variant (int variant)
+pf_debug_set_variant (pf_ctx *ctx, int variant)
 {
+  if (!ctx)
+    return PF_BAD_ARG;
+#ifdef PF_TUNING_VARIANTS
   if (variant < 1 || variant > 21)
     return PF_BAD_ARG;
-  g_apply_variant = variant;
+#else
+  if (variant != 16)
+    return fail (ctx, PF_UNSUPPORTED, "apply-kernel variant %d is a tuning variant: build with `make TUNING=1`", variant);
+#endif
+  for (pf_ctx *c = ctx; c; c = c->coarse)
+    c->apply_variant = variant;
   return PF_OK;
 }
 
 int
-pf_debug_disable_iso (int on)
+pf_debug_disable_iso (pf_ctx *ctx, int on)
 {
-  g_no_iso = on;
+  if (!ctx)
+    return PF_BAD_ARG;
+  for (pf_ctx *c = ctx; c; c = c->coarse)
+    c->no_iso = on;
   return PF_OK;
 }
 
 int
-pf_debug_force_generic (int on)
+pf_debug_force_generic (pf_ctx *ctx, int on)
 {
-  g_force_generic = on;
+  if (!ctx)
+    return PF_BAD_ARG;
+  for (pf_ctx *c = ctx; c; c = c->coarse)
+    c->force_generic = on;
   return PF_OK;
 }
 

@@ -287,7 +287,7 @@ FracturePhaseFieldProblem::newton_active_set ()
     {
       int64_t n_active = 0, n_cycling = 0;
       int changed = 0;
-      pf_check (ctx_, pf_active_set_update (ctx_, 1e+1 * E_modulus, nullptr, &n_active, &n_cycling, &changed));
+      pf_check (ctx_, pf_active_set_update (ctx_, 1e+1 * (hetero () ? active_set_E_ : E_modulus), nullptr, &n_active, &n_cycling, &changed));
       pf_check (ctx_, pf_setup_jacobian (ctx_));                       // assemble_system()
       pf_check (ctx_, pf_residual (ctx_, nullptr, nullptr, nullptr));  // its rhs + set_zero
       int no_linear_iterations = 0;
@@ -571,9 +571,11 @@ FracturePhaseFieldProblem::run ()
       while (true);
 
       pf_check (ctx_, pf_project_phase_field (ctx_));
-      if (miehe () && use_forest ())
+      if ((miehe () || hetero ()) && use_forest ())
         {
-          // predictor-corrector refinement (cracks.cc:4419-4431): if refine_mesh() changed the mesh, redo the step
+          // predictor-corrector refinement (cracks.cc:4419-4431; every non-sneddon case, so also `multiple het`,
+          // whose shipped .prm grows its cracks through cells below the level cap): if refine_mesh() changed the
+          // mesh, redo the step
           if (forest_refine_phase_field_and_transfer ())
             {
               pcout_ << "MESH CHANGED!" << std::endl;
@@ -790,6 +792,9 @@ FracturePhaseFieldProblem::forest_create_context ()
           double x[3];
           f.cell_centre (c, x);
           const double E = func_emodulus.value (x, 3);
+          // the reference overwrites its member E_modulus cell by cell (cracks.cc:2209-2210), so the active-set
+          // constant c = 10 E_modulus (2859) is taken with the value the LAST assembled cell left there: E + 1
+          active_set_E_ = E + 1.0;
           for (int which = 0; which < 2; ++which)
             {
               const double Ev = which == 0 ? E + 1.0 : E;
@@ -906,8 +911,12 @@ FracturePhaseFieldProblem::forest_miehe_boundary_values (double t) const
 bool
 FracturePhaseFieldProblem::forest_refine_phase_field_and_transfer ()
 {
+  // refine_mesh(), strategy "phase field" (cracks.cc:3971-3995) with the level cap (4108-4116) and the
+  // SolutionTransfer of solution / old / old_old (4137-4159); dimension-generic: the Miehe cases (2-D) and
+  // `multiple het` (3-D, every step of every non-sneddon case, cracks.cc:4419-4431)
   const Forest coarse = *forest_;
-  const long long nn_old = coarse.n_nodes (), nd_old = nn_old * 3;
+  const int nc = dim_ + 1, nv = 1 << dim_;
+  const long long nn_old = coarse.n_nodes (), nd_old = nn_old * nc;
   std::vector<double> blk[3];
   for (int w = 0; w < 3; ++w)
     {
@@ -921,8 +930,8 @@ FracturePhaseFieldProblem::forest_refine_phase_field_and_transfer ()
     {
       if (coarse.cells ()[(size_t) c].level >= cap)
         continue;
-      for (int v = 0; v < 4; ++v)
-        if (blk[0][(size_t) (2 * nn_old + coarse.connectivity ()[(size_t) (4 * c + v)])] < value_phase_field_for_refinement)
+      for (int v = 0; v < nv; ++v)
+        if (blk[0][(size_t) (dim_ * nn_old + coarse.connectivity ()[(size_t) (nv * c + v)])] < value_phase_field_for_refinement)
           flags[(size_t) c] = 1;
       any = any || flags[(size_t) c];
     }
@@ -932,22 +941,23 @@ FracturePhaseFieldProblem::forest_refine_phase_field_and_transfer ()
   setup_system ();
   const long long nn_new = forest_->n_nodes ();
   std::vector<double> out[3];
-  std::vector<double> nodal_old ((size_t) nd_old), nodal_new ((size_t) nn_new * 3);
+  std::vector<double> nodal_old ((size_t) nd_old), nodal_new ((size_t) nn_new * nc);
   for (int w = 0; w < 3; ++w)
     {
+      // block layout [u | phi] <-> node-major for the transfer
       for (long long i = 0; i < nn_old; ++i)
         {
-          nodal_old[(size_t) (3 * i)] = blk[w][(size_t) (2 * i)];
-          nodal_old[(size_t) (3 * i + 1)] = blk[w][(size_t) (2 * i + 1)];
-          nodal_old[(size_t) (3 * i + 2)] = blk[w][(size_t) (2 * nn_old + i)];
+          for (int d = 0; d < dim_; ++d)
+            nodal_old[(size_t) (nc * i + d)] = blk[w][(size_t) (dim_ * i + d)];
+          nodal_old[(size_t) (nc * i + dim_)] = blk[w][(size_t) (dim_ * nn_old + i)];
         }
-      forest_->transfer (coarse, nodal_old.data (), nodal_new.data (), 3);
-      out[w].resize ((size_t) nn_new * 3);
+      forest_->transfer (coarse, nodal_old.data (), nodal_new.data (), nc);
+      out[w].resize ((size_t) nn_new * nc);
       for (long long i = 0; i < nn_new; ++i)
         {
-          out[w][(size_t) (2 * i)] = nodal_new[(size_t) (3 * i)];
-          out[w][(size_t) (2 * i + 1)] = nodal_new[(size_t) (3 * i + 1)];
-          out[w][(size_t) (2 * nn_new + i)] = nodal_new[(size_t) (3 * i + 2)];
+          for (int d = 0; d < dim_; ++d)
+            out[w][(size_t) (dim_ * i + d)] = nodal_new[(size_t) (nc * i + d)];
+          out[w][(size_t) (dim_ * nn_new + i)] = nodal_new[(size_t) (nc * i + dim_)];
         }
     }
   pf_check (ctx_, pf_set_state (ctx_, out[0].data (), out[1].data (), out[2].data (), old_timestep, old_old_timestep, 0,

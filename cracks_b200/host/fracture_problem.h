@@ -126,6 +126,7 @@ private:
   std::vector<std::vector<std::string>> output_file_names_by_timestep_;
   std::vector<std::pair<double, std::string>> times_and_names_;
   double tcv_ = 0;
+  double active_set_E_ = 1.0; // `multiple het`: E_modulus as the last assembled cell leaves it (cracks.cc:2209-2210, 2859)
   std::vector<std::pair<double, double>> cod_; // (x, COD(x)) lines of compute_functional_values
   unsigned total_newton_its_ = 0, total_linear_its_ = 0;
 };

@@ -310,12 +310,15 @@ int pf_profile_read (pf_ctx *ctx, double *total_ms, int64_t *count);
 /* pinned host memory for callers that want full PCIe bandwidth */
 int pf_host_alloc (void **out, size_t bytes);
 int pf_host_free (void *p);
-/* testing aid: route the 3-D apply through the dimension-generic kernel */
-int pf_debug_force_generic (int on);
-/* testing aid: do not use the cubic-cell (isotropic scale) specialisation of the tiled apply */
-int pf_debug_disable_iso (int on);
-/* testing aid: select the generation of the tiled 3-D apply kernel (1 or 2, default 2) */
-int pf_debug_set_variant (int variant);
+/* testing aids, per context (every level of its multigrid hierarchy follows):
+ * route the 3-D apply / residual through the dimension-generic thread-per-cell kernels (the independent second
+ * implementation the parity tests compare the tiled kernels with) */
+int pf_debug_force_generic (pf_ctx *ctx, int on);
+/* do not use the cubic-cell (isotropic scale) specialisation of the tiled apply */
+int pf_debug_disable_iso (pf_ctx *ctx, int on);
+/* select a tuning variant of the tiled 3-D apply kernel; 16 = the default.  Other numbers exist only in a library
+ * built with `make TUNING=1` (-DPF_TUNING_VARIANTS) and return PF_UNSUPPORTED otherwise */
+int pf_debug_set_variant (pf_ctx *ctx, int variant);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,8 @@ def lib():
         _LIB.pfo_load_2d.restype = None
         _LIB.pfo_load_2d.argtypes = [MP, PP, dp, dp]
         _LIB.pfo_num_threads.restype = C.c_int
+        _LIB.pfo_set_num_threads.restype = None
+        _LIB.pfo_set_num_threads.argtypes = [C.c_int]
     return _LIB
 
 
@@ -271,8 +273,13 @@ class SneddonRun:
         self.statistics = []
         self.logs = []
 
-    def newton_active_set(self, old):
+    def linear_solve(self, J, rhs):
+        """solve() of the reference (cracks.cc:2744-2777); the oracle's default is a sparse direct solve
+        (oracle/cpu_newton.py overrides it with the Krylov solver a benchmark-sized mesh needs)."""
         import scipy.sparse.linalg as spla
+        return spla.spsolve(J.tocsc(), rhs)
+
+    def newton_active_set(self, old):
         p = self.p
         nc, dim = p.nc, p.dim
         log = NewtonLog()
@@ -295,7 +302,7 @@ class SneddonRun:
             changed = int(np.any(active != active_old))
             J = p.jacobian(sol, old, oldold, self.constrained)
             r_pde, _ = p.residual(sol, old, oldold, self.constrained)
-            update = spla.spsolve(J.tocsc(), r_pde)
+            update = self.linear_solve(J, r_pde)
             update[self.constrained == 1] = 0.0
             saved = sol.copy()
             ls = 0

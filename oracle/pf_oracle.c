@@ -31,3 +31,16 @@ pfo_num_threads (void)
   return 1;
 #endif
 }
+
+/* bench.py's CPU arm: torchrun exports OMP_NUM_THREADS=1 to every rank, which would make the
+ * baseline a single-threaded one; the arm asks for all host cores explicitly. */
+void
+pfo_set_num_threads (int n)
+{
+#ifdef _OPENMP
+  if (n > 0)
+    omp_set_num_threads (n);
+#else
+  (void) n;
+#endif
+}

@@ -99,6 +99,7 @@ void pfo_decompose_stress_2d (const double *E, const double *E_lin, double lambd
 void pfo_load_2d (const pfo_mesh *, const pfo_params *, const double *sol, double *load /* [2] */);
 
 int pfo_num_threads (void);
+void pfo_set_num_threads (int n);
 
 #ifdef __cplusplus
 }

@@ -8,8 +8,8 @@ The sources are copied to tests/emu/_gen/ with three mechanical rewrites, nothin
   2. `extern __shared__` -> `extern thread_local` (the dynamic shared-memory array is one buffer per OS thread,
      i.e. per running block, emu_runtime.cc);
   3. the block reductions of pf_vector.cuh go through shared memory instead of warp shuffles (speed);
-  4. the TMA variant (pf_apply3d_v3.cuh: inline PTX, CUtensorMap) is cut out and its launcher returns
-     PF_UNSUPPORTED; the reduction grid is shrunk (RED_BLOCKS x RED_THREADS = 3 x 32) because every CUDA
+  4. the tuning variants (PF_TUNING_VARIANTS, incl. the TMA kernel pf_apply3d_v3.cuh with its inline PTX) are
+     not compiled, as in the product build; the reduction grid is shrunk (RED_BLOCKS x RED_THREADS = 3 x 32) because every CUDA
      thread of a cooperative kernel is an OS thread here.
 """
 import os
@@ -91,7 +91,7 @@ def split_top(s):
 def generate():
     os.makedirs(GEN, exist_ok=True)
     for name in sorted(os.listdir(SRC)):
-        if not name.endswith((".cu", ".cuh")) or name == "pf_apply3d_v3.cuh":
+        if not name.endswith((".cu", ".cuh")) or name in ("pf_apply3d_v3.cuh", "pf_apply3d_v5.cuh"):
             continue
         text = open(os.path.join(SRC, name)).read()
         text = text.replace("extern __shared__", "extern thread_local")
@@ -109,14 +109,9 @@ def generate():
             text = re.sub(r"constexpr int RED_BLOCKS = \d+;", "constexpr int RED_BLOCKS = 3;", text)
             text = re.sub(r"constexpr int RED_THREADS = \d+;", "constexpr int RED_THREADS = 32;", text)
         if name == "pf_api.cu":
-            text = text.replace('#include "pf_apply3d_v3.cuh"\n', "")
+            # the tuning variants (incl. the TMA kernel: inline PTX, CUtensorMap) sit behind PF_TUNING_VARIANTS,
+            # which this build does not define
             text = text.replace('#include "../../include/cracks_b200.h"', '#include "../../../include/cracks_b200.h"')
-            a = text.index("// cuTensorMapEncodeTiled through the runtime's driver entry point")
-            b = text.index("int g_force_generic = 0;")
-            v3 = open(os.path.join(SRC, "pf_apply3d_v3.cuh")).read()
-            pack = v3[v3.index("__global__ void\nk_pack_aux"):v3.index("} // namespace pf")]
-            text = text[:a] + "namespace pf {\n" + pack + "}\nusing pf::k_pack_aux;\n" + ("template <int TX, int TY, int TZ, int MINB>\nint\nlaunch_apply3d_v3 (pf_ctx *ctx, const double *, double *)\n"
-                               "{\n  return fail (ctx, PF_UNSUPPORTED, \"the TMA variant is not part of the CPU emulation\");\n}\n") + text[b:]
             text = rewrite_launches(text)
         assert "<<<" not in text, name
         open(os.path.join(GEN, name), "w").write(text)

@@ -13,28 +13,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
-def main():
-    import torch
-    import torch.distributed as dist
-    import cracks_b200 as pf
-    import newton_oracle as orc
-    from cracks_b200.api import mesh_diameter
-
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt = torch.frombuffer(bytearray(pf.PhaseFieldContext.nccl_unique_id()), dtype=torch.uint8).cuda()
-    dist.broadcast(idt, 0)
-    nccl_id = idt.cpu().numpy().tobytes()
-
-    def allsum(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
-        dist.all_reduce(t)
-        return t.cpu().numpy()
-
-    n, h = (12, 9, 10), (0.5, 0.4, 0.3)
+def small_mesh_parity(pf, orc, rank, world, local, nccl_id, allsum):
+    """apply / residual / diagonal / functionals of the slab-decomposed CUDA path on `world` ranks against the
+    single-domain CPU oracle on a small anisotropic mesh (12 x 9 x max(10, 3*world) cells); relative errors, rank 0."""
+    nz = max(10, 3 * world)
+    n, h = (12, 9, nz), (0.5, 0.4, 0.3)
     lo = tuple(-0.5 * n[d] * h[d] for d in range(3))
     hi = tuple(0.5 * n[d] * h[d] for d in range(3))
     prob = orc.Problem(3, n, lo, hi, kappa_of_h=lambda hh: 1e-3, pressure=1e-3)
@@ -78,9 +61,36 @@ def main():
         b_ref, c_ref = prob.energy(sol)
         errs["bulk"], errs["crack"] = abs(bulk - b_ref) / b_ref, abs(crack - c_ref) / c_ref
         errs["tcv"] = abs(tcv - prob.tcv(sol)) / abs(prob.tcv(sol))
+    ctx.close()
+
+    return errs
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import cracks_b200 as pf
+    import newton_oracle as orc
+    from cracks_b200.api import mesh_diameter
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(pf.PhaseFieldContext.nccl_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    nccl_id = idt.cpu().numpy().tobytes()
+
+    def allsum(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    errs = small_mesh_parity(pf, orc, rank, world, local, nccl_id, allsum)
+    if rank == 0:
         print("errors vs single-domain oracle:", errs, flush=True)
         assert all(v <= 1e-11 for v in errs.values()), errs
-    ctx.close()
 
     # KAT-1 end to end on `world` GPUs
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "sneddon_3d_1.json")))

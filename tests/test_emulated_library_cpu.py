@@ -309,7 +309,7 @@ def test_forest_context_entry_points(oracle, epf):
 def test_cpp_host_driver_on_the_forest_path(emu_so, tmp_path):
     """cracks_b200/host (C++: .prm surface, FracturePhaseFieldProblem, host forest) linked against the emulated
     build: tests/sneddon_2d_1.prm -- local pre-refinement, hanging nodes, the refinement cycle at the end --
-    through the command line, like tests/test_gpu_forest_experimental.py::test_kat2_through_the_cli on a GPU."""
+    through the command line, like tests/test_gpu_forest.py::test_kat2_through_the_cli on a GPU."""
     host = os.path.join(ROOT, "cracks_b200", "host")
     exe = os.path.join(HERE, "emu", "cracks_b200_run_emu")
     srcs = [os.path.join(host, f) for f in ("main.cc", "fracture_problem.cc", "parameter_handler.cc", "function_parser.cc",

@@ -1,7 +1,7 @@
-"""OPT-IN (PF_EXPERIMENTAL=1): the device path for locally refined meshes with hanging nodes
-(pf_create_forest, cracks_b200/csrc/pf_forest.cuh) against the hanging-node oracle and the KAT-2 golden.
-This code was written after the round's GPU budget was spent and has not been run on a GPU yet, so it
-does not gate the suite; the box-mesh paths do not touch it."""
+"""The device path for locally refined meshes with hanging nodes (pf_create_forest,
+cracks_b200/csrc/pf_forest.cuh) against the hanging-node oracle and the reference's adaptive goldens:
+KAT-2 (sneddon_2d_1), miehe_shear_1, miehe_tension_adaptive_1 and KAT-5 (hetero_3d_1), through the
+Python mirror and through the C++ command line.  Gating since round 2 (first B200 run: round 1, 7 passed)."""
 import json
 import os
 import sys
@@ -9,8 +9,7 @@ import sys
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PF_EXPERIMENTAL") != "1", reason="experimental forest path: set PF_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 

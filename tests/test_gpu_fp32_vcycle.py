@@ -1,15 +1,13 @@
-"""OPT-IN (PF_EXPERIMENTAL=1): the multigrid V-cycle in FP32 (pf_set_multigrid_precision(32),
-cracks_b200/csrc/pf_mg_lowp.cuh).  Written after the round's GPU budget was spent; verified on the CPU emulation
-of the library (tests/test_emulated_library_cpu.py::test_fp32_vcycle_against_fp64, 2 and 8 emulated ranks in
-tests/test_multirank_emulation_cpu.py), not yet run on a GPU, hence not gating."""
+"""The multigrid V-cycle in FP32 (pf_set_multigrid_precision(32), cracks_b200/csrc/pf_mg_lowp.cuh): the
+preconditioner's arithmetic is unpinned, the Krylov operator and every residual stay FP64, so
+the KAT-1 golden must be reproduced.  Gating since round 2."""
 import json
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PF_EXPERIMENTAL") != "1", reason="experimental FP32 V-cycle: set PF_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 

@@ -29,7 +29,10 @@ def test_sneddon_3d_golden(pf):
     assert drv.history[0][0].residual < 1e-5 * golden["initial_newton_residual"][0]
     for got, ref in zip(stats, golden["statistics"]):
         assert got["crack"] == pytest.approx(ref["crack"], rel=1e-8)
-    assert stats[0]["bulk"] == pytest.approx(golden["statistics"][0]["bulk"], rel=1e-7)
+    # converged energies <= 1e-8 relative.  Row 0 holds that.  Rows 1-3 stop at |r| < 1e-7 with a
+    # round-off-determined active set (preamble): the oracle itself, pinned to this golden, is within
+    # 5e-7 there (tests/test_oracle_golden.py) and the reference's own harness accepts abs 1e-6 on a 1e-4 number
+    assert stats[0]["bulk"] == pytest.approx(golden["statistics"][0]["bulk"], rel=1e-8)
     for got, ref in zip(stats[1:], golden["statistics"][1:]):
         assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-6)
     assert stats[0]["diff"] == pytest.approx(golden["timestep_difference_linfty"][0], rel=1e-5)
@@ -72,4 +75,69 @@ def test_properties_at_benchmark_size(pf):
     ctx.vmult(y2, xu2)
     a, b = np.dot(y1[: n * dim], xu2[: n * dim]), np.dot(xu1[: n * dim], y2[: n * dim])
     assert a == pytest.approx(b, rel=1e-10)
+    ctx.close()
+
+
+def test_apply_and_residual_vs_oracle_refine3(pf, oracle):
+    """GPU vmult / pf_residual against the CPU oracle at the CPU-feasible BASELINE size (3 refinements:
+    512 000 cells, 2 125 764 DoF), <= 1e-12 relative (FP64 reassociation only)."""
+    prob = oracle.sneddon_3d(3, kappa_of_h=lambda h: 1e-8 * h)
+    mesh = pf.sneddon_mesh(3, 3)
+    ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh))
+    rng = np.random.default_rng(20240229)
+    nn = prob.n_nodes
+    xs = prob.node_coords()
+    sol = prob.initial_sneddon().reshape(nn, 4)
+    for d in range(3):      # the smooth displacement field of the operator benchmark (SURVEY.md 8d)
+        f = 1e-3 * np.ones(nn)
+        for e in range(3):
+            f *= np.sin(np.pi * xs[e] / 10.0) if e == d else np.cos(np.pi * xs[e] / 20.0)
+        sol[:, d] = f
+    old = sol.copy(); old[:, 3] = np.clip(sol[:, 3] - 0.05 * rng.random(nn), 0, 1)
+    oo = old.copy(); oo[:, 3] = np.clip(old[:, 3] - 0.05 * rng.random(nn), 0, 1)
+    sol, old, oo = sol.reshape(-1), old.reshape(-1), oo.reshape(-1)
+    con = prob.dirichlet_mask().reshape(nn, 4)
+    con[:, 3] = sol.reshape(nn, 4)[:, 3] == 0.0
+    con = np.ascontiguousarray(con.reshape(-1))
+    prob.prm.dt_old, prob.prm.dt_oldold = 1.0, 1.0
+    ctx.set_state(ctx.to_block(sol), ctx.to_block(old), ctx.to_block(oo), 1.0, 1.0, False, prob.pressure)
+    cb = ctx.to_block(con).astype(np.uint8)
+    ctx.set_constraints(cb, cb)
+    r_pde, r_tot, nrm = ctx.residual()
+    r_pde_ref, r_tot_ref = prob.residual(sol, old, oo, con)
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    assert rel(ctx.to_nodal(r_tot), r_tot_ref) <= 1e-12
+    assert rel(ctx.to_nodal(r_pde), r_pde_ref) <= 1e-12
+    assert nrm == pytest.approx(float(np.linalg.norm(r_pde_ref)), rel=1e-12)
+    ctx.setup_jacobian()
+    x = rng.standard_normal(prob.n_dofs)
+    y = np.zeros(prob.n_dofs)
+    ctx.vmult(y, ctx.to_block(x))
+    assert rel(ctx.to_nodal(y), prob.apply_jacobian(sol, old, oo, con, x)) <= 1e-12
+    bulk, crack = ctx.energy()
+    b_ref, c_ref = prob.energy(sol)
+    assert bulk == pytest.approx(b_ref, rel=1e-12) and crack == pytest.approx(c_ref, rel=1e-12)
+    ctx.close()
+
+
+@pytest.mark.parametrize("refine", [2, 3])
+def test_time_step_0_vs_cpu_stand_in(pf, refine):
+    """crack energy within 1e-6 relative of the CPU stand-in at benchmark sizes.  The fixture
+    is time step 0 of parameters_sneddon_3d.prm solved by the assembled-matrix CPU path (oracle loop, CSR Jacobian,
+    Jacobi-GMRES; tests/golden/make_sneddon_refine_cpu.py) at 2 and 3 refinements (275 684 / 2 125 764 DoF)."""
+    from cracks_b200.api import mesh_diameter
+    path = os.path.join(HERE, "golden", "sneddon_3d_refine%d_cpu.json" % refine)
+    g = json.load(open(path))
+    mesh = pf.sneddon_mesh(3, refine)
+    ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh))
+    assert ctx.n_dofs == g["n_dofs"]
+    drv = pf.SneddonDriver(ctx, pressure=lambda t: g["pressure"], max_no_timesteps=0,
+                           newton_lower_bound=g["newton_lower_bound"], max_newton=50, max_line_search=10, gmres_max_it=200)
+    st = drv.run(mesh_diameter(mesh))[0]
+    ref = g["statistics"][0]
+    assert st["crack"] == pytest.approx(ref["crack"], rel=1e-6)
+    assert st["bulk"] == pytest.approx(ref["bulk"], rel=1e-6)
+    assert st["diff"] == pytest.approx(ref["diff"], rel=1e-6)
+    # the converged active set (unlike the per-iteration #A.Set column) is implementation independent (SURVEY.md)
+    assert drv.history[0][-1].n_active == ref["n_active"]
     ctx.close()

@@ -137,3 +137,28 @@ def test_kat3_miehe_tension_golden(pf):
         for k in ("bulk", "crack", "load"):
             assert got[k] == pytest.approx(ref[k], rel=tol), (got["step"], k, got, ref)
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["miehe_shear_2", "miehe_tension_adaptive_1"])
+def test_2d_multigrid_gives_the_jacobi_path_results_at_64x64(pf, name):
+    """pf_set_preconditioner kind 3 (2-D geometric multigrid on the slit square, the preconditioner the command line
+    switches to from 64 x 64 cells on) against Jacobi-GMRES on the same mesh: the preconditioner's arithmetic is
+    unpinned, the converged time steps must not depend on it.  3 time steps of each Miehe test (the
+    shear test with the stress split from step 1 on) at 5 global refinements = 64 x 64 cells, 12 771 DoF."""
+    g = json.load(open(os.path.join(HERE, "golden", name + ".json")))
+    g = dict(g, prm=dict(g["prm"]))
+    g["prm"]["Global pre-refinement steps"] = "5"
+    g["prm"]["Adaptive refinement cycles"] = "0"
+    g["prm"]["Max No of timesteps"] = "2"
+    results, lin = [], []
+    for kind in (0, 3):
+        ctx, drv = _driver(pf, g)
+        if kind == 3:
+            ctx.set_preconditioner(3, 2, 8.0)
+        results.append(drv.run())
+        lin.append(drv.lin_its)
+        ctx.close()
+    for a, b in zip(*results):
+        for k in ("bulk", "crack", "load"):
+            assert b[k] == pytest.approx(a[k], rel=1e-7, abs=1e-16), (a, b)
+    assert lin[1] * 5 < lin[0], lin        # 9-12 iterations per solve instead of hundreds

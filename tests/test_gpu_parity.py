@@ -76,35 +76,33 @@ def test_apply_jacobian_3d(oracle, pf, n, h):
     ctx.vmult(y, ctx.to_block(x))
     assert _relerr(ctx.to_nodal(y), y_ref) <= TOL
     # the dimension-generic kernel is an independent second implementation
-    ctx.lib.pf_debug_force_generic(1)
+    ctx.lib.pf_debug_force_generic(ctx.h, 1)
     try:
         y2 = np.zeros(prob.n_dofs)
         ctx.vmult(y2, ctx.to_block(x))
     finally:
-        ctx.lib.pf_debug_force_generic(0)
+        ctx.lib.pf_debug_force_generic(ctx.h, 0)
     assert _relerr(ctx.to_nodal(y2), y_ref) <= TOL
     # the first-generation tiled kernel stays available for A/B measurements
     # cubic cells use a specialisation with the gradient scales folded into constants
-    ctx.lib.pf_debug_disable_iso(1)
+    ctx.lib.pf_debug_disable_iso(ctx.h, 1)
     try:
         y4 = np.zeros(prob.n_dofs)
         ctx.vmult(y4, ctx.to_block(x))
     finally:
-        ctx.lib.pf_debug_disable_iso(0)
+        ctx.lib.pf_debug_disable_iso(ctx.h, 0)
     assert _relerr(ctx.to_nodal(y4), y_ref) <= TOL
-    # variant 1 = first-generation kernel, 2..7 = tile shapes of v2, 12..15 = persistent
-    # TMA-fed kernel (v3); 16 = v4 (symmetric strain sums, closed-form phi Laplacian) is the default
-    # 17 / 18 / 20 / 21 = v4 under register caps, 19 = v5 (y-collapse staged in shared memory): tuning variants
-    variants = (1, 2, 3, 4, 5, 6, 7, 12, 13, 14, 15, 17, 18, 19, 20, 21)
-    if os.environ.get("PF_EMULATED_LIBRARY") == "1":
-        variants = tuple(v for v in variants if not 12 <= v <= 15)   # the TMA kernel is not emulated
-    for variant in variants:
-        assert ctx.lib.pf_debug_set_variant(variant) == 0
+    # earlier generations / tuning experiments of the tiled kernel exist only in a `make TUNING=1` library
+    # (1 = first generation, 2..7 = tile shapes of v2, 12..15 = persistent TMA-fed v3, 17..21 = v4 under register
+    # caps and v5); the product build answers PF_UNSUPPORTED and ships variant 16 alone
+    for variant in (1, 2, 3, 4, 5, 6, 7, 12, 13, 14, 15, 17, 18, 19, 20, 21):
+        if ctx.lib.pf_debug_set_variant(ctx.h, variant) != 0:
+            continue
         try:
             y3 = np.zeros(prob.n_dofs)
             ctx.vmult(y3, ctx.to_block(x))
         finally:
-            ctx.lib.pf_debug_set_variant(16)
+            ctx.lib.pf_debug_set_variant(ctx.h, 16)
         assert _relerr(ctx.to_nodal(y3), y_ref) <= TOL, variant
     ctx.close()
 
@@ -159,11 +157,11 @@ def test_residual_diag_energy(oracle, pf, dim, n, h):
     assert _relerr(ctx.to_nodal(r_pde), r_pde_ref) <= TOL
     assert nrm == pytest.approx(np.linalg.norm(r_pde_ref), rel=1e-12)
     # 3-D has a tiled residual kernel; the generic one is the independent second implementation
-    ctx.lib.pf_debug_force_generic(1)
+    ctx.lib.pf_debug_force_generic(ctx.h, 1)
     try:
         r_pde2, r_tot2, nrm2 = ctx.residual()
     finally:
-        ctx.lib.pf_debug_force_generic(0)
+        ctx.lib.pf_debug_force_generic(ctx.h, 0)
     assert _relerr(ctx.to_nodal(r_tot2), r_tot_ref) <= TOL and nrm2 == pytest.approx(nrm, rel=1e-12)
     ctx.setup_jacobian()
     d_ref = prob.jacobian(sol, old, oo, None).diagonal()

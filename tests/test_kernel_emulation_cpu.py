@@ -6,7 +6,7 @@ the order pf_api.cu launches them on a forest mesh (mark hanging, lumped mass, r
 fold, distribute -> init -> cell kernel -> fold).  That holds the kernel logic of the hanging-node device
 path against the oracle -- which reproduces the reference's sneddon_2d_1 and hetero_3d_1 goldens -- without
 a GPU.  It is test infrastructure, not a CPU fallback: nothing under cracks_b200/ links it, and the launch
-plumbing of pf_api.cu itself still needs its first GPU run (tests/test_gpu_forest_experimental.py)."""
+plumbing of pf_api.cu itself still needs its first GPU run (tests/test_gpu_forest.py)."""
 import ctypes as C
 import json
 import os

@@ -11,7 +11,7 @@ ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh))
 ctx.set_dirichlet_all_faces(); ctx.interpolate_sneddon(mesh_diameter(mesh)); ctx.set_time_parameters(1.0, 1.0, False, 1e-3)
 st = torch.cuda.ExternalStream(ctx.stream)
 for generic in (0, 1):
-    ctx.lib.pf_debug_force_generic(generic)
+    ctx.lib.pf_debug_force_generic(ctx.h, generic)
     for _ in range(3):
         ctx.residual(want_vectors=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -23,5 +23,5 @@ for generic in (0, 1):
     ms = e0.elapsed_time(e1) / 20
     nb = 16 * ctx.n_dofs + 17 * ctx.n_nodes
     print(f"{'generic' if generic else 'tiled  '} residual incl. memset/finish/norm: {ms:.3f} ms  ({ctx.n_dofs/ms/1e3:.0f} MDoF/s, {nb/ms/1e6:.0f} GB/s algorithmic)")
-ctx.lib.pf_debug_force_generic(0)
+ctx.lib.pf_debug_force_generic(ctx.h, 0)
 ctx.close()
