@@ -168,12 +168,13 @@ def cpu_reference_sample(steps, warmup, refine=2, newton=False):
     # vmult per GMRES iteration (about 12 per step with a multigrid-quality preconditioner): an upper
     # bound on its Newton-its/s that ignores the AMG set-up, the V-cycles and the residual assemblies
     newton_bound = 1.0 / (t_asm + 12.0 * t)
+    nnz = int(col.shape[0])
+    del val, col, rowptr
     measured = None
     if newton:
         # a MEASURED active-set Newton step of the assembled-matrix path (SURVEY.md 8d iii): residual + active
         # set + assembly + GMRES(1e-8) + one line-search residual, at 3 refinements (about 20 s of CPU work)
         import cpu_newton
-        del val, col, rowptr
         measured = cpu_newton.time_one_newton_step(refine=min(refine, 3), threads=host_cores())
     return {
         "newton_its_per_s": measured["newton_its_per_s"] if measured else None,
@@ -183,7 +184,7 @@ def cpu_reference_sample(steps, warmup, refine=2, newton=False):
                                                     measured["preconditioner"])) if measured else None,
         "value": prob.n_dofs / t / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
         "sample": (f"CSR SpMV (the reference's vmult) on Sneddon-3D at {refine} global refinements: "
-                   f"{prob.n_dofs} DoF, {col.shape[0]} nnz, {steps} applies after {warmup} warm-ups; "
+                   f"{prob.n_dofs} DoF, {nnz} nnz, {steps} applies after {warmup} warm-ups; "
                    f"Jacobian assembly (needed once per Newton step by the reference) took {t_asm:.2f} s "
                    f"= {prob.n_dofs / t_asm / 1e6:.3f} MDoF/s; assembly + 12 vmults bound the CPU path to "
                    f"{newton_bound:.2f} Newton-its/s at this size"),
@@ -244,6 +245,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-newton", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the timing of the FP32 (inexact-Newton) Jacobian")
     ap.add_argument("--variant", type=int, default=0, help="debug: apply-kernel variant (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -366,6 +368,40 @@ def main():
         ms_total, kern_ms = float(t[0]), float(t[1])
     ms_step = ms_total / args.steps
 
+    # ---- the inexact-Newton operator: the same 27-point evaluation in FP32 on FP64 vectors (pf_set_jacobian_precision).
+    # Reported beside the headline, never instead of it: `value` above is the exact FP64 operator.
+    inexact = None
+    if not args.no_fp32 and not args.variant:
+        ctx.vmult_dev(y_dev, x_dev)
+        y64 = ctx.download(y_dev)
+        ctx.set_jacobian_precision(32)
+        ctx.setup_jacobian()
+        for _ in range(args.warmup):
+            ctx.vmult_dev(y_dev, x_dev)
+        barrier()
+        ctx.profile_enable(True)
+        with torch.cuda.stream(stream):
+            e0.record()
+        for _ in range(args.steps):
+            ctx.vmult_dev(y_dev, x_dev)
+        with torch.cuda.stream(stream):
+            e1.record()
+        barrier()
+        ms32 = e0.elapsed_time(e1) / args.steps
+        k32_ms, k32_cnt = ctx.profile_read()
+        ctx.profile_enable(False)
+        y32 = ctx.download(y_dev)
+        if world > 1:
+            t = torch.tensor([ms32, k32_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms32, k32_ms = float(t[0]), float(t[1])
+        inexact = {"dtype": "f32 arithmetic on f64 vectors", "ms_per_step": ms32, "value": nd / (ms32 * 1e-3) / 1e6, "unit": UNIT,
+                   "kernel_ms": k32_ms / max(k32_cnt, 1),
+                   "relerr_vs_f64": float(np.max(np.abs(y32 - y64)) / np.max(np.abs(y64)))}
+        del y32, y64
+        ctx.set_jacobian_precision(64)
+        ctx.setup_jacobian()
+
     # ---- end to end through the host-buffer ABI call (H2D + apply + D2H per step)
     ctx.vmult(y_host, x_host)
     barrier()
@@ -458,6 +494,9 @@ def main():
         }
         if fp64:
             line["roofline_fp64"] = fp64
+        if inexact:
+            inexact["roofline_frac_hbm"] = b_alg / (inexact["kernel_ms"] * 1e-3) / 1e9 / peak
+            line["inexact_newton_operator"] = inexact
         if parity is not None:
             line["parity"] = parity
         if newton is not None:

@@ -22,6 +22,7 @@
 #include "pf_apply3d.cuh"
 #include "pf_apply3d_v2.cuh"
 #include "pf_apply3d_v4.cuh"
+#include "pf_apply3d_v6.cuh"
 #ifdef PF_TUNING_VARIANTS // earlier generations and tuning experiments of the apply kernel: `make TUNING=1`, A/B runs only
 #include "pf_apply3d_v3.cuh"
 #include "pf_apply3d_v5.cuh"
@@ -177,6 +178,11 @@ struct pf_ctx
   double *lame_dev = nullptr, *lame_energy_dev = nullptr, *level_h_dev = nullptr;
   double *fx = nullptr;               // distributed copy of the input vector of an apply
   uint8_t *zero_mask = nullptr;       // "nothing constrained", for the hanging-node-only constraint set
+  // v6 apply kernel (pf_apply3d_v6.cuh, cubic cells): two state coefficients per quadrature point, refreshed by
+  // pf_setup_jacobian; the FP32 set only exists after pf_set_jacobian_precision (ctx, 32)
+  double2 *coef64 = nullptr;
+  float2 *coef32 = nullptr;
+  int jacobian_bits = 64;      // precision of the Krylov operator: 64 = exact, 32 = inexact-Newton Jacobian in FP32
   // tuning / debugging switches (per context; the environment is read once, by pf_create)
   int apply_variant = 16;      // 16 = default exact kernel; other numbers only in a PF_TUNING_VARIANTS build
   int force_generic = 0;       // pf_debug_force_generic: the thread-per-cell second implementation
@@ -653,6 +659,81 @@ launch_apply3d_v5 (pf_ctx *ctx, const double *x, double *y)
 
 #endif // PF_TUNING_VARIANTS
 
+// ---- v6: cubic cells, cached state coefficients (pf_apply3d_v6.cuh) -------------------------------
+inline bool
+v6_possible (const pf_ctx *ctx)
+{
+  const Grid &g = ctx->g;
+  return ctx->dim == 3 && !ctx->forest && g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
+}
+
+K6
+make_k6 (const pf_ctx *ctx)
+{
+  const Grid &g = ctx->g;
+  const Phys &p = ctx->p;
+  K6 k;
+  const double gam = ctx->k3.gu[0], omk = 1.0 - p.kappa;
+  k.s = ctx->k3.s;
+  k.gam = gam;
+  k.lam2 = p.lambda / (2.0 * p.mu);
+  k.beta = p.P1 * gam / (omk * 2.0 * p.mu * gam * gam);
+  k.k1 = 0.5 * omk * p.mu * gam * gam;
+  k.w[0] = 25.0 / 81.0, k.w[1] = 40.0 / 81.0, k.w[2] = 64.0 / 81.0;
+  for (int q = 0; q < 3; ++q)
+    k.wz[q] = ctx->k3.wvol * ctx->k3.wq[q];
+  k.kl[0] = p.G_c * p.eps * g.h[0] * 0.5;
+  k.kl[1] = p.G_c * p.eps * g.h[0] * (1.0 / 3.0);
+  k.kl[2] = p.G_c * p.eps * g.h[0] * (1.0 / 6.0);
+  return k;
+}
+
+constexpr int V6_TX = 16, V6_TY = 4;
+
+// the coefficient records of every cell layer this rank evaluates (once per pf_setup_jacobian)
+template <typename R>
+int
+v6_refresh_coefficients (pf_ctx *ctx, typename Pair<R>::type **buf)
+{
+  using T = Tile3v6<V6_TX, V6_TY>;
+  const Grid &g = ctx->g;
+  const int tiles_x = (g.n[0] + V6_TX - 1) / V6_TX, tiles_y = (g.n[1] + V6_TY - 1) / V6_TY, layers = g.cell_end - g.cell_begin;
+  if (!*buf)
+    CU (cudaMalloc (buf, sizeof (typename Pair<R>::type) * T::coef_per_tile * (size_t) tiles_x * tiles_y * layers));
+  k_point_coeffs<R, V6_TX, V6_TY><<<(unsigned) tiles_x * tiles_y * layers, T::NT, 0, ctx->stream>>> (
+    g, ctx->p, ctx->k3, tiles_x, tiles_y, g.cell_begin, ctx->sol, ctx->pt, *buf);
+  KCHECK ();
+  return PF_OK;
+}
+
+template <typename R, int MINB>
+int
+launch_apply3d_v6 (pf_ctx *ctx, const double *x, double *y, const typename Pair<R>::type *coef)
+{
+  using T = Tile3v6<V6_TX, V6_TY>;
+  Grid g = ctx->g;
+  const int layer0 = g.cell_begin;
+  if (ctx->range_begin >= 0)
+    {
+      g.cell_begin = ctx->range_begin;
+      g.cell_end = ctx->range_end;
+      g.layer_stride = ctx->range_stride;
+    }
+  const int tiles_x = (g.n[0] + V6_TX - 1) / V6_TX, tiles_y = (g.n[1] + V6_TY - 1) / V6_TY;
+  const int tiles_z = g.layer_stride > 1 ? 2 : g.cell_end - g.cell_begin;
+  static const char attr_tag = 0;
+  if (ctx->attr_done.insert (&attr_tag).second)
+    {
+      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V6_TX, V6_TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::smem_bytes<R> ()));
+      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V6_TX, V6_TY, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+  k_apply3d_v6<R, V6_TX, V6_TY, MINB><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes<R> (), ctx->stream>>> (
+    g, make_k6 (ctx), tiles_x, tiles_y, layer0, x, ctx->sol, ctx->mask, coef, y);
+  KCHECK ();
+  return PF_OK;
+}
+
 // the tiled kernel the library uses by default (exact 27-point rule, or the
 // 2-point rule of the preconditioner-only operator)
 int
@@ -662,6 +743,13 @@ launch_tiled_default (pf_ctx *ctx, const double *x, double *y, bool approx)
   if (ctx->apply_variant == 3)
     return approx ? launch_apply3d_v2<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v2<16, 4, 1> (ctx, x, y);
 #endif
+  if (!approx && ctx->apply_variant == 16 && v6_possible (ctx))
+    {
+      if (ctx->jacobian_bits == 32 && ctx->coef32)
+        return launch_apply3d_v6<float, 8> (ctx, x, y, ctx->coef32);
+      if (ctx->coef64)
+        return launch_apply3d_v6<double, 4> (ctx, x, y, ctx->coef64);
+    }
   return approx ? launch_apply3d_v4<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v4<16, 4, 1> (ctx, x, y);
 }
 
@@ -930,10 +1018,11 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
             // v4 capped at exactly 200 / 184 registers (5 CTAs = 10 warps per SM), to be measured
             case 20: rc = launch_apply3d_v4_maxr<16, 4, 1, 200> (ctx, x, y); break;
             case 21: rc = launch_apply3d_v4_maxr<16, 4, 1, 184> (ctx, x, y); break;
-            default: rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y); break; // variant 16: fastest measured
+            case 23: rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y); break;  // v4: the default of round 1
+            default: rc = launch_tiled_default (ctx, x, y, false); break;  // variant 16: v6 on cubic cells, else v4
             }
 #else
-          rc = launch_apply3d_v4<16, 4, 1> (ctx, x, y);
+          rc = launch_tiled_default (ctx, x, y, false);
 #endif
           if (rc)
             return rc;
@@ -2242,10 +2331,14 @@ pf_destroy (pf_ctx *ctx)
     g_trace.dump (ctx->rank);
   if (ctx->coarse)
     pf_destroy (ctx->coarse);
+  if (ctx->mg_graph) // before the communicator: a captured V-cycle may hold NCCL nodes
+    cudaGraphExecDestroy (ctx->mg_graph);
   if (ctx->comm && ctx->owns_comm)
     g_nccl.CommDestroy (ctx->comm);
-  if (ctx->mg_graph)
-    cudaGraphExecDestroy (ctx->mg_graph);
+  if (ctx->coef64)
+    cudaFree (ctx->coef64);
+  if (ctx->coef32)
+    cudaFree (ctx->coef32);
   for (float *v : {ctx->f_sol, ctx->f_pt, ctx->f_idiag, ctx->f_b, ctx->f_x, ctx->f_y, ctx->f_d, ctx->f_r})
     if (v)
       cudaFree (v);
@@ -2484,6 +2577,15 @@ pf_setup_jacobian (pf_ctx *ctx)
   int rc = diag_and_aux (ctx);
   if (rc)
     return rc;
+  if (v6_possible (ctx) && ctx->apply_variant == 16)
+    {
+      if (ctx->jacobian_bits == 32)
+        rc = v6_refresh_coefficients<float> (ctx, &ctx->coef32);
+      else
+        rc = v6_refresh_coefficients<double> (ctx, &ctx->coef64);
+      if (rc)
+        return rc;
+    }
   ctx->jac_ready = true;
   ctx->mg_ready = false;
   ctx->mg_graph_valid = false;
@@ -2514,6 +2616,21 @@ pf_set_multigrid_precision (pf_ctx *ctx, int bits)
   for (pf_ctx *c = ctx; c; c = c->coarse)
     c->mg_fp32 = bits == 32;
   ctx->jac_ready = false; // the float copies are made by pf_setup_jacobian
+  return PF_OK;
+}
+
+// Precision of the Krylov operator (the Jacobian inside pf_solve / pf_apply_jacobian): 64 = the exact FP64 evaluation
+// (default), 32 = inexact Newton: the same 27-point evaluation in FP32 on FP64 vectors.  Residuals, the active-set
+// test, the energies and the outer GMRES vectors are FP64 in both cases, so the Newton fixed point is unchanged.
+int
+pf_set_jacobian_precision (pf_ctx *ctx, int bits)
+{
+  if (!ctx || (bits != 32 && bits != 64))
+    return PF_BAD_ARG;
+  if (bits == 32 && !v6_possible (ctx))
+    return fail (ctx, PF_UNSUPPORTED, "the FP32 Jacobian needs a 3-D box mesh with cubic cells");
+  ctx->jacobian_bits = bits;
+  ctx->jac_ready = false; // the coefficient records are made by pf_setup_jacobian
   return PF_OK;
 }
 
@@ -3359,11 +3476,12 @@ pf_debug_set_variant (pf_ctx *ctx, int variant)
   if (variant < 1 || variant > 21)
     return PF_BAD_ARG;
 #else
-  if (variant != 16)
+  if (variant != 16 && variant != 23)
     return fail (ctx, PF_UNSUPPORTED, "apply-kernel variant %d is a tuning variant: build with `make TUNING=1`", variant);
 #endif
   for (pf_ctx *c = ctx; c; c = c->coarse)
     c->apply_variant = variant;
+  ctx->jac_ready = false; // the v6 coefficient records are made by pf_setup_jacobian
   return PF_OK;
 }
 

@@ -214,6 +214,11 @@ int pf_set_multigrid_precision (pf_ctx *ctx, int bits);
  * BlockDiagonalPreconditioner, cracks.cc:2717-2740); host buffers, block layout,
  * n_dofs doubles each.  pf_setup_jacobian must have been called. */
 int pf_apply_preconditioner (pf_ctx *ctx, const double *v, double *z);
+/* Precision of the Krylov operator (the Jacobian inside pf_solve / pf_apply_jacobian*): 64 = exact FP64 (default),
+ * 32 = inexact Newton, the same 27-point evaluation in FP32 on FP64 vectors (3-D box meshes with cubic cells).
+ * Residuals (cracks.cc:2393-2432), the active-set test, energies and the outer GMRES vectors stay FP64, so the
+ * Newton fixed point and every parity metric are unchanged.  Takes effect at the next pf_setup_jacobian. */
+int pf_set_jacobian_precision (pf_ctx *ctx, int bits);
 /* Restart length of GMRES (deal.II's SolverGMRES default keeps 28 basis vectors,
  * cracks.cc:2764; this library's default is 30).  Ill-conditioned small 2-D
  * problems, which the reference hands to a sparse direct solver (2750-2759),

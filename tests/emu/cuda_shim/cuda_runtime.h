@@ -30,6 +30,10 @@ struct double2
 {
   double x, y;
 };
+struct float2
+{
+  float x, y;
+};
 struct double4
 {
   double x, y, z, w;

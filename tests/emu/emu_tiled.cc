@@ -19,6 +19,7 @@ alignas (16) unsigned char smem_raw[256 * 1024];
 
 #include "../../cracks_b200/csrc/pf_apply3d_v4.cuh"
 #include "../../cracks_b200/csrc/pf_apply3d_v5.cuh"
+#include "../../cracks_b200/csrc/pf_apply3d_v6.cuh"
 #include "../../cracks_b200/csrc/pf_residual3d.cuh"
 #include "../../cracks_b200/csrc/pf_vector.cuh"
 
@@ -114,6 +115,34 @@ emu_apply3d (int variant, int nq, const int *n, const double *h, const double *p
   const int tiles_x = (n[0] + TX - 1) / TX, tiles_y = (n[1] + TY - 1) / TY, tiles_z = (n[2] + TZ - 1) / TZ;
   const unsigned grid = (unsigned) (tiles_x * tiles_y * tiles_z);
   const bool iso = h[0] == h[1] && h[1] == h[2];
+  if (variant == 26 || variant == 27)
+    {
+      // v6: cubic cells only; the coefficient records first (k_point_coeffs), then the tiles -- as pf_setup_jacobian /
+      // launch_apply3d_v6 do.  27 = the FP32 Jacobian of the inexact-Newton path.
+      using T6 = Tile3v6<16, 4>;
+      K6 k6;
+      const double gam = k.gu[0], omk = 1.0 - p.kappa;
+      k6.s = k.s, k6.gam = gam, k6.lam2 = p.lambda / (2.0 * p.mu);
+      k6.beta = p.P1 * gam / (omk * 2.0 * p.mu * gam * gam);
+      k6.k1 = 0.5 * omk * p.mu * gam * gam;
+      k6.w[0] = 25.0 / 81.0, k6.w[1] = 40.0 / 81.0, k6.w[2] = 64.0 / 81.0;
+      for (int q = 0; q < 3; ++q)
+        k6.wz[q] = k.wvol * k.wq[q];
+      k6.kl[0] = p.G_c * p.eps * h[0] * 0.5, k6.kl[1] = p.G_c * p.eps * h[0] / 3.0, k6.kl[2] = p.G_c * p.eps * h[0] / 6.0;
+      if (variant == 26)
+        {
+          std::vector<double2> coef (T6::coef_per_tile * grid);
+          launch_blocks (k_point_coeffs<double, 16, 4>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
+          launch_blocks (k_apply3d_v6<double, 16, 4, 4>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask, (const double2 *) coef.data (), y);
+        }
+      else
+        {
+          std::vector<float2> coef (T6::coef_per_tile * grid);
+          launch_blocks (k_point_coeffs<float, 16, 4>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
+          launch_blocks (k_apply3d_v6<float, 16, 4, 8>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask, (const float2 *) coef.data (), y);
+        }
+      return;
+    }
 #define EMU_LAUNCH(KERNEL) launch_blocks (KERNEL, grid, (unsigned) (TX * TY * TZ), g, p, k, tiles_x, tiles_y, x, sol, pt, mask, y)
   if (variant == 19)
     iso ? EMU_LAUNCH ((k_apply3d_v5<TX, TY, TZ, 2, 3, true>) ) : EMU_LAUNCH ((k_apply3d_v5<TX, TY, TZ, 2, 3, false>) );

@@ -160,5 +160,6 @@ def test_2d_multigrid_gives_the_jacobi_path_results_at_64x64(pf, name):
         ctx.close()
     for a, b in zip(*results):
         for k in ("bulk", "crack", "load"):
-            assert b[k] == pytest.approx(a[k], rel=1e-7, abs=1e-16), (a, b)
+            # both solves stop at |r| <= 1e-8 |b| (cracks.cc:2762): the energies agree to the solver tolerance
+            assert b[k] == pytest.approx(a[k], rel=1e-6, abs=1e-16), (a, b)
     assert lin[1] * 5 < lin[0], lin        # 9-12 iterations per solve instead of hundreds

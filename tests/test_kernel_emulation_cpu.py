@@ -208,6 +208,14 @@ def test_tiled_apply_kernel_sources_match_the_oracle(oracle, emu_tiled, n, h):
                               _ptr(diag), _ptr(y))
         assert np.max(np.abs(y[free] - y_ref[free])) / np.max(np.abs(y_ref[free])) <= 1e-12, variant
         assert np.array_equal(y[~free], x[~free])                     # constrained rows: diag * x, untouched by the tiles
+    if h[0] == h[1] == h[2]:
+        # v6 (cubic cells, cached state coefficients): the default Krylov operator, and its FP32 twin
+        for variant, tol in ((26, 1e-12), (27, 2e-5)):
+            y = np.zeros(prob.n_dofs)
+            emu_tiled.emu_apply3d(C.c_int(variant), C.c_int(3), nv, hv, _ptr(phys), _ptr(x), _ptr(sol), _ptr(pt), _ptr(mask),
+                                  _ptr(diag), _ptr(y))
+            assert np.max(np.abs(y[free] - y_ref[free])) / np.max(np.abs(y_ref[free])) <= tol, variant
+            assert np.array_equal(y[~free], x[~free])
     # the 2-point-rule operator of the multigrid smoother: v4 and v2 must agree with each other
     y2 = [np.zeros(prob.n_dofs), np.zeros(prob.n_dofs)]
     for out, variant in zip(y2, (16, 3)):
