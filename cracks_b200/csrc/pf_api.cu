@@ -182,6 +182,8 @@ struct pf_ctx
   // pf_setup_jacobian; the FP32 set only exists after pf_set_jacobian_precision (ctx, 32)
   double2 *coef64 = nullptr;
   float2 *coef32 = nullptr;
+  double2 *coef2_64 = nullptr; // the same for the 2-point-rule operator of the multigrid smoother (every level)
+  float2 *coef2_32 = nullptr;
   int jacobian_bits = 64;      // precision of the Krylov operator: 64 = exact, 32 = inexact-Newton Jacobian in FP32
   // tuning / debugging switches (per context; the environment is read once, by pf_create)
   int apply_variant = 16;      // 16 = default exact kernel; other numbers only in a PF_TUNING_VARIANTS build
@@ -685,32 +687,42 @@ make_k6 (const pf_ctx *ctx)
   k.kl[0] = p.G_c * p.eps * g.h[0] * 0.5;
   k.kl[1] = p.G_c * p.eps * g.h[0] * (1.0 / 3.0);
   k.kl[2] = p.G_c * p.eps * g.h[0] * (1.0 / 6.0);
+  k.s2 = ctx->k3.s2;
+  k.wvol = ctx->k3.wvol;
+  k.cge = p.G_c * p.eps * 8.0 * gam * gam;
   return k;
 }
 
-constexpr int V6_TX = 16, V6_TY = 4;
+// tile shapes: 16 x 4 cells for FP64 (64-bit shared-memory accesses are conflict free at any row pitch); FP32 uses
+// 32 x 2 so that the 32 lanes of a warp read 32 consecutive words (16 x 4 has a row pitch of 17 words: 2-way conflicts)
+template <typename R> struct V6Shape;
+template <> struct V6Shape<double> { static constexpr int TX = 16, TY = 4; };
+template <> struct V6Shape<float> { static constexpr int TX = 32, TY = 2; };
 
-// the coefficient records of every cell layer this rank evaluates (once per pf_setup_jacobian)
-template <typename R>
+// the coefficient records of every cell layer this rank evaluates (once per pf_setup_jacobian and level)
+template <typename R, int NQ>
 int
 v6_refresh_coefficients (pf_ctx *ctx, typename Pair<R>::type **buf)
 {
-  using T = Tile3v6<V6_TX, V6_TY>;
+  constexpr int TX = V6Shape<R>::TX, TY = V6Shape<R>::TY;
+  using T = Tile3v6<TX, TY, NQ>;
   const Grid &g = ctx->g;
-  const int tiles_x = (g.n[0] + V6_TX - 1) / V6_TX, tiles_y = (g.n[1] + V6_TY - 1) / V6_TY, layers = g.cell_end - g.cell_begin;
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY, layers = g.cell_end - g.cell_begin;
   if (!*buf)
     CU (cudaMalloc (buf, sizeof (typename Pair<R>::type) * T::coef_per_tile * (size_t) tiles_x * tiles_y * layers));
-  k_point_coeffs<R, V6_TX, V6_TY><<<(unsigned) tiles_x * tiles_y * layers, T::NT, 0, ctx->stream>>> (
+  k_point_coeffs<R, TX, TY, NQ><<<(unsigned) tiles_x * tiles_y * layers, T::NT, 0, ctx->stream>>> (
     g, ctx->p, ctx->k3, tiles_x, tiles_y, g.cell_begin, ctx->sol, ctx->pt, *buf);
   KCHECK ();
   return PF_OK;
 }
 
-template <typename R, int MINB>
+// R = arithmetic of the cell walk, V = type of the global vectors, NQ = 3 (exact rule) or 2 (smoother operator)
+template <typename R, typename V, int NQ, int MINB>
 int
-launch_apply3d_v6 (pf_ctx *ctx, const double *x, double *y, const typename Pair<R>::type *coef)
+launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename Pair<R>::type *coef)
 {
-  using T = Tile3v6<V6_TX, V6_TY>;
+  constexpr int TX = V6Shape<R>::TX, TY = V6Shape<R>::TY;
+  using T = Tile3v6<TX, TY, NQ>;
   Grid g = ctx->g;
   const int layer0 = g.cell_begin;
   if (ctx->range_begin >= 0)
@@ -719,17 +731,17 @@ launch_apply3d_v6 (pf_ctx *ctx, const double *x, double *y, const typename Pair<
       g.cell_end = ctx->range_end;
       g.layer_stride = ctx->range_stride;
     }
-  const int tiles_x = (g.n[0] + V6_TX - 1) / V6_TX, tiles_y = (g.n[1] + V6_TY - 1) / V6_TY;
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = g.layer_stride > 1 ? 2 : g.cell_end - g.cell_begin;
   static const char attr_tag = 0;
   if (ctx->attr_done.insert (&attr_tag).second)
     {
-      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V6_TX, V6_TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int) T::smem_bytes<R> ()));
-      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V6_TX, V6_TY, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) T::template smem_bytes<R> ()));
+      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
-  k_apply3d_v6<R, V6_TX, V6_TY, MINB><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::smem_bytes<R> (), ctx->stream>>> (
-    g, make_k6 (ctx), tiles_x, tiles_y, layer0, x, ctx->sol, ctx->mask, coef, y);
+  k_apply3d_v6<R, V, NQ, TX, TY, MINB><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::template smem_bytes<R> (),
+                                         ctx->stream>>> (g, make_k6 (ctx), tiles_x, tiles_y, layer0, x, sol, ctx->mask, coef, y);
   KCHECK ();
   return PF_OK;
 }
@@ -743,12 +755,14 @@ launch_tiled_default (pf_ctx *ctx, const double *x, double *y, bool approx)
   if (ctx->apply_variant == 3)
     return approx ? launch_apply3d_v2<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v2<16, 4, 1> (ctx, x, y);
 #endif
-  if (!approx && ctx->apply_variant == 16 && v6_possible (ctx))
+  if (ctx->apply_variant == 16 && v6_possible (ctx))
     {
-      if (ctx->jacobian_bits == 32 && ctx->coef32)
-        return launch_apply3d_v6<float, 8> (ctx, x, y, ctx->coef32);
-      if (ctx->coef64)
-        return launch_apply3d_v6<double, 4> (ctx, x, y, ctx->coef64);
+      if (approx && ctx->coef2_64)
+        return launch_apply3d_v6<double, double, 2, 4> (ctx, x, ctx->sol, y, ctx->coef2_64);
+      if (!approx && ctx->jacobian_bits == 32 && ctx->coef32)
+        return launch_apply3d_v6<float, double, 3, 8> (ctx, x, ctx->sol, y, ctx->coef32);
+      if (!approx && ctx->coef64)
+        return launch_apply3d_v6<double, double, 3, 4> (ctx, x, ctx->sol, y, ctx->coef64);
     }
   return approx ? launch_apply3d_v4<16, 4, 1, 2, 2> (ctx, x, y) : launch_apply3d_v4<16, 4, 1> (ctx, x, y);
 }
@@ -1534,6 +1548,8 @@ launch_apply3d_mg (pf_ctx *ctx, const float *x, float *y)
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
   const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
+  if (ctx->apply_variant == 16 && v6_possible (ctx) && ctx->coef2_32)
+    return launch_apply3d_v6<float, float, 2, 8> (ctx, x, ctx->f_sol, y, ctx->coef2_32);
   const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
   if (iso)
     k_apply3d_mg<float, TX, TY, TZ, MINB, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
@@ -1785,6 +1801,14 @@ diag_and_aux (pf_ctx *ctx)
   int rc = halo_exchange (ctx, ctx->diag, ctx->nc);
   if (rc)
     return rc;
+  if (ctx->precond == 1 && ctx->mg_approx && ctx->apply_variant == 16 && v6_possible (ctx))
+    {
+      // state coefficients of the 2-point-rule smoother operator on this level, in the V-cycle's precision
+      rc = ctx->mg_fp32 ? v6_refresh_coefficients<float, 2> (ctx, &ctx->coef2_32)
+                        : v6_refresh_coefficients<double, 2> (ctx, &ctx->coef2_64);
+      if (rc)
+        return rc;
+    }
 #ifdef PF_TUNING_VARIANTS
   if (ctx->dim == 3)
     {
@@ -2335,10 +2359,9 @@ pf_destroy (pf_ctx *ctx)
     cudaGraphExecDestroy (ctx->mg_graph);
   if (ctx->comm && ctx->owns_comm)
     g_nccl.CommDestroy (ctx->comm);
-  if (ctx->coef64)
-    cudaFree (ctx->coef64);
-  if (ctx->coef32)
-    cudaFree (ctx->coef32);
+  for (void *p : {(void *) ctx->coef64, (void *) ctx->coef32, (void *) ctx->coef2_64, (void *) ctx->coef2_32})
+    if (p)
+      cudaFree (p);
   for (float *v : {ctx->f_sol, ctx->f_pt, ctx->f_idiag, ctx->f_b, ctx->f_x, ctx->f_y, ctx->f_d, ctx->f_r})
     if (v)
       cudaFree (v);
@@ -2580,9 +2603,9 @@ pf_setup_jacobian (pf_ctx *ctx)
   if (v6_possible (ctx) && ctx->apply_variant == 16)
     {
       if (ctx->jacobian_bits == 32)
-        rc = v6_refresh_coefficients<float> (ctx, &ctx->coef32);
+        rc = v6_refresh_coefficients<float, 3> (ctx, &ctx->coef32);
       else
-        rc = v6_refresh_coefficients<double> (ctx, &ctx->coef64);
+        rc = v6_refresh_coefficients<double, 3> (ctx, &ctx->coef64);
       if (rc)
         return rc;
     }

@@ -4,6 +4,7 @@
 // the oracle without a GPU.  Only kernels that do not use shared memory, barriers or warp shuffles
 // may be *run* this way; the others merely have to compile.  Nothing under cracks_b200/ includes this.
 #pragma once
+#define PF_EMULATION 1 // kernel sources take their plain-C++ path where the device path is inline PTX
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -33,6 +34,10 @@ struct double2
 struct float2
 {
   float x, y;
+};
+struct float4
+{
+  float x, y, z, w;
 };
 struct double4
 {

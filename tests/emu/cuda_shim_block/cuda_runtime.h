@@ -3,6 +3,7 @@
 // std::barrier over the block, the dynamic shared-memory array is one buffer per block, atomicAdd is a
 // real atomic.  Blocks run one after the other.  See tests/emu/emu_tiled.cc.
 #pragma once
+#define PF_EMULATION 1 // kernel sources take their plain-C++ path where the device path is inline PTX
 #include <atomic>
 #include <barrier>
 #include <cmath>
@@ -35,6 +36,10 @@ struct float2
 {
   float x, y;
 };
+struct float4
+{
+  float x, y, z, w;
+};
 struct double4
 {
   double x, y, z, w;
@@ -54,6 +59,16 @@ atomicAdd (double *p, double v)
 {
   std::atomic_ref<double> a (*p);
   double old = a.load (std::memory_order_relaxed);
+  while (!a.compare_exchange_weak (old, old + v, std::memory_order_relaxed))
+    {
+    }
+  return old;
+}
+inline float
+atomicAdd (float *p, float v)
+{
+  std::atomic_ref<float> a (*p);
+  float old = a.load (std::memory_order_relaxed);
   while (!a.compare_exchange_weak (old, old + v, std::memory_order_relaxed))
     {
     }

@@ -8,6 +8,7 @@
 // std::atomic_ref (blocks run concurrently).  Test infrastructure only (tests/test_emulated_library_cpu.py): it is a checker of
 // the library's host logic and kernel sources, never a fallback -- nothing under cracks_b200/ refers to it.
 #pragma once
+#define PF_EMULATION 1 // kernel sources take their plain-C++ path where the device path is inline PTX
 #include <atomic>
 #include <cmath>
 #include <cstdint>

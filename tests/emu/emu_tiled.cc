@@ -129,17 +129,30 @@ emu_apply3d (int variant, int nq, const int *n, const double *h, const double *p
       for (int q = 0; q < 3; ++q)
         k6.wz[q] = k.wvol * k.wq[q];
       k6.kl[0] = p.G_c * p.eps * h[0] * 0.5, k6.kl[1] = p.G_c * p.eps * h[0] / 3.0, k6.kl[2] = p.G_c * p.eps * h[0] / 6.0;
-      if (variant == 26)
+      k6.s2 = k.s2, k6.wvol = k.wvol, k6.cge = p.G_c * p.eps * 8.0 * gam * gam;
+      if (variant == 26 && nq == 3)
         {
           std::vector<double2> coef (T6::coef_per_tile * grid);
-          launch_blocks (k_point_coeffs<double, 16, 4>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
-          launch_blocks (k_apply3d_v6<double, 16, 4, 4>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask, (const double2 *) coef.data (), y);
+          launch_blocks (k_point_coeffs<double, 16, 4, 3>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
+          launch_blocks (k_apply3d_v6<double, double, 3, 16, 4, 4>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask,
+                         (const double2 *) coef.data (), y);
+        }
+      else if (variant == 26)
+        {
+          std::vector<double2> coef (Tile3v6<16, 4, 2>::coef_per_tile * grid);
+          launch_blocks (k_point_coeffs<double, 16, 4, 2>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
+          launch_blocks (k_apply3d_v6<double, double, 2, 16, 4, 4>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask,
+                         (const double2 *) coef.data (), y);
         }
       else
         {
-          std::vector<float2> coef (T6::coef_per_tile * grid);
-          launch_blocks (k_point_coeffs<float, 16, 4>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
-          launch_blocks (k_apply3d_v6<float, 16, 4, 8>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask, (const float2 *) coef.data (), y);
+          // the FP32 instantiations use 32 x 2 tiles (pf_api.cu: V6Shape<float>)
+          const int fx = (n[0] + 31) / 32, fy = (n[1] + 1) / 2;
+          const unsigned fgrid = (unsigned) (fx * fy * n[2]);
+          std::vector<float2> coef (Tile3v6<32, 2, 3>::coef_per_tile * fgrid);
+          launch_blocks (k_point_coeffs<float, 32, 2, 3>, fgrid, 64u, g, p, k, fx, fy, 0, sol, pt, coef.data ());
+          launch_blocks (k_apply3d_v6<float, double, 3, 32, 2, 8>, fgrid, 64u, g, k6, fx, fy, 0, x, sol, mask,
+                         (const float2 *) coef.data (), y);
         }
       return;
     }

@@ -222,6 +222,11 @@ def test_tiled_apply_kernel_sources_match_the_oracle(oracle, emu_tiled, n, h):
         emu_tiled.emu_apply3d(C.c_int(variant), C.c_int(2), nv, hv, _ptr(phys), _ptr(x), _ptr(sol), _ptr(pt), _ptr(mask),
                               _ptr(diag), _ptr(out))
     assert np.max(np.abs(y2[0] - y2[1])) / np.max(np.abs(y2[1])) <= 1e-12
+    if h[0] == h[1] == h[2]:
+        y26 = np.zeros(prob.n_dofs)                                   # v6 with the 2-point rule: the same operator again
+        emu_tiled.emu_apply3d(C.c_int(26), C.c_int(2), nv, hv, _ptr(phys), _ptr(x), _ptr(sol), _ptr(pt), _ptr(mask),
+                              _ptr(diag), _ptr(y26))
+        assert np.max(np.abs(y26 - y2[1])) / np.max(np.abs(y2[1])) <= 1e-12
     # and it is a different (under-integrated) operator, close to the exact one
     assert 1e-6 < np.max(np.abs(y2[0][free] - y_ref[free])) / np.max(np.abs(y_ref[free])) < 0.5
 

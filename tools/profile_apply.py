@@ -20,12 +20,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--refine", type=int, default=4)
     ap.add_argument("--applies", type=int, default=6)
+    ap.add_argument("--bits", type=int, default=64, help="precision of the Krylov operator (pf_set_jacobian_precision)")
+    ap.add_argument("--variant", type=int, default=0, help="pf_debug_set_variant (23 = v4)")
     args = ap.parse_args()
     import cracks_b200 as pf
     from bench import sneddon_state, SEED
     mesh = pf.sneddon_mesh(3, args.refine)
     ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh))
     ctx.set_preconditioner(0, 2, 20.0)
+    if args.variant:
+        ctx._check(ctx.lib.pf_debug_set_variant(ctx.h, args.variant))
+    if args.bits != 64:
+        ctx.set_jacobian_precision(args.bits)
     sol, active = sneddon_state(mesh.n[0], mesh.h[0])
     ctx.set_state(sol, sol, sol, 1.0, 1.0, False, 1e-3)
     ctx.set_dirichlet_all_faces()
