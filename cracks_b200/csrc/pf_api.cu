@@ -180,10 +180,10 @@ struct pf_ctx
   uint8_t *zero_mask = nullptr;       // "nothing constrained", for the hanging-node-only constraint set
   // v6 apply kernel (pf_apply3d_v6.cuh, cubic cells): two state coefficients per quadrature point, refreshed by
   // pf_setup_jacobian; the FP32 set only exists after pf_set_jacobian_precision (ctx, 32)
-  double2 *coef64 = nullptr;
-  float2 *coef32 = nullptr;
-  double2 *coef2_64 = nullptr; // the same for the 2-point-rule operator of the multigrid smoother (every level)
-  float2 *coef2_32 = nullptr;
+  double *coef64 = nullptr;
+  float *coef32 = nullptr;
+  double *coef2_64 = nullptr; // the same for the 2-point-rule operator of the multigrid smoother (every level)
+  float *coef2_32 = nullptr;
   int jacobian_bits = 64;      // precision of the Krylov operator: 64 = exact, 32 = inexact-Newton Jacobian in FP32
   // tuning / debugging switches (per context; the environment is read once, by pf_create)
   int apply_variant = 16;      // 16 = default exact kernel; other numbers only in a PF_TUNING_VARIANTS build
@@ -693,24 +693,26 @@ make_k6 (const pf_ctx *ctx)
   return k;
 }
 
-// tile shapes: 16 x 4 cells for FP64 (64-bit shared-memory accesses are conflict free at any row pitch); FP32 uses
-// 32 x 2 so that the 32 lanes of a warp read 32 consecutive words (16 x 4 has a row pitch of 17 words: 2-way conflicts)
+// tile shapes: 16 x 4 cells and one cell per thread for FP64; FP32 runs two x-adjacent cells per thread in packed
+// arithmetic (f32x2: FFMA2 / FADD2 / FMUL2) on 32 x 4 tiles, i.e. 64 threads per CTA in both cases
 template <typename R> struct V6Shape;
 template <> struct V6Shape<double> { static constexpr int TX = 16, TY = 4; };
 template <> struct V6Shape<float> { static constexpr int TX = 32, TY = 2; };
+template <> struct V6Shape<f32x2> { static constexpr int TX = 32, TY = 4; };
 
 // the coefficient records of every cell layer this rank evaluates (once per pf_setup_jacobian and level)
 template <typename R, int NQ>
 int
-v6_refresh_coefficients (pf_ctx *ctx, typename Pair<R>::type **buf)
+v6_refresh_coefficients (pf_ctx *ctx, typename Lane<R>::S **buf)
 {
-  constexpr int TX = V6Shape<R>::TX, TY = V6Shape<R>::TY;
-  using T = Tile3v6<TX, TY, NQ>;
+  using S = typename Lane<R>::S;
+  constexpr int TX = V6Shape<R>::TX, TY = V6Shape<R>::TY, W = Lane<R>::W;
+  using T = Tile3v6<TX, TY, NQ, W>;
   const Grid &g = ctx->g;
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY, layers = g.cell_end - g.cell_begin;
   if (!*buf)
-    CU (cudaMalloc (buf, sizeof (typename Pair<R>::type) * T::coef_per_tile * (size_t) tiles_x * tiles_y * layers));
-  k_point_coeffs<R, TX, TY, NQ><<<(unsigned) tiles_x * tiles_y * layers, T::NT, 0, ctx->stream>>> (
+    CU (cudaMalloc (buf, sizeof (S) * T::coef_per_tile * (size_t) tiles_x * tiles_y * layers));
+  k_point_coeffs<S, TX, TY, NQ, W><<<(unsigned) tiles_x * tiles_y * layers, TX * TY, 0, ctx->stream>>> (
     g, ctx->p, ctx->k3, tiles_x, tiles_y, g.cell_begin, ctx->sol, ctx->pt, *buf);
   KCHECK ();
   return PF_OK;
@@ -719,10 +721,12 @@ v6_refresh_coefficients (pf_ctx *ctx, typename Pair<R>::type **buf)
 // R = arithmetic of the cell walk, V = type of the global vectors, NQ = 3 (exact rule) or 2 (smoother operator)
 template <typename R, typename V, int NQ, int MINB>
 int
-launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename Pair<R>::type *coef)
+launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename Lane<R>::S *coef)
 {
-  constexpr int TX = V6Shape<R>::TX, TY = V6Shape<R>::TY;
-  using T = Tile3v6<TX, TY, NQ>;
+  using S = typename Lane<R>::S;
+  constexpr int TX = V6Shape<R>::TX, TY = V6Shape<R>::TY, W = Lane<R>::W;
+  using T = Tile3v6<TX, TY, NQ, W>;
+  constexpr size_t smem = (T::smem_elems * sizeof (S) + 15) / 16 * 16 + 2 * T::coef_per_plane * sizeof (S) + 32;
   Grid g = ctx->g;
   const int layer0 = g.cell_begin;
   if (ctx->range_begin >= 0)
@@ -736,12 +740,11 @@ launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename P
   static const char attr_tag = 0;
   if (ctx->attr_done.insert (&attr_tag).second)
     {
-      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int) T::template smem_bytes<R> ()));
+      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
-  k_apply3d_v6<R, V, NQ, TX, TY, MINB><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, T::template smem_bytes<R> (),
-                                         ctx->stream>>> (g, make_k6 (ctx), tiles_x, tiles_y, layer0, x, sol, ctx->mask, coef, y);
+  k_apply3d_v6<R, V, NQ, TX, TY, MINB><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, smem, ctx->stream>>> (
+    g, make_k6 (ctx), tiles_x, tiles_y, layer0, x, sol, ctx->mask, coef, y);
   KCHECK ();
   return PF_OK;
 }
@@ -760,7 +763,7 @@ launch_tiled_default (pf_ctx *ctx, const double *x, double *y, bool approx)
       if (approx && ctx->coef2_64)
         return launch_apply3d_v6<double, double, 2, 4> (ctx, x, ctx->sol, y, ctx->coef2_64);
       if (!approx && ctx->jacobian_bits == 32 && ctx->coef32)
-        return launch_apply3d_v6<float, double, 3, 8> (ctx, x, ctx->sol, y, ctx->coef32);
+        return launch_apply3d_v6<f32x2, double, 3, 4> (ctx, x, ctx->sol, y, ctx->coef32);
       if (!approx && ctx->coef64)
         return launch_apply3d_v6<double, double, 3, 4> (ctx, x, ctx->sol, y, ctx->coef64);
     }
@@ -1549,7 +1552,7 @@ launch_apply3d_mg (pf_ctx *ctx, const float *x, float *y)
   const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
   const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
   if (ctx->apply_variant == 16 && v6_possible (ctx) && ctx->coef2_32)
-    return launch_apply3d_v6<float, float, 2, 8> (ctx, x, ctx->f_sol, y, ctx->coef2_32);
+    return launch_apply3d_v6<f32x2, float, 2, 4> (ctx, x, ctx->f_sol, y, ctx->coef2_32);
   const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
   if (iso)
     k_apply3d_mg<float, TX, TY, TZ, MINB, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
@@ -1804,7 +1807,7 @@ diag_and_aux (pf_ctx *ctx)
   if (ctx->precond == 1 && ctx->mg_approx && ctx->apply_variant == 16 && v6_possible (ctx))
     {
       // state coefficients of the 2-point-rule smoother operator on this level, in the V-cycle's precision
-      rc = ctx->mg_fp32 ? v6_refresh_coefficients<float, 2> (ctx, &ctx->coef2_32)
+      rc = ctx->mg_fp32 ? v6_refresh_coefficients<f32x2, 2> (ctx, &ctx->coef2_32)
                         : v6_refresh_coefficients<double, 2> (ctx, &ctx->coef2_64);
       if (rc)
         return rc;
@@ -2603,7 +2606,7 @@ pf_setup_jacobian (pf_ctx *ctx)
   if (v6_possible (ctx) && ctx->apply_variant == 16)
     {
       if (ctx->jacobian_bits == 32)
-        rc = v6_refresh_coefficients<float, 3> (ctx, &ctx->coef32);
+        rc = v6_refresh_coefficients<f32x2, 3> (ctx, &ctx->coef32);
       else
         rc = v6_refresh_coefficients<double, 3> (ctx, &ctx->coef64);
       if (rc)
@@ -2959,30 +2962,31 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
             return rc;
           if ((rc = apply_dev (ctx, z, w)))
             return rc;
-          // CGS2: two passes of classical Gram-Schmidt, fused multi-dot / multi-axpy
+          // CGS2: two passes of classical Gram-Schmidt with fused multi-dot / multi-axpy kernels and TWO all-reduces
+          // per Arnoldi step: the norm of the new basis vector rides on the second pass (|w'|^2 - sum h2^2) and
+          // the normalisation is part of its axpy sweep
           if ((rc = dots (k + 1, w, 0)))
             return rc;
-          double *gs0 = ctx->h_gs, *gs1 = ctx->h_gs + (m + 2), *gs2 = ctx->h_gs + 2 * (m + 2);
+          double *gs0 = ctx->h_gs, *gs1 = ctx->h_gs + (m + 2);
           CU (cudaMemcpyAsync (gs0, ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToHost,
                                ctx->stream));
           k_multi_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w);
           KCHECK ();
-          if ((rc = dots (k + 1, w, 0)))
+          if ((rc = dots (k + 1, w, 1)))
             return rc;
-          CU (cudaMemcpyAsync (gs1, ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToHost,
+          CU (cudaMemcpyAsync (gs1, ctx->hdev, sizeof (double) * (k + 2), cudaMemcpyDeviceToHost,
                                ctx->stream));
-          k_multi_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w);
-          KCHECK ();
-          if ((rc = dots (0, w, 1)))
-            return rc;
-          CU (cudaMemcpyAsync (gs2, ctx->hdev, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
-          k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, 1.0, 1, w, vk1);
+          k_multi_axpy_scale<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w, vk1);
           KCHECK ();
           CU (cudaStreamSynchronize (ctx->stream));
           ++its;
+          double hk1sq = gs1[k + 1];
           for (int j = 0; j <= k; ++j)
-            H[(size_t) j * m + k] = gs0[j] + gs1[j];
-          const double hk1 = std::sqrt (gs2[0]);
+            {
+              H[(size_t) j * m + k] = gs0[j] + gs1[j];
+              hk1sq -= gs1[j] * gs1[j];
+            }
+          const double hk1 = hk1sq > 0 ? std::sqrt (hk1sq) : 0.0;
           H[(size_t) (k + 1) * m + k] = hk1;
           // Givens rotations
           for (int j = 0; j < k; ++j)

@@ -22,6 +22,8 @@
 // R = float : the same kernel in FP32 for the inexact-Newton Jacobian (pf_set_jacobian_precision); global vectors
 //             stay FP64 (converted on load, z-differences formed in FP64 before the conversion), the residual that
 //             defines the Newton fixed point is never evaluated in reduced precision.
+// R = f32x2 : two x-adjacent cells per thread in packed FP32 (FFMA2 / FADD2 / FMUL2, sm_100 only): the FP32 kernels
+//             are bound by instruction issue, not by the FP32 pipe, and a packed instruction does the work of two.
 #pragma once
 #include "pf_apply3d_v2.cuh"
 
@@ -36,6 +38,65 @@ template <> struct Quad<float> { using type = float4; };
 
 __device__ __forceinline__ double fma_r (double a, double b, double c) { return fma (a, b, c); }
 __device__ __forceinline__ float fma_r (float a, float b, float c) { return fmaf (a, b, c); }
+
+// ---- packed pair of floats: lane x = left cell, lane y = right cell of a thread's pair ---------------------------
+struct f32x2
+{
+  float2 v;
+  __device__ __forceinline__ f32x2 () {}
+  __device__ __forceinline__ f32x2 (float a) { v = make_float2 (a, a); }
+  __device__ __forceinline__ f32x2 (double a) { v = make_float2 ((float) a, (float) a); }
+  __device__ __forceinline__ f32x2 (int a) { v = make_float2 ((float) a, (float) a); }
+  __device__ __forceinline__ f32x2 (float a, float b) { v = make_float2 (a, b); }
+};
+__device__ __forceinline__ f32x2 operator- (f32x2 a) { return f32x2 (-a.v.x, -a.v.y); }
+__device__ __forceinline__ f32x2 operator+ (f32x2 a, f32x2 b) { f32x2 r; r.v = __fadd2_rn (a.v, b.v); return r; }
+__device__ __forceinline__ f32x2 operator- (f32x2 a, f32x2 b) { f32x2 r; r.v = __fadd2_rn (a.v, (-b).v); return r; }
+__device__ __forceinline__ f32x2 operator* (f32x2 a, f32x2 b) { f32x2 r; r.v = __fmul2_rn (a.v, b.v); return r; }
+__device__ __forceinline__ f32x2 &operator+= (f32x2 &a, f32x2 b) { a = a + b; return a; }
+__device__ __forceinline__ f32x2 &operator-= (f32x2 &a, f32x2 b) { a = a - b; return a; }
+__device__ __forceinline__ f32x2 fma_r (f32x2 a, f32x2 b, f32x2 c) { f32x2 r; r.v = __ffma2_rn (a.v, b.v, c.v); return r; }
+
+// ---- how a thread sees the staging arrays: one cell (scalar R) or a pair of x-adjacent cells (f32x2) ---------------
+template <typename R> struct Lane
+{
+  using S = R;                       // element type of the staging arrays in shared memory
+  static constexpr int W = 1;        // cells per thread
+  static __device__ __forceinline__ R ld (const S *p) { return p[0]; }        // node column c of the thread
+  static __device__ __forceinline__ R ld1 (const S *p, R) { return p[1]; }    // node column c + 1
+  static __device__ __forceinline__ void rec (const S *r, R &wg, R &c2) { wg = r[0], c2 = r[1]; }
+  // y tile: phase A adds the contributions to the thread's first node column(s), phase B to its last one
+  static __device__ __forceinline__ void add_a (S *p, R v0, R) { p[0] += v0; }
+  static __device__ __forceinline__ void add_b (S *p, R v1) { p[1] += v1; }
+  static __device__ __forceinline__ R drop_right (R v) { return v; }
+};
+template <> struct Lane<f32x2>
+{
+  using S = float;
+  static constexpr int W = 2;
+  static __device__ __forceinline__ f32x2 ld (const float *p)
+  {
+    f32x2 r;
+    r.v = *reinterpret_cast<const float2 *> (p); // columns (c, c + 1): c is even, the row pitch too
+    return r;
+  }
+  static __device__ __forceinline__ f32x2 ld1 (const float *p, f32x2 a) { return f32x2 (a.v.y, p[2]); } // columns (c + 1, c + 2)
+  static __device__ __forceinline__ void rec (const float *r, f32x2 &wg, f32x2 &c2)
+  {
+    const float4 q = *reinterpret_cast<const float4 *> (r); // (wg left, wg right, c2 left, c2 right)
+    wg = f32x2 (q.x, q.y), c2 = f32x2 (q.z, q.w);
+  }
+  // the middle column c + 1 belongs to both cells of the pair: summed in the thread
+  static __device__ __forceinline__ void add_a (float *p, f32x2 v0, f32x2 v1)
+  {
+    float2 t = *reinterpret_cast<float2 *> (p);
+    t.x += v0.v.x;
+    t.y += v1.v.x + v0.v.y;
+    *reinterpret_cast<float2 *> (p) = t;
+  }
+  static __device__ __forceinline__ void add_b (float *p, f32x2 v1) { p[2] += v1.v.y; }
+  static __device__ __forceinline__ f32x2 drop_right (f32x2 v) { return f32x2 (v.v.x, 0.0f); }
+};
 
 // ---- the coefficient stream: TMA bulk copies (cp.async.bulk, completion on an mbarrier) ---------------------------
 // One contiguous block per (tile, Gauss plane), 9 (or 4) records per cell: thread 0 of the CTA issues the copy, the
@@ -88,26 +149,25 @@ v6_async_proxy_fence ()
 }
 #endif
 
-template <int TX, int TY, int NQ = 3> struct Tile3v6
+// TX x TY cells per tile, W cells per thread; the row pitch of the staging arrays is even when W == 2
+template <int TX, int TY, int NQ = 3, int W = 1> struct Tile3v6
 {
+  static_assert (TX % W == 0, "a thread's cells lie in one tile row");
   static constexpr int NX = TX + 1, NY = TY + 1;
-  static constexpr int NN = NX * NY * 2; // nodes of the tile (one cell layer)
-  static constexpr int NC2 = NX * NY;    // node columns
-  static constexpr int NXC = NX * TY;    // (x-node, cell row)
-  static constexpr int NT = TX * TY;
-  static constexpr int SY = NX, SZ = NX * NY;
+  static constexpr int PX = (W == 2 && NX % 2) ? NX + 1 : NX; // row pitch of the node arrays
+  static constexpr int NN = PX * NY * 2; // nodes of the tile (one cell layer), padded rows
+  static constexpr int NC2 = PX * NY;    // node columns
+  static constexpr int NXC = PX * TY;    // (x-node, cell row)
+  static constexpr int NT = TX / W * TY; // threads
+  static constexpr int SY = PX, SZ = PX * NY;
   static constexpr int NF = 8;  // staged nodal fields: x_u (3), x_phi / 8, u (3), phi / 8
   static constexpr int NFZ = 7; // fields with a z-difference chain: all but phi
   static constexpr int NQP = NQ * NQ * NQ;
   static constexpr size_t scratch = (NFZ * NC2 > 4 * NN) ? (size_t) NFZ * NC2 : (size_t) 4 * NN; // DZ, then the y tile
   static constexpr size_t smem_elems = (size_t) NQ * NF * NC2 + (size_t) NFZ * NQ * NXC + NXC + scratch;
-  // coefficient records of one tile, and of one Gauss plane of it (one bulk copy)
-  static constexpr size_t coef_per_tile = (size_t) NQP * NT;
-  static constexpr size_t coef_per_plane = (size_t) NQ * NQ * NT;
-  // staging arrays (rounded up to 16 bytes) + two plane buffers of coefficient records + 4 mbarriers
-  template <typename R> static constexpr size_t off_cf () { return (smem_elems * sizeof (R) + 15) / 16 * 16; }
-  template <typename R> static constexpr size_t off_mbar () { return off_cf<R> () + 2 * coef_per_plane * 2 * sizeof (R); }
-  template <typename R> static constexpr size_t smem_bytes () { return off_mbar<R> () + 4 * sizeof (unsigned long long); }
+  // coefficient scalars (wg and c2 of every cell) of one tile, and of one Gauss plane of it (one bulk copy)
+  static constexpr size_t coef_per_tile = (size_t) NQP * TX * TY * 2;
+  static constexpr size_t coef_per_plane = (size_t) NQ * NQ * TX * TY * 2;
 };
 
 // constants of one launch, derived on the host from Phys / K3 (cubic cells: h = hx = hy = hz)
@@ -127,32 +187,34 @@ struct K6
 };
 
 // ---- set-up: the two state coefficients per quadrature point ---------------------------------------------
-// One thread per cell, tiles and record order exactly as the apply kernel reads them.  Everything in FP64.
-template <typename R, int TX, int TY, int NQ = 3>
+// One thread per cell; record order exactly as the apply kernel reads it: per (tile, point, thread of the apply
+// kernel) the W values of wg, then the W values of c2.  Everything is computed in FP64 and stored as CS.
+template <typename CS, int TX, int TY, int NQ, int W>
 __global__ void __launch_bounds__ (TX * TY)
 k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, const double *__restrict__ sol,
-                const double *__restrict__ pt, typename Pair<R>::type *__restrict__ coef)
+                const double *__restrict__ pt, CS *__restrict__ coef)
 {
-  using T = Tile3v6<TX, TY, NQ>;
-  const int tid = threadIdx.x;
+  using T = Tile3v6<TX, TY, NQ, W>;
+  const int tid = threadIdx.x, lx = tid % TX, ly = tid / TX;
   int b = blockIdx.x;
   const int bx = b % tiles_x;
   b /= tiles_x;
   const int by = b % tiles_y, bz = b / tiles_y;
-  const int cx = bx * TX + tid % TX, cy = by * TY + tid / TX, cz = g.cell_begin + bz;
-  typename Pair<R>::type *out = coef + ((size_t) ((cz - layer0) * tiles_y + by) * tiles_x + bx) * T::coef_per_tile + tid;
+  const int cx = bx * TX + lx, cy = by * TY + ly, cz = g.cell_begin + bz;
+  const int thread = lx / W + (TX / W) * ly, lane = lx % W; // thread of the apply kernel that owns this cell
+  CS *out = coef + ((size_t) ((cz - layer0) * tiles_y + by) * tiles_x + bx) * T::coef_per_tile + (size_t) thread * 2 * W + lane;
   const bool valid = cx < g.n[0] && cy < g.n[1] && cz < g.cell_end;
-  double u[8][3], ph[8], pe[8];
+  double u[8][3], pe[8];
 #pragma unroll
   for (int v = 0; v < 8; ++v)
     {
-      u[v][0] = u[v][1] = u[v][2] = ph[v] = pe[v] = 0;
+      u[v][0] = u[v][1] = u[v][2] = pe[v] = 0;
       if (valid)
         {
           const long long n = (cx + (v & 1)) + (long long) g.nn[0] * (cy + ((v >> 1) & 1))
                               + g.nodes_per_plane * (cz + (v >> 2) - g.plane_begin);
           const double4 s = *reinterpret_cast<const double4 *> (sol + 4 * n);
-          u[v][0] = s.x, u[v][1] = s.y, u[v][2] = s.z, ph[v] = s.w, pe[v] = pt[n];
+          u[v][0] = s.x, u[v][1] = s.y, u[v][2] = s.z, pe[v] = pt[n];
         }
     }
   const double gam = k.gu[0];
@@ -181,7 +243,7 @@ k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, cons
               G[c][2] = fma (d2, u[v][c], G[c][2]);
             }
         }
-      // true gradient = k.ih * G / 4 = (4 gam) G / 4 = gam G
+      // true gradient = (1/h) G / 4 = gam G
       if (p.clamp_extra)
         pte = fmin (fmax (pte, 0.0), 1.0);
       const double gdeg = fma (omk * pte, pte, p.kappa);
@@ -199,16 +261,9 @@ k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, cons
         for (int d = 0; d < 3; ++d)
           ee = fma (E[c][d], E[c][d], ee);
       const double sE = p.lambda * tr * tr + 2.0 * p.mu * ee; // sigma(u) : E(u)
-      typename Pair<R>::type rec;
-      rec.x = (R) (w * gdeg * two_mu_g2);
-      rec.y = (R) (0.125 * w * (omk * sE + p.G_c / p.eps - 2.0 * p.P1 * tr));
-      if (valid)
-        out[(size_t) q * T::NT] = rec;
-      else
-        {
-          rec.x = rec.y = 0;
-          out[(size_t) q * T::NT] = rec;
-        }
+      CS *rec = out + (size_t) q * T::NT * 2 * W;
+      rec[0] = valid ? (CS) (w * gdeg * two_mu_g2) : (CS) 0;
+      rec[W] = valid ? (CS) (0.125 * w * (omk * sE + p.G_c / p.eps - 2.0 * p.P1 * tr)) : (CS) 0;
     }
 }
 
@@ -218,57 +273,61 @@ k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, cons
 template <typename R, int TX, int TY, int NQ>
 __device__ __forceinline__ void
 tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const int cy0, const int cz0,
-               const R *__restrict__ AZ, const R *__restrict__ BZ, const R *__restrict__ BR,
-               const typename Pair<R>::type *__restrict__ coef_tile, typename Pair<R>::type *CF,
-               unsigned long long *mbar, R *__restrict__ ys)
+               const typename Lane<R>::S *__restrict__ AZ, const typename Lane<R>::S *__restrict__ BZ,
+               const typename Lane<R>::S *__restrict__ BR, const typename Lane<R>::S *__restrict__ coef_tile,
+               typename Lane<R>::S *CF, unsigned long long *mbar, typename Lane<R>::S *__restrict__ ys)
 {
-  using T = Tile3v6<TX, TY, NQ>;
-  using R2 = typename Pair<R>::type;
-  constexpr unsigned plane_bytes = (unsigned) (T::coef_per_plane * sizeof (R2));
-  constexpr int NN = T::NN, NX = T::NX, NC2 = T::NC2, NXC = T::NXC, NF = T::NF, NT = T::NT;
+  using L = Lane<R>;
+  using S = typename L::S;
+  constexpr int W = L::W;
+  using T = Tile3v6<TX, TY, NQ, W>;
+  constexpr int NN = T::NN, PX = T::PX, NC2 = T::NC2, NXC = T::NXC, NF = T::NF, NT = T::NT;
+  constexpr unsigned plane_bytes = (unsigned) (T::coef_per_plane * sizeof (S));
   constexpr bool CEN = NQ == 3; // the 3-point rule has a centre point and uses the closed-form Laplacian
   constexpr int NCQ = CEN ? 3 : 4; // components whose fluxes go through the quadrature
-  const R S = (R) (CEN ? k.s : k.s2);
-  const int tx = tid % TX, ty = tid / TX;
-  const bool valid = (cx0 + tx < g.n[0]) && (cy0 + ty < g.n[1]) && (cz0 < g.cell_end);
-  const int c00 = tx + NX * ty;  // node column (tx, ty) of AZ
-  const int it0 = tx + NX * ty;  // (x-node tx, cell row ty) of BZ (NXC = NX * TY: same linear index)
-  const int nbase = tx + T::SY * ty;
+  const R Sq = (R) (CEN ? k.s : k.s2);
+  const int tx = tid % (TX / W), ty = tid / (TX / W);
+  const bool valid = (cx0 + W * tx < g.n[0]) && (cy0 + ty < g.n[1]) && (cz0 < g.cell_end);
+  const bool right_valid = W == 1 || (cx0 + W * tx + 1 < g.n[0]); // W == 2: the second cell of the pair exists
+  const int c00 = W * tx + PX * ty;  // first node column of the thread in AZ; (x-node, cell row) in BZ alike
+  const int nbase = W * tx + T::SY * ty;
   const R lam2 = (R) k.lam2, nbeta = (R) -k.beta;
-  const R es[3] = {-S, CEN ? (R) 0 : S, S};
+  const R es[3] = {-Sq, CEN ? (R) 0 : Sq, Sq};
   const R kl1 = (R) k.kl[0], kl2 = (R) k.kl[1], kl3 = (R) k.kl[2];
   const R wb = (R) (k.wvol * k.cge); // NQ == 2: weight of the phi-gradient flux (every point has JxW = h^3/8)
+  const R half = (R) 0.5, two = (R) 2;
 
 #pragma unroll 1
   for (int qz = 0; qz < NQ; ++qz)
     {
-      const R ez = (qz == 0) ? -S : ((CEN && qz == 1) ? (R) 0 : S);
-      const R *Aq = AZ + qz * NF * NC2 + c00;
+      const R ez = (qz == 0) ? -Sq : ((CEN && qz == 1) ? (R) 0 : Sq);
+      const S *Aq = AZ + qz * NF * NC2 + c00;
       // the coefficient records of this plane: buffer qz % 2, filled by the bulk copy that signals mbar[qz]
-      const R2 *cf = CF + (size_t) (qz & 1) * T::coef_per_plane + tid;
+      const S *cf = CF + (size_t) (qz & 1) * T::coef_per_plane + (size_t) tid * 2 * W;
 #ifndef PF_EMULATION
       v6_mbar_wait (mbar + qz, 0);
 #endif
       // (phi,u) weight of the point classes of this plane: JxW k1
-      const R wzk = (R) ((CEN ? k.wz[qz] : k.wvol) * k.k1);
-      const R wk[3] = {CEN ? wzk * (R) k.w[0] : wzk, wzk * (R) k.w[1], wzk * (R) k.w[2]};
+      const double wzk = (CEN ? k.wz[qz] : k.wvol) * k.k1;
+      const R wk[3] = {(R) (CEN ? wzk * k.w[0] : wzk), (R) (wzk * k.w[1]), (R) (wzk * k.w[2])};
       R VP[4][2], VR[4][2], DP[4][2], DR[4][2], YP[4], YR[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         {
-          YP[c] = YR[c] = 0;
+          YP[c] = YR[c] = (R) 0;
 #pragma unroll
           for (int vx = 0; vx < 2; ++vx)
-            VP[c][vx] = VR[c][vx] = DP[c][vx] = DR[c][vx] = 0;
+            VP[c][vx] = VR[c][vx] = DP[c][vx] = DR[c][vx] = (R) 0;
         }
       if (valid)
         {
-          // plane level: in-plane sums and differences of the four node columns of the cell
+          // plane level: in-plane sums and differences of the four node columns of a cell
           R s0[NF], s1[NF], r0[NF], r1[NF];
 #pragma unroll
           for (int f = 0; f < NF; ++f)
             {
-              const R a00 = Aq[f * NC2], a10 = Aq[f * NC2 + 1], a01 = Aq[f * NC2 + NX], a11 = Aq[f * NC2 + NX + 1];
+              const R a00 = L::ld (Aq + f * NC2), a10 = L::ld1 (Aq + f * NC2, a00);
+              const R a01 = L::ld (Aq + f * NC2 + PX), a11 = L::ld1 (Aq + f * NC2 + PX, a01);
               s0[f] = a00 + a01, s1[f] = a10 + a11, r0[f] = a01 - a00, r1[f] = a11 - a10;
             }
 #pragma unroll
@@ -276,7 +335,10 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
             {
               const R ey = es[qy];
               const bool ceny = CEN && qy == 1;
-              const R2 c0 = cf[(qy * NQ + 0) * NT], c1 = cf[(qy * NQ + 1) * NT], c2 = CEN ? cf[(qy * NQ + 2) * NT] : c1;
+              R wg3[3], c23[3];
+#pragma unroll
+              for (int qx = 0; qx < NQ; ++qx)
+                L::rec (cf + (size_t) (qy * NQ + qx) * NT * 2 * W, wg3[qx], c23[qx]);
               // x-derivative (constant along x), y-derivative and z-derivative (linear in xi_x: P + ex R) of the
               // displacement-like fields f = 0..2 (x), 4..6 (U) and -- 2-point rule only -- of x's phi (f = 3)
               R dx[7], PxDy[7], RxDy[7], PxBz[7], RxBz[7];
@@ -289,7 +351,8 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
                   dx[f] = ceny ? ds : fma_r (ey, dr, ds);
                   PxDy[f] = r0[f] + r1[f];
                   RxDy[f] = dr;
-                  const R z0 = BZ[(f * NQ + qy) * NXC + it0], z1 = BZ[(f * NQ + qy) * NXC + it0 + 1];
+                  const S *bz = BZ + (f * NQ + qy) * NXC + c00;
+                  const R z0 = L::ld (bz), z1 = L::ld1 (bz, z0);
                   PxBz[f] = z0 + z1;
                   RxBz[f] = z1 - z0;
                 }
@@ -300,14 +363,14 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
               const R oP01 = PxDy[0] + dx[1], oP02 = PxBz[0] + dx[2], oP12 = PxBz[1] + PxDy[2], oR12 = RxBz[1] + RxDy[2];
               const R uP01 = PxDy[4] + dx[5], uP02 = PxBz[4] + dx[6], uP12 = PxBz[5] + PxDy[6], uR12 = RxBz[5] + RxDy[6];
               // accumulators of the transposed x-collapse: stresses S00 S01 S02 S11 S12 S22 (sum and xi_x-weighted sum)
-              R P00 = 0, P01 = 0, P02 = 0, P11 = 0, P12 = 0, P22 = 0, R01 = 0, R02 = 0, R11 = 0, R12 = 0, R22 = 0;
-              R AP = 0, AR = 0;
-              R F1R = 0, F2R = 0; // 2-point rule: xi_x-weighted sums of the phi-gradient (its plain sums are closed forms)
+              R P00 = (R) 0, P01 = (R) 0, P02 = (R) 0, P11 = (R) 0, P12 = (R) 0, P22 = (R) 0;
+              R R01 = (R) 0, R02 = (R) 0, R11 = (R) 0, R12 = (R) 0, R22 = (R) 0;
+              R AP = (R) 0, AR = (R) 0;
+              R F1R = (R) 0, F2R = (R) 0; // 2-point rule: xi_x-weighted sums of the phi-gradient (its plain sums are closed forms)
 #pragma unroll
               for (int qx = 0; qx < NQ; ++qx)
                 {
                   const R ex = es[qx];
-                  const R2 c = qx == 0 ? c0 : (qx == 1 ? c1 : c2);
                   const bool cen = CEN && qx == 1;
                   const R G00 = dx[0], U00 = dx[4];
                   const R G11 = cen ? PxDy[1] : fma_r (ex, RxDy[1], PxDy[1]);
@@ -327,14 +390,14 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
                   const R tU = fma_r (lam2, trU, nbeta);
                   const R dd = fma_r (U00, G00, fma_r (U11, G11, U22 * G22));
                   const R od = fma_r (u01, o01, fma_r (u02, o02, u12 * o12));
-                  const R spg = fma_r (tU, trG, fma_r ((R) 0.5, od, dd));
+                  const R spg = fma_r (tU, trG, fma_r (half, od, dd));
                   const int wc = CEN ? (qx == 1) + (qy == 1) : 0; // point class: corner-, edge-, centre-like in the plane
-                  const R wa = fma_r (pf * wk[wc], spg, dphi * c.y);
+                  const R wa = fma_r (pf * wk[wc], spg, dphi * c23[qx]);
                   AP += wa;
                   if (!cen)
                     AR = fma_r (ex, wa, AR);
                   // (u,u): stress in units of 2 mu gam^2, weight wg = JxW g(phi~) 2 mu gam^2 from the coefficient record
-                  const R wg = c.x, wgh = (R) 0.5 * c.x;
+                  const R wg = wg3[qx], wgh = half * wg;
                   const R t00 = fma_r (lam2, trG, G00), t11 = fma_r (lam2, trG, G11), t22 = fma_r (lam2, trG, G22);
                   P00 = fma_r (wg, t00, P00);
                   P11 = fma_r (wg, t11, P11);
@@ -359,17 +422,18 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
                     }
                 }
               // fx = (S00, S01, S02), fy = (S01, S11, S12), fz = (S02, S12, S22); NQ == 2: + G_c eps grad(dphi)
-              const R XS[4] = {P00, P01, P02, CEN ? (R) 0 : (R) 2 * wb * dx[3]};
-              const R yP[4] = {P01, P11, P12, CEN ? (R) 0 : (R) 2 * wb * PxDy[3]}, yR[4] = {R01, R11, R12, wb * F1R};
-              const R ZP[4] = {P02, P12, P22, CEN ? (R) 0 : (R) 2 * wb * PxBz[3]}, ZR[4] = {R02, R12, R22, wb * F2R};
+              const R XS[4] = {P00, P01, P02, CEN ? (R) 0 : two * wb * dx[3]};
+              const R yP[4] = {P01, P11, P12, CEN ? (R) 0 : two * wb * PxDy[3]}, yR[4] = {R01, R11, R12, wb * F1R};
+              const R ZP[4] = {P02, P12, P22, CEN ? (R) 0 : two * wb * PxBz[3]}, ZR[4] = {R02, R12, R22, wb * F2R};
               if (CEN && qy == 1 && qz == 1)
                 {
                   // closed-form G_c eps grad(dphi).grad(psi) (cracks.cc:2378): the Q1 Laplacian is diagonal in the
                   // sum / difference basis of the 8 cell nodes; x-inverse here, y and z by stage 4 (xi_z = 0 here)
-                  const R r0y = BR[it0], r1y = BR[it0 + 1];
+                  const R r0y = L::ld (BR + c00), r1y = L::ld1 (BR + c00, r0y);
                   const R dxp = s1[3] - s0[3];                       // x-difference of the y-sum (xi_y = 0)
                   const R pdy = r0[3] + r1[3], rdy = r1[3] - r0[3];  // y-difference: x-sum and x-difference
-                  const R z0 = BZ[(3 * NQ + 1) * NXC + it0], z1 = BZ[(3 * NQ + 1) * NXC + it0 + 1];
+                  const S *bz = BZ + (3 * NQ + 1) * NXC + c00;
+                  const R z0 = L::ld (bz), z1 = L::ld1 (bz, z0);
                   const R pbz = z0 + z1, rbz = z1 - z0;
                   const R o_rpp = kl1 * dxp, o_prp = kl1 * pdy, o_ppr = kl1 * pbz;
                   const R o_rrp = kl2 * rdy, o_rpr = kl2 * rbz, o_prr = kl2 * (r0y + r1y);
@@ -414,8 +478,9 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
                 }
             }
         }
-      // ---- stage 4: plane -> shared y tile.  x-neighbours are lanes of one warp (TX == 16 or 32): the two vx
-      // phases are ordered with __syncwarp; y-neighbours may sit in other warps: block barriers between vy phases
+      // ---- stage 4: plane -> shared y tile.  x-neighbours are lanes of one warp: the writes to a thread's first
+      // node column(s) (phase A) and to its last one (phase B, the first column of the next thread) are ordered with
+      // __syncwarp; y-neighbours may sit in other warps: block barriers between the vy phases
       const R omez = (R) 1 - ez, opez = (R) 1 + ez;
 #pragma unroll
       for (int vy = 0; vy < 2; ++vy)
@@ -423,33 +488,39 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
 #pragma unroll
           for (int vz = 0; vz < 2; ++vz)
             {
+              R val[2][4];
 #pragma unroll
               for (int vx = 0; vx < 2; ++vx)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  {
+                    R a;
+                    if (c >= NCQ)
+                      a = (vy == 0) ? VP[c][vx] - VR[c][vx] : VP[c][vx] + VR[c][vx];
+                    else
+                      {
+                        const R yv = vx == 0 ? YP[c] - YR[c] : YP[c] + YR[c];
+                        a = (vy == 0) ? VP[c][vx] - VR[c][vx] - yv : VP[c][vx] + VR[c][vx] + yv;
+                      }
+                    const R d = (vy == 0) ? DP[c][vx] - DR[c][vx] : DP[c][vx] + DR[c][vx];
+                    const R v = (vz == 0) ? fma_r (a, omez, -d) : fma_r (a, opez, d);
+                    val[vx][c] = right_valid ? v : L::drop_right (v);
+                  }
+              S *yn = ys + nbase + T::SY * vy + T::SZ * vz;
+              if (valid)
                 {
-                  R val[4];
 #pragma unroll
                   for (int c = 0; c < 4; ++c)
-                    {
-                      R a;
-                      if (c >= NCQ)
-                        a = (vy == 0) ? VP[c][vx] - VR[c][vx] : VP[c][vx] + VR[c][vx];
-                      else
-                        {
-                          const R yv = vx == 0 ? YP[c] - YR[c] : YP[c] + YR[c];
-                          a = (vy == 0) ? VP[c][vx] - VR[c][vx] - yv : VP[c][vx] + VR[c][vx] + yv;
-                        }
-                      const R d = (vy == 0) ? DP[c][vx] - DR[c][vx] : DP[c][vx] + DR[c][vx];
-                      val[c] = (vz == 0) ? fma_r (a, omez, -d) : fma_r (a, opez, d);
-                    }
-                  const int n0 = nbase + vx + T::SY * vy + T::SZ * vz;
-                  if (valid)
-                    {
-#pragma unroll
-                      for (int c = 0; c < 4; ++c)
-                        ys[c * NN + n0] += val[c];
-                    }
-                  __syncwarp ();
+                    L::add_a (yn + c * NN, val[0][c], val[1][c]);
                 }
+              __syncwarp ();
+              if (valid)
+                {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    L::add_b (yn + c * NN, val[1][c]);
+                }
+              __syncwarp ();
             }
           __syncthreads ();
         }
@@ -473,25 +544,28 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
 
 // the whole kernel: staging (stages 1 and 2), the cell walk, the flush of the y tile.
 // V = type of the global vectors x, sol, y (FP64 for the Krylov operator, FP32 inside the FP32 V-cycle);
-// R = arithmetic type of the cell walk.  The z-collapse of stage 1 is done in V.
+// R = arithmetic type of the cell walk (double, float, or f32x2 = two cells per thread in packed FP32).
+// The z-collapse of stage 1 is done in V.
 template <typename R, typename V, int NQ, int TX, int TY, int MINB>
-__global__ void __launch_bounds__ (TX * TY, MINB)
+__global__ void __launch_bounds__ (TX / Lane<R>::W * TY, MINB)
 k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__restrict__ x,
               const V *__restrict__ sol, const uint8_t *__restrict__ mask,
-              const typename Pair<R>::type *__restrict__ coef, V *__restrict__ y)
+              const typename Lane<R>::S *__restrict__ coef, V *__restrict__ y)
 {
-  using T = Tile3v6<TX, TY, NQ>;
+  using S = typename Lane<R>::S;
+  constexpr int W = Lane<R>::W;
+  using T = Tile3v6<TX, TY, NQ, W>;
   using V4 = typename Quad<V>::type;
-  constexpr int NN = T::NN, NT = T::NT, NX = T::NX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC, NF = T::NF, NFZ = T::NFZ;
+  constexpr int NN = T::NN, NT = T::NT, NX = T::NX, PX = T::PX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC, NF = T::NF,
+                NFZ = T::NFZ;
   extern __shared__ __align__ (16) unsigned char smem_raw[];
-  R *AZ = reinterpret_cast<R *> (smem_raw); // [NQ][NF][NC2]
-  R *BZ = AZ + NQ * NF * NC2;               // [NFZ][NQ][NXC]
-  R *BR = BZ + NFZ * NQ * NXC;              // [NXC]: y-difference of the z-difference of x's phi
-  R *DZ = BR + NXC;                         // [NFZ][NC2], stage 1 -> 2 only
-  R *ys = DZ;                               // [4][NN], aliases DZ
-  using R2 = typename Pair<R>::type;
-  constexpr size_t off_cf = (T::smem_elems * sizeof (R) + 15) / 16 * 16, off_mbar = off_cf + 2 * T::coef_per_plane * sizeof (R2);
-  R2 *CF = reinterpret_cast<R2 *> (smem_raw + off_cf);                                // [2][NQ*NQ][NT]
+  S *AZ = reinterpret_cast<S *> (smem_raw); // [NQ][NF][NC2]
+  S *BZ = AZ + NQ * NF * NC2;               // [NFZ][NQ][NXC]
+  S *BR = BZ + NFZ * NQ * NXC;              // [NXC]: y-difference of the z-difference of x's phi
+  S *DZ = BR + NXC;                         // [NFZ][NC2], stage 1 -> 2 only
+  S *ys = DZ;                               // [4][NN], aliases DZ
+  constexpr size_t off_cf = (T::smem_elems * sizeof (S) + 15) / 16 * 16, off_mbar = off_cf + 2 * T::coef_per_plane * sizeof (S);
+  S *CF = reinterpret_cast<S *> (smem_raw + off_cf);                                       // [2][NQ*NQ][NT][2 W]
   unsigned long long *mbar = reinterpret_cast<unsigned long long *> (smem_raw + off_mbar); // one per Gauss plane
 
   const int tid = threadIdx.x;
@@ -501,7 +575,7 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
   const int by = b % tiles_y;
   const int bz = b / tiles_y;
   const int cx0 = bx * TX, cy0 = by * TY, cz0 = g.cell_begin + bz * g.layer_stride;
-  const R2 *coef_tile = coef + ((size_t) ((cz0 - layer0) * tiles_y + by) * tiles_x + bx) * T::coef_per_tile;
+  const S *coef_tile = coef + ((size_t) ((cz0 - layer0) * tiles_y + by) * tiles_x + bx) * T::coef_per_tile;
   // the records of the first two Gauss planes start to arrive while x and U are staged
 #ifndef PF_EMULATION
   if (tid == 0)
@@ -509,7 +583,7 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
       for (int q = 0; q < NQ; ++q)
         v6_mbar_init (mbar + q);
       v6_mbar_init_fence ();
-      constexpr unsigned plane_bytes = (unsigned) (T::coef_per_plane * sizeof (R2));
+      constexpr unsigned plane_bytes = (unsigned) (T::coef_per_plane * sizeof (S));
       v6_bulk_load (CF, coef_tile, plane_bytes, mbar);
       v6_bulk_load (CF + T::coef_per_plane, coef_tile + T::coef_per_plane, plane_bytes, mbar + 1);
     }
@@ -519,19 +593,19 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
 #endif
   const int nnx = g.nn[0], nny = g.nn[1];
   const long long pstride = g.nodes_per_plane;
-  const V S = (V) (NQ == 3 ? k.s : k.s2);
+  const V Sq = (V) (NQ == 3 ? k.s : k.s2);
   const V eighth = (V) 0.125;
 
   // ---- stage 1: z-collapse per node column, in the precision of the global vectors ----------------
   for (int i = tid; i < NC2; i += NT)
     {
-      const int ix = i % NX, iy = i / NX;
+      const int ix = i % PX, iy = i / PX;
       const int gx = cx0 + ix, gy = cy0 + iy;
       V f0[NF], f1[NF];
 #pragma unroll
       for (int f = 0; f < NF; ++f)
         f0[f] = f1[f] = 0;
-      if (gx < nnx && gy < nny && cz0 < g.cell_end)
+      if (ix < NX && gx < nnx && gy < nny && cz0 < g.cell_end)
         {
           const long long n0 = gx + (long long) nnx * gy + pstride * (cz0 - g.plane_begin);
           const long long n1 = n0 + pstride;
@@ -555,31 +629,31 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
       for (int f = 0; f < NF; ++f)
         {
           const V s = f0[f] + f1[f], r = f1[f] - f0[f];
-          AZ[(0 * NF + f) * NC2 + i] = (R) fma_r (-S, r, s);
-          AZ[(1 * NF + f) * NC2 + i] = (NQ == 3) ? (R) s : (R) fma_r (S, r, s);
+          AZ[(0 * NF + f) * NC2 + i] = (S) fma_r (-Sq, r, s);
+          AZ[(1 * NF + f) * NC2 + i] = (NQ == 3) ? (S) s : (S) fma_r (Sq, r, s);
           if (NQ == 3)
-            AZ[(2 * NF + f) * NC2 + i] = (R) fma_r (S, r, s);
+            AZ[(2 * NF + f) * NC2 + i] = (S) fma_r (Sq, r, s);
           if (f < NFZ)
-            DZ[f * NC2 + i] = (R) r;
+            DZ[f * NC2 + i] = (S) r;
         }
     }
   __syncthreads ();
   // ---- stage 2: y-collapse of the z-difference chain ------------------------------
   for (int i = tid; i < NXC; i += NT)
     {
-      const int ix = i % NX, cy = i / NX;
-      const int c0 = ix + NX * cy;
+      const int ix = i % PX, cy = i / PX;
+      const int c0 = ix + PX * cy;
 #pragma unroll
       for (int f = 0; f < NFZ; ++f)
         {
-          const R d0 = DZ[f * NC2 + c0], d1 = DZ[f * NC2 + c0 + NX];
-          const R P = d0 + d1, Rd = d1 - d0;
+          const S d0 = DZ[f * NC2 + c0], d1 = DZ[f * NC2 + c0 + PX];
+          const S P = d0 + d1, Rd = d1 - d0;
           if (f == 3)
             BR[i] = Rd;
-          BZ[(f * NQ + 0) * NXC + i] = fma_r ((R) -S, Rd, P);
-          BZ[(f * NQ + 1) * NXC + i] = (NQ == 3) ? P : fma_r ((R) S, Rd, P);
+          BZ[(f * NQ + 0) * NXC + i] = fma_r ((S) -Sq, Rd, P);
+          BZ[(f * NQ + 1) * NXC + i] = (NQ == 3) ? P : fma_r ((S) Sq, Rd, P);
           if (NQ == 3)
-            BZ[(f * NQ + 2) * NXC + i] = fma_r ((R) S, Rd, P);
+            BZ[(f * NQ + 2) * NXC + i] = fma_r ((S) Sq, Rd, P);
         }
     }
   __syncthreads ();
@@ -592,9 +666,9 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
   // ---- flush the y tile -----------------------------------------------------------
   for (int i = tid; i < NN; i += NT)
     {
-      const int ix = i % NX, iy = (i / NX) % NY, iz = i / (NX * NY);
+      const int ix = i % PX, iy = (i / PX) % NY, iz = i / (PX * NY);
       const int gx = cx0 + ix, gy = cy0 + iy, gz = cz0 + iz;
-      if (gx < nnx && gy < nny && cz0 < g.cell_end)
+      if (ix < NX && gx < nnx && gy < nny && cz0 < g.cell_end)
         {
           const long long n = gx + (long long) nnx * gy + pstride * (gz - g.plane_begin);
           const uint8_t m = mask[n];

@@ -420,6 +420,28 @@ k_multi_axpy (long long n, int k, const double *__restrict__ V, long long stride
     }
 }
 
+// second Gram-Schmidt pass and normalisation in one sweep: v_next = (w - sum_j h[j] V_j) / hk1 with
+// hk1^2 = |w|^2 - sum_j h[j]^2 (h[k] = |w|^2 of the vector BEFORE this pass; the h[j] of a second pass are at
+// round-off level, so the Pythagorean form loses nothing).  hk1 == 0: v_next = the unscaled vector (breakdown,
+// detected by the host from the same numbers).
+__global__ void __launch_bounds__ (RED_THREADS)
+k_multi_axpy_scale (long long n, int k, const double *__restrict__ V, long long stride, const double *__restrict__ h,
+                    const double *__restrict__ w, double *__restrict__ v_next)
+{
+  double s2 = h[k];
+  for (int j = 0; j < k; ++j)
+    s2 = fma (-h[j], h[j], s2);
+  const double inv = s2 > 0 ? rsqrt (s2) : 1.0;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long) gridDim.x * blockDim.x)
+    {
+      double wi = w[i];
+      for (int j = 0; j < k; ++j)
+        wi = fma (-h[j], V[j * stride + i], wi);
+      v_next[i] = wi * inv;
+    }
+}
+
 // x += sum_j yv[j] V_j  (solution update; yv on device)
 __global__ void __launch_bounds__ (RED_THREADS)
 k_combine (long long n, int k, const double *__restrict__ V, long long stride,

@@ -40,6 +40,12 @@ struct float4
 {
   float x, y, z, w;
 };
+// packed FP32 intrinsics of sm_100 (pf_apply3d_v6.cuh: two cells per thread), lane by lane
+inline float2 make_float2 (float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+inline float2 __ffma2_rn (float2 a, float2 b, float2 c) { return make_float2 (std::fma (a.x, b.x, c.x), std::fma (a.y, b.y, c.y)); }
+inline float2 __fadd2_rn (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
+inline float2 __fmul2_rn (float2 a, float2 b) { return make_float2 (a.x * b.x, a.y * b.y); }
+
 struct double4
 {
   double x, y, z, w;

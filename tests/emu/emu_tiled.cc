@@ -132,27 +132,37 @@ emu_apply3d (int variant, int nq, const int *n, const double *h, const double *p
       k6.s2 = k.s2, k6.wvol = k.wvol, k6.cge = p.G_c * p.eps * 8.0 * gam * gam;
       if (variant == 26 && nq == 3)
         {
-          std::vector<double2> coef (T6::coef_per_tile * grid);
-          launch_blocks (k_point_coeffs<double, 16, 4, 3>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
+          std::vector<double> coef (T6::coef_per_tile * grid);
+          launch_blocks (k_point_coeffs<double, 16, 4, 3, 1>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
           launch_blocks (k_apply3d_v6<double, double, 3, 16, 4, 4>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask,
-                         (const double2 *) coef.data (), y);
+                         (const double *) coef.data (), y);
         }
       else if (variant == 26)
         {
-          std::vector<double2> coef (Tile3v6<16, 4, 2>::coef_per_tile * grid);
-          launch_blocks (k_point_coeffs<double, 16, 4, 2>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
+          std::vector<double> coef (Tile3v6<16, 4, 2>::coef_per_tile * grid);
+          launch_blocks (k_point_coeffs<double, 16, 4, 2, 1>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
           launch_blocks (k_apply3d_v6<double, double, 2, 16, 4, 4>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask,
-                         (const double2 *) coef.data (), y);
+                         (const double *) coef.data (), y);
         }
       else
         {
-          // the FP32 instantiations use 32 x 2 tiles (pf_api.cu: V6Shape<float>)
-          const int fx = (n[0] + 31) / 32, fy = (n[1] + 1) / 2;
+          // the FP32 Jacobian: two cells per thread in packed arithmetic on 32 x 4 tiles (pf_api.cu: V6Shape<f32x2>)
+          const int fx = (n[0] + 31) / 32, fy = (n[1] + 3) / 4;
           const unsigned fgrid = (unsigned) (fx * fy * n[2]);
-          std::vector<float2> coef (Tile3v6<32, 2, 3>::coef_per_tile * fgrid);
-          launch_blocks (k_point_coeffs<float, 32, 2, 3>, fgrid, 64u, g, p, k, fx, fy, 0, sol, pt, coef.data ());
-          launch_blocks (k_apply3d_v6<float, double, 3, 32, 2, 8>, fgrid, 64u, g, k6, fx, fy, 0, x, sol, mask,
-                         (const float2 *) coef.data (), y);
+          if (nq == 3)
+            {
+              std::vector<float> coef (Tile3v6<32, 4, 3, 2>::coef_per_tile * fgrid);
+              launch_blocks (k_point_coeffs<float, 32, 4, 3, 2>, fgrid, 128u, g, p, k, fx, fy, 0, sol, pt, coef.data ());
+              launch_blocks (k_apply3d_v6<f32x2, double, 3, 32, 4, 4>, fgrid, 64u, g, k6, fx, fy, 0, x, sol, mask,
+                             (const float *) coef.data (), y);
+            }
+          else
+            {
+              std::vector<float> coef (Tile3v6<32, 4, 2, 2>::coef_per_tile * fgrid);
+              launch_blocks (k_point_coeffs<float, 32, 4, 2, 2>, fgrid, 128u, g, p, k, fx, fy, 0, sol, pt, coef.data ());
+              launch_blocks (k_apply3d_v6<f32x2, double, 2, 32, 4, 4>, fgrid, 64u, g, k6, fx, fy, 0, x, sol, mask,
+                             (const float *) coef.data (), y);
+            }
         }
       return;
     }
