@@ -422,36 +422,46 @@ def main():
     owned_nodes = (lay.owned_end - lay.owned_begin) * lay.n_nodes_plane
 
     newton = None
+    newton_inexact = None
     if not args.no_newton:
         # second half of BASELINE.json's metric: Newton-its/s of the device-resident
         # active-set Newton loop (cracks.cc:2780-2994) on the same mesh (all ranks, same
         # z-slab decomposition), real time steps 0..1 of parameters_sneddon_3d.prm from the
-        # interpolated initial condition
-        nctx = pf.PhaseFieldContext(mesh, params, device=local_rank, rank=rank, nranks=world, nccl_id=fresh_nccl_id())
-        drv = pf.SneddonDriver(nctx, pressure=lambda t: 1e-3, max_no_timesteps=1, newton_lower_bound=1e-7,
-                               max_newton=50, max_line_search=10, gmres_max_it=200)
-        barrier()
-        t0 = time.perf_counter()
-        try:
-            # every decision in the loop is taken on all-reduced values, so a failure is raised on all ranks alike
-            nstats, nerr = drv.run(mesh_diameter(mesh)), None
-        except pf.PFError as exc:
-            nstats, nerr = drv.statistics, str(exc)
-        nctx.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t[0])
-        newton = {"newton_its_per_s": drv.newton_its / dt, "newton_its": drv.newton_its,
-                  "linear_its": drv.lin_its, "time_steps": len(nstats), "wall_s": dt,
-                  "crack_energy": nstats[-1]["crack"] if nstats else None,
-                  "bulk_energy": nstats[-1]["bulk"] if nstats else None,
-                  "preconditioner": "matrix-free geometric multigrid V-cycle (z-slab levels, replicated below), "
-                                    "Chebyshev-Jacobi smoothing"}
-        if nerr:
-            newton["error"] = nerr
-        nctx.close()
+        # interpolated initial condition.  Run twice: with the exact FP64 Jacobian (the library default) and
+        # as inexact Newton with the FP32 Jacobian (pf_set_jacobian_precision); residuals are FP64 in both.
+        def newton_run(jacobian_bits):
+            nctx = pf.PhaseFieldContext(mesh, params, device=local_rank, rank=rank, nranks=world, nccl_id=fresh_nccl_id())
+            if jacobian_bits != 64:
+                nctx.set_jacobian_precision(jacobian_bits)
+            drv = pf.SneddonDriver(nctx, pressure=lambda t: 1e-3, max_no_timesteps=1, newton_lower_bound=1e-7,
+                                   max_newton=50, max_line_search=10, gmres_max_it=200)
+            barrier()
+            t0 = time.perf_counter()
+            try:
+                # every decision in the loop is taken on all-reduced values, so a failure is raised on all ranks alike
+                nstats, nerr = drv.run(mesh_diameter(mesh)), None
+            except pf.PFError as exc:
+                nstats, nerr = drv.statistics, str(exc)
+            nctx.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t[0])
+            out = {"newton_its_per_s": drv.newton_its / dt, "newton_its": drv.newton_its,
+                   "linear_its": drv.lin_its, "time_steps": len(nstats), "wall_s": dt,
+                   "crack_energy": nstats[-1]["crack"] if nstats else None,
+                   "bulk_energy": nstats[-1]["bulk"] if nstats else None,
+                   "jacobian": "exact FP64 27-point apply" if jacobian_bits == 64 else "FP32 27-point apply on FP64 vectors (inexact Newton)",
+                   "preconditioner": "matrix-free geometric multigrid V-cycle in FP32 (z-slab levels, replicated below), "
+                                     "Chebyshev-Jacobi smoothing"}
+            if nerr:
+                out["error"] = nerr
+            nctx.close()
+            return out
+
+        newton = newton_run(64)
+        newton_inexact = newton_run(32)
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -501,6 +511,7 @@ def main():
             line["parity"] = parity
         if newton is not None:
             line["newton"] = newton
+            line["newton_inexact"] = newton_inexact
         if not args.no_cpu_baseline:
             cb = cpu_reference_sample(10, 2, refine=3, newton=not args.no_cpu_newton)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "newton_its_per_s",

@@ -73,6 +73,8 @@ def build_library(force: bool = False) -> str:
 _SIGS = {
     "pf_create": [C.POINTER(Mesh), C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)],
     "pf_create_forest": [C.c_void_p, C.POINTER(Params), C.c_int, C.POINTER(C.c_void_p)],   # see cracks_b200/forest.py
+    "pf_create_forest_distributed": [C.c_void_p, C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.POINTER(C.c_void_p)],
     "pf_destroy": [C.c_void_p],
     "pf_nccl_unique_id": [C.c_void_p],
     "pf_get_layout": [C.c_void_p, C.POINTER(Layout)],

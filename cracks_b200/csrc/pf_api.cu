@@ -164,13 +164,19 @@ struct pf_ctx
   // the V-cycle in FP32 (pf_mg_lowp.cuh; opt-in, pf_set_multigrid_precision): per level the state, the inverse
   // diagonal and the work vectors in float; set-up (diagonal, power iteration) stays FP64
   bool mg2d = false; // multigrid also on 2-D box / slit meshes (pf_set_preconditioner kind 3), single rank
-  int mg_fp32 = getenv ("PF_MG_FP32") ? atoi (getenv ("PF_MG_FP32")) : 0;
+  // default since round 2 (measured: profiles/r2_newton.json); PF_MG_FP32=0 or pf_set_multigrid_precision (ctx, 64) switch it off
+  int mg_fp32 = getenv ("PF_MG_FP32") ? atoi (getenv ("PF_MG_FP32")) : 1;
   float *f_sol = nullptr, *f_pt = nullptr, *f_idiag = nullptr;
   float *f_b = nullptr, *f_x = nullptr, *f_y = nullptr, *f_d = nullptr, *f_r = nullptr;
   double *mg_in = nullptr;  // fixed input buffer of the captured V-cycle
   double *mg_out = nullptr; // output buffer it was captured with
-  // forest (locally refined) mesh, see pf_create_forest -- EXPERIMENTAL, not yet run on a GPU
+  // forest (locally refined) mesh, see pf_create_forest.  On several ranks (pf_create_forest_distributed) every rank
+  // holds the whole mesh and every vector; the cell loops are split into the contiguous ranges [part_lo, part_hi) of
+  // the forest's space-filling-curve order (the p4est partition, cracks.cc:1083, 1180) and their nodal results are
+  // summed by one all-reduce.  nranks stays 1 for these contexts: no slab, no halo.
   bool forest = false;
+  int part_rank = 0, part_n = 1;
+  long long part_lo = 0, part_hi = 0;
   long long n_hanging = 0;
   long long *hang = nullptr;          // [n_hanging][5]: node, parents (-1 = unused)
   long long *conn_dev = nullptr;
@@ -881,32 +887,75 @@ mark_hanging (pf_ctx *ctx)
   return PF_OK;
 }
 
+// the cells of this rank as a Grid the cell kernels can run on unchanged: table pointers advanced to part_lo
+Grid
+forest_part (const pf_ctx *ctx, const double *lame = nullptr)
+{
+  Grid g = ctx->g;
+  if (lame)
+    g.cell_lame = lame;
+  if (ctx->forest && ctx->part_n > 1)
+    {
+      const long long nv = 1ll << ctx->dim;
+      g.conn += ctx->part_lo * nv;
+      g.cell_level += ctx->part_lo;
+      if (g.cell_lame)
+        g.cell_lame += 2 * ctx->part_lo;
+      g.n_local_cells = ctx->part_hi - ctx->part_lo;
+      g.n[0] = (int) g.n_local_cells;
+    }
+  return g;
+}
+
+// sum of the per-rank nodal (or scalar) contributions of a partitioned forest
+int
+forest_allreduce (pf_ctx *ctx, double *v, size_t n)
+{
+  if (!ctx->forest || ctx->part_n == 1)
+    return PF_OK;
+  NC_ (g_nccl.AllReduce (v, v, n, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+  return PF_OK;
+}
+
 // y = (H F)^T J (H F) x + D x on a forest mesh (F drops the constrained columns, D is the decoupled
 // diagonal of constrained and hanging rows): generic cell kernels between a distribute and a fold
 int
 apply_forest_dev (pf_ctx *ctx, const double *x, double *y)
 {
-  const Grid &g = ctx->g;
-  const long long nl = g.n_local_nodes;
+  const Grid g = forest_part (ctx);
+  const long long nl = ctx->g.n_local_nodes;
   int rc;
   CU (cudaMemcpyAsync (ctx->fx, x, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice, ctx->stream));
   if ((rc = hanging_distribute (ctx, ctx->fx, 1)))
     return rc;
+  // the decoupled diagonal of the constrained rows enters the sum over the ranks once
+  if (ctx->part_rank > 0)
+    CU (cudaMemsetAsync (y, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
   if (ctx->dim == 2)
     {
-      k_apply_init<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
-      KCHECK ();
-      k_apply_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-        g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->fx, ctx->sol, ctx->pt, ctx->mask, y);
+      if (ctx->part_rank == 0)
+        {
+          k_apply_init<2><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
+          KCHECK ();
+        }
+      if (g.n_local_cells > 0)
+        k_apply_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+          g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->fx, ctx->sol, ctx->pt, ctx->mask, y);
     }
   else
     {
-      k_apply_init<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
-      KCHECK ();
-      k_apply_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-        g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->fx, ctx->sol, ctx->pt, ctx->mask, y);
+      if (ctx->part_rank == 0)
+        {
+          k_apply_init<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
+          KCHECK ();
+        }
+      if (g.n_local_cells > 0)
+        k_apply_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+          g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->fx, ctx->sol, ctx->pt, ctx->mask, y);
     }
   KCHECK ();
+  if ((rc = forest_allreduce (ctx, y, (size_t) ctx->n_local_dofs)))
+    return rc;
   return hanging_fold (ctx, ctx->diag, x, y, true);
 }
 
@@ -1056,15 +1105,18 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
 int
 residual_dev (pf_ctx *ctx, double *l2)
 {
-  const Grid &g = ctx->g;
+  const Grid g = forest_part (ctx);
   const long long nl = g.n_local_nodes;
   g_trace.begin (ctx->stream);
   CU (cudaMemsetAsync (ctx->r_total, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
   if (ctx->dim == 2)
     {
-      k_residual_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-        g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
+      if (g.n_local_cells > 0)
+        k_residual_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+          g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
       KCHECK ();
+      if (int rcp = forest_allreduce (ctx, ctx->r_total, (size_t) ctx->n_local_dofs))
+        return rcp;
       if (int rcf = hanging_fold (ctx, nullptr, nullptr, ctx->r_total, false))
         return rcf;
       k_residual_finish<2><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi,
@@ -1074,8 +1126,11 @@ residual_dev (pf_ctx *ctx, double *l2)
   else
     {
       if (ctx->force_generic || ctx->forest)
-        k_residual_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-          g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
+        {
+          if (g.n_local_cells > 0)
+            k_residual_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+              g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
+        }
       else
         {
           using TR = TileR3<16, 4, 1>;
@@ -1090,6 +1145,8 @@ residual_dev (pf_ctx *ctx, double *l2)
             g, ctx->p, ctx->k3, tiles_x, tiles_y, ctx->sol, ctx->pt, ctx->r_total);
         }
       KCHECK ();
+      if (int rcp = forest_allreduce (ctx, ctx->r_total, (size_t) ctx->n_local_dofs))
+        return rcp;
       if (int rcf = hanging_fold (ctx, nullptr, nullptr, ctx->r_total, false))
         return rcf;
       k_residual_finish<3><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi,
@@ -1783,15 +1840,20 @@ precond_apply (pf_ctx *ctx, const double *v, double *z)
 int
 diag_and_aux (pf_ctx *ctx)
 {
-  const Grid &g = ctx->g;
+  const Grid g = forest_part (ctx);
   CU (cudaMemsetAsync (ctx->diag, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
-  if (ctx->dim == 2)
-    k_diag_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-      g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
-  else
-    k_diag_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-      g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
+  if (g.n_local_cells > 0)
+    {
+      if (ctx->dim == 2)
+        k_diag_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+          g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
+      else
+        k_diag_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+          g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
+    }
   KCHECK ();
+  if (int rcp = forest_allreduce (ctx, ctx->diag, (size_t) ctx->n_local_dofs))
+    return rcp;
   if (ctx->forest && ctx->n_hanging > 0)
     {
       if (ctx->dim == 2)
@@ -2339,6 +2401,41 @@ create_forest_impl (const pf_forest_mesh *fm, const pf_params *params, int devic
 } // namespace
 
 extern "C" {
+
+// Forest context on `nranks` GPUs.  The cells must be given identically on every rank (the host forest's
+// deterministic order, cracks_b200/host/forest.h): rank r evaluates the contiguous range
+// [r n / nranks, (r + 1) n / nranks) of them -- an equal-count cut like p4est's of its Morton curve (cracks.cc:1083, 1180) --
+// while nodal vectors are held completely by every rank and summed by one all-reduce per operator application,
+// residual, diagonal and functional.  Every rank therefore sees the whole solution and takes the same decisions.
+int
+pf_create_forest_distributed (const pf_forest_mesh *mesh, const pf_params *params, int device, int rank, int nranks,
+                              const void *nccl_id, pf_ctx **out)
+{
+  if (nranks < 1 || rank < 0 || rank >= nranks || !mesh)
+    return PF_BAD_ARG;
+  int rc = create_forest_impl (mesh, params, device, out);
+  if (rc || nranks == 1)
+    return rc;
+  pf_ctx *ctx = *out;
+  ctx->part_rank = rank;
+  ctx->part_n = nranks;
+  ctx->part_lo = mesh->n_cells * rank / nranks;
+  ctx->part_hi = mesh->n_cells * (rank + 1) / nranks;
+  if (!nccl_id)
+    return fail (ctx, PF_BAD_ARG, "nranks > 1 needs an ncclUniqueId");
+  if (!g_nccl.load (ctx->err))
+    return PF_NCCL_ERROR;
+  ncclUniqueId id;
+  memcpy (&id, nccl_id, sizeof id);
+  NC_ (g_nccl.CommInitRank (&ctx->comm, nranks, id, rank));
+  ctx->owns_comm = true;
+  // NCCL connects lazily: pay for the first all-reduce here, not inside the first solve
+  CU (cudaMemsetAsync (ctx->red, 0, sizeof (double), ctx->stream));
+  if ((rc = forest_allreduce (ctx, ctx->red, 1)))
+    return rc;
+  CU (cudaStreamSynchronize (ctx->stream));
+  return PF_OK;
+}
 
 int
 pf_create_forest (const pf_forest_mesh *mesh, const pf_params *params, int device, pf_ctx **out)
@@ -3057,19 +3154,23 @@ pf_energy (pf_ctx *ctx, double *bulk, double *crack)
   if (!ctx)
     return PF_BAD_ARG;
   CU (cudaSetDevice (ctx->device));
-  Grid g = ctx->g;
-  if (ctx->lame_energy_dev)
-    g.cell_lame = ctx->lame_energy_dev; // compute_energy's coefficients differ from the assembly's (cracks.cc:3651)
+  // compute_energy's coefficients differ from the assembly's (cracks.cc:3651)
+  const Grid g = forest_part (ctx, ctx->lame_energy_dev);
   CU (cudaMemsetAsync (ctx->red, 0, 4 * sizeof (double), ctx->stream));
-  if (ctx->dim == 2)
-    k_functionals_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-      g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->own_cell_begin, ctx->own_cell_end, ctx->red);
-  else
-    k_functionals_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-      g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->own_cell_begin, ctx->own_cell_end, ctx->red);
+  if (g.n_local_cells > 0)
+    {
+      if (ctx->dim == 2)
+        k_functionals_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+          g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->own_cell_begin, ctx->own_cell_end, ctx->red);
+      else
+        k_functionals_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+          g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->own_cell_begin, ctx->own_cell_end, ctx->red);
+    }
   KCHECK ();
   int rc = allreduce_sum (ctx, ctx->red, 3);
   if (rc)
+    return rc;
+  if ((rc = forest_allreduce (ctx, ctx->red, 3)))
     return rc;
   CU (cudaMemcpyAsync (ctx->h_red, ctx->red, 3 * sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
   CU (cudaStreamSynchronize (ctx->stream));

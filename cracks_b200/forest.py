@@ -4,9 +4,10 @@ The host forest is the product-side stand-in for the reference's p4est triangula
 make_hanging_node_constraints + SolutionTransfer (cracks.cc:3895-4163, 1630-1634); it is pure host
 code and is checked against the CPU oracle's forests in tests/test_host_forest.py.
 
-EXPERIMENTAL device side: `ForestContext` (pf_create_forest) and `ForestSneddonDriver` were written
-against the hanging-node oracle but have not been run on a GPU yet; their tests are opt-in
-(PF_EXPERIMENTAL=1).
+Device side: `ForestContext` (pf_create_forest / pf_create_forest_distributed) and the drivers below, held
+against the hanging-node oracle and the reference's adaptive goldens in tests/test_gpu_forest.py (one GPU)
+and tests/mgpu_forest_check.py (several ranks: replicated vectors, partitioned cells, one all-reduce per
+operator application).
 """
 from __future__ import annotations
 
@@ -136,10 +137,13 @@ class ForestMeshStruct(C.Structure):
 
 
 class ForestContext(api.PhaseFieldContext):
-    """pf_create_forest: the (u,phi) problem on a HostForest mesh (EXPERIMENTAL, see module docstring).
+    """pf_create_forest: the (u,phi) problem on a HostForest mesh.
     Vectors cross the ABI in the block layout [u | phi] over the forest's node numbering."""
 
-    def __init__(self, forest: HostForest, params: api.Params, device: int = 0, cell_lame=None, cell_lame_energy=None):
+    def __init__(self, forest: HostForest, params: api.Params, device: int = 0, cell_lame=None, cell_lame_energy=None,
+                 dist=None):
+        """dist = (rank, nranks, fresh_id) for several GPUs: fresh_id() returns an ncclUniqueId (128 bytes) that
+        rank 0 made and every rank received -- a new one per context, the adaptive drivers build many"""
         self.lib = api.load_library()
         self.forest, self.params = forest, params
         self.dim, self.nc = forest.dim, forest.dim + 1
@@ -155,7 +159,13 @@ class ForestContext(api.PhaseFieldContext):
             self._keep += [la, le]
             fm.cell_lame, fm.cell_lame_energy = la.ctypes.data, le.ctypes.data
         h = C.c_void_p()
-        rc = self.lib.pf_create_forest(C.cast(C.pointer(fm), C.c_void_p), C.byref(params), device, C.byref(h))
+        if dist is None or dist[1] == 1:
+            rc = self.lib.pf_create_forest(C.cast(C.pointer(fm), C.c_void_p), C.byref(params), device, C.byref(h))
+        else:
+            rank, nranks, fresh_id = dist
+            self._nccl_id = C.create_string_buffer(bytes(fresh_id()), 128)
+            rc = self.lib.pf_create_forest_distributed(C.cast(C.pointer(fm), C.c_void_p), C.byref(params), device, rank,
+                                                       nranks, self._nccl_id, C.byref(h))
         self.h = h
         self._check(rc)
         lay = api.Layout()
@@ -223,11 +233,12 @@ class ForestMieheDriver(api.SneddonDriver):
     (`ref strategy = phase field`, cracks.cc:4166-4581, 3971-3995, 4108-4159, 4419-4431) on a HostForest:
     after every converged step the cells holding a phase-field dof below the threshold are refined (level
     cap, 2:1 balance), solution / old / old_old are interpolated to the new forest, a new device context
-    is built and the step is redone.  EXPERIMENTAL like the rest of the forest device path."""
+    is built and the step is redone.  """
 
     def __init__(self, test, refine, params_of_h, E, timestep, max_no_timesteps, cycles=1, timestep_2=None,
-                 switch_timestep=0, d_rhs=0.0, d_mat=0.0, refine_threshold=0.8, device=0, krylov_dim=300, **kw):
+                 switch_timestep=0, d_rhs=0.0, d_mat=0.0, refine_threshold=0.8, device=0, krylov_dim=300, dist=None, **kw):
         self.kind = {"miehe tension": 1, "miehe shear": 2}[test]
+        self.dist = dist
         self.forest = HostForest(2, (2, 2), (0.0, 0.0), (1.0, 1.0), slit=True)
         self.forest.refine_global(refine)
         self.level_cap = refine + cycles
@@ -242,7 +253,7 @@ class ForestMieheDriver(api.SneddonDriver):
     def _new_context(self):
         """setup_system() on the current forest: tables -> device, Dirichlet rows of set_newton_bc (2584-2625)"""
         f = self.forest
-        ctx = ForestContext(f, self.params, device=self.device)
+        ctx = ForestContext(f, self.params, device=self.device, dist=self.dist)
         ctx.set_krylov_dim(self.krylov_dim)
         t = ctx.tables
         x, y = t["coords"][:, 0], t["coords"][:, 1]
@@ -350,11 +361,11 @@ class ForestHeteroDriver(api.SneddonDriver):
     [0,10]^3 of meshes/unit_cube_10.inp, global refinement, local pre-refinement with `ref strategy = phase field`
     on the interpolated initial cracks, Lame coefficients per cell from an E-modulus field (the reference's
     BitmapFunction; `e_modulus_of_cells(centres) -> E`), `E + 1` in the assembly but not in compute_energy
-    (2209-2210 vs 3651), pressure as a function of time.  EXPERIMENTAL like the rest of the forest device path."""
+    (2209-2210 vs 3651), pressure as a function of time.  """
 
     def __init__(self, e_modulus_of_cells, global_refine=3, local_pre_refine=1, nu=0.2, G_c=1.0, pressure=lambda t: 1e3 * t,
                  kappa_of_h=lambda h: 0.0, eps_of_h=lambda h: 1.5, E_active_set=1e4, refine_threshold=0.4, timestep=0.01,
-                 max_no_timesteps=1, device=0, krylov_dim=300, **kw):
+                 max_no_timesteps=1, device=0, krylov_dim=300, dist=None, **kw):
         f = HostForest(3, (1, 1, 1), (0.0,) * 3, (10.0,) * 3)
         f.refine_global(global_refine)
         cap = global_refine + local_pre_refine
@@ -375,7 +386,7 @@ class ForestHeteroDriver(api.SneddonDriver):
             return np.stack([(2 * nu * mu) / (1.0 - 2 * nu), mu], axis=1)
 
         params = api.Params(1.0, 1.0, G_c, kappa_of_h(h), eps_of_h(h), 0.0)     # lambda, mu come per cell
-        ctx = ForestContext(f, params, device=device, cell_lame=lame(E + 1.0), cell_lame_energy=lame(E))
+        ctx = ForestContext(f, params, device=device, cell_lame=lame(E + 1.0), cell_lame_energy=lame(E), dist=dist)
         ctx.set_krylov_dim(krylov_dim)
         xyz = t["coords"]
         on_b = ((xyz == 0.0) | (xyz == 10.0)).any(axis=1)

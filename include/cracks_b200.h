@@ -120,6 +120,15 @@ typedef struct
   const double *cell_lame_energy; /* NULL (= cell_lame), or the values compute_energy uses (3646-3656) */
 } pf_forest_mesh;
 int pf_create_forest (const pf_forest_mesh *mesh, const pf_params *params, int device, pf_ctx **out);
+/* The same on `nranks` GPUs (one process per GPU, nccl_id from pf_nccl_unique_id of rank 0).  Stands in for the
+ * p4est partition of the reference (parallel::distributed::Triangulation, cracks.cc:1083, 1180): the cells, given
+ * identically on every rank (the host forest orders them by lower corner), are cut into `nranks` contiguous
+ * equal-count ranges the way p4est cuts its Morton curve; rank r evaluates range r, results do not depend on the cut.  Nodal vectors are replicated on every rank and the per-rank cell
+ * sums meet in ONE all-reduce per operator application / residual / diagonal / functional (the reference:
+ * ghost import + compress(add), cracks.cc:2147-2154, 2470-2475).  Every [collective] call must be entered by all
+ * ranks; host vectors are the complete vectors on every rank. */
+int pf_create_forest_distributed (const pf_forest_mesh *mesh, const pf_params *params, int device, int rank,
+                                  int nranks, const void *nccl_id, pf_ctx **out);
 
 /* One level of the geometric multigrid hierarchy that replaces the reference's ML AMG set-up
  * (cracks.cc:2477-2497) as `rank` of `nranks` sees it. */

@@ -18,3 +18,15 @@ def test_two_gpu_parity(pf):
                         os.path.join(ROOT, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=900)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0 and "MGPU_OK" in r.stdout
+
+
+def test_two_gpu_forest(pf):
+    """the forest path on 2 GPUs: hetero_3d_1 (config 5 in small) and adaptive miehe_shear_1 (config 4 in small)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543",
+                        os.path.join(ROOT, "tests", "mgpu_forest_check.py")], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0 and "MGPU_FOREST_OK" in r.stdout

@@ -113,3 +113,45 @@ def test_eight_ranks_distributed_and_replicated_levels(built, one_rank_32, tmp_p
         assert a["crack"] == pytest.approx(b["crack"], rel=1e-10)
         assert a["bulk"] == pytest.approx(b["bulk"], rel=1e-7)
     assert eight["newton_its"] == one["newton_its"]
+
+
+def _run_forest(nranks, case, tmp_path, timeout, *args):
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(EMU, "fake_nccl") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    id_prefix, out_file = str(tmp_path / ("fid_%s_%d" % (case, nranks))), str(tmp_path / ("fout_%s_%d.json" % (case, nranks)))
+    procs = [subprocess.Popen([sys.executable, os.path.join(EMU, "multirank_forest_worker.py"), str(r), str(nranks), id_prefix,
+                               out_file, case, *map(str, args)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(nranks)]
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=timeout)[0])
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    assert all(p.returncode == 0 for p in procs), "\n".join(o[-1500:] for o in outs)
+    return json.load(open(out_file))
+
+
+def test_hetero_3d_golden_on_two_and_three_forest_ranks(built, tmp_path):
+    """pf_create_forest_distributed (replicated vectors, cells cut into contiguous ranges, one all-reduce per operator
+    application / residual / diagonal / functional) on KAT-5, tests/hetero_3d_1.mpirun-4.statistics: 932 cells with
+    318 hanging nodes and per-cell Lame coefficients.  3 ranks: ranges of unequal length."""
+    g = json.load(open(os.path.join(HERE, "golden", "hetero_3d_1.json")))
+    for nranks in (2, 3):
+        out = _run_forest(nranks, "hetero", tmp_path, 1500)
+        for got, ref in zip(out["statistics"], g["statistics"]):
+            assert got["dofs"] == 5288
+            assert got["crack"] == pytest.approx(ref["crack"], rel=1e-7)
+            assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-6)
+
+
+def test_adaptive_miehe_shear_on_two_forest_ranks(built, tmp_path):
+    """BASELINE config 4 in small on 2 ranks: stress split + predictor-corrector refinement (a new distributed
+    context, i.e. a new communicator, after every mesh change); the first rows of tests/miehe_shear_1.statistics"""
+    g = json.load(open(os.path.join(HERE, "golden", "miehe_shear_1.json")))
+    out = _run_forest(2, "shear", tmp_path, 2400, 6)
+    assert [r["dofs"] for r in out["statistics"]] == [r["dofs"] for r in g["statistics"][:7]]
+    for got, ref in zip(out["statistics"], g["statistics"]):
+        for k in ("bulk", "crack", "load"):
+            assert got[k] == pytest.approx(ref[k], rel=1e-6), (got["step"], k)
