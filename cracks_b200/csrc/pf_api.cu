@@ -954,9 +954,12 @@ apply_forest_dev (pf_ctx *ctx, const double *x, double *y)
           g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->fx, ctx->sol, ctx->pt, ctx->mask, y);
     }
   KCHECK ();
-  if ((rc = forest_allreduce (ctx, y, (size_t) ctx->n_local_dofs)))
+  // the fold is linear in y: it is applied to the rank's partial sums BEFORE they meet, so that what every rank holds
+  // afterwards is the all-reduce's own (bitwise identical) result -- the fold adds with atomics, and replicated
+  // Krylov vectors that differ in the last bit drift apart over a long Arnoldi process
+  if ((rc = hanging_fold (ctx, ctx->part_rank == 0 ? ctx->diag : nullptr, x, y, true)))
     return rc;
-  return hanging_fold (ctx, ctx->diag, x, y, true);
+  return forest_allreduce (ctx, y, (size_t) ctx->n_local_dofs);
 }
 
 // approx = true: the under-integrated (2-point Gauss) operator used only inside the
@@ -1115,10 +1118,10 @@ residual_dev (pf_ctx *ctx, double *l2)
         k_residual_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
           g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->r_total);
       KCHECK ();
-      if (int rcp = forest_allreduce (ctx, ctx->r_total, (size_t) ctx->n_local_dofs))
-        return rcp;
       if (int rcf = hanging_fold (ctx, nullptr, nullptr, ctx->r_total, false))
         return rcf;
+      if (int rcp = forest_allreduce (ctx, ctx->r_total, (size_t) ctx->n_local_dofs))
+        return rcp;
       k_residual_finish<2><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi,
                                                                         ctx->r_total, ctx->mask, ctx->r_pde,
                                                                         ctx->partial);
@@ -1145,10 +1148,10 @@ residual_dev (pf_ctx *ctx, double *l2)
             g, ctx->p, ctx->k3, tiles_x, tiles_y, ctx->sol, ctx->pt, ctx->r_total);
         }
       KCHECK ();
-      if (int rcp = forest_allreduce (ctx, ctx->r_total, (size_t) ctx->n_local_dofs))
-        return rcp;
       if (int rcf = hanging_fold (ctx, nullptr, nullptr, ctx->r_total, false))
         return rcf;
+      if (int rcp = forest_allreduce (ctx, ctx->r_total, (size_t) ctx->n_local_dofs))
+        return rcp;
       k_residual_finish<3><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nl, ctx->owned_lo, ctx->owned_hi,
                                                                         ctx->r_total, ctx->mask, ctx->r_pde,
                                                                         ctx->partial);
@@ -1852,8 +1855,6 @@ diag_and_aux (pf_ctx *ctx)
           g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
     }
   KCHECK ();
-  if (int rcp = forest_allreduce (ctx, ctx->diag, (size_t) ctx->n_local_dofs))
-    return rcp;
   if (ctx->forest && ctx->n_hanging > 0)
     {
       if (ctx->dim == 2)
@@ -1862,6 +1863,9 @@ diag_and_aux (pf_ctx *ctx)
         k_hanging_fold_diag<4><<<nblk (ctx->n_hanging * 4, 256), 256, 0, ctx->stream>>> (ctx->n_hanging, ctx->hang, ctx->diag);
       KCHECK ();
     }
+  // (linear) fold of the rank's partial sums first, then the all-reduce: every rank holds the same bits
+  if (int rcp = forest_allreduce (ctx, ctx->diag, (size_t) ctx->n_local_dofs))
+    return rcp;
   // complete the diagonal on the ghost planes (their cells are only partly local)
   int rc = halo_exchange (ctx, ctx->diag, ctx->nc);
   if (rc)
@@ -2432,6 +2436,12 @@ pf_create_forest_distributed (const pf_forest_mesh *mesh, const pf_params *param
   // NCCL connects lazily: pay for the first all-reduce here, not inside the first solve
   CU (cudaMemsetAsync (ctx->red, 0, sizeof (double), ctx->stream));
   if ((rc = forest_allreduce (ctx, ctx->red, 1)))
+    return rc;
+  // the lumped mass was summed with atomics: rank 0's copy becomes everybody's, bit for bit (it enters the
+  // active-set criterion, whose decisions must be the same on every rank)
+  if (rank > 0)
+    CU (cudaMemsetAsync (ctx->mass, 0, sizeof (double) * (size_t) ctx->g.n_local_nodes, ctx->stream));
+  if ((rc = forest_allreduce (ctx, ctx->mass, (size_t) ctx->g.n_local_nodes)))
     return rc;
   CU (cudaStreamSynchronize (ctx->stream));
   return PF_OK;
