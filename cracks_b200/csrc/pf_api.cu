@@ -1892,18 +1892,21 @@ diag_and_aux (pf_ctx *ctx)
 // Host-buffer apply (block layout in, block layout out) as a three-stage
 // pipeline over chunks of cell layers: PCIe upload of chunk c+1, permute +
 // operator on chunk c and PCIe download of the finished planes of chunk c-1
-// run concurrently on three streams.  Single rank, dim 3.
+// run concurrently on three streams.  dim 3, any number of ranks: a rank reads the node planes of its slab
+// (ghost planes included) straight from the host vector -- on several ranks the caller passes the complete
+// vector, like the ghosted vectors of the reference (cracks.cc:2147-2154), so no NCCL exchange is needed --
+// and writes back the planes it owns.
 int
 apply_host_pipelined (pf_ctx *ctx, const double *xh, double *yh)
 {
   if (!ctx->jac_ready)
     return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must be called before applying the Jacobian");
   const Grid &g = ctx->g;
-  const long long npp = g.nodes_per_plane, nn = g.n_global_nodes;
-  const int layers = g.n[2];
+  const long long npp = g.nodes_per_plane, nn = g.n_global_nodes, nl = g.n_local_nodes;
+  const int layers = g.cell_end - g.cell_begin;
   // chunks of >= 2 cell layers; the first upload and the last download are not overlapped, so their share
-  // (1 / n_chunks each) is what the pipeline cannot hide.  Measured with 8 (3.75 ms at 16.7 M DoF, PCIe-bound);
-  // 16 is the default since (PF_E2E_CHUNKS for the A/B)
+  // (1 / n_chunks each) is what the pipeline cannot hide.  Measured with 8, 16 and 32 chunks at 16.7 M DoF on one
+  // GPU: 3.86 ms each, the PCIe transfers bound it (profiles/README.md); PF_E2E_CHUNKS for the A/B
   static const int max_chunks = std::max (1, std::min (32, getenv ("PF_E2E_CHUNKS") ? atoi (getenv ("PF_E2E_CHUNKS")) : 16));
   const int n_chunks = std::max (1, std::min (max_chunks, layers / 2));
   if (!ctx->h2d_stream)
@@ -1917,8 +1920,8 @@ apply_host_pipelined (pf_ctx *ctx, const double *xh, double *yh)
         }
       CU (cudaMalloc (&ctx->stage2, sizeof (double) * ctx->n_local_dofs));
     }
-  double *ub = ctx->stage, *pb = ctx->stage + nn * 3;     // upload staging, block layout
-  double *ub2 = ctx->stage2, *pb2 = ctx->stage2 + nn * 3; // download staging
+  double *ub = ctx->stage, *pb = ctx->stage + nl * 3;     // upload staging, block layout, local planes
+  double *ub2 = ctx->stage2, *pb2 = ctx->stage2 + nl * 3; // download staging
   double *x = ctx->xa, *y = ctx->ya;
   // the upload stream must not overwrite staging still in use by earlier work on the compute stream
   CU (cudaEventRecord (ctx->ev_x, ctx->stream));
@@ -1927,18 +1930,20 @@ apply_host_pipelined (pf_ctx *ctx, const double *xh, double *yh)
   int rc = PF_OK;
   for (int c = 0; c < n_chunks; ++c)
     {
-      const int c0 = (int) ((long long) layers * c / n_chunks), c1 = (int) ((long long) layers * (c + 1) / n_chunks);
-      // node planes first needed by this chunk: (c0, c1], plus plane 0 for the first chunk
-      const long long pa = c == 0 ? 0 : c0 + 1, pe = c1 + 1;
-      const long long na = pa * npp, cnt = (pe - pa) * npp;
-      CU (cudaMemcpyAsync (ub + na * 3, xh + na * 3, sizeof (double) * cnt * 3, cudaMemcpyHostToDevice, ctx->h2d_stream));
-      CU (cudaMemcpyAsync (pb + na, xh + nn * 3 + na, sizeof (double) * cnt, cudaMemcpyHostToDevice, ctx->h2d_stream));
+      // global cell layers [c0, c1) of this chunk
+      const int c0 = g.cell_begin + (int) ((long long) layers * c / n_chunks);
+      const int c1 = g.cell_begin + (int) ((long long) layers * (c + 1) / n_chunks);
+      // node planes first needed by this chunk: (c0, c1], plus the slab's first plane for the first chunk
+      const long long pa = c == 0 ? c0 : c0 + 1, pe = c1 + 1;
+      const long long ga = pa * npp, la = (pa - g.plane_begin) * npp, cnt = (pe - pa) * npp; // global / local node offsets
+      CU (cudaMemcpyAsync (ub + la * 3, xh + ga * 3, sizeof (double) * cnt * 3, cudaMemcpyHostToDevice, ctx->h2d_stream));
+      CU (cudaMemcpyAsync (pb + la, xh + nn * 3 + ga, sizeof (double) * cnt, cudaMemcpyHostToDevice, ctx->h2d_stream));
       CU (cudaEventRecord (ctx->ev_up[c], ctx->h2d_stream));
       CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_up[c], 0));
-      k_block_to_nodal<3><<<nblk (cnt, 256), 256, 0, ctx->stream>>> (cnt, ub + na * 3, pb + na, x + na * 4);
+      k_block_to_nodal<3><<<nblk (cnt, 256), 256, 0, ctx->stream>>> (cnt, ub + la * 3, pb + la, x + la * 4);
       KCHECK ();
-      k_apply_init<3><<<nblk (cnt, 256), 256, 0, ctx->stream>>> (cnt, x + na * 4, ctx->diag + na * 4, ctx->mask + na,
-                                                                 y + na * 4);
+      k_apply_init<3><<<nblk (cnt, 256), 256, 0, ctx->stream>>> (cnt, x + la * 4, ctx->diag + la * 4, ctx->mask + la,
+                                                                 y + la * 4);
       KCHECK ();
       ctx->range_begin = c0;
       ctx->range_end = c1;
@@ -1946,15 +1951,20 @@ apply_host_pipelined (pf_ctx *ctx, const double *xh, double *yh)
       ctx->range_begin = ctx->range_end = -1;
       if (rc)
         return rc;
-      // planes [c0, c1) are complete now (plane c1 still misses the next chunk), the last chunk completes c1 too
-      const long long qa = c0, qe = c == n_chunks - 1 ? c1 + 1 : c1;
-      const long long ma = qa * npp, mcnt = (qe - qa) * npp;
-      k_nodal_to_block<3><<<nblk (mcnt, 256), 256, 0, ctx->stream>>> (mcnt, y + ma * 4, ub2 + ma * 3, pb2 + ma);
-      KCHECK ();
-      CU (cudaEventRecord (ctx->ev_done[c], ctx->stream));
-      CU (cudaStreamWaitEvent (ctx->d2h_stream, ctx->ev_done[c], 0));
-      CU (cudaMemcpyAsync (yh + ma * 3, ub2 + ma * 3, sizeof (double) * mcnt * 3, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-      CU (cudaMemcpyAsync (yh + nn * 3 + ma, pb2 + ma, sizeof (double) * mcnt, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+      // planes [c0, c1) have received every local layer now (plane c1 still misses the next chunk; the last chunk
+      // completes it too); of those this rank returns the ones it owns
+      const long long qa = std::max<long long> (c0, g.owned_begin);
+      const long long qe = std::min<long long> (c == n_chunks - 1 ? c1 + 1 : c1, g.owned_end);
+      if (qe > qa)
+        {
+          const long long gq = qa * npp, lq = (qa - g.plane_begin) * npp, mcnt = (qe - qa) * npp;
+          k_nodal_to_block<3><<<nblk (mcnt, 256), 256, 0, ctx->stream>>> (mcnt, y + lq * 4, ub2 + lq * 3, pb2 + lq);
+          KCHECK ();
+          CU (cudaEventRecord (ctx->ev_done[c], ctx->stream));
+          CU (cudaStreamWaitEvent (ctx->d2h_stream, ctx->ev_done[c], 0));
+          CU (cudaMemcpyAsync (yh + gq * 3, ub2 + lq * 3, sizeof (double) * mcnt * 3, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+          CU (cudaMemcpyAsync (yh + nn * 3 + gq, pb2 + lq, sizeof (double) * mcnt, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
     }
   CU (cudaStreamSynchronize (ctx->d2h_stream));
   CU (cudaStreamSynchronize (ctx->stream));
@@ -2805,8 +2815,8 @@ pf_apply_jacobian (pf_ctx *ctx, const double *x, double *y)
     return PF_BAD_ARG;
   CU (cudaSetDevice (ctx->device));
   int rc;
-  if (ctx->dim == 3 && ctx->nranks == 1 && !ctx->force_generic && !ctx->forest
-      && (ctx->apply_variant == 3 || ctx->apply_variant == 16) && ctx->g.n[2] >= 16)
+  if (ctx->dim == 3 && !ctx->force_generic && !ctx->forest && (ctx->apply_variant == 3 || ctx->apply_variant == 16)
+      && ctx->g.cell_end - ctx->g.cell_begin >= 16)
     return apply_host_pipelined (ctx, x, y);
   if ((rc = upload_block (ctx, x, ctx->xa)))
     return rc;

@@ -13,10 +13,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
-def small_mesh_parity(pf, orc, rank, world, local, nccl_id, allsum):
+def small_mesh_parity(pf, orc, rank, world, local, nccl_id, allsum, nz=None):
     """apply / residual / diagonal / functionals of the slab-decomposed CUDA path on `world` ranks against the
     single-domain CPU oracle on a small anisotropic mesh (12 x 9 x max(10, 3*world) cells); relative errors, rank 0."""
-    nz = max(10, 3 * world)
+    nz = nz or max(10, 3 * world)        # >= 16 layers per rank: pf_apply_jacobian takes its chunk-pipelined path
     n, h = (12, 9, nz), (0.5, 0.4, 0.3)
     lo = tuple(-0.5 * n[d] * h[d] for d in range(3))
     hi = tuple(0.5 * n[d] * h[d] for d in range(3))
@@ -90,6 +90,11 @@ def main():
     errs = small_mesh_parity(pf, orc, rank, world, local, nccl_id, allsum)
     if rank == 0:
         print("errors vs single-domain oracle:", errs, flush=True)
+        assert all(v <= 1e-11 for v in errs.values()), errs
+    # slabs of 18 cell layers: the host-buffer apply runs as the H2D / apply / D2H pipeline on every rank
+    errs = small_mesh_parity(pf, orc, rank, world, local, _fresh_id(pf, dist, torch, rank), allsum, nz=18 * world)
+    if rank == 0:
+        print("errors vs single-domain oracle, pipelined host apply:", errs, flush=True)
         assert all(v <= 1e-11 for v in errs.values()), errs
 
     # KAT-1 end to end on `world` GPUs

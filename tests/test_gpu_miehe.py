@@ -158,8 +158,11 @@ def test_2d_multigrid_gives_the_jacobi_path_results_at_64x64(pf, name):
         results.append(drv.run())
         lin.append(drv.lin_its)
         ctx.close()
+    dev = max(abs(b[k] - a[k]) / max(abs(a[k]), 1e-300) for a, b in zip(*results) for k in ("bulk", "crack", "load") if abs(a[k]) > 1e-12)
+    print("largest relative deviation between the Jacobi and the multigrid path:", dev, "GMRES iterations:", lin)
     for a, b in zip(*results):
         for k in ("bulk", "crack", "load"):
-            # both solves stop at |r| <= 1e-8 |b| (cracks.cc:2762): the energies agree to the solver tolerance
-            assert b[k] == pytest.approx(a[k], rel=1e-6, abs=1e-16), (a, b)
+            # both linear solves stop at |r| <= 1e-8 |b| (cracks.cc:2762) in different preconditioned norms and the Newton
+            # loop at |r| < 1e-6: the converged steps agree to the stopping tolerances, not to round-off
+            assert b[k] == pytest.approx(a[k], rel=1e-5, abs=1e-14), (a, b)
     assert lin[1] * 5 < lin[0], lin        # 9-12 iterations per solve instead of hundreds
