@@ -94,6 +94,7 @@ _SIGS = {
     "pf_set_preconditioner": [C.c_void_p, C.c_int, C.c_int, C.c_double],
     "pf_set_multigrid_precision": [C.c_void_p, C.c_int],
     "pf_set_jacobian_precision": [C.c_void_p, C.c_int],
+    "pf_set_deterministic": [C.c_void_p, C.c_int],
     "pf_apply_preconditioner": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_set_krylov_dim": [C.c_void_p, C.c_int],
     "pf_apply_jacobian": [C.c_void_p, C.c_void_p, C.c_void_p],
@@ -363,6 +364,10 @@ class PhaseFieldContext:
     def set_preconditioner(self, kind=1, cheb_degree=2, cheb_ratio=20.0):
         """0 = Jacobi, 1 = geometric multigrid (stand-in for the reference's ML AMG)"""
         self._check(self.lib.pf_set_preconditioner(self.h, kind, cheb_degree, cheb_ratio))
+
+    def set_deterministic(self, on=True):
+        """scatter kernels colour by colour: bit-identical results run to run (3-D box meshes)"""
+        self._check(self.lib.pf_set_deterministic(self.h, int(on)))
 
     def set_jacobian_precision(self, bits=64):
         """64 (default) or 32: inexact Newton with the Jacobian apply in FP32 (residuals and GMRES vectors stay FP64)"""

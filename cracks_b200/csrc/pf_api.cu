@@ -198,6 +198,7 @@ struct pf_ctx
   bool no_overlap = false;     // PF_NO_OVERLAP: halo exchange not overlapped with the interior layers (A/B)
   bool split_boundary = false; // PF_SPLIT_BOUNDARY: two boundary launches of a middle slab instead of one (A/B)
   bool mg_use_graph = false;   // PF_MG_GRAPH=1
+  bool deterministic = false;  // pf_set_deterministic: scatter kernels launched colour by colour (Grid::colour)
   std::set<const void *> attr_done; // kernels whose per-device function attributes this context has set
   double last_rnorm = 0;
   long long launches = 0;
@@ -579,14 +580,20 @@ launch_apply3d_v4 (pf_ctx *ctx, const double *x, double *y)
         }
     }
   const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
-  const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
-  if (iso)
-    k_apply3d_v4<TX, TY, TZ, MINB, NQ, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
-      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
-  else
-    k_apply3d_v4<TX, TY, TZ, MINB, NQ, false><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
-      g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
-  KCHECK ();
+  for (int colour = ctx->deterministic ? 0 : -1; colour < (ctx->deterministic ? 8 : 0); ++colour)
+    {
+      g.colour = colour;
+      const unsigned grid = (unsigned) tiles_of_colour (colour, tiles_x, tiles_y, tiles_z);
+      if (grid == 0)
+        continue;
+      if (iso)
+        k_apply3d_v4<TX, TY, TZ, MINB, NQ, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+          g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+      else
+        k_apply3d_v4<TX, TY, TZ, MINB, NQ, false><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+          g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
+      KCHECK ();
+    }
   return PF_OK;
 }
 
@@ -749,9 +756,17 @@ launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename L
       CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
       CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
-  k_apply3d_v6<R, V, NQ, TX, TY, MINB><<<(unsigned) tiles_x * tiles_y * tiles_z, T::NT, smem, ctx->stream>>> (
-    g, make_k6 (ctx), tiles_x, tiles_y, layer0, x, sol, ctx->mask, coef, y);
-  KCHECK ();
+  const K6 k6 = make_k6 (ctx);
+  for (int colour = ctx->deterministic ? 0 : -1; colour < (ctx->deterministic ? 8 : 0); ++colour)
+    {
+      g.colour = colour;
+      const unsigned grid = (unsigned) tiles_of_colour (colour, tiles_x, tiles_y, tiles_z);
+      if (grid == 0)
+        continue;
+      k_apply3d_v6<R, V, NQ, TX, TY, MINB><<<grid, T::NT, smem, ctx->stream>>> (g, k6, tiles_x, tiles_y, layer0, x, sol,
+                                                                                ctx->mask, coef, y);
+      KCHECK ();
+    }
   return PF_OK;
 }
 
@@ -1144,8 +1159,17 @@ residual_dev (pf_ctx *ctx, double *l2)
               CU (cudaFuncSetAttribute (k_residual3d<16, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int) TR::smem_bytes));
             }
-          k_residual3d<16, 4, 1, 2><<<(unsigned) tiles_x * tiles_y * tiles_z, TR::NT, TR::smem_bytes, ctx->stream>>> (
-            g, ctx->p, ctx->k3, tiles_x, tiles_y, ctx->sol, ctx->pt, ctx->r_total);
+          Grid gc = g;
+          for (int colour = ctx->deterministic ? 0 : -1; colour < (ctx->deterministic ? 8 : 0); ++colour)
+            {
+              gc.colour = colour;
+              const unsigned grid = (unsigned) tiles_of_colour (colour, tiles_x, tiles_y, tiles_z);
+              if (grid == 0)
+                continue;
+              k_residual3d<16, 4, 1, 2><<<grid, TR::NT, TR::smem_bytes, ctx->stream>>> (gc, ctx->p, ctx->k3, tiles_x, tiles_y,
+                                                                                      ctx->sol, ctx->pt, ctx->r_total);
+              KCHECK ();
+            }
         }
       KCHECK ();
       if (int rcf = hanging_fold (ctx, nullptr, nullptr, ctx->r_total, false))
@@ -1365,6 +1389,7 @@ mg_setup_level (pf_ctx *ctx)
   c->coarsest_degree = ctx->coarsest_degree;
   c->mg_fp32 = ctx->mg_fp32;
   c->apply_variant = ctx->apply_variant;
+  c->deterministic = ctx->deterministic;
   c->no_iso = ctx->no_iso;
   c->force_generic = ctx->force_generic;
   Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}, c->g.plane_begin},
@@ -1851,8 +1876,17 @@ diag_and_aux (pf_ctx *ctx)
         k_diag_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
           g, ctx->p, (const FeTab<2> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
       else
-        k_diag_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
-          g, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
+        {
+          Grid gc = g;
+          for (int colour = (ctx->deterministic && !ctx->forest) ? 0 : -1; colour < ((ctx->deterministic && !ctx->forest) ? 8 : 0);
+               ++colour)
+            {
+              gc.colour = colour;
+              k_diag_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
+                gc, ctx->p, (const FeTab<3> *) ctx->fetab, ctx->sol, ctx->pt, ctx->diag);
+              KCHECK ();
+            }
+        }
     }
   KCHECK ();
   if (ctx->forest && ctx->n_hanging > 0)
@@ -2774,6 +2808,20 @@ pf_set_jacobian_precision (pf_ctx *ctx, int bits)
     return fail (ctx, PF_UNSUPPORTED, "the FP32 Jacobian needs a 3-D box mesh with cubic cells");
   ctx->jacobian_bits = bits;
   ctx->jac_ready = false; // the coefficient records are made by pf_setup_jacobian
+  return PF_OK;
+}
+
+// Deterministic scatter: the tiled 3-D kernels (operator, smoother operator, residual) and the diagonal are launched
+// colour by colour (8 launches whose tiles / cells share no node), so every nodal sum is formed in the same order in
+// every run and the whole Newton history is reproducible bit for bit on a given number of ranks.  Off by default
+// (one launch, atomics in scheduler order: last-bit differences between runs).  3-D box meshes.
+int
+pf_set_deterministic (pf_ctx *ctx, int on)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  for (pf_ctx *c = ctx; c; c = c->coarse)
+    c->deterministic = on != 0;
   return PF_OK;
 }
 

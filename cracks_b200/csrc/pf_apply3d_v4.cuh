@@ -312,11 +312,8 @@ apply3d_v4_body (const Grid &g, const Phys &p, const K3 &k, int tiles_x, int til
   double *ys = DZ;                                    // [4][NN], aliases DZ
 
   const int tid = threadIdx.x;
-  int b = blockIdx.x;
-  const int bx = b % tiles_x;
-  b /= tiles_x;
-  const int by = b % tiles_y;
-  const int bz = b / tiles_y;
+  int bx, by, bz;
+  decode_tile (g, (int) blockIdx.x, tiles_x, tiles_y, bx, by, bz);
   const int cx0 = bx * TX, cy0 = by * TY, cz0 = g.cell_begin + bz * TZ * g.layer_stride;
   const int nnx = g.nn[0], nny = g.nn[1];
   const int lz_off = g.plane_begin;

@@ -569,11 +569,8 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
   unsigned long long *mbar = reinterpret_cast<unsigned long long *> (smem_raw + off_mbar); // one per Gauss plane
 
   const int tid = threadIdx.x;
-  int b = blockIdx.x;
-  const int bx = b % tiles_x;
-  b /= tiles_x;
-  const int by = b % tiles_y;
-  const int bz = b / tiles_y;
+  int bx, by, bz;
+  decode_tile (g, (int) blockIdx.x, tiles_x, tiles_y, bx, by, bz);
   const int cx0 = bx * TX, cy0 = by * TY, cz0 = g.cell_begin + bz * g.layer_stride;
   const S *coef_tile = coef + ((size_t) ((cz0 - layer0) * tiles_y + by) * tiles_x + bx) * T::coef_per_tile;
   // the records of the first two Gauss planes start to arrive while x and U are staged

@@ -40,7 +40,42 @@ struct Grid
   const long long *conn;           // [n_local_cells][2^dim] node numbers
   const unsigned char *cell_level; // [n_local_cells] index into the FeTab array
   const double *cell_lame;         // [n_local_cells][2] = (lambda, mu) or null
+  // deterministic mode (pf_set_deterministic): a launch covers only the tiles (or cells) whose index parities in
+  // x, y, z are the three bits of `colour`.  Tiles of one colour share no node, the eight colours are launched one
+  // after the other: the scatter adds of a launch never meet and every node sees its contributions in the same
+  // order in every run.  -1: all tiles in one launch (order of the adds left to the scheduler).
+  int colour = -1;
 };
+
+// linear block index -> tile index of the tiled 3-D kernels (all tiles, or the tiles of Grid::colour)
+__host__ __device__ inline void
+decode_tile (const Grid &g, int b, int tiles_x, int tiles_y, int &bx, int &by, int &bz)
+{
+  if (g.colour < 0)
+    {
+      bx = b % tiles_x;
+      b /= tiles_x;
+      by = b % tiles_y;
+      bz = b / tiles_y;
+      return;
+    }
+  const int px = g.colour & 1, py = (g.colour >> 1) & 1, pz = g.colour >> 2;
+  const int hx = (tiles_x + 1 - px) >> 1, hy = (tiles_y + 1 - py) >> 1;
+  bx = 2 * (b % hx) + px;
+  b /= hx;
+  by = 2 * (b % hy) + py;
+  bz = 2 * (b / hy) + pz;
+}
+
+// number of tiles a launch with this colour covers
+inline long long
+tiles_of_colour (int colour, int tiles_x, int tiles_y, int tiles_z)
+{
+  if (colour < 0)
+    return (long long) tiles_x * tiles_y * tiles_z;
+  const int px = colour & 1, py = (colour >> 1) & 1, pz = colour >> 2;
+  return (long long) ((tiles_x + 1 - px) >> 1) * ((tiles_y + 1 - py) >> 1) * ((tiles_z + 1 - pz) >> 1);
+}
 
 // quantities that change per Newton step / time step
 struct Phys

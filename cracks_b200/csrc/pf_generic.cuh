@@ -10,6 +10,24 @@
 
 namespace pf {
 
+// deterministic mode on box meshes: is the cell one of Grid::colour (index parities in x, y, z)?
+template <int DIM>
+__device__ __forceinline__ bool
+cell_has_colour (const Grid &g, long long lc)
+{
+  if (g.colour < 0 || g.conn)
+    return true;
+  int par = 0;
+  long long rem = lc;
+  for (int d = 0; d < DIM - 1; ++d)
+    {
+      par |= (int) ((rem % g.n[d]) & 1) << d;
+      rem /= g.n[d];
+    }
+  par |= (int) ((rem + g.cell_begin) & 1) << (DIM - 1);
+  return par == (DIM == 3 ? g.colour : (g.colour & 3));
+}
+
 template <int DIM>
 __device__ __forceinline__ void
 cell_nodes (const Grid &g, long long lc, long long *node)
@@ -302,7 +320,7 @@ k_diag_generic (Grid g, Phys p_in, const FeTab<DIM> *__restrict__ tab,
 {
   constexpr int NC = DIM + 1, NV = 1 << DIM, NQ = FeTab<DIM>::NQ;
   const long long lc = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-  if (lc >= g.n_local_cells)
+  if (lc >= g.n_local_cells || !cell_has_colour<DIM> (g, lc))
     return;
   const FeTab<DIM> &t = cell_table<DIM> (g, tab, lc);
   const Phys p = cell_phys (g, p_in, lc);

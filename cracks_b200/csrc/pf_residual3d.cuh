@@ -40,11 +40,8 @@ k_residual3d (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, const double *__re
   double *ys = DZ;                                    // [4][NN], aliases DZ
 
   const int tid = threadIdx.x;
-  int b = blockIdx.x;
-  const int bx = b % tiles_x;
-  b /= tiles_x;
-  const int by = b % tiles_y;
-  const int bz = b / tiles_y;
+  int bx, by, bz;
+  decode_tile (g, (int) blockIdx.x, tiles_x, tiles_y, bx, by, bz);
   const int cx0 = bx * TX, cy0 = by * TY, cz0 = g.cell_begin + bz * TZ;
   const int nnx = g.nn[0], nny = g.nn[1];
   const int lz_off = g.plane_begin;

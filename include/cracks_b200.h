@@ -228,6 +228,12 @@ int pf_apply_preconditioner (pf_ctx *ctx, const double *v, double *z);
  * Residuals (cracks.cc:2393-2432), the active-set test, energies and the outer GMRES vectors stay FP64, so the
  * Newton fixed point and every parity metric are unchanged.  Takes effect at the next pf_setup_jacobian. */
 int pf_set_jacobian_precision (pf_ctx *ctx, int bits);
+/* Deterministic scatter (3-D box meshes): the tiled kernels (operator, smoother operator, residual) and the diagonal are
+ * launched colour by colour -- 8 launches whose tiles share no node -- so every nodal sum is formed in the same order in
+ * every run and a Newton history is reproducible bit for bit on a given number of ranks.  Default off: one launch,
+ * red.global.add in scheduler order, results equal up to the last bits (which can move the round-off-determined
+ * active-set history of the reference's algorithm, cracks.cc:2863, never the converged step). */
+int pf_set_deterministic (pf_ctx *ctx, int on);
 /* Restart length of GMRES (deal.II's SolverGMRES default keeps 28 basis vectors,
  * cracks.cc:2764; this library's default is 30).  Ill-conditioned small 2-D
  * problems, which the reference hands to a sparse direct solver (2750-2759),

@@ -82,6 +82,21 @@ def test_apply_residual_diag_3d(oracle, epf):
     b_ref, c_ref = prob.energy(sol)
     bulk, crack = ctx.energy()
     assert bulk == pytest.approx(b_ref, rel=1e-12) and crack == pytest.approx(c_ref, rel=1e-12)
+    # pf_set_deterministic: the same operator / residual / diagonal launched colour by colour (8 launches whose tiles
+    # share no node); blocks run concurrently in the emulation too, so the bits must repeat
+    ctx.set_deterministic(True)
+    ctx.setup_jacobian()
+    outs = []
+    for _ in range(2):
+        yd = np.zeros(prob.n_dofs)
+        ctx.vmult(yd, ctx.to_block(x))
+        rd = ctx.residual()[1]
+        outs.append((yd, rd, ctx.jacobian_diagonal()))
+        ctx.setup_jacobian()
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))
+    assert _relerr(ctx.to_nodal(outs[0][0]), prob.apply_jacobian(sol, old, oo, con, x)) <= 1e-12
+    assert _relerr(ctx.to_nodal(outs[0][1]), r_tot_ref) <= 1e-12
+    assert _relerr(ctx.to_nodal(outs[0][2]), prob.jacobian(sol, old, oo, None).diagonal()) <= 1e-12
     ctx.close()
 
 

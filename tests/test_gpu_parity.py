@@ -250,3 +250,36 @@ def test_preconditioners_give_the_same_newton_update(oracle, pf, kind):
     with pytest.raises(pf.PFError):
         ctx.set_preconditioner(1, cheb_degree=0)
     ctx.close()
+
+
+def test_deterministic_mode_is_bit_identical_run_to_run(oracle, pf):
+    """pf_set_deterministic: operator, residual and diagonal launched colour by colour.  Two Newton runs (time step 0
+    of the Sneddon test at 1 refinement, multigrid V-cycle, about 10 Newton steps with a round-off-determined active-set
+    history, SURVEY.md preamble) must repeat each other bit for bit -- residual history, active-set sizes, GMRES
+    iteration counts, energies -- and the apply must still match the oracle to 1e-12."""
+    from cracks_b200.api import mesh_diameter
+    prob, ctx, sol, old, oo, con, rng = _case(oracle, pf, 3, (33, 9, 5), (0.25, 0.25, 0.25), seed=3)
+    ctx.set_deterministic(True)
+    ctx.setup_jacobian()
+    x = rng.standard_normal(prob.n_dofs)
+    ys = []
+    for _ in range(3):
+        y = np.zeros(prob.n_dofs)
+        ctx.vmult(y, ctx.to_block(x))
+        ys.append(y)
+    assert np.array_equal(ys[0], ys[1]) and np.array_equal(ys[0], ys[2])
+    assert _relerr(ctx.to_nodal(ys[0]), prob.apply_jacobian(sol, old, oo, con, x)) <= TOL
+    ctx.close()
+    histories = []
+    for _ in range(2):
+        mesh = pf.sneddon_mesh(3, 1)
+        c = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh))
+        c.set_deterministic(True)
+        drv = pf.SneddonDriver(c, pressure=lambda t: 1e-3, max_no_timesteps=0, newton_lower_bound=1e-7, max_newton=50,
+                               max_line_search=10, gmres_max_it=200)
+        st = drv.run(mesh_diameter(mesh))
+        histories.append(([(r.n_active, r.residual, r.line_search, r.lin_its) for r in drv.history[0]], st[0]["bulk"], st[0]["crack"]))
+        c.close()
+    assert histories[0][0] == histories[1][0]
+    # the energy functionals add their block sums with atomics (reporting only, never fed back): equal to round-off
+    assert histories[0][1] == pytest.approx(histories[1][1], rel=1e-13) and histories[0][2] == pytest.approx(histories[1][2], rel=1e-13)
