@@ -3083,6 +3083,7 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
   double res = bnorm;
   bool converged = false;
   bool first_cycle = true;
+  int verify_budget = 3; // true-residual checks (and refinement cycles) before the recurrence is taken at its word
   while (its < max_it && !converged)
     {
       // r = b - J x  (x = 0 on the first cycle)
@@ -3173,7 +3174,14 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
           if (res <= tol || !(hk1 > 0))
             {
               ++k;
-              converged = res <= tol;
+              // With the exact FP64 operator the recurrence's claim is verified: the next pass of the outer loop forms
+              // the true residual b - J x and either accepts it or restarts from it (iterative refinement).  The
+              // preconditioner may run in FP32 (right preconditioning: x = M^-1 V y carries its rounding), the
+              // linear solve still ends at |b - J x| <= tol like the reference's (cracks.cc:2762).  The FP32
+              // Jacobian (inexact Newton, opt-in) cannot resolve 1e-8: there the recurrence decides.
+              converged = res <= tol && (ctx->jacobian_bits != 64 || verify_budget == 0);
+              if (res <= tol && !converged)
+                --verify_budget;
               break;
             }
         }

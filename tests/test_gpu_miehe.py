@@ -164,5 +164,6 @@ def test_2d_multigrid_gives_the_jacobi_path_results_at_64x64(pf, name):
         for k in ("bulk", "crack", "load"):
             # both linear solves stop at |r| <= 1e-8 |b| (cracks.cc:2762) in different preconditioned norms and the Newton
             # loop at |r| < 1e-6: the converged steps agree to the stopping tolerances, not to round-off
-            assert b[k] == pytest.approx(a[k], rel=1e-5, abs=1e-14), (a, b)
+            # (the crack energy of these first steps is ~1e-6 of the bulk energy: absolute floor on that scale)
+            assert b[k] == pytest.approx(a[k], rel=1e-5, abs=1e-7 * abs(a["bulk"])), (k, a, b)
     assert lin[1] * 5 < lin[0], lin        # 9-12 iterations per solve instead of hundreds
