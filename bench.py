@@ -433,6 +433,7 @@ def main():
             nctx = pf.PhaseFieldContext(mesh, params, device=local_rank, rank=rank, nranks=world, nccl_id=fresh_nccl_id())
             if jacobian_bits != 64:
                 nctx.set_jacobian_precision(jacobian_bits)
+                nctx.set_multigrid_precision(jacobian_bits)
             drv = pf.SneddonDriver(nctx, pressure=lambda t: 1e-3, max_no_timesteps=1, newton_lower_bound=1e-7,
                                    max_newton=50, max_line_search=10, gmres_max_it=200)
             barrier()
@@ -453,8 +454,8 @@ def main():
                    "crack_energy": nstats[-1]["crack"] if nstats else None,
                    "bulk_energy": nstats[-1]["bulk"] if nstats else None,
                    "jacobian": "exact FP64 27-point apply" if jacobian_bits == 64 else "FP32 27-point apply on FP64 vectors (inexact Newton)",
-                   "preconditioner": "matrix-free geometric multigrid V-cycle in FP32 (z-slab levels, replicated below), "
-                                     "Chebyshev-Jacobi smoothing"}
+                   "preconditioner": "matrix-free geometric multigrid V-cycle in FP%d (z-slab levels, replicated below), "
+                                     "Chebyshev-Jacobi smoothing" % jacobian_bits}
             if nerr:
                 out["error"] = nerr
             nctx.close()

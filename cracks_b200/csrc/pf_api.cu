@@ -164,8 +164,10 @@ struct pf_ctx
   // the V-cycle in FP32 (pf_mg_lowp.cuh; opt-in, pf_set_multigrid_precision): per level the state, the inverse
   // diagonal and the work vectors in float; set-up (diagonal, power iteration) stays FP64
   bool mg2d = false; // multigrid also on 2-D box / slit meshes (pf_set_preconditioner kind 3), single rank
-  // default since round 2 (measured: profiles/r2_newton.json); PF_MG_FP32=0 or pf_set_multigrid_precision (ctx, 64) switch it off
-  int mg_fp32 = getenv ("PF_MG_FP32") ? atoi (getenv ("PF_MG_FP32")) : 1;
+  // opt-in (pf_set_multigrid_precision (ctx, 32) or PF_MG_FP32=1): with the FP64 Jacobian pf_solve then verifies the true
+  // residual and refines, which costs about what the cheaper cycle saves (profiles/README.md); the fast configuration
+  // is FP32 V-cycle + FP32 Jacobian (inexact Newton)
+  int mg_fp32 = getenv ("PF_MG_FP32") ? atoi (getenv ("PF_MG_FP32")) : 0;
   float *f_sol = nullptr, *f_pt = nullptr, *f_idiag = nullptr;
   float *f_b = nullptr, *f_x = nullptr, *f_y = nullptr, *f_d = nullptr, *f_r = nullptr;
   double *mg_in = nullptr;  // fixed input buffer of the captured V-cycle
@@ -1942,7 +1944,9 @@ apply_host_pipelined (pf_ctx *ctx, const double *xh, double *yh)
   // (1 / n_chunks each) is what the pipeline cannot hide.  Measured with 8, 16 and 32 chunks at 16.7 M DoF on one
   // GPU: 3.86 ms each, the PCIe transfers bound it (profiles/README.md); PF_E2E_CHUNKS for the A/B
   static const int max_chunks = std::max (1, std::min (32, getenv ("PF_E2E_CHUNKS") ? atoi (getenv ("PF_E2E_CHUNKS")) : 16));
-  const int n_chunks = std::max (1, std::min (max_chunks, layers / 2));
+  // at least 5 cell layers (about 4 MB at 161^2 nodes per plane) per chunk: a thin slab of a many-rank run is bound by
+  // the ~12 asynchronous calls a chunk costs, not by its bytes (8 GPUs, 21 layers: 10 chunks took 2.0 ms)
+  const int n_chunks = std::max (1, std::min (max_chunks, layers / 5));
   if (!ctx->h2d_stream)
     {
       CU (cudaStreamCreateWithFlags (&ctx->h2d_stream, cudaStreamNonBlocking));

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 5 (`multiple het`, parameters_hetero_3d.prm) at scale: the forest operator apply on N GPUs.
 
-  python tools/hetero_scale.py --global-refine 7 --local 1                      # one GPU
+  python tools/hetero_scale.py --global-refine 7 --local-refine 1                      # one GPU
   torchrun --nproc-per-node 8 ... tools/hetero_scale.py --global-refine 8      # 6.8e7 DoF on 8 GPUs
 
 The single-tree cube [0,10]^3 is refined `--global-refine` times, then `--local` times where the interpolated initial
@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--global-refine", type=int, default=6)
-    ap.add_argument("--local", type=int, default=1)
+    ap.add_argument("--local-refine", type=int, default=1)
     ap.add_argument("--applies", type=int, default=10)
     args = ap.parse_args()
     import torch
@@ -50,8 +50,8 @@ def main():
     t0 = time.perf_counter()
     f = HostForest(3, (1, 1, 1), (0.0,) * 3, (10.0,) * 3)
     f.refine_global(args.global_refine)
-    cap = args.global_refine + args.local
-    for _ in range(args.local):
+    cap = args.global_refine + args.local_refine
+    for _ in range(args.local_refine):
         t = f.tables()
         phi = initial_multiple_het_3d(t["coords"], f.min_cell_diameter)
         f.refine((t["level"] < cap) & (phi[t["conn"]] < 0.4).any(axis=1))
@@ -115,7 +115,7 @@ def main():
     y = ctx.download(y_dev)
     if rank == 0:
         print(json.dumps({"what": "forest operator apply, multiple het 3-D (BASELINE config 5)", "n_gpus": world,
-                          "global_refine": args.global_refine, "local_refine": args.local, "n_cells": int(f.n_cells),
+                          "global_refine": args.global_refine, "local_refine": args.local_refine, "n_cells": int(f.n_cells),
                           "n_nodes": int(nn), "n_dofs": int(ctx.n_dofs), "n_hanging": int(f.n_hanging),
                           "host_forest_s": round(t_forest, 1), "ms_per_apply": ms_apply,
                           "MDoF_per_s": ctx.n_dofs / (ms_apply * 1e-3) / 1e6, "ms_per_residual": ms_res,
