@@ -434,6 +434,10 @@ def main():
             if jacobian_bits != 64:
                 nctx.set_jacobian_precision(jacobian_bits)
                 nctx.set_multigrid_precision(jacobian_bits)
+            # one untimed time step first: the context allocates its Krylov basis, multigrid levels and coefficient
+            # records on first use (the reference allocates in setup_system(), outside newton_active_set() too)
+            pf.SneddonDriver(nctx, pressure=lambda t: 1e-3, max_no_timesteps=0, newton_lower_bound=1e-7, max_newton=50,
+                             max_line_search=10, gmres_max_it=200).run(mesh_diameter(mesh))
             drv = pf.SneddonDriver(nctx, pressure=lambda t: 1e-3, max_no_timesteps=1, newton_lower_bound=1e-7,
                                    max_newton=50, max_line_search=10, gmres_max_it=200)
             barrier()

@@ -361,7 +361,7 @@ class PhaseFieldContext:
         self._check(self.lib.pf_residual(self.h, None, None, C.byref(nrm)))
         return None, None, nrm.value
 
-    def set_preconditioner(self, kind=1, cheb_degree=2, cheb_ratio=20.0):
+    def set_preconditioner(self, kind=1, cheb_degree=2, cheb_ratio=6.0):
         """0 = Jacobi, 1 = geometric multigrid (stand-in for the reference's ML AMG)"""
         self._check(self.lib.pf_set_preconditioner(self.h, kind, cheb_degree, cheb_ratio))
 

@@ -150,7 +150,9 @@ struct pf_ctx
   int cheb_degree = 2;
   int coarsest_degree = 16;
   bool mg_approx = true;    // smoother / coarse operators use the 2-point Gauss rule (preconditioner only)
-  double cheb_ratio = 20.0; // smoothing range lambda_max / lambda_min targeted by the smoother
+  // smoothing range lambda_max / lambda_min targeted by the smoother.  Swept on the B200 at 16.7 M DoF (profiles/README.md):
+  // 3..8 are within 5 % of each other, 20 (the value of round 1) costs 25 % more GMRES iterations
+  double cheb_ratio = 6.0;
   double lam_max = 0;
   double *mg_b = nullptr, *mg_x = nullptr, *mg_y = nullptr, *mg_d = nullptr, *mg_r = nullptr, *mg_ev = nullptr;
   bool mg_ev_valid = false; // mg_ev holds the eigenvector estimate of the previous set-up
@@ -1315,7 +1317,7 @@ mg_setup_level (pf_ctx *ctx)
       KCHECK ();
       return allreduce_sum (ctx, ctx->red, 1);
     };
-    int n_it = 4;
+    int n_it = 2; // warm start from the previous Newton step's eigenvector estimate (lam_max carries a 20 % margin)
     if (!ctx->mg_ev_valid)
       {
         k_fill_hash<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, v);
@@ -2247,7 +2249,7 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
   CU (cudaMemsetAsync (ctx->mask, 0, nn, ctx->stream));
   CU (cudaMemsetAsync (ctx->cycle, 0, nn * sizeof (int), ctx->stream));
   CU (cudaMalloc (&ctx->red, 64 * sizeof (double)));
-  CU (cudaMalloc (&ctx->hdev, (size_t) (ctx->krylov_m + 2) * sizeof (double)));
+  CU (cudaMalloc (&ctx->hdev, (size_t) 2 * (ctx->krylov_m + 2) * sizeof (double)));
   CU (cudaMalloc (&ctx->partial, (size_t) RED_BLOCKS * (ctx->krylov_m + 2) * sizeof (double)));
   CU (cudaMallocHost (&ctx->h_gs, (size_t) 3 * (ctx->krylov_m + 2) * sizeof (double)));
   CU (cudaMalloc (&ctx->counts, 4 * sizeof (unsigned long long)));
@@ -2379,7 +2381,7 @@ create_forest_impl (const pf_forest_mesh *fm, const pf_params *params, int devic
   CU (cudaMemsetAsync (ctx->zero_mask, 0, nn, ctx->stream));
   CU (cudaMemsetAsync (ctx->cycle, 0, nn * sizeof (int), ctx->stream));
   CU (cudaMalloc (&ctx->red, 64 * sizeof (double)));
-  CU (cudaMalloc (&ctx->hdev, (size_t) (ctx->krylov_m + 2) * sizeof (double)));
+  CU (cudaMalloc (&ctx->hdev, (size_t) 2 * (ctx->krylov_m + 2) * sizeof (double)));
   CU (cudaMalloc (&ctx->partial, (size_t) RED_BLOCKS * (ctx->krylov_m + 2) * sizeof (double)));
   CU (cudaMallocHost (&ctx->h_gs, (size_t) 3 * (ctx->krylov_m + 2) * sizeof (double)));
   CU (cudaMalloc (&ctx->counts, 4 * sizeof (unsigned long long)));
@@ -2845,7 +2847,7 @@ pf_set_krylov_dim (pf_ctx *ctx, int m)
   CU (cudaFree (ctx->partial));
   CU (cudaFreeHost (ctx->h_gs));
   ctx->krylov_m = m;
-  CU (cudaMalloc (&ctx->hdev, (size_t) (m + 2) * sizeof (double)));
+  CU (cudaMalloc (&ctx->hdev, (size_t) 2 * (m + 2) * sizeof (double)));
   CU (cudaMalloc (&ctx->partial, (size_t) RED_BLOCKS * (m + 2) * sizeof (double)));
   CU (cudaMallocHost (&ctx->h_gs, (size_t) 3 * (m + 2) * sizeof (double)));
   return PF_OK;
@@ -3140,10 +3142,27 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
           double *gs0 = ctx->h_gs, *gs1 = ctx->h_gs + (m + 2);
           CU (cudaMemcpyAsync (gs0, ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToHost,
                                ctx->stream));
-          k_multi_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w);
-          KCHECK ();
-          if ((rc = dots (k + 1, w, 1)))
-            return rc;
+          if (k + 1 <= 16)
+            {
+              // first update and the second pass's dots (+ norm) in one sweep over the basis; the coefficients of the
+              // first pass move to a second buffer because the reduction overwrites hdev
+              CU (cudaMemcpyAsync (ctx->hdev + (m + 2), ctx->hdev, sizeof (double) * (k + 1), cudaMemcpyDeviceToDevice,
+                                   ctx->stream));
+              k_multi_axpy_dot<16><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, lo, hi, k + 1, V, nd, ctx->hdev + (m + 2), w,
+                                                                               ctx->partial);
+              KCHECK ();
+              k_reduce_partials<<<k + 2, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, k + 2, ctx->partial, ctx->hdev);
+              KCHECK ();
+              if ((rc = allreduce_sum (ctx, ctx->hdev, k + 2)))
+                return rc;
+            }
+          else
+            {
+              k_multi_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w);
+              KCHECK ();
+              if ((rc = dots (k + 1, w, 1)))
+                return rc;
+            }
           CU (cudaMemcpyAsync (gs1, ctx->hdev, sizeof (double) * (k + 2), cudaMemcpyDeviceToHost,
                                ctx->stream));
           k_multi_axpy_scale<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k + 1, V, nd, ctx->hdev, w, vk1);

@@ -420,6 +420,54 @@ k_multi_axpy (long long n, int k, const double *__restrict__ V, long long stride
     }
 }
 
+// first Gram-Schmidt update and the dot products of the second pass in one sweep over the basis:
+//   w <- w - sum_j h[j] V_j,   partial[j*nb + b] = V_j . w (new w),   partial[k*nb + b] = w . w (new w)
+// The update is element-wise, so the second pass's dots can be taken of the updated element at once: the k basis
+// vectors are read from DRAM once instead of twice (the second read of V_j[i] hits L1).  k <= KMAX.
+// Dots over [lo, hi) only (owned entries), the update over the whole local vector [0, n).
+template <int KMAX>
+__global__ void __launch_bounds__ (RED_THREADS)
+k_multi_axpy_dot (long long n, long long lo, long long hi, int k, const double *__restrict__ V, long long stride,
+                  const double *__restrict__ h, double *__restrict__ w, double *__restrict__ partial)
+{
+  __shared__ double sh[RED_THREADS / 32];
+  double acc[KMAX], nrm = 0, hj[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    {
+      acc[j] = 0;
+      hj[j] = j < k ? h[j] : 0.0;
+    }
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x)
+    {
+      double wi = w[i];
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j)
+        if (j < k)
+          wi = fma (-hj[j], V[j * stride + i], wi);
+      w[i] = wi;
+      if (i >= lo && i < hi)
+        {
+#pragma unroll
+          for (int j = 0; j < KMAX; ++j)
+            if (j < k)
+              acc[j] = fma (V[j * stride + i], wi, acc[j]);
+          nrm = fma (wi, wi, nrm);
+        }
+    }
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < k)
+      {
+        const double s = block_reduce_sum (acc[j], sh);
+        if (threadIdx.x == 0)
+          partial[(long long) j * gridDim.x + blockIdx.x] = s;
+      }
+  const double s = block_reduce_sum (nrm, sh);
+  if (threadIdx.x == 0)
+    partial[(long long) k * gridDim.x + blockIdx.x] = s;
+}
+
 // second Gram-Schmidt pass and normalisation in one sweep: v_next = (w - sum_j h[j] V_j) / hk1 with
 // hk1^2 = |w|^2 - sum_j h[j]^2 (h[k] = |w|^2 of the vector BEFORE this pass; the h[j] of a second pass are at
 // round-off level, so the Pythagorean form loses nothing).  hk1 == 0: v_next = the unscaled vector (breakdown,

@@ -2,7 +2,7 @@
 """Newton-its/s of the device-resident active-set Newton loop (cracks.cc:2780-2994)
 on Sneddon-3D (parameters_sneddon_3d.prm values) at a given global refinement.
 
-  python tools/newton_bench.py --refine 3 --steps 2 [--precond 1 --degree 3 --ratio 20]
+  python tools/newton_bench.py --refine 3 --steps 2 [--precond 1 --degree 2 --ratio 6]
 
 Prints the reference-style Newton table and one JSON line with Newton
 iterations per second, total linear iterations and the energies.
@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2, help="time steps to run")
     ap.add_argument("--precond", type=int, default=1)
     ap.add_argument("--degree", type=int, default=2)
-    ap.add_argument("--ratio", type=float, default=20.0)
+    ap.add_argument("--ratio", type=float, default=6.0)
     ap.add_argument("--gmres-max-it", type=int, default=200)
     ap.add_argument("--quiet", action="store_true")
     ap.add_argument("--jacobian-bits", type=int, default=64, help="32: inexact Newton, Jacobian apply in FP32")
