@@ -1317,7 +1317,9 @@ mg_setup_level (pf_ctx *ctx)
       KCHECK ();
       return allreduce_sum (ctx, ctx->red, 1);
     };
-    int n_it = 2; // warm start from the previous Newton step's eigenvector estimate (lam_max carries a 20 % margin)
+    // warm start from the previous Newton step's eigenvector estimate.  Two iterations were tried and lose the 2-D
+    // Miehe runs: when the stress split switches on (time step 1) the operator changes more than the 20 % margin covers
+    int n_it = 4;
     if (!ctx->mg_ev_valid)
       {
         k_fill_hash<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, v);
