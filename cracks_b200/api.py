@@ -95,6 +95,7 @@ _SIGS = {
     "pf_set_multigrid_precision": [C.c_void_p, C.c_int],
     "pf_set_jacobian_precision": [C.c_void_p, C.c_int],
     "pf_set_deterministic": [C.c_void_p, C.c_int],
+    "pf_set_multigrid_coupling": [C.c_void_p, C.c_int],
     "pf_apply_preconditioner": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_set_krylov_dim": [C.c_void_p, C.c_int],
     "pf_apply_jacobian": [C.c_void_p, C.c_void_p, C.c_void_p],
@@ -364,6 +365,10 @@ class PhaseFieldContext:
     def set_preconditioner(self, kind=1, cheb_degree=2, cheb_ratio=6.0):
         """0 = Jacobi, 1 = geometric multigrid (stand-in for the reference's ML AMG)"""
         self._check(self.lib.pf_set_preconditioner(self.h, kind, cheb_degree, cheb_ratio))
+
+    def set_multigrid_coupling(self, coupled=True):
+        """False: block-diagonal smoother operator (no (phi,u) block), like the reference's BlockDiagonalPreconditioner"""
+        self._check(self.lib.pf_set_multigrid_coupling(self.h, int(coupled)))
 
     def set_deterministic(self, on=True):
         """scatter kernels colour by colour: bit-identical results run to run (3-D box meshes)"""

@@ -202,6 +202,7 @@ struct pf_ctx
   bool no_overlap = false;     // PF_NO_OVERLAP: halo exchange not overlapped with the interior layers (A/B)
   bool split_boundary = false; // PF_SPLIT_BOUNDARY: two boundary launches of a middle slab instead of one (A/B)
   bool mg_use_graph = false;   // PF_MG_GRAPH=1
+  bool mg_uncoupled = false;   // pf_set_multigrid_coupling (ctx, 0): the smoother operator without its (phi,u) block
   bool deterministic = false;  // pf_set_deterministic: scatter kernels launched colour by colour (Grid::colour)
   std::set<const void *> attr_done; // kernels whose per-device function attributes this context has set
   double last_rnorm = 0;
@@ -736,13 +737,13 @@ v6_refresh_coefficients (pf_ctx *ctx, typename Lane<R>::S **buf)
 }
 
 // R = arithmetic of the cell walk, V = type of the global vectors, NQ = 3 (exact rule) or 2 (smoother operator)
-template <typename R, typename V, int NQ, int MINB>
+template <typename R, typename V, int NQ, int MINB, bool COUPLED = true>
 int
 launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename Lane<R>::S *coef)
 {
   using S = typename Lane<R>::S;
   constexpr int TX = V6Shape<R>::TX, TY = V6Shape<R>::TY, W = Lane<R>::W;
-  using T = Tile3v6<TX, TY, NQ, W>;
+  using T = Tile3v6<TX, TY, NQ, W, COUPLED>;
   constexpr size_t smem = (T::smem_elems * sizeof (S) + 15) / 16 * 16 + 2 * T::coef_per_plane * sizeof (S) + 32;
   Grid g = ctx->g;
   const int layer0 = g.cell_begin;
@@ -757,8 +758,10 @@ launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename L
   static const char attr_tag = 0;
   if (ctx->attr_done.insert (&attr_tag).second)
     {
-      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int) smem));
+      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                100));
     }
   const K6 k6 = make_k6 (ctx);
   for (int colour = ctx->deterministic ? 0 : -1; colour < (ctx->deterministic ? 8 : 0); ++colour)
@@ -767,8 +770,8 @@ launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename L
       const unsigned grid = (unsigned) tiles_of_colour (colour, tiles_x, tiles_y, tiles_z);
       if (grid == 0)
         continue;
-      k_apply3d_v6<R, V, NQ, TX, TY, MINB><<<grid, T::NT, smem, ctx->stream>>> (g, k6, tiles_x, tiles_y, layer0, x, sol,
-                                                                                ctx->mask, coef, y);
+      k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED><<<grid, T::NT, smem, ctx->stream>>> (g, k6, tiles_x, tiles_y, layer0, x,
+                                                                                         sol, ctx->mask, coef, y);
       KCHECK ();
     }
   return PF_OK;
@@ -786,7 +789,8 @@ launch_tiled_default (pf_ctx *ctx, const double *x, double *y, bool approx)
   if (ctx->apply_variant == 16 && v6_possible (ctx))
     {
       if (approx && ctx->coef2_64)
-        return launch_apply3d_v6<double, double, 2, 4> (ctx, x, ctx->sol, y, ctx->coef2_64);
+        return ctx->mg_uncoupled ? launch_apply3d_v6<double, double, 2, 4, false> (ctx, x, ctx->sol, y, ctx->coef2_64)
+                                 : launch_apply3d_v6<double, double, 2, 4> (ctx, x, ctx->sol, y, ctx->coef2_64);
       if (!approx && ctx->jacobian_bits == 32 && ctx->coef32)
         return launch_apply3d_v6<f32x2, double, 3, 4> (ctx, x, ctx->sol, y, ctx->coef32);
       if (!approx && ctx->coef64)
@@ -1396,6 +1400,7 @@ mg_setup_level (pf_ctx *ctx)
   c->mg_fp32 = ctx->mg_fp32;
   c->apply_variant = ctx->apply_variant;
   c->deterministic = ctx->deterministic;
+  c->mg_uncoupled = ctx->mg_uncoupled;
   c->no_iso = ctx->no_iso;
   c->force_generic = ctx->force_generic;
   Dims3 dc{{c->g.nn[0], c->g.nn[1], c->g.nn[2]}, c->g.plane_begin},
@@ -1643,7 +1648,8 @@ launch_apply3d_mg (pf_ctx *ctx, const float *x, float *y)
   const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
   const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
   if (ctx->apply_variant == 16 && v6_possible (ctx) && ctx->coef2_32)
-    return launch_apply3d_v6<f32x2, float, 2, 4> (ctx, x, ctx->f_sol, y, ctx->coef2_32);
+    return ctx->mg_uncoupled ? launch_apply3d_v6<f32x2, float, 2, 4, false> (ctx, x, ctx->f_sol, y, ctx->coef2_32)
+                             : launch_apply3d_v6<f32x2, float, 2, 4> (ctx, x, ctx->f_sol, y, ctx->coef2_32);
   const unsigned grid = (unsigned) tiles_x * tiles_y * tiles_z;
   if (iso)
     k_apply3d_mg<float, TX, TY, TZ, MINB, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
@@ -2830,6 +2836,20 @@ pf_set_deterministic (pf_ctx *ctx, int on)
     return PF_BAD_ARG;
   for (pf_ctx *c = ctx; c; c = c->coarse)
     c->deterministic = on != 0;
+  return PF_OK;
+}
+
+// Smoother operator of the multigrid V-cycle with (1, default) or without (0) the (phi,u) block of the Jacobian.
+// Without it the preconditioner is block diagonal like the reference's (BlockDiagonalPreconditioner,
+// cracks.cc:2717-2740: one AMG V-cycle per diagonal block) and a smoother application neither stages nor
+// interpolates the state U.  The Krylov operator is never affected.  3-D box meshes with cubic cells.
+int
+pf_set_multigrid_coupling (pf_ctx *ctx, int coupled)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  for (pf_ctx *c = ctx; c; c = c->coarse)
+    c->mg_uncoupled = coupled == 0;
   return PF_OK;
 }
 

@@ -150,7 +150,9 @@ v6_async_proxy_fence ()
 #endif
 
 // TX x TY cells per tile, W cells per thread; the row pitch of the staging arrays is even when W == 2
-template <int TX, int TY, int NQ = 3, int W = 1> struct Tile3v6
+// COUPLED = false: the operator without its (phi,u) block, i.e. block diagonal like the reference's own preconditioner
+// (BlockDiagonalPreconditioner, cracks.cc:2717-2740) -- multigrid smoother only; the state U is then not staged at all
+template <int TX, int TY, int NQ = 3, int W = 1, bool COUPLED = true> struct Tile3v6
 {
   static_assert (TX % W == 0, "a thread's cells lie in one tile row");
   static constexpr int NX = TX + 1, NY = TY + 1;
@@ -160,8 +162,8 @@ template <int TX, int TY, int NQ = 3, int W = 1> struct Tile3v6
   static constexpr int NXC = PX * TY;    // (x-node, cell row)
   static constexpr int NT = TX / W * TY; // threads
   static constexpr int SY = PX, SZ = PX * NY;
-  static constexpr int NF = 8;  // staged nodal fields: x_u (3), x_phi / 8, u (3), phi / 8
-  static constexpr int NFZ = 7; // fields with a z-difference chain: all but phi
+  static constexpr int NF = COUPLED ? 8 : 4;  // staged nodal fields: x_u (3), x_phi / 8, u (3), phi / 8
+  static constexpr int NFZ = COUPLED ? 7 : 4; // fields with a z-difference chain: all but phi
   static constexpr int NQP = NQ * NQ * NQ;
   static constexpr size_t scratch = (NFZ * NC2 > 4 * NN) ? (size_t) NFZ * NC2 : (size_t) 4 * NN; // DZ, then the y tile
   static constexpr size_t smem_elems = (size_t) NQ * NF * NC2 + (size_t) NFZ * NQ * NXC + NXC + scratch;
@@ -270,7 +272,7 @@ k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, cons
 // ---- stages 3 and 4 of the apply for one tile (contains block barriers: all threads of the CTA call it) ---
 // NQ = 3: the exact rule, G_c eps grad(dphi).grad(psi) in closed form.  NQ = 2: the under-integrated operator of the
 // multigrid smoother (preconditioner only), phi-gradient flux inside the quadrature.
-template <typename R, int TX, int TY, int NQ>
+template <typename R, int TX, int TY, int NQ, bool COUPLED>
 __device__ __forceinline__ void
 tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const int cy0, const int cz0,
                const typename Lane<R>::S *__restrict__ AZ, const typename Lane<R>::S *__restrict__ BZ,
@@ -280,7 +282,7 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
   using L = Lane<R>;
   using S = typename L::S;
   constexpr int W = L::W;
-  using T = Tile3v6<TX, TY, NQ, W>;
+  using T = Tile3v6<TX, TY, NQ, W, COUPLED>;
   constexpr int NN = T::NN, PX = T::PX, NC2 = T::NC2, NXC = T::NXC, NF = T::NF, NT = T::NT;
   constexpr unsigned plane_bytes = (unsigned) (T::coef_per_plane * sizeof (S));
   constexpr bool CEN = NQ == 3; // the 3-point rule has a centre point and uses the closed-form Laplacian
@@ -345,7 +347,7 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
 #pragma unroll
               for (int f = 0; f < 7; ++f)
                 {
-                  if (CEN && f == 3)
+                  if ((CEN && f == 3) || (!COUPLED && f > 3))
                     continue;
                   const R ds = s1[f] - s0[f], dr = r1[f] - r0[f];
                   dx[f] = ceny ? ds : fma_r (ey, dr, ds);
@@ -357,11 +359,19 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
                   RxBz[f] = z1 - z0;
                 }
               const R b0p = ceny ? s0[3] : fma_r (ey, r0[3], s0[3]), b1p = ceny ? s1[3] : fma_r (ey, r1[3], s1[3]);
-              const R b0f = ceny ? s0[7] : fma_r (ey, r0[7], s0[7]), b1f = ceny ? s1[7] : fma_r (ey, r1[7], s1[7]);
-              const R Pdphi = b0p + b1p, Rdphi = b1p - b0p, Ppf = b0f + b1f, Rpf = b1f - b0f;
+              R Ppf = (R) 0, Rpf = (R) 0;
+              if (COUPLED)
+                {
+                  const R b0f = ceny ? s0[NF - 1] : fma_r (ey, r0[NF - 1], s0[NF - 1]);
+                  const R b1f = ceny ? s1[NF - 1] : fma_r (ey, r1[NF - 1], s1[NF - 1]);
+                  Ppf = b0f + b1f, Rpf = b1f - b0f;
+                }
+              const R Pdphi = b0p + b1p, Rdphi = b1p - b0p;
               // symmetric off-diagonal strain sums, linear in xi_x
               const R oP01 = PxDy[0] + dx[1], oP02 = PxBz[0] + dx[2], oP12 = PxBz[1] + PxDy[2], oR12 = RxBz[1] + RxDy[2];
-              const R uP01 = PxDy[4] + dx[5], uP02 = PxBz[4] + dx[6], uP12 = PxBz[5] + PxDy[6], uR12 = RxBz[5] + RxDy[6];
+              R uP01 = (R) 0, uP02 = (R) 0, uP12 = (R) 0, uR12 = (R) 0;
+              if (COUPLED)
+                uP01 = PxDy[4] + dx[5], uP02 = PxBz[4] + dx[6], uP12 = PxBz[5] + PxDy[6], uR12 = RxBz[5] + RxDy[6];
               // accumulators of the transposed x-collapse: stresses S00 S01 S02 S11 S12 S22 (sum and xi_x-weighted sum)
               R P00 = (R) 0, P01 = (R) 0, P02 = (R) 0, P11 = (R) 0, P12 = (R) 0, P22 = (R) 0;
               R R01 = (R) 0, R02 = (R) 0, R11 = (R) 0, R12 = (R) 0, R22 = (R) 0;
@@ -372,27 +382,33 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
                 {
                   const R ex = es[qx];
                   const bool cen = CEN && qx == 1;
-                  const R G00 = dx[0], U00 = dx[4];
+                  const R G00 = dx[0];
                   const R G11 = cen ? PxDy[1] : fma_r (ex, RxDy[1], PxDy[1]);
                   const R G22 = cen ? PxBz[2] : fma_r (ex, RxBz[2], PxBz[2]);
-                  const R U11 = cen ? PxDy[5] : fma_r (ex, RxDy[5], PxDy[5]);
-                  const R U22 = cen ? PxBz[6] : fma_r (ex, RxBz[6], PxBz[6]);
                   const R o01 = cen ? oP01 : fma_r (ex, RxDy[0], oP01);
                   const R o02 = cen ? oP02 : fma_r (ex, RxBz[0], oP02);
                   const R o12 = cen ? oP12 : fma_r (ex, oR12, oP12);
-                  const R u01 = cen ? uP01 : fma_r (ex, RxDy[4], uP01);
-                  const R u02 = cen ? uP02 : fma_r (ex, RxBz[4], uP02);
-                  const R u12 = cen ? uP12 : fma_r (ex, uR12, uP12);
                   const R dphi = cen ? Pdphi : fma_r (ex, Rdphi, Pdphi);
-                  const R pf = cen ? Ppf : fma_r (ex, Rpf, Ppf);
-                  const R trG = G00 + G11 + G22, trU = U00 + U11 + U22;
-                  // (phi,u) and (phi,phi): a = pf w k1 [ (lam2 trU - beta) trG + U:G ] + dphi c2
-                  const R tU = fma_r (lam2, trU, nbeta);
-                  const R dd = fma_r (U00, G00, fma_r (U11, G11, U22 * G22));
-                  const R od = fma_r (u01, o01, fma_r (u02, o02, u12 * o12));
-                  const R spg = fma_r (tU, trG, fma_r (half, od, dd));
-                  const int wc = CEN ? (qx == 1) + (qy == 1) : 0; // point class: corner-, edge-, centre-like in the plane
-                  const R wa = fma_r (pf * wk[wc], spg, dphi * c23[qx]);
+                  const R trG = G00 + G11 + G22;
+                  R wa = dphi * c23[qx]; // (phi,phi): dphi c2
+                  if (COUPLED)
+                    {
+                      // (phi,u): pf w k1 [ (lam2 trU - beta) trG + U:G ]
+                      const R U00 = dx[4];
+                      const R U11 = cen ? PxDy[5] : fma_r (ex, RxDy[5], PxDy[5]);
+                      const R U22 = cen ? PxBz[6] : fma_r (ex, RxBz[6], PxBz[6]);
+                      const R u01 = cen ? uP01 : fma_r (ex, RxDy[4], uP01);
+                      const R u02 = cen ? uP02 : fma_r (ex, RxBz[4], uP02);
+                      const R u12 = cen ? uP12 : fma_r (ex, uR12, uP12);
+                      const R pf = cen ? Ppf : fma_r (ex, Rpf, Ppf);
+                      const R trU = U00 + U11 + U22;
+                      const R tU = fma_r (lam2, trU, nbeta);
+                      const R dd = fma_r (U00, G00, fma_r (U11, G11, U22 * G22));
+                      const R od = fma_r (u01, o01, fma_r (u02, o02, u12 * o12));
+                      const R spg = fma_r (tU, trG, fma_r (half, od, dd));
+                      const int wc = CEN ? (qx == 1) + (qy == 1) : 0; // point class: corner-, edge-, centre-like in the plane
+                      wa = fma_r (pf * wk[wc], spg, wa);
+                    }
                   AP += wa;
                   if (!cen)
                     AR = fma_r (ex, wa, AR);
@@ -546,7 +562,7 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
 // V = type of the global vectors x, sol, y (FP64 for the Krylov operator, FP32 inside the FP32 V-cycle);
 // R = arithmetic type of the cell walk (double, float, or f32x2 = two cells per thread in packed FP32).
 // The z-collapse of stage 1 is done in V.
-template <typename R, typename V, int NQ, int TX, int TY, int MINB>
+template <typename R, typename V, int NQ, int TX, int TY, int MINB, bool COUPLED = true>
 __global__ void __launch_bounds__ (TX / Lane<R>::W * TY, MINB)
 k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__restrict__ x,
               const V *__restrict__ sol, const uint8_t *__restrict__ mask,
@@ -554,7 +570,7 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
 {
   using S = typename Lane<R>::S;
   constexpr int W = Lane<R>::W;
-  using T = Tile3v6<TX, TY, NQ, W>;
+  using T = Tile3v6<TX, TY, NQ, W, COUPLED>;
   using V4 = typename Quad<V>::type;
   constexpr int NN = T::NN, NT = T::NT, NX = T::NX, PX = T::PX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC, NF = T::NF,
                 NFZ = T::NFZ;
@@ -608,8 +624,6 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
           const long long n1 = n0 + pstride;
           const V4 xa = *reinterpret_cast<const V4 *> (x + 4 * n0);
           const V4 xb = *reinterpret_cast<const V4 *> (x + 4 * n1);
-          const V4 sa = *reinterpret_cast<const V4 *> (sol + 4 * n0);
-          const V4 sb = *reinterpret_cast<const V4 *> (sol + 4 * n1);
           const uint8_t m0 = mask[n0], m1 = mask[n1];
           f0[0] = (m0 & 1) ? (V) 0 : xa.x;
           f0[1] = (m0 & 2) ? (V) 0 : xa.y;
@@ -619,8 +633,13 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
           f1[1] = (m1 & 2) ? (V) 0 : xb.y;
           f1[2] = (m1 & 4) ? (V) 0 : xb.z;
           f1[3] = (m1 & 8) ? (V) 0 : eighth * xb.w;
-          f0[4] = sa.x, f0[5] = sa.y, f0[6] = sa.z, f0[7] = eighth * sa.w;
-          f1[4] = sb.x, f1[5] = sb.y, f1[6] = sb.z, f1[7] = eighth * sb.w;
+          if (COUPLED)
+            {
+              const V4 sa = *reinterpret_cast<const V4 *> (sol + 4 * n0);
+              const V4 sb = *reinterpret_cast<const V4 *> (sol + 4 * n1);
+              f0[NF - 4] = sa.x, f0[NF - 3] = sa.y, f0[NF - 2] = sa.z, f0[NF - 1] = eighth * sa.w;
+              f1[NF - 4] = sb.x, f1[NF - 3] = sb.y, f1[NF - 2] = sb.z, f1[NF - 1] = eighth * sb.w;
+            }
         }
 #pragma unroll
       for (int f = 0; f < NF; ++f)
@@ -658,7 +677,7 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
     ys[i] = 0;
   __syncthreads ();
 
-  tile_cells_v6<R, TX, TY, NQ> (g, k, tid, cx0, cy0, cz0, AZ, BZ, BR, coef_tile, CF, mbar, ys);
+  tile_cells_v6<R, TX, TY, NQ, COUPLED> (g, k, tid, cx0, cy0, cz0, AZ, BZ, BR, coef_tile, CF, mbar, ys);
 
   // ---- flush the y tile -----------------------------------------------------------
   for (int i = tid; i < NN; i += NT)

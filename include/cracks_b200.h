@@ -234,6 +234,10 @@ int pf_set_jacobian_precision (pf_ctx *ctx, int bits);
  * red.global.add in scheduler order, results equal up to the last bits (which can move the round-off-determined
  * active-set history of the reference's algorithm, cracks.cc:2863, never the converged step). */
 int pf_set_deterministic (pf_ctx *ctx, int on);
+/* Smoother operator of the multigrid V-cycle with (1, default) or without (0) the (phi,u) block.  Without it the
+ * preconditioner is block diagonal like the reference's BlockDiagonalPreconditioner (cracks.cc:2717-2740) and a
+ * smoother application neither stages nor interpolates the state U.  The Krylov operator is not affected. */
+int pf_set_multigrid_coupling (pf_ctx *ctx, int coupled);
 /* Restart length of GMRES (deal.II's SolverGMRES default keeps 28 basis vectors,
  * cracks.cc:2764; this library's default is 30).  Ill-conditioned small 2-D
  * problems, which the reference hands to a sparse direct solver (2750-2759),

@@ -115,7 +115,7 @@ emu_apply3d (int variant, int nq, const int *n, const double *h, const double *p
   const int tiles_x = (n[0] + TX - 1) / TX, tiles_y = (n[1] + TY - 1) / TY, tiles_z = (n[2] + TZ - 1) / TZ;
   const unsigned grid = (unsigned) (tiles_x * tiles_y * tiles_z);
   const bool iso = h[0] == h[1] && h[1] == h[2];
-  if (variant == 26 || variant == 27)
+  if (variant == 26 || variant == 27 || variant == 28)
     {
       // v6: cubic cells only; the coefficient records first (k_point_coeffs), then the tiles -- as pf_setup_jacobian /
       // launch_apply3d_v6 do.  27 = the FP32 Jacobian of the inexact-Newton path.
@@ -135,6 +135,14 @@ emu_apply3d (int variant, int nq, const int *n, const double *h, const double *p
           std::vector<double> coef (T6::coef_per_tile * grid);
           launch_blocks (k_point_coeffs<double, 16, 4, 3, 1>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
           launch_blocks (k_apply3d_v6<double, double, 3, 16, 4, 4>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask,
+                         (const double *) coef.data (), y);
+        }
+      else if (variant == 28)
+        {
+          // the 2-point-rule smoother operator without its (phi,u) block (pf_set_multigrid_coupling 0)
+          std::vector<double> coef (Tile3v6<16, 4, 2>::coef_per_tile * grid);
+          launch_blocks (k_point_coeffs<double, 16, 4, 2, 1>, grid, 64u, g, p, k, tiles_x, tiles_y, 0, sol, pt, coef.data ());
+          launch_blocks (k_apply3d_v6<double, double, 2, 16, 4, 4, false>, grid, 64u, g, k6, tiles_x, tiles_y, 0, x, sol, mask,
                          (const double *) coef.data (), y);
         }
       else if (variant == 26)

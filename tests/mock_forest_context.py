@@ -37,7 +37,7 @@ def make_mock(ao, orc):
     """-> a class with ForestContext's constructor signature"""
 
     class MockForestContext:
-        def __init__(self, forest, params, device=0, cell_lame=None, cell_lame_energy=None):
+        def __init__(self, forest, params, device=0, cell_lame=None, cell_lame_energy=None, dist=None):
             self.forest, self.params = forest, params
             self.tables = forest.tables()
             self.dim, self.nc = forest.dim, forest.dim + 1

@@ -504,7 +504,9 @@ def test_cpp_host_driver_miehe_multigrid_from_64_cells(epf, emu_so, tmp_path):
     for row, b in zip(rows, ref):
         assert int(row[2]) == 12771
         for col, k in ((4, "bulk"), (5, "crack"), (6, "load")):
-            assert float(row[col]) == pytest.approx(b[k], rel=1e-6), (row[0], k)
+            # the crack energy of these first steps is 1e-3 of the bulk energy and moves with the Newton stopping point
+            # (|r| < 1e-6): an absolute floor on the bulk energy's scale
+            assert float(row[col]) == pytest.approx(b[k], rel=1e-6, abs=1e-6 * abs(b["bulk"])), (row[0], k)
 
 
 def test_forest_hetero_3d_kat5_end_to_end(epf):

@@ -20,12 +20,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--refine", type=int, default=7)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--case", default="shear", choices=["shear", "tension"],
+                    help="shear: parameters_miehe_shear (stress split, BASELINE config 4 physics); tension: "
+                         "parameters_miehe_tension_adaptive on the uniform mesh (BASELINE config 2)")
     ap.add_argument("--exe", default=os.path.join(ROOT, "cracks_b200", "cracks_b200_run"))
     args = ap.parse_args()
-    g = json.load(open(os.path.join(ROOT, "tests", "golden", "miehe_shear_2.json")))
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "miehe_shear_2.json" if args.case == "shear"
+                                    else "miehe_tension_adaptive_1.json")))
     with tempfile.TemporaryDirectory() as tmp:
         prm = write_prm(os.path.join(tmp, "m.prm"), g["prm"], 2, os.path.join(tmp, "out"), Max_No_of_timesteps=args.steps - 1,
-                        exact={"Global pre-refinement steps": args.refine})
+                        exact={"Global pre-refinement steps": args.refine, "Adaptive refinement cycles": 0})
         t0 = time.time()
         r = subprocess.run([args.exe, prm, "--no-output"], capture_output=True, text=True)
         wall = time.time() - t0
@@ -35,9 +39,9 @@ def main():
         its = [tuple(map(int, m)) for m in re.findall(r"Newton iterations: (\d+) total linear iterations: (\d+)", r.stdout)]
         dofs = re.search(r"DoFs: .* = (\d+)", r.stdout).group(1)
         rows = [l.split() for l in open(os.path.join(tmp, "out", "statistics")) if not l.startswith("#")]
-        print(json.dumps({"n_dofs": int(dofs), "time_steps": len(rows), "newton_its": sum(a for a, _ in its),
+        print(json.dumps({"case": "miehe " + args.case, "n_dofs": int(dofs), "time_steps": len(rows), "newton_its": sum(a for a, _ in its),
                           "linear_its": sum(b for _, b in its), "wall_s": round(wall, 2),
-                          "last_row": {"bulk": float(rows[-1][4]), "crack": float(rows[-1][5]), "load_x": float(rows[-1][6])}}))
+                          "last_row": {"bulk": float(rows[-1][4]), "crack": float(rows[-1][5]), "load": float(rows[-1][6])}}))
 
 
 if __name__ == "__main__":
