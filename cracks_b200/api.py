@@ -96,6 +96,7 @@ _SIGS = {
     "pf_set_jacobian_precision": [C.c_void_p, C.c_int],
     "pf_set_deterministic": [C.c_void_p, C.c_int],
     "pf_set_multigrid_coupling": [C.c_void_p, C.c_int],
+    "pf_set_multigrid_graph": [C.c_void_p, C.c_int],
     "pf_apply_preconditioner": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_set_krylov_dim": [C.c_void_p, C.c_int],
     "pf_apply_jacobian": [C.c_void_p, C.c_void_p, C.c_void_p],
@@ -369,6 +370,10 @@ class PhaseFieldContext:
     def set_multigrid_coupling(self, coupled=True):
         """False: block-diagonal smoother operator (no (phi,u) block), like the reference's BlockDiagonalPreconditioner"""
         self._check(self.lib.pf_set_multigrid_coupling(self.h, int(coupled)))
+
+    def set_multigrid_graph(self, on=True):
+        """the V-cycle as one CUDA graph launch (several GPUs: the cycle is launch-bound)"""
+        self._check(self.lib.pf_set_multigrid_graph(self.h, int(on)))
 
     def set_deterministic(self, on=True):
         """scatter kernels colour by colour: bit-identical results run to run (3-D box meshes)"""

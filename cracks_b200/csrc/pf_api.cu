@@ -162,6 +162,7 @@ struct pf_ctx
   // every pf_setup_jacobian (the Chebyshev coefficients are kernel arguments).
   cudaGraphExec_t mg_graph = nullptr;
   bool mg_graph_valid = false;
+  bool mg_graph_warm = false; // one V-cycle has run outside a capture
   long long mg_graph_launches = 0;
   // the V-cycle in FP32 (pf_mg_lowp.cuh; opt-in, pf_set_multigrid_precision): per level the state, the inverse
   // diagonal and the work vectors in float; set-up (diagonal, power iteration) stays FP64
@@ -1804,36 +1805,52 @@ mg_vcycle_lowp (pf_ctx *ctx, const float *b, float *x)
 int
 precond_apply (pf_ctx *ctx, const double *v, double *z)
 {
-  if (ctx->precond == 1 && ctx->mg_ready && ctx->coarse && ctx->mg_fp32 && ctx->f_b)
+  const bool mg = ctx->precond == 1 && ctx->mg_ready && ctx->coarse;
+  if (!mg)
     {
-      // FP64 Krylov vector -> FP32 V-cycle -> FP64 (right preconditioning: the outer iteration stays FP64)
-      const long long nd = ctx->n_local_dofs;
-      k_convert<double, float><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, v, ctx->f_b);
-      KCHECK ();
-      const int rc = mg_vcycle_lowp (ctx, ctx->f_b, ctx->f_x);
-      if (rc)
-        return rc;
-      k_convert<float, double><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->f_x, z);
+      k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->n_local_dofs, ctx->diag, v, z);
       KCHECK ();
       return PF_OK;
     }
-  // Opt-in (PF_MG_GRAPH=1), single rank only.  Measured on B200 at 16.7 M DoF: 9.27 vs 9.26
-  // Newton-its/s, i.e. the V-cycle is not launch-bound on one GPU; with NCCL nodes in the graph
-  // (2 and 4 ranks) the solve ran but the processes hung at tear-down, so it stays off there.
-  const bool use_graph = ctx->mg_use_graph;
-  if (ctx->precond == 1 && ctx->mg_ready && ctx->coarse && use_graph && ctx->nranks == 1 && !ctx->profiling
-      && !g_trace.on)
+  const long long nd = ctx->n_local_dofs;
+  const bool lowp = ctx->mg_fp32 && ctx->f_b;
+  // The V-cycle as ONE CUDA graph launch (pf_set_multigrid_graph / PF_MG_GRAPH=1).  A cycle is about 200 kernel
+  // launches and, on several ranks, 20-30 NCCL calls on levels of a few cell layers per rank: on 8 GPUs the host's
+  // launch rate bounds it, not the GPUs.  The graph is captured from the same code (halo exchanges on
+  // the second stream and NCCL calls included) after every pf_setup_jacobian -- the Chebyshev coefficients are kernel
+  // arguments -- and updated in place when the topology is unchanged.
+  const bool graph_ok = ctx->mg_use_graph && !ctx->profiling && !g_trace.on;
+  int rc;
+  // FP64 Krylov vector -> FP32 V-cycle -> FP64 (right preconditioning: the outer iteration stays FP64)
+  if (lowp)
+    {
+      k_convert<double, float><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, v, ctx->f_b);
+      KCHECK ();
+    }
+  else if (graph_ok)
     {
       if (!ctx->mg_in)
-        CU (cudaMalloc (&ctx->mg_in, sizeof (double) * ctx->n_local_dofs));
-      CU (cudaMemcpyAsync (ctx->mg_in, v, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice, ctx->stream));
-      if (!ctx->mg_graph_valid || ctx->mg_out != z)
+        CU (cudaMalloc (&ctx->mg_in, sizeof (double) * nd));
+      CU (cudaMemcpyAsync (ctx->mg_in, v, sizeof (double) * nd, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  auto cycle = [&]() -> int {
+    return lowp ? mg_vcycle_lowp (ctx, ctx->f_b, ctx->f_x) : mg_vcycle (ctx, graph_ok ? ctx->mg_in : v, z);
+  };
+  if (!graph_ok || !ctx->mg_graph_warm)
+    {
+      // (the first cycle of a context runs uncaptured: it sets function attributes and lets NCCL connect)
+      if ((rc = cycle ()))
+        return rc;
+      ctx->mg_graph_warm = true;
+    }
+  else
+    {
+      if (!ctx->mg_graph_valid || (!lowp && ctx->mg_out != z))
         {
-          // capture one V-cycle (all levels, halo exchanges on the second stream included)
           const long long l0 = ctx->launches;
           cudaGraph_t graph = nullptr;
           CU (cudaStreamBeginCapture (ctx->stream, cudaStreamCaptureModeThreadLocal));
-          const int rc = mg_vcycle (ctx, ctx->mg_in, z);
+          rc = cycle ();
           const cudaError_t ce = cudaStreamEndCapture (ctx->stream, &graph);
           if (rc || ce != cudaSuccess || !graph)
             {
@@ -1868,12 +1885,12 @@ precond_apply (pf_ctx *ctx, const double *v, double *z)
         }
       CU (cudaGraphLaunch (ctx->mg_graph, ctx->stream));
       ctx->launches += ctx->mg_graph_launches;
-      return PF_OK;
     }
-  if (ctx->precond == 1 && ctx->mg_ready && ctx->coarse)
-    return mg_vcycle (ctx, v, z);
-  k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (ctx->n_local_dofs, ctx->diag, v, z);
-  KCHECK ();
+  if (lowp)
+    {
+      k_convert<float, double><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->f_x, z);
+      KCHECK ();
+    }
   return PF_OK;
 }
 
@@ -2850,6 +2867,17 @@ pf_set_multigrid_coupling (pf_ctx *ctx, int coupled)
     return PF_BAD_ARG;
   for (pf_ctx *c = ctx; c; c = c->coarse)
     c->mg_uncoupled = coupled == 0;
+  return PF_OK;
+}
+
+// The multigrid V-cycle as one CUDA graph launch (see precond_apply).  [collective: the same on every rank]
+int
+pf_set_multigrid_graph (pf_ctx *ctx, int on)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  ctx->mg_use_graph = on != 0;
+  ctx->mg_graph_valid = false;
   return PF_OK;
 }
 

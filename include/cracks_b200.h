@@ -238,6 +238,10 @@ int pf_set_deterministic (pf_ctx *ctx, int on);
  * preconditioner is block diagonal like the reference's BlockDiagonalPreconditioner (cracks.cc:2717-2740) and a
  * smoother application neither stages nor interpolates the state U.  The Krylov operator is not affected. */
 int pf_set_multigrid_coupling (pf_ctx *ctx, int coupled);
+/* The multigrid V-cycle as ONE CUDA graph launch (captured after every pf_setup_jacobian, halo exchanges and NCCL
+ * calls included): on several GPUs a cycle is bound by the host's launch rate (about 200 launches and 20-30 NCCL calls
+ * on levels of a few cell layers per rank).  Default off; PF_MG_GRAPH=1 switches it on at pf_create.  [collective] */
+int pf_set_multigrid_graph (pf_ctx *ctx, int on);
 /* Restart length of GMRES (deal.II's SolverGMRES default keeps 28 basis vectors,
  * cracks.cc:2764; this library's default is 30).  Ill-conditioned small 2-D
  * problems, which the reference hands to a sparse direct solver (2750-2759),
