@@ -2330,7 +2330,7 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
   CU (cudaStreamSynchronize (ctx->stream));
   return PF_OK;
 }
-// EXPERIMENTAL (not yet run on a GPU): context on a locally refined mesh given by flat tables
+// context on a locally refined mesh given by flat tables (GPU suite: tests/test_gpu_forest.py)
 int
 create_forest_impl (const pf_forest_mesh *fm, const pf_params *params, int device, pf_ctx **out)
 {

@@ -1,8 +1,8 @@
 // pf_forest.cuh -- kernels for locally refined (forest) meshes with hanging nodes.
 //
-// EXPERIMENTAL: written against the CPU oracle's formulation (oracle/adaptive_oracle.py, which
-// reproduces the reference's sneddon_2d_1 / miehe_shear_1 / hetero_3d_1 goldens) but not yet run
-// on a GPU; only reachable through pf_create_forest.  The box-mesh paths do not use this file.
+// Written against the CPU oracle's formulation (oracle/adaptive_oracle.py, which
+// reproduces the reference's sneddon_2d_1 / miehe_shear_1 / hetero_3d_1 goldens); on the GPU the same goldens are
+// reproduced by tests/test_gpu_forest.py.  Only reachable through pf_create_forest[_distributed].  The box-mesh paths do not use this file.
 //
 // The reference resolves hanging-node constraints inside distribute_local_to_global
 // (cracks.cc:2439-2464) with the AffineConstraints built at 1630-1642.  Here they are applied

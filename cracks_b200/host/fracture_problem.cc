@@ -709,7 +709,7 @@ FracturePhaseFieldProblem::run ()
   pcout_ << "Finishing time step loop: " << finishing_timestep_loop << std::endl;
 }
 
-// ---- forest path (EXPERIMENTAL: device side not yet run on a GPU) ---------------------------------
+// ---- forest path (locally refined meshes) -----------------------------------------
 
 long long
 FracturePhaseFieldProblem::n_nodes () const

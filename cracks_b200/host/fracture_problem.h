@@ -59,7 +59,7 @@ public:
   unsigned total_linear_iterations () const { return total_linear_its_; }
   // knobs that are not part of the reference's .prm surface
   int device = 0;
-  // EXPERIMENTAL: run the Miehe tests with `Adaptive refinement cycles` > 0 on the host forest and follow
+  // run the Miehe tests with `Adaptive refinement cycles` > 0 on the host forest and follow
   // refine_mesh() (phase-field flags, level cap, solution transfer, redo of the step) instead of stopping
   // where the mesh would change
   bool adaptive_forest = false;
@@ -78,7 +78,7 @@ private:
   void write_statistics () const;
   void output_results (); // cracks.cc:3142-3258
   bool miehe () const { return test_case == "miehe tension" || test_case == "miehe shear"; }
-  // EXPERIMENTAL (device side not yet run on a GPU): Sneddon 2-D with local pre-refinement
+  // forest path (GPU suite: tests/test_gpu_forest.py): Sneddon 2-D with local pre-refinement
   // / refinement cycles on the host forest, strategy `fixed preref sneddon`
   bool use_forest () const { return forest_ != nullptr; }
   bool hetero () const { return test_case == "multiple het"; }

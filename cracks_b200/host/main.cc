@@ -31,7 +31,7 @@ main (int argc, char *argv[])
           else if (!std::strcmp (argv[i], "--no-output"))
             write_output = false; // skip the .vtu files of output_results() (benchmark-sized runs)
           else if (!std::strcmp (argv[i], "--adaptive"))
-            adaptive = true; // follow refine_mesh() on the host forest (experimental)
+            adaptive = true; // follow refine_mesh() on the host forest
           else if (!std::strcmp (argv[i], "--source-dir") && i + 1 < argc)
             source_dir = argv[++i]; // where test.pgm lives (multiple het)
           else

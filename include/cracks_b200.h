@@ -100,12 +100,12 @@ int pf_get_layout (const pf_ctx *ctx, pf_local_layout *out);
  * 1180); cell_* pointers may be NULL. */
 int pf_slab_layout (const pf_mesh *mesh, int rank, int nranks, pf_local_layout *out, int *cell_begin,
                     int *cell_end, int *own_cell_begin, int *own_cell_end);
-/* EXPERIMENTAL (written against the hanging-node oracle, not yet run on a GPU): a locally refined
+/* A locally refined
  * mesh as flat tables, the output of the host forest (cracks_b200/host/forest.h) that stands in for
  * the reference's p4est triangulation after refine_mesh() (cracks.cc:3895-4163).  All cells are
  * axis-aligned; a cell's level selects its edge lengths.  Hanging nodes (make_hanging_node_constraints,
- * 1630-1634) are constrained to the mean of their 2 (edge) or 4 (face) parents.  Single rank, Jacobi
- * preconditioner; Dirichlet rows come from pf_set_constraints, initial values from pf_set_state. */
+ * 1630-1634) are constrained to the mean of their 2 (edge) or 4 (face) parents.  Jacobi preconditioner;
+ * several GPUs: pf_create_forest_distributed.  Dirichlet rows come from pf_set_constraints, initial values from pf_set_state. */
 typedef struct
 {
   int dim;
@@ -304,7 +304,7 @@ int pf_load (pf_ctx *ctx, double *load_x, double *load_y);
 /* set_initial_bc() for arbitrary Dirichlet data (cracks.cc:2700-2707): writes values[dof] (host, block
  * layout) into the solution on every displacement dof whose Dirichlet bit is set (pf_set_constraints). */
 int pf_set_dirichlet_values (pf_ctx *ctx, const double *values);
-/* compute_load() on a forest mesh (EXPERIMENTAL, see pf_create_forest): `cells` lists the cells whose top
+/* compute_load() on a forest mesh (see pf_create_forest): `cells` lists the cells whose top
  * edge lies on boundary id 3. */
 int pf_load_cells (pf_ctx *ctx, const int64_t *cells, int64_t n_cells, double *load_x, double *load_y);
 /* min over the owned phase-field dofs: the indicator refine_mesh() tests

@@ -14,8 +14,8 @@ for s in $steps; do
   case $s in
     tests)        # the gating suite
       timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 ;;
-    experimental) # forest / hanging-node device path, written in round 1 without a GPU at hand
-      PF_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_forest.py -x -q 2>&1 | tail -30 ;;
+    forest)       # forest / hanging-node device path (part of `tests` as well)
+      timeout 600 python -m pytest tests/test_gpu_forest.py -x -q 2>&1 | tail -30 ;;
     bench)
       timeout 600 python bench.py --steps 50 --warmup 10 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
       cat gpurun_out/bench_n1.json ;;
