@@ -25,7 +25,8 @@ for s in $steps; do
         timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
           --master-port 29617 bench.py --gpus $n --steps 50 --warmup 10 2> gpurun_out/bench_n$n.err | tail -1 | tee gpurun_out/bench_n$n.json
       done ;;
-    variants)     # A/B of apply-kernel variants prepared offline: 16 = v4 default (222 regs, 8 warps/SM),
+    variants)     # needs a tuning build (make -C cracks_b200/csrc TUNING=1).  Measured in round 2 (profiles/r2_variants_ab.json):
+                  # every variant below is slower than 16.  A/B of apply-kernel variants: 16 = default, 23 = v4,
                   # 17 / 18 = v4 with __launch_bounds__ (64, 6 / 5): 168 registers (12 / 10 warps/SM, 164 / 256 B spills),
                   # 20 / 21 = v4 with __maxnreg__ (200 / 184): 10 warps/SM, 56 / 176 B spills,
                   # 19 = v5 (y-collapse staged in shared memory: 178 registers, no spills, 54 KB per CTA -> 8 warps/SM)
