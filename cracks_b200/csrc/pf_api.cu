@@ -113,6 +113,7 @@ struct pf_ctx
   int device = 0, rank = 0, nranks = 1;
   int own_cell_begin = 0, own_cell_end = 0;
   cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaStream_t launch_stream = nullptr; // tiled apply kernels go here instead of `stream` (boundary layers, see apply_dev)
   cudaEvent_t ev_x = nullptr, ev_halo = nullptr;
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_up[32] = {}, ev_done[32] = {};
@@ -201,6 +202,7 @@ struct pf_ctx
   int force_generic = 0;       // pf_debug_force_generic: the thread-per-cell second implementation
   int no_iso = 0;              // pf_debug_disable_iso: general (anisotropic) code path on cubic cells
   bool no_overlap = false;     // PF_NO_OVERLAP: halo exchange not overlapped with the interior layers (A/B)
+  bool boundary_seq = false;   // PF_BOUNDARY_SEQ: boundary layers after the interior on the compute stream (A/B, as in round 1)
   bool split_boundary = false; // PF_SPLIT_BOUNDARY: two boundary launches of a middle slab instead of one (A/B)
   bool mg_use_graph = false;   // PF_MG_GRAPH=1
   bool mg_uncoupled = false;   // pf_set_multigrid_coupling (ctx, 0): the smoother operator without its (phi,u) block
@@ -592,11 +594,12 @@ launch_apply3d_v4 (pf_ctx *ctx, const double *x, double *y)
       const unsigned grid = (unsigned) tiles_of_colour (colour, tiles_x, tiles_y, tiles_z);
       if (grid == 0)
         continue;
+      const cudaStream_t st = ctx->launch_stream ? ctx->launch_stream : ctx->stream;
       if (iso)
-        k_apply3d_v4<TX, TY, TZ, MINB, NQ, true><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+        k_apply3d_v4<TX, TY, TZ, MINB, NQ, true><<<grid, T::NT, T::smem_bytes, st>>> (
           g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
       else
-        k_apply3d_v4<TX, TY, TZ, MINB, NQ, false><<<grid, T::NT, T::smem_bytes, ctx->stream>>> (
+        k_apply3d_v4<TX, TY, TZ, MINB, NQ, false><<<grid, T::NT, T::smem_bytes, st>>> (
           g, ctx->p, ctx->k3, tiles_x, tiles_y, x, ctx->sol, ctx->pt, ctx->mask, y);
       KCHECK ();
     }
@@ -771,8 +774,8 @@ launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename L
       const unsigned grid = (unsigned) tiles_of_colour (colour, tiles_x, tiles_y, tiles_z);
       if (grid == 0)
         continue;
-      k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED><<<grid, T::NT, smem, ctx->stream>>> (g, k6, tiles_x, tiles_y, layer0, x,
-                                                                                         sol, ctx->mask, coef, y);
+      k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED><<<grid, T::NT, smem, ctx->launch_stream ? ctx->launch_stream : ctx->stream>>> (
+        g, k6, tiles_x, tiles_y, layer0, x, sol, ctx->mask, coef, y);
       KCHECK ();
     }
   return PF_OK;
@@ -1008,11 +1011,17 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
                        && (approx || ctx->apply_variant == 3 || ctx->apply_variant == 16) && hi_b > lo_b;
   if (overlap)
     {
+      // y is initialised first: the boundary layers are evaluated on the communication stream, right behind the
+      // exchange they depend on and CONCURRENTLY with the interior layers on the compute stream (they fill the
+      // partial last wave of the interior launch; round 1 ran them after it)
+      k_apply_init<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
+      KCHECK ();
       CU (cudaEventRecord (ctx->ev_x, ctx->stream));
       CU (cudaStreamWaitEvent (ctx->comm_stream, ctx->ev_x, 0));
       if ((rc = halo_exchange (ctx, x, ctx->nc, ctx->comm_stream)))
         return rc;
-      CU (cudaEventRecord (ctx->ev_halo, ctx->comm_stream));
+      if (ctx->boundary_seq || ctx->deterministic) // (deterministic mode: no two launches may add to one node plane at once)
+        CU (cudaEventRecord (ctx->ev_halo, ctx->comm_stream));
     }
   else if ((rc = halo_exchange (ctx, x, ctx->nc)))
     return rc;
@@ -1026,8 +1035,11 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
     }
   else
     {
-      k_apply_init<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
-      KCHECK ();
+      if (!overlap)
+        {
+          k_apply_init<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->diag, ctx->mask, y);
+          KCHECK ();
+        }
       if (ctx->force_generic)
         {
           k_apply_generic<3><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
@@ -1054,21 +1066,36 @@ apply_dev (pf_ctx *ctx, double *x, double *y, bool approx = false)
                 ctx->range_stride = 1;
                 return r;
               };
-              if ((rc = run (lo_b, hi_b)))
-                return rc;
-              CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
-              if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !ctx->split_boundary)
-                {
+              auto boundary = [&]() -> int {
+                if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !ctx->split_boundary)
                   // a slab in the middle: its two boundary layers in ONE launch (each alone is less than a wave)
-                  if ((rc = run (g.cell_begin, g.cell_end, g.cell_end - 1 - g.cell_begin)))
+                  return run (g.cell_begin, g.cell_end, g.cell_end - 1 - g.cell_begin);
+                int r = PF_OK;
+                if (ctx->rank > 0 && (r = run (g.cell_begin, lo_b)))
+                  return r;
+                if (ctx->rank < ctx->nranks - 1 && (r = run (hi_b, g.cell_end)))
+                  return r;
+                return PF_OK;
+              };
+              if (ctx->boundary_seq || ctx->deterministic)
+                {
+                  if ((rc = run (lo_b, hi_b)))
+                    return rc;
+                  CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
+                  if ((rc = boundary ()))
                     return rc;
                 }
               else
                 {
-                  if (ctx->rank > 0 && (rc = run (g.cell_begin, lo_b)))
+                  ctx->launch_stream = ctx->comm_stream; // behind the exchange, in stream order
+                  rc = boundary ();
+                  ctx->launch_stream = nullptr;
+                  if (rc)
                     return rc;
-                  if (ctx->rank < ctx->nranks - 1 && (rc = run (hi_b, g.cell_end)))
+                  CU (cudaEventRecord (ctx->ev_halo, ctx->comm_stream));
+                  if ((rc = run (lo_b, hi_b)))
                     return rc;
+                  CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
                 }
               if (ctx->profiling)
                 {
@@ -1672,19 +1699,22 @@ apply_lowp (pf_ctx *ctx, float *x, float *y)
   const int hi_b = g.cell_end - (ctx->rank < ctx->nranks - 1 ? 1 : 0);
   const bool no_overlap = ctx->no_overlap;
   const bool overlap = !no_overlap && ctx->nranks > 1 && hi_b > lo_b;
+  // boundary layers on the communication stream, concurrent with the interior (see apply_dev); needs the v6 launcher
+  const bool concurrent = overlap && !ctx->boundary_seq && !ctx->deterministic && ctx->apply_variant == 16 && v6_possible (ctx) && ctx->coef2_32;
+  const long long nl = g.n_local_nodes;
+  k_apply_init_r<float><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->f_idiag, ctx->mask, y);
+  KCHECK ();
   if (overlap)
     {
       CU (cudaEventRecord (ctx->ev_x, ctx->stream));
       CU (cudaStreamWaitEvent (ctx->comm_stream, ctx->ev_x, 0));
       if ((rc = halo_exchange (ctx, x, 4, ctx->comm_stream)))
         return rc;
-      CU (cudaEventRecord (ctx->ev_halo, ctx->comm_stream));
+      if (!concurrent)
+        CU (cudaEventRecord (ctx->ev_halo, ctx->comm_stream));
     }
   else if ((rc = halo_exchange (ctx, x, 4)))
     return rc;
-  const long long nl = g.n_local_nodes;
-  k_apply_init_r<float><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, x, ctx->f_idiag, ctx->mask, y);
-  KCHECK ();
   auto run = [&](int c0, int c1, int stride = 1) -> int {
     ctx->range_begin = c0;
     ctx->range_end = c1;
@@ -1696,16 +1726,33 @@ apply_lowp (pf_ctx *ctx, float *x, float *y)
   };
   if (!overlap)
     return launch_apply3d_mg<16, 4, 1, 8> (ctx, x, y);
+  auto boundary = [&]() -> int {
+    if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !ctx->split_boundary)
+      return run (g.cell_begin, g.cell_end, g.cell_end - 1 - g.cell_begin);
+    int r = PF_OK;
+    if (ctx->rank > 0 && (r = run (g.cell_begin, lo_b)))
+      return r;
+    if (ctx->rank < ctx->nranks - 1 && (r = run (hi_b, g.cell_end)))
+      return r;
+    return PF_OK;
+  };
+  if (concurrent)
+    {
+      ctx->launch_stream = ctx->comm_stream;
+      rc = boundary ();
+      ctx->launch_stream = nullptr;
+      if (rc)
+        return rc;
+      CU (cudaEventRecord (ctx->ev_halo, ctx->comm_stream));
+      if ((rc = run (lo_b, hi_b)))
+        return rc;
+      CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
+      return PF_OK;
+    }
   if ((rc = run (lo_b, hi_b)))
     return rc;
   CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_halo, 0));
-  if (ctx->rank > 0 && ctx->rank < ctx->nranks - 1 && !ctx->split_boundary)
-    return run (g.cell_begin, g.cell_end, g.cell_end - 1 - g.cell_begin);
-  if (ctx->rank > 0 && (rc = run (g.cell_begin, lo_b)))
-    return rc;
-  if (ctx->rank < ctx->nranks - 1 && (rc = run (hi_b, g.cell_end)))
-    return rc;
-  return PF_OK;
+  return boundary ();
 }
 
 // float copies of what a level's V-cycle reads; called once per pf_setup_jacobian and level
@@ -2178,6 +2225,7 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
   // A/B switches for measurements: read once per context, here
   ctx->no_overlap = getenv ("PF_NO_OVERLAP") != nullptr;
   ctx->split_boundary = getenv ("PF_SPLIT_BOUNDARY") != nullptr;
+  ctx->boundary_seq = getenv ("PF_BOUNDARY_SEQ") != nullptr;
   ctx->mg_use_graph = getenv ("PF_MG_GRAPH") && atoi (getenv ("PF_MG_GRAPH")) == 1;
 #ifdef PF_TUNING_VARIANTS
   if (getenv ("PF_APPLY_VARIANT"))
