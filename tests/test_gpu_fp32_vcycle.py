@@ -11,12 +11,14 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(pf, refine, bits, steps=0):
+def _run(pf, refine, bits, steps=0, jacobian_bits=64):
     from cracks_b200.api import mesh_diameter
     g = json.load(open(os.path.join(HERE, "golden", "sneddon_3d_1.json")))
     mesh = pf.sneddon_mesh(3, refine)
     ctx = pf.PhaseFieldContext(mesh, pf.sneddon_params(mesh, kappa_of_h=(lambda hh: 0.0) if refine == 0 else (lambda hh: 1e-8 * hh)))
     ctx.set_multigrid_precision(bits)
+    if jacobian_bits != 64:
+        ctx.set_jacobian_precision(jacobian_bits)
     drv = pf.SneddonDriver(ctx, pressure=lambda t: g["prm"]["pressure"], max_no_timesteps=steps,
                            newton_lower_bound=g["prm"]["newton_lower_bound"], max_newton=g["prm"]["newton_max_steps"],
                            max_line_search=g["prm"]["line_search_max_steps"], gmres_max_it=300)
@@ -47,3 +49,27 @@ def test_fp32_vcycle_is_as_good_a_preconditioner(pf, refine):
     assert n32 == n64
     assert l32 <= 1.15 * l64 + 3
     assert np.linalg.norm(z32 - z64) <= 1e-3 * np.linalg.norm(z64)
+
+
+def test_kat1_golden_with_the_fp32_jacobian(pf):
+    """Inexact Newton (pf_set_jacobian_precision 32 + FP32 V-cycle): the Krylov operator is the packed-FP32 27-point
+    apply, the residual that defines the Newton fixed point stays FP64 -- the reference's golden energies of all four
+    time steps must come out as with the exact operator (tests/sneddon_3d_1.mpirun=4.statistics)."""
+    g, stats, _, _, _ = _run(pf, 0, 32, steps=3, jacobian_bits=32)
+    assert len(stats) == 4
+    for got, ref in zip(stats, g["statistics"]):
+        assert got["crack"] == pytest.approx(ref["crack"], rel=1e-8)
+        assert got["bulk"] == pytest.approx(ref["bulk"], rel=1e-7 if got["step"] == 0 else 1e-6)
+
+
+def test_inexact_newton_at_refine2_matches_the_exact_run(pf):
+    """275 684 DoF, four multigrid levels: same Newton history length and energies with the FP32 Jacobian, and the
+    CPU stand-in's energies (tests/golden/sneddon_3d_refine2_cpu.json) to 1e-6"""
+    _, s64, n64, l64, _ = _run(pf, 2, 64)
+    _, s32, n32, l32, _ = _run(pf, 2, 32, jacobian_bits=32)
+    cpu = json.load(open(os.path.join(HERE, "golden", "sneddon_3d_refine2_cpu.json")))["statistics"][0]
+    print("Newton", n64, n32, "GMRES", l64, l32)
+    assert n32 <= n64 + 1
+    assert s32[0]["crack"] == pytest.approx(s64[0]["crack"], rel=1e-9)
+    assert s32[0]["crack"] == pytest.approx(cpu["crack"], rel=1e-6)
+    assert s32[0]["bulk"] == pytest.approx(cpu["bulk"], rel=1e-6)
