@@ -165,15 +165,7 @@ template <int TX, int TY, int NQ = 3, int W = 1, bool COUPLED = true> struct Til
   static constexpr int NF = COUPLED ? 8 : 4;  // staged nodal fields: x_u (3), x_phi / 8, u (3), phi / 8
   static constexpr int NFZ = COUPLED ? 7 : 4; // fields with a z-difference chain: all but phi
   static constexpr int NQP = NQ * NQ * NQ;
-  // y tile: one private copy per warp (its RW cell rows touch RW + 1 node rows), so that two cells that add to the same
-  // node are always lanes of ONE warp and __syncwarp orders them; the node row two warps share is summed by the flush.
-  static_assert ((32 * W) % TX == 0 && NT % 32 == 0, "a warp covers whole cell rows");
-  static constexpr int RW = 32 * W / TX;      // cell rows per warp
-  static constexpr int NWARP = NT / 32;
-  static_assert (RW * NWARP == TY, "warps tile the cell rows");
-  static constexpr int NNW = 2 * (RW + 1) * PX; // entries of one component of a warp's y tile: [vz][RW + 1][PX]
-  static constexpr size_t ytile = (size_t) NWARP * 4 * NNW;
-  static constexpr size_t scratch = (NFZ * NC2 > ytile) ? (size_t) NFZ * NC2 : ytile; // DZ, then the y tiles
+  static constexpr size_t scratch = (NFZ * NC2 > 4 * NN) ? (size_t) NFZ * NC2 : (size_t) 4 * NN; // DZ, then the y tile
   static constexpr size_t smem_elems = (size_t) NQ * NF * NC2 + (size_t) NFZ * NQ * NXC + NXC + scratch;
   // coefficient scalars (wg and c2 of every cell) of one tile, and of one Gauss plane of it (one bulk copy)
   static constexpr size_t coef_per_tile = (size_t) NQP * TX * TY * 2;
@@ -291,7 +283,7 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
   using S = typename L::S;
   constexpr int W = L::W;
   using T = Tile3v6<TX, TY, NQ, W, COUPLED>;
-  constexpr int PX = T::PX, NC2 = T::NC2, NXC = T::NXC, NF = T::NF, NT = T::NT, RW = T::RW, NNW = T::NNW;
+  constexpr int NN = T::NN, PX = T::PX, NC2 = T::NC2, NXC = T::NXC, NF = T::NF, NT = T::NT;
   constexpr unsigned plane_bytes = (unsigned) (T::coef_per_plane * sizeof (S));
   constexpr bool CEN = NQ == 3; // the 3-point rule has a centre point and uses the closed-form Laplacian
   constexpr int NCQ = CEN ? 3 : 4; // components whose fluxes go through the quadrature
@@ -300,8 +292,7 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
   const bool valid = (cx0 + W * tx < g.n[0]) && (cy0 + ty < g.n[1]) && (cz0 < g.cell_end);
   const bool right_valid = W == 1 || (cx0 + W * tx + 1 < g.n[0]); // W == 2: the second cell of the pair exists
   const int c00 = W * tx + PX * ty;  // first node column of the thread in AZ; (x-node, cell row) in BZ alike
-  // the thread's corner in its warp's private y tile [c][vz][RW + 1][PX]
-  S *ywarp = ys + (size_t) (tid / 32) * 4 * NNW + W * tx + PX * (ty % RW);
+  const int nbase = W * tx + T::SY * ty;
   const R lam2 = (R) k.lam2, nbeta = (R) -k.beta;
   const R es[3] = {-Sq, CEN ? (R) 0 : Sq, Sq};
   const R kl1 = (R) k.kl[0], kl2 = (R) k.kl[1], kl3 = (R) k.kl[2];
@@ -503,9 +494,9 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
                 }
             }
         }
-      // ---- stage 4: plane -> the warp's y tile.  Every pair of cells that adds to one node is a pair of lanes of this
-      // warp: the writes to a thread's first node column(s) (phase A), to its last one (phase B, the first column of
-      // the next thread) and of the two vy phases are ordered with __syncwarp alone, no block barrier
+      // ---- stage 4: plane -> shared y tile.  x-neighbours are lanes of one warp: the writes to a thread's first
+      // node column(s) (phase A) and to its last one (phase B, the first column of the next thread) are ordered with
+      // __syncwarp; y-neighbours may sit in other warps: block barriers between the vy phases
       const R omez = (R) 1 - ez, opez = (R) 1 + ez;
 #pragma unroll
       for (int vy = 0; vy < 2; ++vy)
@@ -531,27 +522,27 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
                     const R v = (vz == 0) ? fma_r (a, omez, -d) : fma_r (a, opez, d);
                     val[vx][c] = right_valid ? v : L::drop_right (v);
                   }
-              S *yn = ywarp + PX * vy + (RW + 1) * PX * vz;
+              S *yn = ys + nbase + T::SY * vy + T::SZ * vz;
               if (valid)
                 {
 #pragma unroll
                   for (int c = 0; c < 4; ++c)
-                    L::add_a (yn + c * NNW, val[0][c], val[1][c]);
+                    L::add_a (yn + c * NN, val[0][c], val[1][c]);
                 }
               __syncwarp ();
               if (valid)
                 {
 #pragma unroll
                   for (int c = 0; c < 4; ++c)
-                    L::add_b (yn + c * NNW, val[1][c]);
+                    L::add_b (yn + c * NN, val[1][c]);
                 }
               __syncwarp ();
             }
+          __syncthreads ();
         }
       if (NQ == 3 && qz == 0)
         {
-          // once every thread is done with plane 0, buffer 0 is free for the records of plane 2
-          __syncthreads ();
+          // every thread has passed the barrier above: buffer 0 is free for the records of plane 2
 #ifndef PF_EMULATION
           if (tid == 0)
             {
@@ -582,13 +573,13 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
   using T = Tile3v6<TX, TY, NQ, W, COUPLED>;
   using V4 = typename Quad<V>::type;
   constexpr int NN = T::NN, NT = T::NT, NX = T::NX, PX = T::PX, NY = T::NY, NC2 = T::NC2, NXC = T::NXC, NF = T::NF,
-                NFZ = T::NFZ, RW = T::RW, NWARP = T::NWARP, NNW = T::NNW;
+                NFZ = T::NFZ;
   extern __shared__ __align__ (16) unsigned char smem_raw[];
   S *AZ = reinterpret_cast<S *> (smem_raw); // [NQ][NF][NC2]
   S *BZ = AZ + NQ * NF * NC2;               // [NFZ][NQ][NXC]
   S *BR = BZ + NFZ * NQ * NXC;              // [NXC]: y-difference of the z-difference of x's phi
   S *DZ = BR + NXC;                         // [NFZ][NC2], stage 1 -> 2 only
-  S *ys = DZ;                               // [NWARP][4][2][RW + 1][PX], aliases DZ
+  S *ys = DZ;                               // [4][NN], aliases DZ
   constexpr size_t off_cf = (T::smem_elems * sizeof (S) + 15) / 16 * 16, off_mbar = off_cf + 2 * T::coef_per_plane * sizeof (S);
   S *CF = reinterpret_cast<S *> (smem_raw + off_cf);                                       // [2][NQ*NQ][NT][2 W]
   unsigned long long *mbar = reinterpret_cast<unsigned long long *> (smem_raw + off_mbar); // one per Gauss plane
@@ -682,14 +673,13 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
         }
     }
   __syncthreads ();
-  for (int i = tid; i < (int) T::ytile; i += NT)
+  for (int i = tid; i < 4 * NN; i += NT)
     ys[i] = 0;
   __syncthreads ();
 
   tile_cells_v6<R, TX, TY, NQ, COUPLED> (g, k, tid, cx0, cy0, cz0, AZ, BZ, BR, coef_tile, CF, mbar, ys);
 
-  // ---- flush the y tiles (the node row two warps share is the sum of both copies) -----------------
-  __syncthreads ();
+  // ---- flush the y tile -----------------------------------------------------------
   for (int i = tid; i < NN; i += NT)
     {
       const int ix = i % PX, iy = (i / PX) % NY, iz = i / (PX * NY);
@@ -698,14 +688,10 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
         {
           const long long n = gx + (long long) nnx * gy + pstride * (gz - g.plane_begin);
           const uint8_t m = mask[n];
-          const int w1 = iy < NY - 1 ? iy / RW : NWARP - 1, lr1 = iy - w1 * RW; // the warp whose cell row iy (or the last one) it is
-          const bool two = iy > 0 && iy < NY - 1 && iy % RW == 0;               // also the top row of the warp below
-          const S *p1 = ys + (size_t) w1 * 4 * NNW + iz * (RW + 1) * PX + lr1 * PX + ix;
-          const S *p0 = ys + (size_t) (w1 - 1) * 4 * NNW + iz * (RW + 1) * PX + RW * PX + ix;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             if (!((m >> c) & 1))
-              atomicAdd (&y[4 * n + c], (V) (two ? p1[c * NNW] + p0[c * NNW] : p1[c * NNW]));
+              atomicAdd (&y[4 * n + c], (V) ys[c * NN + i]);
         }
     }
 }
