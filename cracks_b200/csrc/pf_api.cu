@@ -198,6 +198,7 @@ struct pf_ctx
   float *coef2_32 = nullptr;
   int jacobian_bits = 64;      // precision of the Krylov operator: 64 = exact, 32 = inexact-Newton Jacobian in FP32
   // tuning / debugging switches (per context; the environment is read once, by pf_create)
+  int v6_mode = getenv ("PF_V6_MODE") ? atoi (getenv ("PF_V6_MODE")) : 0; // coefficient feed / CTAs per SM of v6 (launch_apply3d_v6)
   int apply_variant = 16;      // 16 = default exact kernel; other numbers only in a PF_TUNING_VARIANTS build
   int force_generic = 0;       // pf_debug_force_generic: the thread-per-cell second implementation
   int no_iso = 0;              // pf_debug_disable_iso: general (anisotropic) code path on cubic cells
@@ -741,14 +742,14 @@ v6_refresh_coefficients (pf_ctx *ctx, typename Lane<R>::S **buf)
 }
 
 // R = arithmetic of the cell walk, V = type of the global vectors, NQ = 3 (exact rule) or 2 (smoother operator)
-template <typename R, typename V, int NQ, int MINB, bool COUPLED = true>
+template <typename R, typename V, int NQ, int MINB, bool COUPLED, int CFM>
 int
-launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename Lane<R>::S *coef)
+launch_apply3d_v6_feed (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename Lane<R>::S *coef)
 {
   using S = typename Lane<R>::S;
   constexpr int TX = V6Shape<R>::TX, TY = V6Shape<R>::TY, W = Lane<R>::W;
   using T = Tile3v6<TX, TY, NQ, W, COUPLED>;
-  constexpr size_t smem = (T::smem_elems * sizeof (S) + 15) / 16 * 16 + 2 * T::coef_per_plane * sizeof (S) + 32;
+  constexpr size_t smem = T::template smem_bytes<S> (CFM);
   Grid g = ctx->g;
   const int layer0 = g.cell_begin;
   if (ctx->range_begin >= 0)
@@ -762,9 +763,9 @@ launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename L
   static const char attr_tag = 0;
   if (ctx->attr_done.insert (&attr_tag).second)
     {
-      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED, CFM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int) smem));
-      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      CU (cudaFuncSetAttribute (k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED, CFM>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                 100));
     }
   const K6 k6 = make_k6 (ctx);
@@ -774,11 +775,29 @@ launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename L
       const unsigned grid = (unsigned) tiles_of_colour (colour, tiles_x, tiles_y, tiles_z);
       if (grid == 0)
         continue;
-      k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED><<<grid, T::NT, smem, ctx->launch_stream ? ctx->launch_stream : ctx->stream>>> (
+      k_apply3d_v6<R, V, NQ, TX, TY, MINB, COUPLED, CFM><<<grid, T::NT, smem, ctx->launch_stream ? ctx->launch_stream : ctx->stream>>> (
         g, k6, tiles_x, tiles_y, layer0, x, sol, ctx->mask, coef, y);
       KCHECK ();
     }
   return PF_OK;
+}
+
+// ctx->v6_mode (A/B switch, PF_V6_MODE): how the coefficient records are fed and how many CTAs per SM the kernel is built for
+template <typename R, typename V, int NQ, int MINB, bool COUPLED = true>
+int
+launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename Lane<R>::S *coef)
+{
+  switch (ctx->v6_mode)
+    {
+    case 1:
+      return launch_apply3d_v6_feed<R, V, NQ, 5, COUPLED, 1> (ctx, x, sol, y, coef);
+    case 2:
+      return launch_apply3d_v6_feed<R, V, NQ, 6, COUPLED, 1> (ctx, x, sol, y, coef);
+    case 3:
+      return launch_apply3d_v6_feed<R, V, NQ, 5, COUPLED, 2> (ctx, x, sol, y, coef);
+    default:
+      return launch_apply3d_v6_feed<R, V, NQ, MINB, COUPLED, 0> (ctx, x, sol, y, coef);
+    }
 }
 
 // the tiled kernel the library uses by default (exact 27-point rule, or the

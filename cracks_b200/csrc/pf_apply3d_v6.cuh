@@ -57,6 +57,17 @@ __device__ __forceinline__ f32x2 &operator+= (f32x2 &a, f32x2 b) { a = a + b; re
 __device__ __forceinline__ f32x2 &operator-= (f32x2 &a, f32x2 b) { a = a - b; return a; }
 __device__ __forceinline__ f32x2 fma_r (f32x2 a, f32x2 b, f32x2 c) { f32x2 r; r.v = __ffma2_rn (a.v, b.v, c.v); return r; }
 
+template <typename T>
+__device__ __forceinline__ T
+v6_ldg (const T *p)
+{
+#ifndef PF_EMULATION
+  return __ldg (p);
+#else
+  return *p;
+#endif
+}
+
 // ---- how a thread sees the staging arrays: one cell (scalar R) or a pair of x-adjacent cells (f32x2) ---------------
 template <typename R> struct Lane
 {
@@ -65,6 +76,11 @@ template <typename R> struct Lane
   static __device__ __forceinline__ R ld (const S *p) { return p[0]; }        // node column c of the thread
   static __device__ __forceinline__ R ld1 (const S *p, R) { return p[1]; }    // node column c + 1
   static __device__ __forceinline__ void rec (const S *r, R &wg, R &c2) { wg = r[0], c2 = r[1]; }
+  static __device__ __forceinline__ void rec_g (const S *r, R &wg, R &c2) // the same record straight from global memory
+  {
+    const typename Pair<S>::type q = v6_ldg (reinterpret_cast<const typename Pair<S>::type *> (r));
+    wg = q.x, c2 = q.y;
+  }
   // y tile: phase A adds the contributions to the thread's first node column(s), phase B to its last one
   static __device__ __forceinline__ void add_a (S *p, R v0, R) { p[0] += v0; }
   static __device__ __forceinline__ void add_b (S *p, R v1) { p[1] += v1; }
@@ -84,6 +100,11 @@ template <> struct Lane<f32x2>
   static __device__ __forceinline__ void rec (const float *r, f32x2 &wg, f32x2 &c2)
   {
     const float4 q = *reinterpret_cast<const float4 *> (r); // (wg left, wg right, c2 left, c2 right)
+    wg = f32x2 (q.x, q.y), c2 = f32x2 (q.z, q.w);
+  }
+  static __device__ __forceinline__ void rec_g (const float *r, f32x2 &wg, f32x2 &c2)
+  {
+    const float4 q = v6_ldg (reinterpret_cast<const float4 *> (r));
     wg = f32x2 (q.x, q.y), c2 = f32x2 (q.z, q.w);
   }
   // the middle column c + 1 belongs to both cells of the pair: summed in the thread
@@ -170,6 +191,12 @@ template <int TX, int TY, int NQ = 3, int W = 1, bool COUPLED = true> struct Til
   // coefficient scalars (wg and c2 of every cell) of one tile, and of one Gauss plane of it (one bulk copy)
   static constexpr size_t coef_per_tile = (size_t) NQP * TX * TY * 2;
   static constexpr size_t coef_per_plane = (size_t) NQ * NQ * TX * TY * 2;
+  // shared memory of the kernel by coefficient feed (CFM, see k_apply3d_v6): staging arrays, record ring, mbarriers
+  static constexpr size_t ring_planes (int cfm) { return cfm == 0 ? 2 : (cfm == 2 ? 1 : 0); }
+  template <typename S> static constexpr size_t smem_bytes (int cfm)
+  {
+    return (smem_elems * sizeof (S) + 15) / 16 * 16 + ring_planes (cfm) * coef_per_plane * sizeof (S) + (cfm == 1 ? 0 : 32);
+  }
 };
 
 // constants of one launch, derived on the host from Phys / K3 (cubic cells: h = hx = hy = hz)
@@ -272,7 +299,7 @@ k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, cons
 // ---- stages 3 and 4 of the apply for one tile (contains block barriers: all threads of the CTA call it) ---
 // NQ = 3: the exact rule, G_c eps grad(dphi).grad(psi) in closed form.  NQ = 2: the under-integrated operator of the
 // multigrid smoother (preconditioner only), phi-gradient flux inside the quadrature.
-template <typename R, int TX, int TY, int NQ, bool COUPLED>
+template <typename R, int TX, int TY, int NQ, bool COUPLED, int CFM>
 __device__ __forceinline__ void
 tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const int cy0, const int cz0,
                const typename Lane<R>::S *__restrict__ AZ, const typename Lane<R>::S *__restrict__ BZ,
@@ -298,6 +325,15 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
   const R kl1 = (R) k.kl[0], kl2 = (R) k.kl[1], kl3 = (R) k.kl[2];
   const R wb = (R) (k.wvol * k.cge); // NQ == 2: weight of the phi-gradient flux (every point has JxW = h^3/8)
   const R half = (R) 0.5, two = (R) 2;
+  // CFM == 1: the records of the next row of points (qz, qy) are in flight in registers while this one is evaluated
+  const S *cg = coef_tile + (size_t) tid * 2 * W;
+  R wgN[NQ], c2N[NQ];
+  if (CFM == 1)
+    {
+#pragma unroll
+      for (int qx = 0; qx < NQ; ++qx)
+        L::rec_g (cg + (size_t) qx * NT * 2 * W, wgN[qx], c2N[qx]);
+    }
 
 #pragma unroll 1
   for (int qz = 0; qz < NQ; ++qz)
@@ -305,9 +341,10 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
       const R ez = (qz == 0) ? -Sq : ((CEN && qz == 1) ? (R) 0 : Sq);
       const S *Aq = AZ + qz * NF * NC2 + c00;
       // the coefficient records of this plane: buffer qz % 2, filled by the bulk copy that signals mbar[qz]
-      const S *cf = CF + (size_t) (qz & 1) * T::coef_per_plane + (size_t) tid * 2 * W;
+      const S *cf = CF + (size_t) (CFM == 0 ? (qz & 1) : 0) * T::coef_per_plane + (size_t) tid * 2 * W;
 #ifndef PF_EMULATION
-      v6_mbar_wait (mbar + qz, 0);
+      if (CFM != 1)
+        v6_mbar_wait (mbar + qz, 0);
 #endif
       // (phi,u) weight of the point classes of this plane: JxW k1
       const double wzk = (CEN ? k.wz[qz] : k.wvol) * k.k1;
@@ -338,9 +375,23 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
               const R ey = es[qy];
               const bool ceny = CEN && qy == 1;
               R wg3[3], c23[3];
+              if (CFM == 1)
+                {
+                  const int row = qz * NQ + qy + 1;
 #pragma unroll
-              for (int qx = 0; qx < NQ; ++qx)
-                L::rec (cf + (size_t) (qy * NQ + qx) * NT * 2 * W, wg3[qx], c23[qx]);
+                  for (int qx = 0; qx < NQ; ++qx)
+                    {
+                      wg3[qx] = wgN[qx], c23[qx] = c2N[qx];
+                      if (row < NQ * NQ)
+                        L::rec_g (cg + (size_t) (row * NQ + qx) * NT * 2 * W, wgN[qx], c2N[qx]);
+                    }
+                }
+              else
+                {
+#pragma unroll
+                  for (int qx = 0; qx < NQ; ++qx)
+                    L::rec (cf + (size_t) (qy * NQ + qx) * NT * 2 * W, wg3[qx], c23[qx]);
+                }
               // x-derivative (constant along x), y-derivative and z-derivative (linear in xi_x: P + ex R) of the
               // displacement-like fields f = 0..2 (x), 4..6 (U) and -- 2-point rule only -- of x's phi (f = 3)
               R dx[7], PxDy[7], RxDy[7], PxBz[7], RxBz[7];
@@ -539,8 +590,22 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
               __syncwarp ();
             }
           __syncthreads ();
+          if (CFM == 2 && vy == 0 && qz + 1 < NQ)
+            {
+              // single-slot ring: every thread has read this plane's records, the next plane can land on them
+#ifndef PF_EMULATION
+              if (tid == 0)
+                {
+                  v6_async_proxy_fence ();
+                  v6_bulk_load (CF, coef_tile + (size_t) (qz + 1) * T::coef_per_plane, plane_bytes, mbar + qz + 1);
+                }
+#else
+              for (int i = tid; i < (int) T::coef_per_plane; i += NT)
+                CF[i] = coef_tile[(size_t) (qz + 1) * T::coef_per_plane + i];
+#endif
+            }
         }
-      if (NQ == 3 && qz == 0)
+      if (CFM == 0 && NQ == 3 && qz == 0)
         {
           // every thread has passed the barrier above: buffer 0 is free for the records of plane 2
 #ifndef PF_EMULATION
@@ -562,7 +627,10 @@ tile_cells_v6 (const Grid &g, const K6 &k, const int tid, const int cx0, const i
 // V = type of the global vectors x, sol, y (FP64 for the Krylov operator, FP32 inside the FP32 V-cycle);
 // R = arithmetic type of the cell walk (double, float, or f32x2 = two cells per thread in packed FP32).
 // The z-collapse of stage 1 is done in V.
-template <typename R, typename V, int NQ, int TX, int TY, int MINB, bool COUPLED = true>
+// CFM = how the coefficient records reach the cell walk: 0 = two-plane ring in shared memory filled by TMA bulk copies one
+// Gauss plane ahead; 1 = no ring, each thread loads its own records one row of points ahead into registers (least
+// shared memory: more CTAs per SM); 2 = one-plane ring, refilled by TMA as soon as every thread has read the plane.
+template <typename R, typename V, int NQ, int TX, int TY, int MINB, bool COUPLED = true, int CFM = 0>
 __global__ void __launch_bounds__ (TX / Lane<R>::W * TY, MINB)
 k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__restrict__ x,
               const V *__restrict__ sol, const uint8_t *__restrict__ mask,
@@ -580,7 +648,8 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
   S *BR = BZ + NFZ * NQ * NXC;              // [NXC]: y-difference of the z-difference of x's phi
   S *DZ = BR + NXC;                         // [NFZ][NC2], stage 1 -> 2 only
   S *ys = DZ;                               // [4][NN], aliases DZ
-  constexpr size_t off_cf = (T::smem_elems * sizeof (S) + 15) / 16 * 16, off_mbar = off_cf + 2 * T::coef_per_plane * sizeof (S);
+  constexpr size_t off_cf = (T::smem_elems * sizeof (S) + 15) / 16 * 16,
+                   ring = (CFM == 0 ? 2 : (CFM == 2 ? 1 : 0)) * T::coef_per_plane, off_mbar = off_cf + ring * sizeof (S);
   S *CF = reinterpret_cast<S *> (smem_raw + off_cf);                                       // [2][NQ*NQ][NT][2 W]
   unsigned long long *mbar = reinterpret_cast<unsigned long long *> (smem_raw + off_mbar); // one per Gauss plane
 
@@ -591,17 +660,18 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
   const S *coef_tile = coef + ((size_t) ((cz0 - layer0) * tiles_y + by) * tiles_x + bx) * T::coef_per_tile;
   // the records of the first two Gauss planes start to arrive while x and U are staged
 #ifndef PF_EMULATION
-  if (tid == 0)
+  if (CFM != 1 && tid == 0)
     {
       for (int q = 0; q < NQ; ++q)
         v6_mbar_init (mbar + q);
       v6_mbar_init_fence ();
       constexpr unsigned plane_bytes = (unsigned) (T::coef_per_plane * sizeof (S));
       v6_bulk_load (CF, coef_tile, plane_bytes, mbar);
-      v6_bulk_load (CF + T::coef_per_plane, coef_tile + T::coef_per_plane, plane_bytes, mbar + 1);
+      if (CFM == 0)
+        v6_bulk_load (CF + T::coef_per_plane, coef_tile + T::coef_per_plane, plane_bytes, mbar + 1);
     }
 #else
-  for (int i = tid; i < 2 * (int) T::coef_per_plane; i += NT)
+  for (int i = tid; i < (int) ring; i += NT)
     CF[i] = coef_tile[i];
 #endif
   const int nnx = g.nn[0], nny = g.nn[1];
@@ -677,7 +747,7 @@ k_apply3d_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const V *__res
     ys[i] = 0;
   __syncthreads ();
 
-  tile_cells_v6<R, TX, TY, NQ, COUPLED> (g, k, tid, cx0, cy0, cz0, AZ, BZ, BR, coef_tile, CF, mbar, ys);
+  tile_cells_v6<R, TX, TY, NQ, COUPLED, CFM> (g, k, tid, cx0, cy0, cz0, AZ, BZ, BR, coef_tile, CF, mbar, ys);
 
   // ---- flush the y tile -----------------------------------------------------------
   for (int i = tid; i < NN; i += NT)
