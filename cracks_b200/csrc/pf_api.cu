@@ -16,6 +16,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/cracks_b200.h"
@@ -198,7 +199,7 @@ struct pf_ctx
   float *coef2_32 = nullptr;
   int jacobian_bits = 64;      // precision of the Krylov operator: 64 = exact, 32 = inexact-Newton Jacobian in FP32
   // tuning / debugging switches (per context; the environment is read once, by pf_create)
-  int v6_mode = getenv ("PF_V6_MODE") ? atoi (getenv ("PF_V6_MODE")) : 0; // coefficient feed / CTAs per SM of v6 (launch_apply3d_v6)
+  int v6_mode = getenv ("PF_V6_MODE") ? atoi (getenv ("PF_V6_MODE")) : -1; // tuning build: forces one coefficient feed of v6 (launch_apply3d_v6)
   int apply_variant = 16;      // 16 = default exact kernel; other numbers only in a PF_TUNING_VARIANTS build
   int force_generic = 0;       // pf_debug_force_generic: the thread-per-cell second implementation
   int no_iso = 0;              // pf_debug_disable_iso: general (anisotropic) code path on cubic cells
@@ -782,13 +783,19 @@ launch_apply3d_v6_feed (pf_ctx *ctx, const V *x, const V *sol, V *y, const typen
   return PF_OK;
 }
 
-// ctx->v6_mode (A/B switch, PF_V6_MODE): how the coefficient records are fed and how many CTAs per SM the kernel is built for
+// Coefficient feed and CTAs per SM of each instantiation, as measured at 16.7 M DoF (profiles/r2_v6_feed_modes.json):
+// the exact FP64 rule runs best with the one-plane TMA ring at 5 CTAs per SM (166 registers, 43 KB), the FP32 Jacobian
+// with register-prefetched records at 6 CTAs per SM (168 registers, 34 KB); the 2-point smoother operators show no
+// difference inside the V-cycle and keep the two-plane ring.  PF_V6_MODE (tuning build only) forces one mode for all.
 template <typename R, typename V, int NQ, int MINB, bool COUPLED = true>
 int
 launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename Lane<R>::S *coef)
 {
+#ifdef PF_TUNING_VARIANTS
   switch (ctx->v6_mode)
     {
+    case 0:
+      return launch_apply3d_v6_feed<R, V, NQ, MINB, COUPLED, 0> (ctx, x, sol, y, coef);
     case 1:
       return launch_apply3d_v6_feed<R, V, NQ, 5, COUPLED, 1> (ctx, x, sol, y, coef);
     case 2:
@@ -796,8 +803,15 @@ launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename L
     case 3:
       return launch_apply3d_v6_feed<R, V, NQ, 5, COUPLED, 2> (ctx, x, sol, y, coef);
     default:
-      return launch_apply3d_v6_feed<R, V, NQ, MINB, COUPLED, 0> (ctx, x, sol, y, coef);
+      break;
     }
+#endif
+  if constexpr (NQ == 3 && std::is_same<R, double>::value)
+    return launch_apply3d_v6_feed<R, V, NQ, 5, COUPLED, 2> (ctx, x, sol, y, coef);
+  else if constexpr (NQ == 3)
+    return launch_apply3d_v6_feed<R, V, NQ, 6, COUPLED, 1> (ctx, x, sol, y, coef);
+  else
+    return launch_apply3d_v6_feed<R, V, NQ, MINB, COUPLED, 0> (ctx, x, sol, y, coef);
 }
 
 // the tiled kernel the library uses by default (exact 27-point rule, or the
