@@ -1352,10 +1352,11 @@ mg_coarse_distributed (const pf_ctx *ctx)
 int create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank, int nranks,
                  const void *nccl_id, ncclComm_t shared_comm, pf_ctx **out);
 
-int diag_and_aux (pf_ctx *ctx);
+int diag_and_aux (pf_ctx *ctx, bool records_fresh = false);
 
 // (re)builds the level below ctx and transfers state, constraints and parameters to it
 int mg_lowp_refresh (pf_ctx *ctx);
+int apply_lowp (pf_ctx *ctx, float *x, float *y);
 int mg2_setup_coarse (pf_ctx *ctx);
 
 int
@@ -1367,6 +1368,14 @@ mg_setup_level (pf_ctx *ctx)
       double **vecs[] = {&ctx->mg_b, &ctx->mg_x, &ctx->mg_y, &ctx->mg_d, &ctx->mg_r, &ctx->mg_ev};
       for (double **v : vecs)
         CU (cudaMalloc (v, sizeof (double) * nd));
+    }
+  // the FP32 V-cycle's copies of the state first: the power iteration below runs on its operator
+  const bool lowp = ctx->mg_fp32 && ctx->dim == 3;
+  if (lowp)
+    {
+      const int rcl = mg_lowp_refresh (ctx);
+      if (rcl)
+        return rcl;
     }
   // lambda_max of D^-1 J by power iterations.  The iterate stays on the device and is
   // normalised there (one host read per level, not two per iteration); later Newton steps
@@ -1397,7 +1406,17 @@ mg_setup_level (pf_ctx *ctx)
     KCHECK ();
     for (int it = 0; it < n_it; ++it)
       {
-        if ((rc = apply_dev (ctx, v, w, ctx->mg_approx)))
+        if (lowp && ctx->mg_approx)
+          {
+            // the smoother's own operator (2-point rule in FP32): a 20 % margin on lambda_max covers its rounding
+            k_convert<double, float><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, v, ctx->f_x);
+            KCHECK ();
+            if ((rc = apply_lowp (ctx, ctx->f_x, ctx->f_y)))
+              return rc;
+            k_convert<float, double><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->f_y, w);
+            KCHECK ();
+          }
+        else if ((rc = apply_dev (ctx, v, w, ctx->mg_approx)))
           return rc;
         k_jacobi<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->diag, w, w);
         KCHECK ();
@@ -1419,12 +1438,6 @@ mg_setup_level (pf_ctx *ctx)
   }
   if (ctx->dim == 2)
     return mg2_setup_coarse (ctx);
-  if (ctx->mg_fp32)
-    {
-      const int rcl = mg_lowp_refresh (ctx);
-      if (rcl)
-        return rcl;
-    }
   if (!mg_possible (ctx))
     {
       ctx->mg_ready = true;
@@ -1975,11 +1988,36 @@ precond_apply (pf_ctx *ctx, const double *v, double *z)
 }
 
 int
-diag_and_aux (pf_ctx *ctx)
+diag_and_aux (pf_ctx *ctx, bool records_fresh)
 {
   const Grid g = forest_part (ctx);
   CU (cudaMemsetAsync (ctx->diag, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
-  if (g.n_local_cells > 0)
+  // records_fresh: pf_setup_jacobian has just written the 27-point coefficient records of this state (fine level only)
+  const bool from_records = records_fresh && !ctx->deterministic && ctx->apply_variant == 16 && v6_possible (ctx)
+                            && (ctx->jacobian_bits == 32 ? ctx->coef32 != nullptr : ctx->coef64 != nullptr);
+  if (from_records)
+    {
+      const int layers = g.cell_end - g.cell_begin;
+      const K6 k6 = make_k6 (ctx);
+      if (ctx->jacobian_bits == 32)
+        {
+          constexpr int TX = V6Shape<f32x2>::TX, TY = V6Shape<f32x2>::TY;
+          const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+          if (layers > 0)
+            k_diag_v6<float, TX, TY, 2><<<(unsigned) tiles_x * tiles_y * layers, TX * TY, 0, ctx->stream>>> (
+              g, k6, tiles_x, tiles_y, g.cell_begin, ctx->coef32, ctx->diag);
+        }
+      else
+        {
+          constexpr int TX = V6Shape<double>::TX, TY = V6Shape<double>::TY;
+          const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+          if (layers > 0)
+            k_diag_v6<double, TX, TY, 1><<<(unsigned) tiles_x * tiles_y * layers, TX * TY, 0, ctx->stream>>> (
+              g, k6, tiles_x, tiles_y, g.cell_begin, ctx->coef64, ctx->diag);
+        }
+      KCHECK ();
+    }
+  else if (g.n_local_cells > 0)
     {
       if (ctx->dim == 2)
         k_diag_generic<2><<<nblk (g.n_local_cells, 128), 128, 0, ctx->stream>>> (
@@ -2863,10 +2901,9 @@ pf_setup_jacobian (pf_ctx *ctx)
   if (!ctx)
     return PF_BAD_ARG;
   CU (cudaSetDevice (ctx->device));
-  int rc = diag_and_aux (ctx);
-  if (rc)
-    return rc;
-  if (v6_possible (ctx) && ctx->apply_variant == 16)
+  int rc = PF_OK;
+  const bool records = v6_possible (ctx) && ctx->apply_variant == 16;
+  if (records)
     {
       if (ctx->jacobian_bits == 32)
         rc = v6_refresh_coefficients<f32x2, 3> (ctx, &ctx->coef32);
@@ -2875,6 +2912,8 @@ pf_setup_jacobian (pf_ctx *ctx)
       if (rc)
         return rc;
     }
+  if ((rc = diag_and_aux (ctx, records)))
+    return rc;
   ctx->jac_ready = true;
   ctx->mg_ready = false;
   ctx->mg_graph_valid = false;

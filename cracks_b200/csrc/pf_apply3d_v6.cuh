@@ -296,6 +296,131 @@ k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, cons
     }
 }
 
+// ---- the diagonal of the exact Jacobian from the coefficient records (Jacobi / Chebyshev preconditioner) ---------
+// diag(J)[v, c] of a cell, in the units of the records: u rows  sum_q wg [(lam2 + 1/2) d_c^2 + |d|^2 / 2], phi row
+// sum_q c2 a^2 / 8 + G_c eps h / 3 (the Q1 Laplacian in closed form), with a = prod (1 +- xi_k) and d_k = a without its
+// k-th factor: separable in the three directions, so the 27 points collapse x -> y -> z like the apply itself.  Per cell
+// the absolute value, and the cell's mean where an entry is zero, as k_diag_generic (pf_generic.cuh) does to mimic
+// AffineConstraints::distribute_local_to_global.  One thread per cell, thread / record mapping of k_point_coeffs;
+// cells that share a node within the tile are ordered by eight barrier-separated vertex phases (no shared atomics).
+template <typename CS, int TX, int TY, int W>
+__global__ void __launch_bounds__ (TX * TY)
+k_diag_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const CS *__restrict__ coef, double *__restrict__ diag)
+{
+  using T = Tile3v6<TX, TY, 3, W>;
+  constexpr int NN = T::NN, PX = T::PX, NX = T::NX, NY = T::NY, NTH = TX * TY;
+  __shared__ double dt[4 * NN];
+  const int tid = threadIdx.x, lx = tid % TX, ly = tid / TX;
+  int b = blockIdx.x;
+  const int bx = b % tiles_x;
+  b /= tiles_x;
+  const int by = b % tiles_y, bz = b / tiles_y;
+  const int cx0 = bx * TX, cy0 = by * TY, cz = g.cell_begin + bz;
+  const int cx = cx0 + lx, cy = cy0 + ly;
+  const int thread = lx / W + (TX / W) * ly, lane = lx % W;
+  const CS *rec = coef + ((size_t) ((cz - layer0) * tiles_y + by) * tiles_x + bx) * T::coef_per_tile + (size_t) thread * 2 * W + lane;
+  const bool valid = cx < g.n[0] && cy < g.n[1] && cz < g.cell_end;
+  for (int i = tid; i < 4 * NN; i += NTH)
+    dt[i] = 0;
+  // (1 -+ xi)^2 at the three abscissae, for the lower (0) and the upper (1) node of a direction
+  const double sm = (1.0 - k.s) * (1.0 - k.s), sp = (1.0 + k.s) * (1.0 + k.s);
+  const double sq[3][2] = {{sp, sm}, {1.0, 1.0}, {sm, sp}};
+  double T0[2][2] = {{0, 0}, {0, 0}}, T1[2][2] = {{0, 0}, {0, 0}}, T2[2][2] = {{0, 0}, {0, 0}};
+  double T3[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+  if (valid)
+    {
+#pragma unroll
+      for (int qz = 0; qz < 3; ++qz)
+        {
+          double Y0[2] = {0, 0}, Y1[2] = {0, 0}, Y2[2][2] = {{0, 0}, {0, 0}}, Yc[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+          for (int qy = 0; qy < 3; ++qy)
+            {
+              double X0 = 0, X1[2] = {0, 0}, Xc[2] = {0, 0};
+#pragma unroll
+              for (int qx = 0; qx < 3; ++qx)
+                {
+                  const CS *r = rec + (size_t) ((qz * 3 + qy) * 3 + qx) * T::NT * 2 * W;
+                  const double wg = (double) v6_ldg (r), c2 = (double) v6_ldg (r + W);
+                  X0 += wg;
+#pragma unroll
+                  for (int b0 = 0; b0 < 2; ++b0)
+                    {
+                      X1[b0] = fma (wg, sq[qx][b0], X1[b0]);
+                      Xc[b0] = fma (c2, sq[qx][b0], Xc[b0]);
+                    }
+                }
+#pragma unroll
+              for (int b1 = 0; b1 < 2; ++b1)
+                {
+                  Y0[b1] = fma (X0, sq[qy][b1], Y0[b1]);
+                  Y1[b1] += X1[b1];
+#pragma unroll
+                  for (int b0 = 0; b0 < 2; ++b0)
+                    {
+                      Y2[b0][b1] = fma (X1[b0], sq[qy][b1], Y2[b0][b1]);
+                      Yc[b0][b1] = fma (Xc[b0], sq[qy][b1], Yc[b0][b1]);
+                    }
+                }
+            }
+#pragma unroll
+          for (int b2 = 0; b2 < 2; ++b2)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+              {
+                T0[a][b2] = fma (Y0[a], sq[qz][b2], T0[a][b2]); // d_0^2 = a_1^2 a_2^2: [v1][v2]
+                T1[a][b2] = fma (Y1[a], sq[qz][b2], T1[a][b2]); // d_1^2 = a_0^2 a_2^2: [v0][v2]
+                T3[0][a][b2] = fma (Yc[0][a], sq[qz][b2], T3[0][a][b2]);
+                T3[1][a][b2] = fma (Yc[1][a], sq[qz][b2], T3[1][a][b2]);
+              }
+#pragma unroll
+          for (int b0 = 0; b0 < 2; ++b0)
+#pragma unroll
+            for (int b1 = 0; b1 < 2; ++b1)
+              T2[b0][b1] += Y2[b0][b1]; // d_2^2 = a_0^2 a_1^2: [v0][v1]
+        }
+    }
+  double out[8][4], avg = 0;
+#pragma unroll
+  for (int v = 0; v < 8; ++v)
+    {
+      const int b0 = v & 1, b1 = (v >> 1) & 1, b2 = v >> 2;
+      const double d0 = T0[b1][b2], d1 = T1[b0][b2], d2 = T2[b0][b1], hs = 0.5 * (d0 + d1 + d2);
+      out[v][0] = fabs (fma (k.lam2 + 0.5, d0, hs));
+      out[v][1] = fabs (fma (k.lam2 + 0.5, d1, hs));
+      out[v][2] = fabs (fma (k.lam2 + 0.5, d2, hs));
+      out[v][3] = fabs (fma (0.125, T3[b0][b1][b2], k.kl[1]));
+      avg += out[v][0] + out[v][1] + out[v][2] + out[v][3];
+    }
+  avg *= 1.0 / 32.0;
+  __syncthreads ();
+#pragma unroll
+  for (int v = 0; v < 8; ++v)
+    {
+      if (valid)
+        {
+          double *d = dt + (lx + (v & 1)) + PX * (ly + ((v >> 1) & 1)) + PX * NY * (v >> 2);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            d[c * NN] += out[v][c] != 0.0 ? out[v][c] : avg;
+        }
+      __syncthreads ();
+    }
+  const int nnx = g.nn[0], nny = g.nn[1];
+  for (int i = tid; i < NN; i += NTH)
+    {
+      const int ix = i % PX, iy = (i / PX) % NY, iz = i / (PX * NY);
+      const int gx = cx0 + ix, gy = cy0 + iy, gz = cz + iz;
+      if (ix < NX && gx < nnx && gy < nny && cz < g.cell_end)
+        {
+          const long long n = gx + (long long) nnx * gy + g.nodes_per_plane * (gz - g.plane_begin);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            atomicAdd (&diag[4 * n + c], dt[c * NN + i]);
+        }
+    }
+}
+
 // ---- stages 3 and 4 of the apply for one tile (contains block barriers: all threads of the CTA call it) ---
 // NQ = 3: the exact rule, G_c eps grad(dphi).grad(psi) in closed form.  NQ = 2: the under-integrated operator of the
 // multigrid smoother (preconditioner only), phi-gradient flux inside the quadrature.

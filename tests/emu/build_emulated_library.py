@@ -23,7 +23,7 @@ SRC = os.path.join(ROOT, "cracks_b200", "csrc")
 GEN = os.path.join(HERE, "_gen")
 
 # kernels that synchronise within a block (barriers, shared-memory staging, warp shuffles)
-COOPERATIVE = ("k_apply3d", "k_residual3d", "k_multi_dot", "k_multi_axpy_dot", "k_reduce_partials", "k_residual_finish", "k_absdiff_max",
+COOPERATIVE = ("k_apply3d", "k_diag_v6", "k_residual3d", "k_multi_dot", "k_multi_axpy_dot", "k_reduce_partials", "k_residual_finish", "k_absdiff_max",
                "k_one_minus_phi_max", "k_functionals_generic", "k_cod_generic", "k_load_top_2d")
 
 
