@@ -215,11 +215,14 @@ struct K6
   double cge;    // G_c eps 8 gam^2: phi-gradient flux of the 2-point rule (the 3-point rule uses the closed form)
 };
 
+#ifndef PF_POINT_COEFFS_THREADS
+#define PF_POINT_COEFFS_THREADS 384 // resident threads per SM the set-up kernel is built for (register cap 168)
+#endif
 // ---- set-up: the two state coefficients per quadrature point ---------------------------------------------
 // One thread per cell; record order exactly as the apply kernel reads it: per (tile, point, thread of the apply
 // kernel) the W values of wg, then the W values of c2.  Everything is computed in FP64 and stored as CS.
 template <typename CS, int TX, int TY, int NQ, int W>
-__global__ void __launch_bounds__ (TX * TY)
+__global__ void __launch_bounds__ (TX * TY, PF_POINT_COEFFS_THREADS / (TX * TY))
 k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, const double *__restrict__ sol,
                 const double *__restrict__ pt, CS *__restrict__ coef)
 {
@@ -247,52 +250,92 @@ k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, cons
         }
     }
   const double gam = k.gu[0];
-  const double two_mu_g2 = 2.0 * p.mu * gam * gam, omk = 1.0 - p.kappa;
+  const double two_mu_g2 = 2.0 * p.mu * gam * gam, omk = 1.0 - p.kappa, g2 = gam * gam;
   const double es[3] = {NQ == 3 ? -k.s : -k.s2, NQ == 3 ? 0.0 : k.s2, k.s};
-#pragma unroll 1
-  for (int q = 0; q < NQ * NQ * NQ; ++q)
+  // The interpolation collapses z -> y -> x like the apply (vertex v = vx + 2 vy + 4 vz, shape function
+  // prod (1 +- xi) / 8): per node column the z-sum s and z-difference r of a field; a gradient is gam times a
+  // difference of such sums.  Fields 0..2 = u, 3 = phi~ (value only).
+  double sz[4][4], rz[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
     {
-      const double e[3] = {es[q % NQ], es[(q / NQ) % NQ], es[q / (NQ * NQ)]};
-      const double w = NQ == 3 ? k.wvol * k.wq[q % 3] * k.wq[(q / 3) % 3] * k.wq[q / 9] : k.wvol;
-      double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, pte = 0;
 #pragma unroll
-      for (int v = 0; v < 8; ++v)
+      for (int c = 0; c < 3; ++c)
+        sz[c][j] = u[j + 4][c] + u[j][c], rz[c][j] = u[j + 4][c] - u[j][c];
+      sz[3][j] = pe[j + 4] + pe[j], rz[3][j] = pe[j + 4] - pe[j];
+    }
+#pragma unroll 1
+  for (int qz = 0; qz < NQ; ++qz)
+    {
+      const double ez = qz == 0 ? es[0] : (qz == 1 ? es[1] : es[2]);
+      const double wzq = k.wvol * (qz == 1 ? k.wq[1] : k.wq[0]); // the rule is symmetric: wq[2] = wq[0]
+      // z-derivative chain: y-collapse at the NQ abscissae, then sum / difference in x (the same in every Gauss plane;
+      // recomputed per plane, 18 fewer live values than carried through the loop)
+      double PB[3][NQ], RB[3][NQ];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
         {
-          // shape function (1 +- e0)(1 +- e1)(1 +- e2) / 8, gradient (+-1/h)(1 +- e)(1 +- e) / 4
-          const double a0 = (v & 1) ? 1.0 + e[0] : 1.0 - e[0], a1 = (v & 2) ? 1.0 + e[1] : 1.0 - e[1],
-                       a2 = (v & 4) ? 1.0 + e[2] : 1.0 - e[2];
-          const double d0 = ((v & 1) ? 1.0 : -1.0) * a1 * a2, d1 = ((v & 2) ? 1.0 : -1.0) * a0 * a2,
-                       d2 = ((v & 4) ? 1.0 : -1.0) * a0 * a1;
-          pte = fma (0.125 * a0 * a1 * a2, pe[v], pte);
+          const double p0 = rz[c][0] + rz[c][2], d0 = rz[c][2] - rz[c][0], p1 = rz[c][1] + rz[c][3], d1 = rz[c][3] - rz[c][1];
 #pragma unroll
-          for (int c = 0; c < 3; ++c)
+          for (int qy = 0; qy < NQ; ++qy)
             {
-              G[c][0] = fma (d0, u[v][c], G[c][0]);
-              G[c][1] = fma (d1, u[v][c], G[c][1]);
-              G[c][2] = fma (d2, u[v][c], G[c][2]);
+              const double b0 = fma (es[qy], d0, p0), b1 = fma (es[qy], d1, p1);
+              PB[c][qy] = b0 + b1, RB[c][qy] = b1 - b0;
             }
         }
-      // true gradient = (1/h) G / 4 = gam G
-      if (p.clamp_extra)
-        pte = fmin (fmax (pte, 0.0), 1.0);
-      const double gdeg = fma (omk * pte, pte, p.kappa);
-      double E[3][3];
+      // y-sums and y-differences of the plane values, per x-node; x-sum / x-difference of the y-differences
+      double Py[4][2], Ry[4][2], PDy[3], RDy[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
+      for (int f = 0; f < 4; ++f)
+        {
+          const double a0 = fma (ez, rz[f][0], sz[f][0]), a1 = fma (ez, rz[f][1], sz[f][1]);
+          const double a2 = fma (ez, rz[f][2], sz[f][2]), a3 = fma (ez, rz[f][3], sz[f][3]);
+          Py[f][0] = a0 + a2, Ry[f][0] = a2 - a0, Py[f][1] = a1 + a3, Ry[f][1] = a3 - a1;
+          if (f < 3)
+            PDy[f] = Ry[f][0] + Ry[f][1], RDy[f] = Ry[f][1] - Ry[f][0];
+        }
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
-          E[c][d] = 0.5 * gam * (G[c][d] + G[d][c]);
-      const double tr = E[0][0] + E[1][1] + E[2][2];
-      double ee = 0;
+      for (int qy = 0; qy < NQ; ++qy)
+        {
+          const double ey = es[qy];
+          double dxv[3], Pp, Rp;
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
+          for (int c = 0; c < 3; ++c)
+            dxv[c] = fma (ey, Ry[c][1], Py[c][1]) - fma (ey, Ry[c][0], Py[c][0]);
+          {
+            const double v0 = fma (ey, Ry[3][0], Py[3][0]), v1 = fma (ey, Ry[3][1], Py[3][1]);
+            Pp = v0 + v1, Rp = v1 - v0;
+          }
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
-          ee = fma (E[c][d], E[c][d], ee);
-      const double sE = p.lambda * tr * tr + 2.0 * p.mu * ee; // sigma(u) : E(u)
-      CS *rec = out + (size_t) q * T::NT * 2 * W;
-      rec[0] = valid ? (CS) (w * gdeg * two_mu_g2) : (CS) 0;
-      rec[W] = valid ? (CS) (0.125 * w * (omk * sE + p.G_c / p.eps - 2.0 * p.P1 * tr)) : (CS) 0;
+          for (int qx = 0; qx < NQ; ++qx)
+            {
+              const double ex = es[qx];
+              const int q = (qz * NQ + qy) * NQ + qx;
+              const double w = NQ == 3 ? wzq * k.wq[qx] * k.wq[qy] : k.wvol;
+              double G[3][3];
+#pragma unroll
+              for (int c = 0; c < 3; ++c)
+                {
+                  G[c][0] = dxv[c];
+                  G[c][1] = fma (ex, RDy[c], PDy[c]);
+                  G[c][2] = fma (ex, RB[c][qy], PB[c][qy]);
+                }
+              double pte = 0.125 * fma (ex, Rp, Pp);
+              if (p.clamp_extra)
+                pte = fmin (fmax (pte, 0.0), 1.0);
+              const double gdeg = fma (omk * pte, pte, p.kappa);
+              // E = gam sym(G): tr E = gam tr G, E:E = gam^2 (sum of squared diagonal + half the squared off-diagonal sums)
+              const double trG = G[0][0] + G[1][1] + G[2][2];
+              const double o01 = G[0][1] + G[1][0], o02 = G[0][2] + G[2][0], o12 = G[1][2] + G[2][1];
+              const double dd = fma (G[0][0], G[0][0], fma (G[1][1], G[1][1], G[2][2] * G[2][2]));
+              const double od = fma (o01, o01, fma (o02, o02, o12 * o12));
+              const double tr = gam * trG, ee = g2 * fma (0.5, od, dd);
+              const double sE = p.lambda * tr * tr + 2.0 * p.mu * ee; // sigma(u) : E(u)
+              CS *rec = out + (size_t) q * T::NT * 2 * W;
+              rec[0] = valid ? (CS) (w * gdeg * two_mu_g2) : (CS) 0;
+              rec[W] = valid ? (CS) (0.125 * w * (omk * sE + p.G_c / p.eps - 2.0 * p.P1 * tr)) : (CS) 0;
+            }
+        }
     }
 }
 
