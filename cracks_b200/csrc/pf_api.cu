@@ -1352,7 +1352,7 @@ mg_coarse_distributed (const pf_ctx *ctx)
 int create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank, int nranks,
                  const void *nccl_id, ncclComm_t shared_comm, pf_ctx **out);
 
-int diag_and_aux (pf_ctx *ctx, bool records_fresh = false);
+int diag_and_aux (pf_ctx *ctx, int records = 0);
 
 // (re)builds the level below ctx and transfers state, constraints and parameters to it
 int mg_lowp_refresh (pf_ctx *ctx);
@@ -1516,7 +1516,7 @@ mg_setup_level (pf_ctx *ctx)
           return fail (ctx, rc, "multigrid: coarse halo: %s", pf_last_error (c));
       }
   }
-  rc = diag_and_aux (c);
+  rc = diag_and_aux (c, 2);
   if (rc)
     return fail (ctx, rc, "multigrid: coarse diagonal: %s", pf_last_error (c));
   c->jac_ready = true;
@@ -1988,32 +1988,54 @@ precond_apply (pf_ctx *ctx, const double *v, double *z)
 }
 
 int
-diag_and_aux (pf_ctx *ctx, bool records_fresh)
+diag_and_aux (pf_ctx *ctx, int records)
 {
   const Grid g = forest_part (ctx);
   CU (cudaMemsetAsync (ctx->diag, 0, sizeof (double) * ctx->n_local_dofs, ctx->stream));
-  // records_fresh: pf_setup_jacobian has just written the 27-point coefficient records of this state (fine level only)
-  const bool from_records = records_fresh && !ctx->deterministic && ctx->apply_variant == 16 && v6_possible (ctx)
-                            && (ctx->jacobian_bits == 32 ? ctx->coef32 != nullptr : ctx->coef64 != nullptr);
+  int rc;
+  // state coefficients of the 2-point-rule smoother operator on this level, in the V-cycle's precision
+  const bool smoother_records = ctx->precond == 1 && ctx->mg_approx && ctx->apply_variant == 16 && v6_possible (ctx);
+  if (smoother_records)
+    {
+      rc = ctx->mg_fp32 ? v6_refresh_coefficients<f32x2, 2> (ctx, &ctx->coef2_32)
+                        : v6_refresh_coefficients<double, 2> (ctx, &ctx->coef2_64);
+      if (rc)
+        return rc;
+    }
+  // records == 3: pf_setup_jacobian has just written the 27-point records of this state (fine level): the diagonal of
+  // the exact Jacobian from them.  records == 2 (coarse multigrid levels): the diagonal of the smoother's own 2-point
+  // operator from the records above.  Otherwise, and in deterministic mode, the thread-per-cell kernel.
+  const bool fine = records == 3 && (ctx->jacobian_bits == 32 ? ctx->coef32 != nullptr : ctx->coef64 != nullptr);
+  const bool coarse = records == 2 && smoother_records;
+  const bool from_records = (fine || coarse) && !ctx->deterministic && ctx->apply_variant == 16 && v6_possible (ctx);
   if (from_records)
     {
       const int layers = g.cell_end - g.cell_begin;
       const K6 k6 = make_k6 (ctx);
-      if (ctx->jacobian_bits == 32)
+      const bool f32 = fine ? ctx->jacobian_bits == 32 : ctx->mg_fp32 != 0;
+      if (f32)
         {
           constexpr int TX = V6Shape<f32x2>::TX, TY = V6Shape<f32x2>::TY;
           const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
-          if (layers > 0)
-            k_diag_v6<float, TX, TY, 2><<<(unsigned) tiles_x * tiles_y * layers, TX * TY, 0, ctx->stream>>> (
-              g, k6, tiles_x, tiles_y, g.cell_begin, ctx->coef32, ctx->diag);
+          const unsigned grid = (unsigned) tiles_x * tiles_y * std::max (layers, 0);
+          if (grid > 0 && fine)
+            k_diag_v6<float, TX, TY, 2, 3><<<grid, TX * TY, 0, ctx->stream>>> (g, k6, tiles_x, tiles_y, g.cell_begin,
+                                                                              ctx->coef32, ctx->diag);
+          else if (grid > 0)
+            k_diag_v6<float, TX, TY, 2, 2><<<grid, TX * TY, 0, ctx->stream>>> (g, k6, tiles_x, tiles_y, g.cell_begin,
+                                                                              ctx->coef2_32, ctx->diag);
         }
       else
         {
           constexpr int TX = V6Shape<double>::TX, TY = V6Shape<double>::TY;
           const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
-          if (layers > 0)
-            k_diag_v6<double, TX, TY, 1><<<(unsigned) tiles_x * tiles_y * layers, TX * TY, 0, ctx->stream>>> (
-              g, k6, tiles_x, tiles_y, g.cell_begin, ctx->coef64, ctx->diag);
+          const unsigned grid = (unsigned) tiles_x * tiles_y * std::max (layers, 0);
+          if (grid > 0 && fine)
+            k_diag_v6<double, TX, TY, 1, 3><<<grid, TX * TY, 0, ctx->stream>>> (g, k6, tiles_x, tiles_y, g.cell_begin,
+                                                                               ctx->coef64, ctx->diag);
+          else if (grid > 0)
+            k_diag_v6<double, TX, TY, 1, 2><<<grid, TX * TY, 0, ctx->stream>>> (g, k6, tiles_x, tiles_y, g.cell_begin,
+                                                                               ctx->coef2_64, ctx->diag);
         }
       KCHECK ();
     }
@@ -2048,17 +2070,8 @@ diag_and_aux (pf_ctx *ctx, bool records_fresh)
   if (int rcp = forest_allreduce (ctx, ctx->diag, (size_t) ctx->n_local_dofs))
     return rcp;
   // complete the diagonal on the ghost planes (their cells are only partly local)
-  int rc = halo_exchange (ctx, ctx->diag, ctx->nc);
-  if (rc)
+  if ((rc = halo_exchange (ctx, ctx->diag, ctx->nc)))
     return rc;
-  if (ctx->precond == 1 && ctx->mg_approx && ctx->apply_variant == 16 && v6_possible (ctx))
-    {
-      // state coefficients of the 2-point-rule smoother operator on this level, in the V-cycle's precision
-      rc = ctx->mg_fp32 ? v6_refresh_coefficients<f32x2, 2> (ctx, &ctx->coef2_32)
-                        : v6_refresh_coefficients<double, 2> (ctx, &ctx->coef2_64);
-      if (rc)
-        return rc;
-    }
 #ifdef PF_TUNING_VARIANTS
   if (ctx->dim == 3)
     {
@@ -2912,7 +2925,7 @@ pf_setup_jacobian (pf_ctx *ctx)
       if (rc)
         return rc;
     }
-  if ((rc = diag_and_aux (ctx, records)))
+  if ((rc = diag_and_aux (ctx, records ? 3 : 0)))
     return rc;
   ctx->jac_ready = true;
   ctx->mg_ready = false;

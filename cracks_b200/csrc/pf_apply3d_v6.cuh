@@ -216,7 +216,8 @@ struct K6
 };
 
 #ifndef PF_POINT_COEFFS_THREADS
-#define PF_POINT_COEFFS_THREADS 384 // resident threads per SM the set-up kernel is built for (register cap 168)
+#define PF_POINT_COEFFS_THREADS 256 // resident threads per SM the set-up kernel is built for: no register cap (0.45 ms;
+                                    // 384, i.e. 168 registers and 200 B of spills: 0.54 ms at 16.7 M DoF)
 #endif
 // ---- set-up: the two state coefficients per quadrature point ---------------------------------------------
 // One thread per cell; record order exactly as the apply kernel reads it: per (tile, point, thread of the apply
@@ -339,18 +340,20 @@ k_point_coeffs (Grid g, Phys p, K3 k, int tiles_x, int tiles_y, int layer0, cons
     }
 }
 
-// ---- the diagonal of the exact Jacobian from the coefficient records (Jacobi / Chebyshev preconditioner) ---------
+// ---- the diagonal of the Jacobian from the coefficient records (Jacobi / Chebyshev preconditioner) ---------------
+// NQ = 3: records of the exact rule (fine level: the diagonal pf_jacobian_diagonal returns); NQ = 2: records of the
+// smoother's 2-point operator (coarse multigrid levels, where only those exist).
 // diag(J)[v, c] of a cell, in the units of the records: u rows  sum_q wg [(lam2 + 1/2) d_c^2 + |d|^2 / 2], phi row
 // sum_q c2 a^2 / 8 + G_c eps h / 3 (the Q1 Laplacian in closed form), with a = prod (1 +- xi_k) and d_k = a without its
 // k-th factor: separable in the three directions, so the 27 points collapse x -> y -> z like the apply itself.  Per cell
 // the absolute value, and the cell's mean where an entry is zero, as k_diag_generic (pf_generic.cuh) does to mimic
 // AffineConstraints::distribute_local_to_global.  One thread per cell, thread / record mapping of k_point_coeffs;
 // cells that share a node within the tile are ordered by eight barrier-separated vertex phases (no shared atomics).
-template <typename CS, int TX, int TY, int W>
+template <typename CS, int TX, int TY, int W, int NQ>
 __global__ void __launch_bounds__ (TX * TY)
 k_diag_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const CS *__restrict__ coef, double *__restrict__ diag)
 {
-  using T = Tile3v6<TX, TY, 3, W>;
+  using T = Tile3v6<TX, TY, NQ, W>;
   constexpr int NN = T::NN, PX = T::PX, NX = T::NX, NY = T::NY, NTH = TX * TY;
   __shared__ double dt[4 * NN];
   const int tid = threadIdx.x, lx = tid % TX, ly = tid / TX;
@@ -366,24 +369,24 @@ k_diag_v6 (Grid g, K6 k, int tiles_x, int tiles_y, int layer0, const CS *__restr
   for (int i = tid; i < 4 * NN; i += NTH)
     dt[i] = 0;
   // (1 -+ xi)^2 at the three abscissae, for the lower (0) and the upper (1) node of a direction
-  const double sm = (1.0 - k.s) * (1.0 - k.s), sp = (1.0 + k.s) * (1.0 + k.s);
-  const double sq[3][2] = {{sp, sm}, {1.0, 1.0}, {sm, sp}};
+  const double sa = NQ == 3 ? k.s : k.s2, sm = (1.0 - sa) * (1.0 - sa), sp = (1.0 + sa) * (1.0 + sa);
+  const double sq[3][2] = {{sp, sm}, {NQ == 3 ? 1.0 : sm, NQ == 3 ? 1.0 : sp}, {sm, sp}};
   double T0[2][2] = {{0, 0}, {0, 0}}, T1[2][2] = {{0, 0}, {0, 0}}, T2[2][2] = {{0, 0}, {0, 0}};
   double T3[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
   if (valid)
     {
 #pragma unroll
-      for (int qz = 0; qz < 3; ++qz)
+      for (int qz = 0; qz < NQ; ++qz)
         {
           double Y0[2] = {0, 0}, Y1[2] = {0, 0}, Y2[2][2] = {{0, 0}, {0, 0}}, Yc[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll
-          for (int qy = 0; qy < 3; ++qy)
+          for (int qy = 0; qy < NQ; ++qy)
             {
               double X0 = 0, X1[2] = {0, 0}, Xc[2] = {0, 0};
 #pragma unroll
-              for (int qx = 0; qx < 3; ++qx)
+              for (int qx = 0; qx < NQ; ++qx)
                 {
-                  const CS *r = rec + (size_t) ((qz * 3 + qy) * 3 + qx) * T::NT * 2 * W;
+                  const CS *r = rec + (size_t) ((qz * NQ + qy) * NQ + qx) * T::NT * 2 * W;
                   const double wg = (double) v6_ldg (r), c2 = (double) v6_ldg (r + W);
                   X0 += wg;
 #pragma unroll
