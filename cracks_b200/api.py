@@ -96,6 +96,8 @@ _SIGS = {
     "pf_set_jacobian_precision": [C.c_void_p, C.c_int],
     "pf_set_deterministic": [C.c_void_p, C.c_int],
     "pf_set_multigrid_coupling": [C.c_void_p, C.c_int],
+    "pf_set_block_solve": [C.c_void_p, C.c_int],
+    "pf_debug_set_block": [C.c_void_p, C.c_int],
     "pf_set_multigrid_graph": [C.c_void_p, C.c_int],
     "pf_apply_preconditioner": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_set_krylov_dim": [C.c_void_p, C.c_int],
@@ -366,6 +368,10 @@ class PhaseFieldContext:
     def set_preconditioner(self, kind=1, cheb_degree=2, cheb_ratio=6.0):
         """0 = Jacobi, 1 = geometric multigrid (stand-in for the reference's ML AMG)"""
         self._check(self.lib.pf_set_preconditioner(self.h, kind, cheb_degree, cheb_ratio))
+
+    def set_block_solve(self, on=True):
+        """pf_solve as a u stage followed by a phi stage (the Jacobian has no (u,phi) block, cracks.cc:2333-2337)"""
+        self._check(self.lib.pf_set_block_solve(self.h, int(on)))
 
     def set_multigrid_coupling(self, coupled=True):
         """False: block-diagonal smoother operator (no (phi,u) block), like the reference's BlockDiagonalPreconditioner"""

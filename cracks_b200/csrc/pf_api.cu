@@ -24,6 +24,7 @@
 #include "pf_apply3d_v2.cuh"
 #include "pf_apply3d_v4.cuh"
 #include "pf_apply3d_v6.cuh"
+#include "pf_apply3d_phi.cuh"
 #ifdef PF_TUNING_VARIANTS // earlier generations and tuning experiments of the apply kernel: `make TUNING=1`, A/B runs only
 #include "pf_apply3d_v3.cuh"
 #include "pf_apply3d_v5.cuh"
@@ -128,6 +129,16 @@ struct pf_ctx
   double *diag = nullptr, *mass = nullptr, *r_total = nullptr, *r_pde = nullptr, *dx = nullptr;
   double *stage = nullptr, *xa = nullptr, *ya = nullptr, *saved = nullptr;
   uint8_t *mask = nullptr, *stage8 = nullptr;
+  // Block-triangular solve (pf_set_block_solve): `mask` is the constraint mask every kernel reads; during the u / phi
+  // stage of pf_solve it points to mask_blk[0] (= mask_home with every phi dof marked constrained) / mask_blk[1]
+  // (every u dof marked), so that operator, smoother and transfers act on one block and are the identity on the other
+  uint8_t *mask_home = nullptr, *mask_blk[2] = {nullptr, nullptr};
+  int block = 0;       // 0 = full system, 1 = u block, 2 = phi block (see set_block)
+  double *blk_b = nullptr, *blk_x = nullptr; // right-hand side and u update of the stages
+  double block_oversolve = 1e-2;             // the u stage, when it runs, ends this factor below its share of the tolerance
+  double block_u_floor = 1e-12;              // ... and is skipped while |b_u| <= block_u_floor * bnorm_ref
+  double bnorm_ref = 0;                      // largest |b| pf_solve has seen since the state / time step last changed
+  int block_solve = getenv ("PF_BLOCK_SOLVE") ? atoi (getenv ("PF_BLOCK_SOLVE")) : 0;
   double2 *aux = nullptr; // {phi~, mask} records for the TMA path
   unsigned long long *tile_counter = nullptr, tile_epoch = 0;
   int sm_count = 148;
@@ -814,6 +825,36 @@ launch_apply3d_v6 (pf_ctx *ctx, const V *x, const V *sol, V *y, const typename L
     return launch_apply3d_v6_feed<R, V, NQ, MINB, COUPLED, 0> (ctx, x, sol, y, coef);
 }
 
+// the (phi,phi) block alone (pf_apply3d_phi.cuh) on the records of v6; same cell ranges, colours and streams as above
+template <typename CS, typename V, int W, int NQ>
+int
+launch_apply3d_phi (pf_ctx *ctx, const V *x, V *y, const CS *coef)
+{
+  constexpr int TX = W == 2 ? V6Shape<f32x2>::TX : V6Shape<double>::TX, TY = W == 2 ? V6Shape<f32x2>::TY : V6Shape<double>::TY;
+  Grid g = ctx->g;
+  const int layer0 = g.cell_begin;
+  if (ctx->range_begin >= 0)
+    {
+      g.cell_begin = ctx->range_begin;
+      g.cell_end = ctx->range_end;
+      g.layer_stride = ctx->range_stride;
+    }
+  const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
+  const int tiles_z = g.layer_stride > 1 ? 2 : g.cell_end - g.cell_begin;
+  const K6 k6 = make_k6 (ctx);
+  for (int colour = ctx->deterministic ? 0 : -1; colour < (ctx->deterministic ? 8 : 0); ++colour)
+    {
+      g.colour = colour;
+      const unsigned grid = (unsigned) tiles_of_colour (colour, tiles_x, tiles_y, tiles_z);
+      if (grid == 0)
+        continue;
+      k_apply3d_phi<CS, V, TX, TY, W, NQ><<<grid, TX * TY, 0, ctx->launch_stream ? ctx->launch_stream : ctx->stream>>> (
+        g, k6, tiles_x, tiles_y, layer0, x, ctx->mask, coef, y);
+      KCHECK ();
+    }
+  return PF_OK;
+}
+
 // the tiled kernel the library uses by default (exact 27-point rule, or the
 // 2-point rule of the preconditioner-only operator)
 int
@@ -825,6 +866,16 @@ launch_tiled_default (pf_ctx *ctx, const double *x, double *y, bool approx)
 #endif
   if (ctx->apply_variant == 16 && v6_possible (ctx))
     {
+      if (ctx->block == 2)
+        {
+          // phi stage of the block-triangular solve: x_u = 0 and the u rows are identity rows, only B is evaluated
+          if (approx && ctx->coef2_64)
+            return launch_apply3d_phi<double, double, 1, 2> (ctx, x, y, ctx->coef2_64);
+          if (!approx && ctx->jacobian_bits == 32 && ctx->coef32)
+            return launch_apply3d_phi<float, double, 2, 3> (ctx, x, y, ctx->coef32);
+          if (!approx && ctx->coef64)
+            return launch_apply3d_phi<double, double, 1, 3> (ctx, x, y, ctx->coef64);
+        }
       if (approx && ctx->coef2_64)
         return ctx->mg_uncoupled ? launch_apply3d_v6<double, double, 2, 4, false> (ctx, x, ctx->sol, y, ctx->coef2_64)
                                  : launch_apply3d_v6<double, double, 2, 4> (ctx, x, ctx->sol, y, ctx->coef2_64);
@@ -1353,6 +1404,7 @@ int create_impl (const pf_mesh *mesh, const pf_params *params, int device, int r
                  const void *nccl_id, ncclComm_t shared_comm, pf_ctx **out);
 
 int diag_and_aux (pf_ctx *ctx, int records = 0);
+int build_block_masks (pf_ctx *ctx);
 
 // (re)builds the level below ctx and transfers state, constraints and parameters to it
 int mg_lowp_refresh (pf_ctx *ctx);
@@ -1721,6 +1773,8 @@ launch_apply3d_mg (pf_ctx *ctx, const float *x, float *y)
   const int tiles_x = (g.n[0] + TX - 1) / TX, tiles_y = (g.n[1] + TY - 1) / TY;
   const int tiles_z = g.layer_stride > 1 ? 2 : (g.cell_end - g.cell_begin + TZ - 1) / TZ;
   const bool iso = g.h[0] == g.h[1] && g.h[1] == g.h[2] && !ctx->no_iso;
+  if (ctx->apply_variant == 16 && v6_possible (ctx) && ctx->coef2_32 && ctx->block == 2)
+    return launch_apply3d_phi<float, float, 2, 2> (ctx, x, y, ctx->coef2_32);
   if (ctx->apply_variant == 16 && v6_possible (ctx) && ctx->coef2_32)
     return ctx->mg_uncoupled ? launch_apply3d_v6<f32x2, float, 2, 4, false> (ctx, x, ctx->f_sol, y, ctx->coef2_32)
                              : launch_apply3d_v6<f32x2, float, 2, 4> (ctx, x, ctx->f_sol, y, ctx->coef2_32);
@@ -2392,6 +2446,7 @@ create_impl (const pf_mesh *mesh, const pf_params *params, int device, int rank,
   CU (cudaMalloc (&ctx->pt, nn * sizeof (double)));
   CU (cudaMalloc (&ctx->mass, nn * sizeof (double)));
   CU (cudaMalloc (&ctx->mask, nn));
+  ctx->mask_home = ctx->mask;
 #ifdef PF_TUNING_VARIANTS
 #ifdef PF_TUNING_VARIANTS
   CU (cudaMalloc (&ctx->aux, nn * sizeof (double2)));
@@ -2524,6 +2579,7 @@ create_forest_impl (const pf_forest_mesh *fm, const pf_params *params, int devic
   CU (cudaMalloc (&ctx->pt, nn * sizeof (double)));
   CU (cudaMalloc (&ctx->mass, nn * sizeof (double)));
   CU (cudaMalloc (&ctx->mask, nn));
+  ctx->mask_home = ctx->mask;
   CU (cudaMalloc (&ctx->zero_mask, nn));
 #ifdef PF_TUNING_VARIANTS
   CU (cudaMalloc (&ctx->aux, nn * sizeof (double2)));
@@ -2682,11 +2738,11 @@ pf_destroy (pf_ctx *ctx)
   for (float *v : {ctx->f_sol, ctx->f_pt, ctx->f_idiag, ctx->f_b, ctx->f_x, ctx->f_y, ctx->f_d, ctx->f_r})
     if (v)
       cudaFree (v);
-  for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r, ctx->mg_ev, ctx->mg_in})
+  for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r, ctx->mg_ev, ctx->mg_in, ctx->blk_b, ctx->blk_x})
     if (v)
       cudaFree (v);
   void *ptrs[] = {ctx->sol,   ctx->old,  ctx->oldold, ctx->pt,     ctx->diag,  ctx->mass, ctx->r_total,
-                  ctx->r_pde, ctx->dx,   ctx->stage,  ctx->xa,     ctx->ya,    ctx->zvec, ctx->mask,
+                  ctx->r_pde, ctx->dx,   ctx->stage,  ctx->xa,     ctx->ya,    ctx->zvec, ctx->mask_home, ctx->mask_blk[0], ctx->mask_blk[1],
                   ctx->saved, ctx->aux, ctx->tile_counter, ctx->stage8, ctx->cycle, ctx->fetab, ctx->red,   ctx->hdev,  ctx->partial, ctx->counts,
                   ctx->V, ctx->hang, ctx->conn_dev, ctx->level_dev, ctx->lame_dev, ctx->lame_energy_dev, ctx->fx,
                   ctx->zero_mask, ctx->level_h_dev};
@@ -2776,6 +2832,7 @@ pf_set_params (pf_ctx *ctx, const pf_params *params)
 {
   if (!ctx || !params)
     return PF_BAD_ARG;
+  ctx->bnorm_ref = 0; // the u equation changes: the block solve measures its residual against this time step's
   ctx->prm = *params;
   update_phys (ctx);
   ctx->jac_ready = false;
@@ -2788,6 +2845,7 @@ pf_set_state (pf_ctx *ctx, const double *sol, const double *old, const double *o
 {
   if (!ctx || !(dt_oldold > 0))
     return PF_BAD_ARG;
+  ctx->bnorm_ref = 0; // the u equation changes: the block solve measures its residual against this time step's
   CU (cudaSetDevice (ctx->device));
   int rc;
   if (sol && (rc = upload_block (ctx, sol, ctx->sol)))
@@ -2931,7 +2989,22 @@ pf_setup_jacobian (pf_ctx *ctx)
   ctx->mg_ready = false;
   ctx->mg_graph_valid = false;
   if (ctx->precond == 1 && !ctx->forest && (ctx->dim == 3 || (ctx->mg2d && ctx->nranks == 1)))
-    return mg_setup_level (ctx);
+    if ((rc = mg_setup_level (ctx)))
+      return rc;
+  if (ctx->block_solve && ctx->dim == 3 && !ctx->forest)
+    return build_block_masks (ctx);
+  return PF_OK;
+}
+
+// Linear solves as two block stages (u, then phi) instead of one GMRES on the whole system: the reference's Jacobian has
+// no (u,phi) block (cracks.cc:2333-2337).  3-D box meshes; the result satisfies the same |b - J dx| <= tol.
+int
+pf_set_block_solve (pf_ctx *ctx, int on)
+{
+  if (!ctx)
+    return PF_BAD_ARG;
+  ctx->block_solve = on ? 1 : 0;
+  ctx->jac_ready = false; // the stage masks are made by pf_setup_jacobian
   return PF_OK;
 }
 
@@ -3216,58 +3289,84 @@ pf_active_set_update (pf_ctx *ctx, double c, uint8_t *active_mask, int64_t *n_ac
 }
 
 // ---- solve(): restarted right-preconditioned GMRES, CGS2 orthogonalisation
+} // extern "C"
+
+namespace {
+
+// hdev[0..k) = V^T w, hdev[k] = w.w (if with_norm); all-reduced
 int
-pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
+krylov_dots (pf_ctx *ctx, int k, const double *wv, int with_norm)
 {
-  if (!ctx || max_it < 1)
-    return PF_BAD_ARG;
-  if (!ctx->jac_ready)
-    return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must precede pf_solve");
-  CU (cudaSetDevice (ctx->device));
-  const int m = ctx->krylov_m;
   const long long nd = ctx->n_local_dofs;
   const long long lo = ctx->owned_lo * ctx->nc, hi = ctx->owned_hi * ctx->nc;
-  if (!ctx->V)
-    CU (cudaMalloc (&ctx->V, sizeof (double) * nd * (size_t) (m + 1)));
-  double *V = ctx->V, *w = ctx->ya, *z = ctx->zvec, *x = ctx->dx, *b = ctx->r_pde;
-  int rc;
-  CU (cudaMemsetAsync (x, 0, sizeof (double) * nd, ctx->stream));
+  const double *V = ctx->V;
+  for (int j0 = 0; j0 < k || (j0 == 0 && with_norm); j0 += 8)
+    {
+      k_multi_dot<8><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (lo, hi, j0, k, V, nd, wv, with_norm && j0 == 0, ctx->partial);
+      KCHECK ();
+      if (k == 0)
+        break;
+    }
+  k_reduce_partials<<<k + 1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, k + (with_norm ? 1 : 0), ctx->partial, ctx->hdev);
+  KCHECK ();
+  return allreduce_sum (ctx, ctx->hdev, k + 1);
+}
 
-  auto dots = [&](int k, const double *wv, int with_norm) -> int {
-    // hdev[0..k) = V^T w, hdev[k] = w.w (if with_norm); all-reduced
-    for (int j0 = 0; j0 < k || (j0 == 0 && with_norm); j0 += 8)
-      {
-        k_multi_dot<8><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (lo, hi, j0, k, V, nd, wv,
-                                                                     with_norm && j0 == 0, ctx->partial);
-        KCHECK ();
-        if (k == 0)
-          break;
-      }
-    k_reduce_partials<<<k + 1, RED_THREADS, 0, ctx->stream>>> (RED_BLOCKS, k + (with_norm ? 1 : 0), ctx->partial,
-                                                              ctx->hdev);
-    KCHECK ();
-    return allreduce_sum (ctx, ctx->hdev, k + 1);
-  };
-
-  // beta = ||b||
-  if ((rc = dots (0, b, 1)))
+// |v|_2 over the owned dofs (one host synchronisation)
+int
+vector_norm (pf_ctx *ctx, const double *v, double *out)
+{
+  int rc = krylov_dots (ctx, 0, v, 1);
+  if (rc)
     return rc;
   CU (cudaMemcpyAsync (ctx->h_red, ctx->hdev, sizeof (double), cudaMemcpyDeviceToHost, ctx->stream));
   CU (cudaStreamSynchronize (ctx->stream));
-  const double bnorm = std::sqrt (ctx->h_red[0]);
-  const double tol = tol_rel * bnorm;
-  int its = 0;
-  if (n_it)
-    *n_it = 0;
-  if (!std::isfinite (bnorm))
-    return fail (ctx, PF_NUMERIC, "non-finite right-hand side in pf_solve");
-  if (bnorm == 0.0)
-    {
-      if (dx)
-        return download_block (ctx, x, dx);
-      return PF_OK;
-    }
+  *out = std::sqrt (ctx->h_red[0]);
+  return PF_OK;
+}
 
+// the block of the system every kernel sees through ctx->mask, on every multigrid level (pf_ctx::mask_blk)
+void
+set_block (pf_ctx *ctx, int block)
+{
+  for (pf_ctx *c = ctx; c; c = c->coarse)
+    if (block == 0 || c->mask_blk[block - 1])
+      {
+        c->block = block;
+        c->mask = block ? c->mask_blk[block - 1] : c->mask_home;
+      }
+}
+
+// mask_blk[0] = mask | phi bit, mask_blk[1] = mask | u bits, on every level (after the coarse masks have been injected)
+int
+build_block_masks (pf_ctx *ctx)
+{
+  for (pf_ctx *c = ctx; c; c = c->coarse)
+    {
+      const long long nl = c->g.n_local_nodes;
+      for (int b = 0; b < 2; ++b)
+        if (!c->mask_blk[b])
+          CU (cudaMalloc (&c->mask_blk[b], (size_t) nl));
+      k_block_masks<<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, c->dim, c->mask_home, c->mask_blk[0], c->mask_blk[1]);
+      KCHECK ();
+    }
+  return PF_OK;
+}
+
+// Restarted GMRES(m), right-preconditioned, on the operator the current block selects: x = 0 on entry (zeroed here),
+// ends at |b - J x| <= tol.  bnorm = |b| > 0.  *converged says whether the tolerance was met within max_it iterations.
+int
+gmres_block (pf_ctx *ctx, const double *b, double *x, double bnorm, double tol, int max_it, int *its_out, double *res_out,
+             bool *converged_out)
+{
+  const int m = ctx->krylov_m;
+  const long long nd = ctx->n_local_dofs;
+  const long long lo = ctx->owned_lo * ctx->nc, hi = ctx->owned_hi * ctx->nc;
+  double *V = ctx->V, *w = ctx->ya, *z = ctx->zvec;
+  int rc;
+  int its = 0;
+  auto dots = [&](int k, const double *wv, int with_norm) -> int { return krylov_dots (ctx, k, wv, with_norm); };
+  CU (cudaMemsetAsync (x, 0, sizeof (double) * nd, ctx->stream));
   std::vector<double> H ((size_t) (m + 1) * m), cs (m), sn (m), gvec (m + 1), yv (m);
   double res = bnorm;
   bool converged = false;
@@ -3279,6 +3378,9 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
       double beta;
       if (first_cycle)
         {
+          // hdev[0] = |b|^2 for the normalisation
+          if ((rc = dots (0, b, 1)))
+            return rc;
           k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, 1.0, 1, b, V);
           KCHECK ();
           beta = bnorm;
@@ -3408,6 +3510,139 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
       k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, 1.0, z, x);
       KCHECK ();
       CU (cudaStreamSynchronize (ctx->stream));
+    }
+  *its_out = its;
+  *res_out = res;
+  *converged_out = converged;
+  return PF_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int
+pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
+{
+  if (!ctx || max_it < 1)
+    return PF_BAD_ARG;
+  if (!ctx->jac_ready)
+    return fail (ctx, PF_BAD_ARG, "pf_setup_jacobian must precede pf_solve");
+  CU (cudaSetDevice (ctx->device));
+  const int m = ctx->krylov_m;
+  const long long nd = ctx->n_local_dofs;
+  if (!ctx->V)
+    CU (cudaMalloc (&ctx->V, sizeof (double) * nd * (size_t) (m + 1)));
+  double *x = ctx->dx, *b = ctx->r_pde;
+  int rc;
+  CU (cudaMemsetAsync (x, 0, sizeof (double) * nd, ctx->stream));
+  double bnorm;
+  if ((rc = vector_norm (ctx, b, &bnorm)))
+    return rc;
+  const double tol = tol_rel * bnorm;
+  int its = 0;
+  if (n_it)
+    *n_it = 0;
+  if (!std::isfinite (bnorm))
+    return fail (ctx, PF_NUMERIC, "non-finite right-hand side in pf_solve");
+  if (bnorm == 0.0)
+    {
+      if (dx)
+        return download_block (ctx, x, dx);
+      return PF_OK;
+    }
+  double res = bnorm;
+  bool converged = false;
+  const bool blocks = ctx->block_solve && ctx->dim == 3 && !ctx->forest && !ctx->mg_use_graph && ctx->mask_blk[0];
+  if (!blocks)
+    {
+      if ((rc = gmres_block (ctx, b, x, bnorm, tol, max_it, &its, &res, &converged)))
+        return rc;
+    }
+  else
+    {
+      // Block (u,phi) of the Jacobian is identically zero (cracks.cc:2333-2337): A du = b_u, then B dphi = b_phi - C du.
+      // Each stage is the same preconditioned GMRES on the operator restricted by the stage's constraint mask; the
+      // two residuals add up to |b - J dx| <= tol.  The u equation is linear in u and independent of phi within a time
+      // step, so after the first Newton step |b_u| is at the level the previous solve left it: the u stage is skipped
+      // while that is below its share of the tolerance, and over-solved by block_oversolve when it runs so that the
+      // next Newton steps can skip it.
+      const long long nl = ctx->g.n_local_nodes;
+      if (!ctx->blk_b)
+        {
+          CU (cudaMalloc (&ctx->blk_b, sizeof (double) * nd));
+          CU (cudaMalloc (&ctx->blk_x, sizeof (double) * nd));
+        }
+      double *bb = ctx->blk_b, *xu = ctx->blk_x;
+      const double tol_blk = tol / std::sqrt (2.0);
+      struct Restore
+      {
+        pf_ctx *c;
+        ~Restore () { set_block (c, 0); }
+      } restore{ctx};
+      // ---- u stage
+      CU (cudaMemcpyAsync (bb, b, sizeof (double) * nd, cudaMemcpyDeviceToDevice, ctx->stream));
+      k_zero_constrained<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask_blk[0], bb);
+      KCHECK ();
+      double bu_norm, res_u = 0, res_p = 0;
+      if ((rc = vector_norm (ctx, bb, &bu_norm)))
+        return rc;
+      bool conv_u = true, conv_p = true, have_u = false;
+      res_u = bu_norm;
+      ctx->bnorm_ref = std::max (ctx->bnorm_ref, bnorm);
+      // The u residual does not depend on phi, so what is left of it after a solve is what the next Newton steps see.
+      // Below block_u_floor (1e-12) of the time step's largest right-hand side it is the round-off of the residual
+      // evaluation itself (the Newton residual of Sneddon-3D stagnates near 1e-14): no stage is spent on it.
+      const double skip_u = std::max (tol_blk, ctx->block_u_floor * ctx->bnorm_ref);
+      if (bu_norm > skip_u)
+        {
+          int its_u = 0;
+          set_block (ctx, 1);
+          const double tol_u = std::max (tol_blk * ctx->block_oversolve, 1e-11 * bu_norm);
+          rc = gmres_block (ctx, bb, xu, bu_norm, tol_u, max_it, &its_u, &res_u, &conv_u);
+          set_block (ctx, 0);
+          if (rc)
+            return rc;
+          its += its_u;
+          have_u = true;
+          conv_u = conv_u || res_u <= tol_blk;
+        }
+      // ---- phi stage: b_phi - C du
+      CU (cudaMemcpyAsync (bb, b, sizeof (double) * nd, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (have_u)
+        {
+          if ((rc = apply_dev (ctx, xu, ctx->ya)))
+            return rc;
+          k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, -1.0, ctx->ya, bb);
+          KCHECK ();
+        }
+      k_zero_constrained<3><<<nblk (nl, 256), 256, 0, ctx->stream>>> (nl, ctx->mask_blk[1], bb);
+      KCHECK ();
+      double bp_norm;
+      if ((rc = vector_norm (ctx, bb, &bp_norm)))
+        return rc;
+      res_p = bp_norm;
+      if (bp_norm > tol_blk)
+        {
+          int its_p = 0;
+          set_block (ctx, 2);
+          rc = gmres_block (ctx, bb, x, bp_norm, tol_blk, std::max (1, max_it - its), &its_p, &res_p, &conv_p);
+          set_block (ctx, 0);
+          if (rc)
+            return rc;
+          its += its_p;
+        }
+      if (have_u)
+        {
+          k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, 1.0, xu, x);
+          KCHECK ();
+        }
+      res = std::sqrt (res_u * res_u + res_p * res_p);
+      converged = conv_u && conv_p;
+      static const bool trace = getenv ("PF_BLOCK_TRACE") != nullptr;
+      if (trace && ctx->rank == 0)
+        fprintf (stderr, "pf_solve stages: |b| %.3e tol %.3e | u: |b_u| %.3e %s res %.3e | phi: |b_phi - C du| %.3e res %.3e | %d its\n",
+                 bnorm, tol, bu_norm, have_u ? "solved" : "skipped", res_u, bp_norm, res_p, its);
     }
   // constraints_update.distribute(newton_update): homogeneous -> zero (cracks.cc:2773)
   const long long nl = ctx->g.n_local_nodes;
@@ -3541,6 +3776,7 @@ pf_interpolate_unbroken (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  ctx->bnorm_ref = 0; // the u equation changes: the block solve measures its residual against this time step's
   CU (cudaSetDevice (ctx->device));
   // InitialValuesTensionOrShear / InitialValuesNoCrack: u = 0, phi = 1 (cracks.cc:679-691, 727-737)
   const long long nl = ctx->g.n_local_nodes;
@@ -3583,6 +3819,7 @@ pf_set_dirichlet_values (pf_ctx *ctx, const double *values)
 {
   if (!ctx || !values)
     return PF_BAD_ARG;
+  ctx->bnorm_ref = 0; // the u equation changes: the block solve measures its residual against this time step's
   CU (cudaSetDevice (ctx->device));
   int rc = upload_block (ctx, values, ctx->xa);
   if (rc)
@@ -3675,6 +3912,7 @@ pf_interpolate_sneddon (pf_ctx *ctx, double h_diam)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  ctx->bnorm_ref = 0; // the u equation changes: the block solve measures its residual against this time step's
   CU (cudaSetDevice (ctx->device));
   if (ctx->forest)
     return fail (ctx, PF_UNSUPPORTED, "the initial condition of a forest mesh is interpolated by the host (pf_set_state)");
@@ -3697,6 +3935,7 @@ pf_advance_timestep (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  ctx->bnorm_ref = 0; // the u equation changes: the block solve measures its residual against this time step's
   CU (cudaSetDevice (ctx->device));
   // old_old_solution = old_solution; old_solution = solution (cracks.cc:4302-4303)
   std::swap (ctx->old, ctx->oldold);
@@ -3712,6 +3951,7 @@ pf_set_time_parameters (pf_ctx *ctx, double dt_old, double dt_oldold, int use_ol
 {
   if (!ctx || !(dt_oldold > 0))
     return PF_BAD_ARG;
+  ctx->bnorm_ref = 0; // the u equation changes: the block solve measures its residual against this time step's
   ctx->dt_old = dt_old;
   ctx->dt_oldold = dt_oldold;
   ctx->use_old_timestep_pf = use_old_timestep_pf;
@@ -3747,6 +3987,7 @@ pf_restore_old_solution (pf_ctx *ctx)
 {
   if (!ctx)
     return PF_BAD_ARG;
+  ctx->bnorm_ref = 0; // the u equation changes: the block solve measures its residual against this time step's
   CU (cudaSetDevice (ctx->device));
   CU (cudaMemcpyAsync (ctx->sol, ctx->old, sizeof (double) * ctx->n_local_dofs, cudaMemcpyDeviceToDevice,
                        ctx->stream));
@@ -3892,6 +4133,17 @@ pf_debug_set_variant (pf_ctx *ctx, int variant)
   for (pf_ctx *c = ctx; c; c = c->coarse)
     c->apply_variant = variant;
   ctx->jac_ready = false; // the v6 coefficient records are made by pf_setup_jacobian
+  return PF_OK;
+}
+
+int
+pf_debug_set_block (pf_ctx *ctx, int block)
+{
+  if (!ctx || block < 0 || block > 2)
+    return PF_BAD_ARG;
+  if (block && !ctx->mask_blk[0])
+    return fail (ctx, PF_BAD_ARG, "pf_debug_set_block needs pf_set_block_solve and pf_setup_jacobian first");
+  set_block (ctx, block);
   return PF_OK;
 }
 

@@ -505,6 +505,20 @@ k_combine (long long n, int k, const double *__restrict__ V, long long stride,
     }
 }
 
+// constraint masks of the two stages of the block-triangular solve: every phi dof constrained (u stage), every u dof
+// constrained (phi stage); bit c of a node's byte = component c constrained, phi is component dim
+__global__ void
+k_block_masks (long long n_nodes, int dim, const uint8_t *__restrict__ mask, uint8_t *__restrict__ mask_u,
+               uint8_t *__restrict__ mask_phi)
+{
+  const long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes)
+    return;
+  const uint8_t m = mask[n], phi = (uint8_t) (1u << dim);
+  mask_u[n] = m | phi;
+  mask_phi[n] = m | (uint8_t) (phi - 1u);
+}
+
 template <int DIM>
 __global__ void
 k_zero_constrained (long long n_nodes, const uint8_t *__restrict__ mask, double *__restrict__ v)

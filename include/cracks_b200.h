@@ -238,6 +238,19 @@ int pf_set_deterministic (pf_ctx *ctx, int on);
  * preconditioner is block diagonal like the reference's BlockDiagonalPreconditioner (cracks.cc:2717-2740) and a
  * smoother application neither stages nor interpolates the state U.  The Krylov operator is not affected. */
 int pf_set_multigrid_coupling (pf_ctx *ctx, int coupled);
+/* pf_solve as two block stages instead of one GMRES on the whole system.  The reference zeroes the linearised
+ * stresses for phi trial functions (cracks.cc:2333-2337), so block (u,phi) of its Jacobian is identically zero and
+ * J dx = b is  A du = b_u  followed by  B dphi = b_phi - C du.  Each stage runs the same preconditioned GMRES with the
+ * other block's dofs treated as constrained; together they end at |b - J dx| <= tol like the monolithic solve
+ * (cracks.cc:2762-2771).  The u equation is linear in u and independent of phi within a time step (phi~ is
+ * extrapolated from the old time steps, cracks.cc:2262-2277), so after the first Newton step the u stage is skipped
+ * as long as |b_u| is below its share of the tolerance, and the phi stage evaluates only the (phi,phi) block
+ * (pf_apply3d_phi.cuh) -- the active-set iteration of a time step then costs scalar solves.  3-D box meshes.
+ * PF_BLOCK_SOLVE=0/1 sets the default at pf_create. */
+int pf_set_block_solve (pf_ctx *ctx, int on);
+/* Tests: restrict the operator to one block (0 = whole system, 1 = u block, 2 = phi block) for pf_apply_jacobian /
+ * pf_apply_preconditioner; needs pf_set_block_solve(ctx, 1) and pf_setup_jacobian before. */
+int pf_debug_set_block (pf_ctx *ctx, int block);
 /* The multigrid V-cycle as ONE CUDA graph launch (captured after every pf_setup_jacobian, halo exchanges and NCCL
  * calls included): on several GPUs a cycle is bound by the host's launch rate (about 200 launches and 20-30 NCCL calls
  * on levels of a few cell layers per rank).  Default off; PF_MG_GRAPH=1 switches it on at pf_create.  [collective] */
