@@ -246,6 +246,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-newton", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the timing of the FP32 (inexact-Newton) Jacobian")
+    ap.add_argument("--no-block-solve", action="store_true", help="skip the A/B Newton runs with the other linear-solve structure")
     ap.add_argument("--variant", type=int, default=0, help="debug: apply-kernel variant (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -429,8 +430,10 @@ def main():
         # z-slab decomposition), real time steps 0..1 of parameters_sneddon_3d.prm from the
         # interpolated initial condition.  Run twice: with the exact FP64 Jacobian (the library default) and
         # as inexact Newton with the FP32 Jacobian (pf_set_jacobian_precision); residuals are FP64 in both.
-        def newton_run(jacobian_bits):
+        def newton_run(jacobian_bits, block_solve=None):
             nctx = pf.PhaseFieldContext(mesh, params, device=local_rank, rank=rank, nranks=world, nccl_id=fresh_nccl_id())
+            if block_solve is not None:
+                nctx.set_block_solve(block_solve)
             if jacobian_bits != 64:
                 nctx.set_jacobian_precision(jacobian_bits)
                 nctx.set_multigrid_precision(jacobian_bits)
@@ -459,7 +462,10 @@ def main():
                    "bulk_energy": nstats[-1]["bulk"] if nstats else None,
                    "jacobian": "exact FP64 27-point apply" if jacobian_bits == 64 else "FP32 27-point apply on FP64 vectors (inexact Newton)",
                    "preconditioner": "matrix-free geometric multigrid V-cycle in FP%d (z-slab levels, replicated below), "
-                                     "Chebyshev-Jacobi smoothing" % jacobian_bits}
+                                     "Chebyshev-Jacobi smoothing" % jacobian_bits,
+                   "linear_solve": ("library default" if block_solve is None else
+                                    "u stage + phi stage (pf_set_block_solve: block (u,phi) of the Jacobian is zero, "
+                                    "cracks.cc:2333-2337)" if block_solve else "one GMRES on the whole system")}
             if nerr:
                 out["error"] = nerr
             nctx.close()
@@ -467,6 +473,11 @@ def main():
 
         newton = newton_run(64)
         newton_inexact = newton_run(32)
+        newton_stages = None
+        if not args.no_block_solve:
+            # the same two runs with the other linear-solve structure than the library default (A/B record)
+            other = not ctx.block_solve()
+            newton_stages = {"block_solve": other, "exact": newton_run(64, other), "inexact": newton_run(32, other)}
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -517,6 +528,8 @@ def main():
         if newton is not None:
             line["newton"] = newton
             line["newton_inexact"] = newton_inexact
+            if newton_stages is not None:
+                line["newton_other_linear_solve"] = newton_stages
         if not args.no_cpu_baseline:
             cb = cpu_reference_sample(10, 2, refine=3, newton=not args.no_cpu_newton)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "newton_its_per_s",

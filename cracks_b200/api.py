@@ -98,6 +98,7 @@ _SIGS = {
     "pf_set_multigrid_coupling": [C.c_void_p, C.c_int],
     "pf_set_block_solve": [C.c_void_p, C.c_int],
     "pf_debug_set_block": [C.c_void_p, C.c_int],
+    "pf_get_block_solve": [C.c_void_p],
     "pf_set_multigrid_graph": [C.c_void_p, C.c_int],
     "pf_apply_preconditioner": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_set_krylov_dim": [C.c_void_p, C.c_int],
@@ -368,6 +369,10 @@ class PhaseFieldContext:
     def set_preconditioner(self, kind=1, cheb_degree=2, cheb_ratio=6.0):
         """0 = Jacobi, 1 = geometric multigrid (stand-in for the reference's ML AMG)"""
         self._check(self.lib.pf_set_preconditioner(self.h, kind, cheb_degree, cheb_ratio))
+
+    def block_solve(self):
+        """whether pf_solve runs as u stage + phi stage on this context"""
+        return bool(self.lib.pf_get_block_solve(self.h))
 
     def set_block_solve(self, on=True):
         """pf_solve as a u stage followed by a phi stage (the Jacobian has no (u,phi) block, cracks.cc:2333-2337)"""

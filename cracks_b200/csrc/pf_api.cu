@@ -3009,6 +3009,12 @@ pf_set_block_solve (pf_ctx *ctx, int on)
 }
 
 int
+pf_get_block_solve (pf_ctx *ctx)
+{
+  return ctx && ctx->block_solve ? 1 : 0;
+}
+
+int
 pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio)
 {
   if (!ctx || kind < 0 || kind > 3 || cheb_degree < 1 || !(cheb_ratio > 1.0))

@@ -248,6 +248,7 @@ int pf_set_multigrid_coupling (pf_ctx *ctx, int coupled);
  * (pf_apply3d_phi.cuh) -- the active-set iteration of a time step then costs scalar solves.  3-D box meshes.
  * PF_BLOCK_SOLVE=0/1 sets the default at pf_create. */
 int pf_set_block_solve (pf_ctx *ctx, int on);
+int pf_get_block_solve (pf_ctx *ctx); /* 1 / 0: the setting in force (library default or PF_BLOCK_SOLVE) */
 /* Tests: restrict the operator to one block (0 = whole system, 1 = u block, 2 = phi block) for pf_apply_jacobian /
  * pf_apply_preconditioner; needs pf_set_block_solve(ctx, 1) and pf_setup_jacobian before. */
 int pf_debug_set_block (pf_ctx *ctx, int block);
