@@ -138,7 +138,7 @@ struct pf_ctx
   double block_oversolve = 1e-2;             // the u stage, when it runs, ends this factor below its share of the tolerance
   double block_u_floor = 1e-12;              // ... and is skipped while |b_u| <= block_u_floor * bnorm_ref
   double bnorm_ref = 0;                      // largest |b| pf_solve has seen since the state / time step last changed
-  int block_solve = getenv ("PF_BLOCK_SOLVE") ? atoi (getenv ("PF_BLOCK_SOLVE")) : 0;
+  int block_solve = getenv ("PF_BLOCK_SOLVE") ? atoi (getenv ("PF_BLOCK_SOLVE")) : 1; // default on (3-D box meshes)
   double2 *aux = nullptr; // {phi~, mask} records for the TMA path
   unsigned long long *tile_counter = nullptr, tile_epoch = 0;
   int sm_count = 148;

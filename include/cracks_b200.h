@@ -246,7 +246,7 @@ int pf_set_multigrid_coupling (pf_ctx *ctx, int coupled);
  * extrapolated from the old time steps, cracks.cc:2262-2277), so after the first Newton step the u stage is skipped
  * as long as |b_u| is below its share of the tolerance, and the phi stage evaluates only the (phi,phi) block
  * (pf_apply3d_phi.cuh) -- the active-set iteration of a time step then costs scalar solves.  3-D box meshes.
- * PF_BLOCK_SOLVE=0/1 sets the default at pf_create. */
+ * Default on; PF_BLOCK_SOLVE=0/1 sets the default at pf_create, 0 gives the monolithic GMRES. */
 int pf_set_block_solve (pf_ctx *ctx, int on);
 int pf_get_block_solve (pf_ctx *ctx); /* 1 / 0: the setting in force (library default or PF_BLOCK_SOLVE) */
 /* Tests: restrict the operator to one block (0 = whole system, 1 = u block, 2 = phi block) for pf_apply_jacobian /

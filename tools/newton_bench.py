@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--quiet", action="store_true")
     ap.add_argument("--jacobian-bits", type=int, default=64, help="32: inexact Newton, Jacobian apply in FP32")
     ap.add_argument("--uncoupled", action="store_true", help="block-diagonal smoother operator (pf_set_multigrid_coupling 0)")
+    ap.add_argument("--block-solve", type=int, default=-1, help="1 / 0: pf_set_block_solve (default: the library's setting)")
     ap.add_argument("--mg-bits", type=int, default=0, help="32 / 64: precision of the V-cycle (0 = library default)")
     args = ap.parse_args()
     import cracks_b200 as pf
@@ -57,6 +58,8 @@ def main():
         ctx.set_multigrid_precision(args.mg_bits)
     if args.uncoupled:
         ctx.set_multigrid_coupling(False)
+    if args.block_solve >= 0:
+        ctx.set_block_solve(bool(args.block_solve))
     log = (lambda s: None) if args.quiet else (lambda s: print(s, flush=True))
     # parameters_sneddon_3d.prm: Newton lower bound 1e-7, max 50 steps, line search 10 x 0.5
     drv = pf.SneddonDriver(ctx, pressure=lambda t: 1e-3, max_no_timesteps=args.steps - 1, newton_lower_bound=1e-7,
