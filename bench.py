@@ -434,6 +434,7 @@ def main():
             nctx = pf.PhaseFieldContext(mesh, params, device=local_rank, rank=rank, nranks=world, nccl_id=fresh_nccl_id())
             if block_solve is not None:
                 nctx.set_block_solve(block_solve)
+            stages = nctx.block_solve()
             if jacobian_bits != 64:
                 nctx.set_jacobian_precision(jacobian_bits)
                 nctx.set_multigrid_precision(jacobian_bits)
@@ -463,9 +464,9 @@ def main():
                    "jacobian": "exact FP64 27-point apply" if jacobian_bits == 64 else "FP32 27-point apply on FP64 vectors (inexact Newton)",
                    "preconditioner": "matrix-free geometric multigrid V-cycle in FP%d (z-slab levels, replicated below), "
                                      "Chebyshev-Jacobi smoothing" % jacobian_bits,
-                   "linear_solve": ("library default" if block_solve is None else
-                                    "u stage + phi stage (pf_set_block_solve: block (u,phi) of the Jacobian is zero, "
-                                    "cracks.cc:2333-2337)" if block_solve else "one GMRES on the whole system")}
+                   "linear_solve": ("u stage + phi stage (pf_set_block_solve: block (u,phi) of the Jacobian is zero, "
+                                    "cracks.cc:2333-2337)" if stages else "one GMRES on the whole system")
+                                   + (" [library default]" if block_solve is None else "")}
             if nerr:
                 out["error"] = nerr
             nctx.close()
