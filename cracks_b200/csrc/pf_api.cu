@@ -135,6 +135,8 @@ struct pf_ctx
   uint8_t *mask_home = nullptr, *mask_blk[2] = {nullptr, nullptr};
   int block = 0;       // 0 = full system, 1 = u block, 2 = phi block (see set_block)
   double *blk_b = nullptr, *blk_x = nullptr; // right-hand side and u update of the stages
+  double *blk_v = nullptr;                   // 4-component copy of a compact basis vector (phi stage)
+  int block_compact = getenv ("PF_BLOCK_COMPACT") ? atoi (getenv ("PF_BLOCK_COMPACT")) : 1; // phi stage: one value per node in the Krylov basis
   double block_oversolve = 1e-2;             // the u stage, when it runs, ends this factor below its share of the tolerance
   double block_u_floor = 1e-12;              // ... and is skipped while |b_u| <= block_u_floor * bnorm_ref
   double bnorm_ref = 0;                      // largest |b| pf_solve has seen since the state / time step last changed
@@ -2738,7 +2740,7 @@ pf_destroy (pf_ctx *ctx)
   for (float *v : {ctx->f_sol, ctx->f_pt, ctx->f_idiag, ctx->f_b, ctx->f_x, ctx->f_y, ctx->f_d, ctx->f_r})
     if (v)
       cudaFree (v);
-  for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r, ctx->mg_ev, ctx->mg_in, ctx->blk_b, ctx->blk_x})
+  for (double *v : {ctx->mg_b, ctx->mg_x, ctx->mg_y, ctx->mg_d, ctx->mg_r, ctx->mg_ev, ctx->mg_in, ctx->blk_b, ctx->blk_x, ctx->blk_v})
     if (v)
       cudaFree (v);
   void *ptrs[] = {ctx->sol,   ctx->old,  ctx->oldold, ctx->pt,     ctx->diag,  ctx->mass, ctx->r_total,
@@ -3301,10 +3303,11 @@ namespace {
 
 // hdev[0..k) = V^T w, hdev[k] = w.w (if with_norm); all-reduced
 int
-krylov_dots (pf_ctx *ctx, int k, const double *wv, int with_norm)
+krylov_dots (pf_ctx *ctx, int k, const double *wv, int with_norm, bool compact = false)
 {
-  const long long nd = ctx->n_local_dofs;
-  const long long lo = ctx->owned_lo * ctx->nc, hi = ctx->owned_hi * ctx->nc;
+  // compact: one value per node (the phi stage keeps its Krylov basis without the three idle u components)
+  const long long nd = compact ? ctx->g.n_local_nodes : ctx->n_local_dofs;
+  const long long lo = ctx->owned_lo * (compact ? 1 : ctx->nc), hi = ctx->owned_hi * (compact ? 1 : ctx->nc);
   const double *V = ctx->V;
   for (int j0 = 0; j0 < k || (j0 == 0 && with_norm); j0 += 8)
     {
@@ -3363,16 +3366,36 @@ build_block_masks (pf_ctx *ctx)
 // ends at |b - J x| <= tol.  bnorm = |b| > 0.  *converged says whether the tolerance was met within max_it iterations.
 int
 gmres_block (pf_ctx *ctx, const double *b, double *x, double bnorm, double tol, int max_it, int *its_out, double *res_out,
-             bool *converged_out)
+             bool *converged_out, bool compact = false)
 {
+  // compact (phi stage): the Krylov basis, the Gram-Schmidt sweeps and the update hold ONE value per node -- the u
+  // components of every vector of the stage are zero -- and only the vectors the preconditioner and the operator see
+  // are expanded to the 4-component layout (k_scatter_component / k_gather_component).
   const int m = ctx->krylov_m;
-  const long long nd = ctx->n_local_dofs;
-  const long long lo = ctx->owned_lo * ctx->nc, hi = ctx->owned_hi * ctx->nc;
-  double *V = ctx->V, *w = ctx->ya, *z = ctx->zvec;
+  const long long nd4 = ctx->n_local_dofs, nn = ctx->g.n_local_nodes;
+  const long long nd = compact ? nn : nd4; // length of a basis vector
+  const long long lo = ctx->owned_lo * (compact ? 1 : ctx->nc), hi = ctx->owned_hi * (compact ? 1 : ctx->nc);
+  const int nc = ctx->nc, comp = ctx->dim;
+  double *V = ctx->V, *w4 = ctx->ya, *z = ctx->zvec;
+  double *w = compact ? V + (size_t) (m + 1) * nd : w4; // compact work vector: behind the compact basis
+  double *v4 = nullptr;                                  // 4-component copy of a basis vector, u components zero
   int rc;
   int its = 0;
-  auto dots = [&](int k, const double *wv, int with_norm) -> int { return krylov_dots (ctx, k, wv, with_norm); };
-  CU (cudaMemsetAsync (x, 0, sizeof (double) * nd, ctx->stream));
+  if (compact)
+    {
+      if (!ctx->blk_v)
+        CU (cudaMalloc (&ctx->blk_v, sizeof (double) * nd4));
+      v4 = ctx->blk_v;
+      CU (cudaMemsetAsync (v4, 0, sizeof (double) * nd4, ctx->stream));
+    }
+  auto dots = [&](int k, const double *wv, int with_norm) -> int { return krylov_dots (ctx, k, wv, with_norm, compact); };
+  auto gather = [&](const double *src4, double *dst) {
+    k_gather_component<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nn, nc, comp, src4, dst);
+  };
+  auto scatter = [&](const double *src, double *dst4) {
+    k_scatter_component<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nn, nc, comp, src, dst4);
+  };
+  CU (cudaMemsetAsync (x, 0, sizeof (double) * nd4, ctx->stream));
   std::vector<double> H ((size_t) (m + 1) * m), cs (m), sn (m), gvec (m + 1), yv (m);
   double res = bnorm;
   bool converged = false;
@@ -3385,21 +3408,33 @@ gmres_block (pf_ctx *ctx, const double *b, double *x, double bnorm, double tol, 
       if (first_cycle)
         {
           // hdev[0] = |b|^2 for the normalisation
-          if ((rc = dots (0, b, 1)))
+          const double *b0 = b;
+          if (compact)
+            {
+              gather (b, w);
+              KCHECK ();
+              b0 = w;
+            }
+          if ((rc = dots (0, b0, 1)))
             return rc;
-          k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, 1.0, 1, b, V);
+          k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, 1.0, 1, b0, V);
           KCHECK ();
           beta = bnorm;
           first_cycle = false;
         }
       else
         {
-          if ((rc = apply_dev (ctx, x, w)))
+          if ((rc = apply_dev (ctx, x, w4)))
             return rc;
-          k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, -1.0, 0, w, w);
+          k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd4, ctx->hdev, -1.0, 0, w4, w4);
           KCHECK ();
-          k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, 1.0, b, w);
+          k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd4, 1.0, b, w4);
           KCHECK ();
+          if (compact)
+            {
+              gather (w4, w);
+              KCHECK ();
+            }
           if ((rc = dots (0, w, 1)))
             return rc;
           k_scale_copy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, ctx->hdev, 1.0, 1, w, V);
@@ -3421,10 +3456,20 @@ gmres_block (pf_ctx *ctx, const double *b, double *x, double bnorm, double tol, 
         {
           double *vk = V + (size_t) k * nd, *vk1 = V + (size_t) (k + 1) * nd;
           // z = M^{-1} v_k ; w = J z
-          if ((rc = precond_apply (ctx, vk, z)))
+          if (compact)
+            {
+              scatter (vk, v4);
+              KCHECK ();
+            }
+          if ((rc = precond_apply (ctx, compact ? v4 : vk, z)))
             return rc;
-          if ((rc = apply_dev (ctx, z, w)))
+          if ((rc = apply_dev (ctx, z, w4)))
             return rc;
+          if (compact)
+            {
+              gather (w4, w);
+              KCHECK ();
+            }
           // CGS2: two passes of classical Gram-Schmidt with fused multi-dot / multi-axpy kernels and TWO all-reduces
           // per Arnoldi step: the norm of the new basis vector rides on the second pass (|w'|^2 - sum h2^2) and
           // the normalisation is part of its axpy sweep
@@ -3511,9 +3556,14 @@ gmres_block (pf_ctx *ctx, const double *b, double *x, double bnorm, double tol, 
       CU (cudaMemsetAsync (w, 0, sizeof (double) * nd, ctx->stream));
       k_combine<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, k, V, nd, ctx->hdev, w);
       KCHECK ();
-      if ((rc = precond_apply (ctx, w, z)))
+      if (compact)
+        {
+          scatter (w, v4);
+          KCHECK ();
+        }
+      if ((rc = precond_apply (ctx, compact ? v4 : w, z)))
         return rc;
-      k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd, 1.0, z, x);
+      k_axpy<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>> (nd4, 1.0, z, x);
       KCHECK ();
       CU (cudaStreamSynchronize (ctx->stream));
     }
@@ -3632,7 +3682,8 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
         {
           int its_p = 0;
           set_block (ctx, 2);
-          rc = gmres_block (ctx, bb, x, bp_norm, tol_blk, std::max (1, max_it - its), &its_p, &res_p, &conv_p);
+          rc = gmres_block (ctx, bb, x, bp_norm, tol_blk, std::max (1, max_it - its), &its_p, &res_p, &conv_p,
+                            ctx->block_compact != 0);
           set_block (ctx, 0);
           if (rc)
             return rc;

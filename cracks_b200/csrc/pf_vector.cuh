@@ -505,6 +505,20 @@ k_combine (long long n, int k, const double *__restrict__ V, long long stride,
     }
 }
 
+// one component of a node-major vector <-> a vector with one value per node (compact Krylov basis of the phi stage)
+__global__ void __launch_bounds__ (RED_THREADS)
+k_gather_component (long long n_nodes, int nc, int comp, const double *__restrict__ src, double *__restrict__ dst)
+{
+  for (long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x; n < n_nodes; n += (long long) gridDim.x * blockDim.x)
+    dst[n] = src[n * nc + comp];
+}
+__global__ void __launch_bounds__ (RED_THREADS)
+k_scatter_component (long long n_nodes, int nc, int comp, const double *__restrict__ src, double *__restrict__ dst)
+{
+  for (long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x; n < n_nodes; n += (long long) gridDim.x * blockDim.x)
+    dst[n * nc + comp] = src[n];
+}
+
 // constraint masks of the two stages of the block-triangular solve: every phi dof constrained (u stage), every u dof
 // constrained (phi stage); bit c of a node's byte = component c constrained, phi is component dim
 __global__ void
