@@ -194,8 +194,8 @@ def test_block_restricted_operator(oracle, epf, h):
     ctx.close()
 
 
-@pytest.mark.parametrize("mg_bits,jac_bits", [(64, 64), (32, 32)])
-def test_block_solve_kat1(epf, mg_bits, jac_bits):
+@pytest.mark.parametrize("mg_bits,jac_bits,steps", [(64, 64, 1), (32, 32, 0)])
+def test_block_solve_kat1(epf, mg_bits, jac_bits, steps):
     """pf_set_block_solve on the sneddon_3d_1 golden: pf_solve as u stage + phi stage gives the golden energies and the
     Newton history of the monolithic solve; once u has been solved the later Newton steps of a time step skip the
     u stage (their GMRES iterations are phi iterations: fewer per Newton step than the monolithic solve needs)."""
@@ -210,7 +210,7 @@ def test_block_solve_kat1(epf, mg_bits, jac_bits):
         if jac_bits != 64:
             ctx.set_jacobian_precision(jac_bits)
         ctx.set_block_solve(block)
-        drv = pf.SneddonDriver(ctx, pressure=lambda t: g["prm"]["pressure"], max_no_timesteps=1,
+        drv = pf.SneddonDriver(ctx, pressure=lambda t: g["prm"]["pressure"], max_no_timesteps=steps,
                                newton_lower_bound=g["prm"]["newton_lower_bound"], max_newton=g["prm"]["newton_max_steps"],
                                max_line_search=g["prm"]["line_search_max_steps"], gmres_max_it=300)
         stats = drv.run(mesh_diameter(mesh))
