@@ -3,7 +3,7 @@
 # Every step is wrapped in `timeout`; a multi-rank hang must never eat the budget again
 # (round 1 lost 53 GPU-minutes to two 300 s tear-down hangs on a 4-GPU box).
 # Suggested first call of a round (1 GPU, about 15 minutes of box time):
-#   bash tools/gpu_round_checks.sh tests bench variants fp32 chunks miehe2d ncu
+#   bash tools/gpu_round_checks.sh tests bench variants feed block fp32 chunks miehe2d ncu
 # then make the fastest apply variant / V-cycle precision / chunk count the default and re-run `tests bench`;
 # `bench_multi` and the 2-rank half of `fp32` need a multi-GPU box (gpurun --gpus 2|4|8).
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}" || exit 1
@@ -54,6 +54,15 @@ for s in $steps; do
       fi ;;
     graph)        # PF_MG_GRAPH=1: V-cycle as a CUDA graph; hung at tear-down with NCCL nodes (2 ranks) in round 1
       PF_MG_GRAPH=1 timeout 120 python tools/newton_bench.py --refine 4 --steps 2 --quiet | cut -c1-300 ;;
+    feed)         # needs a tuning build: coefficient feed / CTAs per SM of k_apply3d_v6 (profiles/r2_v6_feed_modes.json)
+      for m in 0 1 2 3; do
+        echo "PF_V6_MODE=$m"; PF_V6_MODE=$m timeout 200 python bench.py --steps 30 --warmup 5 --no-newton --no-cpu-baseline | cut -c1-330
+      done ;;
+    block)        # linear solves as u stage + phi stage (default) against one GMRES on the whole system, stage trace
+      for b in 1 0; do
+        echo "block solve $b"; PF_BLOCK_TRACE=1 timeout 120 python tools/newton_bench.py --refine 4 --steps 2 --quiet --block-solve $b 2>&1 | tail -30 | cut -c1-400
+      done
+      echo "4-component Krylov basis in the phi stage"; PF_BLOCK_COMPACT=0 timeout 120 python tools/newton_bench.py --refine 4 --steps 2 --quiet | cut -c1-400 ;;
     ncu)          # full capture of the default apply kernel (full grid, deterministic launch index)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_apply3d -s 3 -c 2 \
         -o gpurun_out/prof_apply -f python tools/profile_apply.py --refine 4 --applies 6 > gpurun_out/ncu.log 2>&1
