@@ -469,6 +469,11 @@ def main():
                                    + (" [library default]" if block_solve is None else "")}
             if nerr:
                 out["error"] = nerr
+            if stages:
+                try:    # counters since the context was created (the untimed first time step included)
+                    out["stages"] = nctx.block_solve_stats()
+                except Exception as exc:    # a diagnostic must not cost the bench line
+                    out["stages"] = str(exc)
             nctx.close()
             return out
 

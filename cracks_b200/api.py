@@ -99,6 +99,7 @@ _SIGS = {
     "pf_set_block_solve": [C.c_void_p, C.c_int],
     "pf_debug_set_block": [C.c_void_p, C.c_int],
     "pf_get_block_solve": [C.c_void_p],
+    "pf_get_block_solve_stats": [C.c_void_p, C.POINTER(C.c_int64)],
     "pf_set_multigrid_graph": [C.c_void_p, C.c_int],
     "pf_apply_preconditioner": [C.c_void_p, C.c_void_p, C.c_void_p],
     "pf_set_krylov_dim": [C.c_void_p, C.c_int],
@@ -373,6 +374,12 @@ class PhaseFieldContext:
     def block_solve(self):
         """whether pf_solve runs as u stage + phi stage on this context"""
         return bool(self.lib.pf_get_block_solve(self.h))
+
+    def block_solve_stats(self):
+        """counters of the staged linear solves since the context was created"""
+        out = (C.c_int64 * 4)()
+        self._check(self.lib.pf_get_block_solve_stats(self.h, out))
+        return {"solves": int(out[0]), "with_u_stage": int(out[1]), "u_iterations": int(out[2]), "phi_iterations": int(out[3])}
 
     def set_block_solve(self, on=True):
         """pf_solve as a u stage followed by a phi stage (the Jacobian has no (u,phi) block, cracks.cc:2333-2337)"""

@@ -140,6 +140,7 @@ struct pf_ctx
   double block_oversolve = 1e-2;             // the u stage, when it runs, ends this factor below its share of the tolerance
   double block_u_floor = 1e-12;              // ... and is skipped while |b_u| <= block_u_floor * bnorm_ref
   double bnorm_ref = 0;                      // largest |b| pf_solve has seen since the state / time step last changed
+  long long blk_stats[4] = {0, 0, 0, 0};     // staged solves, of which with a u stage, GMRES iterations of the u / phi stages
   int block_solve = getenv ("PF_BLOCK_SOLVE") ? atoi (getenv ("PF_BLOCK_SOLVE")) : 1; // default on (3-D box meshes)
   double2 *aux = nullptr; // {phi~, mask} records for the TMA path
   unsigned long long *tile_counter = nullptr, tile_epoch = 0;
@@ -3017,6 +3018,16 @@ pf_get_block_solve (pf_ctx *ctx)
 }
 
 int
+pf_get_block_solve_stats (pf_ctx *ctx, int64_t *out)
+{
+  if (!ctx || !out)
+    return PF_BAD_ARG;
+  for (int i = 0; i < 4; ++i)
+    out[i] = ctx->blk_stats[i];
+  return PF_OK;
+}
+
+int
 pf_set_preconditioner (pf_ctx *ctx, int kind, int cheb_degree, double cheb_ratio)
 {
   if (!ctx || kind < 0 || kind > 3 || cheb_degree < 1 || !(cheb_ratio > 1.0))
@@ -3644,6 +3655,7 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
       if ((rc = vector_norm (ctx, bb, &bu_norm)))
         return rc;
       bool conv_u = true, conv_p = true, have_u = false;
+      int its_u_total = 0;
       res_u = bu_norm;
       ctx->bnorm_ref = std::max (ctx->bnorm_ref, bnorm);
       // The u residual does not depend on phi, so what is left of it after a solve is what the next Newton steps see.
@@ -3660,6 +3672,7 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
           if (rc)
             return rc;
           its += its_u;
+          its_u_total = its_u;
           have_u = true;
           conv_u = conv_u || res_u <= tol_blk;
         }
@@ -3696,6 +3709,10 @@ pf_solve (pf_ctx *ctx, double tol_rel, int max_it, double *dx, int *n_it)
         }
       res = std::sqrt (res_u * res_u + res_p * res_p);
       converged = conv_u && conv_p;
+      ctx->blk_stats[0] += 1;
+      ctx->blk_stats[1] += have_u ? 1 : 0;
+      ctx->blk_stats[3] += its - its_u_total;
+      ctx->blk_stats[2] += its_u_total;
       static const bool trace = getenv ("PF_BLOCK_TRACE") != nullptr;
       if (trace && ctx->rank == 0)
         fprintf (stderr, "pf_solve stages: |b| %.3e tol %.3e | u: |b_u| %.3e %s res %.3e | phi: |b_phi - C du| %.3e res %.3e | %d its\n",

@@ -249,6 +249,9 @@ int pf_set_multigrid_coupling (pf_ctx *ctx, int coupled);
  * Default on; PF_BLOCK_SOLVE=0/1 sets the default at pf_create, 0 gives the monolithic GMRES. */
 int pf_set_block_solve (pf_ctx *ctx, int on);
 int pf_get_block_solve (pf_ctx *ctx); /* 1 / 0: the setting in force (library default or PF_BLOCK_SOLVE) */
+/* Counters since pf_create: out[0] = pf_solve calls that ran as stages, out[1] = of which with a u stage (the others
+ * found |b_u| below its tolerance), out[2] / out[3] = GMRES iterations of the u / phi stages. */
+int pf_get_block_solve_stats (pf_ctx *ctx, int64_t *out);
 /* Tests: restrict the operator to one block (0 = whole system, 1 = u block, 2 = phi block) for pf_apply_jacobian /
  * pf_apply_preconditioner; needs pf_set_block_solve(ctx, 1) and pf_setup_jacobian before. */
 int pf_debug_set_block (pf_ctx *ctx, int block);

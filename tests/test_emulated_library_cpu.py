@@ -215,6 +215,14 @@ def test_block_solve_kat1(epf, mg_bits, jac_bits, steps):
                                max_line_search=g["prm"]["line_search_max_steps"], gmres_max_it=300)
         stats = drv.run(mesh_diameter(mesh))
         out[block] = (stats, drv.newton_its, drv.lin_its, [[(r.n_active, r.line_search) for r in rows] for rows in drv.history])
+        st = ctx.block_solve_stats()
+        if block:
+            # every solve ran as stages; the u stage ran in the first Newton step of a time step and was skipped in
+            # others (|b_u| is what the previous u solve left); the iteration counts add up to the driver's
+            assert st["solves"] == drv.newton_its and 1 <= st["with_u_stage"] < st["solves"], st
+            assert st["u_iterations"] + st["phi_iterations"] == drv.lin_its and st["phi_iterations"] > 0, st
+        else:
+            assert st["solves"] == 0, st
         ctx.close()
     for block in (False, True):
         for got, ref in zip(out[block][0], g["statistics"]):
